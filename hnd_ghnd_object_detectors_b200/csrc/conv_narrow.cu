@@ -1,0 +1,560 @@
+// Narrow (bottleneck-side) convolutions and the stem weight gradient: HBM-bound SIMT kernels.
+//   enc7  Conv2d(64->bch,k2,p1)  and  dec2  Conv2d(bch->64,k2,p0)   (resnet_layer.py:50,55)
+// The wide side of each conv is an NHWC 16-bit tensor (one 128-byte pixel row per 64 channels,
+// read/written as 8 lanes x 16 B so a warp touches 4 whole pixels = 512 contiguous bytes); the
+// narrow side is the planar fp32 bottleneck tensor the quantizer works on.
+#include "common.cuh"
+
+namespace ghnd {
+
+static constexpr int kNarrowMaxC = 16;   // bottleneck channels supported (bch <= 15 in the reference)
+static constexpr int kNarrowMaxTaps = 4;
+
+struct NarrowTaps {
+  int n_taps;
+  int dh[kNarrowMaxTaps], dw[kNarrowMaxTaps];
+};
+
+// out[n][co][i][j] (planar fp32, co < CN) = sum_{tap,ci} wt[tap][ci][co] * in[n][i+dh][j+dw][ci]
+// `in` NHWC 16-bit with CW wide channels; lanes = CW/8 threads cooperate on one pixel.
+template <int CN_T>
+__global__ void __launch_bounds__(256)
+    narrow_out_kernel(const uint4* __restrict__ in, int in_fmt, const float* __restrict__ wt,
+                      float* __restrict__ out, int N, int Hi, int Wi, int CW, int CN, int Ho, int Wo,
+                      NarrowTaps taps) {
+  extern __shared__ float s_w[];  // [tap][CW][CN]
+  const int nw = taps.n_taps * CW * CN;
+  for (int i = threadIdx.x; i < nw; i += blockDim.x) s_w[i] = wt[i];
+  __syncthreads();
+  const int lanes = CW >> 3;
+  const int cg = threadIdx.x % lanes;
+  const int64_t npix = (int64_t)N * Ho * Wo;
+  const int64_t pstep = (int64_t)gridDim.x * (blockDim.x / lanes);
+  for (int64_t p0 = (int64_t)blockIdx.x * (blockDim.x / lanes); p0 < npix; p0 += pstep) {
+    const int64_t p = p0 + threadIdx.x / lanes;
+    const bool live = p < npix;
+    int n = 0, i = 0, j = 0;
+    if (live) {
+      j = (int)(p % Wo);
+      const int64_t t = p / Wo;
+      i = (int)(t % Ho);
+      n = (int)(t / Ho);
+    }
+    float acc[CN_T];
+#pragma unroll
+    for (int k = 0; k < CN_T; ++k) acc[k] = 0.f;
+    if (live) {
+      for (int t = 0; t < taps.n_taps; ++t) {
+        const int h = i + taps.dh[t], w = j + taps.dw[t];
+        if (h < 0 || h >= Hi || w < 0 || w >= Wi) continue;
+        const uint4 v = __ldg(in + (((int64_t)n * Hi + h) * Wi + w) * lanes + cg);
+        const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+        const float* wrow = s_w + ((size_t)t * CW + cg * 8) * CN;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = unpack2(u[e], in_fmt);
+#pragma unroll
+          for (int k = 0; k < CN_T; ++k) {
+            if (k < CN) {
+              acc[k] = fmaf(f.x, wrow[(2 * e) * CN + k], acc[k]);
+              acc[k] = fmaf(f.y, wrow[(2 * e + 1) * CN + k], acc[k]);
+            }
+          }
+        }
+      }
+    }
+    // reduce over the `lanes` threads of the pixel (lanes is a power of two <= 32)
+#pragma unroll
+    for (int k = 0; k < CN_T; ++k) {
+      float a = acc[k];
+      for (int o = lanes >> 1; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      if (live && cg == 0 && k < CN) out[(((int64_t)n * CN + k) * Ho + i) * Wo + j] = a;
+    }
+  }
+}
+
+// out[n][i][j][co] (NHWC 16-bit, co < CW) = sum_{tap,ci<CN} wt[tap][ci][co] * f(in[n][ci][i+dh][j+dw])
+// f(v) = pre ? (relu ? max(v*sc+sh,0) : v*sc+sh) : v ; padding is applied after f (zero taps).
+__global__ void __launch_bounds__(256)
+    narrow_in_kernel(const float* __restrict__ in, const float* __restrict__ pre, int pre_relu,
+                     const float* __restrict__ wt, uint4* __restrict__ out, int out_fmt, int N, int Hi,
+                     int Wi, int CN, int CW, int Ho, int Wo, NarrowTaps taps) {
+  extern __shared__ float s_w[];  // [tap][CN][CW]
+  const int nw = taps.n_taps * CN * CW;
+  for (int i = threadIdx.x; i < nw; i += blockDim.x) s_w[i] = wt[i];
+  __syncthreads();
+  const int lanes = CW >> 3;
+  const int cg = threadIdx.x % lanes;
+  const int64_t npix = (int64_t)N * Ho * Wo;
+  const int64_t pstep = (int64_t)gridDim.x * (blockDim.x / lanes);
+  for (int64_t p = (int64_t)blockIdx.x * (blockDim.x / lanes) + threadIdx.x / lanes; p < npix;
+       p += pstep) {
+    const int j = (int)(p % Wo);
+    const int64_t t0 = p / Wo;
+    const int i = (int)(t0 % Ho);
+    const int n = (int)(t0 / Ho);
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    for (int t = 0; t < taps.n_taps; ++t) {
+      const int h = i + taps.dh[t], w = j + taps.dw[t];
+      if (h < 0 || h >= Hi || w < 0 || w >= Wi) continue;
+      for (int c = 0; c < CN; ++c) {
+        float v = __ldg(in + (((int64_t)n * CN + c) * Hi + h) * Wi + w);
+        if (pre != nullptr) {
+          v = fmaf(v, __ldg(pre + c), __ldg(pre + CN + c));
+          if (pre_relu) v = fmaxf(v, 0.f);
+        }
+        const float* wrow = s_w + ((size_t)t * CN + c) * CW + cg * 8;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = fmaf(v, wrow[e], acc[e]);
+      }
+    }
+    uint4 o;
+    o.x = pack2(acc[0], acc[1], out_fmt);
+    o.y = pack2(acc[2], acc[3], out_fmt);
+    o.z = pack2(acc[4], acc[5], out_fmt);
+    o.w = pack2(acc[6], acc[7], out_fmt);
+    out[p * lanes + cg] = o;
+  }
+}
+
+// acc[ca][tap][cb] += f(a[n][ca][i][j]) * b[n][i+dh][j+dw][cb]   for ca in [ca0, ca0+3)
+__global__ void __launch_bounds__(256)
+    wgrad_narrow_kernel(const float* __restrict__ a, const float* __restrict__ pre, int pre_relu,
+                        const uint4* __restrict__ b, int b_fmt, float* __restrict__ accum, int N,
+                        int Ha, int Wa, int Ca, int ca0, int Hb, int Wb, int Cb, NarrowTaps taps) {
+  const int lanes = Cb >> 3;
+  const int cg = threadIdx.x % lanes;
+  const int64_t npix = (int64_t)N * Ha * Wa;
+  const int64_t pstep = (int64_t)gridDim.x * (blockDim.x / lanes);
+  float acc[3][kNarrowMaxTaps][8];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int t = 0; t < kNarrowMaxTaps; ++t)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[c][t][e] = 0.f;
+  for (int64_t p = (int64_t)blockIdx.x * (blockDim.x / lanes) + threadIdx.x / lanes; p < npix;
+       p += pstep) {
+    const int j = (int)(p % Wa);
+    const int64_t t0 = p / Wa;
+    const int i = (int)(t0 % Ha);
+    const int n = (int)(t0 / Ha);
+    float av[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int ca = ca0 + c;
+      float v = 0.f;
+      if (ca < Ca) {
+        v = __ldg(a + (((int64_t)n * Ca + ca) * Ha + i) * Wa + j);
+        if (pre != nullptr) {
+          v = fmaf(v, __ldg(pre + ca), __ldg(pre + Ca + ca));
+          if (pre_relu) v = fmaxf(v, 0.f);
+        }
+      }
+      av[c] = v;
+    }
+#pragma unroll
+    for (int t = 0; t < kNarrowMaxTaps; ++t) {
+      if (t >= taps.n_taps) break;
+      const int h = i + taps.dh[t], w = j + taps.dw[t];
+      if (h < 0 || h >= Hb || w < 0 || w >= Wb) continue;
+      const uint4 v = __ldg(b + (((int64_t)n * Hb + h) * Wb + w) * lanes + cg);
+      const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = unpack2(u[e], b_fmt);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          acc[c][t][2 * e] = fmaf(av[c], f.x, acc[c][t][2 * e]);
+          acc[c][t][2 * e + 1] = fmaf(av[c], f.y, acc[c][t][2 * e + 1]);
+        }
+      }
+    }
+  }
+  // fold the pixel lanes of the warp that share a channel group, then one atomic per value
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int t = 0; t < kNarrowMaxTaps; ++t)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float v = acc[c][t][e];
+        for (int o = 16; o >= lanes; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) < lanes && t < taps.n_taps && ca0 + c < Ca)
+          atomicAdd(accum + ((size_t)(ca0 + c) * taps.n_taps + t) * Cb + cg * 8 + e, v);
+      }
+}
+
+// accum[ca][tap][cb] -> OIHW dw
+__global__ void wgrad_narrow_finish_kernel(const float* __restrict__ accum, float* __restrict__ dw,
+                                           int a_is_output, int Ca, int Cb, int R, int S) {
+  const int total = Ca * Cb * R * S;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int t = i;
+    const int s = t % S;
+    t /= S;
+    const int r = t % R;
+    t /= R;
+    int o, c;
+    if (a_is_output) {  // dw[k=ca][c=cb][r][s]
+      c = t % Cb;
+      o = t / Cb;
+      dw[i] = accum[((size_t)o * R * S + r * S + s) * Cb + c];
+    } else {  // dw[k=cb][c=ca][r][s]
+      c = t % Ca;
+      o = t / Ca;
+      dw[i] = accum[((size_t)c * R * S + r * S + s) * Cb + o];
+    }
+  }
+}
+
+// build the smem weight tables on device from OIHW fp32
+// mode 0: wt[tap][ci=c][co=k] = w[k][c][r][s]      (narrow_out fwd: wide in c, narrow out k)
+// mode 1: wt[tap][ci=k][co=c] = w[k][c][r][s]      (narrow_out_dgrad / narrow_in flip: reduce over k)
+__global__ void narrow_wtable_kernel(const float* __restrict__ w, float* __restrict__ wt, int K, int C,
+                                     int R, int S, int mode) {
+  const int total = K * C * R * S;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int t = i;
+    const int s = t % S;
+    t /= S;
+    const int r = t % R;
+    t /= R;
+    const int c = t % C;
+    const int k = t / C;
+    const int tap = r * S + s;
+    if (mode == 0)
+      wt[((size_t)tap * C + c) * K + k] = w[i];
+    else
+      wt[((size_t)tap * K + k) * C + c] = w[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// stem conv1 weight gradient (SIMT): out[k][q] = sum_pix g[pix][k] * patch[pix][q],
+// q = r*28 + s*4 + c over the packed 4-channel image; 8 k x 7 q register tile per thread.
+// ------------------------------------------------------------------------------------------------
+static constexpr int kSwPix = 64;  // output pixels (one row segment) per smem chunk
+__global__ void __launch_bounds__(256)
+    stem_wgrad_kernel(const uint16_t* __restrict__ xp, int x_fmt, const uint16_t* __restrict__ g,
+                      int g_fmt, float* __restrict__ accum, int N, int Ho, int Wo, int rows, int cols) {
+  __shared__ __align__(16) uint16_t s_g[kSwPix * 64];
+  __shared__ __align__(16) uint16_t s_x[7 * (2 * kSwPix + 6) * 4];
+  constexpr int RW = (2 * kSwPix + 6) * 4;  // smem patch row width in elements
+  const int tk = threadIdx.x >> 5;          // 8 groups of 8 output channels
+  const int tq = threadIdx.x & 31;
+  int qoff[7];
+  bool qok[7];
+#pragma unroll
+  for (int m = 0; m < 7; ++m) {
+    const int q = tq + 32 * m;
+    qok[m] = q < 196;
+    const int r = qok[m] ? q / 28 : 0, s4 = qok[m] ? q % 28 : 0;
+    qoff[m] = r * RW + s4;
+  }
+  float acc[8][7];
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int m = 0; m < 7; ++m) acc[a][m] = 0.f;
+  const int segs = (Wo + kSwPix - 1) / kSwPix;
+  const int64_t chunks = (int64_t)N * Ho * segs;
+  for (int64_t ch = blockIdx.x; ch < chunks; ch += gridDim.x) {
+    const int seg = (int)(ch % segs);
+    const int64_t t = ch / segs;
+    const int ho = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    const int wo0 = seg * kSwPix;
+    const int np = min(kSwPix, Wo - wo0);
+    __syncthreads();
+    // g tile: np pixels x 64 channels
+    for (int i = threadIdx.x; i < kSwPix * 8; i += blockDim.x) {
+      const int px = i >> 3, v = i & 7;
+      uint4 val = make_uint4(0, 0, 0, 0);
+      if (px < np)
+        val = __ldg(reinterpret_cast<const uint4*>(g + (((int64_t)n * Ho + ho) * Wo + wo0 + px) * 64) + v);
+      reinterpret_cast<uint4*>(s_g)[i] = val;
+    }
+    // image patch rows 2ho..2ho+6, cols 2wo0 .. 2wo0 + 2*kSwPix+5 (packed coords, frame included)
+    for (int i = threadIdx.x; i < 7 * (2 * kSwPix + 6); i += blockDim.x) {
+      const int r = i / (2 * kSwPix + 6), cpx = i % (2 * kSwPix + 6);
+      const int row = 2 * ho + r, col = 2 * wo0 + cpx;
+      uint2 val = make_uint2(0, 0);
+      if (row < rows && col < cols)
+        val = __ldg(reinterpret_cast<const uint2*>(xp + (((int64_t)n * rows + row) * cols + col) * 4));
+      reinterpret_cast<uint2*>(s_x)[i] = val;
+    }
+    __syncthreads();
+    for (int px = 0; px < np; ++px) {
+      const uint4 gv = *reinterpret_cast<const uint4*>(s_g + px * 64 + tk * 8);
+      const uint32_t gu[4] = {gv.x, gv.y, gv.z, gv.w};
+      float gf[8];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = unpack2(gu[e], g_fmt);
+        gf[2 * e] = f.x;
+        gf[2 * e + 1] = f.y;
+      }
+      float xf[7];
+#pragma unroll
+      for (int m = 0; m < 7; ++m) xf[m] = qok[m] ? h16_to_float(s_x[qoff[m] + 8 * px], x_fmt) : 0.f;
+#pragma unroll
+      for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int m = 0; m < 7; ++m) acc[a][m] = fmaf(gf[a], xf[m], acc[a][m]);
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int m = 0; m < 7; ++m)
+      if (qok[m]) atomicAdd(accum + (size_t)(tk * 8 + a) * 196 + tq + 32 * m, acc[a][m]);
+}
+
+// accum[k][r*28 + s*4 + c] -> dw[k][c][r][s] * scale[k]
+__global__ void stem_wgrad_finish_kernel(const float* __restrict__ accum,
+                                         const float* __restrict__ scale, float* __restrict__ dw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 64 * 3 * 49) return;
+  int t = i;
+  const int s = t % 7;
+  t /= 7;
+  const int r = t % 7;
+  t /= 7;
+  const int c = t % 3;
+  const int k = t / 3;
+  dw[i] = accum[(size_t)k * 196 + r * 28 + s * 4 + c] * (scale ? scale[k] : 1.f);
+}
+
+// stem weights: OIHW [64][3][7][7] fp32 (x scale[k]) -> [64][7][32] 16-bit, q = s*4 + c, zero padded
+__global__ void stem_pack_weight_kernel(const float* __restrict__ w, const float* __restrict__ scale,
+                                        uint16_t* __restrict__ dst, int fmt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 64 * 7 * 32) return;
+  const int q = i & 31, r = (i >> 5) % 7, k = i / (7 * 32);
+  const int s = q >> 2, c = q & 3;
+  float v = 0.f;
+  if (s < 7 && c < 3) v = w[(((size_t)k * 3 + c) * 7 + r) * 7 + s] * (scale ? scale[k] : 1.f);
+  dst[i] = float_to_h16(v, fmt);
+}
+
+static int blocks_for_pixels(int64_t npix, int pix_per_block, int per_sm = 4) {
+  int64_t b = (npix + pix_per_block - 1) / pix_per_block;
+  const int64_t cap = (int64_t)num_sms() * per_sm;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+static bool pow2_lanes(int cw) {
+  const int l = cw / 8;
+  return cw % 8 == 0 && l >= 1 && l <= 32 && (l & (l - 1)) == 0;
+}
+
+}  // namespace ghnd
+
+extern "C" {
+using namespace ghnd;
+
+// workspace layout for the narrow convs: a small fp32 weight table
+size_t ghnd_conv_narrow_workspace_bytes(int C, int K, int R, int S) {
+  return (size_t)C * K * R * S * sizeof(float);
+}
+
+int ghnd_conv_narrow_out(const void* x, int x_fmt, const float* w, float* y, int N, int H, int W,
+                         int C, int K, int R, int S, int pad, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  GHND_CHECK_ARG(x && w && y && workspace, "conv_narrow_out: null pointer");
+  GHND_CHECK_ARG(pow2_lanes(C) && K >= 1 && K <= kNarrowMaxC && R * S <= kNarrowMaxTaps && R >= 1 &&
+                     S >= 1,
+                 "conv_narrow_out: unsupported shape C=%d K=%d %dx%d", C, K, R, S);
+  GHND_CHECK_ARG(workspace_bytes >= ghnd_conv_narrow_workspace_bytes(C, K, R, S),
+                 "conv_narrow_out: workspace too small");
+  const int Ho = H + 2 * pad - R + 1, Wo = W + 2 * pad - S + 1;
+  GHND_CHECK_ARG(Ho > 0 && Wo > 0, "conv_narrow_out: empty output");
+  cudaStream_t st = (cudaStream_t)stream;
+  narrow_wtable_kernel<<<4, 256, 0, st>>>(w, (float*)workspace, K, C, R, S, 0);
+  GHND_LAUNCH_CHECK("narrow_wtable_kernel");
+  NarrowTaps taps;
+  taps.n_taps = R * S;
+  for (int r = 0; r < R; ++r)
+    for (int s = 0; s < S; ++s) {
+      taps.dh[r * S + s] = r - pad;
+      taps.dw[r * S + s] = s - pad;
+    }
+  const int lanes = C / 8;
+  const int64_t npix = (int64_t)N * Ho * Wo;
+  if (K <= 3)
+    narrow_out_kernel<3><<<blocks_for_pixels(npix, 256 / lanes), 256,
+                           (size_t)R * S * C * K * sizeof(float), st>>>(
+        (const uint4*)x, x_fmt, (const float*)workspace, y, N, H, W, C, K, Ho, Wo, taps);
+  else
+    narrow_out_kernel<kNarrowMaxC><<<blocks_for_pixels(npix, 256 / lanes), 256,
+                                     (size_t)R * S * C * K * sizeof(float), st>>>(
+        (const uint4*)x, x_fmt, (const float*)workspace, y, N, H, W, C, K, Ho, Wo, taps);
+  GHND_LAUNCH_CHECK("narrow_out_kernel");
+  return GHND_OK;
+}
+
+int ghnd_conv_narrow_out_dgrad(const void* dy, int dy_fmt, const float* w, float* dx, int N, int H,
+                               int W, int C, int K, int R, int S, int pad, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+  // forward conv: x[N][C(narrow)][H][W] -> y[N][Ho][Wo][K(wide)], w[K][C][R][S]
+  GHND_CHECK_ARG(dy && w && dx && workspace, "conv_narrow_out_dgrad: null pointer");
+  GHND_CHECK_ARG(pow2_lanes(K) && C >= 1 && C <= kNarrowMaxC && R * S <= kNarrowMaxTaps && R >= 1 &&
+                     S >= 1,
+                 "conv_narrow_out_dgrad: unsupported shape C=%d K=%d %dx%d", C, K, R, S);
+  GHND_CHECK_ARG(workspace_bytes >= ghnd_conv_narrow_workspace_bytes(C, K, R, S),
+                 "conv_narrow_out_dgrad: workspace too small");
+  const int Ho = H + 2 * pad - R + 1, Wo = W + 2 * pad - S + 1;
+  GHND_CHECK_ARG(Ho > 0 && Wo > 0, "conv_narrow_out_dgrad: empty output");
+  cudaStream_t st = (cudaStream_t)stream;
+  // table wt[tap][ci=k][co=c]
+  narrow_wtable_kernel<<<4, 256, 0, st>>>(w, (float*)workspace, K, C, R, S, 1);
+  GHND_LAUNCH_CHECK("narrow_wtable_kernel");
+  NarrowTaps taps;
+  taps.n_taps = R * S;
+  for (int r = 0; r < R; ++r)
+    for (int s = 0; s < S; ++s) {
+      taps.dh[r * S + s] = pad - r;
+      taps.dw[r * S + s] = pad - s;
+    }
+  const int lanes = K / 8;
+  const int64_t npix = (int64_t)N * H * W;
+  if (C <= 3)
+    narrow_out_kernel<3><<<blocks_for_pixels(npix, 256 / lanes), 256,
+                           (size_t)R * S * C * K * sizeof(float), st>>>(
+        (const uint4*)dy, dy_fmt, (const float*)workspace, dx, N, Ho, Wo, K, C, H, W, taps);
+  else
+    narrow_out_kernel<kNarrowMaxC><<<blocks_for_pixels(npix, 256 / lanes), 256,
+                                     (size_t)R * S * C * K * sizeof(float), st>>>(
+        (const uint4*)dy, dy_fmt, (const float*)workspace, dx, N, Ho, Wo, K, C, H, W, taps);
+  GHND_LAUNCH_CHECK("narrow_out_kernel(dgrad)");
+  return GHND_OK;
+}
+
+int ghnd_conv_narrow_in(const float* x, const float* pre_scale_shift, int pre_relu, const float* w,
+                        int flip, void* y, int y_fmt, int N, int H, int W, int C, int K, int R,
+                        int S, int pad, void* workspace, size_t workspace_bytes, void* stream) {
+  // flip=0: forward conv x[N][C][H][W] (narrow) -> y[N][Ho][Wo][K] (wide), w[K][C][R][S], pad
+  // flip=1: dgrad of a narrow-OUT conv (wide C_w=K here -> narrow C here): x = dy_narrow
+  //         [N][C][H][W], y = dx_wide [N][Hx][Wx][K]; w is that conv's OIHW weight [C][K][R][S].
+  GHND_CHECK_ARG(x && w && y && workspace, "conv_narrow_in: null pointer");
+  GHND_CHECK_ARG(pow2_lanes(K) && C >= 1 && C <= kNarrowMaxC && R * S <= kNarrowMaxTaps && R >= 1 &&
+                     S >= 1,
+                 "conv_narrow_in: unsupported shape C=%d K=%d %dx%d", C, K, R, S);
+  GHND_CHECK_ARG(workspace_bytes >= ghnd_conv_narrow_workspace_bytes(C, K, R, S),
+                 "conv_narrow_in: workspace too small");
+  GHND_CHECK_ARG(y_fmt == GHND_F16 || y_fmt == GHND_BF16, "conv_narrow_in: bad format");
+  cudaStream_t st = (cudaStream_t)stream;
+  NarrowTaps taps;
+  taps.n_taps = R * S;
+  int Ho, Wo;
+  if (!flip) {
+    Ho = H + 2 * pad - R + 1;
+    Wo = W + 2 * pad - S + 1;
+    // wt[tap][ci=c][co=k] = w[k][c][r][s] : mode 1 of the table builder with (K,C) as stored
+    narrow_wtable_kernel<<<4, 256, 0, st>>>(w, (float*)workspace, K, C, R, S, 0);
+    // mode 0 gives wt[tap][c][k] which is exactly [tap][ci][co]
+    for (int r = 0; r < R; ++r)
+      for (int s = 0; s < S; ++s) {
+        taps.dh[r * S + s] = r - pad;
+        taps.dw[r * S + s] = s - pad;
+      }
+  } else {
+    // the narrow-out conv mapped wide[Hx][Wx] -> narrow[H][W] with H = Hx + 2*pad - R + 1
+    Ho = H - 2 * pad + R - 1;
+    Wo = W - 2 * pad + S - 1;
+    // w is [Knarrow=C][Cwide=K][R][S]; need wt[tap][ci=narrow][co=wide] -> mode 1 with (K=C, C=K)
+    narrow_wtable_kernel<<<4, 256, 0, st>>>(w, (float*)workspace, C, K, R, S, 1);
+    for (int r = 0; r < R; ++r)
+      for (int s = 0; s < S; ++s) {
+        taps.dh[r * S + s] = pad - r;
+        taps.dw[r * S + s] = pad - s;
+      }
+  }
+  GHND_LAUNCH_CHECK("narrow_wtable_kernel");
+  GHND_CHECK_ARG(Ho > 0 && Wo > 0, "conv_narrow_in: empty output");
+  const int lanes = K / 8;
+  const int64_t npix = (int64_t)N * Ho * Wo;
+  narrow_in_kernel<<<blocks_for_pixels(npix, 256 / lanes), 256,
+                     (size_t)R * S * C * K * sizeof(float), st>>>(
+      x, pre_scale_shift, pre_relu, (const float*)workspace, (uint4*)y, y_fmt, N, H, W, C, K, Ho, Wo,
+      taps);
+  GHND_LAUNCH_CHECK("narrow_in_kernel");
+  return GHND_OK;
+}
+
+size_t ghnd_wgrad_narrow_workspace_bytes(int Ca, int Cb, int R, int S) {
+  return (size_t)Ca * Cb * R * S * sizeof(float);
+}
+
+int ghnd_wgrad_narrow(const float* a, const float* pre_scale_shift, int pre_relu, const void* b,
+                      int b_fmt, float* dw_oihw, int a_is_output, int N, int Ha, int Wa, int Ca,
+                      int Hb, int Wb, int Cb, int R, int S, int pad, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  GHND_CHECK_ARG(a && b && dw_oihw && workspace, "wgrad_narrow: null pointer");
+  GHND_CHECK_ARG(pow2_lanes(Cb) && Ca >= 1 && Ca <= kNarrowMaxC && R * S <= kNarrowMaxTaps && R >= 1 &&
+                     S >= 1,
+                 "wgrad_narrow: unsupported shape Ca=%d Cb=%d %dx%d", Ca, Cb, R, S);
+  GHND_CHECK_ARG(workspace_bytes >= ghnd_wgrad_narrow_workspace_bytes(Ca, Cb, R, S),
+                 "wgrad_narrow: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  GHND_CUDA(cudaMemsetAsync(workspace, 0, ghnd_wgrad_narrow_workspace_bytes(Ca, Cb, R, S), st));
+  NarrowTaps taps;
+  taps.n_taps = R * S;
+  for (int r = 0; r < R; ++r)
+    for (int s = 0; s < S; ++s) {
+      taps.dh[r * S + s] = a_is_output ? r - pad : pad - r;
+      taps.dw[r * S + s] = a_is_output ? s - pad : pad - s;
+    }
+  const int lanes = Cb / 8;
+  const int64_t npix = (int64_t)N * Ha * Wa;
+  for (int ca0 = 0; ca0 < Ca; ca0 += 3) {
+    wgrad_narrow_kernel<<<blocks_for_pixels(npix, (256 / lanes) * 8, 2), 256, 0, st>>>(
+        a, pre_scale_shift, pre_relu, (const uint4*)b, b_fmt, (float*)workspace, N, Ha, Wa, Ca, ca0,
+        Hb, Wb, Cb, taps);
+    GHND_LAUNCH_CHECK("wgrad_narrow_kernel");
+  }
+  wgrad_narrow_finish_kernel<<<4, 256, 0, st>>>((const float*)workspace, dw_oihw, a_is_output, Ca, Cb,
+                                                R, S);
+  GHND_LAUNCH_CHECK("wgrad_narrow_finish_kernel");
+  return GHND_OK;
+}
+
+int ghnd_stem_pack_weight(const float* w_oihw, const float* scale_o, void* dst, int dst_fmt,
+                          void* stream) {
+  GHND_CHECK_ARG(w_oihw && dst && (dst_fmt == GHND_F16 || dst_fmt == GHND_BF16),
+                 "stem_pack_weight: bad argument");
+  stem_pack_weight_kernel<<<(64 * 7 * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      w_oihw, scale_o, (uint16_t*)dst, dst_fmt);
+  GHND_LAUNCH_CHECK("stem_pack_weight_kernel");
+  return GHND_OK;
+}
+
+size_t ghnd_stem_wgrad_workspace_bytes(void) { return (size_t)64 * 196 * sizeof(float); }
+
+int ghnd_stem_wgrad(const void* x_packed, int x_fmt, const void* g, int g_fmt, const float* scale_o,
+                    float* dw_oihw, int N, int Hp, int Wp, void* workspace, size_t workspace_bytes,
+                    void* stream) {
+  GHND_CHECK_ARG(x_packed && g && dw_oihw && workspace, "stem_wgrad: null pointer");
+  GHND_CHECK_ARG(N > 0 && Hp > 0 && Wp > 0 && Hp % 2 == 0 && Wp % 8 == 0, "stem_wgrad: bad geometry");
+  GHND_CHECK_ARG(workspace_bytes >= ghnd_stem_wgrad_workspace_bytes(), "stem_wgrad: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  GHND_CUDA(cudaMemsetAsync(workspace, 0, ghnd_stem_wgrad_workspace_bytes(), st));
+  const int Ho = Hp / 2, Wo = Wp / 2;
+  const int segs = (Wo + kSwPix - 1) / kSwPix;
+  const int64_t chunks = (int64_t)N * Ho * segs;
+  int blocks = num_sms() * 2;
+  if (blocks > chunks) blocks = (int)chunks;
+  stem_wgrad_kernel<<<blocks, 256, 0, st>>>((const uint16_t*)x_packed, x_fmt, (const uint16_t*)g, g_fmt,
+                                            (float*)workspace, N, Ho, Wo, Hp + 6, Wp + 8);
+  GHND_LAUNCH_CHECK("stem_wgrad_kernel");
+  stem_wgrad_finish_kernel<<<(64 * 3 * 49 + 255) / 256, 256, 0, st>>>((const float*)workspace, scale_o,
+                                                                      dw_oihw);
+  GHND_LAUNCH_CHECK("stem_wgrad_finish_kernel");
+  return GHND_OK;
+}
+}

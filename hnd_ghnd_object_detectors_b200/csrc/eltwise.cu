@@ -1,0 +1,735 @@
+// HBM-bound helper kernels of the GHND path: layout boundary, stem input packing, max-pool,
+// training-mode BatchNorm (stats / apply / backward), weight repacking, fused Adam.
+#include "common.cuh"
+
+namespace ghnd {
+
+static inline int grid_for(int64_t work_items, int threads, int per_sm = 8) {
+  int64_t b = (work_items + threads - 1) / threads;
+  int64_t cap = (int64_t)num_sms() * per_sm;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+// ------------------------------------------------------------------------------------------------
+// NCHW fp32 <-> NHWC 16-bit (module boundary only; 32x32 smem transpose)
+// ------------------------------------------------------------------------------------------------
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst,
+                                    int fmt, int C, int64_t HW) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int64_t p0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i;
+    const int64_t p = p0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && p < HW) ? src[((int64_t)n * C + c) * HW + p] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t p = p0 + i;
+    const int c = c0 + threadIdx.x;
+    if (c < C && p < HW) dst[((int64_t)n * HW + p) * C + c] = float_to_h16(tile[threadIdx.x][i], fmt);
+  }
+}
+
+__global__ void nhwc_to_nchw_kernel(const uint16_t* __restrict__ src, int fmt,
+                                    float* __restrict__ dst, int C, int64_t HW) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int64_t p0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t p = p0 + i;
+    const int c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && p < HW) ? h16_to_float(src[((int64_t)n * HW + p) * C + c], fmt) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i;
+    const int64_t p = p0 + threadIdx.x;
+    if (c < C && p < HW) dst[((int64_t)n * C + c) * HW + p] = tile[threadIdx.x][i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// stem input: normalise + zero-pad + 4-channel pixel interleave, inside a 3-px zero frame
+// ------------------------------------------------------------------------------------------------
+__global__ void stem_pack_kernel(const float* __restrict__ img, int H, int W, float m0, float m1,
+                                 float m2, float s0, float s1, float s2, uint2* __restrict__ dst,
+                                 int fmt, int rows, int cols) {
+  const int64_t total = (int64_t)rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), c = (int)(i - (int64_t)r * cols);
+    const int h = r - 3, w = c - 3;
+    uint2 o = make_uint2(0u, 0u);
+    if (h >= 0 && h < H && w >= 0 && w < W) {
+      const int64_t hw = (int64_t)H * W, at = (int64_t)h * W + w;
+      // (image - mean) / std, true division like torchvision's normalize
+      const float a = __fdiv_rn(__fsub_rn(img[at], m0), s0);
+      const float b = __fdiv_rn(__fsub_rn(img[hw + at], m1), s1);
+      const float d = __fdiv_rn(__fsub_rn(img[2 * hw + at], m2), s2);
+      o.x = pack2(a, b, fmt);
+      o.y = pack2(d, 0.f, fmt);
+    }
+    dst[i] = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// max-pool 3x3 s2 p1 (NHWC, 8 channels per thread) + backward fused with the ReLU mask
+// ------------------------------------------------------------------------------------------------
+__global__ void maxpool_kernel(const uint4* __restrict__ x, uint4* __restrict__ y,
+                               uint2* __restrict__ argmax, int fmt, int N, int H, int W, int C8,
+                               int Ho, int Wo) {
+  const int64_t total = (int64_t)N * Ho * Wo * C8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % C8);
+    int64_t t = i / C8;
+    const int wo = (int)(t % Wo);
+    t /= Wo;
+    const int ho = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    float best[8];
+    uint32_t idx[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      best[j] = -INFINITY;
+      idx[j] = 0;
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int h = 2 * ho - 1 + r;
+      if (h < 0 || h >= H) continue;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int w = 2 * wo - 1 + s;
+        if (w < 0 || w >= W) continue;
+        const uint4 v = __ldg(x + (((int64_t)n * H + h) * W + w) * C8 + cg);
+        const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = unpack2(u[e], fmt);
+          if (f.x > best[2 * e]) {
+            best[2 * e] = f.x;
+            idx[2 * e] = r * 3 + s;
+          }
+          if (f.y > best[2 * e + 1]) {
+            best[2 * e + 1] = f.y;
+            idx[2 * e + 1] = r * 3 + s;
+          }
+        }
+      }
+    }
+    uint4 o;
+    o.x = pack2(best[0], best[1], fmt);
+    o.y = pack2(best[2], best[3], fmt);
+    o.z = pack2(best[4], best[5], fmt);
+    o.w = pack2(best[6], best[7], fmt);
+    y[i] = o;
+    if (argmax != nullptr) {
+      uint2 a;
+      a.x = idx[0] | (idx[1] << 8) | (idx[2] << 16) | (idx[3] << 24);
+      a.y = idx[4] | (idx[5] << 8) | (idx[6] << 16) | (idx[7] << 24);
+      argmax[i] = a;
+    }
+  }
+}
+
+__global__ void maxpool_bwd_kernel(const uint4* __restrict__ x, int x_fmt,
+                                   const uint2* __restrict__ argmax, const uint4* __restrict__ dy,
+                                   int dy_fmt, uint4* __restrict__ dx, int dx_fmt, int N, int H, int W,
+                                   int C8, int Ho, int Wo) {
+  const int64_t total = (int64_t)N * H * W * C8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % C8);
+    int64_t t = i / C8;
+    const int w = (int)(t % W);
+    t /= W;
+    const int h = (int)(t % H);
+    const int n = (int)(t / H);
+    float g[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = 0.f;
+    // windows ho with 2ho-1 <= h <= 2ho+1
+    const int ho_lo = h / 2, ho_hi = (h + 1) / 2;
+    const int wo_lo = w / 2, wo_hi = (w + 1) / 2;
+    for (int ho = ho_lo; ho <= ho_hi; ++ho) {
+      if (ho >= Ho) continue;
+      const uint32_t r = (uint32_t)(h - (2 * ho - 1));
+      for (int wo = wo_lo; wo <= wo_hi; ++wo) {
+        if (wo >= Wo) continue;
+        const uint32_t s = (uint32_t)(w - (2 * wo - 1));
+        const uint32_t me = r * 3 + s;
+        const int64_t o = (((int64_t)n * Ho + ho) * Wo + wo) * C8 + cg;
+        const uint2 a = __ldg(argmax + o);
+        const uint4 d = __ldg(dy + o);
+        const uint32_t du[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = unpack2(du[e], dy_fmt);
+          const uint32_t a0 = ((e < 2 ? a.x : a.y) >> (16 * (e & 1))) & 0xff;
+          const uint32_t a1 = ((e < 2 ? a.x : a.y) >> (16 * (e & 1) + 8)) & 0xff;
+          if (a0 == me) g[2 * e] += f.x;
+          if (a1 == me) g[2 * e + 1] += f.y;
+        }
+      }
+    }
+    const uint4 xv = __ldg(x + i);
+    const uint32_t xu[4] = {xv.x, xv.y, xv.z, xv.w};
+    uint32_t ou[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = unpack2(xu[e], x_fmt);
+      ou[e] = pack2(f.x > 0.f ? g[2 * e] : 0.f, f.y > 0.f ? g[2 * e + 1] : 0.f, dx_fmt);
+    }
+    dx[i] = make_uint4(ou[0], ou[1], ou[2], ou[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm (training): statistics, finalize, apply, backward
+// ------------------------------------------------------------------------------------------------
+// NHWC 16-bit: thread owns one 8-channel group and strides over pixels
+template <bool kBwd>
+__global__ void __launch_bounds__(256)
+    bn_reduce_nhwc_kernel(const uint4* __restrict__ x, int x_fmt, const uint4* __restrict__ dy,
+                          int dy_fmt, int64_t npix, int C, const float* __restrict__ scale_shift,
+                          const float* __restrict__ mean_invstd, int relu,
+                          double* __restrict__ sums) {
+  extern __shared__ float sh[];  // [2*C]
+  const int C8 = C >> 3;
+  const int lanes = blockDim.x / C8;  // pixel lanes per block
+  const int cg = threadIdx.x % C8;
+  const int lane = threadIdx.x / C8;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  float a[8], b[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = b[j] = 0.f;
+  float sc[8], shf[8], mu[8], is[8];
+  if (kBwd) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sc[j] = scale_shift[cg * 8 + j];
+      shf[j] = scale_shift[C + cg * 8 + j];
+      mu[j] = mean_invstd[cg * 8 + j];
+      is[j] = mean_invstd[C + cg * 8 + j];
+    }
+  }
+  if (lane < lanes) {
+    for (int64_t p = (int64_t)blockIdx.x * lanes + lane; p < npix; p += (int64_t)gridDim.x * lanes) {
+      const uint4 v = ld_stream(x + p * C8 + cg);
+      const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+      if (!kBwd) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = unpack2(u[e], x_fmt);
+          a[2 * e] += f.x;
+          a[2 * e + 1] += f.y;
+          b[2 * e] = fmaf(f.x, f.x, b[2 * e]);
+          b[2 * e + 1] = fmaf(f.y, f.y, b[2 * e + 1]);
+        }
+      } else {
+        const uint4 dv = ld_stream(dy + p * C8 + cg);
+        const uint32_t du[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = unpack2(u[e], x_fmt);
+          float2 g = unpack2(du[e], dy_fmt);
+          if (relu) {
+            if (!(fmaf(f.x, sc[2 * e], shf[2 * e]) > 0.f)) g.x = 0.f;
+            if (!(fmaf(f.y, sc[2 * e + 1], shf[2 * e + 1]) > 0.f)) g.y = 0.f;
+          }
+          a[2 * e] += g.x;
+          a[2 * e + 1] += g.y;
+          b[2 * e] = fmaf(g.x, (f.x - mu[2 * e]) * is[2 * e], b[2 * e]);
+          b[2 * e + 1] = fmaf(g.y, (f.y - mu[2 * e + 1]) * is[2 * e + 1], b[2 * e + 1]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&sh[cg * 8 + j], a[j]);
+      atomicAdd(&sh[C + cg * 8 + j], b[j]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&sums[i], (double)sh[i]);
+}
+
+// planar fp32 [N][C][HW]: grid (chunks, C, N)
+template <bool kBwd>
+__global__ void __launch_bounds__(256)
+    bn_reduce_planar_kernel(const float* __restrict__ x, const float* __restrict__ dy, int64_t hw,
+                            int C, const float* __restrict__ scale_shift,
+                            const float* __restrict__ mean_invstd, int relu,
+                            double* __restrict__ sums) {
+  const int c = blockIdx.y, n = blockIdx.z;
+  const float* xp = x + ((int64_t)n * C + c) * hw;
+  const float* dp = kBwd ? dy + ((int64_t)n * C + c) * hw : nullptr;
+  float sc = 0, shf = 0, mu = 0, is = 0;
+  if (kBwd) {
+    sc = scale_shift[c];
+    shf = scale_shift[C + c];
+    mu = mean_invstd[c];
+    is = mean_invstd[C + c];
+  }
+  double a = 0.0, b = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hw;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = xp[i];
+    if (!kBwd) {
+      a += v;
+      b += (double)v * v;
+    } else {
+      float g = dp[i];
+      if (relu && !(fmaf(v, sc, shf) > 0.f)) g = 0.f;
+      a += g;
+      b += (double)g * ((v - mu) * is);
+    }
+  }
+  __shared__ double ra[8], rb[8];
+  a = warp_sum(a);
+  b = warp_sum(b);
+  if ((threadIdx.x & 31) == 0) {
+    ra[threadIdx.x >> 5] = a;
+    rb[threadIdx.x >> 5] = b;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ta = 0, tb = 0;
+    for (int w = 0; w < 8; ++w) {
+      ta += ra[w];
+      tb += rb[w];
+    }
+    atomicAdd(&sums[c], ta);
+    atomicAdd(&sums[C + c], tb);
+  }
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, int C,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float eps, float momentum, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, int64_t* __restrict__ nbt,
+                                   float* __restrict__ scale_shift, float* __restrict__ mean_invstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && nbt != nullptr) *nbt += 1;
+  if (c >= C) return;
+  const double mean = sums[c] / count;
+  double var = sums[C + c] / count - mean * mean;  // biased
+  if (var < 0.0) var = 0.0;
+  const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  const float sc = g * invstd;
+  scale_shift[c] = sc;
+  scale_shift[C + c] = b - (float)mean * sc;
+  mean_invstd[c] = (float)mean;
+  mean_invstd[C + c] = invstd;
+  if (running_mean != nullptr) {
+    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+__global__ void bn_eval_params_kernel(int C, const float* __restrict__ gamma,
+                                      const float* __restrict__ beta, const float* __restrict__ rm,
+                                      const float* __restrict__ rv, float eps,
+                                      float* __restrict__ scale_shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float invstd = 1.0f / sqrtf(rv[c] + eps);
+  const float sc = (gamma ? gamma[c] : 1.f) * invstd;
+  scale_shift[c] = sc;
+  scale_shift[C + c] = (beta ? beta[c] : 0.f) - rm[c] * sc;
+}
+
+__global__ void __launch_bounds__(256)
+    bn_apply_kernel(const uint4* __restrict__ x, int x_fmt, uint4* __restrict__ y, int y_fmt,
+                    int64_t nvec, int C8, const float* __restrict__ scale_shift, int relu) {
+  const int C = C8 * 8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % C8);
+    const uint4 v = ld_stream(x + i);
+    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = unpack2(u[e], x_fmt);
+      const int c = cg * 8 + 2 * e;
+      float a = fmaf(f.x, __ldg(scale_shift + c), __ldg(scale_shift + C + c));
+      float b = fmaf(f.y, __ldg(scale_shift + c + 1), __ldg(scale_shift + C + c + 1));
+      if (relu) {
+        a = fmaxf(a, 0.f);
+        b = fmaxf(b, 0.f);
+      }
+      o[e] = pack2(a, b, y_fmt);
+    }
+    y[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    bn_bwd_apply_nhwc_kernel(const uint4* __restrict__ dy, int dy_fmt, const uint4* __restrict__ x,
+                             int x_fmt, uint4* __restrict__ dx, int dx_fmt, int64_t nvec, int C8,
+                             double inv_count, const float* __restrict__ gamma,
+                             const float* __restrict__ scale_shift,
+                             const float* __restrict__ mean_invstd, int relu,
+                             const double* __restrict__ sums) {
+  const int C = C8 * 8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % C8);
+    const uint4 xv = ld_stream(x + i), dv = ld_stream(dy + i);
+    const uint32_t xu[4] = {xv.x, xv.y, xv.z, xv.w}, du[4] = {dv.x, dv.y, dv.z, dv.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = unpack2(xu[e], x_fmt);
+      const float2 g = unpack2(du[e], dy_fmt);
+      float r[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = cg * 8 + 2 * e + h;
+        const float xv1 = h ? f.y : f.x;
+        float gv = h ? g.y : g.x;
+        const float sc = __ldg(scale_shift + c), sf = __ldg(scale_shift + C + c);
+        if (relu && !(fmaf(xv1, sc, sf) > 0.f)) gv = 0.f;
+        const float xhat = (xv1 - __ldg(mean_invstd + c)) * __ldg(mean_invstd + C + c);
+        const float mg = (float)(sums[c] * inv_count), mgx = (float)(sums[C + c] * inv_count);
+        r[h] = sc * (gv - mg - xhat * mgx);  // sc = gamma*invstd
+      }
+      o[e] = pack2(r[0], r[1], dx_fmt);
+    }
+    dx[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+  (void)gamma;
+}
+
+__global__ void __launch_bounds__(256)
+    bn_bwd_apply_planar_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                               float* __restrict__ dx, int64_t hw, int C, double inv_count,
+                               const float* __restrict__ scale_shift,
+                               const float* __restrict__ mean_invstd, int relu,
+                               const double* __restrict__ sums) {
+  const int c = blockIdx.y, n = blockIdx.z;
+  const int64_t base = ((int64_t)n * C + c) * hw;
+  const float sc = scale_shift[c], sf = scale_shift[C + c];
+  const float mu = mean_invstd[c], is = mean_invstd[C + c];
+  const float mg = (float)(sums[c] * inv_count), mgx = (float)(sums[C + c] * inv_count);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hw;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = x[base + i];
+    float g = dy[base + i];
+    if (relu && !(fmaf(v, sc, sf) > 0.f)) g = 0.f;
+    dx[base + i] = sc * (g - mg - (v - mu) * is * mgx);
+  }
+}
+
+__global__ void bn_param_grads_kernel(const double* __restrict__ sums, int C,
+                                      float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  if (dbeta) dbeta[c] = (float)sums[c];
+  if (dgamma) dgamma[c] = (float)sums[C + c];
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight repack / gradient unpack
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_weight_kernel(const float* __restrict__ w, const float* __restrict__ scale, int O,
+                                   int I, int R, int S, int transpose, uint16_t* __restrict__ dst,
+                                   int fmt) {
+  const int64_t total = (int64_t)O * I * R * S;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    // i indexes dst
+    int64_t t = i;
+    int o, c, r, s;
+    if (!transpose) {  // [O][R][S][I]
+      c = (int)(t % I);
+      t /= I;
+      s = (int)(t % S);
+      t /= S;
+      r = (int)(t % R);
+      o = (int)(t / R);
+    } else {  // [I][R][S][O]
+      o = (int)(t % O);
+      t /= O;
+      s = (int)(t % S);
+      t /= S;
+      r = (int)(t % R);
+      c = (int)(t / R);
+    }
+    float v = w[(((int64_t)o * I + c) * R + r) * S + s];
+    if (scale != nullptr) v *= scale[o];
+    dst[i] = float_to_h16(v, fmt);
+  }
+}
+
+__global__ void unpack_wgrad_kernel(const float* __restrict__ dw, float* __restrict__ dst, int O, int I,
+                                    int R, int S, float alpha) {
+  const int64_t total = (int64_t)O * I * R * S;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    // i indexes dst (OIHW)
+    int64_t t = i;
+    const int s = (int)(t % S);
+    t /= S;
+    const int r = (int)(t % R);
+    t /= R;
+    const int c = (int)(t % I);
+    const int o = (int)(t / I);
+    dst[i] = alpha * dw[(((int64_t)o * R + r) * S + s) * I + c];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused Adam over a flat buffer (torch.optim.Adam, amsgrad=False)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                float* __restrict__ v, int64_t n, float beta1, float beta2, float eps, float wd,
+                float gscale, float step_size, float inv_sqrt_bc2) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float grad = g[i] * gscale;
+    const float pv = p[i];
+    if (wd != 0.f) grad = fmaf(wd, pv, grad);
+    const float mi = fmaf(beta1, m[i], (1.f - beta1) * grad);
+    const float vi = fmaf(beta2, v[i], (1.f - beta2) * grad * grad);
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
+    p[i] = pv - step_size * (mi / denom);
+  }
+}
+
+}  // namespace ghnd
+
+extern "C" {
+using namespace ghnd;
+
+static bool fmt16(int f) { return f == GHND_F16 || f == GHND_BF16; }
+
+int ghnd_nchw_f32_to_nhwc16(const float* src, void* dst, int dst_fmt, int N, int C, int H, int W,
+                            void* stream) {
+  GHND_CHECK_ARG(src && dst && fmt16(dst_fmt) && N > 0 && C > 0 && H > 0 && W > 0,
+                 "nchw_f32_to_nhwc16: bad argument");
+  const int64_t hw = (int64_t)H * W;
+  dim3 grid((unsigned)((hw + 31) / 32), (unsigned)((C + 31) / 32), (unsigned)N), block(32, 8);
+  nchw_to_nhwc_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src, (uint16_t*)dst, dst_fmt, C, hw);
+  GHND_LAUNCH_CHECK("nchw_to_nhwc_kernel");
+  return GHND_OK;
+}
+
+int ghnd_nhwc16_to_nchw_f32(const void* src, int src_fmt, float* dst, int N, int C, int H, int W,
+                            void* stream) {
+  GHND_CHECK_ARG(src && dst && fmt16(src_fmt) && N > 0 && C > 0 && H > 0 && W > 0,
+                 "nhwc16_to_nchw_f32: bad argument");
+  const int64_t hw = (int64_t)H * W;
+  dim3 grid((unsigned)((hw + 31) / 32), (unsigned)((C + 31) / 32), (unsigned)N), block(32, 8);
+  nhwc_to_nchw_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const uint16_t*)src, src_fmt, dst, C,
+                                                                hw);
+  GHND_LAUNCH_CHECK("nhwc_to_nchw_kernel");
+  return GHND_OK;
+}
+
+int ghnd_stem_pack_image(const float* img_chw, int H, int W, const float* mean, const float* std_,
+                         void* dst, int dst_fmt, int n_index, int Hp, int Wp, void* stream) {
+  GHND_CHECK_ARG(img_chw && mean && std_ && dst && fmt16(dst_fmt), "stem_pack_image: bad argument");
+  GHND_CHECK_ARG(H > 0 && W > 0 && H <= Hp && W <= Wp && Hp % 2 == 0 && Wp % 8 == 0 && n_index >= 0,
+                 "stem_pack_image: bad geometry H=%d W=%d Hp=%d Wp=%d", H, W, Hp, Wp);
+  const int rows = Hp + 6, cols = Wp + 8;
+  uint2* d = (uint2*)dst + (int64_t)n_index * rows * cols;
+  stem_pack_kernel<<<grid_for((int64_t)rows * cols, 256), 256, 0, (cudaStream_t)stream>>>(
+      img_chw, H, W, mean[0], mean[1], mean[2], std_[0], std_[1], std_[2], d, dst_fmt, rows, cols);
+  GHND_LAUNCH_CHECK("stem_pack_kernel");
+  return GHND_OK;
+}
+
+int ghnd_maxpool3x3s2(const void* x, void* y, void* argmax, int fmt, int N, int H, int W, int C,
+                      void* stream) {
+  GHND_CHECK_ARG(x && y && fmt16(fmt) && N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0,
+                 "maxpool3x3s2: bad argument");
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+  const int64_t total = (int64_t)N * Ho * Wo * (C / 8);
+  maxpool_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const uint4*)x, (uint4*)y, (uint2*)argmax, fmt, N, H, W, C / 8, Ho, Wo);
+  GHND_LAUNCH_CHECK("maxpool_kernel");
+  return GHND_OK;
+}
+
+int ghnd_maxpool3x3s2_bwd(const void* x, int x_fmt, const void* argmax, const void* dy, int dy_fmt,
+                          void* dx, int dx_fmt, int N, int H, int W, int C, void* stream) {
+  GHND_CHECK_ARG(x && argmax && dy && dx && fmt16(x_fmt) && fmt16(dy_fmt) && fmt16(dx_fmt),
+                 "maxpool3x3s2_bwd: bad argument");
+  GHND_CHECK_ARG(N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "maxpool3x3s2_bwd: bad geometry");
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+  const int64_t total = (int64_t)N * H * W * (C / 8);
+  maxpool_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const uint4*)x, x_fmt, (const uint2*)argmax, (const uint4*)dy, dy_fmt, (uint4*)dx, dx_fmt, N, H,
+      W, C / 8, Ho, Wo);
+  GHND_LAUNCH_CHECK("maxpool_bwd_kernel");
+  return GHND_OK;
+}
+
+static int bn_geom_ok(int planar, int C) {
+  if (planar) return C > 0;
+  // NHWC: one thread per 8-channel group, 256 threads must be a multiple of the group count
+  return C >= 8 && C % 8 == 0 && C / 8 <= 256 && 256 % (C / 8) == 0;
+}
+
+int ghnd_bn_stats(const void* x, int fmt, int planar, int N, int64_t hw, int C, double* sums,
+                  void* stream) {
+  GHND_CHECK_ARG(x && sums && N > 0 && hw > 0, "bn_stats: bad argument");
+  GHND_CHECK_ARG(bn_geom_ok(planar, C), "bn_stats: unsupported channel count %d", C);
+  cudaStream_t st = (cudaStream_t)stream;
+  GHND_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
+  if (planar) {
+    dim3 grid((unsigned)grid_for(hw, 256 * 8, 2), (unsigned)C, (unsigned)N);
+    bn_reduce_planar_kernel<false><<<grid, 256, 0, st>>>((const float*)x, nullptr, hw, C, nullptr,
+                                                         nullptr, 0, sums);
+  } else {
+    GHND_CHECK_ARG(fmt16(fmt), "bn_stats: bad format");
+    const int64_t npix = (int64_t)N * hw;
+    const int lanes = 256 / (C / 8);
+    bn_reduce_nhwc_kernel<false><<<grid_for(npix, lanes * 8, 4), 256, 2 * C * sizeof(float), st>>>(
+        (const uint4*)x, fmt, nullptr, 0, npix, C, nullptr, nullptr, 0, sums);
+  }
+  GHND_LAUNCH_CHECK("bn_reduce_kernel");
+  return GHND_OK;
+}
+
+int ghnd_bn_finalize(const double* sums, int64_t count, int C, const float* gamma,
+                     const float* beta, float eps, float momentum, float* running_mean,
+                     float* running_var, int64_t* num_batches_tracked, float* scale_shift,
+                     float* mean_invstd, void* stream) {
+  GHND_CHECK_ARG(sums && scale_shift && mean_invstd && count > 0 && C > 0,
+                 "bn_finalize: bad argument");
+  GHND_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr),
+                 "bn_finalize: running_mean/var must both be given or both be null");
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      sums, (double)count, C, gamma, beta, eps, momentum, running_mean, running_var,
+      num_batches_tracked, scale_shift, mean_invstd);
+  GHND_LAUNCH_CHECK("bn_finalize_kernel");
+  return GHND_OK;
+}
+
+int ghnd_bn_eval_params(int C, const float* gamma, const float* beta, const float* running_mean,
+                        const float* running_var, float eps, float* scale_shift, void* stream) {
+  GHND_CHECK_ARG(C > 0 && running_mean && running_var && scale_shift, "bn_eval_params: bad argument");
+  bn_eval_params_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      C, gamma, beta, running_mean, running_var, eps, scale_shift);
+  GHND_LAUNCH_CHECK("bn_eval_params_kernel");
+  return GHND_OK;
+}
+
+int ghnd_bn_apply(const void* x, int x_fmt, void* y, int y_fmt, int64_t npix, int C,
+                  const float* scale_shift, int relu, void* stream) {
+  GHND_CHECK_ARG(x && y && scale_shift && fmt16(x_fmt) && fmt16(y_fmt) && npix > 0 && C > 0 &&
+                     C % 8 == 0,
+                 "bn_apply: bad argument");
+  const int64_t nvec = npix * (C / 8);
+  bn_apply_kernel<<<grid_for(nvec, 256 * 2), 256, 0, (cudaStream_t)stream>>>(
+      (const uint4*)x, x_fmt, (uint4*)y, y_fmt, nvec, C / 8, scale_shift, relu);
+  GHND_LAUNCH_CHECK("bn_apply_kernel");
+  return GHND_OK;
+}
+
+int ghnd_bn_bwd_reduce(const void* dy, int dy_fmt, const void* x, int x_fmt, int planar, int N,
+                       int64_t hw, int C, const float* scale_shift, const float* mean_invstd,
+                       int relu, double* sums, void* stream) {
+  GHND_CHECK_ARG(dy && x && scale_shift && mean_invstd && sums && N > 0 && hw > 0,
+                 "bn_bwd_reduce: bad argument");
+  GHND_CHECK_ARG(bn_geom_ok(planar, C), "bn_bwd_reduce: unsupported channel count %d", C);
+  cudaStream_t st = (cudaStream_t)stream;
+  GHND_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
+  if (planar) {
+    dim3 grid((unsigned)grid_for(hw, 256 * 8, 2), (unsigned)C, (unsigned)N);
+    bn_reduce_planar_kernel<true><<<grid, 256, 0, st>>>((const float*)x, (const float*)dy, hw, C,
+                                                        scale_shift, mean_invstd, relu, sums);
+  } else {
+    GHND_CHECK_ARG(fmt16(dy_fmt) && fmt16(x_fmt), "bn_bwd_reduce: bad format");
+    const int64_t npix = (int64_t)N * hw;
+    const int lanes = 256 / (C / 8);
+    bn_reduce_nhwc_kernel<true><<<grid_for(npix, lanes * 8, 4), 256, 2 * C * sizeof(float), st>>>(
+        (const uint4*)x, x_fmt, (const uint4*)dy, dy_fmt, npix, C, scale_shift, mean_invstd, relu,
+        sums);
+  }
+  GHND_LAUNCH_CHECK("bn_bwd_reduce_kernel");
+  return GHND_OK;
+}
+
+int ghnd_bn_bwd_apply(const void* dy, int dy_fmt, const void* x, int x_fmt, void* dx, int dx_fmt,
+                      int planar, int N, int64_t hw, int C, const float* gamma,
+                      const float* scale_shift, const float* mean_invstd, int relu,
+                      const double* sums, float* dgamma, float* dbeta, void* stream) {
+  GHND_CHECK_ARG(dy && x && dx && scale_shift && mean_invstd && sums && N > 0 && hw > 0,
+                 "bn_bwd_apply: bad argument");
+  GHND_CHECK_ARG(bn_geom_ok(planar, C), "bn_bwd_apply: unsupported channel count %d", C);
+  cudaStream_t st = (cudaStream_t)stream;
+  const double inv_count = 1.0 / ((double)N * (double)hw);
+  if (planar) {
+    dim3 grid((unsigned)grid_for(hw, 256 * 4, 2), (unsigned)C, (unsigned)N);
+    bn_bwd_apply_planar_kernel<<<grid, 256, 0, st>>>((const float*)dy, (const float*)x, (float*)dx, hw,
+                                                     C, inv_count, scale_shift, mean_invstd, relu,
+                                                     sums);
+  } else {
+    GHND_CHECK_ARG(fmt16(dy_fmt) && fmt16(x_fmt) && fmt16(dx_fmt), "bn_bwd_apply: bad format");
+    const int64_t nvec = (int64_t)N * hw * (C / 8);
+    bn_bwd_apply_nhwc_kernel<<<grid_for(nvec, 256 * 2), 256, 0, st>>>(
+        (const uint4*)dy, dy_fmt, (const uint4*)x, x_fmt, (uint4*)dx, dx_fmt, nvec, C / 8, inv_count,
+        gamma, scale_shift, mean_invstd, relu, sums);
+  }
+  GHND_LAUNCH_CHECK("bn_bwd_apply_kernel");
+  if (dgamma != nullptr || dbeta != nullptr) {
+    bn_param_grads_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, C, dgamma, dbeta);
+    GHND_LAUNCH_CHECK("bn_param_grads_kernel");
+  }
+  return GHND_OK;
+}
+
+int ghnd_pack_weight(const float* w_oihw, const float* scale_o, int O, int I, int R, int S,
+                     int transpose, void* dst, int dst_fmt, void* stream) {
+  GHND_CHECK_ARG(w_oihw && dst && fmt16(dst_fmt) && O > 0 && I > 0 && R > 0 && S > 0,
+                 "pack_weight: bad argument");
+  const int64_t total = (int64_t)O * I * R * S;
+  pack_weight_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      w_oihw, scale_o, O, I, R, S, transpose, (uint16_t*)dst, dst_fmt);
+  GHND_LAUNCH_CHECK("pack_weight_kernel");
+  return GHND_OK;
+}
+
+int ghnd_unpack_wgrad(const float* dw_orsi, float* dst_oihw, int O, int I, int R, int S,
+                      float alpha, void* stream) {
+  GHND_CHECK_ARG(dw_orsi && dst_oihw && O > 0 && I > 0 && R > 0 && S > 0, "unpack_wgrad: bad argument");
+  const int64_t total = (int64_t)O * I * R * S;
+  unpack_wgrad_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(dw_orsi, dst_oihw, O, I,
+                                                                              R, S, alpha);
+  GHND_LAUNCH_CHECK("unpack_wgrad_kernel");
+  return GHND_OK;
+}
+
+int ghnd_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                   float lr, float beta1, float beta2, float eps, float weight_decay,
+                   float grad_scale, int step, void* stream) {
+  GHND_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && n > 0 && step >= 1,
+                 "adam_step: bad argument");
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  const float step_size = (float)((double)lr / bc1);
+  const float inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+  adam_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
+      param, grad, exp_avg, exp_avg_sq, n, beta1, beta2, eps, weight_decay, grad_scale, step_size,
+      inv_sqrt_bc2);
+  GHND_LAUNCH_CHECK("adam_kernel");
+  return GHND_OK;
+}
+}

@@ -1,0 +1,237 @@
+// 8-bit affine quantizer / dequantizer of the bottleneck tensor (HBM-bound, bit-exact).
+// Arithmetic follows src/myutils/pytorch/tensor_util.py:8-22 of the reference operation by
+// operation with explicit round-to-nearest intrinsics (no FMA contraction, no fast division).
+#include <math.h>
+
+#include "common.cuh"
+
+namespace ghnd {
+
+static constexpr int kQThreads = 256;
+static constexpr int kQMaxBlocks = 1024;
+
+// torch.min/max propagate NaN
+__device__ __forceinline__ float nan_min(float a, float b) {
+  return (a != a) ? a : ((b != b) ? b : fminf(a, b));
+}
+__device__ __forceinline__ float nan_max(float a, float b) {
+  return (a != a) ? a : ((b != b) ? b : fmaxf(a, b));
+}
+
+__device__ __forceinline__ void block_minmax(float& mn, float& mx) {
+  __shared__ float s_mn[32], s_mx[32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = nan_min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = nan_max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) {
+    s_mn[w] = mn;
+    s_mx[w] = mx;
+  }
+  __syncthreads();
+  const int nw = blockDim.x >> 5;
+  mn = (l < nw) ? s_mn[l] : s_mn[0];
+  mx = (l < nw) ? s_mx[l] : s_mx[0];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = nan_min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = nan_max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  __syncthreads();
+}
+
+// pass 1: per-block min / max partials (no atomics -> deterministic, no init needed)
+__global__ void __launch_bounds__(kQThreads)
+    quant_minmax_kernel(const float* __restrict__ x, int64_t n, int vec_ok,
+                        float* __restrict__ partial) {
+  float mn = INFINITY, mx = -INFINITY;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  int64_t done = 0;
+  if (vec_ok) {
+    const int64_t n4 = n >> 2;
+    const uint4* x4 = reinterpret_cast<const uint4*>(x);
+    for (int64_t i = tid; i < n4; i += nthreads) {
+      uint4 v = ld_stream(x4 + i);
+      float a = __uint_as_float(v.x), b = __uint_as_float(v.y), c = __uint_as_float(v.z),
+            d = __uint_as_float(v.w);
+      mn = nan_min(nan_min(mn, a), nan_min(b, nan_min(c, d)));
+      mx = nan_max(nan_max(mx, a), nan_max(b, nan_max(c, d)));
+    }
+    done = n4 << 2;
+  }
+  for (int64_t i = done + tid; i < n; i += nthreads) {
+    float a = x[i];
+    mn = nan_min(mn, a);
+    mx = nan_max(mx, a);
+  }
+  block_minmax(mn, mx);
+  if (threadIdx.x == 0) {
+    partial[2 * blockIdx.x] = mn;
+    partial[2 * blockIdx.x + 1] = mx;
+  }
+}
+
+struct QParams {
+  float scale;
+  int zero_point;
+  float mn, mx;
+};
+
+// pass 2: every block folds the partials (L2 resident), derives scale / zero-point, quantizes.
+__global__ void __launch_bounds__(kQThreads)
+    quant_apply_kernel(const float* __restrict__ x, int64_t n, int vec_ok,
+                       const float* __restrict__ partial, int n_partial, float qmax,
+                       float inv_range, int scale_mode, uint8_t* __restrict__ q,
+                       QParams* __restrict__ qp) {
+  float mn = INFINITY, mx = -INFINITY;
+  for (int i = threadIdx.x; i < n_partial; i += blockDim.x) {
+    mn = nan_min(mn, partial[2 * i]);
+    mx = nan_max(mx, partial[2 * i + 1]);
+  }
+  block_minmax(mn, mx);
+  // scale = (max - min) / (qmax - qmin)        tensor_util.py:12
+  const float range = __fsub_rn(mx, mn);
+  const float scale =
+      scale_mode == GHND_QSCALE_RECIP ? __fmul_rn(range, inv_range) : __fdiv_rn(range, qmax);
+  // initial_zero_point = qmin - min / scale    tensor_util.py:13
+  const float izp = __fsub_rn(0.0f, __fdiv_rn(mn, scale));
+  // clamp to [qmin, qmax] then int() truncation   tensor_util.py:14-15 ; NaN -> marker
+  int zp;
+  if (izp < 0.0f)
+    zp = 0;
+  else if (izp > qmax)
+    zp = (int)qmax;
+  else if (izp != izp)
+    zp = INT_MIN;
+  else
+    zp = (int)izp;  // cvt.rzi
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    qp->scale = scale;
+    qp->zero_point = zp;
+    qp->mn = mn;
+    qp->mx = mx;
+  }
+  const float zpf = (float)zp;
+  auto quant1 = [&](float v) -> uint32_t {
+    // qx = zero_point + x / scale ; clamp ; round-half-even ; byte   tensor_util.py:16-17
+    float t = __fadd_rn(zpf, __fdiv_rn(v, scale));
+    t = t < 0.0f ? 0.0f : (t > qmax ? qmax : t);
+    return (uint32_t)(int)rintf(t) & 0xffu;
+  };
+  auto quant4 = [&](uint4 v) -> uint32_t {
+    return quant1(__uint_as_float(v.x)) | (quant1(__uint_as_float(v.y)) << 8) |
+           (quant1(__uint_as_float(v.z)) << 16) | (quant1(__uint_as_float(v.w)) << 24);
+  };
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  int64_t done = 0;
+  if (vec_ok) {
+    const int64_t n16 = n >> 4;
+    const uint4* x4 = reinterpret_cast<const uint4*>(x);
+    uint4* q16 = reinterpret_cast<uint4*>(q);
+    for (int64_t i = tid; i < n16; i += nthreads) {
+      uint4 a = ld_stream(x4 + 4 * i), b = ld_stream(x4 + 4 * i + 1), c = ld_stream(x4 + 4 * i + 2),
+            d = ld_stream(x4 + 4 * i + 3);
+      uint4 o;
+      o.x = quant4(a);
+      o.y = quant4(b);
+      o.z = quant4(c);
+      o.w = quant4(d);
+      st_stream(q16 + i, o);
+    }
+    done = n16 << 4;
+  }
+  for (int64_t i = done + tid; i < n; i += nthreads) q[i] = (uint8_t)quant1(x[i]);
+}
+
+__global__ void __launch_bounds__(kQThreads)
+    dequant_kernel(const uint8_t* __restrict__ q, int64_t n, int vec_ok,
+                   const QParams* __restrict__ qp, float* __restrict__ out) {
+  const float scale = qp->scale;
+  const float zpf = (float)qp->zero_point;
+  // scale * (q.float() - zero_point)   tensor_util.py:22
+  auto dq = [&](uint32_t b) -> float { return __fmul_rn(scale, __fsub_rn((float)b, zpf)); };
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  int64_t done = 0;
+  if (vec_ok) {
+    const int64_t n16 = n >> 4;
+    const uint4* q16 = reinterpret_cast<const uint4*>(q);
+    uint4* o4 = reinterpret_cast<uint4*>(out);
+    for (int64_t i = tid; i < n16; i += nthreads) {
+      uint4 v = ld_stream(q16 + i);
+      uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 o;
+        o.x = __float_as_uint(dq(w[j] & 0xff));
+        o.y = __float_as_uint(dq((w[j] >> 8) & 0xff));
+        o.z = __float_as_uint(dq((w[j] >> 16) & 0xff));
+        o.w = __float_as_uint(dq(w[j] >> 24));
+        st_stream(o4 + 4 * i + j, o);
+      }
+    }
+    done = n16 << 4;
+  }
+  for (int64_t i = done + tid; i < n; i += nthreads) out[i] = dq(q[i]);
+}
+
+static int quant_blocks(int64_t n) {
+  int64_t per_block = (int64_t)kQThreads * 16;
+  int64_t b = (n + per_block - 1) / per_block;
+  int64_t cap = (int64_t)num_sms() * 4;
+  if (cap > kQMaxBlocks) cap = kQMaxBlocks;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace ghnd
+
+extern "C" {
+
+size_t ghnd_quantize_u8_workspace_bytes(int64_t n) {
+  (void)n;
+  return (size_t)ghnd::kQMaxBlocks * 2 * sizeof(float);
+}
+
+int ghnd_quantize_u8(const float* x, int64_t n, int num_bits, int scale_mode, uint8_t* q,
+                     void* qparams, void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace ghnd;
+  GHND_CHECK_ARG(x && q && qparams && workspace, "quantize_u8: null pointer");
+  GHND_CHECK_ARG(n > 0, "quantize_u8: empty tensor (reference: min() of an empty tensor raises)");
+  GHND_CHECK_ARG(num_bits >= 1 && num_bits <= 8, "quantize_u8: num_bits %d not in [1,8]", num_bits);
+  GHND_CHECK_ARG(scale_mode == GHND_QSCALE_DIV || scale_mode == GHND_QSCALE_RECIP,
+                 "quantize_u8: bad scale_mode %d", scale_mode);
+  GHND_CHECK_ARG(workspace_bytes >= ghnd_quantize_u8_workspace_bytes(n),
+                 "quantize_u8: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int vec_ok = ((((uintptr_t)x) & 15) == 0 && (((uintptr_t)q) & 15) == 0) ? 1 : 0;
+  const int blocks = quant_blocks(n);
+  const float qmax = (float)((1 << num_bits) - 1);
+  const float inv_range = 1.0f / qmax;  // torch CUDA: a / cpu_scalar == a * (1/scalar) in fp32
+  quant_minmax_kernel<<<blocks, kQThreads, 0, st>>>(x, n, vec_ok, (float*)workspace);
+  GHND_LAUNCH_CHECK("quant_minmax_kernel");
+  quant_apply_kernel<<<blocks, kQThreads, 0, st>>>(x, n, vec_ok, (const float*)workspace, blocks,
+                                                   qmax, inv_range, scale_mode, q,
+                                                   (QParams*)qparams);
+  GHND_LAUNCH_CHECK("quant_apply_kernel");
+  return GHND_OK;
+}
+
+int ghnd_dequantize_u8(const uint8_t* q, int64_t n, const void* qparams, float* out,
+                       void* stream) {
+  using namespace ghnd;
+  GHND_CHECK_ARG(q && qparams && out, "dequantize_u8: null pointer");
+  GHND_CHECK_ARG(n >= 0, "dequantize_u8: negative size");
+  if (n == 0) return GHND_OK;
+  const int vec_ok = ((((uintptr_t)out) & 15) == 0 && (((uintptr_t)q) & 15) == 0) ? 1 : 0;
+  dequant_kernel<<<quant_blocks(n), kQThreads, 0, (cudaStream_t)stream>>>(
+      q, n, vec_ok, (const QParams*)qparams, out);
+  GHND_LAUNCH_CHECK("dequant_kernel");
+  return GHND_OK;
+}
+}

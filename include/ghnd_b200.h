@@ -1,0 +1,274 @@
+/*
+ * ghnd_b200.h -- C ABI of the B200-native GHND hot path (libghnd_b200.so).
+ *
+ * The reference (yoshitomo-matsubara/hnd-ghnd-object-detectors) is pure Python and has no FFI;
+ * each entry point below replaces the implicit torch/cuDNN library call made at the cited
+ * reference location (paths relative to the reference root).  Rules of the boundary:
+ *   - extern "C", plain pointers and sizes, a cudaStream_t passed as void*; no torch types.
+ *   - every pointer is DEVICE memory owned by the caller unless the comment says "host".
+ *   - no allocation of tensor memory, no ownership transfer, no hidden synchronisation;
+ *     work is enqueued on the given stream (CUDA-graph capturable).
+ *   - return value: GHND_OK or an error code; ghnd_last_error() gives the message (thread local).
+ *
+ * Tensors on the 16-bit activation path are NHWC ("pixel-major": [N][H][W][C], C contiguous);
+ * element format is a run-time flag: GHND_F16 or GHND_BF16.
+ */
+#ifndef GHND_B200_H
+#define GHND_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GHND_OK 0
+#define GHND_ERR_INVALID 1
+#define GHND_ERR_CUDA 2
+#define GHND_ERR_UNSUPPORTED 3
+
+#define GHND_F16 0  /* IEEE half   (matches the tcgen05 kind::f16 a/b format code) */
+#define GHND_BF16 1 /* bfloat16 */
+
+#define GHND_ABI_VERSION 1
+
+const char* ghnd_last_error(void);
+int ghnd_abi_version(void);
+/* GHND_OK iff the current CUDA device is compute capability 10.x (the only target). */
+int ghnd_device_check(void);
+
+/* ------------------------------------------------------------------------------------------
+ * 8-bit affine quantizer of the bottleneck tensor.
+ * Replaces myutils.pytorch.tensor_util.quantize_tensor / dequantize_tensor
+ * (src/myutils/pytorch/tensor_util.py:8-22), reached through structure.transformer.Quantizer /
+ * Dequantizer (src/structure/transformer.py:131-153).
+ *   scale = (max-min)/(2^bits-1); zp = trunc(clamp(0 - min/scale, 0, qmax));
+ *   q = u8(rint(clamp(zp + x/scale, 0, qmax)))          (one scale for the whole tensor)
+ * scale_mode selects how torch evaluates "tensor / python_float" for `scale`:
+ *   GHND_QSCALE_DIV   IEEE division            (reference executed on CPU; oracle and goldens)
+ *   GHND_QSCALE_RECIP multiply by fl(1/255)    (reference executed by torch on a CUDA device)
+ * qparams (device, 16 bytes): [0] float scale, [1] int32 zero_point, [2] float min, [3] float max
+ * ------------------------------------------------------------------------------------------ */
+#define GHND_QSCALE_DIV 0
+#define GHND_QSCALE_RECIP 1
+size_t ghnd_quantize_u8_workspace_bytes(int64_t n);
+int ghnd_quantize_u8(const float* x, int64_t n, int num_bits, int scale_mode, uint8_t* q,
+                     void* qparams, void* workspace, size_t workspace_bytes, void* stream);
+/* out = scale * (float(q) - zero_point)   (tensor_util.py:21-22) */
+int ghnd_dequantize_u8(const uint8_t* q, int64_t n, const void* qparams, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * HND / GHND feature-mimicking loss, forward + backward fused.
+ * Replaces GeneralizedCustomLoss.forward with MSELoss(reduction='sum') terms
+ * (src/distillation/loss.py:25-34, src/myutils/pytorch/func_util.py:9-13) and its autograd
+ * backward:  L = sum_l factor_l * sum (t_l - s_l)^2 ;  dL/ds_l = 2 * factor_l * (s_l - t_l).
+ * loss_out (device): float[1 + n_levels] = { L, factor_0*SSE_0, ... }.
+ * `levels` is a HOST array. grad may be NULL (forward only).
+ * ------------------------------------------------------------------------------------------ */
+#define GHND_SSE_MAX_LEVELS 8
+typedef struct ghnd_sse_level {
+  const void* teacher;
+  const void* student;
+  void* grad; /* same shape as student, grad_fmt; may be NULL */
+  int64_t n;  /* elements, multiple of 8 */
+  float factor;
+  int relu_mask; /* 1: grad = student>0 ? 2f(s-t) : 0  (student is a post-ReLU output whose
+                    gradient is consumed directly as the pre-activation gradient) */
+} ghnd_sse_level_t;
+size_t ghnd_sse_workspace_bytes(void);
+int ghnd_sse_fwd_bwd(const ghnd_sse_level_t* levels, int n_levels, int in_fmt, int grad_fmt,
+                     float* loss_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Layout / dtype boundary kernels (module boundary: reference tensors are NCHW fp32).
+ * ------------------------------------------------------------------------------------------ */
+int ghnd_nchw_f32_to_nhwc16(const float* src, void* dst, int dst_fmt, int N, int C, int H, int W,
+                            void* stream);
+int ghnd_nhwc16_to_nchw_f32(const void* src, int src_fmt, float* dst, int N, int C, int H, int W,
+                            void* stream);
+
+/* Input transform of GeneralizedRCNNTransform.normalize + batch_images for images that need no
+ * resize (src/models/org/rcnn.py:73-80; torchvision transform.py normalize/batch_images):
+ * dst[n][h+3][w+3][0..3] = ((img-mean)/std, 0) as 4-channel pixels inside a zero frame of 3 px
+ * (the 7x7 stem's padding), dst dims [N][Hp+6][Wp+8][4], dst_fmt 16-bit.  One image per call.
+ * mean/std: host float[3]. */
+int ghnd_stem_pack_image(const float* img_chw, int H, int W, const float* mean, const float* std_,
+                         void* dst, int dst_fmt, int n_index, int Hp, int Wp, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Wide convolutions: implicit GEMM on tcgen05 tensor cores (TMA-fed, TMEM accumulators).
+ * Replaces nn.Conv2d (+FrozenBatchNorm2d +ReLU +residual) forward and its autograd dgrad:
+ *   student layer1 k=2 convs   src/models/mimic/resnet_layer.py:42-65
+ *   teacher layer1, layer2-4   torchvision Bottleneck via src/models/org/rcnn.py:388-396
+ * A plan binds geometry + device pointers (TMA descriptors embed them); run enqueues it.
+ *   FWD  : src = x  [N,H,W,C]   weights = [K][R][S][C]    dst = y  [N,Ho,Wo,K]
+ *   DGRAD: src = dy [N,Ho,Wo,K] weights = [C][R][S][K]    dst = dx [N,H,W,C]
+ *          (weights for DGRAD are the forward weights transposed, NOT flipped)
+ * Epilogue (all indexed like dst): v = acc + bias[ch] + residual; relu; v = mask>0 ? v : 0;
+ * accumulate: dst += v.
+ * ------------------------------------------------------------------------------------------ */
+#define GHND_CONV_FWD 0
+#define GHND_CONV_DGRAD 1
+typedef struct ghnd_conv_desc {
+  int kind;
+  int N, H, W, C; /* forward-input geometry */
+  int K;          /* forward-output channels */
+  int R, S, stride, pad;
+  const void* src;
+  int src_fmt;
+  const void* weights;
+  int w_fmt;
+  void* dst;
+  int dst_fmt;
+  const float* bias;
+  const void* residual;
+  int res_fmt;
+  int relu;
+  const void* mask;
+  int mask_fmt;
+  int accumulate;
+  double* stats; /* optional: [2*channels] sum / sum-of-squares of the stored (rounded) output */
+} ghnd_conv_desc_t;
+typedef struct ghnd_conv_plan ghnd_conv_plan_t;
+int ghnd_conv_plan_create(const ghnd_conv_desc_t* desc, ghnd_conv_plan_t** plan);
+int ghnd_conv_plan_run(const ghnd_conv_plan_t* plan, void* stream);
+void ghnd_conv_plan_destroy(ghnd_conv_plan_t* plan);
+/* number of kernel launches one run of the plan enqueues (for gpu_launches accounting) */
+int ghnd_conv_plan_launches(const ghnd_conv_plan_t* plan);
+
+/* Weight gradient of a wide conv on tcgen05 (MN-major operands straight from NHWC tensors):
+ *   dw[K][R][S][C] (fp32) = sum_{n,ho,wo} dy[n,ho,wo,k] * x[n, ho*stride+r-pad, wo*stride+s-pad, c]
+ * stride must be 1 (only the student's layer1 convs are trainable, all stride 1). */
+typedef struct ghnd_wgrad_desc {
+  int N, H, W, C, K, R, S, pad;
+  const void* x;
+  int x_fmt;
+  const void* dy;
+  int dy_fmt;
+  float* dw; /* [K][R][S][C] fp32, overwritten */
+} ghnd_wgrad_desc_t;
+typedef struct ghnd_wgrad_plan ghnd_wgrad_plan_t;
+int ghnd_wgrad_plan_create(const ghnd_wgrad_desc_t* desc, ghnd_wgrad_plan_t** plan);
+int ghnd_wgrad_plan_run(const ghnd_wgrad_plan_t* plan, void* stream);
+void ghnd_wgrad_plan_destroy(ghnd_wgrad_plan_t* plan);
+
+/* Weight repack: OIHW fp32 (nn.Conv2d.weight) * optional per-O scale -> [O][R][S][I] 16-bit
+ * (transpose=0, forward layout) or [I][R][S][O] (transpose=1, dgrad layout).  I is zero-padded to
+ * I_pad / O to O_pad in the packed tensor. */
+int ghnd_pack_weight(const float* w_oihw, const float* scale_o, int O, int I, int R, int S,
+                     int transpose, void* dst, int dst_fmt, void* stream);
+/* inverse for gradients: dw [O][R][S][I] fp32 -> OIHW fp32 (scaled by alpha) */
+int ghnd_unpack_wgrad(const float* dw_orsi, float* dst_oihw, int O, int I, int R, int S,
+                      float alpha, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Narrow (bottleneck-side) convolutions, k=2 stride 1: HBM-bound SIMT kernels.
+ *   enc7: Conv2d(64 -> bch, k2, p1)  resnet_layer.py:50     (narrow OUTPUT, planar fp32 NCHW z)
+ *   dec2: Conv2d(bch -> 64, k2, p0)  resnet_layer.py:55     (narrow INPUT,  planar fp32 NCHW z)
+ * wide side is NHWC 16-bit, narrow side is NCHW fp32 (it is the quantizer's tensor).
+ * ------------------------------------------------------------------------------------------ */
+/* y[n][k][ho][wo] = sum_{r,s,c} w[k][c][r][s] * x[n][ho+r-pad][wo+s-pad][c];  w: OIHW fp32 */
+size_t ghnd_conv_narrow_workspace_bytes(int C, int K, int R, int S);
+int ghnd_conv_narrow_out(const void* x, int x_fmt, const float* w, float* y, int N, int H, int W,
+                         int C, int K, int R, int S, int pad, void* workspace,
+                         size_t workspace_bytes, void* stream);
+/* flip=0: y[n][ho][wo][k] = sum_{r,s,c} w[k][c][r][s] * f(x[n][c][ho+r-pad][wo+s-pad]),
+ *   f(v) = pre_scale_shift ? (v*scale[c]+shift[c], then max(.,0) if pre_relu) : v
+ *   (decoder BN0+ReLU fused; zero padding is applied AFTER f).  w: OIHW [K][C][R][S].
+ * flip=1: data-gradient of a narrow-OUT conv (wide K ch -> narrow C ch, weight OIHW [C][K][R][S],
+ *   padding pad): x = dy of that conv, planar [N][C][H][W]; y = dx, NHWC [N][H-2pad+R-1][..][K]. */
+int ghnd_conv_narrow_in(const float* x, const float* pre_scale_shift, int pre_relu, const float* w,
+                        int flip, void* y, int y_fmt, int N, int H, int W, int C, int K, int R,
+                        int S, int pad, void* workspace, size_t workspace_bytes, void* stream);
+/* dgrad of a narrow-IN conv: dx[n][c][h][w] = sum_{r,s,k} w[k][c][r][s]*dy[n][h+pad-r][w+pad-s][k]
+ * (dy NHWC 16-bit, dx NCHW fp32) -- same arithmetic as narrow_out with flipped taps. */
+int ghnd_conv_narrow_out_dgrad(const void* dy, int dy_fmt, const float* w, float* dx, int N, int H,
+                               int W, int C, int K, int R, int S, int pad, void* workspace,
+                               size_t workspace_bytes, void* stream);
+/* weight gradient between a planar fp32 narrow tensor a[N][Ca][Ha][Wa] and an NHWC 16-bit wide
+ * tensor b[N][Hb][Wb][Cb]:  out[ca][cb][r][s] = sum a[n][ca][i][j] * b[n][i+r-pad][j+s-pad][cb]
+ * (a_is_output=1: a = dy of narrow-out conv, b = its input  -> dw[k=ca][c=cb][r][s])
+ * (a_is_output=0: a = x of narrow-in conv, b = its dy      -> dw[k=cb][c=ca][r][s], taps mirrored)
+ * dw is written in OIHW fp32.  pre_* as in narrow_in (applied to a when a_is_output=0). */
+int ghnd_wgrad_narrow(const float* a, const float* pre_scale_shift, int pre_relu, const void* b,
+                      int b_fmt, float* dw_oihw, int a_is_output, int N, int Ha, int Wa, int Ca,
+                      int Hb, int Wb, int Cb, int R, int S, int pad, void* workspace,
+                      size_t workspace_bytes, void* stream);
+size_t ghnd_wgrad_narrow_workspace_bytes(int Ca, int Cb, int R, int S);
+
+/* ------------------------------------------------------------------------------------------
+ * Stem: conv1 7x7 s2 p3 (3->64) + FrozenBatchNorm2d + ReLU, then MaxPool 3x3 s2 p1
+ * (src/models/custom/resnet.py:26-30,96-99).  Input = ghnd_stem_pack_image output.
+ * Implicit GEMM on tcgen05: K = 7 rows x 32 (7 px x 4 ch + 4 zero) = 224.
+ *   weights: [64][7][32] 16-bit from ghnd_stem_pack_weight (FrozenBN scale folded), bias fp32[64]
+ * ------------------------------------------------------------------------------------------ */
+int ghnd_stem_pack_weight(const float* w_oihw /*[64][3][7][7]*/, const float* scale_o, void* dst,
+                          int dst_fmt, void* stream);
+typedef struct ghnd_stem_plan ghnd_stem_plan_t;
+/* y = relu(conv(x)+bias) : [N][Hp/2][Wp/2][64] */
+int ghnd_stem_conv_plan_create(const void* x_packed, int x_fmt, const void* w_packed, int w_fmt,
+                               const float* bias, void* y, int y_fmt, int N, int Hp, int Wp,
+                               ghnd_stem_plan_t** plan);
+int ghnd_stem_conv_plan_run(const ghnd_stem_plan_t* plan, void* stream);
+void ghnd_stem_plan_destroy(ghnd_stem_plan_t* plan);
+/* maxpool 3x3 s2 p1 on NHWC 16-bit: y[N][Ho][Wo][C], Ho=(H+1)/2; argmax (nullable) receives the
+ * window position 0..8 of the first maximum, one byte per output element. */
+int ghnd_maxpool3x3s2(const void* x, void* y, void* argmax, int fmt, int N, int H, int W, int C,
+                      void* stream);
+/* backward of relu+maxpool: dx[n][h][w][c] = sum of dy over the pool windows whose argmax is
+ * (h,w), zero where x (the post-ReLU conv output) is not > 0. */
+int ghnd_maxpool3x3s2_bwd(const void* x, int x_fmt, const void* argmax, const void* dy, int dy_fmt,
+                          void* dx, int dx_fmt, int N, int H, int W, int C, void* stream);
+/* dW of conv1: dw[k][c][r][s] = scale[k] * sum g[n][ho][wo][k] * xpacked[n][2ho+r][2wo+s][c]
+ * (fp32 OIHW [64][3][7][7]); SIMT register-tiled, split over pixels, fp32 atomics into workspace. */
+size_t ghnd_stem_wgrad_workspace_bytes(void);
+int ghnd_stem_wgrad(const void* x_packed, int x_fmt, const void* g, int g_fmt,
+                    const float* scale_o, float* dw_oihw, int N, int Hp, int Wp, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Training-mode BatchNorm2d around the student's layer1 convs (nn.BatchNorm2d forward/backward,
+ * resnet_layer.py:43-64; batch statistics, biased var for normalisation, unbiased for running).
+ * x is NHWC 16-bit with npix = N*H*W pixels, or planar fp32 (planar=1: [N][C][HW]).
+ * ------------------------------------------------------------------------------------------ */
+/* sums[2C] (double) = {sum x, sum x^2}; zeroed by the call itself before accumulation. */
+int ghnd_bn_stats(const void* x, int fmt, int planar, int N, int64_t hw, int C, double* sums,
+                  void* stream);
+/* From sums: scale_shift[2C] = {gamma*invstd, beta-mean*gamma*invstd}, mean_invstd[2C];
+ * running stats updated in place (momentum), num_batches_tracked += 1 (int64, nullable). */
+int ghnd_bn_finalize(const double* sums, int64_t count, int C, const float* gamma,
+                     const float* beta, float eps, float momentum, float* running_mean,
+                     float* running_var, int64_t* num_batches_tracked, float* scale_shift,
+                     float* mean_invstd, void* stream);
+/* eval mode: scale_shift from running stats */
+int ghnd_bn_eval_params(int C, const float* gamma, const float* beta, const float* running_mean,
+                        const float* running_var, float eps, float* scale_shift, void* stream);
+/* y = x*scale+shift (optionally relu); NHWC 16-bit in/out */
+int ghnd_bn_apply(const void* x, int x_fmt, void* y, int y_fmt, int64_t npix, int C,
+                  const float* scale_shift, int relu, void* stream);
+/* backward, pass 1: sums[2C] = { sum g', sum g'*xhat } with g' = dy * (relu ? (x*scale+shift>0):1) */
+int ghnd_bn_bwd_reduce(const void* dy, int dy_fmt, const void* x, int x_fmt, int planar, int N,
+                       int64_t hw, int C, const float* scale_shift, const float* mean_invstd,
+                       int relu, double* sums, void* stream);
+/* backward, pass 2: dx = gamma*invstd*(g' - sum_g/M - xhat*sum_gx/M); also dgamma=sum_gx,
+ * dbeta=sum_g written (fp32[C] each, nullable). */
+int ghnd_bn_bwd_apply(const void* dy, int dy_fmt, const void* x, int x_fmt, void* dx, int dx_fmt,
+                      int planar, int N, int64_t hw, int C, const float* gamma,
+                      const float* scale_shift, const float* mean_invstd, int relu,
+                      const double* sums, float* dgamma, float* dbeta, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused multi-tensor Adam over one flat fp32 parameter/gradient buffer
+ * (torch.optim.Adam step, src/mimic_runner.py:52-54; lr schedule stays on the host).
+ * grad_scale multiplies the gradient first (1/world_size after the all-reduce SUM).
+ * step is the 1-based step count used for bias correction.
+ * ------------------------------------------------------------------------------------------ */
+int ghnd_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                   float lr, float beta1, float beta2, float eps, float weight_decay,
+                   float grad_scale, int step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GHND_B200_H */
