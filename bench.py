@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py -- GHND distillation throughput on B200 (BASELINE.json configs[1]).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on host cores
+
+Workload (N=1): Faster R-CNN ResNet-50-FPN b3ch GHND distillation step -- teacher forward, student
+forward, 4-level SSE loss, student backward, gradient all-reduce (N>1), fused Adam -- on 4 synthetic
+3x800x1333 images per GPU (config/ghnd/faster_rcnn-backbone_resnet50-b3ch.yaml: batch_size 4),
+random-init weights.  One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+IMG_H, IMG_W = 800, 1333
+PER_GPU_BATCH = 4
+METRIC = "ghnd_distill_images_per_sec"
+WORKLOAD = ("Faster R-CNN ResNet-50-FPN b3ch GHND distillation step (teacher fwd + student fwd/bwd + "
+            "4-level SSE loss + Adam), %d synthetic 3x800x1333 images per GPU, random init" % PER_GPU_BATCH)
+
+
+def model_config(student, bch=3):
+    cfg = {
+        "name": "faster_rcnn",
+        "backbone": {"name": "custom_resnet50" if student else "resnet50",
+                     "params": {"pretrained": False, "freeze_layers": not student}},
+        "params": {"num_classes": 91, "pretrained": False},
+        "ckpt": "./resource/ckpt/none.pt",
+    }
+    if student:
+        cfg["backbone"]["params"]["layer1"] = {"name": "Bottleneck4LargeResNet", "bottleneck_channel": bch}
+        cfg["frozen_modules"] = ["backbone.body.layer2", "backbone.body.layer3", "backbone.body.layer4",
+                                 "backbone.fpn", "rpn", "roi_heads"]
+    return cfg
+
+
+def criterion_config():
+    terms = {lv: {"ts_modules": ["backbone.body." + lv, "backbone.body." + lv],
+                  "criterion": {"type": "MSELoss", "params": {"reduction": "sum"}}, "factor": 1.0}
+             for lv in ("layer1", "layer2", "layer3", "layer4")}
+    return {"type": "general", "params": {"org_loss_factor": 0.0}, "terms": terms}
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 4), ("hw_thermal_slowdown", 5), ("sw_thermal_slowdown", 6),
+                              ("sw_power_cap", 7)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            d = json.load(f)
+        return {"bf16_tflops_sustained": d.get("bf16_tflops_sustained", 1400.0),
+                "hbm_gbs": d.get("hbm_gbs", 6650.0), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference algorithm on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_step_fn(sample_batch):
+    import torch
+    from oracle import ghnd_oracle as O
+    from oracle import weights
+    torch.set_num_threads(os.cpu_count() or 1)
+    t_sd, s_sd = weights.teacher_student(3, seed=0)
+    g = torch.Generator().manual_seed(0)
+    images = [torch.rand(3, IMG_H, IMG_W, generator=g) for _ in range(sample_batch)]
+
+    def step():
+        res = O.distill_step(t_sd, s_sd, images)
+        return float(res["loss"])
+    return step
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample_batch = 1
+    step = cpu_step_fn(sample_batch)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = sample_batch * args.steps / dt
+    cores = os.cpu_count() or 1
+    sample = ("each step = oracle port (torch CPU fp32, oracle/ghnd_oracle.py distill_step) of the same "
+              "GHND step on %d image of 3x800x1333" % sample_batch)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": WORKLOAD, "sample_batch": sample_batch},
+            "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# CUDA arm
+# ------------------------------------------------------------------------------------------------
+def conv_flops_per_step(plan):
+    """Algorithmic FLOPs (2*MACs) of every conv_tc_kernel launch in one step, from the plans."""
+    total = 0.0
+
+    def conv(N, Ho, Wo, K, C, R, S):
+        return 2.0 * N * Ho * Wo * K * C * R * S
+
+    def block(b, bwd):
+        f = conv(b.N, b.H, b.W, b.planes, b.cin, 1, 1) + conv(b.N, b.Ho, b.Wo, b.planes, b.planes, 3, 3) + \
+            conv(b.N, b.Ho, b.Wo, b.cout, b.planes, 1, 1)
+        if b.cd is not None:
+            f += conv(b.N, b.Ho, b.Wo, b.cout, b.cin, 1, 1)
+        return f * (2 if bwd else 1)
+
+    for r in plan.t_layers.values():
+        total += sum(block(b, False) for b in r.blocks)
+    for r in plan.s_layers.values():
+        total += sum(block(b, True) for b in r.blocks)
+    l1 = plan.s_l1
+    for u in (l1.e0, l1.e1, l1.e2, l1.d4, l1.d7, l1.d9):
+        total += 2 * conv(u.N, u.Ho, u.Wo, u.K, u.C, 2, 2)  # forward + dgrad
+    stem = 2.0 * plan.N * (plan.Hp // 2) * (plan.Wp // 2) * 64 * 147
+    total += 2 * stem  # teacher + student stem forward
+    return total
+
+
+def time_conv_family(plan):
+    """CUDA-event time of all conv_tc_kernel launches of one (eager, un-graphed) step."""
+    import torch
+    from hnd_ghnd_object_detectors_b200 import ops
+    spans = []
+    orig_conv, orig_stem = ops.ConvPlan.run, ops.StemPlan.run
+
+    def wrap(fn):
+        def run(self, stream=None):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn(self, stream)
+            b.record()
+            spans.append((a, b))
+        return run
+    ops.ConvPlan.run, ops.StemPlan.run = wrap(orig_conv), wrap(orig_stem)
+    try:
+        plan.forward_backward()
+        torch.cuda.synchronize()
+    finally:
+        ops.ConvPlan.run, ops.StemPlan.run = orig_conv, orig_stem
+    return sum(a.elapsed_time(b) for a, b in spans) * 1e-3, len(spans)
+
+
+def run_cuda(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the GHND path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import __graft_entry__
+    __graft_entry__.build()
+    from hnd_ghnd_object_detectors_b200 import models, module_util, ops
+    from hnd_ghnd_object_detectors_b200.optim import FusedAdam
+    from hnd_ghnd_object_detectors_b200.tool import DistillationBox
+
+    torch.manual_seed(0)
+    teacher = models.get_model(model_config(False), dev)
+    student = models.get_model(model_config(True), dev)
+    student.load_state_dict(teacher.state_dict(), strict=False)  # layer2-4 identical (pretrained flow)
+    module_util.freeze_module_params(teacher)
+    for path in model_config(True)["frozen_modules"]:
+        module_util.freeze_module_params(module_util.get_module(student, path))
+    teacher.eval()
+    student.train()
+    teacher.distill_backbone_only = student.distill_backbone_only = True
+    box = DistillationBox(teacher, student, criterion_config())
+    opt = FusedAdam([p for p in student.parameters() if p.requires_grad], lr=1e-3,
+                    grad_scale=1.0 / world)
+
+    g = torch.Generator().manual_seed(1000 + rank)
+    host_images = [torch.rand(3, IMG_H, IMG_W, generator=g).pin_memory() for _ in range(PER_GPU_BATCH)]
+    dev_images = [im.to(dev) for im in host_images]
+    targets = [{"boxes": torch.tensor([[10., 10., 100., 100.]], device=dev),
+                "labels": torch.tensor([1], device=dev)} for _ in range(PER_GPU_BATCH)]
+
+    # first call builds + captures the plan
+    loss = box(dev_images, targets)
+    opt.attach(box.flat)
+    plan = list(box._plans.values())[0]
+    torch.cuda.synchronize()
+
+    def device_step():
+        plan.step()  # images already packed in HBM; graph replay of fwd + loss + bwd
+        if world > 1:
+            dist.all_reduce(box.flat.grad)
+        opt.step()
+
+    def e2e_step():
+        imgs = [h.to(dev, non_blocking=True) for h in host_images]
+        l = box(imgs, targets)
+        opt.zero_grad(set_to_none=True)
+        l.backward()
+        if world > 1:
+            dist.all_reduce(box.flat.grad)
+        opt.step()
+        return l.item()  # device -> host read of the step's loss
+
+    def timed(fn, steps, warmup, sampler=None):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        if sampler:
+            sampler.start()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ops.launches()
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        clocks = sampler.stop() if sampler else None
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), ops.launches() - l0, clocks
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms, launches, clocks = timed(device_step, args.steps, args.warmup, sampler)
+    e2e_steps = max(3, min(args.steps, 10))
+    ms_e2e, _, _ = timed(e2e_step, e2e_steps, max(3, min(args.warmup, 3)))
+    images_per_step = PER_GPU_BATCH * world
+    value = images_per_step * args.steps / (ms * 1e-3)
+    e2e_value = images_per_step * e2e_steps / (ms_e2e * 1e-3)
+
+    roof = cpu = None
+    if rank == 0:
+        peaks = measured_peaks()
+        conv_s, n_conv = time_conv_family(plan)
+        flops = conv_flops_per_step(plan)
+        achieved = flops / conv_s / 1e12
+        roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv fwd/dgrad, %d launches/step)" % n_conv,
+                "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None,
+                "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
+                "conv_share_of_step": conv_s / (ms * 1e-3 / args.steps)}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        step = cpu_step_fn(1)
+        step()
+        t0 = time.perf_counter()
+        n = 2
+        for _ in range(n):
+            step()
+        dt = (time.perf_counter() - t0) / n
+        cpu = {"value": 1.0 / dt, "unit": "images/s", "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": "oracle port (torch CPU fp32) of the same GHND step, 1 image of 3x800x1333 per "
+                         "step, 1 warm-up + %d timed steps" % n}
+    if rank == 0:
+        h2d = sum(h.numel() * 4 for h in host_images)
+        line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None,
+                "dtype": "f16 forward / bf16 gradients, fp32 accumulate (tcgen05 kind::f16)",
+                "data": "synthetic",
+                "config": {"workload": WORKLOAD, "global_batch": images_per_step, "per_gpu_batch": PER_GPU_BATCH,
+                           "parallelism": "dp%d" % world,
+                           "l2": "per-step working set (several GB of activations) exceeds the 126 MB L2",
+                           "cuda_graph": True},
+                "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": 4, "steps": e2e_steps,
+                        "api": "DistillationBox(images from pinned host memory) + backward + FusedAdam + loss.item()"},
+                "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
+                "loss": float(loss.item())}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -413,6 +413,9 @@ int ghnd_conv_plan_create(const ghnd_conv_desc_t* d, ghnd_conv_plan_t** out) {
   GHND_CHECK_ARG(d->pad >= 0 && d->pad < 4, "conv: pad %d unsupported", d->pad);
   GHND_CHECK_ARG(d->src && d->weights && d->dst, "conv: null tensor pointer");
   GHND_CHECK_ARG(fmt_ok(d->src_fmt) && fmt_ok(d->w_fmt) && fmt_ok(d->dst_fmt), "conv: bad format");
+  GHND_CHECK_ARG(d->src_fmt == d->w_fmt,
+                 "conv: src and weights must share one 16-bit format (tcgen05 kind::f16 rejects "
+                 "mixed f16 x bf16 operands on sm_100a)");
   GHND_CHECK_ARG(!d->residual || fmt_ok(d->res_fmt), "conv: bad residual format");
   GHND_CHECK_ARG(!d->mask || fmt_ok(d->mask_fmt), "conv: bad mask format");
   GHND_CHECK_ARG(d->stats == nullptr, "conv: fused statistics not available in this build");
@@ -604,6 +607,7 @@ int ghnd_stem_conv_plan_create(const void* x_packed, int x_fmt, const void* w_pa
   GHND_CHECK_ARG(N > 0 && Hp > 0 && Wp > 0 && Hp % 2 == 0 && Wp % 8 == 0,
                  "stem conv: padded size must be even x multiple of 8 (Hp=%d Wp=%d)", Hp, Wp);
   GHND_CHECK_ARG(fmt_ok(x_fmt) && fmt_ok(w_fmt) && fmt_ok(y_fmt), "stem conv: bad format");
+  GHND_CHECK_ARG(x_fmt == w_fmt, "stem conv: image and weights must share one 16-bit format");
   const int Ho = Hp / 2, Wo = Wp / 2;
   const int rows = Hp + 6, RP = (Wp + 8) * 4;  // packed image rows / row pitch in elements
   ghnd_stem_plan* plan = new ghnd_stem_plan();

@@ -351,14 +351,15 @@ __global__ void bn_eval_params_kernel(int C, const float* __restrict__ gamma,
 
 __global__ void __launch_bounds__(256)
     bn_apply_kernel(const uint4* __restrict__ x, int x_fmt, uint4* __restrict__ y, int y_fmt,
-                    int64_t nvec, int C8, const float* __restrict__ scale_shift, int relu) {
+                    uint4* __restrict__ y2, int y2_fmt, int64_t nvec, int C8,
+                    const float* __restrict__ scale_shift, int relu) {
   const int C = C8 * 8;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
        i += (int64_t)gridDim.x * blockDim.x) {
     const int cg = (int)(i % C8);
     const uint4 v = ld_stream(x + i);
     const uint32_t u[4] = {v.x, v.y, v.z, v.w};
-    uint32_t o[4];
+    uint32_t o[4], o2[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const float2 f = unpack2(u[e], x_fmt);
@@ -370,8 +371,10 @@ __global__ void __launch_bounds__(256)
         b = fmaxf(b, 0.f);
       }
       o[e] = pack2(a, b, y_fmt);
+      o2[e] = pack2(a, b, y2_fmt);
     }
     y[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    if (y2 != nullptr) y2[i] = make_uint4(o2[0], o2[1], o2[2], o2[3]);
   }
 }
 
@@ -440,6 +443,23 @@ __global__ void bn_param_grads_kernel(const double* __restrict__ sums, int C,
   if (dgamma) dgamma[c] = (float)sums[C + c];
 }
 
+__global__ void __launch_bounds__(256)
+    convert16_kernel(const uint4* __restrict__ x, int x_fmt, uint4* __restrict__ y, int y_fmt,
+                     int64_t nvec) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const uint4 v = ld_stream(x + i);
+    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = unpack2(u[e], x_fmt);
+      o[e] = pack2(f.x, f.y, y_fmt);
+    }
+    y[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // weight repack / gradient unpack
 // ------------------------------------------------------------------------------------------------
@@ -495,15 +515,15 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dw, float* __restr
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
     adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                float* __restrict__ v, int64_t n, float beta1, float beta2, float eps, float wd,
-                float gscale, float step_size, float inv_sqrt_bc2) {
+                float* __restrict__ v, int64_t n, float beta1, float beta2, float omb1, float omb2,
+                float eps, float wd, float gscale, float step_size, float inv_sqrt_bc2) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
     float grad = g[i] * gscale;
     const float pv = p[i];
     if (wd != 0.f) grad = fmaf(wd, pv, grad);
-    const float mi = fmaf(beta1, m[i], (1.f - beta1) * grad);
-    const float vi = fmaf(beta2, v[i], (1.f - beta2) * grad * grad);
+    const float mi = fmaf(beta1, m[i], omb1 * grad);
+    const float vi = fmaf(beta2, v[i], omb2 * grad * grad);
     m[i] = mi;
     v[i] = vi;
     const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
@@ -631,15 +651,24 @@ int ghnd_bn_eval_params(int C, const float* gamma, const float* beta, const floa
   return GHND_OK;
 }
 
-int ghnd_bn_apply(const void* x, int x_fmt, void* y, int y_fmt, int64_t npix, int C,
-                  const float* scale_shift, int relu, void* stream) {
+int ghnd_bn_apply(const void* x, int x_fmt, void* y, int y_fmt, void* y2, int y2_fmt, int64_t npix,
+                  int C, const float* scale_shift, int relu, void* stream) {
   GHND_CHECK_ARG(x && y && scale_shift && fmt16(x_fmt) && fmt16(y_fmt) && npix > 0 && C > 0 &&
-                     C % 8 == 0,
+                     C % 8 == 0 && (y2 == nullptr || fmt16(y2_fmt)),
                  "bn_apply: bad argument");
   const int64_t nvec = npix * (C / 8);
   bn_apply_kernel<<<grid_for(nvec, 256 * 2), 256, 0, (cudaStream_t)stream>>>(
-      (const uint4*)x, x_fmt, (uint4*)y, y_fmt, nvec, C / 8, scale_shift, relu);
+      (const uint4*)x, x_fmt, (uint4*)y, y_fmt, (uint4*)y2, y2_fmt, nvec, C / 8, scale_shift, relu);
   GHND_LAUNCH_CHECK("bn_apply_kernel");
+  return GHND_OK;
+}
+
+int ghnd_convert16(const void* x, int x_fmt, void* y, int y_fmt, int64_t n, void* stream) {
+  GHND_CHECK_ARG(x && y && fmt16(x_fmt) && fmt16(y_fmt) && n > 0 && n % 8 == 0,
+                 "convert16: bad argument (n must be a positive multiple of 8)");
+  convert16_kernel<<<grid_for(n / 8, 256 * 2), 256, 0, (cudaStream_t)stream>>>(
+      (const uint4*)x, x_fmt, (uint4*)y, y_fmt, n / 8);
+  GHND_LAUNCH_CHECK("convert16_kernel");
   return GHND_OK;
 }
 
@@ -718,16 +747,17 @@ int ghnd_unpack_wgrad(const float* dw_orsi, float* dst_oihw, int O, int I, int R
 }
 
 int ghnd_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
-                   float lr, float beta1, float beta2, float eps, float weight_decay,
-                   float grad_scale, int step, void* stream) {
+                   double lr, double beta1, double beta2, double eps, double weight_decay,
+                   double grad_scale, int step, void* stream) {
   GHND_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && n > 0 && step >= 1,
                  "adam_step: bad argument");
-  const double bc1 = 1.0 - pow((double)beta1, (double)step);
-  const double bc2 = 1.0 - pow((double)beta2, (double)step);
-  const float step_size = (float)((double)lr / bc1);
+  const double bc1 = 1.0 - pow(beta1, (double)step);
+  const double bc2 = 1.0 - pow(beta2, (double)step);
+  const float step_size = (float)(lr / bc1);
   const float inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
   adam_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
-      param, grad, exp_avg, exp_avg_sq, n, beta1, beta2, eps, weight_decay, grad_scale, step_size,
+      param, grad, exp_avg, exp_avg_sq, n, (float)beta1, (float)beta2, (float)(1.0 - beta1),
+      (float)(1.0 - beta2), (float)eps, (float)weight_decay, (float)grad_scale, step_size,
       inv_sqrt_bc2);
   GHND_LAUNCH_CHECK("adam_kernel");
   return GHND_OK;

@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(kWgThreads, 1)
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
         uint8_t* sb = sa + a_bytes;
-        mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(a_bytes + p.n_taps * b_tap_bytes));
+        mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)p.stage_bytes);
         // rows operand: unshifted when it is dy, shifted per tap when it is x
         if (p.rows_is_dy) {
           for (int b = 0; b < p.row_boxes; ++b)
@@ -229,6 +229,9 @@ int ghnd_wgrad_plan_create(const ghnd_wgrad_desc_t* d, ghnd_wgrad_plan_t** out) 
   GHND_CHECK_ARG((d->x_fmt == GHND_F16 || d->x_fmt == GHND_BF16) &&
                      (d->dy_fmt == GHND_F16 || d->dy_fmt == GHND_BF16),
                  "wgrad: bad format");
+  GHND_CHECK_ARG(d->x_fmt == d->dy_fmt,
+                 "wgrad: x and dy must share one 16-bit format (tcgen05 kind::f16 rejects mixed "
+                 "f16 x bf16 operands on sm_100a)");
   const int Ho = d->H + 2 * d->pad - d->R + 1;
   const int Wo = d->W + 2 * d->pad - d->S + 1;
   GHND_CHECK_ARG(Ho > 0 && Wo > 0, "wgrad: empty output");

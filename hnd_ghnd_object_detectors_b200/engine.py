@@ -1,0 +1,667 @@
+"""Fixed-shape execution plans of the GHND hot path on one B200.
+
+A plan owns the HBM-resident NHWC 16-bit activation / gradient buffers (allocated once through
+torch, the allocator is plumbing) and the C-ABI launch plans bound to them, so that one
+distillation step is a fixed sequence of hand-written kernels that can be captured in a CUDA graph:
+
+  teacher : stem -> layer1..4 (frozen Bottlenecks, FrozenBN folded)            forward
+  student : stem -> layer1 (encoder -> bch bottleneck -> decoder, batch-stat BN) -> layer2..4
+  loss    : fused multi-level SSE forward + dL/ds
+  backward: layer4..2 dgrad -> layer1 BN-bwd / dgrad / wgrad -> pool+ReLU bwd -> conv1 wgrad
+
+Numeric types: forward tensors and weights fp16, gradient tensors bf16, all accumulation fp32
+(BN statistics fp64).  tcgen05 kind::f16 needs both MMA operands in ONE 16-bit format, so the
+student's layer1 activations are additionally kept as bf16 copies for the weight-gradient GEMMs.
+
+Reference mapping: src/distillation/tool.py:40-61 (step), src/models/org/rcnn.py:102-110
+(distill_backbone_only short-circuit), src/models/mimic/resnet_layer.py:40-70 (student layer1),
+torchvision Bottleneck / FrozenBatchNorm2d (frozen layers), src/mimic_runner.py:48-59 (loop).
+"""
+import torch
+
+from . import _lib, ops
+from ._lib import CONV_DGRAD, CONV_FWD
+
+LEVELS = ("layer1", "layer2", "layer3", "layer4")
+PLANES = {"layer1": 64, "layer2": 128, "layer3": 256, "layer4": 512}
+IMAGE_MEAN = (0.485, 0.456, 0.406)
+IMAGE_STD = (0.229, 0.224, 0.225)
+
+
+def _empty(shape, dtype, device):
+    return torch.empty(shape, dtype=dtype, device=device)
+
+
+def fold_frozen_bn(bn):
+    """FrozenBatchNorm2d -> per-channel (scale, shift) fp32 (tiny host-side tensor math)."""
+    eps = float(getattr(bn, "eps", 1e-5))
+    w, b = bn.weight.detach().float(), bn.bias.detach().float()
+    rm, rv = bn.running_mean.detach().float(), bn.running_var.detach().float()
+    scale = w * torch.rsqrt(rv + eps)
+    return scale.contiguous(), (b - rm * scale).contiguous()
+
+
+class FrozenConv(object):
+    """Packed weights of one frozen conv + FrozenBN: forward [K][R][S][C] (act dtype) and, when a
+    data gradient is needed, transposed [C][R][S][K] (grad dtype); bias = BN shift."""
+
+    def __init__(self, conv, bn, act_dtype, grad_dtype, need_dgrad):
+        scale, shift = fold_frozen_bn(bn)
+        self.K, self.C, self.R, self.S = conv.weight.shape
+        self.stride = conv.stride[0]
+        self.pad = conv.padding[0]
+        self.w = ops.pack_weight(conv.weight, scale, False, act_dtype)
+        self.wt = ops.pack_weight(conv.weight, scale, True, grad_dtype) if need_dgrad else None
+        self.bias = shift
+
+
+class BottleneckRunner(object):
+    """One torchvision Bottleneck with FrozenBN: forward, and dgrad when need_bwd."""
+
+    def __init__(self, block, x, N, H, W, act_dtype, grad_dtype, need_bwd):
+        dev = x.device
+        self.x, self.N, self.H, self.W = x, N, H, W
+        self.need_bwd = need_bwd
+        self.c1 = FrozenConv(block.conv1, block.bn1, act_dtype, grad_dtype, need_bwd)
+        self.c2 = FrozenConv(block.conv2, block.bn2, act_dtype, grad_dtype, need_bwd)
+        self.c3 = FrozenConv(block.conv3, block.bn3, act_dtype, grad_dtype, need_bwd)
+        self.cd = None
+        if block.downsample is not None:
+            self.cd = FrozenConv(block.downsample[0], block.downsample[1], act_dtype, grad_dtype, need_bwd)
+        cin, p = self.c1.C, self.c1.K
+        s = self.c2.stride
+        self.stride = s
+        self.Ho, self.Wo = (H + 2 - 3) // s + 1, (W + 2 - 3) // s + 1
+        self.cin, self.planes, self.cout = cin, p, self.c3.K
+        self.a1 = _empty((N, H, W, p), act_dtype, dev)
+        self.a2 = _empty((N, self.Ho, self.Wo, p), act_dtype, dev)
+        self.out = _empty((N, self.Ho, self.Wo, self.cout), act_dtype, dev)
+        self.idn = _empty((N, self.Ho, self.Wo, self.cout), act_dtype, dev) if self.cd else None
+        self.fwd = [
+            ops.ConvPlan(CONV_FWD, N, H, W, cin, p, 1, 1, 1, 0, x, self.c1.w, self.a1, bias=self.c1.bias,
+                         relu=True),
+            ops.ConvPlan(CONV_FWD, N, H, W, p, p, 3, 3, s, 1, self.a1, self.c2.w, self.a2,
+                         bias=self.c2.bias, relu=True),
+        ]
+        if self.cd:
+            self.fwd.append(ops.ConvPlan(CONV_FWD, N, H, W, cin, self.cout, 1, 1, s, 0, x, self.cd.w,
+                                         self.idn, bias=self.cd.bias))
+        self.fwd.append(ops.ConvPlan(CONV_FWD, N, self.Ho, self.Wo, p, self.cout, 1, 1, 1, 0, self.a2,
+                                     self.c3.w, self.out, bias=self.c3.bias,
+                                     residual=self.idn if self.cd else x, relu=True))
+        self.bwd = []
+
+    def plan_backward(self, g_out, g_x, loss_grad_x, grad_dtype):
+        """g_out: gradient w.r.t. this block's pre-ReLU output (already masked).  Writes g_x =
+        mask(x>0) * (dL/dx [+ loss_grad_x]) i.e. the same convention for the producer of x."""
+        dev = g_out.device
+        N, H, W, Ho, Wo = self.N, self.H, self.W, self.Ho, self.Wo
+        p, cin, cout, s = self.planes, self.cin, self.cout, self.stride
+        self.g_a2 = _empty((N, Ho, Wo, p), grad_dtype, dev)
+        self.g_a1 = _empty((N, H, W, p), grad_dtype, dev)
+        self.bwd = [
+            ops.ConvPlan(CONV_DGRAD, N, Ho, Wo, p, cout, 1, 1, 1, 0, g_out, self.c3.wt, self.g_a2,
+                         mask=self.a2),
+            ops.ConvPlan(CONV_DGRAD, N, H, W, p, p, 3, 3, s, 1, self.g_a2, self.c2.wt, self.g_a1,
+                         mask=self.a1),
+        ]
+        if self.cd is None:
+            assert loss_grad_x is None
+            self.bwd.append(ops.ConvPlan(CONV_DGRAD, N, H, W, cin, p, 1, 1, 1, 0, self.g_a1, self.c1.wt,
+                                         g_x, residual=g_out, mask=self.x))
+        else:
+            self.bwd.append(ops.ConvPlan(CONV_DGRAD, N, H, W, cin, p, 1, 1, 1, 0, self.g_a1, self.c1.wt,
+                                         g_x, residual=loss_grad_x, mask=self.x))
+            self.bwd.append(ops.ConvPlan(CONV_DGRAD, N, H, W, cin, cout, 1, 1, s, 0, g_out, self.cd.wt,
+                                         g_x, mask=self.x, accumulate=True))
+
+    def forward(self):
+        for p in self.fwd:
+            p.run()
+
+    def backward(self):
+        for p in self.bwd:
+            p.run()
+
+
+class FrozenLayerRunner(object):
+    """nn.Sequential of Bottlenecks (teacher layer1..4, student layer2..4)."""
+
+    def __init__(self, layer, x, N, H, W, act_dtype, grad_dtype, need_bwd):
+        self.blocks = []
+        for block in layer:
+            r = BottleneckRunner(block, x, N, H, W, act_dtype, grad_dtype, need_bwd)
+            self.blocks.append(r)
+            x, H, W = r.out, r.Ho, r.Wo
+        self.out, self.Ho, self.Wo = x, H, W
+
+    def forward(self):
+        for b in self.blocks:
+            b.forward()
+
+    def plan_backward(self, g_out, g_x, loss_grad_x, grad_dtype):
+        """g_out: masked gradient at this layer's output; g_x: buffer for the layer input's."""
+        dev = g_out.device
+        g = g_out
+        for i in range(len(self.blocks) - 1, -1, -1):
+            b = self.blocks[i]
+            if i == 0:
+                b.plan_backward(g, g_x, loss_grad_x, grad_dtype)
+            else:
+                gx = _empty((b.N, b.H, b.W, b.cin), grad_dtype, dev)
+                b.plan_backward(g, gx, None, grad_dtype)
+                g = gx
+
+    def backward(self):
+        for b in reversed(self.blocks):
+            b.backward()
+
+
+class StemRunner(object):
+    """conv1 7x7 s2 + FrozenBN + ReLU (tcgen05 implicit GEMM) -> MaxPool 3x3 s2."""
+
+    def __init__(self, body, packed, N, Hp, Wp, act_dtype, grad_dtype, trainable):
+        dev = packed.device
+        self.body, self.packed = body, packed
+        self.N, self.Hp, self.Wp = N, Hp, Wp
+        self.trainable = trainable
+        self.scale, self.shift = fold_frozen_bn(body.bn1)
+        self.w = _empty((64, 7, 32), act_dtype, dev)
+        self.conv = _empty((N, Hp // 2, Wp // 2, 64), act_dtype, dev)
+        self.Ho, self.Wo = (Hp // 2 + 1) // 2, (Wp // 2 + 1) // 2
+        self.out = _empty((N, self.Ho, self.Wo, 64), act_dtype, dev)
+        self.argmax = _empty((N, self.Ho, self.Wo, 64), torch.uint8, dev) if trainable else None
+        self.plan = ops.StemPlan(packed, self.w, self.shift, self.conv, N, Hp, Wp)
+        self.refresh_weights()
+        if trainable:
+            self.g_conv = _empty((N, Hp // 2, Wp // 2, 64), grad_dtype, dev)
+            self.ws = _empty((_lib.load().ghnd_stem_wgrad_workspace_bytes(),), torch.uint8, dev)
+
+    def refresh_weights(self):
+        ops.stem_pack_weight(self.body.conv1.weight, self.scale, out=self.w)
+
+    def forward(self):
+        if self.trainable:
+            self.refresh_weights()
+        self.plan.run()
+        ops.maxpool3x3s2(self.conv, self.out, self.argmax)
+
+    def backward(self, g_out, dw):
+        """g_out: gradient w.r.t. the pooled output; dw: fp32 OIHW view for conv1.weight.grad."""
+        ops.maxpool3x3s2_bwd(self.conv, self.argmax, g_out, self.g_conv)
+        ops.stem_wgrad(self.packed, self.g_conv, self.scale, dw, self.N, self.Hp, self.Wp, ws=self.ws)
+
+
+class _BN(object):
+    """Training-mode nn.BatchNorm2d state for one NHWC tensor (or the planar bottleneck)."""
+
+    def __init__(self, bn, C, count, dev):
+        self.bn, self.C, self.count = bn, C, count
+        self.sums = _empty((2 * C,), torch.float64, dev)
+        self.scale_shift = _empty((2 * C,), torch.float32, dev)
+        self.mean_invstd = _empty((2 * C,), torch.float32, dev)
+
+    def finalize(self):
+        bn = self.bn
+        ops.bn_finalize(self.sums, self.count, self.C, bn.weight, bn.bias, bn.eps,
+                        0.1 if bn.momentum is None else bn.momentum, bn.running_mean, bn.running_var,
+                        bn.num_batches_tracked, self.scale_shift, self.mean_invstd)
+
+    def eval_params(self):
+        bn = self.bn
+        ops.bn_eval_params(self.C, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps,
+                           self.scale_shift)
+
+
+class _WideUnit(object):
+    """conv(k2) -> BatchNorm(batch stats) [-> ReLU] of the student's layer1, forward + backward."""
+
+    def __init__(self, conv, bn, relu, x, x_g, N, H, W, act_dtype, grad_dtype, train):
+        dev = x.device
+        K, C, R, S = conv.weight.shape
+        pad = conv.padding[0]
+        self.conv, self.relu, self.x, self.x_g = conv, relu, x, x_g
+        self.N, self.H, self.W, self.C, self.K, self.pad = N, H, W, C, K, pad
+        self.Ho, self.Wo = H + 2 * pad - R + 1, W + 2 * pad - S + 1
+        self.train = train
+        self.w = _empty((K, R, S, C), act_dtype, dev)
+        self.bn = _BN(bn, K, N * self.Ho * self.Wo, dev)
+        self.out = _empty((N, self.Ho, self.Wo, K), act_dtype, dev)
+        if train:
+            self.raw = _empty((N, self.Ho, self.Wo, K), act_dtype, dev)
+            self.out_g = _empty((N, self.Ho, self.Wo, K), grad_dtype, dev)  # bf16 copy for wgrad
+            self.plan = ops.ConvPlan(CONV_FWD, N, H, W, C, K, R, S, 1, pad, x, self.w, self.raw)
+        else:
+            # eval: BN folded into the conv (scale into the weights, shift as bias, ReLU in epilogue)
+            self.raw = self.out_g = None
+            self.plan = ops.ConvPlan(CONV_FWD, N, H, W, C, K, R, S, 1, pad, x, self.w, self.out,
+                                     bias=self.bn.scale_shift[K:], relu=relu)
+
+    def forward(self):
+        if self.train:
+            ops.pack_weight(self.conv.weight, None, False, out=self.w)
+            self.plan.run()
+            ops.bn_stats(self.raw, self.bn.sums)
+            self.bn.finalize()
+            ops.bn_apply(self.raw, self.out, self.bn.scale_shift, self.relu, y2=self.out_g)
+        else:
+            self.bn.eval_params()
+            ops.pack_weight(self.conv.weight, self.bn.scale_shift[:self.K], False, out=self.w)
+            self.plan.run()
+
+    def plan_backward(self, g_out, g_x, grads, names, grad_dtype):
+        """g_out: gradient w.r.t. self.out; g_x: gradient buffer for the input (None: not needed);
+        grads: dict name -> fp32 grad view; names = (conv.weight, bn.weight, bn.bias)."""
+        dev = g_out.device
+        N, H, W, C, K = self.N, self.H, self.W, self.C, self.K
+        R, S = self.conv.weight.shape[2:]
+        self.g_out, self.g_x = g_out, g_x
+        self.g_raw = _empty((N, self.Ho, self.Wo, K), grad_dtype, dev)
+        self.dw_packed = _empty((K, R, S, C), torch.float32, dev)
+        self.dw, self.dgamma, self.dbeta = grads[names[0]], grads[names[1]], grads[names[2]]
+        self.wgrad = ops.WgradPlan(N, H, W, C, K, R, S, self.pad, self.x_g, self.g_raw, self.dw_packed)
+        self.wt = None
+        self.dgrad = None
+        if g_x is not None:
+            self.wt = _empty((C, R, S, K), grad_dtype, dev)
+            self.dgrad = ops.ConvPlan(CONV_DGRAD, N, H, W, C, K, R, S, 1, self.pad, self.g_raw, self.wt, g_x)
+
+    def backward(self):
+        bn = self.bn
+        ops.bn_bwd_reduce(self.g_out, self.raw, bn.scale_shift, bn.mean_invstd, self.relu, bn.sums)
+        ops.bn_bwd_apply(self.g_out, self.raw, self.g_raw, bn.bn.weight, bn.scale_shift, bn.mean_invstd,
+                         self.relu, bn.sums, self.dgamma, self.dbeta)
+        self.wgrad.run()
+        ops.unpack_wgrad(self.dw_packed, self.dw)
+        if self.dgrad is not None:
+            ops.pack_weight(self.conv.weight, None, True, out=self.wt)
+            self.dgrad.run()
+
+
+class StudentLayer1Runner(object):
+    """Bottleneck4LargeResNet (resnet_layer.py:40-70): three wide encoder convs, the narrow
+    64->bch / bch->64 pair around the planar fp32 bottleneck z, three wide decoder convs."""
+
+    def __init__(self, layer1, x, N, H, W, act_dtype, grad_dtype, train, x_g=None):
+        dev = x.device
+        enc, dec = layer1.encoder.encoder, layer1.decoder
+        self.layer1, self.train = layer1, train
+        self.N, self.H, self.W = N, H, W
+        self.act_dtype, self.grad_dtype = act_dtype, grad_dtype
+        self.x = x
+        if train and x_g is None:
+            x_g = _empty(tuple(x.shape), grad_dtype, dev)
+            self._own_xg = True
+        else:
+            self._own_xg = False
+        self.x_g = x_g
+        mk = lambda conv, bn, relu, xin, xin_g, h, w: _WideUnit(conv, bn, relu, xin, xin_g, N, h, w,
+                                                              act_dtype, grad_dtype, train)
+        self.e0 = mk(enc[0], enc[1], False, x, x_g, H, W)
+        self.e1 = mk(enc[2], enc[3], True, self.e0.out, self.e0.out_g, self.e0.Ho, self.e0.Wo)
+        self.e2 = mk(enc[5], enc[6], False, self.e1.out, self.e1.out_g, self.e1.Ho, self.e1.Wo)
+        self.enc7, self.bn0, self.dec2 = enc[7], dec[0], dec[2]
+        self.bch = enc[7].weight.shape[0]
+        self.Hz, self.Wz = self.e2.Ho + 1, self.e2.Wo + 1
+        self.z = _empty((N, self.bch, self.Hz, self.Wz), torch.float32, dev)
+        self.bnz = _BN(dec[0], self.bch, N * self.Hz * self.Wz, dev)
+        self.H3, self.W3 = self.Hz - 1, self.Wz - 1
+        self.nws = ops._narrow_ws(self.bch, 64, 2, 2, dev)
+        # dec2 output + its BN (dec[3], no ReLU)
+        self.raw3 = _empty((N, self.H3, self.W3, 64), act_dtype, dev)
+        self.act3 = _empty((N, self.H3, self.W3, 64), act_dtype, dev)
+        self.act3_g = _empty((N, self.H3, self.W3, 64), grad_dtype, dev) if train else None
+        self.bn3 = _BN(dec[3], 64, N * self.H3 * self.W3, dev)
+        self.d4 = mk(dec[4], dec[5], True, self.act3, self.act3_g, self.H3, self.W3)
+        self.d7 = mk(dec[7], dec[8], False, self.d4.out, self.d4.out_g, self.d4.Ho, self.d4.Wo)
+        self.d9 = mk(dec[9], dec[10], True, self.d7.out, self.d7.out_g, self.d7.Ho, self.d7.Wo)
+        self.out = self.d9.out
+        assert (self.d9.Ho, self.d9.Wo) == (H, W)
+        self.q = None  # set by forward_encoder_quantized
+
+    # ---- forward ----
+    def forward_encoder(self):
+        if self.train and self._own_xg:
+            ops.convert16(self.x, self.x_g)
+        self.e0.forward()
+        self.e1.forward()
+        self.e2.forward()
+        ops.conv_narrow_out(self.e2.out, self.enc7.weight, 1, y=self.z, ws=self.nws)
+        return self.z
+
+    def forward_decoder(self, z=None):
+        z = self.z if z is None else z
+        if self.train:
+            ops.bn_stats(z, self.bnz.sums, planar=True)
+            self.bnz.finalize()
+        else:
+            self.bnz.eval_params()
+        ops.conv_narrow_in(z, self.dec2.weight, 0, pre=self.bnz.scale_shift, pre_relu=True, y=self.raw3,
+                           ws=self.nws)
+        if self.train:
+            ops.bn_stats(self.raw3, self.bn3.sums)
+            self.bn3.finalize()
+        else:
+            self.bn3.eval_params()
+        ops.bn_apply(self.raw3, self.act3, self.bn3.scale_shift, False, y2=self.act3_g)
+        self.d4.forward()
+        self.d7.forward()
+        self.d9.forward()
+        return self.out
+
+    def forward(self):
+        self.forward_encoder()
+        return self.forward_decoder()
+
+    # ---- backward ----
+    def plan_backward(self, g_out, grads, prefix, need_gx=True):
+        """g_out: gradient w.r.t. layer1's output (bf16 NHWC).  grads: name -> fp32 view."""
+        dev = g_out.device
+        N, gd = self.N, self.grad_dtype
+        e, d = prefix + "encoder.encoder.", prefix + "decoder."
+        g = lambda u: _empty((N, u.H, u.W, u.C), gd, dev)
+        self.g_d7out, self.g_d4out, self.g_act3 = g(self.d9), g(self.d7), g(self.d4)
+        self.d9.plan_backward(g_out, self.g_d7out, grads, (d + "9.weight", d + "10.weight", d + "10.bias"), gd)
+        self.d7.plan_backward(self.g_d7out, self.g_d4out, grads, (d + "7.weight", d + "8.weight", d + "8.bias"), gd)
+        self.d4.plan_backward(self.g_d4out, self.g_act3, grads, (d + "4.weight", d + "5.weight", d + "5.bias"), gd)
+        self.g_raw3 = _empty((N, self.H3, self.W3, 64), gd, dev)
+        self.g_zact = _empty(tuple(self.z.shape), torch.float32, dev)  # grad wrt relu(bn0(z))
+        self.g_z = _empty(tuple(self.z.shape), torch.float32, dev)
+        self.wws = _empty((_lib.load().ghnd_wgrad_narrow_workspace_bytes(self.bch, 64, 2, 2),), torch.uint8, dev)
+        self.gr = {k: grads[k] for k in (d + "3.weight", d + "3.bias", d + "2.weight", d + "0.weight",
+                                         d + "0.bias", e + "7.weight")}
+        self.names = (e, d)
+        self.g_e2out, self.g_e1out, self.g_e0out = g_like(self.e2, gd, dev), g_like(self.e1, gd, dev), g_like(self.e0, gd, dev)
+        self.g_x = _empty((N, self.H, self.W, 64), gd, dev) if need_gx else None
+        self.e2.plan_backward(self.g_e2out, self.g_e1out, grads, (e + "5.weight", e + "6.weight", e + "6.bias"), gd)
+        self.e1.plan_backward(self.g_e1out, self.g_e0out, grads, (e + "2.weight", e + "3.weight", e + "3.bias"), gd)
+        self.e0.plan_backward(self.g_e0out, self.g_x, grads, (e + "0.weight", e + "1.weight", e + "1.bias"), gd)
+
+    def backward(self):
+        e, d = self.names
+        self.d9.backward()
+        self.d7.backward()
+        self.d4.backward()
+        # BN dec[3] (no ReLU) on raw3
+        b3 = self.bn3
+        ops.bn_bwd_reduce(self.g_act3, self.raw3, b3.scale_shift, b3.mean_invstd, False, b3.sums)
+        ops.bn_bwd_apply(self.g_act3, self.raw3, self.g_raw3, b3.bn.weight, b3.scale_shift, b3.mean_invstd,
+                         False, b3.sums, self.gr[d + "3.weight"], self.gr[d + "3.bias"])
+        # dec2 (narrow-in conv on relu(bn0(z)))
+        bz = self.bnz
+        ops.wgrad_narrow(self.z, self.g_raw3, self.gr[d + "2.weight"], False, 2, 2, 0, pre=bz.scale_shift,
+                         pre_relu=True, ws=self.wws)
+        ops.conv_narrow_out_dgrad(self.g_raw3, self.dec2.weight, 0, self.Hz, self.Wz, dx=self.g_zact,
+                                  ws=self.nws)
+        # BN dec[0] + ReLU on the planar bottleneck
+        ops.bn_bwd_reduce(self.g_zact, self.z, bz.scale_shift, bz.mean_invstd, True, bz.sums, planar=True)
+        ops.bn_bwd_apply(self.g_zact, self.z, self.g_z, bz.bn.weight, bz.scale_shift, bz.mean_invstd, True,
+                         bz.sums, self.gr[d + "0.weight"], self.gr[d + "0.bias"], planar=True)
+        # enc7 (narrow-out conv)
+        ops.wgrad_narrow(self.g_z, self.e2.out, self.gr[e + "7.weight"], True, 2, 2, 1, ws=self.wws)
+        ops.conv_narrow_in(self.g_z, self.enc7.weight, 1, flip=True, y=self.g_e2out, ws=self.nws)
+        self.e2.backward()
+        self.e1.backward()
+        self.e0.backward()
+
+
+def g_like(unit, dtype, dev):
+    return _empty((unit.N, unit.Ho, unit.Wo, unit.K), dtype, dev)
+
+
+class FlatParams(object):
+    """All trainable student tensors as views of ONE flat fp32 buffer (+ flat grad / Adam moments):
+    a single all-reduce and a single fused Adam kernel cover the 25 tensors."""
+
+    def __init__(self, named_params):
+        named_params = [(n, p) for n, p in named_params if p.requires_grad]
+        assert named_params, "no trainable parameters"
+        dev = named_params[0][1].device
+        sizes = [((p.numel() + 3) // 4) * 4 for _, p in named_params]  # keep 16-byte alignment
+        total = sum(sizes)
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.names, self.params, self.grads = [], {}, {}
+        off = 0
+        for (n, p), sz in zip(named_params, sizes):
+            view = self.flat[off:off + p.numel()].view(p.shape)
+            view.copy_(p.data)
+            p.data = view
+            self.grads[n] = self.grad[off:off + p.numel()].view(p.shape)
+            self.params[n] = p
+            self.names.append(n)
+            off += sz
+        self.total = total
+
+
+class GhndPlan(object):
+    """One fixed-shape GHND / HND distillation step for a (teacher body, student body) pair."""
+
+    def __init__(self, teacher_body, student_body, N, Hp, Wp, levels=LEVELS, factors=None,
+                 act_dtype=torch.float16, grad_dtype=torch.bfloat16, device=None, flat=None,
+                 image_mean=IMAGE_MEAN, image_std=IMAGE_STD):
+        _lib.check(_lib.load().ghnd_device_check(), "ghnd_device_check")
+        dev = torch.device(device) if device is not None else next(student_body.parameters()).device
+        self.device, self.N, self.Hp, self.Wp = dev, N, Hp, Wp
+        self.levels = tuple(l for l in LEVELS if l in levels)
+        assert self.levels, "no loss levels"
+        self.factors = {l: 1.0 for l in self.levels}
+        if factors:
+            self.factors.update(factors)
+        self.act_dtype, self.grad_dtype = act_dtype, grad_dtype
+        self.mean, self.std = tuple(image_mean), tuple(image_std)
+        top = max(LEVELS.index(l) for l in self.levels)
+        self.top = LEVELS[top]
+        self.packed = torch.zeros((N, Hp + 6, Wp + 8, 4), dtype=act_dtype, device=dev)
+        # ---- teacher (forward only) ----
+        self.t_stem = StemRunner(teacher_body, self.packed, N, Hp, Wp, act_dtype, grad_dtype, False)
+        self.t_layers, x, H, W = {}, self.t_stem.out, self.t_stem.Ho, self.t_stem.Wo
+        for name in LEVELS[:top + 1]:
+            r = FrozenLayerRunner(getattr(teacher_body, name), x, N, H, W, act_dtype, grad_dtype, False)
+            self.t_layers[name] = r
+            x, H, W = r.out, r.Ho, r.Wo
+        # ---- student ----
+        self.flat = flat if flat is not None else FlatParams(
+            [("backbone.body." + n, p) for n, p in student_body.named_parameters()])
+        grads = self.flat.grads
+        self.s_stem = StemRunner(student_body, self.packed, N, Hp, Wp, act_dtype, grad_dtype, True)
+        self.s_l1 = StudentLayer1Runner(student_body.layer1, self.s_stem.out, N, self.s_stem.Ho,
+                                        self.s_stem.Wo, act_dtype, grad_dtype, True)
+        self.s_layers, x, H, W = {}, self.s_l1.out, self.s_stem.Ho, self.s_stem.Wo
+        for name in LEVELS[1:top + 1]:
+            r = FrozenLayerRunner(getattr(student_body, name), x, N, H, W, act_dtype, grad_dtype, True)
+            self.s_layers[name] = r
+            x, H, W = r.out, r.Ho, r.Wo
+        # ---- loss ----
+        self.feat_t = {"layer1": self.t_layers["layer1"].out}
+        self.feat_s = {"layer1": self.s_l1.out}
+        for name in LEVELS[1:top + 1]:
+            self.feat_t[name] = self.t_layers[name].out
+            self.feat_s[name] = self.s_layers[name].out
+        self.loss_grads = {l: torch.empty_like(self.feat_s[l], dtype=grad_dtype) for l in self.levels}
+        self.loss_out = torch.zeros(1 + len(self.levels), dtype=torch.float32, device=dev)
+        self.sse_ws = _empty((_lib.load().ghnd_sse_workspace_bytes(),), torch.uint8, dev)
+        # ---- backward plans (top level down) ----
+        g = self.loss_grads[self.top]  # masked by the SSE kernel (relu_mask on the top level)
+        for name in reversed(LEVELS[1:top + 1]):
+            r = self.s_layers[name]
+            below = LEVELS[LEVELS.index(name) - 1]
+            g_x = torch.empty_like(r.blocks[0].x, dtype=grad_dtype)
+            r.plan_backward(g, g_x, self.loss_grads.get(below), grad_dtype)
+            g = g_x
+        self.s_l1.plan_backward(g, grads, "backbone.body.layer1.")
+        self.graph = None
+        self.step_count = 0
+
+    # ------------------------------------------------------------------------------------------
+    def load_images(self, images):
+        """images: list of N fp32 [3,H,W] CUDA tensors in [0,1] (already at network scale)."""
+        assert len(images) == self.N, "plan was built for batch %d" % self.N
+        for i, im in enumerate(images):
+            ops.stem_pack_image(im, self.packed, i, self.Hp, self.Wp, self.mean, self.std)
+
+    def forward_backward(self):
+        """Enqueue teacher fwd, student fwd, loss and student bwd on the current stream."""
+        self.t_stem.forward()
+        for name in LEVELS:
+            if name in self.t_layers:
+                self.t_layers[name].forward()
+        self.s_stem.forward()
+        self.s_l1.forward()
+        for name in LEVELS[1:]:
+            if name in self.s_layers:
+                self.s_layers[name].forward()
+        lv = [(self.feat_t[l], self.feat_s[l], self.loss_grads[l], self.factors[l], l == self.top)
+              for l in self.levels]
+        ops.sse_fwd_bwd(lv, self.grad_dtype, self.loss_out, self.sse_ws)
+        for name in reversed(LEVELS[1:]):
+            if name in self.s_layers:
+                self.s_layers[name].backward()
+        self.s_l1.backward()
+        self.s_stem.backward(self.s_l1.g_x, self.flat.grads["backbone.body.conv1.weight"])
+        return self.loss_out
+
+    def capture(self):
+        """Capture forward_backward() into a CUDA graph (buffers and plans are static)."""
+        torch.cuda.synchronize()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self.forward_backward()  # warm-up outside capture (lazy module loading)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        before = ops.launches()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.forward_backward()
+        self.launches_per_step = ops.launches() - before
+        self.graph = g
+        return g
+
+    def step(self, images=None):
+        if images is not None:
+            self.load_images(images)
+        if self.graph is not None:
+            self.graph.replay()
+            ops._count(self.launches_per_step)
+        else:
+            self.forward_backward()
+        self.step_count += 1
+        return self.loss_out
+
+
+class EncodePlan(object):
+    """Split-computing head (RcnnHead, split_rcnn.py:23-37) for a fixed shape: stem -> layer1
+    encoder with eval-mode BN folded into the convs -> fused 8-bit quantizer."""
+
+    def __init__(self, student_body, N, Hp, Wp, num_bits=8, act_dtype=torch.float16, device=None,
+                 image_mean=IMAGE_MEAN, image_std=IMAGE_STD, scale_mode=_lib.QSCALE_DIV):
+        _lib.check(_lib.load().ghnd_device_check(), "ghnd_device_check")
+        dev = torch.device(device) if device is not None else next(student_body.parameters()).device
+        self.N, self.Hp, self.Wp, self.num_bits, self.scale_mode = N, Hp, Wp, num_bits, scale_mode
+        self.mean, self.std = tuple(image_mean), tuple(image_std)
+        self.packed = torch.zeros((N, Hp + 6, Wp + 8, 4), dtype=act_dtype, device=dev)
+        self.stem = StemRunner(student_body, self.packed, N, Hp, Wp, act_dtype, torch.bfloat16, False)
+        self.l1 = StudentLayer1Runner(student_body.layer1, self.stem.out, N, self.stem.Ho, self.stem.Wo,
+                                      act_dtype, torch.bfloat16, False)
+        self.z = self.l1.z
+        self.q = torch.empty(tuple(self.z.shape), dtype=torch.uint8, device=dev)
+        self.qparams = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.qws_bytes = _lib.load().ghnd_quantize_u8_workspace_bytes(self.z.numel())
+        self.qws = _empty((self.qws_bytes,), torch.uint8, dev)
+        self.graph = None
+
+    def load_images(self, images):
+        assert len(images) == self.N
+        for i, im in enumerate(images):
+            ops.stem_pack_image(im, self.packed, i, self.Hp, self.Wp, self.mean, self.std)
+
+    def forward(self):
+        self.stem.refresh_weights()
+        self.stem.forward()
+        self.l1.forward_encoder()
+        if self.num_bits == 16:
+            return self.z
+        _lib.call("ghnd_quantize_u8", _lib.ptr(self.z), self.z.numel(), self.num_bits, self.scale_mode,
+                  _lib.ptr(self.q), _lib.ptr(self.qparams), _lib.ptr(self.qws), self.qws_bytes,
+                  _lib.stream_ptr())
+        ops._count(2)
+        return self.q
+
+    def capture(self):
+        torch.cuda.synchronize()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self.forward()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        before = ops.launches()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.forward()
+        self.launches_per_step = ops.launches() - before
+        self.graph = g
+        return g
+
+    def run(self, images=None):
+        if images is not None:
+            self.load_images(images)
+        if self.graph is not None:
+            self.graph.replay()
+            ops._count(self.launches_per_step)
+        else:
+            self.forward()
+        return self.q, self.qparams
+
+
+class BodyPlan(object):
+    """Forward-only backbone body (stem -> layer1..4) for a fixed shape: the teacher's frozen
+    ResNet-50 or the student's bottleneck-injected one (BN in eval mode unless layer1.training).
+    Used by CustomRCNN.backbone_features / distill_backbone_only (rcnn.py:102-110)."""
+
+    def __init__(self, body, N, Hp, Wp, act_dtype=torch.float16, image_mean=IMAGE_MEAN,
+                 image_std=IMAGE_STD, device=None):
+        from .resnet_layer import BottleneckBase4Ext
+        _lib.check(_lib.load().ghnd_device_check(), "ghnd_device_check")
+        dev = torch.device(device) if device is not None else body.conv1.weight.device
+        self.body, self.N, self.Hp, self.Wp = body, N, Hp, Wp
+        self.mean, self.std = tuple(image_mean), tuple(image_std)
+        self.packed = torch.zeros((N, Hp + 6, Wp + 8, 4), dtype=act_dtype, device=dev)
+        self.stem = StemRunner(body, self.packed, N, Hp, Wp, act_dtype, torch.bfloat16, False)
+        x, H, W = self.stem.out, self.stem.Ho, self.stem.Wo
+        self.student = isinstance(body.layer1, BottleneckBase4Ext)
+        self.feats = {}
+        if self.student:
+            self.l1_train = bool(body.layer1.training)
+            self.l1 = StudentLayer1Runner(body.layer1, x, N, H, W, act_dtype, torch.bfloat16, self.l1_train)
+            x = self.l1.out
+        else:
+            self.l1 = FrozenLayerRunner(body.layer1, x, N, H, W, act_dtype, torch.bfloat16, False)
+            x, H, W = self.l1.out, self.l1.Ho, self.l1.Wo
+        self.feats["layer1"] = x
+        self.layers = []
+        for name in LEVELS[1:]:
+            r = FrozenLayerRunner(getattr(body, name), x, N, H, W, act_dtype, torch.bfloat16, False)
+            self.layers.append(r)
+            x, H, W = r.out, r.Ho, r.Wo
+            self.feats[name] = x
+
+    def run(self, images):
+        assert len(images) == self.N
+        for i, im in enumerate(images):
+            ops.stem_pack_image(im, self.packed, i, self.Hp, self.Wp, self.mean, self.std)
+        self.stem.refresh_weights()
+        self.stem.forward()
+        if self.student:
+            l1 = self.body.layer1
+            z = self.l1.forward_encoder()
+            if (not l1.training) and l1.bottleneck_transformer is not None and l1.use_bottleneck_transformer:
+                z, _ = l1.bottleneck_transformer(z, None)  # base.py:55-57
+                z = z.to(self.packed.device).contiguous()
+            self.l1.forward_decoder(z)
+        else:
+            self.l1.forward()
+        for r in self.layers:
+            r.forward()
+        return self.feats

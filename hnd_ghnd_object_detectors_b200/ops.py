@@ -1,0 +1,449 @@
+"""Thin torch-tensor wrappers over the C ABI (include/ghnd_b200.h).
+
+torch is used for device memory and streams only; every function here enqueues hand-written
+sm_100a kernels from libghnd_b200.so on the current CUDA stream and raises GhndError on failure.
+There is no CPU path.
+"""
+import ctypes
+from ctypes import byref, c_float, c_void_p
+
+import torch
+
+from . import _lib
+from ._lib import BF16, F16, call, fmt_of, ptr, stream_ptr
+
+# kernel-launch accounting (bench.py reports it as gpu_launches)
+_launches = 0
+
+
+def launches():
+    return _launches
+
+
+def _count(n=1):
+    global _launches
+    _launches += n
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.GhndError("ghnd ops need CUDA tensors (no CPU fallback); got %s" % t.device)
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+# ------------------------------------------------------------------------------------------------
+# quantizer
+# ------------------------------------------------------------------------------------------------
+def quantize_u8(x, num_bits=8, scale_mode=_lib.QSCALE_DIV):
+    """-> (q uint8 like x, qparams: 16-byte device tensor {scale f32, zp i32, min f32, max f32})."""
+    _need_cuda(x)
+    if x.dtype != torch.float32:
+        x = x.float()
+    x = x.contiguous()
+    q = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    qp = torch.empty(4, dtype=torch.int32, device=x.device)
+    n = x.numel()
+    wsz = _lib.load().ghnd_quantize_u8_workspace_bytes(n)
+    ws = _ws(wsz, x.device)
+    call("ghnd_quantize_u8", ptr(x), n, num_bits, scale_mode, ptr(q), ptr(qp), ptr(ws), wsz, stream_ptr())
+    _count(2)
+    return q, qp
+
+
+def dequantize_u8(q, qparams):
+    _need_cuda(q, qparams)
+    q = q.contiguous()
+    out = torch.empty(q.shape, dtype=torch.float32, device=q.device)
+    if q.numel():
+        call("ghnd_dequantize_u8", ptr(q), q.numel(), ptr(qparams), ptr(out), stream_ptr())
+        _count(1)
+    return out
+
+
+def make_qparams(scale, zero_point, device):
+    qp = torch.zeros(4, dtype=torch.int32, device=device)
+    qp[0:1].view(torch.float32).copy_(torch.as_tensor([float(scale)], dtype=torch.float32))
+    qp[1] = int(zero_point)
+    return qp
+
+
+# ------------------------------------------------------------------------------------------------
+# loss
+# ------------------------------------------------------------------------------------------------
+def sse_fwd_bwd(levels, grad_dtype=torch.bfloat16, loss_out=None, workspace=None):
+    """levels: list of (teacher, student, grad_or_None, factor, relu_mask) with 16-bit tensors of
+    identical shape/dtype.  Returns float32 tensor [1+n]: total, then factor*SSE per level."""
+    n = len(levels)
+    arr = (_lib.SseLevel * n)()
+    dev = levels[0][0].device
+    in_fmt = fmt_of(levels[0][0].dtype)
+    for i, (t, s, g, factor, mask) in enumerate(levels):
+        _need_cuda(t, s, g)
+        assert t.shape == s.shape and t.dtype == s.dtype and t.is_contiguous() and s.is_contiguous()
+        arr[i].teacher = t.data_ptr()
+        arr[i].student = s.data_ptr()
+        arr[i].grad = g.data_ptr() if g is not None else None
+        arr[i].n = t.numel()
+        arr[i].factor = float(factor)
+        arr[i].relu_mask = int(mask)
+    if loss_out is None:
+        loss_out = torch.empty(1 + n, dtype=torch.float32, device=dev)
+    wsz = _lib.load().ghnd_sse_workspace_bytes()
+    if workspace is None:
+        workspace = _ws(wsz, dev)
+    call("ghnd_sse_fwd_bwd", arr, n, in_fmt, fmt_of(grad_dtype), ptr(loss_out), ptr(workspace), wsz,
+         stream_ptr())
+    _count(2)
+    return loss_out
+
+
+# ------------------------------------------------------------------------------------------------
+# layout boundary
+# ------------------------------------------------------------------------------------------------
+def to_nhwc16(x, dtype=torch.float16):
+    """NCHW fp32 -> NHWC 16-bit tensor of shape [N,H,W,C]."""
+    _need_cuda(x)
+    x = x.float().contiguous()
+    n, c, h, w = x.shape
+    y = torch.empty((n, h, w, c), dtype=dtype, device=x.device)
+    call("ghnd_nchw_f32_to_nhwc16", ptr(x), ptr(y), fmt_of(dtype), n, c, h, w, stream_ptr())
+    _count()
+    return y
+
+
+def to_nhwc16_into(x, y):
+    """NCHW fp32 -> existing NHWC 16-bit buffer y [N,H,W,C]."""
+    _need_cuda(x, y)
+    x = x.float().contiguous()
+    n, c, h, w = x.shape
+    assert tuple(y.shape) == (n, h, w, c), (tuple(y.shape), (n, h, w, c))
+    call("ghnd_nchw_f32_to_nhwc16", ptr(x), ptr(y), fmt_of(y.dtype), n, c, h, w, stream_ptr())
+    _count()
+    return y
+
+
+def to_nchw_f32(y):
+    """NHWC 16-bit [N,H,W,C] -> NCHW fp32."""
+    _need_cuda(y)
+    y = y.contiguous()
+    n, h, w, c = y.shape
+    x = torch.empty((n, c, h, w), dtype=torch.float32, device=y.device)
+    call("ghnd_nhwc16_to_nchw_f32", ptr(y), fmt_of(y.dtype), ptr(x), n, c, h, w, stream_ptr())
+    _count()
+    return x
+
+
+# ------------------------------------------------------------------------------------------------
+# plans (wide convs)
+# ------------------------------------------------------------------------------------------------
+class ConvPlan(object):
+    """ghnd_conv_plan: tcgen05 implicit-GEMM conv forward / dgrad bound to fixed buffers."""
+
+    def __init__(self, kind, N, H, W, C, K, R, S, stride, pad, src, weights, dst, bias=None,
+                 residual=None, relu=False, mask=None, accumulate=False):
+        d = _lib.ConvDesc()
+        d.kind = kind
+        d.N, d.H, d.W, d.C, d.K, d.R, d.S, d.stride, d.pad = N, H, W, C, K, R, S, stride, pad
+        d.src, d.src_fmt = src.data_ptr(), fmt_of(src.dtype)
+        d.weights, d.w_fmt = weights.data_ptr(), fmt_of(weights.dtype)
+        d.dst, d.dst_fmt = dst.data_ptr(), fmt_of(dst.dtype)
+        d.bias = bias.data_ptr() if bias is not None else None
+        d.residual = residual.data_ptr() if residual is not None else None
+        d.res_fmt = fmt_of(residual.dtype) if residual is not None else 0
+        d.relu = int(bool(relu))
+        d.mask = mask.data_ptr() if mask is not None else None
+        d.mask_fmt = fmt_of(mask.dtype) if mask is not None else 0
+        d.accumulate = int(bool(accumulate))
+        d.stats = None
+        self._keep = (src, weights, dst, bias, residual, mask)  # buffers must outlive the plan
+        self._h = c_void_p()
+        call("ghnd_conv_plan_create", byref(d), byref(self._h))
+        self.n_launches = _lib.load().ghnd_conv_plan_launches(self._h)
+
+    def run(self, stream=None):
+        call("ghnd_conv_plan_run", self._h, stream_ptr(stream))
+        _count(self.n_launches)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                _lib.load().ghnd_conv_plan_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+
+class WgradPlan(object):
+    def __init__(self, N, H, W, C, K, R, S, pad, x, dy, dw):
+        d = _lib.WgradDesc()
+        d.N, d.H, d.W, d.C, d.K, d.R, d.S, d.pad = N, H, W, C, K, R, S, pad
+        d.x, d.x_fmt = x.data_ptr(), fmt_of(x.dtype)
+        d.dy, d.dy_fmt = dy.data_ptr(), fmt_of(dy.dtype)
+        assert dw.dtype == torch.float32 and dw.numel() == K * R * S * C
+        d.dw = dw.data_ptr()
+        self._keep = (x, dy, dw)
+        self._h = c_void_p()
+        call("ghnd_wgrad_plan_create", byref(d), byref(self._h))
+
+    def run(self, stream=None):
+        call("ghnd_wgrad_plan_run", self._h, stream_ptr(stream))
+        _count(1)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                _lib.load().ghnd_wgrad_plan_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+
+class StemPlan(object):
+    def __init__(self, x_packed, w_packed, bias, y, N, Hp, Wp):
+        self._keep = (x_packed, w_packed, bias, y)
+        self._h = c_void_p()
+        call("ghnd_stem_conv_plan_create", ptr(x_packed), fmt_of(x_packed.dtype), ptr(w_packed),
+             fmt_of(w_packed.dtype), ptr(bias), ptr(y), fmt_of(y.dtype), N, Hp, Wp, byref(self._h))
+
+    def run(self, stream=None):
+        call("ghnd_stem_conv_plan_run", self._h, stream_ptr(stream))
+        _count(4)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                _lib.load().ghnd_stem_plan_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+
+# ------------------------------------------------------------------------------------------------
+# weights
+# ------------------------------------------------------------------------------------------------
+def pack_weight(w, scale=None, transpose=False, dtype=torch.float16, out=None):
+    """OIHW fp32 (x per-O scale) -> [O][R][S][I] (or [I][R][S][O] when transpose) 16-bit."""
+    _need_cuda(w)
+    w = w.detach().float().contiguous()
+    o, i, r, s = w.shape
+    if out is None:
+        out = torch.empty((i, r, s, o) if transpose else (o, r, s, i), dtype=dtype, device=w.device)
+    call("ghnd_pack_weight", ptr(w), ptr(scale), o, i, r, s, int(transpose), ptr(out), fmt_of(out.dtype),
+         stream_ptr())
+    _count()
+    return out
+
+
+def unpack_wgrad(dw, out, alpha=1.0):
+    """[O][R][S][I] fp32 -> OIHW fp32 into `out`."""
+    o, i, r, s = out.shape
+    call("ghnd_unpack_wgrad", ptr(dw), ptr(out), o, i, r, s, float(alpha), stream_ptr())
+    _count()
+    return out
+
+
+def stem_pack_weight(w, scale=None, dtype=torch.float16, out=None):
+    w = w.detach().float().contiguous()
+    if out is None:
+        out = torch.empty((64, 7, 32), dtype=dtype, device=w.device)
+    call("ghnd_stem_pack_weight", ptr(w), ptr(scale), ptr(out), fmt_of(out.dtype), stream_ptr())
+    _count()
+    return out
+
+
+def stem_pack_image(img, dst, n_index, Hp, Wp, mean, std):
+    """img [3,H,W] fp32 in [0,1] -> dst[n_index] of the packed batch [N][Hp+6][Wp+8][4]."""
+    _need_cuda(img, dst)
+    img = img.float().contiguous()
+    m = (c_float * 3)(*[float(v) for v in mean])
+    s = (c_float * 3)(*[float(v) for v in std])
+    call("ghnd_stem_pack_image", ptr(img), img.shape[1], img.shape[2], m, s, ptr(dst), fmt_of(dst.dtype),
+         n_index, Hp, Wp, stream_ptr())
+    _count()
+
+
+# ------------------------------------------------------------------------------------------------
+# narrow convs (planar fp32 bottleneck side <-> NHWC 16-bit wide side)
+# ------------------------------------------------------------------------------------------------
+def _narrow_ws(c, k, r, s, device):
+    n = _lib.load().ghnd_conv_narrow_workspace_bytes(c, k, r, s)
+    return _ws(n, device), n
+
+
+def conv_narrow_out(x, w, pad, y=None, ws=None):
+    """x NHWC16 [N,H,W,C], w OIHW fp32 [K,C,R,S] -> y planar fp32 [N,K,Ho,Wo]."""
+    n, h, wd, c = x.shape
+    k, _, r, s = w.shape
+    ho, wo = h + 2 * pad - r + 1, wd + 2 * pad - s + 1
+    if y is None:
+        y = torch.empty((n, k, ho, wo), dtype=torch.float32, device=x.device)
+    if ws is None:
+        ws = _narrow_ws(c, k, r, s, x.device)
+    call("ghnd_conv_narrow_out", ptr(x), fmt_of(x.dtype), ptr(w), ptr(y), n, h, wd, c, k, r, s, pad,
+         ptr(ws[0]), ws[1], stream_ptr())
+    _count(2)
+    return y
+
+
+def conv_narrow_in(x, w, pad, pre=None, pre_relu=False, flip=False, dtype=torch.float16, y=None, ws=None):
+    """flip=False: x planar fp32 [N,C,H,W], w [K,C,R,S] -> y NHWC16 [N,Ho,Wo,K].
+    flip=True : x = dy planar [N,C,H,W] of a narrow-out conv with weight w [C,K,R,S] -> dx NHWC16."""
+    n, c, h, wd = x.shape
+    if not flip:
+        k, _, r, s = w.shape
+        ho, wo = h + 2 * pad - r + 1, wd + 2 * pad - s + 1
+    else:
+        _, k, r, s = w.shape
+        ho, wo = h - 2 * pad + r - 1, wd - 2 * pad + s - 1
+    if y is None:
+        y = torch.empty((n, ho, wo, k), dtype=dtype, device=x.device)
+    if ws is None:
+        ws = _narrow_ws(c, k, r, s, x.device)
+    call("ghnd_conv_narrow_in", ptr(x), ptr(pre), int(bool(pre_relu)), ptr(w), int(bool(flip)), ptr(y),
+         fmt_of(y.dtype), n, h, wd, c, k, r, s, pad, ptr(ws[0]), ws[1], stream_ptr())
+    _count(2)
+    return y
+
+
+def conv_narrow_out_dgrad(dy, w, pad, H, W, dx=None, ws=None):
+    """dgrad of a narrow-in conv (x planar [N,C,H,W] -> y NHWC [N,Ho,Wo,K], w [K,C,R,S]):
+    dy NHWC16 -> dx planar fp32 [N,C,H,W]."""
+    n = dy.shape[0]
+    k, c, r, s = w.shape
+    if dx is None:
+        dx = torch.empty((n, c, H, W), dtype=torch.float32, device=dy.device)
+    if ws is None:
+        ws = _narrow_ws(c, k, r, s, dy.device)
+    call("ghnd_conv_narrow_out_dgrad", ptr(dy), fmt_of(dy.dtype), ptr(w), ptr(dx), n, H, W, c, k, r, s, pad,
+         ptr(ws[0]), ws[1], stream_ptr())
+    _count(2)
+    return dx
+
+
+def wgrad_narrow(a, b, dw, a_is_output, R, S, pad, pre=None, pre_relu=False, ws=None):
+    """a planar fp32 [N,Ca,Ha,Wa], b NHWC16 [N,Hb,Wb,Cb] -> dw OIHW fp32 (see ghnd_b200.h)."""
+    n, ca, ha, wa = a.shape
+    _, hb, wb, cb = b.shape
+    nbytes = _lib.load().ghnd_wgrad_narrow_workspace_bytes(ca, cb, R, S)
+    if ws is None:
+        ws = _ws(nbytes, a.device)
+    call("ghnd_wgrad_narrow", ptr(a), ptr(pre), int(bool(pre_relu)), ptr(b), fmt_of(b.dtype), ptr(dw),
+         int(bool(a_is_output)), n, ha, wa, ca, hb, wb, cb, R, S, pad, ptr(ws), nbytes, stream_ptr())
+    _count(1 + (ca + 2) // 3)
+    return dw
+
+
+# ------------------------------------------------------------------------------------------------
+# stem helpers
+# ------------------------------------------------------------------------------------------------
+def maxpool3x3s2(x, y=None, argmax=None):
+    n, h, w, c = x.shape
+    ho, wo = (h + 1) // 2, (w + 1) // 2
+    if y is None:
+        y = torch.empty((n, ho, wo, c), dtype=x.dtype, device=x.device)
+    call("ghnd_maxpool3x3s2", ptr(x), ptr(y), ptr(argmax), fmt_of(x.dtype), n, h, w, c, stream_ptr())
+    _count()
+    return y
+
+
+def maxpool3x3s2_bwd(x, argmax, dy, dx):
+    n, h, w, c = x.shape
+    call("ghnd_maxpool3x3s2_bwd", ptr(x), fmt_of(x.dtype), ptr(argmax), ptr(dy), fmt_of(dy.dtype), ptr(dx),
+         fmt_of(dx.dtype), n, h, w, c, stream_ptr())
+    _count()
+    return dx
+
+
+def stem_wgrad(x_packed, g, scale, dw, N, Hp, Wp, ws=None):
+    nbytes = _lib.load().ghnd_stem_wgrad_workspace_bytes()
+    if ws is None:
+        ws = _ws(nbytes, g.device)
+    call("ghnd_stem_wgrad", ptr(x_packed), fmt_of(x_packed.dtype), ptr(g), fmt_of(g.dtype), ptr(scale),
+         ptr(dw), N, Hp, Wp, ptr(ws), nbytes, stream_ptr())
+    _count(2)
+    return dw
+
+
+# ------------------------------------------------------------------------------------------------
+# BatchNorm (training) and Adam
+# ------------------------------------------------------------------------------------------------
+def bn_stats(x, sums, planar=False):
+    if planar:
+        n, c, h, w = x.shape
+        call("ghnd_bn_stats", ptr(x), 0, 1, n, h * w, c, ptr(sums), stream_ptr())
+    else:
+        n, h, w, c = x.shape
+        call("ghnd_bn_stats", ptr(x), fmt_of(x.dtype), 0, n, h * w, c, ptr(sums), stream_ptr())
+    _count()
+    return sums
+
+
+def bn_finalize(sums, count, C, gamma, beta, eps, momentum, running_mean, running_var, nbt, scale_shift,
+                mean_invstd):
+    call("ghnd_bn_finalize", ptr(sums), int(count), C, ptr(gamma), ptr(beta), float(eps), float(momentum),
+         ptr(running_mean), ptr(running_var), ptr(nbt), ptr(scale_shift), ptr(mean_invstd), stream_ptr())
+    _count()
+
+
+def bn_eval_params(C, gamma, beta, running_mean, running_var, eps, scale_shift):
+    call("ghnd_bn_eval_params", C, ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var), float(eps),
+         ptr(scale_shift), stream_ptr())
+    _count()
+    return scale_shift
+
+
+def bn_apply(x, y, scale_shift, relu, y2=None):
+    n, h, w, c = x.shape
+    call("ghnd_bn_apply", ptr(x), fmt_of(x.dtype), ptr(y), fmt_of(y.dtype), ptr(y2),
+         fmt_of(y2.dtype) if y2 is not None else 0, n * h * w, c, ptr(scale_shift), int(bool(relu)),
+         stream_ptr())
+    _count()
+    return y
+
+
+def convert16(x, y):
+    call("ghnd_convert16", ptr(x), fmt_of(x.dtype), ptr(y), fmt_of(y.dtype), x.numel(), stream_ptr())
+    _count()
+    return y
+
+
+def bn_bwd_reduce(dy, x, scale_shift, mean_invstd, relu, sums, planar=False):
+    if planar:
+        n, c, h, w = x.shape
+        call("ghnd_bn_bwd_reduce", ptr(dy), 0, ptr(x), 0, 1, n, h * w, c, ptr(scale_shift), ptr(mean_invstd),
+             int(bool(relu)), ptr(sums), stream_ptr())
+    else:
+        n, h, w, c = x.shape
+        call("ghnd_bn_bwd_reduce", ptr(dy), fmt_of(dy.dtype), ptr(x), fmt_of(x.dtype), 0, n, h * w, c,
+             ptr(scale_shift), ptr(mean_invstd), int(bool(relu)), ptr(sums), stream_ptr())
+    _count()
+    return sums
+
+
+def bn_bwd_apply(dy, x, dx, gamma, scale_shift, mean_invstd, relu, sums, dgamma, dbeta, planar=False):
+    if planar:
+        n, c, h, w = x.shape
+        call("ghnd_bn_bwd_apply", ptr(dy), 0, ptr(x), 0, ptr(dx), 0, 1, n, h * w, c, ptr(gamma),
+             ptr(scale_shift), ptr(mean_invstd), int(bool(relu)), ptr(sums), ptr(dgamma), ptr(dbeta),
+             stream_ptr())
+    else:
+        n, h, w, c = x.shape
+        call("ghnd_bn_bwd_apply", ptr(dy), fmt_of(dy.dtype), ptr(x), fmt_of(x.dtype), ptr(dx),
+             fmt_of(dx.dtype), 0, n, h * w, c, ptr(gamma), ptr(scale_shift), ptr(mean_invstd),
+             int(bool(relu)), ptr(sums), ptr(dgamma), ptr(dbeta), stream_ptr())
+    _count(2)
+    return dx
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, grad_scale, step):
+    call("ghnd_adam_step", ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), param.numel(), float(lr),
+         float(beta1), float(beta2), float(eps), float(weight_decay), float(grad_scale), int(step),
+         stream_ptr())
+    _count()

@@ -244,9 +244,14 @@ int ghnd_bn_finalize(const double* sums, int64_t count, int C, const float* gamm
 /* eval mode: scale_shift from running stats */
 int ghnd_bn_eval_params(int C, const float* gamma, const float* beta, const float* running_mean,
                         const float* running_var, float eps, float* scale_shift, void* stream);
-/* y = x*scale+shift (optionally relu); NHWC 16-bit in/out */
-int ghnd_bn_apply(const void* x, int x_fmt, void* y, int y_fmt, int64_t npix, int C,
-                  const float* scale_shift, int relu, void* stream);
+/* y = x*scale+shift (optionally relu); NHWC 16-bit in/out.  y2 (nullable) receives the same values
+ * in a second 16-bit format: forward tensors are fp16, but the weight-gradient MMA needs its two
+ * operands in one format, so the student's activations are also kept as bf16 next to the bf16
+ * gradients. */
+int ghnd_bn_apply(const void* x, int x_fmt, void* y, int y_fmt, void* y2, int y2_fmt, int64_t npix,
+                  int C, const float* scale_shift, int relu, void* stream);
+/* 16-bit format conversion (fp16 <-> bf16), n elements (multiple of 8) */
+int ghnd_convert16(const void* x, int x_fmt, void* y, int y_fmt, int64_t n, void* stream);
 /* backward, pass 1: sums[2C] = { sum g', sum g'*xhat } with g' = dy * (relu ? (x*scale+shift>0):1) */
 int ghnd_bn_bwd_reduce(const void* dy, int dy_fmt, const void* x, int x_fmt, int planar, int N,
                        int64_t hw, int C, const float* scale_shift, const float* mean_invstd,
@@ -265,8 +270,8 @@ int ghnd_bn_bwd_apply(const void* dy, int dy_fmt, const void* x, int x_fmt, void
  * step is the 1-based step count used for bias correction.
  * ------------------------------------------------------------------------------------------ */
 int ghnd_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
-                   float lr, float beta1, float beta2, float eps, float weight_decay,
-                   float grad_scale, int step, void* stream);
+                   double lr, double beta1, double beta2, double eps, double weight_decay,
+                   double grad_scale, int step, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,426 @@
+"""GPU parity tests of the individual C-ABI kernels against the CPU oracle / plain torch fp32
+(run on a B200 with `pytest -m gpu`).  Tolerances are stated per test."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import ghnd_oracle as O  # checker only
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from hnd_ghnd_object_detectors_b200 import _lib, ops
+    _lib.check(_lib.load().ghnd_device_check(), "device_check")
+    return ops
+
+
+def rel(a, b):
+    a = a.double().cpu()
+    b = b.double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def r16(x, dtype):
+    return x.to(dtype).float()
+
+
+# ---------------------------------------------------------------------------------------------
+# quantizer: bit exact
+# ---------------------------------------------------------------------------------------------
+def test_quantizer_golden_bit_exact(ops, golden_dir):
+    from tests.golden.make_golden import quantizer_cases
+    g = np.load(os.path.join(golden_dir, "quantizer.npz"))
+    for name, x in quantizer_cases().items():
+        xt = torch.from_numpy(x).cuda()
+        q, qp = ops.quantize_u8(xt, 8)
+        qp = qp.cpu()
+        assert np.array_equal(q.cpu().numpy(), g[name + ".q"]), name
+        scale = qp[0:1].view(torch.float32).item()
+        assert np.float32(scale) == g[name + ".scale"], name
+        assert int(qp[1]) == int(g[name + ".zp"]), name
+        deq = ops.dequantize_u8(q, qp.cuda())
+        assert np.array_equal(deq.cpu().numpy(), g[name + ".deq"], equal_nan=True), name
+
+
+@pytest.mark.parametrize("shape", [(1, 3, 204, 340), (4, 3, 204, 340), (64, 3, 204, 340), (1, 3, 7, 13)])
+def test_quantizer_vs_oracle_and_torch_cuda(ops, shape):
+    from hnd_ghnd_object_detectors_b200 import _lib
+    torch.manual_seed(shape[0])
+    x = (torch.randn(shape) * 2.5 + 0.3)
+    xc = x.cuda()
+    q, qp = ops.quantize_u8(xc, 8, _lib.QSCALE_DIV)
+    qo, so, zo = O.quantize_tensor_np(x.numpy(), 8, "div")
+    assert np.array_equal(q.cpu().numpy(), qo)
+    assert np.float32(qp[0:1].view(torch.float32).item()) == so and int(qp[1]) == zo
+    # the reference formula executed by torch on this GPU (tensor / python scalar -> reciprocal)
+    q2, qp2 = ops.quantize_u8(xc, 8, _lib.QSCALE_RECIP)
+    mn, mx = xc.min(), xc.max()
+    scale = (mx - mn) / 255.0
+    izp = 0.0 - mn / scale
+    zp = 0 if izp < 0 else 255 if izp > 255 else int(izp)
+    ref = (zp + xc / scale).clamp(0, 255).round().byte()
+    assert qp2[0:1].view(torch.float32).item() == scale.item()
+    assert int(qp2[1]) == zp
+    assert torch.equal(q2, ref)
+    # round trip property: the zero-point is truncated, so the grid is shifted by < 1 step and the
+    # extremes clamp: |dequant(quant(x)) - x| <= scale (+ulp)
+    deq = ops.dequantize_u8(q, qp)
+    assert float((deq - xc).abs().max()) <= 1.0001 * float(so) + 1e-6
+    assert torch.equal(deq, float(so) * (q.float() - zo))
+
+
+def test_quantizer_errors(ops):
+    from hnd_ghnd_object_detectors_b200 import _lib
+    with pytest.raises(_lib.GhndError):
+        ops.quantize_u8(torch.empty(0, device="cuda"))
+    with pytest.raises(_lib.GhndError):
+        ops.quantize_u8(torch.zeros(4))  # CPU tensor: no fallback
+
+
+# ---------------------------------------------------------------------------------------------
+# SSE loss forward + backward; tolerance: loss rel 1e-5 (fp32 partials, fp64 finalize)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_sse_loss(ops, dtype):
+    torch.manual_seed(0)
+    shapes = [(2, 25, 42, 256), (2, 13, 21, 512), (1, 7, 11, 1024), (1, 4, 6, 2048)]
+    levels, refs = [], []
+    for i, s in enumerate(shapes):
+        t = (torch.randn(s) * 3).to(dtype).cuda()
+        st = (torch.randn(s) * 3).relu().to(dtype).cuda()
+        g = torch.empty(s, dtype=torch.bfloat16, device="cuda")
+        levels.append((t, st, g, 1.0 + 0.5 * i, i == 3))
+        refs.append((t.double(), st.double(), 1.0 + 0.5 * i))
+    out = ops.sse_fwd_bwd(levels).cpu().double()
+    tot = 0.0
+    for i, (t, s, f) in enumerate(refs):
+        term = float(((t - s) ** 2).sum() * f)
+        tot += term
+        assert abs(float(out[1 + i]) - term) <= 1e-5 * term
+        gref = 2 * f * (s - t)
+        if i == 3:
+            gref = gref * (s > 0)
+        assert rel(levels[i][2].float(), gref.float().bfloat16().float()) < 1e-6
+    assert abs(float(out[0]) - tot) <= 1e-5 * tot
+
+
+def test_layout_roundtrip(ops):
+    x = torch.randn(2, 70, 9, 13).cuda()
+    y = ops.to_nhwc16(x, torch.float16)
+    assert torch.equal(y, x.permute(0, 2, 3, 1).contiguous().half())
+    assert torch.equal(ops.to_nchw_f32(y), x.half().float())
+
+
+# ---------------------------------------------------------------------------------------------
+# tcgen05 conv forward / dgrad.  Inputs are pre-rounded to the 16-bit format so the only error
+# is accumulation order + output rounding: rel L2 <= 1e-3 (fp16 out) / 4e-3 (bf16 out).
+# ---------------------------------------------------------------------------------------------
+CONV_CASES = [
+    # N, H, W, C, K, R, stride, pad
+    (2, 25, 42, 64, 256, 1, 1, 0),
+    (1, 33, 29, 128, 64, 1, 1, 0),
+    (2, 20, 34, 64, 64, 2, 1, 1),
+    (2, 21, 35, 64, 256, 2, 1, 1),
+    (1, 22, 36, 256, 64, 2, 1, 1),
+    (2, 23, 37, 64, 128, 2, 1, 0),
+    (1, 22, 36, 128, 256, 2, 1, 0),
+    (2, 25, 42, 64, 64, 3, 1, 1),
+    (2, 50, 84, 128, 128, 3, 2, 1),
+    (2, 25, 42, 256, 256, 3, 2, 1),
+    (2, 50, 84, 256, 512, 1, 2, 0),
+    (1, 25, 41, 512, 1024, 1, 2, 0),
+    (1, 13, 21, 512, 2048, 1, 1, 0),
+]
+
+
+def _conv_inputs(N, H, W, C, K, R, dtype, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    x = r16(torch.randn(N, C, H, W, generator=g), dtype)
+    w = r16(torch.randn(K, C, R, R, generator=g) * (2.0 / (C * R * R)) ** 0.5, dtype)
+    return x, w
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_conv_fwd(ops, case, dtype):
+    from hnd_ghnd_object_detectors_b200 import _lib
+    N, H, W, C, K, R, stride, pad = case
+    x, w = _conv_inputs(N, H, W, C, K, R, dtype)
+    bias = torch.randn(K)
+    ref = F.conv2d(x, w, bias, stride, pad)
+    res = r16(torch.randn(ref.shape), dtype)
+    ref = F.relu(ref + res)
+    xd = ops.to_nhwc16(x.cuda(), dtype)
+    wd = ops.pack_weight(w.cuda(), None, False, dtype)
+    resd = ops.to_nhwc16(res.cuda(), dtype)
+    y = torch.zeros((N, ref.shape[2], ref.shape[3], K), dtype=dtype, device="cuda")
+    plan = ops.ConvPlan(_lib.CONV_FWD, N, H, W, C, K, R, R, stride, pad, xd, wd, y, bias=bias.cuda(),
+                        residual=resd, relu=True)
+    plan.run()
+    torch.cuda.synchronize()
+    got = ops.to_nchw_f32(y).cpu()
+    tol = 1e-3 if dtype == torch.float16 else 4e-3
+    assert rel(got, ref) < tol, rel(got, ref)
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_dgrad(ops, case):
+    from hnd_ghnd_object_detectors_b200 import _lib
+    N, H, W, C, K, R, stride, pad = case
+    dtype = torch.bfloat16
+    x, w = _conv_inputs(N, H, W, C, K, R, dtype, seed=1)
+    x.requires_grad_(True)
+    y = F.conv2d(x, w, None, stride, pad)
+    dy = r16(torch.randn(y.shape), dtype)
+    (dx_ref,) = torch.autograd.grad(y, x, dy)
+    mask_src = r16(torch.randn(x.shape), dtype)
+    res = r16(torch.randn(x.shape), dtype)
+    ref = (dx_ref + res) * (mask_src > 0)
+    dyd = ops.to_nhwc16(dy.cuda(), dtype)
+    wt = ops.pack_weight(w.cuda(), None, True, dtype)
+    dx = torch.zeros((N, H, W, C), dtype=dtype, device="cuda")
+    one_by_one_s2 = (R == 1 and stride == 2)
+    if one_by_one_s2:
+        # only the even lattice receives gradient: exercised through accumulate (as the engine does)
+        base = r16(torch.randn(x.shape), dtype)
+        dx.copy_(ops.to_nhwc16(base.cuda(), dtype))
+        plan = ops.ConvPlan(_lib.CONV_DGRAD, N, H, W, C, K, R, R, stride, pad, dyd, wt, dx,
+                            mask=ops.to_nhwc16(mask_src.cuda(), dtype), accumulate=True)
+        ref = base + dx_ref * (mask_src > 0)
+    else:
+        plan = ops.ConvPlan(_lib.CONV_DGRAD, N, H, W, C, K, R, R, stride, pad, dyd, wt, dx,
+                            residual=ops.to_nhwc16(res.cuda(), dtype),
+                            mask=ops.to_nhwc16(mask_src.cuda(), dtype))
+    plan.run()
+    torch.cuda.synchronize()
+    got = ops.to_nchw_f32(dx).cpu()
+    assert rel(got, ref) < 4e-3, rel(got, ref)
+
+
+def test_conv_mixed_formats_rejected(ops):
+    """tcgen05 kind::f16 raises an illegal-instruction fault for f16 x bf16 operands on sm_100a
+    (measured in round 1), so the boundary refuses mixed formats on the host."""
+    from hnd_ghnd_object_detectors_b200 import _lib
+    xd = torch.zeros((1, 8, 8, 64), dtype=torch.bfloat16, device="cuda")
+    wd = torch.zeros((64, 1, 1, 64), dtype=torch.float16, device="cuda")
+    y = torch.zeros((1, 8, 8, 64), dtype=torch.float16, device="cuda")
+    with pytest.raises(_lib.GhndError, match="share one 16-bit format"):
+        ops.ConvPlan(_lib.CONV_FWD, 1, 8, 8, 64, 64, 1, 1, 1, 0, xd, wd, y)
+
+
+# ---------------------------------------------------------------------------------------------
+# tcgen05 weight gradient (MN-major operands); fp32 output, rel L2 <= 2e-3
+# ---------------------------------------------------------------------------------------------
+WGRAD_CASES = [
+    # N, H, W, C, K, R, pad   (the six wide student convs at reduced spatial size)
+    (2, 24, 40, 64, 64, 2, 1),
+    (2, 25, 41, 64, 256, 2, 1),
+    (1, 26, 42, 256, 64, 2, 1),
+    (2, 27, 43, 64, 128, 2, 0),
+    (1, 26, 42, 128, 256, 2, 0),
+    (2, 25, 41, 256, 256, 2, 0),
+]
+
+
+@pytest.mark.parametrize("case", WGRAD_CASES)
+@pytest.mark.parametrize("xdtype", [torch.bfloat16, torch.float16])
+def test_wgrad(ops, case, xdtype):
+    N, H, W, C, K, R, pad = case
+    g = torch.Generator().manual_seed(5)
+    x = r16(torch.randn(N, C, H, W, generator=g), xdtype)
+    w = torch.zeros(K, C, R, R, requires_grad=True)
+    y = F.conv2d(x, w, None, 1, pad)
+    dy = r16(torch.randn(y.shape, generator=g), xdtype)
+    (dw_ref,) = torch.autograd.grad(y, w, dy)
+    xd = ops.to_nhwc16(x.cuda(), xdtype)
+    dyd = ops.to_nhwc16(dy.cuda(), xdtype)
+    dw = torch.empty(K, R, R, C, dtype=torch.float32, device="cuda")
+    ops.WgradPlan(N, H, W, C, K, R, R, pad, xd, dyd, dw).run()
+    out = torch.empty(K, C, R, R, dtype=torch.float32, device="cuda")
+    ops.unpack_wgrad(dw, out)
+    torch.cuda.synchronize()
+    assert rel(out.cpu(), dw_ref) < 2e-3, rel(out.cpu(), dw_ref)
+
+
+# ---------------------------------------------------------------------------------------------
+# BatchNorm (training) forward / backward vs torch fp32 autograd; rel L2 <= 2e-3 (16-bit I/O)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("C,relu", [(64, False), (256, True), (128, True)])
+def test_bn_train_fwd_bwd(ops, C, relu):
+    torch.manual_seed(C)
+    N, H, W = 2, 21, 35
+    dt = torch.float16
+    x = r16(torch.randn(N, C, H, W) * 2 + 0.5, dt)
+    gamma = torch.rand(C) + 0.5
+    beta = torch.randn(C) * 0.1
+    rm, rv = torch.zeros(C), torch.ones(C)
+    xr = x.clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    y = F.batch_norm(xr, rm, rv, gr, br, True, 0.1, 1e-5)
+    if relu:
+        y = F.relu(y)
+    dy = r16(torch.randn(y.shape), torch.bfloat16)
+    dx_ref, dg_ref, db_ref = torch.autograd.grad(y, (xr, gr, br), dy)
+
+    xd = ops.to_nhwc16(x.cuda(), dt)
+    sums = torch.empty(2 * C, dtype=torch.float64, device="cuda")
+    ss = torch.empty(2 * C, device="cuda")
+    mi = torch.empty(2 * C, device="cuda")
+    rmd, rvd = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    nbt = torch.zeros((), dtype=torch.long, device="cuda")
+    ops.bn_stats(xd, sums)
+    ops.bn_finalize(sums, N * H * W, C, gamma.cuda(), beta.cuda(), 1e-5, 0.1, rmd, rvd, nbt, ss, mi)
+    yd = torch.empty_like(xd)
+    yd2 = torch.empty(xd.shape, dtype=torch.bfloat16, device="cuda")
+    ops.bn_apply(xd, yd, ss, relu, y2=yd2)
+    assert rel(ops.to_nchw_f32(yd).cpu(), y.detach()) < 1e-3
+    assert rel(yd2.float(), yd.float()) < 4e-3
+    back = torch.empty_like(yd)
+    assert rel(ops.convert16(yd2, back).float(), yd2.float()) < 1e-3
+    assert rel(rmd.cpu(), rm) < 1e-5 and rel(rvd.cpu(), rv) < 1e-5 and int(nbt) == 1
+    dyd = ops.to_nhwc16(dy.cuda(), torch.bfloat16)
+    dxd = torch.empty((N, H, W, C), dtype=torch.bfloat16, device="cuda")
+    dg, db = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
+    ops.bn_bwd_reduce(dyd, xd, ss, mi, relu, sums)
+    ops.bn_bwd_apply(dyd, xd, dxd, gamma.cuda(), ss, mi, relu, sums, dg, db)
+    assert rel(ops.to_nchw_f32(dxd).cpu(), dx_ref) < 4e-3
+    assert rel(dg.cpu(), dg_ref) < 1e-3 and rel(db.cpu(), db_ref) < 1e-3
+
+
+def test_bn_planar(ops):
+    torch.manual_seed(1)
+    N, C, H, W = 2, 3, 28, 36
+    x = torch.randn(N, C, H, W) * 3 - 1
+    gamma, beta = torch.rand(C) + 0.5, torch.randn(C) * 0.1
+    xr = x.clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    y = F.relu(F.batch_norm(xr, None, None, gr, br, True, 0.1, 1e-5))
+    dy = torch.randn(y.shape)
+    dx_ref, dg_ref, db_ref = torch.autograd.grad(y, (xr, gr, br), dy)
+    xd = x.cuda()
+    sums = torch.empty(2 * C, dtype=torch.float64, device="cuda")
+    ss, mi = torch.empty(2 * C, device="cuda"), torch.empty(2 * C, device="cuda")
+    ops.bn_stats(xd, sums, planar=True)
+    ops.bn_finalize(sums, N * H * W, C, gamma.cuda(), beta.cuda(), 1e-5, 0.1, None, None, None, ss, mi)
+    dxd = torch.empty_like(xd)
+    dg, db = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
+    ops.bn_bwd_reduce(dy.cuda(), xd, ss, mi, True, sums, planar=True)
+    ops.bn_bwd_apply(dy.cuda(), xd, dxd, gamma.cuda(), ss, mi, True, sums, dg, db, planar=True)
+    assert rel(dxd.cpu(), dx_ref) < 1e-4
+    assert rel(dg.cpu(), dg_ref) < 1e-4 and rel(db.cpu(), db_ref) < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------
+# narrow convs (enc7 / dec2) forward, dgrad, wgrad
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("bch", [3, 6])
+def test_narrow_convs(ops, bch):
+    torch.manual_seed(bch)
+    dt = torch.float16
+    N, H, W = 2, 23, 31
+    # enc7: 64 -> bch, k2 p1
+    x = r16(torch.randn(N, 64, H, W), dt).requires_grad_(True)
+    w7 = (torch.randn(bch, 64, 2, 2) * 0.1).requires_grad_(True)
+    z = F.conv2d(x, w7, None, 1, 1)
+    dz = torch.randn(z.shape)
+    dx_ref, dw7_ref = torch.autograd.grad(z, (x, w7), dz)
+    xd = ops.to_nhwc16(x.detach().cuda(), dt)
+    zd = ops.conv_narrow_out(xd, w7.detach().cuda(), 1)
+    assert rel(zd.cpu(), z.detach()) < 1e-5
+    dxd = ops.conv_narrow_in(dz.cuda(), w7.detach().cuda(), 1, flip=True, dtype=torch.bfloat16)
+    assert rel(ops.to_nchw_f32(dxd).cpu(), dx_ref) < 4e-3
+    dw7 = torch.empty(bch, 64, 2, 2, device="cuda")
+    ops.wgrad_narrow(dz.cuda(), xd, dw7, True, 2, 2, 1)
+    assert rel(dw7.cpu(), dw7_ref) < 1e-4
+    # dec2: relu(bn0(z)) -> 64, k2 p0
+    zin = torch.randn(N, bch, H + 1, W + 1).requires_grad_(True)
+    sc, sh = torch.rand(bch) + 0.5, torch.randn(bch) * 0.3
+    a = F.relu(zin * sc[None, :, None, None] + sh[None, :, None, None])
+    w2 = (torch.randn(64, bch, 2, 2) * 0.2).requires_grad_(True)
+    y = F.conv2d(a, w2)
+    dy = r16(torch.randn(y.shape), torch.bfloat16)
+    da_ref, dw2_ref = torch.autograd.grad(y, (a, w2), dy)
+    pre = torch.cat([sc, sh]).cuda()
+    yd = ops.conv_narrow_in(zin.detach().cuda(), w2.detach().cuda(), 0, pre=pre, pre_relu=True, dtype=dt)
+    assert rel(ops.to_nchw_f32(yd).cpu(), y.detach()) < 1e-3
+    dyd = ops.to_nhwc16(dy.cuda(), torch.bfloat16)
+    dad = ops.conv_narrow_out_dgrad(dyd, w2.detach().cuda(), 0, H + 1, W + 1)
+    assert rel(dad.cpu(), da_ref) < 1e-5
+    dw2 = torch.empty(64, bch, 2, 2, device="cuda")
+    ops.wgrad_narrow(zin.detach().cuda(), dyd, dw2, False, 2, 2, 0, pre=pre, pre_relu=True)
+    assert rel(dw2.cpu(), dw2_ref) < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------
+# stem: pack image -> conv1+FBN+ReLU (tcgen05) -> maxpool ; backward: pool/relu bwd -> conv1 wgrad
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+def test_stem(ops, dt):
+    torch.manual_seed(7)
+    imgs = [torch.rand(3, 96, 128), torch.rand(3, 80, 120)]
+    Hp, Wp = 96, 128
+    xb = O.transform_batch(imgs)
+    assert tuple(xb.shape) == (2, 3, Hp, Wp)
+    w = (torch.randn(64, 3, 7, 7) * 0.1).requires_grad_(True)
+    scale, bias = torch.rand(64) + 0.5, torch.randn(64) * 0.2
+    xq = r16(xb, dt)
+    wq = r16(w.detach() * scale[:, None, None, None], dt)
+    conv = F.relu(F.conv2d(xq, wq, bias, 2, 3))
+    pooled = F.max_pool2d(conv, 3, 2, 1)
+
+    packed = torch.empty((2, Hp + 6, Wp + 8, 4), dtype=dt, device="cuda")
+    for i, im in enumerate(imgs):
+        ops.stem_pack_image(im.cuda(), packed, i, Hp, Wp, O.IMAGE_MEAN, O.IMAGE_STD)
+    got_in = packed[:, 3:3 + Hp, 3:3 + Wp, :3].permute(0, 3, 1, 2).float().cpu()
+    assert torch.equal(got_in, xq)
+    assert float(packed[:, :3].abs().max()) == 0 and float(packed[..., 3].abs().max()) == 0
+    wp = ops.stem_pack_weight(w.detach().cuda(), scale.cuda(), dt)
+    y = torch.zeros((2, Hp // 2, Wp // 2, 64), dtype=dt, device="cuda")
+    ops.StemPlan(packed, wp, bias.cuda(), y, 2, Hp, Wp).run()
+    torch.cuda.synchronize()
+    tol = 1e-3 if dt == torch.float16 else 4e-3
+    assert rel(ops.to_nchw_f32(y).cpu(), conv) < tol
+    am = torch.empty((2, Hp // 4, Wp // 4, 64), dtype=torch.uint8, device="cuda")
+    p = ops.maxpool3x3s2(y, argmax=am)
+    ref_pool = F.max_pool2d(ops.to_nchw_f32(y), 3, 2, 1)
+    assert torch.equal(ops.to_nchw_f32(p), ref_pool)
+    assert rel(ops.to_nchw_f32(p).cpu(), pooled) < tol
+
+    # backward through pool + relu, then conv1 wgrad.  The pooling argmax is taken from the
+    # device's own conv output (near-ties differ between fp32 and 16-bit activations), the rest of
+    # the reference is fp32 autograd: rel L2 <= 2e-3
+    yc = ops.to_nchw_f32(y).cpu().requires_grad_(True)
+    out = F.max_pool2d(yc, 3, 2, 1)
+    dyp = r16(torch.randn(out.shape), torch.bfloat16)
+    (g_y,) = torch.autograd.grad(out, yc, dyp)
+    g_pre = r16(g_y * (yc.detach() > 0), torch.bfloat16)
+    dw_ref = torch.nn.grad.conv2d_weight(xq, w.shape, g_pre, stride=2, padding=3) * scale[:, None, None, None]
+    dyd = ops.to_nhwc16(dyp.cuda(), torch.bfloat16)
+    gconv = torch.empty((2, Hp // 2, Wp // 2, 64), dtype=torch.bfloat16, device="cuda")
+    ops.maxpool3x3s2_bwd(y, am, dyd, gconv)
+    dw = torch.empty(64, 3, 7, 7, device="cuda")
+    ops.stem_wgrad(packed, gconv, scale.cuda(), dw, 2, Hp, Wp)
+    torch.cuda.synchronize()
+    assert rel(dw.cpu(), dw_ref) < 2e-3, rel(dw.cpu(), dw_ref)
+
+
+def test_adam(ops):
+    torch.manual_seed(0)
+    n = 586566
+    p = torch.randn(n)
+    g = torch.randn(n) * 100
+    m, v = torch.zeros(n), torch.zeros(n)
+    pd, md, vd = p.cuda(), m.cuda(), v.cuda()
+    for step in (1, 2, 3):
+        gs = g * step
+        p, m, v = O.adam_step(p, gs, m, v, step)
+        ops.adam_step(pd, gs.cuda(), md, vd, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1.0, step)
+    assert rel(pd.cpu(), p) < 1e-6
+    assert rel(md.cpu(), m) < 1e-6 and rel(vd.cpu(), v) < 1e-6
