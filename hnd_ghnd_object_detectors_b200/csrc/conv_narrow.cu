@@ -173,7 +173,11 @@ __global__ void __launch_bounds__(256)
       }
     }
   }
-  // fold the pixel lanes of the warp that share a channel group, then one atomic per value
+  // fold the pixel lanes of the warp that share a channel group, then the warps of the block in
+  // shared memory, then ONE global atomic per value and block
+  __shared__ float s_acc[3 * kNarrowMaxTaps * 64];
+  for (int i = threadIdx.x; i < 3 * kNarrowMaxTaps * 64; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
 #pragma unroll
   for (int c = 0; c < 3; ++c)
 #pragma unroll
@@ -182,9 +186,19 @@ __global__ void __launch_bounds__(256)
       for (int e = 0; e < 8; ++e) {
         float v = acc[c][t][e];
         for (int o = 16; o >= lanes; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if ((threadIdx.x & 31) < lanes && t < taps.n_taps && ca0 + c < Ca)
+        if ((threadIdx.x & 31) < lanes && Cb <= 64)
+          atomicAdd(&s_acc[(c * kNarrowMaxTaps + t) * 64 + cg * 8 + e], v);
+        else if ((threadIdx.x & 31) < lanes && t < taps.n_taps && ca0 + c < Ca)
           atomicAdd(accum + ((size_t)(ca0 + c) * taps.n_taps + t) * Cb + cg * 8 + e, v);
       }
+  __syncthreads();
+  if (Cb <= 64) {
+    for (int i = threadIdx.x; i < 3 * kNarrowMaxTaps * 64; i += blockDim.x) {
+      const int cb = i & 63, t = (i >> 6) % kNarrowMaxTaps, c = i / (64 * kNarrowMaxTaps);
+      if (cb < Cb && t < taps.n_taps && ca0 + c < Ca)
+        atomicAdd(accum + ((size_t)(ca0 + c) * taps.n_taps + t) * Cb + cb, s_acc[i]);
+    }
+  }
 }
 
 // accum[ca][tap][cb] -> OIHW dw

@@ -343,12 +343,28 @@ static int make_a_map(CUtensorMap* m, const void* base, int N, int H, int W, int
   return encode_tmap(m, 2, 4, const_cast<uint8_t*>(b), dims, str, box, 128);
 }
 
-static int pick_block_n(int cout, int m_tiles) {
+// Tile-N choice from a two-term cost model measured in round 1 (profiles/r1_launches.md): the
+// kernel is bound either by the L2->SM operand traffic (every tile streams its A and B stages,
+// ~8 TB/s aggregate) or by the tcgen05 issue rate (128xNx16 per N/2 cycles per SM, wave-quantised).
+static int pick_block_n(int cout, int m_tiles, int k_iters, int row_bytes) {
   const int sms = num_sms();
-  int bn = cout % 256 == 0 ? 256 : (cout % 128 == 0 ? 128 : 64);
-  // keep at least ~2 waves of tiles when the problem allows it
-  while (bn > 64 && (int64_t)m_tiles * (cout / bn) < 2 * sms) bn >>= 1;
-  return bn;
+  int best = 64;
+  double best_t = 1e30;
+  for (int bn = 256; bn >= 64; bn >>= 1) {
+    if (cout % bn != 0) continue;
+    const double tiles = (double)m_tiles * (cout / bn);
+    const double traffic = tiles * k_iters * (128.0 * row_bytes + (double)bn * row_bytes);
+    const double t_l2 = traffic / 8.0e12;
+    const double waves = (double)((int64_t)(tiles + sms - 1) / sms);
+    const double mma_cycles = k_iters * (row_bytes / 32) * (bn < 128 ? 48.0 : bn / 2.0);
+    const double t_mma = waves * mma_cycles / 1.8e9;
+    const double t = (t_l2 > t_mma ? t_l2 : t_mma) + 0.15 * (t_l2 < t_mma ? t_l2 : t_mma);
+    if (t < best_t) {
+      best_t = t;
+      best = bn;
+    }
+  }
+  return best;
 }
 
 static int finish_launch(ConvLaunch* L, const ghnd_conv_desc_t* d, int gemm_cin, int gemm_cout,
@@ -360,7 +376,7 @@ static int finish_launch(ConvLaunch* L, const ghnd_conv_desc_t* d, int gemm_cin,
   const int row_bytes = kblock * 2;
   p.a_bytes = kBlockM * row_bytes;
   const int m_tiles = p.n_img * p.tiles_h * p.tiles_w;
-  p.block_n = pick_block_n(gemm_cout, m_tiles);
+  p.block_n = pick_block_n(gemm_cout, m_tiles, p.n_taps * (gemm_cin / kblock), row_bytes);
   p.n_tiles_n = gemm_cout / p.block_n;
   p.total_tiles = m_tiles * p.n_tiles_n;
   p.stage_bytes = p.a_bytes + p.block_n * row_bytes;

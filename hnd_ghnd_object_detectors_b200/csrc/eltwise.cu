@@ -386,6 +386,18 @@ __global__ void __launch_bounds__(256)
                              const float* __restrict__ mean_invstd, int relu,
                              const double* __restrict__ sums) {
   const int C = C8 * 8;
+  // per-channel constants staged once per block (the fp64 -> fp32 means are computed here, not per
+  // element: the fp64 pipe of B200 is slow)
+  extern __shared__ float s_c[];  // [6][C]: scale, shift, mean, invstd, mean_g, mean_gx
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    s_c[c] = scale_shift[c];
+    s_c[C + c] = scale_shift[C + c];
+    s_c[2 * C + c] = mean_invstd[c];
+    s_c[3 * C + c] = mean_invstd[C + c];
+    s_c[4 * C + c] = (float)(sums[c] * inv_count);
+    s_c[5 * C + c] = (float)(sums[C + c] * inv_count);
+  }
+  __syncthreads();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
        i += (int64_t)gridDim.x * blockDim.x) {
     const int cg = (int)(i % C8);
@@ -402,11 +414,10 @@ __global__ void __launch_bounds__(256)
         const int c = cg * 8 + 2 * e + h;
         const float xv1 = h ? f.y : f.x;
         float gv = h ? g.y : g.x;
-        const float sc = __ldg(scale_shift + c), sf = __ldg(scale_shift + C + c);
+        const float sc = s_c[c], sf = s_c[C + c];
         if (relu && !(fmaf(xv1, sc, sf) > 0.f)) gv = 0.f;
-        const float xhat = (xv1 - __ldg(mean_invstd + c)) * __ldg(mean_invstd + C + c);
-        const float mg = (float)(sums[c] * inv_count), mgx = (float)(sums[C + c] * inv_count);
-        r[h] = sc * (gv - mg - xhat * mgx);  // sc = gamma*invstd
+        const float xhat = (xv1 - s_c[2 * C + c]) * s_c[3 * C + c];
+        r[h] = sc * (gv - s_c[4 * C + c] - xhat * s_c[5 * C + c]);  // sc = gamma*invstd
       }
       o[e] = pack2(r[0], r[1], dx_fmt);
     }
@@ -713,7 +724,7 @@ int ghnd_bn_bwd_apply(const void* dy, int dy_fmt, const void* x, int x_fmt, void
   } else {
     GHND_CHECK_ARG(fmt16(dy_fmt) && fmt16(x_fmt) && fmt16(dx_fmt), "bn_bwd_apply: bad format");
     const int64_t nvec = (int64_t)N * hw * (C / 8);
-    bn_bwd_apply_nhwc_kernel<<<grid_for(nvec, 256 * 2), 256, 0, st>>>(
+    bn_bwd_apply_nhwc_kernel<<<grid_for(nvec, 256 * 2), 256, 6 * C * sizeof(float), st>>>(
         (const uint4*)dy, dy_fmt, (const uint4*)x, x_fmt, (uint4*)dx, dx_fmt, nvec, C / 8, inv_count,
         gamma, scale_shift, mean_invstd, relu, sums);
   }

@@ -524,12 +524,17 @@ class GhndPlan(object):
     def capture(self):
         """Capture forward_backward() into a CUDA graph (buffers and plans are static)."""
         torch.cuda.synchronize()
+        # the warm-up run must not count as a training step: keep the BN running statistics
+        bufs = list(self.s_l1.layer1.buffers())
+        saved = [b.clone() for b in bufs]
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             self.forward_backward()  # warm-up outside capture (lazy module loading)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
+        for b, v in zip(bufs, saved):
+            b.copy_(v)
         before = ops.launches()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):

@@ -1,0 +1,32 @@
+"""One eager (un-graphed) GHND step at the bench workload between cudaProfilerStart/Stop, for
+`ncu --profile-from-start off`.  Usage: python scripts/profile_step.py [batch]"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import bench
+from hnd_ghnd_object_detectors_b200 import models, module_util
+from hnd_ghnd_object_detectors_b200.tool import DistillationBox
+
+batch = int(sys.argv[1]) if len(sys.argv) > 1 else bench.PER_GPU_BATCH
+dev = torch.device("cuda", 0)
+torch.manual_seed(0)
+teacher = models.get_model(bench.model_config(False), dev)
+student = models.get_model(bench.model_config(True), dev)
+student.load_state_dict(teacher.state_dict(), strict=False)
+module_util.freeze_module_params(teacher)
+for path in bench.model_config(True)["frozen_modules"]:
+    module_util.freeze_module_params(module_util.get_module(student, path))
+teacher.eval(); student.train()
+teacher.distill_backbone_only = student.distill_backbone_only = True
+box = DistillationBox(teacher, student, bench.criterion_config(), use_cuda_graph=False)
+images = [torch.rand(3, bench.IMG_H, bench.IMG_W, device=dev) for _ in range(batch)]
+targets = [{"boxes": torch.tensor([[10., 10., 100., 100.]], device=dev), "labels": torch.tensor([1], device=dev)}
+           for _ in range(batch)]
+box(images, targets)
+box(images, targets)
+torch.cuda.synchronize()
+torch.cuda.cudart().cudaProfilerStart()
+box(images, targets)
+torch.cuda.synchronize()
+torch.cuda.cudart().cudaProfilerStop()
+print("profiled one step")

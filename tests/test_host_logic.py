@@ -1,0 +1,162 @@
+"""CPU tests of the host-side mirror of the reference interface (no GPU, no compute kernels):
+names, registries, error behaviour, YAML/JSON config handling, state_dict compatibility, parameter
+flattening and the world_size-2 gloo data-parallel plumbing."""
+import json
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _yaml(tmp_path, text):
+    p = tmp_path / "c.yaml"
+    p.write_text(text)
+    return str(p)
+
+
+def test_yaml_join_and_json_override(tmp_path):
+    from hnd_ghnd_object_detectors_b200 import main_util, yaml_util
+    cfg = yaml_util.load_yaml_file(_yaml(tmp_path, """
+dataset:
+    name: &n 'coco2017'
+    root: &r !join ['./resource/dataset/', *n]
+student_model:
+    bch: &bch 3
+    ckpt: !join ['./ckpt/', *n, '-b', *bch, 'ch.pt']
+train:
+    batch_size: 4
+    optimizer: {type: 'Adam', params: {lr: 0.001}}
+"""))
+    assert cfg["dataset"]["root"] == "./resource/dataset/coco2017"
+    assert cfg["student_model"]["ckpt"] == "./ckpt/coco2017-b3ch.pt"
+    main_util.overwrite_config(cfg, json.dumps({"train": {"batch_size": 8, "optimizer": {"params": {"lr": 0.01}}}}))
+    assert cfg["train"]["batch_size"] == 8 and cfg["train"]["optimizer"]["params"]["lr"] == 0.01
+    assert cfg["train"]["optimizer"]["type"] == "Adam"
+
+
+@pytest.mark.parametrize("model", ["faster_rcnn", "mask_rcnn", "keypoint_rcnn"])
+def test_state_dict_keys_match_reference(model, golden_dir):
+    """Released checkpoints must load with strict=True: same keys and shapes as the reference models
+    (tests/golden/state_dict_keys.json was dumped from the real reference classes)."""
+    from hnd_ghnd_object_detectors_b200 import rcnn
+    gold = json.load(open(os.path.join(golden_dir, "state_dict_keys.json")))[model]
+    params = {"num_classes": 2 if model == "keypoint_rcnn" else 91, "pretrained": False}
+    t = rcnn.get_model(model, backbone_config={"name": "resnet50", "params": {"pretrained": False, "freeze_layers": True}}, **params)
+    s = rcnn.get_model(model, backbone_config={"name": "custom_resnet50", "params": {
+        "pretrained": False, "freeze_layers": False,
+        "layer1": {"name": "Bottleneck4LargeResNet", "bottleneck_channel": 3}}}, **params)
+    for tag, m in (("teacher", t), ("student", s)):
+        got = {k: list(v.shape) for k, v in m.state_dict().items()}
+        assert got == gold[tag], (set(got) ^ set(gold[tag]))
+    names = [n for n, p in s.backbone.body.named_parameters()]
+    assert "layer1.encoder.encoder.7.weight" in names and "layer1.decoder.10.bias" in names
+
+
+def test_trainable_set_is_the_25_tensors():
+    from hnd_ghnd_object_detectors_b200 import module_util, rcnn
+    s = rcnn.get_model("faster_rcnn", False, backbone_config={"name": "custom_resnet50", "params": {
+        "pretrained": False, "freeze_layers": False,
+        "layer1": {"name": "Bottleneck4LargeResNet", "bottleneck_channel": 3}}})
+    for path in ["backbone.body.layer2", "backbone.body.layer3", "backbone.body.layer4", "backbone.fpn", "rpn", "roi_heads"]:
+        module_util.freeze_module_params(module_util.get_module(s, path))
+    names = module_util.get_updatable_param_names(s)
+    assert len(names) == 25 and sum(dict(s.named_parameters())[n].numel() for n in names) == 586566
+    assert module_util.get_module(s, "backbone.body.nope") is None  # prints and returns None
+
+
+def test_error_behaviour_matches_reference():
+    from hnd_ghnd_object_detectors_b200 import loss, models, rcnn, resnet_layer, transformer
+    with pytest.raises(ValueError):
+        loss.get_loss({"type": "nope", "params": {"org_loss_factor": 0}, "terms": {}})
+    with pytest.raises(KeyError):
+        transformer.get_bottleneck_transformer({"order": ["nope"], "components": {"nope": {"params": {}}}})
+    with pytest.raises(ValueError):
+        resnet_layer.get_mimic_layers("custom_resnet50", {"params": {"layer1": {"name": "X", "bottleneck_channel": 3}}})
+    with pytest.raises(ValueError):
+        models.get_model({"name": "yolo", "ckpt": "x", "params": {}}, "cpu")
+    with pytest.raises(KeyError):
+        rcnn.get_model_config("yolo")
+    tr = transformer.get_bottleneck_transformer({"order": ["quantizer", "dequantizer"], "components": {
+        "quantizer": {"params": {"num_bits": 8}}, "dequantizer": {"params": {"num_bits": 8}}}})
+    assert [type(t).__name__ for t in tr.transforms] == ["Quantizer", "Dequantizer"]
+    assert transformer.get_bottleneck_transformer({"order": [], "components": {}}) is None
+
+
+def test_no_cpu_fallback():
+    from hnd_ghnd_object_detectors_b200 import _lib, resnet_layer, tensor_util
+    with pytest.raises(_lib.GhndError):
+        tensor_util.quantize_tensor(torch.randn(1, 3, 4, 4))
+    layer = resnet_layer.Bottleneck4LargeResNet(3, None, None)
+    with pytest.raises(_lib.GhndError):
+        layer(torch.randn(1, 64, 8, 8))
+
+
+def test_flat_params_views():
+    from hnd_ghnd_object_detectors_b200.engine import FlatParams
+    ps = [("a", torch.nn.Parameter(torch.randn(3, 5))), ("b", torch.nn.Parameter(torch.randn(7))),
+          ("c", torch.nn.Parameter(torch.randn(2, 2), requires_grad=False))]
+    ref = {n: p.detach().clone() for n, p in ps}
+    flat = FlatParams(ps)
+    assert flat.names == ["a", "b"] and flat.total % 4 == 0
+    for n in flat.names:
+        assert torch.equal(flat.params[n].data, ref[n])
+    flat.flat.add_(1.0)
+    assert torch.equal(ps[0][1].data, ref["a"] + 1.0)  # parameters are views of the flat buffer
+    flat.grads["b"].fill_(2.0)
+    assert float(flat.grad.sum()) == 14.0
+
+
+def test_shard_indices_cover_all_items():
+    from hnd_ghnd_object_detectors_b200.parallel import shard_indices
+    for n, world in ((10, 2), (7, 4), (8, 8)):
+        seen = set()
+        sizes = set()
+        for r in range(world):
+            idx = shard_indices(n, r, world)
+            sizes.add(len(idx))
+            seen.update(idx)
+        assert seen == set(range(n)) and len(sizes) == 1
+
+
+def _gloo_worker(rank, world, port, q):
+    os.environ.update({"MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(port), "RANK": str(rank),
+                       "WORLD_SIZE": str(world)})
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from hnd_ghnd_object_detectors_b200 import parallel
+    from hnd_ghnd_object_detectors_b200.engine import FlatParams
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(rank)
+    flat = FlatParams([("w", torch.nn.Parameter(torch.randn(5, 3))), ("b", torch.nn.Parameter(torch.randn(6)))])
+    parallel.broadcast_flat_params(flat, 0)
+    flat.grad.copy_(torch.arange(flat.total, dtype=torch.float32) * (rank + 1))
+    parallel.allreduce_flat_grad(flat)
+    q.put((rank, flat.flat.clone(), flat.grad.clone(), parallel.world_size()))
+    dist.destroy_process_group()
+
+
+def test_data_parallel_flat_allreduce_gloo():
+    """world_size 2 on CPU: after broadcast both ranks hold rank 0's parameters; the flat gradient
+    all-reduce is the SUM over ranks (FusedAdam applies 1/world)."""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+    (r0, p0, g0, w0), (r1, p1, g1, w1) = res
+    assert w0 == w1 == 2
+    assert torch.equal(p0, p1)
+    expect = torch.arange(p0.numel(), dtype=torch.float32) * 3
+    assert torch.equal(g0, expect) and torch.equal(g1, expect)
