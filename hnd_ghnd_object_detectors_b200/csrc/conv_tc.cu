@@ -12,21 +12,29 @@
 // * both land in 128B-swizzled K-major shared memory and feed tcgen05.mma.cta_group::1.kind::f16
 //   (M=128, N=BLOCK_N, K=16) issued by one thread; fp32 accumulators live in TMEM, double
 //   buffered so the epilogue of tile i overlaps the MMAs of tile i+1.
+// * epilogue = 64-channel column chunks: tcgen05.ld -> (+bias, +residual, ReLU, mask, +dst) ->
+//   16-bit rows written into a 128B-swizzled staging tile -> ONE TMA tensor store per chunk, so
+//   global writes are whole 128-byte pixel rows and the ragged tile edge is clipped by the TMA unit.
+//   Residual / mask / accumulate operands arrive the same way (TMA loads issued by a dedicated
+//   warp, double buffered), never as per-thread strided global loads.
 // * persistent CTAs (one per SM), warp-specialised: warp0 TMA producer, warp1 MMA issuer (+TMEM
-//   alloc), warps 2..5 epilogue (tcgen05.ld -> bias/residual/ReLU/mask -> 16-bit NHWC stores).
+//   alloc), warp2 epilogue-operand loader, warps 3..6 epilogue.
 //
 // The same kernel runs the data-gradient: dgrad of a stride-1 conv is a conv of dy with mirrored
 // tap offsets over the transposed weights; dgrad of a stride-2 conv is four launches, one per
-// output parity class, each using the taps that hit that class.
+// output parity class, each using the taps that hit that class and storing through a lattice view.
 #include <vector>
 
 #include "common.cuh"
 
 namespace ghnd {
 
-static constexpr int kConvThreads = 192;
+static constexpr int kConvThreads = 224;
+static constexpr int kEpiThreads = 128;
+static constexpr int kEpiWarp0 = 3;
 static constexpr int kBlockM = 128;
 static constexpr int kMaxTaps = 9;
+static constexpr int kChunkBytes = kBlockM * 128;  // one [128 rows][64 ch] 16-bit staging tile
 // GEMM-K per pipeline stage: 64 x 16-bit = 128 B rows (SWIZZLE_128B) for the wide convs, or
 // 32 x 16-bit = 64 B rows (SWIZZLE_64B) for the stem whose im2col row is 7 px x 4 ch (+4 zero).
 
@@ -39,9 +47,12 @@ struct ConvTap {
 struct ConvKernelParams {
   CUtensorMap tmap_a[4];
   CUtensorMap tmap_b;
+  CUtensorMap tmap_out;   // dst viewed on the GEMM-M lattice, box {64, TW, TH, 1}
+  CUtensorMap tmap_in0;   // residual (added before ReLU/mask) or dst itself (accumulate, added last)
+  CUtensorMap tmap_in1;   // ReLU-mask source
   ConvTap taps[kMaxTaps];
   int n_taps;
-  int cin;          // GEMM reduction channels per tap (multiple of 64)
+  int cin;          // GEMM reduction channels per tap (multiple of kblock)
   int cout;         // GEMM output channels (multiple of block_n)
   int block_n;      // 64 / 128 / 256
   int n_stages;
@@ -49,23 +60,24 @@ struct ConvKernelParams {
   int a_bytes;      // 128 rows * kblock * 2
   int stage_bytes;  // a_bytes + block_n*kblock*2
   int a_box_bytes;  // TW*TH*kblock*2
+  int io_box_bytes; // TW*TH*128
   // tile grid over the GEMM-M space
   int n_img;        // images (1 when flattened)
   int tiles_h, tiles_w, th, tw;
-  int ho, wo;       // extent of the M space per image (rows / cols of output positions)
   int n_tiles_n;
   int total_tiles;
-  // dst addressing: GEMM position (n, i, j) -> dst pixel (n, i*osh + ooh, j*osw + oow) in [n_img][OH][OW]
-  int oh_full, ow_full, osh, osw, ooh, oow;
   uint32_t idesc;
   // epilogue
-  void* dst;
   const float* bias;
-  const void* residual;
-  const void* mask;
-  int dst_fmt, res_fmt, mask_fmt;
-  int relu, accumulate;
+  int has_in0, in0_post, has_in1;
+  int out_fmt, in0_fmt, in1_fmt;
+  int relu;
 };
+
+__device__ __forceinline__ uint32_t swz_off(int row, int chunk16) {
+  // byte offset of 16-byte chunk `chunk16` of `row` inside a 128B-swizzled [rows][128 B] tile
+  return (uint32_t)(row * 128 + ((chunk16 ^ (row & 7)) << 4));
+}
 
 __global__ void __launch_bounds__(kConvThreads, 1)
     conv_tc_kernel(const __grid_constant__ ConvKernelParams p) {
@@ -73,12 +85,17 @@ __global__ void __launch_bounds__(kConvThreads, 1)
   // 1024-byte alignment for the 128B swizzle atoms
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.n_stages * p.stage_bytes);
+  const int n_in = p.has_in0 + p.has_in1;
+  uint8_t* epi_out = smem + (size_t)p.n_stages * p.stage_bytes;  // [2][kChunkBytes]
+  uint8_t* epi_in = epi_out + 2 * kChunkBytes;                   // [2][n_in][kChunkBytes]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_in + (size_t)2 * n_in * kChunkBytes);
   uint64_t* full_bar = bars;                    // [n_stages]
   uint64_t* empty_bar = bars + p.n_stages;      // [n_stages]
   uint64_t* tfull_bar = bars + 2 * p.n_stages;  // [2]
   uint64_t* tempty_bar = tfull_bar + 2;         // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* ifull_bar = tempty_bar + 2;         // [2]
+  uint64_t* iempty_bar = ifull_bar + 2;         // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(iempty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -86,13 +103,16 @@ __global__ void __launch_bounds__(kConvThreads, 1)
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 4; ++i) prefetch_tmap(&p.tmap_a[i]);
     prefetch_tmap(&p.tmap_b);
+    prefetch_tmap(&p.tmap_out);
     for (int i = 0; i < p.n_stages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 128);
+      mbar_init(&tempty_bar[i], kEpiThreads);
+      mbar_init(&ifull_bar[i], 1);
+      mbar_init(&iempty_bar[i], kEpiThreads);
     }
     fence_barrier_init();
   }
@@ -106,6 +126,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
   const int row_bytes = p.kblock * 2;
   const int k_iters = p.n_taps * k_chunks;
   const int tiles_per_img = p.tiles_h * p.tiles_w;
+  const int n_chunks = p.block_n >> 6;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -175,14 +196,36 @@ __global__ void __launch_bounds__(kConvThreads, 1)
         umma_commit(&tfull_bar[buf]);  // accumulator complete -> epilogue
       }
     }
+  } else if (warp == 2) {
+    // ===================== epilogue-operand loader =====================
+    if (lane == 0 && n_in > 0) {
+      uint32_t cnt = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles_n;
+        const int m_tile = tile / p.n_tiles_n;
+        const int img = m_tile / tiles_per_img;
+        const int rem = m_tile - img * tiles_per_img;
+        const int h0 = (rem / p.tiles_w) * p.th;
+        const int w0 = (rem % p.tiles_w) * p.tw;
+        for (int c = 0; c < n_chunks; ++c, ++cnt) {
+          const int ib = cnt & 1;
+          mbar_wait(&iempty_bar[ib], ((cnt >> 1) & 1) ^ 1);
+          uint8_t* dst = epi_in + (size_t)ib * n_in * kChunkBytes;
+          mbar_arrive_expect_tx(&ifull_bar[ib], (uint32_t)(n_in * p.io_box_bytes));
+          const int ch = n_tile * p.block_n + c * 64;
+          if (p.has_in0) tma_load_4d(dst, &p.tmap_in0, &ifull_bar[ib], ch, w0, h0, img);
+          if (p.has_in1)
+            tma_load_4d(dst + p.has_in0 * kChunkBytes, &p.tmap_in1, &ifull_bar[ib], ch, w0, h0, img);
+        }
+      }
+    }
   } else {
     // ===================== epilogue (4 warps, TMEM lane quarter = warp % 4) =====================
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
-    const int r_h = row / p.tw;
-    const int r_w = row - r_h * p.tw;
-    const bool row_in_tile = r_h < p.th;
+    const int etid = threadIdx.x - kEpiWarp0 * 32;
     int it = 0;
+    uint32_t cnt = 0;  // chunk counter (staging / operand double buffers)
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
@@ -190,97 +233,107 @@ __global__ void __launch_bounds__(kConvThreads, 1)
       const int m_tile = tile / p.n_tiles_n;
       const int img = m_tile / tiles_per_img;
       const int rem = m_tile - img * tiles_per_img;
-      const int gi = (rem / p.tiles_w) * p.th + r_h;
-      const int gj = (rem % p.tiles_w) * p.tw + r_w;
-      const bool valid = row_in_tile && gi < p.ho && gj < p.wo;
-      const size_t pix =
-          ((size_t)img * p.oh_full + (size_t)(gi * p.osh + p.ooh)) * p.ow_full + (gj * p.osw + p.oow);
-      const size_t off = pix * (size_t)p.cout + (size_t)n_tile * p.block_n;
+      const int h0 = (rem / p.tiles_w) * p.th;
+      const int w0 = (rem % p.tiles_w) * p.tw;
 
       mbar_wait(&tfull_bar[buf], use & 1);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * p.block_n);
-      for (int c = 0; c < p.block_n; c += 32) {
-        uint32_t r[32];
-        tmem_ld32(t_addr + (uint32_t)c, r);
+      for (int c = 0; c < n_chunks; ++c, ++cnt) {
+        uint32_t r[64];
+        tmem_ld32(t_addr + (uint32_t)(c * 64), r);
+        tmem_ld32(t_addr + (uint32_t)(c * 64 + 32), r + 32);
         tmem_ld_wait();
-        if (valid) {
-          float v[32];
+        if (c == n_chunks - 1) {  // accumulator fully read: hand the TMEM buffer back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(&tempty_bar[buf]);
+        }
+        const int ch = n_tile * p.block_n + c * 64;
+        float v[64];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (p.bias != nullptr) {
-            const float4* b4 = reinterpret_cast<const float4*>(p.bias + n_tile * p.block_n + c);
+        for (int j = 0; j < 64; ++j) v[j] = __uint_as_float(r[j]);
+        if (p.bias != nullptr) {
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + ch);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 b = __ldg(b4 + j);
-              v[4 * j] += b.x;
-              v[4 * j + 1] += b.y;
-              v[4 * j + 2] += b.z;
-              v[4 * j + 3] += b.w;
-            }
-          }
-          if (p.residual != nullptr) {
-            const uint4* r4 =
-                reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(p.residual) + off + c);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 q = __ldg(r4 + j);
-              uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float2 f = unpack2(w[e], p.res_fmt);
-                v[8 * j + 2 * e] += f.x;
-                v[8 * j + 2 * e + 1] += f.y;
-              }
-            }
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-          }
-          if (p.mask != nullptr) {
-            const uint4* m4 =
-                reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(p.mask) + off + c);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 q = __ldg(m4 + j);
-              uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float2 f = unpack2(w[e], p.mask_fmt);
-                if (!(f.x > 0.f)) v[8 * j + 2 * e] = 0.f;
-                if (!(f.y > 0.f)) v[8 * j + 2 * e + 1] = 0.f;
-              }
-            }
-          }
-          uint4* d4 = reinterpret_cast<uint4*>(static_cast<uint16_t*>(p.dst) + off + c);
-          if (p.accumulate) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 q = d4[j];
-              uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float2 f = unpack2(w[e], p.dst_fmt);
-                v[8 * j + 2 * e] += f.x;
-                v[8 * j + 2 * e + 1] += f.y;
-              }
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 o;
-            o.x = pack2(v[8 * j], v[8 * j + 1], p.dst_fmt);
-            o.y = pack2(v[8 * j + 2], v[8 * j + 3], p.dst_fmt);
-            o.z = pack2(v[8 * j + 4], v[8 * j + 5], p.dst_fmt);
-            o.w = pack2(v[8 * j + 6], v[8 * j + 7], p.dst_fmt);
-            d4[j] = o;
+          for (int j = 0; j < 16; ++j) {
+            const float4 b = __ldg(b4 + j);
+            v[4 * j] += b.x;
+            v[4 * j + 1] += b.y;
+            v[4 * j + 2] += b.z;
+            v[4 * j + 3] += b.w;
           }
         }
+        const int ib = cnt & 1;
+        const uint8_t* in_base = epi_in + (size_t)ib * n_in * kChunkBytes;
+        if (n_in > 0) mbar_wait(&ifull_bar[ib], (cnt >> 1) & 1);
+        if (p.has_in0 && !p.in0_post) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint4 q = *reinterpret_cast<const uint4*>(in_base + swz_off(row, j));
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = unpack2(w[e], p.in0_fmt);
+              v[8 * j + 2 * e] += f.x;
+              v[8 * j + 2 * e + 1] += f.y;
+            }
+          }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 64; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (p.has_in1) {
+          const uint8_t* m_base = in_base + p.has_in0 * kChunkBytes;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint4 q = *reinterpret_cast<const uint4*>(m_base + swz_off(row, j));
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = unpack2(w[e], p.in1_fmt);
+              if (!(f.x > 0.f)) v[8 * j + 2 * e] = 0.f;
+              if (!(f.y > 0.f)) v[8 * j + 2 * e + 1] = 0.f;
+            }
+          }
+        }
+        if (p.has_in0 && p.in0_post) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint4 q = *reinterpret_cast<const uint4*>(in_base + swz_off(row, j));
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = unpack2(w[e], p.in0_fmt);
+              v[8 * j + 2 * e] += f.x;
+              v[8 * j + 2 * e + 1] += f.y;
+            }
+          }
+        }
+        if (n_in > 0) mbar_arrive(&iempty_bar[ib]);  // operand buffer consumed
+        // ---- stage the 64-channel rows and store them with one TMA tensor store ----
+        const int ob = cnt & 1;
+        uint8_t* o_base = epi_out + (size_t)ob * kChunkBytes;
+        if (etid == 0) bulk_wait_read<1>();  // the store that used this staging buffer has drained
+        named_bar_sync(1, kEpiThreads);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint4 o;
+          o.x = pack2(v[8 * j], v[8 * j + 1], p.out_fmt);
+          o.y = pack2(v[8 * j + 2], v[8 * j + 3], p.out_fmt);
+          o.z = pack2(v[8 * j + 4], v[8 * j + 5], p.out_fmt);
+          o.w = pack2(v[8 * j + 6], v[8 * j + 7], p.out_fmt);
+          *reinterpret_cast<uint4*>(o_base + swz_off(row, j)) = o;
+        }
+        fence_proxy_async();
+        named_bar_sync(1, kEpiThreads);
+        if (etid == 0) {
+          tma_store_4d(&p.tmap_out, o_base, ch, w0, h0, img);
+          bulk_commit();
+        }
       }
-      tc_fence_before();
-      mbar_arrive(&tempty_bar[buf]);
     }
+    if (etid == 0) bulk_wait_all();
   }
 
   tc_fence_before();
@@ -327,25 +380,25 @@ static void choose_tile(int ho, int wo, int* th, int* tw) {
   *tw = btw;
 }
 
-// A-operand view of an NHWC tensor restricted to the (ph,pw) parity lattice when sub==2.
-static int make_a_map(CUtensorMap* m, const void* base, int N, int H, int W, int C, int sub, int ph,
-                      int pw, int th, int tw) {
-  const int hv = sub == 1 ? H : (H - ph + 1) / 2;
-  const int wv = sub == 1 ? W : (W - pw + 1) / 2;
-  if (hv <= 0 || wv <= 0) {
-    // empty lattice (H==1 or W==1): encode a 1x1 view; taps using it are never generated
-    return make_a_map(m, base, N, H, W, C, 1, 0, 0, th, tw);
+// View of an NHWC 16-bit tensor [N][H][W][C] restricted to the lattice h = sub_h*i + ph,
+// w = sub_w*j + pw.  inner = elements of the innermost box dimension (64 -> SWIZZLE_128B).
+static int make_lattice_map(CUtensorMap* m, const void* base, int N, int H, int W, int C, int sub_h,
+                            int sub_w, int ph, int pw, int th, int tw, int inner = 64) {
+  int hv = (H - ph + sub_h - 1) / sub_h;
+  int wv = (W - pw + sub_w - 1) / sub_w;
+  if (hv <= 0 || wv <= 0) {  // empty lattice: encode the full view, taps using it are never generated
+    return make_lattice_map(m, base, N, H, W, C, 1, 1, 0, 0, th, tw, inner);
   }
   const uint8_t* b = static_cast<const uint8_t*>(base) + ((size_t)ph * W + pw) * C * 2;
   uint64_t dims[4] = {(uint64_t)C, (uint64_t)wv, (uint64_t)hv, (uint64_t)N};
-  uint64_t str[4] = {2, (uint64_t)sub * C * 2, (uint64_t)sub * W * C * 2, (uint64_t)H * W * C * 2};
-  uint32_t box[4] = {64, (uint32_t)tw, (uint32_t)th, 1};
-  return encode_tmap(m, 2, 4, const_cast<uint8_t*>(b), dims, str, box, 128);
+  uint64_t str[4] = {2, (uint64_t)sub_w * C * 2, (uint64_t)sub_h * W * C * 2, (uint64_t)H * W * C * 2};
+  uint32_t box[4] = {(uint32_t)inner, (uint32_t)tw, (uint32_t)th, 1};
+  return encode_tmap(m, 2, 4, const_cast<uint8_t*>(b), dims, str, box, inner * 2);
 }
 
-// Tile-N choice from a two-term cost model measured in round 1 (profiles/r1_launches.md): the
-// kernel is bound either by the L2->SM operand traffic (every tile streams its A and B stages,
-// ~8 TB/s aggregate) or by the tcgen05 issue rate (128xNx16 per N/2 cycles per SM, wave-quantised).
+// Tile-N choice from a two-term cost model measured in round 1 (profiles/): the kernel is bound
+// either by the L2->SM operand traffic (every tile streams its A and B stages, ~8 TB/s aggregate)
+// or by the tcgen05 issue rate (128xNx16 per N/2 cycles per SM, wave-quantised).
 static int pick_block_n(int cout, int m_tiles, int k_iters, int row_bytes) {
   const int sms = num_sms();
   int best = 64;
@@ -367,8 +420,14 @@ static int pick_block_n(int cout, int m_tiles, int k_iters, int row_bytes) {
   return best;
 }
 
+// Geometry of the destination lattice of one launch (also used for the residual / mask views).
+struct IoGeom {
+  int N, H, W;  // full dst tensor [N][H][W][cout]
+  int sub_h, sub_w, ph, pw;
+};
+
 static int finish_launch(ConvLaunch* L, const ghnd_conv_desc_t* d, int gemm_cin, int gemm_cout,
-                         const void* weights, int total_taps, int kblock = 64) {
+                         const void* weights, int total_taps, const IoGeom& g, int kblock = 64) {
   ConvKernelParams& p = L->p;
   p.cin = gemm_cin;
   p.cout = gemm_cout;
@@ -380,10 +439,8 @@ static int finish_launch(ConvLaunch* L, const ghnd_conv_desc_t* d, int gemm_cin,
   p.n_tiles_n = gemm_cout / p.block_n;
   p.total_tiles = m_tiles * p.n_tiles_n;
   p.stage_bytes = p.a_bytes + p.block_n * row_bytes;
-  int stages = (200 * 1024) / p.stage_bytes;
-  if (stages > 8) stages = 8;
-  p.n_stages = stages;
   p.a_box_bytes = p.tw * p.th * row_bytes;
+  p.io_box_bytes = p.tw * p.th * 128;
   p.idesc = make_idesc(d->src_fmt, d->w_fmt, 0, 0, kBlockM, p.block_n);
   // weights: 2D [gemm_cout rows][total_taps * gemm_cin]
   uint64_t dims[2] = {(uint64_t)total_taps * gemm_cin, (uint64_t)gemm_cout};
@@ -391,21 +448,64 @@ static int finish_launch(ConvLaunch* L, const ghnd_conv_desc_t* d, int gemm_cin,
   uint32_t box[2] = {(uint32_t)kblock, (uint32_t)p.block_n};
   int rc = encode_tmap(&p.tmap_b, 2, 2, const_cast<void*>(weights), dims, str, box, row_bytes);
   if (rc != GHND_OK) return rc;
-  p.dst = d->dst;
+  // epilogue operands, all on the destination lattice
+  rc = make_lattice_map(&p.tmap_out, d->dst, g.N, g.H, g.W, gemm_cout, g.sub_h, g.sub_w, g.ph, g.pw,
+                        p.th, p.tw);
+  if (rc != GHND_OK) return rc;
+  p.tmap_in0 = p.tmap_out;
+  p.tmap_in1 = p.tmap_out;
+  p.has_in0 = p.has_in1 = p.in0_post = 0;
+  if (d->residual != nullptr && d->accumulate) {
+    set_error("conv: residual and accumulate cannot be combined in one launch");
+    return GHND_ERR_UNSUPPORTED;
+  }
+  if (d->residual != nullptr) {
+    p.has_in0 = 1;
+    p.in0_fmt = d->res_fmt;
+    rc = make_lattice_map(&p.tmap_in0, d->residual, g.N, g.H, g.W, gemm_cout, g.sub_h, g.sub_w, g.ph,
+                          g.pw, p.th, p.tw);
+  } else if (d->accumulate) {
+    p.has_in0 = 1;
+    p.in0_post = 1;
+    p.in0_fmt = d->dst_fmt;
+  }
+  if (rc != GHND_OK) return rc;
+  if (d->mask != nullptr) {
+    p.has_in1 = 1;
+    p.in1_fmt = d->mask_fmt;
+    rc = make_lattice_map(&p.tmap_in1, d->mask, g.N, g.H, g.W, gemm_cout, g.sub_h, g.sub_w, g.ph, g.pw,
+                          p.th, p.tw);
+    if (rc != GHND_OK) return rc;
+  }
   p.bias = d->bias;
-  p.residual = d->residual;
-  p.mask = d->mask;
-  p.dst_fmt = d->dst_fmt;
-  p.res_fmt = d->res_fmt;
-  p.mask_fmt = d->mask_fmt;
+  p.out_fmt = d->dst_fmt;
   p.relu = d->relu;
-  p.accumulate = d->accumulate;
+  const int n_in = p.has_in0 + p.has_in1;
+  const int epi_bytes = (2 + 2 * n_in) * kChunkBytes;
+  int stages = (222 * 1024 - epi_bytes) / p.stage_bytes;
+  if (stages > 8) stages = 8;
+  if (stages < 2) {
+    set_error("conv: shared memory budget leaves %d pipeline stages", stages);
+    return GHND_ERR_UNSUPPORTED;
+  }
+  p.n_stages = stages;
   L->grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  L->smem = (size_t)p.n_stages * p.stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
+  L->smem = (size_t)p.n_stages * p.stage_bytes + epi_bytes + 1024 /*align*/ + 256 /*barriers*/;
   return GHND_OK;
 }
 
 static bool fmt_ok(int f) { return f == GHND_F16 || f == GHND_BF16; }
+
+static int set_conv_attr() {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         227 * 1024);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_tc_kernel)");
+    attr_set = true;
+  }
+  return GHND_OK;
+}
 
 }  // namespace ghnd
 
@@ -451,41 +551,34 @@ int ghnd_conv_plan_create(const ghnd_conv_desc_t* d, ghnd_conv_plan_t** out) {
     ConvLaunch L;
     memset(&L, 0, sizeof(L));
     ConvKernelParams& p = L.p;
+    IoGeom g;
     const bool flat = (d->R == 1 && d->S == 1 && d->stride == 1 && d->pad == 0);
     if (flat) {
       const int64_t npix = (int64_t)d->N * d->H * d->W;
       p.n_img = 1;
       p.th = 1;
       p.tw = 128;
-      p.ho = 1;
-      p.wo = (int)npix;
       p.tiles_h = 1;
       p.tiles_w = (int)((npix + 127) / 128);
-      p.oh_full = 1;
-      p.ow_full = (int)npix;
-      p.osh = p.osw = 1;
-      rc = make_a_map(&p.tmap_a[0], d->src, 1, 1, (int)npix, d->C, 1, 0, 0, 1, 128);
+      g = IoGeom{1, 1, (int)npix, 1, 1, 0, 0};
+      rc = make_lattice_map(&p.tmap_a[0], d->src, 1, 1, (int)npix, d->C, 1, 1, 0, 0, 1, 128);
       for (int i = 1; i < 4 && rc == GHND_OK; ++i) p.tmap_a[i] = p.tmap_a[0];
       p.n_taps = 1;
       p.taps[0] = ConvTap{0, 0, 0, 0};
     } else {
       p.n_img = d->N;
-      p.ho = Ho;
-      p.wo = Wo;
       choose_tile(Ho, Wo, &p.th, &p.tw);
       p.tiles_h = (Ho + p.th - 1) / p.th;
       p.tiles_w = (Wo + p.tw - 1) / p.tw;
-      p.oh_full = Ho;
-      p.ow_full = Wo;
-      p.osh = p.osw = 1;
+      g = IoGeom{d->N, Ho, Wo, 1, 1, 0, 0};
       if (d->stride == 1) {
-        rc = make_a_map(&p.tmap_a[0], d->src, d->N, d->H, d->W, d->C, 1, 0, 0, p.th, p.tw);
+        rc = make_lattice_map(&p.tmap_a[0], d->src, d->N, d->H, d->W, d->C, 1, 1, 0, 0, p.th, p.tw);
         for (int i = 1; i < 4 && rc == GHND_OK; ++i) p.tmap_a[i] = p.tmap_a[0];
       } else {
         for (int ph = 0; ph < 2 && rc == GHND_OK; ++ph)
           for (int pw = 0; pw < 2 && rc == GHND_OK; ++pw)
-            rc = make_a_map(&p.tmap_a[ph * 2 + pw], d->src, d->N, d->H, d->W, d->C, 2, ph, pw, p.th,
-                            p.tw);
+            rc = make_lattice_map(&p.tmap_a[ph * 2 + pw], d->src, d->N, d->H, d->W, d->C, 2, 2, ph, pw,
+                                  p.th, p.tw);
       }
       int nt = 0;
       for (int r = 0; r < d->R; ++r)
@@ -503,7 +596,7 @@ int ghnd_conv_plan_create(const ghnd_conv_desc_t* d, ghnd_conv_plan_t** out) {
         }
       p.n_taps = nt;
     }
-    if (rc == GHND_OK) rc = finish_launch(&L, d, d->C, d->K, d->weights, taps_total);
+    if (rc == GHND_OK) rc = finish_launch(&L, d, d->C, d->K, d->weights, taps_total, g);
     if (rc == GHND_OK) plan->launches.push_back(L);
   } else {
     // DGRAD: src = dy [N,Ho,Wo,K], dst = dx [N,H,W,C], weights [C][R][S][K]
@@ -534,53 +627,35 @@ int ghnd_conv_plan_create(const ghnd_conv_desc_t* d, ghnd_conv_plan_t** out) {
           return GHND_ERR_UNSUPPORTED;
         }
         p.n_taps = nt;
+        IoGeom g;
         const bool flat = (sub == 1 && d->R == 1 && d->S == 1 && d->pad == 0);
         if (flat) {
           const int64_t npix = (int64_t)d->N * d->H * d->W;
           p.n_img = 1;
           p.th = 1;
           p.tw = 128;
-          p.ho = 1;
-          p.wo = (int)npix;
           p.tiles_h = 1;
           p.tiles_w = (int)((npix + 127) / 128);
-          p.oh_full = 1;
-          p.ow_full = (int)npix;
-          p.osh = p.osw = 1;
-          rc = make_a_map(&p.tmap_a[0], d->src, 1, 1, (int)npix, d->K, 1, 0, 0, 1, 128);
+          g = IoGeom{1, 1, (int)npix, 1, 1, 0, 0};
+          rc = make_lattice_map(&p.tmap_a[0], d->src, 1, 1, (int)npix, d->K, 1, 1, 0, 0, 1, 128);
         } else {
           p.n_img = d->N;
-          p.ho = hi;
-          p.wo = wi;
           choose_tile(hi, wi, &p.th, &p.tw);
           p.tiles_h = (hi + p.th - 1) / p.th;
           p.tiles_w = (wi + p.tw - 1) / p.tw;
-          p.oh_full = d->H;
-          p.ow_full = d->W;
-          p.osh = p.osw = sub;
-          p.ooh = ph;
-          p.oow = pw;
-          rc = make_a_map(&p.tmap_a[0], d->src, d->N, Ho, Wo, d->K, 1, 0, 0, p.th, p.tw);
+          g = IoGeom{d->N, d->H, d->W, sub, sub, ph, pw};
+          rc = make_lattice_map(&p.tmap_a[0], d->src, d->N, Ho, Wo, d->K, 1, 1, 0, 0, p.th, p.tw);
         }
         for (int i = 1; i < 4 && rc == GHND_OK; ++i) p.tmap_a[i] = p.tmap_a[0];
-        if (rc == GHND_OK) rc = finish_launch(&L, d, d->K, d->C, d->weights, taps_total);
+        if (rc == GHND_OK) rc = finish_launch(&L, d, d->K, d->C, d->weights, taps_total, g);
         if (rc == GHND_OK) plan->launches.push_back(L);
       }
     }
   }
+  if (rc == GHND_OK) rc = set_conv_attr();
   if (rc != GHND_OK) {
     delete plan;
     return rc;
-  }
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         227 * 1024);
-    if (e != cudaSuccess) {
-      delete plan;
-      return cuda_fail(e, "cudaFuncSetAttribute(conv_tc_kernel)");
-    }
-    attr_set = true;
   }
   *out = plan;
   return GHND_OK;
@@ -643,17 +718,9 @@ int ghnd_stem_conv_plan_create(const void* x_packed, int x_fmt, const void* w_pa
     memset(&L, 0, sizeof(L));
     ConvKernelParams& p = L.p;
     p.n_img = N;
-    p.ho = Ho;
-    p.wo = J;
     choose_tile(Ho, J, &p.th, &p.tw);
     p.tiles_h = (Ho + p.th - 1) / p.th;
     p.tiles_w = (J + p.tw - 1) / p.tw;
-    p.oh_full = Ho;
-    p.ow_full = Wo;
-    p.osh = 1;
-    p.osw = 4;
-    p.ooh = 0;
-    p.oow = q;
     for (int ph = 0; ph < 2 && rc == GHND_OK; ++ph) {
       const uint8_t* base = static_cast<const uint8_t*>(x_packed) + ((size_t)ph * RP + q * 8) * 2;
       uint64_t dims[4] = {32, (uint64_t)J, (uint64_t)((rows - ph + 1) / 2), (uint64_t)N};
@@ -668,18 +735,14 @@ int ghnd_stem_conv_plan_create(const void* x_packed, int x_fmt, const void* w_pa
       const int ph = r & 1;
       p.taps[r] = ConvTap{(int16_t)((r - ph) / 2), 0, (int16_t)ph, (int16_t)r};
     }
-    if (rc == GHND_OK) rc = finish_launch(&L, &d, 32, 64, w_packed, 7, 32);
+    const IoGeom g{N, Ho, Wo, 1, 4, 0, q};
+    if (rc == GHND_OK) rc = finish_launch(&L, &d, 32, 64, w_packed, 7, g, 32);
     if (rc == GHND_OK) plan->launches.push_back(L);
   }
+  if (rc == GHND_OK) rc = set_conv_attr();
   if (rc != GHND_OK) {
     delete plan;
     return rc;
-  }
-  cudaError_t e =
-      cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  if (e != cudaSuccess) {
-    delete plan;
-    return cuda_fail(e, "cudaFuncSetAttribute(conv_tc_kernel)");
   }
   *out = plan;
   return GHND_OK;
