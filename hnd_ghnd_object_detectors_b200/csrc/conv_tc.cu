@@ -29,14 +29,21 @@
 
 namespace ghnd {
 
-static constexpr int kConvThreads = 224;
-static constexpr int kEpiThreads = 128;
+// warp roles: 0 TMA producer, 1 MMA issuer (+TMEM alloc), 2 epilogue-operand loader,
+// 3..6 epilogue group 0, 7..10 epilogue group 1 (TMEM lane quarter = warp % 4 in both groups).
+static constexpr int kConvThreads = 352;
+static constexpr int kEpiGroupThreads = 128;
+static constexpr int kEpiThreads = 2 * kEpiGroupThreads;
 static constexpr int kEpiWarp0 = 3;
 static constexpr int kBlockM = 128;
 static constexpr int kMaxTaps = 9;
+static constexpr int kMaxStages = 8;
+static constexpr int kMaxRing = 4;
 static constexpr int kChunkBytes = kBlockM * 128;  // one [128 rows][64 ch] 16-bit staging tile
-// GEMM-K per pipeline stage: 64 x 16-bit = 128 B rows (SWIZZLE_128B) for the wide convs, or
+// GEMM-K per "unit": 64 x 16-bit = 128 B rows (SWIZZLE_128B) for the wide convs, or
 // 32 x 16-bit = 64 B rows (SWIZZLE_64B) for the stem whose im2col row is 7 px x 4 ch (+4 zero).
+// A pipeline stage holds `units_per_stage` units so that one full-barrier wait + one commit are
+// amortised over >= ~256 tensor-pipe cycles even for N=64 tiles.
 
 struct ConvTap {
   int16_t dh, dw;   // offset added to the tile origin, in the coordinates of view `map`
@@ -58,12 +65,16 @@ struct ConvKernelParams {
   int n_stages;
   int kblock;       // 64 or 32
   int a_bytes;      // 128 rows * kblock * 2
-  int stage_bytes;  // a_bytes + block_n*kblock*2
+  int b_bytes;      // block_n rows * kblock * 2
+  int units_per_stage;
+  int stage_bytes;  // units_per_stage * (a_bytes + b_bytes)
   int a_box_bytes;  // TW*TH*kblock*2
   int io_box_bytes; // TW*TH*128
+  int ring;         // depth of the epilogue-operand ring (chunks)
   // tile grid over the GEMM-M space
   int n_img;        // images (1 when flattened)
   int tiles_h, tiles_w, th, tw;
+  int lim_h, lim_w; // extent of the output lattice (row validity for the fused statistics)
   int n_tiles_n;
   int total_tiles;
   uint32_t idesc;
@@ -72,11 +83,161 @@ struct ConvKernelParams {
   int has_in0, in0_post, has_in1;
   int out_fmt, in0_fmt, in1_fmt;
   int relu;
+  double* stats;    // optional [2*cout]: sum / sum of squares of the stored (rounded) output
 };
 
 __device__ __forceinline__ uint32_t swz_off(int row, int chunk16) {
   // byte offset of 16-byte chunk `chunk16` of `row` inside a 128B-swizzled [rows][128 B] tile
   return (uint32_t)(row * 128 + ((chunk16 ^ (row & 7)) << 4));
+}
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// One GEMM-K unit = KSTEPS tcgen05.mma (K=16 each) whose descriptors differ only in the 14-bit
+// start-address field of the low word (+2 = 32 bytes along the swizzled row per step).  Written as
+// one asm block on 32-bit descriptor halves so that ptxas keeps everything in uniform registers and
+// issues the UTCHMMAs back to back.
+template <int KSTEPS>
+__device__ __forceinline__ void umma_unit(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo,
+                                          uint32_t desc_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      ".reg .b64 da, db;\n\t"
+      ".reg .b32 a, b;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "setp.eq.b32 q, 0, 0;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t"
+      "add.u32 a, %1, 2;\n\t"
+      "add.u32 b, %2, 2;\n\t"
+      "mov.b64 da, {a, %3};\n\t"
+      "mov.b64 db, {b, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, q;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+  if (KSTEPS == 4) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        ".reg .b64 da, db;\n\t"
+        ".reg .b32 a, b;\n\t"
+        "setp.eq.b32 q, 0, 0;\n\t"
+        "add.u32 a, %1, 4;\n\t"
+        "add.u32 b, %2, 4;\n\t"
+        "mov.b64 da, {a, %3};\n\t"
+        "mov.b64 db, {b, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, q;\n\t"
+        "add.u32 a, %1, 6;\n\t"
+        "add.u32 b, %2, 6;\n\t"
+        "mov.b64 da, {a, %3};\n\t"
+        "mov.b64 db, {b, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, q;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc)
+        : "memory");
+  }
+}
+
+template <int FMT>
+__device__ __forceinline__ uint32_t pack2_t(float a, float b) {
+  if (FMT == GHND_F16) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+template <int FMT>
+__device__ __forceinline__ float2 unpack2_t(uint32_t v) {
+  if (FMT == GHND_F16) {
+    __half2 h = *reinterpret_cast<__half2*>(&v);
+    return __half22float2(h);
+  }
+  float2 r;
+  r.x = __uint_as_float(v << 16);
+  r.y = __uint_as_float(v & 0xffff0000u);
+  return r;
+}
+
+// v[0..63] += the 64 channels of `row` of a swizzled 16-bit operand tile
+template <int FMT>
+__device__ __forceinline__ void epi_add_rows(float* v, const uint8_t* base, int row) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint4 q = *reinterpret_cast<const uint4*>(base + swz_off(row, j));
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = unpack2_t<FMT>(w[e]);
+      v[8 * j + 2 * e] += f.x;
+      v[8 * j + 2 * e + 1] += f.y;
+    }
+  }
+}
+// v[i] = mask[i] > 0 ? v[i] : 0
+template <int FMT>
+__device__ __forceinline__ void epi_mask_rows(float* v, const uint8_t* base, int row) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint4 q = *reinterpret_cast<const uint4*>(base + swz_off(row, j));
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = unpack2_t<FMT>(w[e]);
+      if (!(f.x > 0.f)) v[8 * j + 2 * e] = 0.f;
+      if (!(f.y > 0.f)) v[8 * j + 2 * e + 1] = 0.f;
+    }
+  }
+}
+template <int FMT>
+__device__ __forceinline__ void epi_stage_rows(const float* v, uint8_t* base, int row) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    uint4 o;
+    o.x = pack2_t<FMT>(v[8 * j], v[8 * j + 1]);
+    o.y = pack2_t<FMT>(v[8 * j + 2], v[8 * j + 3]);
+    o.z = pack2_t<FMT>(v[8 * j + 4], v[8 * j + 5]);
+    o.w = pack2_t<FMT>(v[8 * j + 6], v[8 * j + 7]);
+    *reinterpret_cast<uint4*>(base + swz_off(row, j)) = o;
+  }
+}
+// Per-channel sum / sum of squares of the staged (rounded) tile: this thread owns the channel
+// pair (2*lane, 2*lane+1) over the 32 rows of its warp's quarter; `valid` = ballot of row validity.
+template <int FMT>
+__device__ __forceinline__ void epi_stats_rows(const uint8_t* base, int quarter, int lane,
+                                               uint32_t valid, float* sstat, int ch, int cout) {
+  float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 8
+  for (int i = 0; i < 32; ++i) {
+    const int r = quarter * 32 + i;
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(base + r * 128 +
+                                                          ((((lane >> 2) ^ (r & 7))) << 4) +
+                                                          ((lane & 3) << 2));
+    if ((valid >> i) & 1u) {
+      const float2 f = unpack2_t<FMT>(w);
+      s0 += f.x;
+      s1 += f.y;
+      q0 = fmaf(f.x, f.x, q0);
+      q1 = fmaf(f.y, f.y, q1);
+    }
+  }
+  atomicAdd(&sstat[ch + 2 * lane], s0);
+  atomicAdd(&sstat[ch + 2 * lane + 1], s1);
+  atomicAdd(&sstat[cout + ch + 2 * lane], q0);
+  atomicAdd(&sstat[cout + ch + 2 * lane + 1], q1);
 }
 
 __global__ void __launch_bounds__(kConvThreads, 1)
@@ -86,18 +247,21 @@ __global__ void __launch_bounds__(kConvThreads, 1)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~(uintptr_t)1023);
   const int n_in = p.has_in0 + p.has_in1;
-  uint8_t* epi_out = smem + (size_t)p.n_stages * p.stage_bytes;  // [2][kChunkBytes]
-  uint8_t* epi_in = epi_out + 2 * kChunkBytes;                   // [2][n_in][kChunkBytes]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_in + (size_t)2 * n_in * kChunkBytes);
-  uint64_t* full_bar = bars;                    // [n_stages]
-  uint64_t* empty_bar = bars + p.n_stages;      // [n_stages]
-  uint64_t* tfull_bar = bars + 2 * p.n_stages;  // [2]
-  uint64_t* tempty_bar = tfull_bar + 2;         // [2]
-  uint64_t* ifull_bar = tempty_bar + 2;         // [2]
-  uint64_t* iempty_bar = ifull_bar + 2;         // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(iempty_bar + 2);
+  uint8_t* epi_out = smem + (size_t)p.n_stages * p.stage_bytes;            // [2 groups][kChunkBytes]
+  uint8_t* epi_in = epi_out + 2 * kChunkBytes;                             // [ring][n_in][kChunkBytes]
+  float* sbias = reinterpret_cast<float*>(epi_in + (size_t)p.ring * n_in * kChunkBytes);  // [cout]
+  float* sstat = sbias + (p.bias != nullptr ? p.cout : 0);                 // [2*cout] when stats
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sstat + (p.stats != nullptr ? 2 * p.cout : 0));
+  uint64_t* full_bar = bars;                        // [kMaxStages]
+  uint64_t* empty_bar = full_bar + kMaxStages;      // [kMaxStages]
+  uint64_t* tfull_bar = empty_bar + kMaxStages;     // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;             // [2]
+  uint64_t* ifull_bar = tempty_bar + 2;             // [kMaxRing]
+  uint64_t* iempty_bar = ifull_bar + kMaxRing;      // [kMaxRing]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(iempty_bar + kMaxRing);
 
-  const int warp = threadIdx.x >> 5;
+  // warp index through a shuffle so that the compiler treats the role branches as warp-uniform
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -111,95 +275,129 @@ __global__ void __launch_bounds__(kConvThreads, 1)
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], kEpiThreads);
+    }
+    for (int i = 0; i < kMaxRing; ++i) {
       mbar_init(&ifull_bar[i], 1);
-      mbar_init(&iempty_bar[i], kEpiThreads);
+      mbar_init(&iempty_bar[i], kEpiGroupThreads);
     }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (p.bias != nullptr)
+    for (int i = threadIdx.x; i < p.cout; i += kConvThreads) sbias[i] = __ldg(p.bias + i);
+  if (p.stats != nullptr)
+    for (int i = threadIdx.x; i < 2 * p.cout; i += kConvThreads) sstat[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
   const int k_chunks = p.cin / p.kblock;
-  const int row_bytes = p.kblock * 2;
-  const int k_iters = p.n_taps * k_chunks;
+  const int n_units = p.n_taps * k_chunks;
+  const int upst = p.units_per_stage;
   const int tiles_per_img = p.tiles_h * p.tiles_w;
   const int n_chunks = p.block_n >> 6;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int n_tile = tile % p.n_tiles_n;
-        const int m_tile = tile / p.n_tiles_n;
-        const int img = m_tile / tiles_per_img;
-        const int rem = m_tile - img * tiles_per_img;
-        const int h0 = (rem / p.tiles_w) * p.th;
-        const int w0 = (rem % p.tiles_w) * p.tw;
-        for (int t = 0; t < p.n_taps; ++t) {
-          const ConvTap tap = p.taps[t];
-          for (int kc = 0; kc < k_chunks; ++kc) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
-            uint8_t* sb = sa + p.a_bytes;
-            mbar_arrive_expect_tx(&full_bar[stage],
-                                  (uint32_t)(p.a_box_bytes + p.block_n * row_bytes));
-            tma_load_4d(sa, &p.tmap_a[tap.map], &full_bar[stage], kc * p.kblock, w0 + tap.dw,
-                        h0 + tap.dh, img);
-            tma_load_2d(sb, &p.tmap_b, &full_bar[stage], tap.wk * p.cin + kc * p.kblock,
-                        n_tile * p.block_n);
-            if (++stage == p.n_stages) {
-              stage = 0;
-              phase ^= 1;
+    // ===================== TMA producer (whole warp converged, one elected lane issues) ==========
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int n_tile = tile % p.n_tiles_n;
+      const int m_tile = tile / p.n_tiles_n;
+      const int img = m_tile / tiles_per_img;
+      const int rem = m_tile - img * tiles_per_img;
+      const int h0 = (rem / p.tiles_w) * p.th;
+      const int w0 = (rem % p.tiles_w) * p.tw;
+      int t = 0, kc = 0;
+      for (int u = 0; u < n_units; u += upst) {
+        const int nu = min(upst, n_units - u);
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
+          uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
+          uint8_t* sb = sa + upst * p.a_bytes;
+          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(nu * (p.a_box_bytes + p.b_bytes)));
+          int tt = t, kk = kc;
+          for (int j = 0; j < nu; ++j) {
+            const ConvTap tap = p.taps[tt];
+            tma_load_4d(sa + j * p.a_bytes, &p.tmap_a[tap.map], &full_bar[stage], kk * p.kblock,
+                        w0 + tap.dw, h0 + tap.dh, img);
+            tma_load_2d(sb + j * p.b_bytes, &p.tmap_b, &full_bar[stage],
+                        tap.wk * p.cin + kk * p.kblock, n_tile * p.block_n);
+            if (++kk == k_chunks) {
+              kk = 0;
+              ++tt;
             }
           }
+        }
+        __syncwarp();
+        // every lane advances (t, kc) by the units of this stage (the elected lane may change)
+        kc += nu;
+        while (kc >= k_chunks) {
+          kc -= k_chunks;
+          ++t;
+        }
+        if (++stage == p.n_stages) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      const uint32_t sw_layout = p.kblock == 64 ? UMMA_SW128 : UMMA_SW64;
-      const uint32_t sbo = 8u * (uint32_t)row_bytes;  // 8-row swizzle atom
-      const int k_steps = p.kblock / 16;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
-        const uint32_t use = (uint32_t)(it >> 1);
-        mbar_wait(&tempty_bar[buf], (use & 1) ^ 1);
+    // ===================== MMA issuer (whole warp converged, one elected lane issues) ============
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t sbo = 8u * (uint32_t)(p.kblock * 2);  // 8-row swizzle atom
+    const uint32_t desc_hi = (sbo >> 4) | (1u << 14) | ((p.kblock == 64 ? (uint32_t)UMMA_SW128
+                                                                         : (uint32_t)UMMA_SW64)
+                                                        << 29);
+    const uint32_t a_step = (uint32_t)p.a_bytes >> 4, b_step = (uint32_t)p.b_bytes >> 4;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      mbar_wait(&tempty_bar[buf], (((uint32_t)it >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.block_n);
+      for (int u = 0; u < n_units; u += upst) {
+        const int nu = min(upst, n_units - u);
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.block_n);
-        for (int ki = 0; ki < k_iters; ++ki) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
-          const uint32_t sb = sa + (uint32_t)p.a_bytes;
-          const uint64_t adesc = make_smem_desc(sa, 16, sbo, sw_layout);
-          const uint64_t bdesc = make_smem_desc(sb, 16, sbo, sw_layout);
-          for (int k = 0; k < k_steps; ++k) {
-            // advance 16 elements (32 B) along K inside the swizzle row: +2 in (addr>>4)
-            umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc,
-                     (uint32_t)((ki | k) != 0));
+        if (elect_one()) {
+          const uint32_t sa = smem_base + (uint32_t)(stage * p.stage_bytes);
+          // descriptor low word: start address >> 4 | LBO(16 B) << 16
+          uint32_t a_lo = ((sa >> 4) & 0x3fffu) | (1u << 16);
+          uint32_t b_lo = (((sa + (uint32_t)(upst * p.a_bytes)) >> 4) & 0x3fffu) | (1u << 16);
+          if (p.kblock == 64) {
+            for (int j = 0; j < nu; ++j) {
+              umma_unit<4>(d_tmem, a_lo, b_lo, desc_hi, p.idesc, (uint32_t)((u + j) != 0));
+              a_lo += a_step;
+              b_lo += b_step;
+            }
+          } else {
+            for (int j = 0; j < nu; ++j) {
+              umma_unit<2>(d_tmem, a_lo, b_lo, desc_hi, p.idesc, (uint32_t)((u + j) != 0));
+              a_lo += a_step;
+              b_lo += b_step;
+            }
           }
           umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
-          if (++stage == p.n_stages) {
-            stage = 0;
-            phase ^= 1;
-          }
         }
-        umma_commit(&tfull_bar[buf]);  // accumulator complete -> epilogue
+        __syncwarp();
+        if (++stage == p.n_stages) {
+          stage = 0;
+          phase ^= 1;
+        }
       }
+      if (elect_one()) umma_commit(&tfull_bar[buf]);  // accumulator complete -> epilogue
+      __syncwarp();
     }
   } else if (warp == 2) {
     // ===================== epilogue-operand loader =====================
-    if (lane == 0 && n_in > 0) {
+    if (n_in > 0) {
       uint32_t cnt = 0;
+      int slot = 0;
+      uint32_t rphase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int n_tile = tile % p.n_tiles_n;
         const int m_tile = tile / p.n_tiles_n;
@@ -208,43 +406,67 @@ __global__ void __launch_bounds__(kConvThreads, 1)
         const int h0 = (rem / p.tiles_w) * p.th;
         const int w0 = (rem % p.tiles_w) * p.tw;
         for (int c = 0; c < n_chunks; ++c, ++cnt) {
-          const int ib = cnt & 1;
-          mbar_wait(&iempty_bar[ib], ((cnt >> 1) & 1) ^ 1);
-          uint8_t* dst = epi_in + (size_t)ib * n_in * kChunkBytes;
-          mbar_arrive_expect_tx(&ifull_bar[ib], (uint32_t)(n_in * p.io_box_bytes));
-          const int ch = n_tile * p.block_n + c * 64;
-          if (p.has_in0) tma_load_4d(dst, &p.tmap_in0, &ifull_bar[ib], ch, w0, h0, img);
-          if (p.has_in1)
-            tma_load_4d(dst + p.has_in0 * kChunkBytes, &p.tmap_in1, &ifull_bar[ib], ch, w0, h0, img);
+          mbar_wait(&iempty_bar[slot], rphase ^ 1);
+          if (elect_one()) {
+            uint8_t* dst = epi_in + (size_t)slot * n_in * kChunkBytes;
+            mbar_arrive_expect_tx(&ifull_bar[slot], (uint32_t)(n_in * p.io_box_bytes));
+            const int ch = n_tile * p.block_n + c * 64;
+            if (p.has_in0) tma_load_4d(dst, &p.tmap_in0, &ifull_bar[slot], ch, w0, h0, img);
+            if (p.has_in1)
+              tma_load_4d(dst + p.has_in0 * kChunkBytes, &p.tmap_in1, &ifull_bar[slot], ch, w0, h0,
+                          img);
+          }
+          __syncwarp();
+          if (++slot == p.ring) {
+            slot = 0;
+            rphase ^= 1;
+          }
         }
       }
     }
   } else {
-    // ===================== epilogue (4 warps, TMEM lane quarter = warp % 4) =====================
-    const int quarter = warp & 3;
+    // ===================== epilogue: two groups of 4 warps, alternating 64-channel chunks ========
+    const int group = (warp - kEpiWarp0) >> 2;
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;
-    const int etid = threadIdx.x - kEpiWarp0 * 32;
+    const int etid = threadIdx.x - (kEpiWarp0 + 4 * group) * 32;
+    const int bar_id = 1 + group;
+    uint8_t* o_base = epi_out + (size_t)group * kChunkBytes;
     int it = 0;
-    uint32_t cnt = 0;  // chunk counter (staging / operand double buffers)
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    uint32_t cnt0 = 0;  // global chunk counter at the start of the tile
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it, cnt0 += n_chunks) {
       const int buf = it & 1;
-      const uint32_t use = (uint32_t)(it >> 1);
+      const uint32_t use = (uint32_t)it >> 1;
       const int n_tile = tile % p.n_tiles_n;
       const int m_tile = tile / p.n_tiles_n;
       const int img = m_tile / tiles_per_img;
       const int rem = m_tile - img * tiles_per_img;
       const int h0 = (rem / p.tiles_w) * p.th;
       const int w0 = (rem % p.tiles_w) * p.tw;
+      uint32_t valid = 0xffffffffu;
+      if (p.stats != nullptr) {
+        const int rh = row / p.tw, rw = row - rh * p.tw;
+        valid = __ballot_sync(0xffffffffu, rh < p.th && h0 + rh < p.lim_h && w0 + rw < p.lim_w);
+      }
+      // chunks of this tile handled by this group: c = c_first, c_first + 2, ...
+      const int c_first = (int)((cnt0 ^ (uint32_t)group) & 1u);
+      int c_last = -1;
+      for (int c = c_first; c < n_chunks; c += 2) c_last = c;
 
-      mbar_wait(&tfull_bar[buf], use & 1);
+      mbar_wait(&tfull_bar[buf], use & 1u);
       tc_fence_after();
+      if (c_last < 0) {  // nothing to read from this accumulator: release our share right away
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[buf]);
+      }
       const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * p.block_n);
-      for (int c = 0; c < n_chunks; ++c, ++cnt) {
+      for (int c = c_first; c < n_chunks; c += 2) {
+        const uint32_t cnt = cnt0 + (uint32_t)c;
         uint32_t r[64];
         tmem_ld32(t_addr + (uint32_t)(c * 64), r);
         tmem_ld32(t_addr + (uint32_t)(c * 64 + 32), r + 32);
         tmem_ld_wait();
-        if (c == n_chunks - 1) {  // accumulator fully read: hand the TMEM buffer back to the MMA warp
+        if (c == c_last) {  // accumulator fully read by this thread: hand TMEM back to the MMA warp
           tc_fence_before();
           mbar_arrive(&tempty_bar[buf]);
         }
@@ -253,31 +475,22 @@ __global__ void __launch_bounds__(kConvThreads, 1)
 #pragma unroll
         for (int j = 0; j < 64; ++j) v[j] = __uint_as_float(r[j]);
         if (p.bias != nullptr) {
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + ch);
+          const float4* b4 = reinterpret_cast<const float4*>(sbias + ch);
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float4 b = __ldg(b4 + j);
+            const float4 b = b4[j];
             v[4 * j] += b.x;
             v[4 * j + 1] += b.y;
             v[4 * j + 2] += b.z;
             v[4 * j + 3] += b.w;
           }
         }
-        const int ib = cnt & 1;
-        const uint8_t* in_base = epi_in + (size_t)ib * n_in * kChunkBytes;
-        if (n_in > 0) mbar_wait(&ifull_bar[ib], (cnt >> 1) & 1);
+        const int slot = (int)(cnt % (uint32_t)p.ring);
+        const uint8_t* in_base = epi_in + (size_t)slot * n_in * kChunkBytes;
+        if (n_in > 0) mbar_wait(&ifull_bar[slot], (cnt / (uint32_t)p.ring) & 1u);
         if (p.has_in0 && !p.in0_post) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const uint4 q = *reinterpret_cast<const uint4*>(in_base + swz_off(row, j));
-            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 f = unpack2(w[e], p.in0_fmt);
-              v[8 * j + 2 * e] += f.x;
-              v[8 * j + 2 * e + 1] += f.y;
-            }
-          }
+          if (p.in0_fmt == GHND_F16) epi_add_rows<GHND_F16>(v, in_base, row);
+          else epi_add_rows<GHND_BF16>(v, in_base, row);
         }
         if (p.relu) {
 #pragma unroll
@@ -285,55 +498,39 @@ __global__ void __launch_bounds__(kConvThreads, 1)
         }
         if (p.has_in1) {
           const uint8_t* m_base = in_base + p.has_in0 * kChunkBytes;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const uint4 q = *reinterpret_cast<const uint4*>(m_base + swz_off(row, j));
-            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 f = unpack2(w[e], p.in1_fmt);
-              if (!(f.x > 0.f)) v[8 * j + 2 * e] = 0.f;
-              if (!(f.y > 0.f)) v[8 * j + 2 * e + 1] = 0.f;
-            }
-          }
+          if (p.in1_fmt == GHND_F16) epi_mask_rows<GHND_F16>(v, m_base, row);
+          else epi_mask_rows<GHND_BF16>(v, m_base, row);
         }
         if (p.has_in0 && p.in0_post) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const uint4 q = *reinterpret_cast<const uint4*>(in_base + swz_off(row, j));
-            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 f = unpack2(w[e], p.in0_fmt);
-              v[8 * j + 2 * e] += f.x;
-              v[8 * j + 2 * e + 1] += f.y;
-            }
-          }
+          if (p.in0_fmt == GHND_F16) epi_add_rows<GHND_F16>(v, in_base, row);
+          else epi_add_rows<GHND_BF16>(v, in_base, row);
         }
-        if (n_in > 0) mbar_arrive(&iempty_bar[ib]);  // operand buffer consumed
+        if (n_in > 0) mbar_arrive(&iempty_bar[slot]);  // operand buffer consumed
         // ---- stage the 64-channel rows and store them with one TMA tensor store ----
-        const int ob = cnt & 1;
-        uint8_t* o_base = epi_out + (size_t)ob * kChunkBytes;
-        if (etid == 0) bulk_wait_read<1>();  // the store that used this staging buffer has drained
-        named_bar_sync(1, kEpiThreads);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          uint4 o;
-          o.x = pack2(v[8 * j], v[8 * j + 1], p.out_fmt);
-          o.y = pack2(v[8 * j + 2], v[8 * j + 3], p.out_fmt);
-          o.z = pack2(v[8 * j + 4], v[8 * j + 5], p.out_fmt);
-          o.w = pack2(v[8 * j + 6], v[8 * j + 7], p.out_fmt);
-          *reinterpret_cast<uint4*>(o_base + swz_off(row, j)) = o;
-        }
+        if (etid == 0) bulk_wait_read<0>();  // the store that used this staging buffer has drained
+        named_bar_sync(bar_id, kEpiGroupThreads);
+        if (p.out_fmt == GHND_F16) epi_stage_rows<GHND_F16>(v, o_base, row);
+        else epi_stage_rows<GHND_BF16>(v, o_base, row);
         fence_proxy_async();
-        named_bar_sync(1, kEpiThreads);
+        named_bar_sync(bar_id, kEpiGroupThreads);
         if (etid == 0) {
           tma_store_4d(&p.tmap_out, o_base, ch, w0, h0, img);
           bulk_commit();
         }
+        if (p.stats != nullptr) {
+          if (p.out_fmt == GHND_F16)
+            epi_stats_rows<GHND_F16>(o_base, quarter, lane, valid, sstat, ch, p.cout);
+          else
+            epi_stats_rows<GHND_BF16>(o_base, quarter, lane, valid, sstat, ch, p.cout);
+        }
       }
     }
     if (etid == 0) bulk_wait_all();
+    if (p.stats != nullptr) {
+      named_bar_sync(3, kEpiThreads);  // both groups: all shared-memory partial sums are in
+      for (int i = threadIdx.x - kEpiWarp0 * 32; i < 2 * p.cout; i += kEpiThreads)
+        atomicAdd(p.stats + i, (double)sstat[i]);
+    }
   }
 
   tc_fence_before();
@@ -399,7 +596,8 @@ static int make_lattice_map(CUtensorMap* m, const void* base, int N, int H, int 
 // Tile-N choice from a two-term cost model measured in round 1 (profiles/): the kernel is bound
 // either by the L2->SM operand traffic (every tile streams its A and B stages, ~8 TB/s aggregate)
 // or by the tcgen05 issue rate (128xNx16 per N/2 cycles per SM, wave-quantised).
-static int pick_block_n(int cout, int m_tiles, int k_iters, int row_bytes) {
+static int pick_block_n(int cout, int m_tiles, int k_iters, int row_bytes, int n_in) {
+  (void)n_in;
   const int sms = num_sms();
   int best = 64;
   double best_t = 1e30;
@@ -426,6 +624,9 @@ struct IoGeom {
   int sub_h, sub_w, ph, pw;
 };
 
+// Shared-memory plan of one launch: [stages][2 staging tiles][operand ring][bias][stats][barriers].
+static const int kSmemBudget = 227 * 1024 - 1024 /*align*/ - 512 /*barriers + tmem slot*/;
+
 static int finish_launch(ConvLaunch* L, const ghnd_conv_desc_t* d, int gemm_cin, int gemm_cout,
                          const void* weights, int total_taps, const IoGeom& g, int kblock = 64) {
   ConvKernelParams& p = L->p;
@@ -435,12 +636,33 @@ static int finish_launch(ConvLaunch* L, const ghnd_conv_desc_t* d, int gemm_cin,
   const int row_bytes = kblock * 2;
   p.a_bytes = kBlockM * row_bytes;
   const int m_tiles = p.n_img * p.tiles_h * p.tiles_w;
-  p.block_n = pick_block_n(gemm_cout, m_tiles, p.n_taps * (gemm_cin / kblock), row_bytes);
+  const int n_units = p.n_taps * (gemm_cin / kblock);
+  p.has_in0 = p.has_in1 = p.in0_post = 0;
+  if (d->residual != nullptr && d->accumulate) {
+    set_error("conv: residual and accumulate cannot be combined in one launch");
+    return GHND_ERR_UNSUPPORTED;
+  }
+  if (d->residual != nullptr || d->accumulate) p.has_in0 = 1;
+  if (d->mask != nullptr) p.has_in1 = 1;
+  const int n_in = p.has_in0 + p.has_in1;
+  p.block_n = pick_block_n(gemm_cout, m_tiles, n_units, row_bytes, n_in);
+  p.b_bytes = p.block_n * row_bytes;
   p.n_tiles_n = gemm_cout / p.block_n;
   p.total_tiles = m_tiles * p.n_tiles_n;
-  p.stage_bytes = p.a_bytes + p.block_n * row_bytes;
+  // units per stage: >= ~256 tensor-pipe cycles (block_n/2 per K=16 step) behind every barrier wait
+  {
+    const int unit_cycles = (kblock / 16) * (p.block_n / 2);
+    int u = (256 + unit_cycles - 1) / unit_cycles;
+    if (u > 4) u = 4;
+    if (u > n_units) u = n_units;
+    if (u < 1) u = 1;
+    p.units_per_stage = u;
+  }
+  p.stage_bytes = p.units_per_stage * (p.a_bytes + p.b_bytes);
   p.a_box_bytes = p.tw * p.th * row_bytes;
   p.io_box_bytes = p.tw * p.th * 128;
+  p.lim_h = (g.H - g.ph + g.sub_h - 1) / g.sub_h;
+  p.lim_w = (g.W - g.pw + g.sub_w - 1) / g.sub_w;
   p.idesc = make_idesc(d->src_fmt, d->w_fmt, 0, 0, kBlockM, p.block_n);
   // weights: 2D [gemm_cout rows][total_taps * gemm_cin]
   uint64_t dims[2] = {(uint64_t)total_taps * gemm_cin, (uint64_t)gemm_cout};
@@ -454,24 +676,16 @@ static int finish_launch(ConvLaunch* L, const ghnd_conv_desc_t* d, int gemm_cin,
   if (rc != GHND_OK) return rc;
   p.tmap_in0 = p.tmap_out;
   p.tmap_in1 = p.tmap_out;
-  p.has_in0 = p.has_in1 = p.in0_post = 0;
-  if (d->residual != nullptr && d->accumulate) {
-    set_error("conv: residual and accumulate cannot be combined in one launch");
-    return GHND_ERR_UNSUPPORTED;
-  }
   if (d->residual != nullptr) {
-    p.has_in0 = 1;
     p.in0_fmt = d->res_fmt;
     rc = make_lattice_map(&p.tmap_in0, d->residual, g.N, g.H, g.W, gemm_cout, g.sub_h, g.sub_w, g.ph,
                           g.pw, p.th, p.tw);
   } else if (d->accumulate) {
-    p.has_in0 = 1;
     p.in0_post = 1;
     p.in0_fmt = d->dst_fmt;
   }
   if (rc != GHND_OK) return rc;
   if (d->mask != nullptr) {
-    p.has_in1 = 1;
     p.in1_fmt = d->mask_fmt;
     rc = make_lattice_map(&p.tmap_in1, d->mask, g.N, g.H, g.W, gemm_cout, g.sub_h, g.sub_w, g.ph, g.pw,
                           p.th, p.tw);
@@ -480,17 +694,30 @@ static int finish_launch(ConvLaunch* L, const ghnd_conv_desc_t* d, int gemm_cin,
   p.bias = d->bias;
   p.out_fmt = d->dst_fmt;
   p.relu = d->relu;
-  const int n_in = p.has_in0 + p.has_in1;
-  const int epi_bytes = (2 + 2 * n_in) * kChunkBytes;
-  int stages = (222 * 1024 - epi_bytes) / p.stage_bytes;
-  if (stages > 8) stages = 8;
+  p.stats = d->stats;
+  // shared-memory split: >= 3 pipeline stages first, then the operand ring (deep enough to keep
+  // ~64 KB of residual / mask loads in flight per SM), the rest goes to more stages
+  const int fixed = 2 * kChunkBytes + (d->bias ? gemm_cout * 4 : 0) + (d->stats ? gemm_cout * 8 : 0);
+  const int stages_per_tile = (n_units + p.units_per_stage - 1) / p.units_per_stage;
+  int ring = 0;
+  if (n_in > 0) {
+    const int want = n_in == 1 ? 4 : 3;
+    ring = (kSmemBudget - fixed - 3 * p.stage_bytes) / (n_in * kChunkBytes);
+    if (ring > want) ring = want;
+    if (ring < 2) ring = 2;
+  }
+  p.ring = ring > 0 ? ring : 1;
+  int stages = (kSmemBudget - fixed - ring * n_in * kChunkBytes) / p.stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  (void)stages_per_tile;
   if (stages < 2) {
     set_error("conv: shared memory budget leaves %d pipeline stages", stages);
     return GHND_ERR_UNSUPPORTED;
   }
   p.n_stages = stages;
   L->grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  L->smem = (size_t)p.n_stages * p.stage_bytes + epi_bytes + 1024 /*align*/ + 256 /*barriers*/;
+  L->smem = (size_t)p.n_stages * p.stage_bytes + (size_t)fixed + (size_t)ring * n_in * kChunkBytes +
+            1024 /*align*/ + 512 /*barriers*/;
   return GHND_OK;
 }
 
@@ -534,7 +761,8 @@ int ghnd_conv_plan_create(const ghnd_conv_desc_t* d, ghnd_conv_plan_t** out) {
                  "mixed f16 x bf16 operands on sm_100a)");
   GHND_CHECK_ARG(!d->residual || fmt_ok(d->res_fmt), "conv: bad residual format");
   GHND_CHECK_ARG(!d->mask || fmt_ok(d->mask_fmt), "conv: bad mask format");
-  GHND_CHECK_ARG(d->stats == nullptr, "conv: fused statistics not available in this build");
+  GHND_CHECK_ARG(d->stats == nullptr || (d->kind == GHND_CONV_FWD && d->stride == 1 && d->K <= 1024),
+                 "conv: fused statistics need a stride-1 forward conv with K <= 1024");
   GHND_CHECK_ARG(((uintptr_t)d->src % 16) == 0 && ((uintptr_t)d->weights % 16) == 0 &&
                      ((uintptr_t)d->dst % 16) == 0 && ((uintptr_t)d->residual % 16) == 0 &&
                      ((uintptr_t)d->mask % 16) == 0 && ((uintptr_t)d->bias % 16) == 0,
@@ -665,6 +893,9 @@ int ghnd_conv_plan_run(const ghnd_conv_plan_t* plan, void* stream) {
   using namespace ghnd;
   GHND_CHECK_ARG(plan != nullptr, "conv_plan_run: null plan");
   for (const ConvLaunch& L : plan->launches) {
+    if (L.p.stats != nullptr)
+      GHND_CUDA(cudaMemsetAsync(L.p.stats, 0, (size_t)2 * L.p.cout * sizeof(double),
+                                (cudaStream_t)stream));
     conv_tc_kernel<<<L.grid, kConvThreads, L.smem, (cudaStream_t)stream>>>(L.p);
     GHND_LAUNCH_CHECK("conv_tc_kernel");
   }

@@ -230,7 +230,9 @@ class _WideUnit(object):
         if train:
             self.raw = _empty((N, self.Ho, self.Wo, K), act_dtype, dev)
             self.out_g = _empty((N, self.Ho, self.Wo, K), grad_dtype, dev)  # bf16 copy for wgrad
-            self.plan = ops.ConvPlan(CONV_FWD, N, H, W, C, K, R, S, 1, pad, x, self.w, self.raw)
+            # batch statistics of the stored conv output are accumulated by the conv epilogue
+            self.plan = ops.ConvPlan(CONV_FWD, N, H, W, C, K, R, S, 1, pad, x, self.w, self.raw,
+                                     stats=self.bn.sums)
         else:
             # eval: BN folded into the conv (scale into the weights, shift as bias, ReLU in epilogue)
             self.raw = self.out_g = None
@@ -241,7 +243,6 @@ class _WideUnit(object):
         if self.train:
             ops.pack_weight(self.conv.weight, None, False, out=self.w)
             self.plan.run()
-            ops.bn_stats(self.raw, self.bn.sums)
             self.bn.finalize()
             ops.bn_apply(self.raw, self.out, self.bn.scale_shift, self.relu, y2=self.out_g)
         else:

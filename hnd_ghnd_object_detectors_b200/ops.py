@@ -144,7 +144,7 @@ class ConvPlan(object):
     """ghnd_conv_plan: tcgen05 implicit-GEMM conv forward / dgrad bound to fixed buffers."""
 
     def __init__(self, kind, N, H, W, C, K, R, S, stride, pad, src, weights, dst, bias=None,
-                 residual=None, relu=False, mask=None, accumulate=False):
+                 residual=None, relu=False, mask=None, accumulate=False, stats=None):
         d = _lib.ConvDesc()
         d.kind = kind
         d.N, d.H, d.W, d.C, d.K, d.R, d.S, d.stride, d.pad = N, H, W, C, K, R, S, stride, pad
@@ -158,8 +158,16 @@ class ConvPlan(object):
         d.mask = mask.data_ptr() if mask is not None else None
         d.mask_fmt = fmt_of(mask.dtype) if mask is not None else 0
         d.accumulate = int(bool(accumulate))
-        d.stats = None
-        self._keep = (src, weights, dst, bias, residual, mask)  # buffers must outlive the plan
+        if stats is not None:
+            assert stats.dtype == torch.float64 and stats.numel() >= 2 * (K if kind == _lib.CONV_FWD else C)
+        d.stats = stats.data_ptr() if stats is not None else None
+        self._keep = (src, weights, dst, bias, residual, mask, stats)  # buffers must outlive the plan
+        self.desc = "%s N%d %dx%d C%d K%d %dx%d s%d p%d%s%s%s%s" % (
+            "fwd" if kind == _lib.CONV_FWD else "dgrad", N, H, W, C, K, R, S, stride, pad,
+            " +res" if residual is not None else "", " relu" if relu else "",
+            " mask" if mask is not None else "", " acc" if accumulate else "")
+        Ho, Wo = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - S) // stride + 1
+        self.flops = 2.0 * N * Ho * Wo * K * C * R * S
         self._h = c_void_p()
         call("ghnd_conv_plan_create", byref(d), byref(self._h))
         self.n_launches = _lib.load().ghnd_conv_plan_launches(self._h)
@@ -187,6 +195,8 @@ class WgradPlan(object):
         assert dw.dtype == torch.float32 and dw.numel() == K * R * S * C
         d.dw = dw.data_ptr()
         self._keep = (x, dy, dw)
+        self.desc = "wgrad N%d %dx%d C%d K%d %dx%d p%d" % (N, H, W, C, K, R, S, pad)
+        self.flops = 2.0 * N * (H + 2 * pad - R + 1) * (W + 2 * pad - S + 1) * K * C * R * S
         self._h = c_void_p()
         call("ghnd_wgrad_plan_create", byref(d), byref(self._h))
 
@@ -207,6 +217,9 @@ class WgradPlan(object):
 class StemPlan(object):
     def __init__(self, x_packed, w_packed, bias, y, N, Hp, Wp):
         self._keep = (x_packed, w_packed, bias, y)
+        self.desc = "stem N%d %dx%d" % (N, Hp, Wp)
+        self.n_launches = 4
+        self.flops = 2.0 * N * (Hp // 2) * (Wp // 2) * 64 * 147
         self._h = c_void_p()
         call("ghnd_stem_conv_plan_create", ptr(x_packed), fmt_of(x_packed.dtype), ptr(w_packed),
              fmt_of(w_packed.dtype), ptr(bias), ptr(y), fmt_of(y.dtype), N, Hp, Wp, byref(self._h))

@@ -1,10 +1,12 @@
 """One eager (un-graphed) GHND step at the bench workload between cudaProfilerStart/Stop, for
-`ncu --profile-from-start off`.  Usage: python scripts/profile_step.py [batch]"""
-import os, sys
+`ncu --profile-from-start off`.  Also writes gpurun_out/step_ops.json: the tensor-core plan runs of
+the step in launch order (description, launches, FLOPs) so the ncu launch list can be joined to
+layers by scripts/join_launches.py.  Usage: python scripts/profile_step.py [batch]"""
+import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import bench
-from hnd_ghnd_object_detectors_b200 import models, module_util
+from hnd_ghnd_object_detectors_b200 import models, module_util, ops
 from hnd_ghnd_object_detectors_b200.tool import DistillationBox
 
 batch = int(sys.argv[1]) if len(sys.argv) > 1 else bench.PER_GPU_BATCH
@@ -25,8 +27,21 @@ targets = [{"boxes": torch.tensor([[10., 10., 100., 100.]], device=dev), "labels
 box(images, targets)
 box(images, targets)
 torch.cuda.synchronize()
+
+trace = []
+def wrap(cls, kernel):
+    orig = cls.run
+    def run(self, stream=None):
+        trace.append({"kernel": kernel, "desc": self.desc, "launches": getattr(self, "n_launches", 1),
+                      "flops": self.flops})
+        return orig(self, stream)
+    cls.run = run
+wrap(ops.ConvPlan, "conv_tc_kernel"); wrap(ops.StemPlan, "conv_tc_kernel"); wrap(ops.WgradPlan, "wgrad_tc_kernel")
 torch.cuda.cudart().cudaProfilerStart()
 box(images, targets)
 torch.cuda.synchronize()
 torch.cuda.cudart().cudaProfilerStop()
-print("profiled one step")
+os.makedirs("gpurun_out", exist_ok=True)
+with open("gpurun_out/step_ops.json", "w") as f:
+    json.dump(trace, f)
+print("profiled one step, %d plan runs" % len(trace))

@@ -204,6 +204,34 @@ def test_conv_dgrad(ops, case):
     assert rel(got, ref) < 4e-3, rel(got, ref)
 
 
+@pytest.mark.parametrize("case", [(2, 21, 35, 64, 256, 2, 1), (1, 22, 36, 256, 64, 2, 1), (2, 23, 37, 64, 128, 2, 0),
+                                  (3, 19, 33, 128, 256, 2, 0), (2, 25, 42, 64, 256, 1, 0)])
+def test_conv_fused_stats(ops, case):
+    """BatchNorm batch statistics fused into the conv epilogue: per-channel sum / sum of squares of
+    the STORED (rounded) output, ragged tile edges excluded.  fp32 partial sums per CTA, fp64 across
+    CTAs: relative error <= 2e-5 against fp64 sums of the stored tensor."""
+    from hnd_ghnd_object_detectors_b200 import _lib
+    N, H, W, C, K, R, pad = case
+    dtype = torch.float16
+    x, w = _conv_inputs(N, H, W, C, K, R, dtype, seed=3)
+    xd = ops.to_nhwc16(x.cuda(), dtype)
+    wd = ops.pack_weight(w.cuda(), None, False, dtype)
+    Ho, Wo = H + 2 * pad - R + 1, W + 2 * pad - R + 1
+    y = torch.zeros((N, Ho, Wo, K), dtype=dtype, device="cuda")
+    stats = torch.full((2 * K,), 7.0, dtype=torch.float64, device="cuda")  # the plan zeroes it
+    plan = ops.ConvPlan(_lib.CONV_FWD, N, H, W, C, K, R, R, 1, pad, xd, wd, y, stats=stats)
+    for _ in range(2):  # second run: no accumulation across runs
+        plan.run()
+    torch.cuda.synchronize()
+    ref = F.conv2d(x, w, None, 1, pad)
+    assert rel(ops.to_nchw_f32(y).cpu(), ref) < 1e-3
+    yd = y.double().reshape(-1, K)
+    s_ref, q_ref = yd.sum(0), (yd * yd).sum(0)
+    got = stats.cpu()
+    assert float((got[:K] - s_ref.cpu()).abs().max() / s_ref.abs().max().cpu()) < 2e-5
+    assert float(((got[K:] - q_ref.cpu()).abs() / q_ref.cpu()).max()) < 2e-5
+
+
 def test_conv_mixed_formats_rejected(ops):
     """tcgen05 kind::f16 raises an illegal-instruction fault for f16 x bf16 operands on sm_100a
     (measured in round 1), so the boundary refuses mixed formats on the host."""
