@@ -83,6 +83,9 @@ SIGNATURES = {
     "ghnd_maxpool3x3s2_bwd": (_I, [_P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P]),
     "ghnd_stem_wgrad_workspace_bytes": (_Z, []),
     "ghnd_stem_wgrad": (_I, [_P, _I, _P, _I, _P, _P, _I, _I, _I, _P, _Z, _P]),
+    "ghnd_stem_wgrad_plan_create": (_I, [_P, _P, _I, _P, _P, _I, _I, _I, _P, _Z, _P]),
+    "ghnd_stem_wgrad_plan_run": (_I, [_P, _P]),
+    "ghnd_stem_wgrad_plan_destroy": (None, [_P]),
     "ghnd_bn_stats": (_I, [_P, _I, _I, _I, _L, _I, _P, _P]),
     "ghnd_bn_finalize": (_I, [_P, _L, _I, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P]),
     "ghnd_bn_eval_params": (_I, [_I, _P, _P, _P, _P, _F, _P, _P]),

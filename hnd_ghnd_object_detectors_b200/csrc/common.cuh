@@ -220,6 +220,19 @@ __device__ __forceinline__ void tc_fence_before() {
 __device__ __forceinline__ void tc_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
+// one lane of a fully converged warp (the role warps run their loops with all 32 lanes so that
+// ptxas keeps addresses / descriptors in uniform registers; only the issue itself is elected)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 // D[tmem] (+)= A[smem desc] * B[smem desc]; issued by ONE thread.
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
                                          uint32_t idesc, uint32_t accumulate) {

@@ -367,6 +367,10 @@ static bool pow2_lanes(int cw) {
   return cw % 8 == 0 && l >= 1 && l <= 32 && (l & (l - 1)) == 0;
 }
 
+void launch_stem_wgrad_finish(const float* accum, const float* scale, float* dw, cudaStream_t st) {
+  stem_wgrad_finish_kernel<<<(64 * 3 * 49 + 255) / 256, 256, 0, st>>>(accum, scale, dw);
+}
+
 }  // namespace ghnd
 
 extern "C" {

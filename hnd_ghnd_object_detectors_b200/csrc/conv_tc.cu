@@ -91,18 +91,6 @@ __device__ __forceinline__ uint32_t swz_off(int row, int chunk16) {
   return (uint32_t)(row * 128 + ((chunk16 ^ (row & 7)) << 4));
 }
 
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "elect.sync _|p, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t"
-      "}\n"
-      : "=r"(pred));
-  return pred != 0;
-}
-
 // One GEMM-K unit = KSTEPS tcgen05.mma (K=16 each) whose descriptors differ only in the 14-bit
 // start-address field of the low word (+2 = 32 bytes along the swizzled row per step).  Written as
 // one asm block on 32-bit descriptor halves so that ptxas keeps everything in uniform registers and

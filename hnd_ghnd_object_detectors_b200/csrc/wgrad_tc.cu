@@ -43,6 +43,30 @@ struct WgradParams {
   int K, C;
 };
 
+
+// the two K=16 MMAs of one 32-pixel stage for one tap (second descriptor = +2048 B)
+__device__ __forceinline__ void umma_pair_wg(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo,
+                                             uint32_t desc_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      ".reg .b64 da, db;\n\t"
+      ".reg .b32 a, b;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "setp.eq.b32 q, 0, 0;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t"
+      "add.u32 a, %1, 128;\n\t"
+      "add.u32 b, %2, 128;\n\t"
+      "mov.b64 da, {a, %3};\n\t"
+      "mov.b64 db, {b, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, q;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 __global__ void __launch_bounds__(kWgThreads, 1)
     wgrad_tc_kernel(const __grid_constant__ WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -54,7 +78,7 @@ __global__ void __launch_bounds__(kWgThreads, 1)
   uint64_t* done_bar = bars + 2 * p.n_stages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -71,7 +95,7 @@ __global__ void __launch_bounds__(kWgThreads, 1)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
   // block decomposition
   const int block = blockIdx.x / p.splits;
@@ -84,21 +108,22 @@ __global__ void __launch_bounds__(kWgThreads, 1)
   const int b_tap_bytes = p.col_boxes * kWgBox;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      const int tiles_per_img = p.ho * p.tiles_w;
-      for (int t = t_begin; t < t_end; ++t) {
-        const int img = t / tiles_per_img;
-        const int rem = t - img * tiles_per_img;
-        const int h = rem / p.tiles_w;
-        const int w0 = (rem - h * p.tiles_w) * kWgPix;
-        mbar_wait(&empty_bar[stage], phase ^ 1);
+    // TMA producer: whole warp converged, one elected lane issues
+    int stage = 0;
+    uint32_t phase = 0;
+    const int tiles_per_img = p.ho * p.tiles_w;
+    for (int t = t_begin; t < t_end; ++t) {
+      const int img = t / tiles_per_img;
+      const int rem = t - img * tiles_per_img;
+      const int h = rem / p.tiles_w;
+      const int w0 = (rem - h * p.tiles_w) * kWgPix;
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      if (elect_one()) {
         uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
         uint8_t* sb = sa + a_bytes;
         mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)p.stage_bytes);
-        // rows operand: unshifted when it is dy, shifted per tap when it is x
         if (p.rows_is_dy) {
+          // rows operand = dy (unshifted), cols operand = x shifted per tap
           for (int b = 0; b < p.row_boxes; ++b)
             tma_load_4d(sa + b * kWgBox, &p.tmap_row, &full_bar[stage], m_tile * 128 + b * 64, w0, h,
                         img);
@@ -109,9 +134,7 @@ __global__ void __launch_bounds__(kWgThreads, 1)
                           n_chunk * p.nb + b * 64, w0 + dw, h + dh, img);
           }
         } else {
-          // rows = x channels: one dy box set (cols), n_taps shifted x box sets (rows).
-          // smem order stays [A region = cols operand here? no: keep A = rows operand]
-          // A region holds n_taps shifted x tiles, B region holds the single dy tile.
+          // rows = x channels: A region holds n_taps shifted x tiles, B region the single dy tile
           for (int tap = 0; tap < p.n_taps; ++tap) {
             const int dh = tap / p.S - p.pad, dw = tap % p.S - p.pad;
             for (int b = 0; b < p.row_boxes; ++b)
@@ -123,23 +146,28 @@ __global__ void __launch_bounds__(kWgThreads, 1)
             tma_load_4d(sd + b * kWgBox, &p.tmap_col, &full_bar[stage], n_chunk * p.nb + b * 64, w0,
                         h, img);
         }
-        if (++stage == p.n_stages) {
-          stage = 0;
-          phase ^= 1;
-        }
+      }
+      __syncwarp();
+      if (++stage == p.n_stages) {
+        stage = 0;
+        phase ^= 1;
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      // rows operand with a single 64-channel box: rows 64..127 alias rows 0..63 (LBO = 0)
-      const uint32_t a_lbo = p.row_boxes == 2 ? kWgBox : 0;
-      const uint32_t b_lbo = kWgBox;
-      for (int t = t_begin; t < t_end; ++t) {
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
+    // MMA issuer: whole warp converged, one elected lane issues; descriptors built from uniform
+    // 32-bit halves so the UTCHMMAs issue back to back from uniform registers
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t smem_base = smem_u32(smem);
+    // rows operand with a single 64-channel box: rows 64..127 alias rows 0..63 (LBO = 0)
+    const uint32_t a_lbo = p.row_boxes == 2 ? kWgBox : 0;
+    const uint32_t b_lbo = kWgBox;
+    const uint32_t desc_hi = (1024u >> 4) | (1u << 14) | ((uint32_t)UMMA_SW128 << 29);
+    for (int t = t_begin; t < t_end; ++t) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sa = smem_base + (uint32_t)(stage * p.stage_bytes);
         for (int tap = 0; tap < p.n_taps; ++tap) {
           uint32_t a_addr, b_addr;
           if (p.rows_is_dy) {
@@ -149,23 +177,22 @@ __global__ void __launch_bounds__(kWgThreads, 1)
             a_addr = sa + tap * a_bytes;
             b_addr = sa + p.n_taps * a_bytes;
           }
-          const uint64_t adesc = make_smem_desc(a_addr, a_lbo, 1024, UMMA_SW128);
-          const uint64_t bdesc = make_smem_desc(b_addr, b_lbo, 1024, UMMA_SW128);
-#pragma unroll
-          for (int k = 0; k < kWgPix / 16; ++k) {
-            // 16 pixels = two 8-row swizzle groups = 2048 B -> +128 in (addr >> 4)
-            umma_f16(tmem_base + (uint32_t)(tap * 128), adesc + (uint64_t)(128 * k),
-                     bdesc + (uint64_t)(128 * k), p.idesc, (uint32_t)((t != t_begin) || (k != 0)));
-          }
+          const uint32_t a_lo = ((a_addr >> 4) & 0x3fffu) | ((a_lbo >> 4) << 16);
+          const uint32_t b_lo = ((b_addr >> 4) & 0x3fffu) | ((b_lbo >> 4) << 16);
+          // 16 pixels = two 8-row swizzle groups = 2048 B -> +128 in (addr >> 4)
+          umma_pair_wg(tmem_base + (uint32_t)(tap * 128), a_lo, b_lo, desc_hi, p.idesc,
+                       (uint32_t)(t != t_begin));
         }
         umma_commit(&empty_bar[stage]);
-        if (++stage == p.n_stages) {
-          stage = 0;
-          phase ^= 1;
-        }
       }
-      umma_commit(done_bar);
+      __syncwarp();
+      if (++stage == p.n_stages) {
+        stage = 0;
+        phase ^= 1;
+      }
     }
+    if (elect_one()) umma_commit(done_bar);
+    __syncwarp();
   } else {
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;

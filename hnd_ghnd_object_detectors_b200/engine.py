@@ -176,6 +176,10 @@ class StemRunner(object):
         if trainable:
             self.g_conv = _empty((N, Hp // 2, Wp // 2, 64), grad_dtype, dev)
             self.ws = _empty((_lib.load().ghnd_stem_wgrad_workspace_bytes(),), torch.uint8, dev)
+            # the tensor-core dW needs image and gradient in ONE 16-bit format: keep a copy of the
+            # packed image in the gradient dtype (refreshed every step, 2 x 35 MB of traffic)
+            self.packed_g = packed if packed.dtype == grad_dtype else torch.zeros_like(packed, dtype=grad_dtype)
+            self.wgrad = None
 
     def refresh_weights(self):
         ops.stem_pack_weight(self.body.conv1.weight, self.scale, out=self.w)
@@ -189,7 +193,13 @@ class StemRunner(object):
     def backward(self, g_out, dw):
         """g_out: gradient w.r.t. the pooled output; dw: fp32 OIHW view for conv1.weight.grad."""
         ops.maxpool3x3s2_bwd(self.conv, self.argmax, g_out, self.g_conv)
-        ops.stem_wgrad(self.packed, self.g_conv, self.scale, dw, self.N, self.Hp, self.Wp, ws=self.ws)
+        if self.packed_g is not self.packed:
+            ops.convert16(self.packed, self.packed_g)
+        if self.wgrad is None or self.wgrad_dw is not dw:
+            self.wgrad = ops.StemWgradPlan(self.packed_g, self.g_conv, self.scale, dw, self.N, self.Hp, self.Wp,
+                                           ws=self.ws)
+            self.wgrad_dw = dw
+        self.wgrad.run()
 
 
 class _BN(object):

@@ -384,6 +384,35 @@ def stem_wgrad(x_packed, g, scale, dw, N, Hp, Wp, ws=None):
     return dw
 
 
+class StemWgradPlan(object):
+    """conv1 weight gradient on tcgen05; x_packed and g must share one 16-bit dtype."""
+
+    def __init__(self, x_packed, g, scale, dw, N, Hp, Wp, ws=None):
+        assert x_packed.dtype == g.dtype, "stem wgrad: packed image and gradient must share one 16-bit dtype"
+        nbytes = _lib.load().ghnd_stem_wgrad_workspace_bytes()
+        if ws is None:
+            ws = _ws(nbytes, g.device)
+        self._keep = (x_packed, g, scale, dw, ws)
+        self._h = c_void_p()
+        call("ghnd_stem_wgrad_plan_create", ptr(x_packed), ptr(g), fmt_of(g.dtype), ptr(scale), ptr(dw), N, Hp,
+             Wp, ptr(ws), nbytes, byref(self._h))
+        self.desc = "stem_wgrad N%d %dx%d" % (N, Hp, Wp)
+        self.flops = 2.0 * N * (Hp // 2) * (Wp // 2) * 64 * 147
+
+    def run(self, stream=None):
+        call("ghnd_stem_wgrad_plan_run", self._h, stream_ptr(stream))
+        _count(2)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                _lib.load().ghnd_stem_wgrad_plan_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+
 # ------------------------------------------------------------------------------------------------
 # BatchNorm (training) and Adam
 # ------------------------------------------------------------------------------------------------

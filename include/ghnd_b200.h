@@ -227,6 +227,17 @@ int ghnd_stem_wgrad(const void* x_packed, int x_fmt, const void* g, int g_fmt,
                     const float* scale_o, float* dw_oihw, int N, int Hp, int Wp, void* workspace,
                     size_t workspace_bytes, void* stream);
 
+/* Same dW on tcgen05 tensor cores: GEMM M = (filter row, 8 px x 4 ch window) = 7 x 32, N = 64,
+ * K = output pixels, both operands MN-major straight from the NHWC tensors by TMA.  x_packed and g
+ * must share ONE 16-bit format (tcgen05 kind::f16 restriction), so the caller keeps a copy of the
+ * packed image in the gradient format.  workspace as for ghnd_stem_wgrad. */
+typedef struct ghnd_stem_wgrad_plan ghnd_stem_wgrad_plan_t;
+int ghnd_stem_wgrad_plan_create(const void* x_packed, const void* g, int fmt, const float* scale_o,
+                                float* dw_oihw, int N, int Hp, int Wp, void* workspace,
+                                size_t workspace_bytes, ghnd_stem_wgrad_plan_t** plan);
+int ghnd_stem_wgrad_plan_run(const ghnd_stem_wgrad_plan_t* plan, void* stream);
+void ghnd_stem_wgrad_plan_destroy(ghnd_stem_wgrad_plan_t* plan);
+
 /* ------------------------------------------------------------------------------------------
  * Training-mode BatchNorm2d around the student's layer1 convs (nn.BatchNorm2d forward/backward,
  * resnet_layer.py:43-64; batch statistics, biased var for normalisation, unbiased for running).

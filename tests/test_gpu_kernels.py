@@ -439,6 +439,31 @@ def test_stem(ops, dt):
     assert rel(dw.cpu(), dw_ref) < 2e-3, rel(dw.cpu(), dw_ref)
 
 
+@pytest.mark.parametrize("geom", [(2, 96, 128), (1, 64, 168), (3, 32, 72)])
+def test_stem_wgrad_tensor_core(ops, geom):
+    """conv1 dW on tcgen05 (MN-major SW64 x SW128 operands) against fp32 conv2d_weight on the same
+    bf16-rounded image and gradient: rel L2 <= 2e-3; must also agree with the SIMT kernel."""
+    N, Hp, Wp = geom
+    g = torch.Generator().manual_seed(11)
+    x = r16(torch.randn(N, 3, Hp, Wp, generator=g), torch.bfloat16)
+    gy = r16(torch.randn(N, 64, Hp // 2, Wp // 2, generator=g), torch.bfloat16)
+    scale = torch.rand(64, generator=g) + 0.5
+    dw_ref = torch.nn.grad.conv2d_weight(x, (64, 3, 7, 7), gy, stride=2, padding=3) * scale[:, None, None, None]
+    packed = torch.zeros((N, Hp + 6, Wp + 8, 4), dtype=torch.bfloat16, device="cuda")
+    packed[:, 3:3 + Hp, 3:3 + Wp, :3] = x.permute(0, 2, 3, 1).to(torch.bfloat16).cuda()
+    gd = ops.to_nhwc16(gy.cuda(), torch.bfloat16)
+    dw = torch.zeros(64, 3, 7, 7, device="cuda")
+    plan = ops.StemWgradPlan(packed, gd, scale.cuda(), dw, N, Hp, Wp)
+    for _ in range(2):  # re-runnable: the plan clears its workspace
+        plan.run()
+    torch.cuda.synchronize()
+    assert rel(dw.cpu(), dw_ref) < 2e-3, rel(dw.cpu(), dw_ref)
+    dw2 = torch.zeros(64, 3, 7, 7, device="cuda")
+    ops.stem_wgrad(packed, gd, scale.cuda(), dw2, N, Hp, Wp)
+    torch.cuda.synchronize()
+    assert rel(dw.cpu(), dw2.cpu()) < 1e-3
+
+
 def test_adam(ops):
     torch.manual_seed(0)
     n = 586566
