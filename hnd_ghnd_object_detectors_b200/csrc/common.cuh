@@ -78,6 +78,59 @@ __device__ __forceinline__ float2 unpack2(uint32_t v, int fmt) {
   return r;
 }
 
+// compile-time format variants (hot loops are instantiated per format instead of branching)
+template <int FMT>
+__device__ __forceinline__ uint32_t pack2_t(float a, float b) {
+  if (FMT == GHND_F16) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+template <int FMT>
+__device__ __forceinline__ float2 unpack2_t(uint32_t v) {
+  if (FMT == GHND_F16) {
+    __half2 h = *reinterpret_cast<__half2*>(&v);
+    return __half22float2(h);
+  }
+  float2 r;
+  r.x = __uint_as_float(v << 16);
+  r.y = __uint_as_float(v & 0xffff0000u);
+  return r;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Division by a run-time constant as multiply-high + shift (host-prepared), for the single-warp
+// role loops where a hardware-emulated integer division (~40 dependent instructions) per tile is
+// a measurable share of the loop.  Exact for 0 <= n < 2^31.
+// ----------------------------------------------------------------------------------------------
+struct FastDiv {
+  uint32_t d, mul, shr;
+};
+inline FastDiv make_fastdiv(int d) {
+  FastDiv f;
+  f.d = (uint32_t)(d < 1 ? 1 : d);
+  if (f.d == 1) {
+    f.mul = 0;
+    f.shr = 0;
+  } else {
+    uint32_t lg = 0;
+    while ((1ull << lg) < f.d) ++lg;
+    const uint32_t p = 31 + lg;
+    f.mul = (uint32_t)(((1ull << p) + f.d - 1) / f.d);
+    f.shr = p - 32;
+  }
+  return f;
+}
+__device__ __forceinline__ int fd_div(const FastDiv& f, int n) {
+  return f.d == 1 ? n : (int)(__umulhi((uint32_t)n, f.mul) >> f.shr);
+}
+__device__ __forceinline__ void fd_divmod(const FastDiv& f, int n, int& q, int& r) {
+  q = fd_div(f, n);
+  r = n - q * (int)f.d;
+}
+
 // ----------------------------------------------------------------------------------------------
 // warp / block reductions
 // ----------------------------------------------------------------------------------------------

@@ -77,6 +77,7 @@ struct ConvKernelParams {
   int lim_h, lim_w; // extent of the output lattice (row validity for the fused statistics)
   int n_tiles_n;
   int total_tiles;
+  FastDiv fd_tiles_n, fd_tiles_per_img, fd_tiles_w, fd_tw, fd_ring;
   uint32_t idesc;
   // epilogue
   const float* bias;
@@ -85,6 +86,10 @@ struct ConvKernelParams {
   int relu;
   double* stats;    // optional [2*cout]: sum / sum of squares of the stored (rounded) output
 };
+
+__device__ __forceinline__ int fd_ring_r(const ConvKernelParams& p, uint32_t cnt) {
+  return (int)cnt - fd_div(p.fd_ring, (int)cnt) * (int)p.fd_ring.d;
+}
 
 __device__ __forceinline__ uint32_t swz_off(int row, int chunk16) {
   // byte offset of 16-byte chunk `chunk16` of `row` inside a 128B-swizzled [rows][128 B] tile
@@ -137,27 +142,6 @@ __device__ __forceinline__ void umma_unit(uint32_t d_tmem, uint32_t a_lo, uint32
         "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc)
         : "memory");
   }
-}
-
-template <int FMT>
-__device__ __forceinline__ uint32_t pack2_t(float a, float b) {
-  if (FMT == GHND_F16) {
-    __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
-  }
-  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
-template <int FMT>
-__device__ __forceinline__ float2 unpack2_t(uint32_t v) {
-  if (FMT == GHND_F16) {
-    __half2 h = *reinterpret_cast<__half2*>(&v);
-    return __half22float2(h);
-  }
-  float2 r;
-  r.x = __uint_as_float(v << 16);
-  r.y = __uint_as_float(v & 0xffff0000u);
-  return r;
 }
 
 // v[0..63] += the 64 channels of `row` of a swizzled 16-bit operand tile
@@ -283,7 +267,6 @@ __global__ void __launch_bounds__(kConvThreads, 1)
   const int k_chunks = p.cin / p.kblock;
   const int n_units = p.n_taps * k_chunks;
   const int upst = p.units_per_stage;
-  const int tiles_per_img = p.tiles_h * p.tiles_w;
   const int n_chunks = p.block_n >> 6;
 
   if (warp == 0) {
@@ -291,12 +274,12 @@ __global__ void __launch_bounds__(kConvThreads, 1)
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int n_tile = tile % p.n_tiles_n;
-      const int m_tile = tile / p.n_tiles_n;
-      const int img = m_tile / tiles_per_img;
-      const int rem = m_tile - img * tiles_per_img;
-      const int h0 = (rem / p.tiles_w) * p.th;
-      const int w0 = (rem % p.tiles_w) * p.tw;
+      int n_tile, m_tile, img, rem, h0, w0;
+      fd_divmod(p.fd_tiles_n, tile, m_tile, n_tile);
+      fd_divmod(p.fd_tiles_per_img, m_tile, img, rem);
+      fd_divmod(p.fd_tiles_w, rem, h0, w0);
+      h0 *= p.th;
+      w0 *= p.tw;
       int t = 0, kc = 0;
       for (int u = 0; u < n_units; u += upst) {
         const int nu = min(upst, n_units - u);
@@ -387,12 +370,12 @@ __global__ void __launch_bounds__(kConvThreads, 1)
       int slot = 0;
       uint32_t rphase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int n_tile = tile % p.n_tiles_n;
-        const int m_tile = tile / p.n_tiles_n;
-        const int img = m_tile / tiles_per_img;
-        const int rem = m_tile - img * tiles_per_img;
-        const int h0 = (rem / p.tiles_w) * p.th;
-        const int w0 = (rem % p.tiles_w) * p.tw;
+        int n_tile, m_tile, img, rem, h0, w0;
+        fd_divmod(p.fd_tiles_n, tile, m_tile, n_tile);
+        fd_divmod(p.fd_tiles_per_img, m_tile, img, rem);
+        fd_divmod(p.fd_tiles_w, rem, h0, w0);
+        h0 *= p.th;
+        w0 *= p.tw;
         for (int c = 0; c < n_chunks; ++c, ++cnt) {
           mbar_wait(&iempty_bar[slot], rphase ^ 1);
           if (elect_one()) {
@@ -425,15 +408,16 @@ __global__ void __launch_bounds__(kConvThreads, 1)
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it, cnt0 += n_chunks) {
       const int buf = it & 1;
       const uint32_t use = (uint32_t)it >> 1;
-      const int n_tile = tile % p.n_tiles_n;
-      const int m_tile = tile / p.n_tiles_n;
-      const int img = m_tile / tiles_per_img;
-      const int rem = m_tile - img * tiles_per_img;
-      const int h0 = (rem / p.tiles_w) * p.th;
-      const int w0 = (rem % p.tiles_w) * p.tw;
+      int n_tile, m_tile, img, rem, h0, w0;
+      fd_divmod(p.fd_tiles_n, tile, m_tile, n_tile);
+      fd_divmod(p.fd_tiles_per_img, m_tile, img, rem);
+      fd_divmod(p.fd_tiles_w, rem, h0, w0);
+      h0 *= p.th;
+      w0 *= p.tw;
       uint32_t valid = 0xffffffffu;
       if (p.stats != nullptr) {
-        const int rh = row / p.tw, rw = row - rh * p.tw;
+        int rh, rw;
+        fd_divmod(p.fd_tw, row, rh, rw);
         valid = __ballot_sync(0xffffffffu, rh < p.th && h0 + rh < p.lim_h && w0 + rw < p.lim_w);
       }
       // chunks of this tile handled by this group: c = c_first, c_first + 2, ...
@@ -473,9 +457,9 @@ __global__ void __launch_bounds__(kConvThreads, 1)
             v[4 * j + 3] += b.w;
           }
         }
-        const int slot = (int)(cnt % (uint32_t)p.ring);
+        const int slot = fd_ring_r(p, cnt);
         const uint8_t* in_base = epi_in + (size_t)slot * n_in * kChunkBytes;
-        if (n_in > 0) mbar_wait(&ifull_bar[slot], (cnt / (uint32_t)p.ring) & 1u);
+        if (n_in > 0) mbar_wait(&ifull_bar[slot], (uint32_t)fd_div(p.fd_ring, (int)cnt) & 1u);
         if (p.has_in0 && !p.in0_post) {
           if (p.in0_fmt == GHND_F16) epi_add_rows<GHND_F16>(v, in_base, row);
           else epi_add_rows<GHND_BF16>(v, in_base, row);
@@ -637,6 +621,10 @@ static int finish_launch(ConvLaunch* L, const ghnd_conv_desc_t* d, int gemm_cin,
   p.b_bytes = p.block_n * row_bytes;
   p.n_tiles_n = gemm_cout / p.block_n;
   p.total_tiles = m_tiles * p.n_tiles_n;
+  p.fd_tiles_n = make_fastdiv(p.n_tiles_n);
+  p.fd_tiles_per_img = make_fastdiv(p.tiles_h * p.tiles_w);
+  p.fd_tiles_w = make_fastdiv(p.tiles_w);
+  p.fd_tw = make_fastdiv(p.tw);
   // units per stage: >= ~256 tensor-pipe cycles (block_n/2 per K=16 step) behind every barrier wait
   {
     const int unit_cycles = (kblock / 16) * (p.block_n / 2);
@@ -695,6 +683,7 @@ static int finish_launch(ConvLaunch* L, const ghnd_conv_desc_t* d, int gemm_cin,
     if (ring < 2) ring = 2;
   }
   p.ring = ring > 0 ? ring : 1;
+  p.fd_ring = make_fastdiv(p.ring);
   int stages = (kSmemBudget - fixed - ring * n_in * kChunkBytes) / p.stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   (void)stages_per_tile;

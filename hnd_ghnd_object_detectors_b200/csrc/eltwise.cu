@@ -454,6 +454,196 @@ __global__ void bn_param_grads_kernel(const double* __restrict__ sums, int C,
   if (dgamma) dgamma[c] = (float)sums[C + c];
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Fast paths of the three streaming BatchNorm kernels (C/8 divides 256): a thread always meets the
+// same 8-channel group, so its per-channel constants live in registers, the loop carries no
+// division, formats are compile-time, and several 16-byte loads are in flight per thread.
+// ------------------------------------------------------------------------------------------------
+template <int XF, int YF, int Y2F, bool RELU>
+__global__ void __launch_bounds__(256)
+    bn_apply_fast_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, uint4* __restrict__ y2,
+                         int64_t nvec, int C8, const float* __restrict__ scale_shift) {
+  constexpr int U = 4;
+  const int cg = threadIdx.x % C8;
+  const int C = C8 * 8;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = __ldg(scale_shift + cg * 8 + j);
+    sh[j] = __ldg(scale_shift + C + cg * 8 + j);
+  }
+  const int64_t stride = (int64_t)gridDim.x * 256;
+  int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  auto one = [&](const uint4 v, int64_t at) {
+    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+    uint32_t o[4], o2[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = unpack2_t<XF>(u[e]);
+      float a = fmaf(f.x, sc[2 * e], sh[2 * e]);
+      float b = fmaf(f.y, sc[2 * e + 1], sh[2 * e + 1]);
+      if (RELU) {
+        a = fmaxf(a, 0.f);
+        b = fmaxf(b, 0.f);
+      }
+      o[e] = pack2_t<YF>(a, b);
+      if (Y2F >= 0) o2[e] = pack2_t<(Y2F >= 0 ? Y2F : 0)>(a, b);
+    }
+    y[at] = make_uint4(o[0], o[1], o[2], o[3]);
+    if (Y2F >= 0) y2[at] = make_uint4(o2[0], o2[1], o2[2], o2[3]);
+  };
+  for (; i + (U - 1) * stride < nvec; i += U * stride) {
+    uint4 v[U];
+#pragma unroll
+    for (int k = 0; k < U; ++k) v[k] = ld_stream(x + i + k * stride);
+#pragma unroll
+    for (int k = 0; k < U; ++k) one(v[k], i + k * stride);
+  }
+  for (; i < nvec; i += stride) one(ld_stream(x + i), i);
+}
+
+template <int XF, int GF, bool RELU>
+__global__ void __launch_bounds__(256)
+    bn_bwd_apply_fast_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x,
+                             uint4* __restrict__ dx, int64_t nvec, int C8, float inv_count,
+                             const float* __restrict__ scale_shift,
+                             const float* __restrict__ mean_invstd,
+                             const double* __restrict__ sums) {
+  constexpr int U = 2;
+  const int cg = threadIdx.x % C8;
+  const int C = C8 * 8;
+  // dx = sc*(g' - mg - xhat*mgx) with xhat = (x-mu)*is  ==  sc*g' + x*k1 + k0
+  float sc[8], sf[8], k1[8], k0[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = cg * 8 + j;
+    sc[j] = __ldg(scale_shift + c);
+    sf[j] = __ldg(scale_shift + C + c);
+    const float mu = __ldg(mean_invstd + c), is = __ldg(mean_invstd + C + c);
+    const float mg = (float)sums[c] * inv_count, mgx = (float)sums[C + c] * inv_count;
+    k1[j] = -sc[j] * is * mgx;
+    k0[j] = sc[j] * (mu * is * mgx - mg);
+  }
+  const int64_t stride = (int64_t)gridDim.x * 256;
+  int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  auto one = [&](const uint4 xv, const uint4 dv, int64_t at) {
+    const uint32_t xu[4] = {xv.x, xv.y, xv.z, xv.w}, du[4] = {dv.x, dv.y, dv.z, dv.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = unpack2_t<XF>(xu[e]);
+      float2 g = unpack2_t<GF>(du[e]);
+      if (RELU) {
+        if (!(fmaf(f.x, sc[2 * e], sf[2 * e]) > 0.f)) g.x = 0.f;
+        if (!(fmaf(f.y, sc[2 * e + 1], sf[2 * e + 1]) > 0.f)) g.y = 0.f;
+      }
+      const float r0 = fmaf(sc[2 * e], g.x, fmaf(f.x, k1[2 * e], k0[2 * e]));
+      const float r1 = fmaf(sc[2 * e + 1], g.y, fmaf(f.y, k1[2 * e + 1], k0[2 * e + 1]));
+      o[e] = pack2_t<GF>(r0, r1);
+    }
+    dx[at] = make_uint4(o[0], o[1], o[2], o[3]);
+  };
+  for (; i + (U - 1) * stride < nvec; i += U * stride) {
+    uint4 xv[U], dv[U];
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      xv[k] = ld_stream(x + i + k * stride);
+      dv[k] = ld_stream(dy + i + k * stride);
+    }
+#pragma unroll
+    for (int k = 0; k < U; ++k) one(xv[k], dv[k], i + k * stride);
+  }
+  for (; i < nvec; i += stride) one(ld_stream(x + i), ld_stream(dy + i), i);
+}
+
+// backward reduction: sums[c] += sum g', sums[C+c] += sum g'*xhat
+template <int XF, int GF, bool RELU>
+__global__ void __launch_bounds__(256)
+    bn_bwd_reduce_fast_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy, int64_t nvec,
+                              int C8, const float* __restrict__ scale_shift,
+                              const float* __restrict__ mean_invstd, double* __restrict__ sums) {
+  constexpr int U = 2;
+  extern __shared__ float sh[];  // [2*C]
+  const int C = C8 * 8;
+  const int cg = threadIdx.x % C8;
+  for (int i = threadIdx.x; i < 2 * C; i += 256) sh[i] = 0.f;
+  __syncthreads();
+  float sc[8], sf[8], mu[8], is[8], a[8], b[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = cg * 8 + j;
+    sc[j] = __ldg(scale_shift + c);
+    sf[j] = __ldg(scale_shift + C + c);
+    mu[j] = __ldg(mean_invstd + c);
+    is[j] = __ldg(mean_invstd + C + c);
+    a[j] = b[j] = 0.f;
+  }
+  const int64_t stride = (int64_t)gridDim.x * 256;
+  int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  auto one = [&](const uint4 xv, const uint4 dv) {
+    const uint32_t xu[4] = {xv.x, xv.y, xv.z, xv.w}, du[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = unpack2_t<XF>(xu[e]);
+      float2 g = unpack2_t<GF>(du[e]);
+      if (RELU) {
+        if (!(fmaf(f.x, sc[2 * e], sf[2 * e]) > 0.f)) g.x = 0.f;
+        if (!(fmaf(f.y, sc[2 * e + 1], sf[2 * e + 1]) > 0.f)) g.y = 0.f;
+      }
+      a[2 * e] += g.x;
+      a[2 * e + 1] += g.y;
+      b[2 * e] = fmaf(g.x, (f.x - mu[2 * e]) * is[2 * e], b[2 * e]);
+      b[2 * e + 1] = fmaf(g.y, (f.y - mu[2 * e + 1]) * is[2 * e + 1], b[2 * e + 1]);
+    }
+  };
+  for (; i + (U - 1) * stride < nvec; i += U * stride) {
+    uint4 xv[U], dv[U];
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      xv[k] = ld_stream(x + i + k * stride);
+      dv[k] = ld_stream(dy + i + k * stride);
+    }
+#pragma unroll
+    for (int k = 0; k < U; ++k) one(xv[k], dv[k]);
+  }
+  for (; i < nvec; i += stride) one(ld_stream(x + i), ld_stream(dy + i));
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    atomicAdd(&sh[cg * 8 + j], a[j]);
+    atomicAdd(&sh[C + cg * 8 + j], b[j]);
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < 2 * C; k += 256) atomicAdd(&sums[k], (double)sh[k]);
+}
+
+static bool fast_c8(int C) { return C >= 8 && C % 8 == 0 && C / 8 <= 256 && 256 % (C / 8) == 0; }
+
+template <int XF, int YF, int Y2F>
+static void launch_bn_apply_fast3(const uint4* x, uint4* y, uint4* y2, int64_t nvec, int C8,
+                                  const float* ss, int relu, int grid, cudaStream_t st) {
+  if (relu) bn_apply_fast_kernel<XF, YF, Y2F, true><<<grid, 256, 0, st>>>(x, y, y2, nvec, C8, ss);
+  else bn_apply_fast_kernel<XF, YF, Y2F, false><<<grid, 256, 0, st>>>(x, y, y2, nvec, C8, ss);
+}
+template <int XF, int YF>
+static void launch_bn_apply_fast2(int y2_fmt, const uint4* x, uint4* y, uint4* y2, int64_t nvec, int C8,
+                                  const float* ss, int relu, int grid, cudaStream_t st) {
+  if (y2 == nullptr) launch_bn_apply_fast3<XF, YF, -1>(x, y, y2, nvec, C8, ss, relu, grid, st);
+  else if (y2_fmt == GHND_F16) launch_bn_apply_fast3<XF, YF, GHND_F16>(x, y, y2, nvec, C8, ss, relu, grid, st);
+  else launch_bn_apply_fast3<XF, YF, GHND_BF16>(x, y, y2, nvec, C8, ss, relu, grid, st);
+}
+static void launch_bn_apply_fast(int x_fmt, int y_fmt, int y2_fmt, const uint4* x, uint4* y, uint4* y2,
+                                 int64_t nvec, int C8, const float* ss, int relu, cudaStream_t st) {
+  const int grid = grid_for(nvec, 256 * 4, 8);
+  if (x_fmt == GHND_F16) {
+    if (y_fmt == GHND_F16) launch_bn_apply_fast2<GHND_F16, GHND_F16>(y2_fmt, x, y, y2, nvec, C8, ss, relu, grid, st);
+    else launch_bn_apply_fast2<GHND_F16, GHND_BF16>(y2_fmt, x, y, y2, nvec, C8, ss, relu, grid, st);
+  } else {
+    if (y_fmt == GHND_F16) launch_bn_apply_fast2<GHND_BF16, GHND_F16>(y2_fmt, x, y, y2, nvec, C8, ss, relu, grid, st);
+    else launch_bn_apply_fast2<GHND_BF16, GHND_BF16>(y2_fmt, x, y, y2, nvec, C8, ss, relu, grid, st);
+  }
+}
+
 __global__ void __launch_bounds__(256)
     convert16_kernel(const uint4* __restrict__ x, int x_fmt, uint4* __restrict__ y, int y_fmt,
                      int64_t nvec) {
@@ -668,8 +858,12 @@ int ghnd_bn_apply(const void* x, int x_fmt, void* y, int y_fmt, void* y2, int y2
                      C % 8 == 0 && (y2 == nullptr || fmt16(y2_fmt)),
                  "bn_apply: bad argument");
   const int64_t nvec = npix * (C / 8);
-  bn_apply_kernel<<<grid_for(nvec, 256 * 2), 256, 0, (cudaStream_t)stream>>>(
-      (const uint4*)x, x_fmt, (uint4*)y, y_fmt, (uint4*)y2, y2_fmt, nvec, C / 8, scale_shift, relu);
+  if (fast_c8(C))
+    launch_bn_apply_fast(x_fmt, y_fmt, y2_fmt, (const uint4*)x, (uint4*)y, (uint4*)y2, nvec, C / 8,
+                         scale_shift, relu, (cudaStream_t)stream);
+  else
+    bn_apply_kernel<<<grid_for(nvec, 256 * 2), 256, 0, (cudaStream_t)stream>>>(
+        (const uint4*)x, x_fmt, (uint4*)y, y_fmt, (uint4*)y2, y2_fmt, nvec, C / 8, scale_shift, relu);
   GHND_LAUNCH_CHECK("bn_apply_kernel");
   return GHND_OK;
 }
@@ -699,9 +893,20 @@ int ghnd_bn_bwd_reduce(const void* dy, int dy_fmt, const void* x, int x_fmt, int
     GHND_CHECK_ARG(fmt16(dy_fmt) && fmt16(x_fmt), "bn_bwd_reduce: bad format");
     const int64_t npix = (int64_t)N * hw;
     const int lanes = 256 / (C / 8);
-    bn_reduce_nhwc_kernel<true><<<grid_for(npix, lanes * 8, 4), 256, 2 * C * sizeof(float), st>>>(
-        (const uint4*)x, x_fmt, (const uint4*)dy, dy_fmt, npix, C, scale_shift, mean_invstd, relu,
-        sums);
+    if (x_fmt == GHND_F16 && dy_fmt == GHND_BF16) {  // the engine's combination: fast path
+      const int64_t nvec = npix * (C / 8);
+      const int grid = grid_for(nvec, 256 * 4, 6);
+      if (relu)
+        bn_bwd_reduce_fast_kernel<GHND_F16, GHND_BF16, true><<<grid, 256, 2 * C * sizeof(float), st>>>(
+            (const uint4*)x, (const uint4*)dy, nvec, C / 8, scale_shift, mean_invstd, sums);
+      else
+        bn_bwd_reduce_fast_kernel<GHND_F16, GHND_BF16, false><<<grid, 256, 2 * C * sizeof(float), st>>>(
+            (const uint4*)x, (const uint4*)dy, nvec, C / 8, scale_shift, mean_invstd, sums);
+    } else {
+      bn_reduce_nhwc_kernel<true><<<grid_for(npix, lanes * 8, 4), 256, 2 * C * sizeof(float), st>>>(
+          (const uint4*)x, x_fmt, (const uint4*)dy, dy_fmt, npix, C, scale_shift, mean_invstd, relu,
+          sums);
+    }
   }
   GHND_LAUNCH_CHECK("bn_bwd_reduce_kernel");
   return GHND_OK;
@@ -724,9 +929,21 @@ int ghnd_bn_bwd_apply(const void* dy, int dy_fmt, const void* x, int x_fmt, void
   } else {
     GHND_CHECK_ARG(fmt16(dy_fmt) && fmt16(x_fmt) && fmt16(dx_fmt), "bn_bwd_apply: bad format");
     const int64_t nvec = (int64_t)N * hw * (C / 8);
-    bn_bwd_apply_nhwc_kernel<<<grid_for(nvec, 256 * 2), 256, 6 * C * sizeof(float), st>>>(
-        (const uint4*)dy, dy_fmt, (const uint4*)x, x_fmt, (uint4*)dx, dx_fmt, nvec, C / 8, inv_count,
-        gamma, scale_shift, mean_invstd, relu, sums);
+    if (x_fmt == GHND_F16 && dy_fmt == GHND_BF16 && dx_fmt == GHND_BF16) {  // engine's combination
+      const int grid = grid_for(nvec, 256 * 4, 6);
+      if (relu)
+        bn_bwd_apply_fast_kernel<GHND_F16, GHND_BF16, true><<<grid, 256, 0, st>>>(
+            (const uint4*)dy, (const uint4*)x, (uint4*)dx, nvec, C / 8, (float)inv_count, scale_shift,
+            mean_invstd, sums);
+      else
+        bn_bwd_apply_fast_kernel<GHND_F16, GHND_BF16, false><<<grid, 256, 0, st>>>(
+            (const uint4*)dy, (const uint4*)x, (uint4*)dx, nvec, C / 8, (float)inv_count, scale_shift,
+            mean_invstd, sums);
+    } else {
+      bn_bwd_apply_nhwc_kernel<<<grid_for(nvec, 256 * 2), 256, 6 * C * sizeof(float), st>>>(
+          (const uint4*)dy, dy_fmt, (const uint4*)x, x_fmt, (uint4*)dx, dx_fmt, nvec, C / 8, inv_count,
+          gamma, scale_shift, mean_invstd, relu, sums);
+    }
   }
   GHND_LAUNCH_CHECK("bn_bwd_apply_kernel");
   if (dgamma != nullptr || dbeta != nullptr) {

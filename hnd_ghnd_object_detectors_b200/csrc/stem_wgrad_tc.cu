@@ -29,6 +29,7 @@ struct StemWgradParams {
   CUtensorMap tmap_g[4];
   int n_img, ho, tiles_j;
   int total_tiles;        // n_img * ho * 4 * tiles_j
+  FastDiv fd_tiles_j, fd_ho;
   uint32_t idesc;
   float* accum;           // [64][196]
 };
@@ -103,12 +104,10 @@ __global__ void __launch_bounds__(kSwtThreads, 1)
     int stage = 0;
     uint32_t phase = 0;
     for (int t = t_begin; t < t_end; ++t) {
-      const int jt = t % p.tiles_j;
-      int rest = t / p.tiles_j;
+      int jt, rest, ho, img;
+      fd_divmod(p.fd_tiles_j, t, rest, jt);
       const int q = rest & 3;
-      rest >>= 2;
-      const int ho = rest % p.ho;
-      const int img = rest / p.ho;
+      fd_divmod(p.fd_ho, rest >> 2, img, ho);
       mbar_wait(&empty_bar[stage], phase ^ 1);
       if (elect_one()) {
         uint8_t* sa = smem + (size_t)stage * kSwtStage;
@@ -241,6 +240,8 @@ int ghnd_stem_wgrad_plan_create(const void* x_packed, const void* g, int fmt, co
   p.ho = Ho;
   p.tiles_j = (J0 + kSwtPix - 1) / kSwtPix;
   p.total_tiles = N * Ho * 4 * p.tiles_j;
+  p.fd_tiles_j = make_fastdiv(p.tiles_j);
+  p.fd_ho = make_fastdiv(Ho);
   p.idesc = make_idesc(fmt, fmt, 1, 1, 128, 64);
   p.accum = static_cast<float*>(workspace);
   plan->scale = scale_o;

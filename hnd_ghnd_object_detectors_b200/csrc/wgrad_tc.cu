@@ -38,6 +38,8 @@ struct WgradParams {
   int tiles_w;            // ceil(wo / 32)
   int total_pix_tiles;    // n_img * ho * tiles_w
   int stage_bytes, n_stages;
+  int tap_dh[kWgMaxTaps], tap_dw[kWgMaxTaps];  // x offset of every tap (already minus pad)
+  FastDiv fd_tiles_per_img, fd_tiles_w;
   uint32_t idesc;
   float* dw;              // [K][taps][C]
   int K, C;
@@ -111,12 +113,12 @@ __global__ void __launch_bounds__(kWgThreads, 1)
     // TMA producer: whole warp converged, one elected lane issues
     int stage = 0;
     uint32_t phase = 0;
-    const int tiles_per_img = p.ho * p.tiles_w;
+    // (img, h, wt) of the first tile by multiply-high division, then carried incrementally
+    int img, rem, h, wt;
+    fd_divmod(p.fd_tiles_per_img, t_begin, img, rem);
+    fd_divmod(p.fd_tiles_w, rem, h, wt);
     for (int t = t_begin; t < t_end; ++t) {
-      const int img = t / tiles_per_img;
-      const int rem = t - img * tiles_per_img;
-      const int h = rem / p.tiles_w;
-      const int w0 = (rem - h * p.tiles_w) * kWgPix;
+      const int w0 = wt * kWgPix;
       mbar_wait(&empty_bar[stage], phase ^ 1);
       if (elect_one()) {
         uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
@@ -128,7 +130,7 @@ __global__ void __launch_bounds__(kWgThreads, 1)
             tma_load_4d(sa + b * kWgBox, &p.tmap_row, &full_bar[stage], m_tile * 128 + b * 64, w0, h,
                         img);
           for (int tap = 0; tap < p.n_taps; ++tap) {
-            const int dh = tap / p.S - p.pad, dw = tap % p.S - p.pad;
+            const int dh = p.tap_dh[tap], dw = p.tap_dw[tap];
             for (int b = 0; b < p.col_boxes; ++b)
               tma_load_4d(sb + tap * b_tap_bytes + b * kWgBox, &p.tmap_col, &full_bar[stage],
                           n_chunk * p.nb + b * 64, w0 + dw, h + dh, img);
@@ -136,7 +138,7 @@ __global__ void __launch_bounds__(kWgThreads, 1)
         } else {
           // rows = x channels: A region holds n_taps shifted x tiles, B region the single dy tile
           for (int tap = 0; tap < p.n_taps; ++tap) {
-            const int dh = tap / p.S - p.pad, dw = tap % p.S - p.pad;
+            const int dh = p.tap_dh[tap], dw = p.tap_dw[tap];
             for (int b = 0; b < p.row_boxes; ++b)
               tma_load_4d(sa + tap * a_bytes + b * kWgBox, &p.tmap_row, &full_bar[stage],
                           m_tile * 128 + b * 64, w0 + dw, h + dh, img);
@@ -148,6 +150,13 @@ __global__ void __launch_bounds__(kWgThreads, 1)
         }
       }
       __syncwarp();
+      if (++wt == p.tiles_w) {
+        wt = 0;
+        if (++h == p.ho) {
+          h = 0;
+          ++img;
+        }
+      }
       if (++stage == p.n_stages) {
         stage = 0;
         phase ^= 1;
@@ -210,7 +219,11 @@ __global__ void __launch_bounds__(kWgThreads, 1)
               const int k = m_tile * 128 + row;
               float* dst = p.dw + ((size_t)k * taps + tap) * p.C + n_chunk * p.nb + c;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(r[j]));
+              for (int j = 0; j < 32; j += 4)  // 16-byte vector reductions (dst is 128 B aligned)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j),
+                             "f"(__uint_as_float(r[j])), "f"(__uint_as_float(r[j + 1])),
+                             "f"(__uint_as_float(r[j + 2])), "f"(__uint_as_float(r[j + 3]))
+                             : "memory");
             } else {
               const int cc = m_tile * 128 + row;
               const int k0 = n_chunk * p.nb + c;
@@ -283,6 +296,12 @@ int ghnd_wgrad_plan_create(const ghnd_wgrad_desc_t* d, ghnd_wgrad_plan_t** out) 
   p.wo = Wo;
   p.tiles_w = (Wo + kWgPix - 1) / kWgPix;
   p.total_pix_tiles = d->N * Ho * p.tiles_w;
+  p.fd_tiles_per_img = make_fastdiv(Ho * p.tiles_w);
+  p.fd_tiles_w = make_fastdiv(p.tiles_w);
+  for (int tap = 0; tap < p.n_taps; ++tap) {
+    p.tap_dh[tap] = tap / d->S - d->pad;
+    p.tap_dw[tap] = tap % d->S - d->pad;
+  }
   const int blocks = p.m_tiles * p.n_chunks;
   int splits = num_sms() / blocks;
   if (splits < 1) splits = 1;
