@@ -255,14 +255,14 @@ __global__ void __launch_bounds__(kConvThreads, 1)
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
-  if (p.bias != nullptr)
-    for (int i = threadIdx.x; i < p.cout; i += kConvThreads) sbias[i] = __ldg(p.bias + i);
-  if (p.stats != nullptr)
-    for (int i = threadIdx.x; i < 2 * p.cout; i += kConvThreads) sstat[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  // Programmatic dependent launch: everything above overlapped the previous kernel's tail; from
+  // here on global memory written by it is read, so wait for its completion + flush.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   const int k_chunks = p.cin / p.kblock;
   const int n_units = p.n_taps * k_chunks;
@@ -403,6 +403,12 @@ __global__ void __launch_bounds__(kConvThreads, 1)
     const int etid = threadIdx.x - (kEpiWarp0 + 4 * group) * 32;
     const int bar_id = 1 + group;
     uint8_t* o_base = epi_out + (size_t)group * kChunkBytes;
+    // bias / statistics scratch are only needed here: fill them off the producer/MMA critical path
+    if (p.bias != nullptr)
+      for (int i = threadIdx.x - kEpiWarp0 * 32; i < p.cout; i += kEpiThreads) sbias[i] = __ldg(p.bias + i);
+    if (p.stats != nullptr)
+      for (int i = threadIdx.x - kEpiWarp0 * 32; i < 2 * p.cout; i += kEpiThreads) sstat[i] = 0.f;
+    named_bar_sync(3, kEpiThreads);
     int it = 0;
     uint32_t cnt0 = 0;  // global chunk counter at the start of the tile
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it, cnt0 += n_chunks) {
@@ -698,6 +704,24 @@ static int finish_launch(ConvLaunch* L, const ghnd_conv_desc_t* d, int gemm_cin,
   return GHND_OK;
 }
 
+// Launch with the programmatic-stream-serialization attribute: the kernel's prologue (barrier init,
+// TMEM allocation, tensor-map prefetch) may start while the previous kernel of the stream drains;
+// the kernel itself waits (griddepcontrol.wait) before touching global memory.
+static cudaError_t launch_conv(const ConvLaunch& L, cudaStream_t st) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)L.grid, 1, 1);
+  cfg.blockDim = dim3(kConvThreads, 1, 1);
+  cfg.dynamicSmemBytes = L.smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, conv_tc_kernel, L.p);
+}
+
 static bool fmt_ok(int f) { return f == GHND_F16 || f == GHND_BF16; }
 
 static int set_conv_attr() {
@@ -873,8 +897,7 @@ int ghnd_conv_plan_run(const ghnd_conv_plan_t* plan, void* stream) {
     if (L.p.stats != nullptr)
       GHND_CUDA(cudaMemsetAsync(L.p.stats, 0, (size_t)2 * L.p.cout * sizeof(double),
                                 (cudaStream_t)stream));
-    conv_tc_kernel<<<L.grid, kConvThreads, L.smem, (cudaStream_t)stream>>>(L.p);
-    GHND_LAUNCH_CHECK("conv_tc_kernel");
+    GHND_CUDA(launch_conv(L, (cudaStream_t)stream));
   }
   return GHND_OK;
 }
@@ -960,8 +983,7 @@ int ghnd_stem_conv_plan_run(const ghnd_stem_plan_t* plan, void* stream) {
   using namespace ghnd;
   GHND_CHECK_ARG(plan != nullptr, "stem_conv_plan_run: null plan");
   for (const ConvLaunch& L : plan->launches) {
-    conv_tc_kernel<<<L.grid, kConvThreads, L.smem, (cudaStream_t)stream>>>(L.p);
-    GHND_LAUNCH_CHECK("conv_tc_kernel(stem)");
+    GHND_CUDA(launch_conv(L, (cudaStream_t)stream));
   }
   return GHND_OK;
 }

@@ -81,18 +81,19 @@ __global__ void stem_pack_kernel(const float* __restrict__ img, int H, int W, fl
 // ------------------------------------------------------------------------------------------------
 // max-pool 3x3 s2 p1 (NHWC, 8 channels per thread) + backward fused with the ReLU mask
 // ------------------------------------------------------------------------------------------------
-__global__ void maxpool_kernel(const uint4* __restrict__ x, uint4* __restrict__ y,
+// grid = (ceil(Wo*C8/256), Ho, N): no per-element division (C8 is a power of two: shift)
+__global__ void __launch_bounds__(256)
+    maxpool_kernel(const uint4* __restrict__ x, uint4* __restrict__ y,
                                uint2* __restrict__ argmax, int fmt, int N, int H, int W, int C8,
-                               int Ho, int Wo) {
-  const int64_t total = (int64_t)N * Ho * Wo * C8;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % C8);
-    int64_t t = i / C8;
-    const int wo = (int)(t % Wo);
-    t /= Wo;
-    const int ho = (int)(t % Ho);
-    const int n = (int)(t / Ho);
+                               int c8_shift, int Ho, int Wo) {
+  {
+    const int v = blockIdx.x * 256 + threadIdx.x;
+    if (v >= Wo * C8) return;
+    const int cg = v & (C8 - 1);
+    const int wo = v >> c8_shift;
+    const int ho = blockIdx.y;
+    const int n = blockIdx.z;
+    const int64_t i = (((int64_t)n * Ho + ho) * Wo + wo) * C8 + cg;
     float best[8];
     uint32_t idx[8];
 #pragma unroll
@@ -139,19 +140,19 @@ __global__ void maxpool_kernel(const uint4* __restrict__ x, uint4* __restrict__ 
   }
 }
 
-__global__ void maxpool_bwd_kernel(const uint4* __restrict__ x, int x_fmt,
+__global__ void __launch_bounds__(256)
+    maxpool_bwd_kernel(const uint4* __restrict__ x, int x_fmt,
                                    const uint2* __restrict__ argmax, const uint4* __restrict__ dy,
                                    int dy_fmt, uint4* __restrict__ dx, int dx_fmt, int N, int H, int W,
-                                   int C8, int Ho, int Wo) {
-  const int64_t total = (int64_t)N * H * W * C8;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % C8);
-    int64_t t = i / C8;
-    const int w = (int)(t % W);
-    t /= W;
-    const int h = (int)(t % H);
-    const int n = (int)(t / H);
+                                   int C8, int c8_shift, int Ho, int Wo) {
+  {
+    const int v = blockIdx.x * 256 + threadIdx.x;
+    if (v >= W * C8) return;
+    const int cg = v & (C8 - 1);
+    const int w = v >> c8_shift;
+    const int h = blockIdx.y;
+    const int n = blockIdx.z;
+    const int64_t i = (((int64_t)n * H + h) * W + w) * C8 + cg;
     float g[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) g[j] = 0.f;
@@ -780,9 +781,14 @@ int ghnd_maxpool3x3s2(const void* x, void* y, void* argmax, int fmt, int N, int 
   GHND_CHECK_ARG(x && y && fmt16(fmt) && N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0,
                  "maxpool3x3s2: bad argument");
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
-  const int64_t total = (int64_t)N * Ho * Wo * (C / 8);
-  maxpool_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const uint4*)x, (uint4*)y, (uint2*)argmax, fmt, N, H, W, C / 8, Ho, Wo);
+  const int C8 = C / 8;
+  GHND_CHECK_ARG((C8 & (C8 - 1)) == 0 && Ho <= 65535 && N <= 65535,
+                 "maxpool3x3s2: C/8 must be a power of two (C=%d)", C);
+  int shift = 0;
+  while ((1 << shift) < C8) ++shift;
+  dim3 grid((unsigned)((Wo * C8 + 255) / 256), (unsigned)Ho, (unsigned)N);
+  maxpool_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)y, (uint2*)argmax, fmt,
+                                                         N, H, W, C8, shift, Ho, Wo);
   GHND_LAUNCH_CHECK("maxpool_kernel");
   return GHND_OK;
 }
@@ -793,10 +799,15 @@ int ghnd_maxpool3x3s2_bwd(const void* x, int x_fmt, const void* argmax, const vo
                  "maxpool3x3s2_bwd: bad argument");
   GHND_CHECK_ARG(N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "maxpool3x3s2_bwd: bad geometry");
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
-  const int64_t total = (int64_t)N * H * W * (C / 8);
-  maxpool_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+  const int C8 = C / 8;
+  GHND_CHECK_ARG((C8 & (C8 - 1)) == 0 && H <= 65535 && N <= 65535,
+                 "maxpool3x3s2_bwd: C/8 must be a power of two (C=%d)", C);
+  int shift = 0;
+  while ((1 << shift) < C8) ++shift;
+  dim3 grid((unsigned)((W * C8 + 255) / 256), (unsigned)H, (unsigned)N);
+  maxpool_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
       (const uint4*)x, x_fmt, (const uint2*)argmax, (const uint4*)dy, dy_fmt, (uint4*)dx, dx_fmt, N, H,
-      W, C / 8, Ho, Wo);
+      W, C8, shift, Ho, Wo);
   GHND_LAUNCH_CHECK("maxpool_bwd_kernel");
   return GHND_OK;
 }
