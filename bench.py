@@ -61,7 +61,7 @@ class ClockSampler(object):
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -94,6 +94,15 @@ class ClockSampler(object):
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
                 "samples": len(sm)}
+
+
+def ncu_traffic():
+    """DRAM bytes of the conv family from the committed ncu capture (profiles/), if present."""
+    path = os.path.join(ROOT, "profiles", "r1_conv_dram_traffic.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            return json.load(f)
+    return {}
 
 
 def measured_peaks():
@@ -179,28 +188,74 @@ def conv_flops_per_step(plan):
     return total
 
 
-def time_conv_family(plan):
-    """CUDA-event time of all conv_tc_kernel launches of one (eager, un-graphed) step."""
+def time_entry_points(fn):
+    """CUDA-event time of every C-ABI entry point called by fn() (one eager, un-graphed pass):
+    {name: (seconds, calls)}.  Events are recorded on torch's current stream, which is the stream
+    every kernel of the path is launched on."""
     import torch
-    from hnd_ghnd_object_detectors_b200 import ops
+    from hnd_ghnd_object_detectors_b200 import _lib, ops
     spans = []
-    orig_conv, orig_stem = ops.ConvPlan.run, ops.StemPlan.run
+    orig_ops, orig_lib = ops.call, _lib.call
 
-    def wrap(fn):
-        def run(self, stream=None):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            fn(self, stream)
-            b.record()
-            spans.append((a, b))
-        return run
-    ops.ConvPlan.run, ops.StemPlan.run = wrap(orig_conv), wrap(orig_stem)
+    def timed_call(name, *a):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        orig_lib(name, *a)
+        e1.record()
+        spans.append((name, e0, e1))
+    ops.call = _lib.call = timed_call
     try:
-        plan.forward_backward()
+        fn()
         torch.cuda.synchronize()
     finally:
-        ops.ConvPlan.run, ops.StemPlan.run = orig_conv, orig_stem
-    return sum(a.elapsed_time(b) for a, b in spans) * 1e-3, len(spans)
+        ops.call, _lib.call = orig_ops, orig_lib
+    out = {}
+    for name, e0, e1 in spans:
+        t, c = out.get(name, (0.0, 0))
+        out[name] = (t + e0.elapsed_time(e1) * 1e-3, c + 1)
+    return out
+
+
+def encode_sweep(dev, batches, iters=10):
+    """Config 5: Keypoint R-CNN b3ch split-computing head (stem + layer1 encoder + 8-bit quantizer),
+    images/s per batch size, inputs resident in HBM; also the quantizer's achieved HBM GB/s."""
+    import torch
+    from hnd_ghnd_object_detectors_b200 import models
+    from hnd_ghnd_object_detectors_b200.split_rcnn import split_rcnn_model
+    cfg = model_config(True)
+    cfg["name"] = "keypoint_rcnn"
+    cfg["params"] = {"num_classes": 2, "pretrained": False, "num_keypoints": 17}
+    torch.manual_seed(0)
+    model = models.get_model(cfg, dev).eval()
+    head, _ = split_rcnn_model(model, 8)
+    out = {}
+    g = torch.Generator().manual_seed(5)
+    pool = [torch.rand(3, IMG_H, IMG_W, generator=g).to(dev) for _ in range(4)]
+    quant_gbs = None
+    for b in batches:
+        images = [pool[i % len(pool)] for i in range(b)]
+        head(images)  # builds + captures the fixed-shape plan
+        plan = head.plan
+        for _ in range(3):
+            plan.run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            plan.run()
+        e1.record()
+        torch.cuda.synchronize()
+        out[str(b)] = b * iters / (e0.elapsed_time(e1) * 1e-3)
+        if b == batches[-1]:
+            plan_graph, plan.graph = plan.graph, None
+            try:
+                t = time_entry_points(plan.run)
+            finally:
+                plan.graph = plan_graph
+            if "ghnd_quantize_u8" in t:
+                quant_gbs = 5.0 * plan.z.numel() / t["ghnd_quantize_u8"][0] / 1e9
+        head.plan = None
+    return out, quant_gbs
 
 
 def run_cuda(args):
@@ -295,17 +350,48 @@ def run_cuda(args):
     value = images_per_step * args.steps / (ms * 1e-3)
     e2e_value = images_per_step * e2e_steps / (ms_e2e * 1e-3)
 
-    roof = cpu = None
+    roof = cpu = hbm_kernels = encode = None
     if rank == 0:
         peaks = measured_peaks()
-        conv_s, n_conv = time_conv_family(plan)
+        ep = time_entry_points(plan.forward_backward)
+        conv_s = sum(ep.get(k, (0.0, 0))[0] for k in ("ghnd_conv_plan_run", "ghnd_stem_conv_plan_run"))
+        n_conv = 0
+        for r in list(plan.t_layers.values()) + list(plan.s_layers.values()):
+            for b in r.blocks:
+                n_conv += sum(c.n_launches for c in b.fwd + b.bwd)
+        l1 = plan.s_l1
+        n_conv += sum(u.plan.n_launches + (u.dgrad.n_launches if u.dgrad else 0)
+                      for u in (l1.e0, l1.e1, l1.e2, l1.d4, l1.d7, l1.d9)) + 8
         flops = conv_flops_per_step(plan)
         achieved = flops / conv_s / 1e12
-        roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv fwd/dgrad, %d launches/step)" % n_conv,
+        ncu = ncu_traffic()
+        roof = {"bound": "tensor",
+                "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv fwd/dgrad + stem, %d launches/step; "
+                          "achieved = algorithmic FLOPs of all launches / summed CUDA-event time)" % n_conv,
                 "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None,
+                "frac": achieved / peaks["bf16_tflops_sustained"],
+                "traffic": ncu.get("conv_tc_dram_bytes_per_step"),
+                "traffic_note": ncu.get("note"),
                 "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
-                "conv_share_of_step": conv_s / (ms * 1e-3 / args.steps)}
+                "conv_share_of_step": conv_s / sum(t for t, _ in ep.values()),
+                "flops_per_step": flops}
+        # memory-bound kernels of the path against the measured copy bandwidth
+        sse_bytes = 6.0 * sum(t.numel() for t in plan.feat_s.values())
+        hbm_kernels = {}
+        if "ghnd_sse_fwd_bwd" in ep:
+            gbs = sse_bytes / ep["ghnd_sse_fwd_bwd"][0] / 1e9
+            hbm_kernels["sse_kernel (4-level loss fwd+bwd, 6 B/elem)"] = {
+                "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"]}
+        breakdown = {k: round(v[0] * 1e3, 4) for k, v in sorted(ep.items(), key=lambda kv: -kv[1][0])}
+        roof["entry_point_ms_per_step"] = breakdown
+        if world == 1 and not args.no_encode:
+            sweep, qgbs = encode_sweep(dev, [1, 2, 4, 8, 16, 32, 64] if args.encode_sweep else [8, 64])
+            encode = {"metric": "head_quant_encode_images_per_sec", "unit": "images/s",
+                      "workload": "Keypoint R-CNN b3ch RcnnHead (stem + layer1 encoder + 8-bit quantize), "
+                                  "synthetic 3x800x1333, inputs resident in HBM", "by_batch": sweep}
+            if qgbs is not None:
+                hbm_kernels["quant_minmax+quant_apply (8-bit quantizer, 5 B/elem)"] = {
+                    "achieved": qgbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": qgbs / peaks["hbm_gbs"]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         step = cpu_step_fn(1)
         step()
@@ -332,7 +418,8 @@ def run_cuda(args):
                 "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": 4, "steps": e2e_steps,
                         "api": "DistillationBox(images from pinned host memory) + backward + FusedAdam + loss.item()"},
-                "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
+                "gpu_launches": launches, "roofline": roof, "roofline_hbm_kernels": hbm_kernels,
+                "encode": encode, "cpu_baseline": cpu,
                 "loss": float(loss.item())}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -342,10 +429,12 @@ def run_cuda(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-encode", action="store_true", help="skip the split-computing head line")
+    ap.add_argument("--encode-sweep", action="store_true", help="encode path at batch 1..64 (config 5)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
