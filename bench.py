@@ -162,30 +162,23 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # CUDA arm
 # ------------------------------------------------------------------------------------------------
-def conv_flops_per_step(plan):
-    """Algorithmic FLOPs (2*MACs) of every conv_tc_kernel launch in one step, from the plans."""
-    total = 0.0
-
-    def conv(N, Ho, Wo, K, C, R, S):
-        return 2.0 * N * Ho * Wo * K * C * R * S
-
-    def block(b, bwd):
-        f = conv(b.N, b.H, b.W, b.planes, b.cin, 1, 1) + conv(b.N, b.Ho, b.Wo, b.planes, b.planes, 3, 3) + \
-            conv(b.N, b.Ho, b.Wo, b.cout, b.planes, 1, 1)
-        if b.cd is not None:
-            f += conv(b.N, b.Ho, b.Wo, b.cout, b.cin, 1, 1)
-        return f * (2 if bwd else 1)
-
-    for r in plan.t_layers.values():
-        total += sum(block(b, False) for b in r.blocks)
-    for r in plan.s_layers.values():
-        total += sum(block(b, True) for b in r.blocks)
+def conv_plans(plan):
+    """Every tcgen05 conv plan (forward / dgrad / stem) one GHND step runs, in no particular order."""
+    out = [plan.t_stem.plan, plan.s_stem.plan]
+    for r in list(plan.t_layers.values()) + list(plan.s_layers.values()):
+        for b in r.blocks:
+            out += list(b.fwd) + list(b.bwd)
     l1 = plan.s_l1
     for u in (l1.e0, l1.e1, l1.e2, l1.d4, l1.d7, l1.d9):
-        total += 2 * conv(u.N, u.Ho, u.Wo, u.K, u.C, 2, 2)  # forward + dgrad
-    stem = 2.0 * plan.N * (plan.Hp // 2) * (plan.Wp // 2) * 64 * 147
-    total += 2 * stem  # teacher + student stem forward
-    return total
+        out.append(u.plan)
+        if u.dgrad is not None:
+            out.append(u.dgrad)
+    return out
+
+
+def conv_flops_per_step(plan):
+    """Algorithmic FLOPs (2*MACs) of every conv_tc_kernel launch in one step, from the plans."""
+    return float(sum(p.flops for p in conv_plans(plan)))
 
 
 def time_entry_points(fn):
@@ -355,13 +348,7 @@ def run_cuda(args):
         peaks = measured_peaks()
         ep = time_entry_points(plan.forward_backward)
         conv_s = sum(ep.get(k, (0.0, 0))[0] for k in ("ghnd_conv_plan_run", "ghnd_stem_conv_plan_run"))
-        n_conv = 0
-        for r in list(plan.t_layers.values()) + list(plan.s_layers.values()):
-            for b in r.blocks:
-                n_conv += sum(c.n_launches for c in b.fwd + b.bwd)
-        l1 = plan.s_l1
-        n_conv += sum(u.plan.n_launches + (u.dgrad.n_launches if u.dgrad else 0)
-                      for u in (l1.e0, l1.e1, l1.e2, l1.d4, l1.d7, l1.d9)) + 8
+        n_conv = sum(p.n_launches for p in conv_plans(plan))
         flops = conv_flops_per_step(plan)
         achieved = flops / conv_s / 1e12
         ncu = ncu_traffic()
@@ -413,6 +400,7 @@ def run_cuda(args):
                 "config": {"workload": WORKLOAD, "global_batch": images_per_step, "per_gpu_batch": PER_GPU_BATCH,
                            "parallelism": "dp%d" % world,
                            "l2": "per-step working set (several GB of activations) exceeds the 126 MB L2",
+                           "shared_frozen_trunk": bool(plan.shared),
                            "cuda_graph": True},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d,

@@ -58,10 +58,13 @@ class FrozenConv(object):
 class BottleneckRunner(object):
     """One torchvision Bottleneck with FrozenBN: forward, and dgrad when need_bwd."""
 
-    def __init__(self, block, x, N, H, W, act_dtype, grad_dtype, need_bwd):
+    def __init__(self, block, x, N, H, W, act_dtype, grad_dtype, need_bwd, out=None, bwd_n=None):
         dev = x.device
         self.x, self.N, self.H, self.W = x, N, H, W
         self.need_bwd = need_bwd
+        # the backward pass may cover only the LAST bwd_n images of the batch (shared frozen trunk:
+        # teacher images first, student images last; only the student half needs gradients)
+        self.bwd_n = N if bwd_n is None else bwd_n
         self.c1 = FrozenConv(block.conv1, block.bn1, act_dtype, grad_dtype, need_bwd)
         self.c2 = FrozenConv(block.conv2, block.bn2, act_dtype, grad_dtype, need_bwd)
         self.c3 = FrozenConv(block.conv3, block.bn3, act_dtype, grad_dtype, need_bwd)
@@ -75,7 +78,8 @@ class BottleneckRunner(object):
         self.cin, self.planes, self.cout = cin, p, self.c3.K
         self.a1 = _empty((N, H, W, p), act_dtype, dev)
         self.a2 = _empty((N, self.Ho, self.Wo, p), act_dtype, dev)
-        self.out = _empty((N, self.Ho, self.Wo, self.cout), act_dtype, dev)
+        self.out = out if out is not None else _empty((N, self.Ho, self.Wo, self.cout), act_dtype, dev)
+        assert tuple(self.out.shape) == (N, self.Ho, self.Wo, self.cout)
         self.idn = _empty((N, self.Ho, self.Wo, self.cout), act_dtype, dev) if self.cd else None
         self.fwd = [
             ops.ConvPlan(CONV_FWD, N, H, W, cin, p, 1, 1, 1, 0, x, self.c1.w, self.a1, bias=self.c1.bias,
@@ -93,27 +97,30 @@ class BottleneckRunner(object):
 
     def plan_backward(self, g_out, g_x, loss_grad_x, grad_dtype):
         """g_out: gradient w.r.t. this block's pre-ReLU output (already masked).  Writes g_x =
-        mask(x>0) * (dL/dx [+ loss_grad_x]) i.e. the same convention for the producer of x."""
+        mask(x>0) * (dL/dx [+ loss_grad_x]) i.e. the same convention for the producer of x.
+        All gradient tensors have batch bwd_n; the saved activations are sliced to those images."""
         dev = g_out.device
-        N, H, W, Ho, Wo = self.N, self.H, self.W, self.Ho, self.Wo
+        N, H, W, Ho, Wo = self.bwd_n, self.H, self.W, self.Ho, self.Wo
         p, cin, cout, s = self.planes, self.cin, self.cout, self.stride
+        o = self.N - N
+        x_b, a1_b, a2_b = self.x[o:], self.a1[o:], self.a2[o:]
         self.g_a2 = _empty((N, Ho, Wo, p), grad_dtype, dev)
         self.g_a1 = _empty((N, H, W, p), grad_dtype, dev)
         self.bwd = [
             ops.ConvPlan(CONV_DGRAD, N, Ho, Wo, p, cout, 1, 1, 1, 0, g_out, self.c3.wt, self.g_a2,
-                         mask=self.a2),
+                         mask=a2_b),
             ops.ConvPlan(CONV_DGRAD, N, H, W, p, p, 3, 3, s, 1, self.g_a2, self.c2.wt, self.g_a1,
-                         mask=self.a1),
+                         mask=a1_b),
         ]
         if self.cd is None:
             assert loss_grad_x is None
             self.bwd.append(ops.ConvPlan(CONV_DGRAD, N, H, W, cin, p, 1, 1, 1, 0, self.g_a1, self.c1.wt,
-                                         g_x, residual=g_out, mask=self.x))
+                                         g_x, residual=g_out, mask=x_b))
         else:
             self.bwd.append(ops.ConvPlan(CONV_DGRAD, N, H, W, cin, p, 1, 1, 1, 0, self.g_a1, self.c1.wt,
-                                         g_x, residual=loss_grad_x, mask=self.x))
+                                         g_x, residual=loss_grad_x, mask=x_b))
             self.bwd.append(ops.ConvPlan(CONV_DGRAD, N, H, W, cin, cout, 1, 1, s, 0, g_out, self.cd.wt,
-                                         g_x, mask=self.x, accumulate=True))
+                                         g_x, mask=x_b, accumulate=True))
 
     def forward(self):
         for p in self.fwd:
@@ -125,12 +132,16 @@ class BottleneckRunner(object):
 
 
 class FrozenLayerRunner(object):
-    """nn.Sequential of Bottlenecks (teacher layer1..4, student layer2..4)."""
+    """nn.Sequential of Bottlenecks (teacher layer1..4, student layer2..4).  `out`: preallocated
+    buffer for the last block's output; `bwd_n`: backward covers only the last bwd_n images."""
 
-    def __init__(self, layer, x, N, H, W, act_dtype, grad_dtype, need_bwd):
+    def __init__(self, layer, x, N, H, W, act_dtype, grad_dtype, need_bwd, out=None, bwd_n=None):
         self.blocks = []
-        for block in layer:
-            r = BottleneckRunner(block, x, N, H, W, act_dtype, grad_dtype, need_bwd)
+        n_blocks = len(layer)
+        self.bwd_n = N if bwd_n is None else bwd_n
+        for i, block in enumerate(layer):
+            r = BottleneckRunner(block, x, N, H, W, act_dtype, grad_dtype, need_bwd,
+                                 out=out if i == n_blocks - 1 else None, bwd_n=bwd_n)
             self.blocks.append(r)
             x, H, W = r.out, r.Ho, r.Wo
         self.out, self.Ho, self.Wo = x, H, W
@@ -148,7 +159,7 @@ class FrozenLayerRunner(object):
             if i == 0:
                 b.plan_backward(g, g_x, loss_grad_x, grad_dtype)
             else:
-                gx = _empty((b.N, b.H, b.W, b.cin), grad_dtype, dev)
+                gx = _empty((b.bwd_n, b.H, b.W, b.cin), grad_dtype, dev)
                 b.plan_backward(g, gx, None, grad_dtype)
                 g = gx
 
@@ -226,7 +237,7 @@ class _BN(object):
 class _WideUnit(object):
     """conv(k2) -> BatchNorm(batch stats) [-> ReLU] of the student's layer1, forward + backward."""
 
-    def __init__(self, conv, bn, relu, x, x_g, N, H, W, act_dtype, grad_dtype, train):
+    def __init__(self, conv, bn, relu, x, x_g, N, H, W, act_dtype, grad_dtype, train, out=None):
         dev = x.device
         K, C, R, S = conv.weight.shape
         pad = conv.padding[0]
@@ -236,7 +247,8 @@ class _WideUnit(object):
         self.train = train
         self.w = _empty((K, R, S, C), act_dtype, dev)
         self.bn = _BN(bn, K, N * self.Ho * self.Wo, dev)
-        self.out = _empty((N, self.Ho, self.Wo, K), act_dtype, dev)
+        self.out = out if out is not None else _empty((N, self.Ho, self.Wo, K), act_dtype, dev)
+        assert tuple(self.out.shape) == (N, self.Ho, self.Wo, K)
         if train:
             self.raw = _empty((N, self.Ho, self.Wo, K), act_dtype, dev)
             self.out_g = _empty((N, self.Ho, self.Wo, K), grad_dtype, dev)  # bf16 copy for wgrad
@@ -293,7 +305,7 @@ class StudentLayer1Runner(object):
     """Bottleneck4LargeResNet (resnet_layer.py:40-70): three wide encoder convs, the narrow
     64->bch / bch->64 pair around the planar fp32 bottleneck z, three wide decoder convs."""
 
-    def __init__(self, layer1, x, N, H, W, act_dtype, grad_dtype, train, x_g=None):
+    def __init__(self, layer1, x, N, H, W, act_dtype, grad_dtype, train, x_g=None, out=None):
         dev = x.device
         enc, dec = layer1.encoder.encoder, layer1.decoder
         self.layer1, self.train = layer1, train
@@ -325,7 +337,8 @@ class StudentLayer1Runner(object):
         self.bn3 = _BN(dec[3], 64, N * self.H3 * self.W3, dev)
         self.d4 = mk(dec[4], dec[5], True, self.act3, self.act3_g, self.H3, self.W3)
         self.d7 = mk(dec[7], dec[8], False, self.d4.out, self.d4.out_g, self.d4.Ho, self.d4.Wo)
-        self.d9 = mk(dec[9], dec[10], True, self.d7.out, self.d7.out_g, self.d7.Ho, self.d7.Wo)
+        self.d9 = _WideUnit(dec[9], dec[10], True, self.d7.out, self.d7.out_g, N, self.d7.Ho, self.d7.Wo,
+                            act_dtype, grad_dtype, train, out=out)
         self.out = self.d9.out
         assert (self.d9.Ho, self.d9.Wo) == (H, W)
         self.q = None  # set by forward_encoder_quantized
@@ -416,6 +429,19 @@ class StudentLayer1Runner(object):
         self.e0.backward()
 
 
+def _same_frozen_layers(teacher_body, student_body, names):
+    """True iff every tensor of the named frozen layers is identical in both bodies."""
+    for name in names:
+        t_sd, s_sd = getattr(teacher_body, name).state_dict(), getattr(student_body, name).state_dict()
+        if t_sd.keys() != s_sd.keys():
+            return False
+        for k, v in t_sd.items():
+            w = s_sd[k]
+            if v.shape != w.shape or v.dtype != w.dtype or not torch.equal(v, w):
+                return False
+    return True
+
+
 def g_like(unit, dtype, dev):
     return _empty((unit.N, unit.Ho, unit.Wo, unit.K), dtype, dev)
 
@@ -450,7 +476,7 @@ class GhndPlan(object):
 
     def __init__(self, teacher_body, student_body, N, Hp, Wp, levels=LEVELS, factors=None,
                  act_dtype=torch.float16, grad_dtype=torch.bfloat16, device=None, flat=None,
-                 image_mean=IMAGE_MEAN, image_std=IMAGE_STD):
+                 image_mean=IMAGE_MEAN, image_std=IMAGE_STD, share_frozen_trunk=None):
         _lib.check(_lib.load().ghnd_device_check(), "ghnd_device_check")
         dev = torch.device(device) if device is not None else next(student_body.parameters()).device
         self.device, self.N, self.Hp, self.Wp = dev, N, Hp, Wp
@@ -464,31 +490,59 @@ class GhndPlan(object):
         top = max(LEVELS.index(l) for l in self.levels)
         self.top = LEVELS[top]
         self.packed = torch.zeros((N, Hp + 6, Wp + 8, 4), dtype=act_dtype, device=dev)
+        # Frozen layers 2..top usually hold IDENTICAL tensors in teacher and student (the student is
+        # the teacher with layer1 replaced, config/ghnd/*.yaml) -> run them once on a 2N batch
+        # (teacher images first): half the launches, twice the tiles per launch.
+        upper = LEVELS[1:top + 1]
+        if share_frozen_trunk is None:
+            share_frozen_trunk = bool(upper) and _same_frozen_layers(teacher_body, student_body, upper)
+        self.shared = bool(share_frozen_trunk) and bool(upper)
         # ---- teacher (forward only) ----
         self.t_stem = StemRunner(teacher_body, self.packed, N, Hp, Wp, act_dtype, grad_dtype, False)
-        self.t_layers, x, H, W = {}, self.t_stem.out, self.t_stem.Ho, self.t_stem.Wo
-        for name in LEVELS[:top + 1]:
-            r = FrozenLayerRunner(getattr(teacher_body, name), x, N, H, W, act_dtype, grad_dtype, False)
-            self.t_layers[name] = r
-            x, H, W = r.out, r.Ho, r.Wo
+        H1, W1 = self.t_stem.Ho, self.t_stem.Wo
+        self.trunk_in = _empty((2 * N, H1, W1, 256), act_dtype, dev) if self.shared else None
+        self.t_layers = {}
+        self.t_layers["layer1"] = FrozenLayerRunner(teacher_body.layer1, self.t_stem.out, N, H1, W1, act_dtype,
+                                                    grad_dtype, False,
+                                                    out=self.trunk_in[:N] if self.shared else None)
+        if not self.shared:
+            x, H, W = self.t_layers["layer1"].out, H1, W1
+            for name in upper:
+                r = FrozenLayerRunner(getattr(teacher_body, name), x, N, H, W, act_dtype, grad_dtype, False)
+                self.t_layers[name] = r
+                x, H, W = r.out, r.Ho, r.Wo
         # ---- student ----
         self.flat = flat if flat is not None else FlatParams(
             [("backbone.body." + n, p) for n, p in student_body.named_parameters()])
         grads = self.flat.grads
         self.s_stem = StemRunner(student_body, self.packed, N, Hp, Wp, act_dtype, grad_dtype, True)
         self.s_l1 = StudentLayer1Runner(student_body.layer1, self.s_stem.out, N, self.s_stem.Ho,
-                                        self.s_stem.Wo, act_dtype, grad_dtype, True)
-        self.s_layers, x, H, W = {}, self.s_l1.out, self.s_stem.Ho, self.s_stem.Wo
-        for name in LEVELS[1:top + 1]:
-            r = FrozenLayerRunner(getattr(student_body, name), x, N, H, W, act_dtype, grad_dtype, True)
-            self.s_layers[name] = r
-            x, H, W = r.out, r.Ho, r.Wo
+                                        self.s_stem.Wo, act_dtype, grad_dtype, True,
+                                        out=self.trunk_in[N:] if self.shared else None)
+        self.s_layers = {}
+        if self.shared:
+            x, H, W = self.trunk_in, H1, W1
+            for name in upper:
+                r = FrozenLayerRunner(getattr(student_body, name), x, 2 * N, H, W, act_dtype, grad_dtype, True,
+                                      bwd_n=N)
+                self.s_layers[name] = r
+                x, H, W = r.out, r.Ho, r.Wo
+        else:
+            x, H, W = self.s_l1.out, H1, W1
+            for name in upper:
+                r = FrozenLayerRunner(getattr(student_body, name), x, N, H, W, act_dtype, grad_dtype, True)
+                self.s_layers[name] = r
+                x, H, W = r.out, r.Ho, r.Wo
         # ---- loss ----
         self.feat_t = {"layer1": self.t_layers["layer1"].out}
         self.feat_s = {"layer1": self.s_l1.out}
-        for name in LEVELS[1:top + 1]:
-            self.feat_t[name] = self.t_layers[name].out
-            self.feat_s[name] = self.s_layers[name].out
+        for name in upper:
+            if self.shared:
+                self.feat_t[name] = self.s_layers[name].out[:N]
+                self.feat_s[name] = self.s_layers[name].out[N:]
+            else:
+                self.feat_t[name] = self.t_layers[name].out
+                self.feat_s[name] = self.s_layers[name].out
         self.loss_grads = {l: torch.empty_like(self.feat_s[l], dtype=grad_dtype) for l in self.levels}
         self.loss_out = torch.zeros(1 + len(self.levels), dtype=torch.float32, device=dev)
         self.sse_ws = _empty((_lib.load().ghnd_sse_workspace_bytes(),), torch.uint8, dev)
@@ -497,7 +551,8 @@ class GhndPlan(object):
         for name in reversed(LEVELS[1:top + 1]):
             r = self.s_layers[name]
             below = LEVELS[LEVELS.index(name) - 1]
-            g_x = torch.empty_like(r.blocks[0].x, dtype=grad_dtype)
+            b0 = r.blocks[0]
+            g_x = _empty((N, b0.H, b0.W, b0.cin), grad_dtype, dev)
             r.plan_backward(g, g_x, self.loss_grads.get(below), grad_dtype)
             g = g_x
         self.s_l1.plan_backward(g, grads, "backbone.body.layer1.")
@@ -521,7 +576,7 @@ class GhndPlan(object):
         self.s_l1.forward()
         for name in LEVELS[1:]:
             if name in self.s_layers:
-                self.s_layers[name].forward()
+                self.s_layers[name].forward()  # both models' images when the frozen trunk is shared
         lv = [(self.feat_t[l], self.feat_s[l], self.loss_grads[l], self.factors[l], l == self.top)
               for l in self.levels]
         ops.sse_fwd_bwd(lv, self.grad_dtype, self.loss_out, self.sse_ws)

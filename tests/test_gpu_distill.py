@@ -191,6 +191,35 @@ def test_hnd_layer1_only(env):
     check_grads({n: params[n].grad for n in res["grads"]}, res["grads"])
 
 
+def test_unshared_frozen_trunk(env):
+    """When the student's frozen layer2-4 differ from the teacher's, the plan must NOT batch the
+    two models through one trunk; loss and gradients still match the oracle run on those weights."""
+    from hnd_ghnd_object_detectors_b200.tool import DistillationBox
+    s_sd = {k: v.clone() for k, v in env["s_sd"].items()}
+    s_sd["backbone.body.layer3.2.conv2.weight"] = s_sd["backbone.body.layer3.2.conv2.weight"] * 1.25
+    env2 = dict(env, s_sd=s_sd)
+    teacher, student = build_pair(env2)
+    box = DistillationBox(teacher, student, criterion_config(), use_cuda_graph=False)
+    images = [im.cuda() for im in small_images()]
+    loss = box(images, targets_for(images))
+    plan = list(box._plans.values())[0]
+    assert plan.shared is False
+    res = O.distill_step(env["t_sd"], s_sd, small_images())
+    assert abs(loss.item() - float(res["loss"])) <= 1e-3 * float(res["loss"])
+    loss.backward()
+    params = dict(student.named_parameters())
+    check_grads({n: params[n].grad for n in res["grads"]}, res["grads"])
+
+
+def test_shared_frozen_trunk_is_detected(env):
+    from hnd_ghnd_object_detectors_b200.tool import DistillationBox
+    teacher, student = build_pair(env)
+    box = DistillationBox(teacher, student, criterion_config(), use_cuda_graph=False)
+    images = [im.cuda() for im in small_images()]
+    box(images, targets_for(images))
+    assert list(box._plans.values())[0].shared is True
+
+
 def test_encode_head_bytes(env, golden_dir):
     """RcnnHead path (split_rcnn.py:23-37).  The quantizer itself is bit-exact for the same input
     tensor (test_gpu_kernels); end to end the fp16 convolutions may move values across a rounding
