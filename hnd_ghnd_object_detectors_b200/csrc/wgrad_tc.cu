@@ -17,7 +17,7 @@
 
 namespace ghnd {
 
-static constexpr int kWgThreads = 192;
+static constexpr int kWgThreads = 224;  // warp0/6 TMA producers, warp1 MMA, warps 2..5 epilogue
 static constexpr int kWgPix = 32;                  // pixels (GEMM-K) per pipeline stage
 static constexpr int kWgBox = kWgPix * 128;        // bytes of one [32 px][64 ch] box = 4 KB
 static constexpr int kWgMaxTaps = 4;
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(kWgThreads, 1)
     prefetch_tmap(&p.tmap_row);
     prefetch_tmap(&p.tmap_col);
     for (int i = 0; i < p.n_stages; ++i) {
-      mbar_init(&full_bar[i], 1);
+      mbar_init(&full_bar[i], 2);  // two producer warps, each posts its own byte count
       mbar_init(&empty_bar[i], 1);
     }
     mbar_init(done_bar, 1);
@@ -109,27 +109,36 @@ __global__ void __launch_bounds__(kWgThreads, 1)
   const int a_bytes = p.row_boxes * kWgBox;
   const int b_tap_bytes = p.col_boxes * kWgBox;
 
-  if (warp == 0) {
-    // TMA producer: whole warp converged, one elected lane issues
+  if (warp == 0 || warp == 6) {
+    // Two TMA producer warps (whole warp converged, one elected lane issues).  A single thread
+    // issuing all ~10 small boxes of a stage was the bottleneck of this kernel (ncu: MMA warp
+    // starved while the producer never waited for a free slot), so the taps are split in halves.
+    const int pw = warp == 0 ? 0 : 1;
+    const int tap_lo = pw == 0 ? 0 : (p.n_taps + 1) / 2;
+    const int tap_hi = pw == 0 ? (p.n_taps + 1) / 2 : p.n_taps;
     int stage = 0;
     uint32_t phase = 0;
     // (img, h, wt) of the first tile by multiply-high division, then carried incrementally
     int img, rem, h, wt;
     fd_divmod(p.fd_tiles_per_img, t_begin, img, rem);
     fd_divmod(p.fd_tiles_w, rem, h, wt);
+    // bytes this warp posts per stage: its taps of the shifted operand (+ the unshifted one for pw 0)
+    const uint32_t shifted_bytes = (uint32_t)((tap_hi - tap_lo) * (p.rows_is_dy ? b_tap_bytes : a_bytes));
+    const uint32_t fixed_bytes = pw == 0 ? (uint32_t)(p.rows_is_dy ? a_bytes : b_tap_bytes) : 0u;
     for (int t = t_begin; t < t_end; ++t) {
       const int w0 = wt * kWgPix;
       mbar_wait(&empty_bar[stage], phase ^ 1);
       if (elect_one()) {
         uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
         uint8_t* sb = sa + a_bytes;
-        mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)p.stage_bytes);
+        mbar_arrive_expect_tx(&full_bar[stage], shifted_bytes + fixed_bytes);
         if (p.rows_is_dy) {
           // rows operand = dy (unshifted), cols operand = x shifted per tap
-          for (int b = 0; b < p.row_boxes; ++b)
-            tma_load_4d(sa + b * kWgBox, &p.tmap_row, &full_bar[stage], m_tile * 128 + b * 64, w0, h,
-                        img);
-          for (int tap = 0; tap < p.n_taps; ++tap) {
+          if (pw == 0)
+            for (int b = 0; b < p.row_boxes; ++b)
+              tma_load_4d(sa + b * kWgBox, &p.tmap_row, &full_bar[stage], m_tile * 128 + b * 64, w0, h,
+                          img);
+          for (int tap = tap_lo; tap < tap_hi; ++tap) {
             const int dh = p.tap_dh[tap], dw = p.tap_dw[tap];
             for (int b = 0; b < p.col_boxes; ++b)
               tma_load_4d(sb + tap * b_tap_bytes + b * kWgBox, &p.tmap_col, &full_bar[stage],
@@ -137,16 +146,18 @@ __global__ void __launch_bounds__(kWgThreads, 1)
           }
         } else {
           // rows = x channels: A region holds n_taps shifted x tiles, B region the single dy tile
-          for (int tap = 0; tap < p.n_taps; ++tap) {
+          for (int tap = tap_lo; tap < tap_hi; ++tap) {
             const int dh = p.tap_dh[tap], dw = p.tap_dw[tap];
             for (int b = 0; b < p.row_boxes; ++b)
               tma_load_4d(sa + tap * a_bytes + b * kWgBox, &p.tmap_row, &full_bar[stage],
                           m_tile * 128 + b * 64, w0 + dw, h + dh, img);
           }
-          uint8_t* sd = sa + p.n_taps * a_bytes;
-          for (int b = 0; b < p.col_boxes; ++b)
-            tma_load_4d(sd + b * kWgBox, &p.tmap_col, &full_bar[stage], n_chunk * p.nb + b * 64, w0,
-                        h, img);
+          if (pw == 0) {
+            uint8_t* sd = sa + p.n_taps * a_bytes;
+            for (int b = 0; b < p.col_boxes; ++b)
+              tma_load_4d(sd + b * kWgBox, &p.tmap_col, &full_bar[stage], n_chunk * p.nb + b * 64, w0,
+                          h, img);
+          }
         }
       }
       __syncwarp();
@@ -202,7 +213,7 @@ __global__ void __launch_bounds__(kWgThreads, 1)
     }
     if (elect_one()) umma_commit(done_bar);
     __syncwarp();
-  } else {
+  } else if (warp < 6) {
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     if (t_end > t_begin) {
