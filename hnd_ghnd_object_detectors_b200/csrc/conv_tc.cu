@@ -23,6 +23,7 @@
 // The same kernel runs the data-gradient: dgrad of a stride-1 conv is a conv of dy with mirrored
 // tap offsets over the transposed weights; dgrad of a stride-2 conv is four launches, one per
 // output parity class, each using the taps that hit that class and storing through a lattice view.
+#include <stdlib.h>
 #include <vector>
 
 #include "common.cuh"
@@ -683,10 +684,13 @@ static int finish_launch(ConvLaunch* L, const ghnd_conv_desc_t* d, int gemm_cin,
   const int stages_per_tile = (n_units + p.units_per_stage - 1) / p.units_per_stage;
   int ring = 0;
   if (n_in > 0) {
-    const int want = n_in == 1 ? 4 : 3;
+    // The ring depth must be EVEN: the two epilogue groups take alternate chunks, so with an even
+    // depth every slot is always consumed by the same group.  With an odd depth a slot alternates
+    // between the groups, and a group that runs ahead can wait for parity p of a slot barrier that
+    // is still one whole phase behind -- a parity wait then passes spuriously (mbarrier parity
+    // aliasing).  Seen on B200 as a rare cudaErrorLaunchFailure in the C64->K256 "+res" convs.
     ring = (kSmemBudget - fixed - 3 * p.stage_bytes) / (n_in * kChunkBytes);
-    if (ring > want) ring = want;
-    if (ring < 2) ring = 2;
+    ring = ring >= 4 ? 4 : 2;
   }
   p.ring = ring > 0 ? ring : 1;
   p.fd_ring = make_fastdiv(p.ring);
@@ -717,8 +721,9 @@ static cudaError_t launch_conv(const ConvLaunch& L, cudaStream_t st) {
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
+  static const bool no_pdl = getenv("GHND_NO_PDL") != nullptr;  // debugging switch
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = no_pdl ? 0 : 1;
   return cudaLaunchKernelEx(&cfg, conv_tc_kernel, L.p);
 }
 

@@ -607,13 +607,21 @@ class GhndPlan(object):
             self.forward_backward()
         self.launches_per_step = ops.launches() - before
         self.graph = g
+        self._inflight = [torch.cuda.Event() for _ in range(3)]
         return g
 
     def step(self, images=None):
         if images is not None:
             self.load_images(images)
         if self.graph is not None:
+            # Bound the number of graph launches in flight: a loop that never reads anything back
+            # (bench.py's device-resident arm) otherwise queues hundreds of 200-node launches, which
+            # crashed inside cudaGraphLaunch on this driver (580.159) after a few hundred replays.
+            ev = self._inflight[self.step_count % len(self._inflight)]
+            if self.step_count >= len(self._inflight):
+                ev.synchronize()
             self.graph.replay()
+            ev.record()
             ops._count(self.launches_per_step)
         else:
             self.forward_backward()

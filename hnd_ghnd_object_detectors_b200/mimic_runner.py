@@ -18,6 +18,7 @@ import time
 import torch
 from torch import distributed as dist
 
+from .prefetch import DevicePrefetcher
 from . import main_util, module_util, parallel, yaml_util
 from .models import get_model, load_ckpt, save_ckpt
 from .optim import FusedAdam
@@ -86,9 +87,8 @@ def distill_model(distillation_box, data_loader, optimizer, log_freq, device, ep
         if warmup_iters > 0:
             lr_scheduler = main_util.warmup_lr_scheduler(optimizer, warmup_iters, warmup_factor)
     t0, seen, last = time.time(), 0, None
-    for it, (images, targets) in enumerate(data_loader):
-        images = list(image.to(device, non_blocking=True) for image in images)
-        targets = [{k: v.to(device) for k, v in t.items()} for t in targets]
+    # the copy of batch i+1 overlaps step i on a side stream (prefetch.py)
+    for it, (images, targets) in enumerate(DevicePrefetcher(data_loader, device)):
         loss = distillation_box(images, targets)
         optimizer.zero_grad()
         loss.backward()

@@ -173,7 +173,10 @@ class ConvPlan(object):
         self.n_launches = _lib.load().ghnd_conv_plan_launches(self._h)
 
     def run(self, stream=None):
-        call("ghnd_conv_plan_run", self._h, stream_ptr(stream))
+        try:
+            call("ghnd_conv_plan_run", self._h, stream_ptr(stream))
+        except _lib.GhndError as e:
+            raise _lib.GhndError("%s [conv plan: %s]" % (e, self.desc))
         _count(self.n_launches)
 
     def __del__(self):

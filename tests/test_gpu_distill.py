@@ -220,6 +220,25 @@ def test_shared_frozen_trunk_is_detected(env):
     assert list(box._plans.values())[0].shared is True
 
 
+def test_prefetcher_and_async_reader(env):
+    """Loop plumbing (prefetch.py): batches arrive on the device unchanged and in order; the scalar
+    reader returns the value pushed one call earlier."""
+    from hnd_ghnd_object_detectors_b200.prefetch import AsyncScalarReader, DevicePrefetcher
+    g = torch.Generator().manual_seed(3)
+    batches = [([torch.rand(3, 8, 12, generator=g) for _ in range(2)],
+                [{"boxes": torch.rand(1, 4, generator=g), "labels": torch.tensor([i])} for _ in range(2)])
+               for i in range(4)]
+    reader, seen = AsyncScalarReader(), []
+    for i, (imgs, tgts) in enumerate(DevicePrefetcher(batches, "cuda")):
+        assert all(a.is_cuda and torch.equal(a.cpu(), b) for a, b in zip(imgs, batches[i][0]))
+        assert int(tgts[0]["labels"][0]) == i and tgts[0]["boxes"].is_cuda
+        seen.append(reader.push(imgs[0].sum()))
+    assert seen[0] is None
+    for i in range(1, 4):
+        assert abs(seen[i] - float(batches[i - 1][0][0].sum())) < 1e-3
+    assert abs(reader.flush() - float(batches[3][0][0].sum())) < 1e-3
+
+
 def test_encode_head_bytes(env, golden_dir):
     """RcnnHead path (split_rcnn.py:23-37).  The quantizer itself is bit-exact for the same input
     tensor (test_gpu_kernels); end to end the fp16 convolutions may move values across a rounding

@@ -232,6 +232,28 @@ def test_conv_fused_stats(ops, case):
     assert float(((got[K:] - q_ref.cpu()).abs() / q_ref.cpu()).max()) < 2e-5
 
 
+def test_conv_repeated_launch_stability(ops):
+    """Regression for a rare synchronisation fault (mbarrier parity aliasing on the epilogue-operand
+    ring when its depth was odd): the C64->K256 1x1 "+residual" conv, 400 back-to-back launches on
+    a tensor larger than L2, result checked at the end."""
+    from hnd_ghnd_object_detectors_b200 import _lib
+    N, H, W, C, K = 4, 200, 336, 64, 256
+    dtype = torch.float16
+    g = torch.Generator(device="cuda").manual_seed(5)
+    xd = torch.randn((N, H, W, C), generator=g, device="cuda").to(dtype)
+    wq = (torch.randn((K, C, 1, 1), generator=g, device="cuda") * (2.0 / C) ** 0.5).to(dtype)
+    wd = ops.pack_weight(wq.float(), None, False, dtype)
+    resd = torch.randn((N, H, W, K), generator=g, device="cuda").to(dtype)
+    bias = torch.randn(K, generator=g, device="cuda")
+    y = torch.zeros((N, H, W, K), dtype=dtype, device="cuda")
+    plan = ops.ConvPlan(_lib.CONV_FWD, N, H, W, C, K, 1, 1, 1, 0, xd, wd, y, bias=bias, residual=resd, relu=True)
+    for _ in range(400):
+        plan.run()
+    torch.cuda.synchronize()
+    ref = torch.relu(xd.float().reshape(-1, C) @ wq.float().reshape(K, C).t() + bias + resd.float().reshape(-1, K))
+    assert rel(y.float().reshape(-1, K), ref) < 1e-3
+
+
 def test_conv_mixed_formats_rejected(ops):
     """tcgen05 kind::f16 raises an illegal-instruction fault for f16 x bf16 operands on sm_100a
     (measured in round 1), so the boundary refuses mixed formats on the host."""
