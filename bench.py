@@ -219,7 +219,9 @@ def encode_sweep(dev, batches, iters=10):
     cfg["name"] = "keypoint_rcnn"
     cfg["params"] = {"num_classes": 2, "pretrained": False, "num_keypoints": 17}
     torch.manual_seed(0)
-    model = models.get_model(cfg, dev).eval()
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):
+        model = models.get_model(cfg, dev).eval()
     head, _ = split_rcnn_model(model, 8)
     out = {}
     g = torch.Generator().manual_seed(5)
@@ -270,8 +272,10 @@ def run_cuda(args):
     from hnd_ghnd_object_detectors_b200.tool import DistillationBox
 
     torch.manual_seed(0)
-    teacher = models.get_model(model_config(False), dev)
-    student = models.get_model(model_config(True), dev)
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):  # "ckpt file is not found" notices: keep stdout = one JSON line
+        teacher = models.get_model(model_config(False), dev)
+        student = models.get_model(model_config(True), dev)
     student.load_state_dict(teacher.state_dict(), strict=False)  # layer2-4 identical (pretrained flow)
     module_util.freeze_module_params(teacher)
     for path in model_config(True)["frozen_modules"]:

@@ -572,23 +572,46 @@ static int make_lattice_map(CUtensorMap* m, const void* base, int N, int H, int 
   return encode_tmap(m, 2, 4, const_cast<uint8_t*>(b), dims, str, box, inner * 2);
 }
 
-// Tile-N choice from a two-term cost model measured in round 1 (profiles/): the kernel is bound
-// either by the L2->SM operand traffic (every tile streams its A and B stages, ~8 TB/s aggregate)
-// or by the tcgen05 issue rate (128xNx16 per N/2 cycles per SM, wave-quantised).
-static int pick_block_n(int cout, int m_tiles, int k_iters, int row_bytes, int n_in) {
-  (void)n_in;
+static const int kSmemBudget = 227 * 1024 - 1024 /*align*/ - 512 /*barriers + tmem slot*/;
+
+// Tile-N choice from a cost model fitted to a forced-block_n sweep of every conv of the GHND step
+// on B200 (scripts/gpu_bn_sweep.sh, profiles/r1_summary.md): a launch is bound by the slowest of
+//   shared-memory ingest  (every tile streams its A and B stages + epilogue operands; ~40 B/clk/SM),
+//   tcgen05 issue         (128xNx16 per max(N/2, 32) clk per SM, wave-quantised),
+//   the epilogue          (~600 clk per 64-channel chunk, two groups in parallel),
+//   HBM                   (unique bytes at ~6.2 TB/s),
+// plus 10 % of the non-dominant terms; a shallow (depth-2) operand ring costs another 8 %.
+static int pick_block_n(int cout, int m_tiles, int n_units, int n_taps, int row_bytes, int n_in,
+                        bool has_bias) {
   const int sms = num_sms();
+  if (const char* force = getenv("GHND_BLOCK_N")) {  // tuning switch: force a tile width where legal
+    const int bn = atoi(force);
+    if ((bn == 64 || bn == 128 || bn == 256) && cout % bn == 0) return bn;
+  }
+  const double clk = 1.9e9;
+  const double px = (double)m_tiles * 128.0;
+  const double cin = (double)n_units / n_taps * (row_bytes / 2);
   int best = 64;
   double best_t = 1e30;
   for (int bn = 256; bn >= 64; bn >>= 1) {
     if (cout % bn != 0) continue;
     const double tiles = (double)m_tiles * (cout / bn);
-    const double traffic = tiles * k_iters * (128.0 * row_bytes + (double)bn * row_bytes);
-    const double t_l2 = traffic / 8.0e12;
     const double waves = (double)((int64_t)(tiles + sms - 1) / sms);
-    const double mma_cycles = k_iters * (row_bytes / 32) * (bn < 128 ? 48.0 : bn / 2.0);
-    const double t_mma = waves * mma_cycles / 1.8e9;
-    const double t = (t_l2 > t_mma ? t_l2 : t_mma) + 0.15 * (t_l2 < t_mma ? t_l2 : t_mma);
+    const double stage = 128.0 * row_bytes + (double)bn * row_bytes;
+    const int fixed = 2 * kChunkBytes + (has_bias ? cout * 4 : 0);
+    const bool ring2 = n_in > 0 && (kSmemBudget - fixed - 3 * (int)stage) / (n_in * kChunkBytes) < 4;
+    const double per_tile = n_units * stage + (double)n_in * bn * 256.0;
+    const double t_ing = waves * per_tile / (40.0 * clk);
+    const double mma_clk = bn / 2.0 > 32.0 ? bn / 2.0 : 32.0;
+    const double t_mma = waves * n_units * (row_bytes / 32) * mma_clk / clk;
+    const double t_epi = waves * (bn / 64) * 600.0 * (1.0 + 0.5 * n_in) / clk / 2.0;
+    const double t_hbm = (px * cout * 2.0 * (1 + n_in) + px * cin * 2.0 * (n_taps == 1 ? 1.0 : 1.2)) / 6.2e12;
+    double mx = t_ing;
+    if (t_mma > mx) mx = t_mma;
+    if (t_epi > mx) mx = t_epi;
+    if (t_hbm > mx) mx = t_hbm;
+    double t = mx + 0.1 * (t_ing + t_mma + t_epi + t_hbm - mx);
+    if (ring2) t *= 1.08;
     if (t < best_t) {
       best_t = t;
       best = bn;
@@ -604,7 +627,6 @@ struct IoGeom {
 };
 
 // Shared-memory plan of one launch: [stages][2 staging tiles][operand ring][bias][stats][barriers].
-static const int kSmemBudget = 227 * 1024 - 1024 /*align*/ - 512 /*barriers + tmem slot*/;
 
 static int finish_launch(ConvLaunch* L, const ghnd_conv_desc_t* d, int gemm_cin, int gemm_cout,
                          const void* weights, int total_taps, const IoGeom& g, int kblock = 64) {
@@ -624,7 +646,7 @@ static int finish_launch(ConvLaunch* L, const ghnd_conv_desc_t* d, int gemm_cin,
   if (d->residual != nullptr || d->accumulate) p.has_in0 = 1;
   if (d->mask != nullptr) p.has_in1 = 1;
   const int n_in = p.has_in0 + p.has_in1;
-  p.block_n = pick_block_n(gemm_cout, m_tiles, n_units, row_bytes, n_in);
+  p.block_n = pick_block_n(gemm_cout, m_tiles, n_units, p.n_taps, row_bytes, n_in, d->bias != nullptr);
   p.b_bytes = p.block_n * row_bytes;
   p.n_tiles_n = gemm_cout / p.block_n;
   p.total_tiles = m_tiles * p.n_tiles_n;
