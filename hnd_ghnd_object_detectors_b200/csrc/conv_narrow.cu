@@ -201,6 +201,404 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tensor-core variants for the 64-channel wide side (the only width the model uses).  The FLOPs
+// are negligible; what the SIMT kernels above lose is issue slots (fp32 FMA + LDS + 64-bit index
+// math per pixel), so these kernels map the small GEMMs onto mma.sync.m16n8k16 and are left with
+// nothing but the streaming loads/stores:
+//   narrow_out : [16 pixels x (tap,64 ch)] x [(tap,64 ch) x 8*NT narrow ch]   (A straight from NHWC)
+//   narrow_in  : [16 pixels x (narrow ch,tap)] x [(narrow ch,tap) x 64 ch]    (D straight to NHWC)
+// The GEMM-K / GEMM-N orderings are free, so they are chosen such that every lane's fragment
+// registers are whole 16-byte pieces of a pixel row (no shuffles, no shared-memory staging).
+// fp32 operands (weights; the narrow activations) enter as hi + lo 16-bit pairs, the lo part
+// scaled by 2^11 (f16) / 2^8 (bf16) and accumulated separately, which keeps ~fp32 accuracy.
+// Fragment layout of mma.m16n8k16 (g = lane/4, t = lane%4):
+//   A regs: {row g, k 2t..2t+1} {row g+8, k 2t..} {row g, k 2t+8..} {row g+8, k 2t+8..}
+//   B regs: {k 2t..2t+1, col g} {k 2t+8..2t+9, col g}      D: {row g, col 2t..2t+1} {row g+8, ..}
+// ------------------------------------------------------------------------------------------------
+template <int FMT>
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0,
+                                         uint32_t b1) {
+  if (FMT == GHND_F16) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+        "{%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  } else {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+        "{%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  }
+}
+template <int FMT>
+struct LoScale {
+  static constexpr float kUp = FMT == GHND_F16 ? 2048.f : 256.f;
+  static constexpr float kDown = FMT == GHND_F16 ? (1.f / 2048.f) : (1.f / 256.f);
+};
+// v ~= hi + lo / kUp with hi, lo 16-bit
+template <int FMT>
+__device__ __forceinline__ void split16(float v, uint32_t& hi, uint32_t& lo) {
+  const uint16_t h = float_to_h16(v, FMT);
+  hi = h;
+  lo = float_to_h16((v - h16_to_float(h, FMT)) * LoScale<FMT>::kUp, FMT);
+}
+
+// out[n][co][i][j] (planar fp32) = sum_{tap,c} wt[tap][c][co] * in[n][i+dh][j+dw][c], 64 wide channels.
+// One warp = 16 consecutive (flattened) output pixels; lane (g,t) loads, for rows g and g+8 and
+// every tap, the two 16-byte pieces t and t+4 of the pixel row.  GEMM-K step (tap, s): lane t's
+// logical k {2t,2t+1 | 2t+8,2t+9} are channels base..base+3, base = 32*(s>>1) + 8t + 4*(s&1).
+template <int FMT, int NT>
+__global__ void __launch_bounds__(256, 2)
+    narrow_out_mma_kernel(const uint4* __restrict__ in, const float* __restrict__ wt,
+                          float* __restrict__ out, int N, int Hi, int Wi, int CN, int Ho, int Wo,
+                          NarrowTaps taps) {
+  __shared__ uint4 s_b[16 * NT * 32];  // [k-step][n-tile][lane] = {b0 hi, b1 hi, b0 lo, b1 lo}
+  for (int idx = threadIdx.x; idx < 16 * NT * 32; idx += blockDim.x) {
+    const int l = idx & 31, nt = (idx >> 5) % NT, ks = idx / (32 * NT);
+    const int g = l >> 2, t = l & 3;
+    const int tap = ks >> 2, s = ks & 3;
+    const int base = (s >> 1) * 32 + 8 * t + (s & 1) * 4;
+    const int co = nt * 8 + g;
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float w = (co < CN && tap < taps.n_taps) ? wt[((size_t)tap * 64 + base + e) * CN + co] : 0.f;
+      split16<FMT>(w, hi[e], lo[e]);
+    }
+    s_b[idx] = make_uint4(hi[0] | (hi[1] << 16), hi[2] | (hi[3] << 16), lo[0] | (lo[1] << 16),
+                          lo[2] | (lo[3] << 16));
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const uint32_t npix = (uint32_t)N * Ho * Wo;
+  const uint32_t tiles = (npix + 15) >> 4;
+  for (uint32_t tile = blockIdx.x * 8 + (threadIdx.x >> 5); tile < tiles; tile += gridDim.x * 8) {
+    bool pv[2];
+    int pn[2], pi[2], pj[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const uint32_t p = tile * 16 + g + 8 * r;
+      pv[r] = p < npix;
+      const uint32_t pp = pv[r] ? p : 0;
+      const uint32_t q = pp / (uint32_t)Wo;
+      pj[r] = (int)(pp - q * Wo);
+      pn[r] = (int)(q / (uint32_t)Ho);
+      pi[r] = (int)(q - (uint32_t)pn[r] * Ho);
+    }
+    uint4 v[kNarrowMaxTaps][2][2];
+#pragma unroll
+    for (int tap = 0; tap < kNarrowMaxTaps; ++tap)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int h = pi[r] + taps.dh[tap], w = pj[r] + taps.dw[tap];
+        const bool ok = pv[r] && tap < taps.n_taps && h >= 0 && h < Hi && w >= 0 && w < Wi;
+        const uint4* src = in + (((size_t)pn[r] * Hi + h) * Wi + w) * 8 + t;
+        v[tap][r][0] = ok ? __ldg(src) : make_uint4(0, 0, 0, 0);
+        v[tap][r][1] = ok ? __ldg(src + 4) : make_uint4(0, 0, 0, 0);
+      }
+    float dhi[NT][4], dlo[NT][4];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) dhi[nt][e] = dlo[nt][e] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 16; ++ks) {
+      const int tap = ks >> 2, s = ks & 3, hf = s >> 1;
+      uint32_t a[4];
+      if ((s & 1) == 0) {
+        a[0] = v[tap][0][hf].x;
+        a[1] = v[tap][1][hf].x;
+        a[2] = v[tap][0][hf].y;
+        a[3] = v[tap][1][hf].y;
+      } else {
+        a[0] = v[tap][0][hf].z;
+        a[1] = v[tap][1][hf].z;
+        a[2] = v[tap][0][hf].w;
+        a[3] = v[tap][1][hf].w;
+      }
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const uint4 b = s_b[(ks * NT + nt) * 32 + lane];
+        mma16816<FMT>(dhi[nt], a, b.x, b.y);
+        mma16816<FMT>(dlo[nt], a, b.z, b.w);
+      }
+    }
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int co = nt * 8 + 2 * t + e;
+        if (co < CN) {
+#pragma unroll
+          for (int r = 0; r < 2; ++r)
+            if (pv[r])
+              out[(((size_t)pn[r] * CN + co) * Ho + pi[r]) * Wo + pj[r]] =
+                  dhi[nt][2 * r + e] + dlo[nt][2 * r + e] * LoScale<FMT>::kDown;
+        }
+      }
+  }
+}
+
+// out[n][i][j][co] (NHWC 16-bit, 64 ch) = sum_{tap,ci<CN} wt[tap][ci][co] * f(in[n][ci][i+dh][j+dw]).
+// GEMM-K index k = ci*4 + tap (KS steps of 16); D column (n-tile nn, col 2t+e) is channel
+// 8t + 2nn + e (nn < 4) or 32 + 8t + 2(nn-4) + e, so lane t stores pieces t and t+4 of a pixel row.
+template <int FMT, int KS>
+__global__ void __launch_bounds__(256, 2)
+    narrow_in_mma_kernel(const float* __restrict__ in, const float* __restrict__ pre, int pre_relu,
+                         const float* __restrict__ wt, uint4* __restrict__ out, int N, int Hi, int Wi,
+                         int CN, int Ho, int Wo, NarrowTaps taps) {
+  __shared__ uint4 s_b[KS * 8 * 32];  // [k-step][n-tile][lane] = {b0 hi, b1 hi, b0 lo, b1 lo}
+  for (int idx = threadIdx.x; idx < KS * 8 * 32; idx += blockDim.x) {
+    const int l = idx & 31, nn = (idx >> 5) & 7, ks = idx >> 8;
+    const int g = l >> 2, t = l & 3;
+    const int co = nn < 4 ? 8 * (g >> 1) + 2 * nn + (g & 1) : 32 + 8 * (g >> 1) + 2 * (nn - 4) + (g & 1);
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int k = 16 * ks + 2 * t + (e & 1) + (e >> 1) * 8;
+      const int ci = k >> 2, tap = k & 3;
+      const float w = (ci < CN && tap < taps.n_taps) ? wt[((size_t)tap * CN + ci) * 64 + co] : 0.f;
+      split16<FMT>(w, hi[e], lo[e]);
+    }
+    s_b[idx] = make_uint4(hi[0] | (hi[1] << 16), hi[2] | (hi[3] << 16), lo[0] | (lo[1] << 16),
+                          lo[2] | (lo[3] << 16));
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  // this lane's two taps (e = 0, 1) and its per-k-step channels / pre-transform
+  int tdh[2], tdw[2];
+  bool tok[2];
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int tap = 2 * (t & 1) + e;
+    tok[e] = tap < taps.n_taps;
+    tdh[e] = tap == 0 ? taps.dh[0] : tap == 1 ? taps.dh[1] : tap == 2 ? taps.dh[2] : taps.dh[3];
+    tdw[e] = tap == 0 ? taps.dw[0] : tap == 1 ? taps.dw[1] : tap == 2 ? taps.dw[2] : taps.dw[3];
+  }
+  float psc[KS][2], psh[KS][2];
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+    for (int cs = 0; cs < 2; ++cs) {
+      const int ci = 4 * ks + 2 * cs + (t >> 1);
+      psc[ks][cs] = (pre != nullptr && ci < CN) ? __ldg(pre + ci) : 1.f;
+      psh[ks][cs] = (pre != nullptr && ci < CN) ? __ldg(pre + CN + ci) : 0.f;
+    }
+  const bool has_pre = pre != nullptr;
+  const uint32_t npix = (uint32_t)N * Ho * Wo;
+  const uint32_t tiles = (npix + 15) >> 4;
+  for (uint32_t tile = blockIdx.x * 8 + (threadIdx.x >> 5); tile < tiles; tile += gridDim.x * 8) {
+    bool pv[2];
+    int pn[2], pi[2], pj[2];
+    uint32_t pp[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const uint32_t p = tile * 16 + g + 8 * r;
+      pv[r] = p < npix;
+      pp[r] = pv[r] ? p : 0;
+      const uint32_t q = pp[r] / (uint32_t)Wo;
+      pj[r] = (int)(pp[r] - q * Wo);
+      pn[r] = (int)(q / (uint32_t)Ho);
+      pi[r] = (int)(q - (uint32_t)pn[r] * Ho);
+    }
+    float dhi[8][4], dlo[8][4];
+#pragma unroll
+    for (int nn = 0; nn < 8; ++nn)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) dhi[nn][e] = dlo[nn][e] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      uint32_t ahi[4], alo[4];
+#pragma unroll
+      for (int cs = 0; cs < 2; ++cs) {
+        const int ci = 4 * ks + 2 * cs + (t >> 1);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          uint32_t h2[2], l2[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int h = pi[r] + tdh[e], w = pj[r] + tdw[e];
+            const bool ok = pv[r] && tok[e] && ci < CN && h >= 0 && h < Hi && w >= 0 && w < Wi;
+            float val = 0.f;
+            if (ok) {
+              val = __ldg(in + (((size_t)pn[r] * CN + ci) * Hi + h) * Wi + w);
+              if (has_pre) {
+                val = fmaf(val, psc[ks][cs], psh[ks][cs]);
+                if (pre_relu) val = fmaxf(val, 0.f);
+              }
+            }
+            split16<FMT>(val, h2[e], l2[e]);
+          }
+          ahi[r + 2 * cs] = h2[0] | (h2[1] << 16);
+          alo[r + 2 * cs] = l2[0] | (l2[1] << 16);
+        }
+      }
+#pragma unroll
+      for (int nn = 0; nn < 8; ++nn) {
+        const uint4 b = s_b[(ks * 8 + nn) * 32 + lane];
+        mma16816<FMT>(dhi[nn], ahi, b.x, b.y);
+        mma16816<FMT>(dlo[nn], alo, b.x, b.y);
+        mma16816<FMT>(dlo[nn], ahi, b.z, b.w);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      uint32_t o[8];
+#pragma unroll
+      for (int nn = 0; nn < 8; ++nn)
+        o[nn] = pack2_t<FMT>(dhi[nn][2 * r] + dlo[nn][2 * r] * LoScale<FMT>::kDown,
+                             dhi[nn][2 * r + 1] + dlo[nn][2 * r + 1] * LoScale<FMT>::kDown);
+      if (pv[r]) {
+        uint4* dst = out + (size_t)pp[r] * 8 + t;
+        dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        dst[4] = make_uint4(o[4], o[5], o[6], o[7]);
+      }
+    }
+  }
+}
+
+// Weight gradient, wide-tensor stationary: the CTA walks 32-pixel chunks of rows of b (NHWC, 64
+// ch); each thread owns one (pixel slot, 8-channel piece) whose 16 bytes arrive through a private
+// cp.async ring (kWgStages chunks in flight, no barrier needed: a thread reads only what it
+// copied itself).  The narrow values f(a[ca][q - tap]) of the chunk are staged once per chunk in
+// shared memory (double buffered, one __syncthreads per chunk).
+//   accum[ca][tap][cb] += f(a[n][ca][ib-dh][jb-dw]) * b[n][ib][jb][cb]   for ca in [ca0, ca0+3)
+static constexpr int kWgStages = 8;
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(256, 2)
+    wgrad_narrow_bs_kernel(const float* __restrict__ a, const float* __restrict__ pre, int pre_relu,
+                           const uint4* __restrict__ b, float* __restrict__ accum, int N, int Ha,
+                           int Wa, int Ca, int ca0, int Hb, int Wb, NarrowTaps taps) {
+  __shared__ uint4 s_ring[kWgStages][256];
+  __shared__ float s_a[2][3 * kNarrowMaxTaps * 32];  // [buf][ca][tap][slot]
+  __shared__ float s_acc[3 * kNarrowMaxTaps * 64];
+  const int cg = threadIdx.x & 7, slot = threadIdx.x >> 3;
+  const int cpr = (Wb + 31) >> 5;  // chunks per row of b
+  const int chunks = N * Hb * cpr;
+  const int stride = gridDim.x;
+  auto chunk_src = [&](int c, int& n, int& ib, int& jb0) {
+    const int row = c / cpr;
+    jb0 = (c - row * cpr) << 5;
+    n = row / Hb;
+    ib = row - n * Hb;
+  };
+  auto issue = [&](int c, int stage) {
+    if (c < chunks) {
+      int n, ib, jb0;
+      chunk_src(c, n, ib, jb0);
+      if (jb0 + slot < Wb)
+        cp_async16(&s_ring[stage][threadIdx.x], b + (((size_t)n * Hb + ib) * Wb + jb0 + slot) * 8 + cg);
+    }
+    cp_async_commit();
+  };
+  // narrow values of chunk c: this thread fetches entries threadIdx.x and threadIdx.x + 256 (< 384)
+  auto fetch_a = [&](int c, float (&val)[2]) {
+    val[0] = val[1] = 0.f;
+    if (c >= chunks) return;
+    int n, ib, jb0;
+    chunk_src(c, n, ib, jb0);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int idx = threadIdx.x + 256 * k;
+      if (idx >= 3 * kNarrowMaxTaps * 32) continue;
+      const int sl = idx & 31, tap = (idx >> 5) & 3, c3 = idx >> 7;
+      const int ca = ca0 + c3;
+      if (tap >= taps.n_taps || ca >= Ca) continue;
+      const int ia = ib - taps.dh[tap], ja = jb0 + sl - taps.dw[tap];
+      if (ia < 0 || ia >= Ha || ja < 0 || ja >= Wa) continue;
+      float v = __ldg(a + (((size_t)n * Ca + ca) * Ha + ia) * Wa + ja);
+      if (pre != nullptr) {
+        v = fmaf(v, __ldg(pre + ca), __ldg(pre + Ca + ca));
+        if (pre_relu) v = fmaxf(v, 0.f);
+      }
+      val[k] = v;
+    }
+  };
+  auto store_a = [&](int buf, const float (&val)[2]) {
+    s_a[buf][threadIdx.x] = val[0];
+    if (threadIdx.x + 256 < 3 * kNarrowMaxTaps * 32) s_a[buf][threadIdx.x + 256] = val[1];
+  };
+  float acc[3][kNarrowMaxTaps][8];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int t = 0; t < kNarrowMaxTaps; ++t)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[c][t][e] = 0.f;
+  for (int i = threadIdx.x; i < 3 * kNarrowMaxTaps * 64; i += blockDim.x) s_acc[i] = 0.f;
+#pragma unroll
+  for (int s = 0; s < kWgStages; ++s) issue((int)blockIdx.x + s * stride, s);
+  {
+    float v0[2];
+    fetch_a((int)blockIdx.x, v0);
+    store_a(0, v0);
+  }
+  __syncthreads();
+  int stage = 0, buf = 0;
+  for (int c = blockIdx.x; c < chunks; c += stride) {
+    float nxt[2];
+    fetch_a(c + stride, nxt);  // latency hidden behind this chunk's FMAs
+    cp_async_wait<kWgStages - 1>();
+    int n, ib, jb0;
+    chunk_src(c, n, ib, jb0);
+    if (jb0 + slot < Wb) {
+      const uint4 v = s_ring[stage][threadIdx.x];
+      const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+      float f[8];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 x2 = unpack2_t<FMT>(u[e]);
+        f[2 * e] = x2.x;
+        f[2 * e + 1] = x2.y;
+      }
+#pragma unroll
+      for (int c3 = 0; c3 < 3; ++c3)
+#pragma unroll
+        for (int t = 0; t < kNarrowMaxTaps; ++t) {
+          const float av = s_a[buf][(c3 * kNarrowMaxTaps + t) * 32 + slot];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[c3][t][e] = fmaf(av, f[e], acc[c3][t][e]);
+        }
+    }
+    issue(c + kWgStages * stride, stage);
+    store_a(buf ^ 1, nxt);
+    __syncthreads();
+    stage = stage + 1 == kWgStages ? 0 : stage + 1;
+    buf ^= 1;
+  }
+  cp_async_wait<0>();
+  // fold the 4 pixel slots of a warp, then the warps of the block, then one atomic per value
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int t = 0; t < kNarrowMaxTaps; ++t)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float v = acc[c][t][e];
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        if ((threadIdx.x & 31) < 8) atomicAdd(&s_acc[(c * kNarrowMaxTaps + t) * 64 + cg * 8 + e], v);
+      }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * kNarrowMaxTaps * 64; i += blockDim.x) {
+    const int cb = i & 63, t = (i >> 6) % kNarrowMaxTaps, c = i / (64 * kNarrowMaxTaps);
+    if (t < taps.n_taps && ca0 + c < Ca)
+      atomicAdd(accum + ((size_t)(ca0 + c) * taps.n_taps + t) * 64 + cb, s_acc[i]);
+  }
+}
+
 // accum[ca][tap][cb] -> OIHW dw
 __global__ void wgrad_narrow_finish_kernel(const float* __restrict__ accum, float* __restrict__ dw,
                                            int a_is_output, int Ca, int Cb, int R, int S) {
@@ -371,6 +769,55 @@ void launch_stem_wgrad_finish(const float* accum, const float* scale, float* dw,
   stem_wgrad_finish_kernel<<<(64 * 3 * 49 + 255) / 256, 256, 0, st>>>(accum, scale, dw);
 }
 
+// mma.sync fast paths (64 wide channels, <= 16 narrow channels, pixel count in 32 bits)
+static bool narrow_fast_ok(int c_wide, int c_narrow, int64_t npix) {
+  return c_wide == 64 && c_narrow >= 1 && c_narrow <= 16 && npix > 0 && npix < (int64_t)1 << 30;
+}
+static int narrow_tile_blocks(int64_t npix) {
+  const int64_t tiles = (npix + 15) / 16;
+  int64_t b = (tiles + 7) / 8;
+  const int64_t cap = (int64_t)num_sms() * 2;
+  if (b > cap) b = cap;
+  return (int)(b < 1 ? 1 : b);
+}
+static void launch_narrow_out_mma(const void* in, int fmt, const float* wt, float* out, int N, int Hi,
+                                  int Wi, int CN, int Ho, int Wo, const NarrowTaps& taps,
+                                  cudaStream_t st) {
+  const int blocks = narrow_tile_blocks((int64_t)N * Ho * Wo);
+#define GHND_NO(FMT, NT)                                                                          \
+  narrow_out_mma_kernel<FMT, NT><<<blocks, 256, 0, st>>>((const uint4*)in, wt, out, N, Hi, Wi, CN, \
+                                                         Ho, Wo, taps)
+  if (fmt == GHND_F16) {
+    if (CN <= 8) GHND_NO(GHND_F16, 1); else GHND_NO(GHND_F16, 2);
+  } else {
+    if (CN <= 8) GHND_NO(GHND_BF16, 1); else GHND_NO(GHND_BF16, 2);
+  }
+#undef GHND_NO
+}
+static void launch_narrow_in_mma(const float* in, const float* pre, int pre_relu, const float* wt,
+                                 void* out, int fmt, int N, int Hi, int Wi, int CN, int Ho, int Wo,
+                                 const NarrowTaps& taps, cudaStream_t st) {
+  const int blocks = narrow_tile_blocks((int64_t)N * Ho * Wo);
+  const int ks = (CN + 3) / 4;
+#define GHND_NI(FMT, KS)                                                                          \
+  narrow_in_mma_kernel<FMT, KS><<<blocks, 256, 0, st>>>(in, pre, pre_relu, wt, (uint4*)out, N, Hi, \
+                                                        Wi, CN, Ho, Wo, taps)
+#define GHND_NI_FMT(FMT)            \
+  switch (ks) {                     \
+    case 1: GHND_NI(FMT, 1); break; \
+    case 2: GHND_NI(FMT, 2); break; \
+    case 3: GHND_NI(FMT, 3); break; \
+    default: GHND_NI(FMT, 4); break; \
+  }
+  if (fmt == GHND_F16) {
+    GHND_NI_FMT(GHND_F16)
+  } else {
+    GHND_NI_FMT(GHND_BF16)
+  }
+#undef GHND_NI_FMT
+#undef GHND_NI
+}
+
 }  // namespace ghnd
 
 extern "C" {
@@ -404,7 +851,9 @@ int ghnd_conv_narrow_out(const void* x, int x_fmt, const float* w, float* y, int
     }
   const int lanes = C / 8;
   const int64_t npix = (int64_t)N * Ho * Wo;
-  if (K <= 3)
+  if (narrow_fast_ok(C, K, npix) && (x_fmt == GHND_F16 || x_fmt == GHND_BF16))
+    launch_narrow_out_mma(x, x_fmt, (const float*)workspace, y, N, H, W, K, Ho, Wo, taps, st);
+  else if (K <= 3)
     narrow_out_kernel<3><<<blocks_for_pixels(npix, 256 / lanes), 256,
                            (size_t)R * S * C * K * sizeof(float), st>>>(
         (const uint4*)x, x_fmt, (const float*)workspace, y, N, H, W, C, K, Ho, Wo, taps);
@@ -441,7 +890,9 @@ int ghnd_conv_narrow_out_dgrad(const void* dy, int dy_fmt, const float* w, float
     }
   const int lanes = K / 8;
   const int64_t npix = (int64_t)N * H * W;
-  if (C <= 3)
+  if (narrow_fast_ok(K, C, npix) && (dy_fmt == GHND_F16 || dy_fmt == GHND_BF16))
+    launch_narrow_out_mma(dy, dy_fmt, (const float*)workspace, dx, N, Ho, Wo, C, H, W, taps, st);
+  else if (C <= 3)
     narrow_out_kernel<3><<<blocks_for_pixels(npix, 256 / lanes), 256,
                            (size_t)R * S * C * K * sizeof(float), st>>>(
         (const uint4*)dy, dy_fmt, (const float*)workspace, dx, N, Ho, Wo, K, C, H, W, taps);
@@ -497,10 +948,14 @@ int ghnd_conv_narrow_in(const float* x, const float* pre_scale_shift, int pre_re
   GHND_CHECK_ARG(Ho > 0 && Wo > 0, "conv_narrow_in: empty output");
   const int lanes = K / 8;
   const int64_t npix = (int64_t)N * Ho * Wo;
-  narrow_in_kernel<<<blocks_for_pixels(npix, 256 / lanes), 256,
-                     (size_t)R * S * C * K * sizeof(float), st>>>(
-      x, pre_scale_shift, pre_relu, (const float*)workspace, (uint4*)y, y_fmt, N, H, W, C, K, Ho, Wo,
-      taps);
+  if (narrow_fast_ok(K, C, npix))
+    launch_narrow_in_mma(x, pre_scale_shift, pre_relu, (const float*)workspace, y, y_fmt, N, H, W, C,
+                         Ho, Wo, taps, st);
+  else
+    narrow_in_kernel<<<blocks_for_pixels(npix, 256 / lanes), 256,
+                       (size_t)R * S * C * K * sizeof(float), st>>>(
+        x, pre_scale_shift, pre_relu, (const float*)workspace, (uint4*)y, y_fmt, N, H, W, C, K, Ho,
+        Wo, taps);
   GHND_LAUNCH_CHECK("narrow_in_kernel");
   return GHND_OK;
 }
@@ -530,10 +985,25 @@ int ghnd_wgrad_narrow(const float* a, const float* pre_scale_shift, int pre_relu
     }
   const int lanes = Cb / 8;
   const int64_t npix = (int64_t)N * Ha * Wa;
+  const int64_t chunks_b = (int64_t)N * Hb * ((Wb + 31) / 32);
+  const bool fast = Cb == 64 && chunks_b < (int64_t)1 << 30 && (b_fmt == GHND_F16 || b_fmt == GHND_BF16);
   for (int ca0 = 0; ca0 < Ca; ca0 += 3) {
-    wgrad_narrow_kernel<<<blocks_for_pixels(npix, (256 / lanes) * 8, 2), 256, 0, st>>>(
-        a, pre_scale_shift, pre_relu, (const uint4*)b, b_fmt, (float*)workspace, N, Ha, Wa, Ca, ca0,
-        Hb, Wb, Cb, taps);
+    if (fast) {
+      int blocks = num_sms() * 2;
+      if (blocks > chunks_b) blocks = (int)chunks_b;
+      if (b_fmt == GHND_F16)
+        wgrad_narrow_bs_kernel<GHND_F16><<<blocks, 256, 0, st>>>(
+            a, pre_scale_shift, pre_relu, (const uint4*)b, (float*)workspace, N, Ha, Wa, Ca, ca0, Hb,
+            Wb, taps);
+      else
+        wgrad_narrow_bs_kernel<GHND_BF16><<<blocks, 256, 0, st>>>(
+            a, pre_scale_shift, pre_relu, (const uint4*)b, (float*)workspace, N, Ha, Wa, Ca, ca0, Hb,
+            Wb, taps);
+    } else {
+      wgrad_narrow_kernel<<<blocks_for_pixels(npix, (256 / lanes) * 8, 2), 256, 0, st>>>(
+          a, pre_scale_shift, pre_relu, (const uint4*)b, b_fmt, (float*)workspace, N, Ha, Wa, Ca, ca0,
+          Hb, Wb, Cb, taps);
+    }
     GHND_LAUNCH_CHECK("wgrad_narrow_kernel");
   }
   wgrad_narrow_finish_kernel<<<4, 256, 0, st>>>((const float*)workspace, dw_oihw, a_is_output, Ca, Cb,

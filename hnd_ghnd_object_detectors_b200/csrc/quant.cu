@@ -80,6 +80,37 @@ struct QParams {
   float mn, mx;
 };
 
+// scale / zero-point from the tensor's min and max, operation by operation as the reference
+__device__ __forceinline__ void derive_qparams(float mn, float mx, float qmax, float inv_range,
+                                               int scale_mode, float& scale, int& zp) {
+  // scale = (max - min) / (qmax - qmin)        tensor_util.py:12
+  const float range = __fsub_rn(mx, mn);
+  scale = scale_mode == GHND_QSCALE_RECIP ? __fmul_rn(range, inv_range) : __fdiv_rn(range, qmax);
+  // initial_zero_point = qmin - min / scale    tensor_util.py:13
+  const float izp = __fsub_rn(0.0f, __fdiv_rn(mn, scale));
+  // clamp to [qmin, qmax] then int() truncation   tensor_util.py:14-15 ; NaN -> marker
+  if (izp < 0.0f)
+    zp = 0;
+  else if (izp > qmax)
+    zp = (int)qmax;
+  else if (izp != izp)
+    zp = INT_MIN;
+  else
+    zp = (int)izp;  // cvt.rzi
+}
+// qx = zero_point + x / scale ; clamp ; round-half-even ; byte   tensor_util.py:16-17
+__device__ __forceinline__ uint32_t quant1(float v, float zpf, float scale, float qmax) {
+  float t = __fadd_rn(zpf, __fdiv_rn(v, scale));
+  t = t < 0.0f ? 0.0f : (t > qmax ? qmax : t);
+  return (uint32_t)(int)rintf(t) & 0xffu;
+}
+__device__ __forceinline__ uint32_t quant4(uint4 v, float zpf, float scale, float qmax) {
+  return quant1(__uint_as_float(v.x), zpf, scale, qmax) |
+         (quant1(__uint_as_float(v.y), zpf, scale, qmax) << 8) |
+         (quant1(__uint_as_float(v.z), zpf, scale, qmax) << 16) |
+         (quant1(__uint_as_float(v.w), zpf, scale, qmax) << 24);
+}
+
 // pass 2: every block folds the partials (L2 resident), derives scale / zero-point, quantizes.
 __global__ void __launch_bounds__(kQThreads)
     quant_apply_kernel(const float* __restrict__ x, int64_t n, int vec_ok,
@@ -92,22 +123,9 @@ __global__ void __launch_bounds__(kQThreads)
     mx = nan_max(mx, partial[2 * i + 1]);
   }
   block_minmax(mn, mx);
-  // scale = (max - min) / (qmax - qmin)        tensor_util.py:12
-  const float range = __fsub_rn(mx, mn);
-  const float scale =
-      scale_mode == GHND_QSCALE_RECIP ? __fmul_rn(range, inv_range) : __fdiv_rn(range, qmax);
-  // initial_zero_point = qmin - min / scale    tensor_util.py:13
-  const float izp = __fsub_rn(0.0f, __fdiv_rn(mn, scale));
-  // clamp to [qmin, qmax] then int() truncation   tensor_util.py:14-15 ; NaN -> marker
+  float scale;
   int zp;
-  if (izp < 0.0f)
-    zp = 0;
-  else if (izp > qmax)
-    zp = (int)qmax;
-  else if (izp != izp)
-    zp = INT_MIN;
-  else
-    zp = (int)izp;  // cvt.rzi
+  derive_qparams(mn, mx, qmax, inv_range, scale_mode, scale, zp);
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     qp->scale = scale;
     qp->zero_point = zp;
@@ -115,16 +133,6 @@ __global__ void __launch_bounds__(kQThreads)
     qp->mx = mx;
   }
   const float zpf = (float)zp;
-  auto quant1 = [&](float v) -> uint32_t {
-    // qx = zero_point + x / scale ; clamp ; round-half-even ; byte   tensor_util.py:16-17
-    float t = __fadd_rn(zpf, __fdiv_rn(v, scale));
-    t = t < 0.0f ? 0.0f : (t > qmax ? qmax : t);
-    return (uint32_t)(int)rintf(t) & 0xffu;
-  };
-  auto quant4 = [&](uint4 v) -> uint32_t {
-    return quant1(__uint_as_float(v.x)) | (quant1(__uint_as_float(v.y)) << 8) |
-           (quant1(__uint_as_float(v.z)) << 16) | (quant1(__uint_as_float(v.w)) << 24);
-  };
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
   int64_t done = 0;
@@ -136,15 +144,128 @@ __global__ void __launch_bounds__(kQThreads)
       uint4 a = ld_stream(x4 + 4 * i), b = ld_stream(x4 + 4 * i + 1), c = ld_stream(x4 + 4 * i + 2),
             d = ld_stream(x4 + 4 * i + 3);
       uint4 o;
-      o.x = quant4(a);
-      o.y = quant4(b);
-      o.z = quant4(c);
-      o.w = quant4(d);
+      o.x = quant4(a, zpf, scale, qmax);
+      o.y = quant4(b, zpf, scale, qmax);
+      o.z = quant4(c, zpf, scale, qmax);
+      o.w = quant4(d, zpf, scale, qmax);
       st_stream(q16 + i, o);
     }
     done = n16 << 4;
   }
-  for (int64_t i = done + tid; i < n; i += nthreads) q[i] = (uint8_t)quant1(x[i]);
+  for (int64_t i = done + tid; i < n; i += nthreads) q[i] = (uint8_t)quant1(x[i], zpf, scale, qmax);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Single-launch quantizer: one persistent CTA per SM.  Phase 1 streams the CTA's contiguous slice
+// of x from HBM ONCE into shared memory (up to kQFSmemBytes of it; the rest of a very large slice
+// is only min/max-reduced) and publishes the CTA's min/max; a grid-wide barrier follows; phase 2
+// folds the partials, derives scale / zero-point and quantizes the slice out of shared memory, so
+// HBM sees the compulsory 4 B read + 1 B write per element.  For the split-computing tensor
+// (bch x 204 x 340 per image) up to 36 images stay fully on chip.
+// Barrier state: counters[0] (arrivals) and counters[1] (departures) must be zero on entry; the last
+// departing CTA zeroes both again.  A CTA that waits longer than ~2 s gives up and flags the
+// result (zero_point = INT_MIN + 1) instead of hanging the device.
+// ------------------------------------------------------------------------------------------------
+static constexpr int kQFThreads = 1024;
+static constexpr int kQFSmemBytes = 200 * 1024;
+static constexpr int kQFResidentVec = kQFSmemBytes / 16;  // uint4 (4-element) vectors kept on chip
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__global__ void __launch_bounds__(kQFThreads, 1)
+    quant_fused_kernel(const float* __restrict__ x, int64_t n, float* partial, unsigned* counters,
+                       float qmax, float inv_range, int scale_mode, uint8_t* __restrict__ q,
+                       QParams* __restrict__ qp) {
+  extern __shared__ uint4 s_x[];
+  __shared__ int s_timeout;
+  const int64_t nvec = n >> 2;  // 4-element vectors (x and q are 16-byte aligned on this path)
+  const int64_t per = (nvec + gridDim.x - 1) / gridDim.x;
+  int64_t v0 = per * blockIdx.x;
+  if (v0 > nvec) v0 = nvec;
+  int64_t v1 = v0 + per;
+  if (v1 > nvec) v1 = nvec;
+  const int len = (int)(v1 - v0);
+  const int res = len < kQFResidentVec ? len : kQFResidentVec;
+  const uint4* x4 = reinterpret_cast<const uint4*>(x) + v0;
+  uint32_t* q4 = reinterpret_cast<uint32_t*>(q) + v0;
+  float mn = INFINITY, mx = -INFINITY;
+  if (threadIdx.x == 0) s_timeout = 0;
+#pragma unroll 4
+  for (int i = threadIdx.x; i < res; i += kQFThreads) {
+    const uint4 v = ld_stream(x4 + i);
+    s_x[i] = v;
+    const float a = __uint_as_float(v.x), b = __uint_as_float(v.y), c = __uint_as_float(v.z),
+                d = __uint_as_float(v.w);
+    mn = nan_min(nan_min(mn, a), nan_min(b, nan_min(c, d)));
+    mx = nan_max(nan_max(mx, a), nan_max(b, nan_max(c, d)));
+  }
+#pragma unroll 4
+  for (int i = res + threadIdx.x; i < len; i += kQFThreads) {
+    const uint4 v = ld_stream(x4 + i);  // re-read in phase 2 (L2 hit at these sizes)
+    const float a = __uint_as_float(v.x), b = __uint_as_float(v.y), c = __uint_as_float(v.z),
+                d = __uint_as_float(v.w);
+    mn = nan_min(nan_min(mn, a), nan_min(b, nan_min(c, d)));
+    mx = nan_max(nan_max(mx, a), nan_max(b, nan_max(c, d)));
+  }
+  if (blockIdx.x == 0)
+    for (int64_t i = (nvec << 2) + threadIdx.x; i < n; i += kQFThreads) {
+      mn = nan_min(mn, x[i]);
+      mx = nan_max(mx, x[i]);
+    }
+  block_minmax(mn, mx);
+  // ---- grid barrier ----
+  if (threadIdx.x == 0) {
+    partial[2 * blockIdx.x] = mn;
+    partial[2 * blockIdx.x + 1] = mx;
+    __threadfence();
+    atomicAdd(&counters[0], 1u);
+    const long long t0 = clock64();
+    while (ld_acquire_u32(&counters[0]) < gridDim.x) {
+      if (clock64() - t0 > 4000000000ll) {
+        s_timeout = 1;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  mn = INFINITY;
+  mx = -INFINITY;
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += kQFThreads) {
+    mn = nan_min(mn, __ldcg(partial + 2 * i));
+    mx = nan_max(mx, __ldcg(partial + 2 * i + 1));
+  }
+  block_minmax(mn, mx);
+  float scale;
+  int zp;
+  derive_qparams(mn, mx, qmax, inv_range, scale_mode, scale, zp);
+  const float zpf = (float)zp;
+#pragma unroll 4
+  for (int i = threadIdx.x; i < res; i += kQFThreads) q4[i] = quant4(s_x[i], zpf, scale, qmax);
+#pragma unroll 4
+  for (int i = res + threadIdx.x; i < len; i += kQFThreads)
+    q4[i] = quant4(ld_stream(x4 + i), zpf, scale, qmax);
+  if (blockIdx.x == 0)
+    for (int64_t i = (nvec << 2) + threadIdx.x; i < n; i += kQFThreads)
+      q[i] = (uint8_t)quant1(x[i], zpf, scale, qmax);
+  // ---- departure: publish the parameters, re-arm the barrier for the next launch ----
+  if (threadIdx.x == 0) {
+    if (blockIdx.x == 0) {  // a barrier that timed out did so for every waiting CTA, this one included
+      qp->scale = scale;
+      qp->zero_point = s_timeout ? INT_MIN + 1 : zp;
+      qp->mn = mn;
+      qp->mx = mx;
+    }
+    __threadfence();
+    const unsigned d = atomicAdd(&counters[1], 1u);
+    if (d == gridDim.x - 1) {
+      counters[0] = 0;
+      counters[1] = 0;
+      __threadfence();
+    }
+  }
 }
 
 __global__ void __launch_bounds__(kQThreads)
@@ -195,7 +316,7 @@ extern "C" {
 
 size_t ghnd_quantize_u8_workspace_bytes(int64_t n) {
   (void)n;
-  return (size_t)ghnd::kQMaxBlocks * 2 * sizeof(float);
+  return (size_t)ghnd::kQMaxBlocks * 2 * sizeof(float) + 4 * sizeof(unsigned);
 }
 
 int ghnd_quantize_u8(const float* x, int64_t n, int num_bits, int scale_mode, uint8_t* q,
@@ -213,6 +334,25 @@ int ghnd_quantize_u8(const float* x, int64_t n, int num_bits, int scale_mode, ui
   const int blocks = quant_blocks(n);
   const float qmax = (float)((1 << num_bits) - 1);
   const float inv_range = 1.0f / qmax;  // torch CUDA: a / cpu_scalar == a * (1/scalar) in fp32
+  if (vec_ok && n >= 4096) {
+    // single persistent launch; workspace = [2 * kQMaxBlocks floats of partials][4 barrier words]
+    static bool attr_set = false;
+    if (!attr_set) {
+      GHND_CUDA(cudaFuncSetAttribute(quant_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     kQFSmemBytes));
+      attr_set = true;
+    }
+    int grid = num_sms();
+    if (grid > kQMaxBlocks) grid = kQMaxBlocks;
+    const int64_t want = ((n >> 2) + kQFThreads - 1) / kQFThreads;  // no CTA without a vector
+    if (grid > want) grid = (int)want;
+    unsigned* counters = (unsigned*)((float*)workspace + 2 * kQMaxBlocks);
+    quant_fused_kernel<<<grid, kQFThreads, kQFSmemBytes, st>>>(x, n, (float*)workspace, counters, qmax,
+                                                             inv_range, scale_mode, q,
+                                                             (QParams*)qparams);
+    GHND_LAUNCH_CHECK("quant_fused_kernel");
+    return GHND_OK;
+  }
   quant_minmax_kernel<<<blocks, kQThreads, 0, st>>>(x, n, vec_ok, (float*)workspace);
   GHND_LAUNCH_CHECK("quant_minmax_kernel");
   quant_apply_kernel<<<blocks, kQThreads, 0, st>>>(x, n, vec_ok, (const float*)workspace, blocks,

@@ -647,7 +647,7 @@ class EncodePlan(object):
         self.q = torch.empty(tuple(self.z.shape), dtype=torch.uint8, device=dev)
         self.qparams = torch.zeros(4, dtype=torch.int32, device=dev)
         self.qws_bytes = _lib.load().ghnd_quantize_u8_workspace_bytes(self.z.numel())
-        self.qws = _empty((self.qws_bytes,), torch.uint8, dev)
+        self.qws = torch.zeros((self.qws_bytes,), dtype=torch.uint8, device=dev)  # barrier words start at 0
         self.graph = None
 
     def load_images(self, images):
@@ -664,7 +664,7 @@ class EncodePlan(object):
         _lib.call("ghnd_quantize_u8", _lib.ptr(self.z), self.z.numel(), self.num_bits, self.scale_mode,
                   _lib.ptr(self.q), _lib.ptr(self.qparams), _lib.ptr(self.qws), self.qws_bytes,
                   _lib.stream_ptr())
-        ops._count(2)
+        ops._count(1)
         return self.q
 
     def capture(self):

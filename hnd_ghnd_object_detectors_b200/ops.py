@@ -48,9 +48,9 @@ def quantize_u8(x, num_bits=8, scale_mode=_lib.QSCALE_DIV):
     qp = torch.empty(4, dtype=torch.int32, device=x.device)
     n = x.numel()
     wsz = _lib.load().ghnd_quantize_u8_workspace_bytes(n)
-    ws = _ws(wsz, x.device)
+    ws = torch.zeros(wsz, dtype=torch.uint8, device=x.device)  # barrier words must start at zero
     call("ghnd_quantize_u8", ptr(x), n, num_bits, scale_mode, ptr(q), ptr(qp), ptr(ws), wsz, stream_ptr())
-    _count(2)
+    _count(1)
     return q, qp
 
 

@@ -62,8 +62,7 @@ class RcnnHead(nn.Module):
             return self.plan.z.half(), tshape, image_sizes, original_image_sizes
         host = qp.cpu()  # python-int zero point of the reference API: one D2H read
         zp = int(host[1])
-        if zp == tensor_util._NAN_MARKER:
-            raise ValueError("cannot convert float NaN to integer")
+        tensor_util.check_zero_point(zp)
         qz = tensor_util.QuantizedTensor(tensor=q, scale=qp[0:1].view(torch.float32).reshape(()), zero_point=zp)
         return qz, tshape, image_sizes, original_image_sizes
 

@@ -15,6 +15,16 @@ from . import _lib, ops
 QuantizedTensor = namedtuple('QuantizedTensor', ['tensor', 'scale', 'zero_point'])
 
 _NAN_MARKER = -2 ** 31
+_BARRIER_TIMEOUT_MARKER = -2 ** 31 + 1  # quant_fused_kernel: a CTA never reached the grid barrier
+
+
+def check_zero_point(zero_point):
+    if zero_point == _NAN_MARKER:
+        raise ValueError("cannot convert float NaN to integer")  # int(nan) in tensor_util.py:15
+    if zero_point == _BARRIER_TIMEOUT_MARKER:
+        raise _lib.GhndError("ghnd_quantize_u8: grid barrier timed out (workspace not zeroed, or the "
+                             "device cannot co-schedule one CTA per SM)")
+    return zero_point
 
 
 def _scale_mode():
@@ -31,8 +41,7 @@ def quantize_tensor(x, num_bits=8):
     q, qp = ops.quantize_u8(x, num_bits, _scale_mode())
     host = qp.cpu()  # the reference API returns a python int zero-point: one unavoidable D2H sync
     zero_point = int(host[1])
-    if zero_point == _NAN_MARKER:
-        raise ValueError("cannot convert float NaN to integer")  # int(nan) in tensor_util.py:15
+    check_zero_point(zero_point)
     scale = qp[0:1].view(torch.float32).reshape(())
     return QuantizedTensor(tensor=q, scale=scale, zero_point=zero_point)
 

@@ -49,6 +49,13 @@ int ghnd_device_check(void);
  *   GHND_QSCALE_DIV   IEEE division            (reference executed on CPU; oracle and goldens)
  *   GHND_QSCALE_RECIP multiply by fl(1/255)    (reference executed by torch on a CUDA device)
  * qparams (device, 16 bytes): [0] float scale, [1] int32 zero_point, [2] float min, [3] float max
+ *   zero_point INT_MIN     : the reference would raise (int(NaN))
+ *   zero_point INT_MIN + 1 : the grid barrier of the single-launch kernel timed out (see below)
+ * workspace: ghnd_quantize_u8_workspace_bytes(n) bytes that MUST BE ZERO on first use; the call
+ *   leaves them zeroed again (per-CTA min/max partials followed by the words of a grid-wide
+ *   barrier: the 16-byte-aligned path is ONE persistent launch, one CTA per SM, that keeps its
+ *   slice of x in shared memory between the min/max pass and the quantize pass).  One workspace
+ *   per stream: concurrent calls must not share it.
  * ------------------------------------------------------------------------------------------ */
 #define GHND_QSCALE_DIV 0
 #define GHND_QSCALE_RECIP 1

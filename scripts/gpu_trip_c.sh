@@ -1,0 +1,17 @@
+# Round-1 trip C: full GPU tests, smoke, bench, launch list, ncu --set full of the bottleneck-side
+# kernels (narrow convs, quantizer) and the other HBM-bound kernels.
+cd ${GRAFT_REPO_ROOT:-.}
+mkdir -p gpurun_out
+bash scripts/gpu_tests.sh
+timeout 600 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke -> $?"; tail -2 gpurun_out/smoke.log
+timeout 1200 python bench.py --steps 40 --warmup 5 > gpurun_out/bench1.log 2>gpurun_out/bench1.err; echo "bench -> $?"; tail -c 5000 gpurun_out/bench1.log; tail -5 gpurun_out/bench1.err
+timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python scripts/profile_step.py > gpurun_out/ncu_step.log 2>&1; echo "ncu list -> $?"
+python scripts/join_launches.py gpurun_out/launches.csv gpurun_out/step_ops.json > gpurun_out/per_layer.txt 2>&1
+python scripts/summarize_launches.py gpurun_out/launches.csv 40 > gpurun_out/launch_summary.txt 2>&1
+head -40 gpurun_out/launch_summary.txt
+timeout 600 ncu --profile-from-start off --set full --clock-control none -k regex:'narrow|sse_kernel|bn_bwd_reduce|maxpool' -f -o /tmp/hbm_kernels python scripts/profile_step.py > gpurun_out/ncu_hbm.log 2>&1; echo "ncu full hbm -> $?"
+ncu -i /tmp/hbm_kernels.ncu-rep --page raw --csv > gpurun_out/hbm_kernels_raw.csv 2>/dev/null
+timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_encode64.csv python scripts/profile_encode.py 64 > gpurun_out/ncu_enc.log 2>&1; echo "ncu encode list -> $?"
+timeout 600 ncu --profile-from-start off --set full --clock-control none -k regex:'quant|narrow' -f -o /tmp/enc_kernels python scripts/profile_encode.py 64 > gpurun_out/ncu_enc_full.log 2>&1; echo "ncu full encode -> $?"
+ncu -i /tmp/enc_kernels.ncu-rep --page raw --csv > gpurun_out/encode_kernels_raw.csv 2>/dev/null
+du -sh gpurun_out; ls gpurun_out

@@ -49,7 +49,36 @@ def test_quantizer_golden_bit_exact(ops, golden_dir):
         assert np.array_equal(deq.cpu().numpy(), g[name + ".deq"], equal_nan=True), name
 
 
-@pytest.mark.parametrize("shape", [(1, 3, 204, 340), (4, 3, 204, 340), (64, 3, 204, 340), (1, 3, 7, 13)])
+def test_quantizer_workspace_reuse_and_unaligned(ops):
+    """The single-launch kernel re-arms its grid barrier: the same (once-zeroed) workspace serves
+    repeated calls.  A 4-byte-aligned-only tensor takes the two-kernel path; both are bit exact."""
+    from hnd_ghnd_object_detectors_b200 import _lib
+    lib = _lib.load()
+    torch.manual_seed(11)
+    xs = [torch.randn(3, 3, 204, 340) * (1 + i) - 0.2 * i for i in range(4)]
+    n = xs[0].numel()
+    wsz = lib.ghnd_quantize_u8_workspace_bytes(n)
+    ws = torch.zeros(wsz, dtype=torch.uint8, device="cuda")
+    q = torch.empty(xs[0].shape, dtype=torch.uint8, device="cuda")
+    qp = torch.zeros(4, dtype=torch.int32, device="cuda")
+    for x in xs:
+        xc = x.cuda()
+        _lib.call("ghnd_quantize_u8", _lib.ptr(xc), n, 8, _lib.QSCALE_DIV, _lib.ptr(q), _lib.ptr(qp),
+                  _lib.ptr(ws), wsz, _lib.stream_ptr())
+        qo, so, zo = O.quantize_tensor_np(x.numpy(), 8, "div")
+        assert np.array_equal(q.cpu().numpy(), qo) and int(qp[1]) == zo
+    assert int(ws.view(torch.int32)[-4:].abs().sum()) == 0  # barrier words left at zero
+    # unaligned input (offset by one float): two-kernel fallback
+    big = torch.randn(n + 1).cuda()
+    xu = big[1:]
+    assert xu.data_ptr() % 16 != 0
+    qu, qpu = ops.quantize_u8(xu.view(3, 3, 204, 340), 8, _lib.QSCALE_DIV)
+    qo, so, zo = O.quantize_tensor_np(xu.cpu().numpy().reshape(3, 3, 204, 340), 8, "div")
+    assert np.array_equal(qu.cpu().numpy(), qo) and int(qpu[1]) == zo
+
+
+@pytest.mark.parametrize("shape", [(1, 3, 204, 340), (4, 3, 204, 340), (36, 3, 204, 340), (64, 3, 204, 340),
+                                   (5, 3, 41, 17), (1, 3, 7, 13)])
 def test_quantizer_vs_oracle_and_torch_cuda(ops, shape):
     from hnd_ghnd_object_detectors_b200 import _lib
     torch.manual_seed(shape[0])
@@ -370,11 +399,13 @@ def test_bn_planar(ops):
 # ---------------------------------------------------------------------------------------------
 # narrow convs (enc7 / dec2) forward, dgrad, wgrad
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("bch", [3, 6])
-def test_narrow_convs(ops, bch):
+@pytest.mark.parametrize("bch,geom", [(3, (2, 23, 31)), (6, (2, 23, 31)), (12, (1, 40, 37)), (3, (2, 100, 171))])
+def test_narrow_convs(ops, bch, geom):
+    """fp32 operands enter the mma.sync kernels as hi + lo 16-bit pairs: results stay at fp32-level
+    accuracy for exactly representable 16-bit inputs (1e-5; 3e-5 with bf16 inputs: 16-bit mantissa)."""
     torch.manual_seed(bch)
     dt = torch.float16
-    N, H, W = 2, 23, 31
+    N, H, W = geom
     # enc7: 64 -> bch, k2 p1
     x = r16(torch.randn(N, 64, H, W), dt).requires_grad_(True)
     w7 = (torch.randn(bch, 64, 2, 2) * 0.1).requires_grad_(True)
@@ -402,7 +433,7 @@ def test_narrow_convs(ops, bch):
     assert rel(ops.to_nchw_f32(yd).cpu(), y.detach()) < 1e-3
     dyd = ops.to_nhwc16(dy.cuda(), torch.bfloat16)
     dad = ops.conv_narrow_out_dgrad(dyd, w2.detach().cuda(), 0, H + 1, W + 1)
-    assert rel(dad.cpu(), da_ref) < 1e-5
+    assert rel(dad.cpu(), da_ref) < 3e-5
     dw2 = torch.empty(64, bch, 2, 2, device="cuda")
     ops.wgrad_narrow(zin.detach().cuda(), dyd, dw2, False, 2, 2, 0, pre=pre, pre_relu=True)
     assert rel(dw2.cpu(), dw2_ref) < 1e-4
