@@ -78,6 +78,54 @@ __global__ void stem_pack_kernel(const float* __restrict__ img, int H, int W, fl
   }
 }
 
+// Same packing with the transform's bilinear resize fused in: the reference
+// normalises, then calls interpolate(scale_factor, mode='bilinear', align_corners=False)
+// (src/models/org/rcnn.py:29-45), then zero-pads in batch_images.  Source index and tap weights
+// follow ATen's upsample_bilinear2d (area_pixel_compute_source_index: src = rscale*(dst+0.5)-0.5,
+// clamped at 0; second tap = first + (first < size-1)); the four taps are normalised first, like
+// the reference's order of operations.
+__global__ void stem_pack_resize_kernel(const float* __restrict__ img, int H, int W, int Ho, int Wo,
+                                        float rh, float rw, float m0, float m1, float m2, float s0,
+                                        float s1, float s2, uint2* __restrict__ dst, int fmt,
+                                        int rows, int cols) {
+  const int64_t total = (int64_t)rows * cols;
+  const int64_t hw = (int64_t)H * W;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), c = (int)(i - (int64_t)r * cols);
+    const int h = r - 3, w = c - 3;
+    uint2 o = make_uint2(0u, 0u);
+    if (h >= 0 && h < Ho && w >= 0 && w < Wo) {
+      float hr = __fsub_rn(__fmul_rn(rh, (float)h + 0.5f), 0.5f);
+      float wr = __fsub_rn(__fmul_rn(rw, (float)w + 0.5f), 0.5f);
+      hr = hr < 0.f ? 0.f : hr;
+      wr = wr < 0.f ? 0.f : wr;
+      int h1 = (int)hr, w1 = (int)wr;
+      h1 = h1 > H - 1 ? H - 1 : h1;
+      w1 = w1 > W - 1 ? W - 1 : w1;
+      const int hp = (h1 < H - 1) ? 1 : 0, wp = (w1 < W - 1) ? 1 : 0;
+      const float h1l = hr - (float)h1, h0l = 1.f - h1l;
+      const float w1l = wr - (float)w1, w0l = 1.f - w1l;
+      const int64_t a00 = (int64_t)h1 * W + w1, a01 = a00 + wp, a10 = a00 + (int64_t)hp * W,
+                    a11 = a10 + wp;
+      const float mean[3] = {m0, m1, m2}, sd[3] = {s0, s1, s2};
+      float v[3];
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {
+        const float* p = img + ch * hw;
+        const float x00 = __fdiv_rn(__fsub_rn(p[a00], mean[ch]), sd[ch]);
+        const float x01 = __fdiv_rn(__fsub_rn(p[a01], mean[ch]), sd[ch]);
+        const float x10 = __fdiv_rn(__fsub_rn(p[a10], mean[ch]), sd[ch]);
+        const float x11 = __fdiv_rn(__fsub_rn(p[a11], mean[ch]), sd[ch]);
+        v[ch] = h0l * (w0l * x00 + w1l * x01) + h1l * (w0l * x10 + w1l * x11);
+      }
+      o.x = pack2(v[0], v[1], fmt);
+      o.y = pack2(v[2], 0.f, fmt);
+    }
+    dst[i] = o;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // max-pool 3x3 s2 p1 (NHWC, 8 channels per thread) + backward fused with the ReLU mask
 // ------------------------------------------------------------------------------------------------
@@ -773,6 +821,24 @@ int ghnd_stem_pack_image(const float* img_chw, int H, int W, const float* mean, 
   stem_pack_kernel<<<grid_for((int64_t)rows * cols, 256), 256, 0, (cudaStream_t)stream>>>(
       img_chw, H, W, mean[0], mean[1], mean[2], std_[0], std_[1], std_[2], d, dst_fmt, rows, cols);
   GHND_LAUNCH_CHECK("stem_pack_kernel");
+  return GHND_OK;
+}
+
+int ghnd_stem_pack_image_resized(const float* img_chw, int H, int W, int Ho, int Wo, float rscale_h,
+                                 float rscale_w, const float* mean, const float* std_, void* dst,
+                                 int dst_fmt, int n_index, int Hp, int Wp, void* stream) {
+  GHND_CHECK_ARG(img_chw && mean && std_ && dst && fmt16(dst_fmt),
+                 "stem_pack_image_resized: bad argument");
+  GHND_CHECK_ARG(H > 0 && W > 0 && Ho > 0 && Wo > 0 && Ho <= Hp && Wo <= Wp && Hp % 2 == 0 &&
+                     Wp % 8 == 0 && n_index >= 0 && rscale_h > 0.f && rscale_w > 0.f,
+                 "stem_pack_image_resized: bad geometry H=%d W=%d Ho=%d Wo=%d Hp=%d Wp=%d", H, W, Ho,
+                 Wo, Hp, Wp);
+  const int rows = Hp + 6, cols = Wp + 8;
+  uint2* d = (uint2*)dst + (int64_t)n_index * rows * cols;
+  stem_pack_resize_kernel<<<grid_for((int64_t)rows * cols, 256), 256, 0, (cudaStream_t)stream>>>(
+      img_chw, H, W, Ho, Wo, rscale_h, rscale_w, mean[0], mean[1], mean[2], std_[0], std_[1], std_[2],
+      d, dst_fmt, rows, cols);
+  GHND_LAUNCH_CHECK("stem_pack_resize_kernel");
   return GHND_OK;
 }
 

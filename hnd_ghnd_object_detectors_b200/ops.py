@@ -274,12 +274,49 @@ def stem_pack_weight(w, scale=None, dtype=torch.float16, out=None):
     return out
 
 
+class ScaledImage:
+    """An image that GeneralizedRCNNTransform.resize (src/models/org/rcnn.py:29-45) would resample by
+    `scale`: the source tensor plus the output geometry; the bilinear resample itself happens inside
+    the stem pack kernel (ghnd_stem_pack_image_resized).  `.shape` is the shape AFTER resizing, so
+    callers that size the batch from `img.shape` work on either kind."""
+
+    def __init__(self, src, scale):
+        import math
+        self.src = src
+        self.scale = float(scale)
+        h, w = src.shape[-2:]
+        # ATen upsample output size: floor(double(in) * scale_factor)
+        self.shape = torch.Size((src.shape[0], int(math.floor(float(h) * self.scale)),
+                                 int(math.floor(float(w) * self.scale))))
+        if self.shape[1] < 1 or self.shape[2] < 1:
+            raise ValueError("scale_factor %g collapses a %dx%d image" % (self.scale, h, w))
+
+    @property
+    def is_cuda(self):
+        return self.src.is_cuda
+
+    @property
+    def device(self):
+        return self.src.device
+
+
 def stem_pack_image(img, dst, n_index, Hp, Wp, mean, std):
-    """img [3,H,W] fp32 in [0,1] -> dst[n_index] of the packed batch [N][Hp+6][Wp+8][4]."""
-    _need_cuda(img, dst)
-    img = img.float().contiguous()
+    """img [3,H,W] fp32 in [0,1] (or a ScaledImage) -> dst[n_index] of the packed batch
+    [N][Hp+6][Wp+8][4]."""
     m = (c_float * 3)(*[float(v) for v in mean])
     s = (c_float * 3)(*[float(v) for v in std])
+    if isinstance(img, ScaledImage):
+        src = img.src
+        _need_cuda(src, dst)
+        src = src.float().contiguous()
+        rs = 1.0 / img.scale  # ATen: static_cast<float>(1.0 / scale_factor), same for both axes
+        call("ghnd_stem_pack_image_resized", ptr(src), src.shape[1], src.shape[2], img.shape[1],
+             img.shape[2], c_float(rs), c_float(rs), m, s, ptr(dst), fmt_of(dst.dtype), n_index, Hp, Wp,
+             stream_ptr())
+        _count()
+        return
+    _need_cuda(img, dst)
+    img = img.float().contiguous()
     call("ghnd_stem_pack_image", ptr(img), img.shape[1], img.shape[2], m, s, ptr(dst), fmt_of(dst.dtype),
          n_index, Hp, Wp, stream_ptr())
     _count()

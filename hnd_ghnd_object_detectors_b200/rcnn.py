@@ -51,9 +51,10 @@ class CustomRCNN(nn.Module):
 
     # ---- CUDA feature path ----------------------------------------------------------------
     def _scaled_images(self, images, fixed_sizes=None):
-        """normalize happens inside the stem pack kernel; resize follows CustomRCNNTransform.resize
-        (rcnn.py:29-45): identity when the image is already at network scale, otherwise a bilinear
-        resample (torch interpolate; fusing it into the pack kernel is SURVEY 8(f)1)."""
+        """normalize, resize and zero-pad all happen inside the stem pack kernel; this only decides
+        each image's scale factor like CustomRCNNTransform.resize (rcnn.py:29-45): identity when the
+        image is already at network scale, otherwise an ops.ScaledImage (source + output geometry)
+        that ghnd_stem_pack_image_resized resamples bilinearly while packing."""
         import random
         out = []
         tr = self.transform
@@ -73,8 +74,7 @@ class CustomRCNN(nn.Module):
             if mx * scale > tr.max_size:
                 scale = tr.max_size / mx
             if scale != 1.0:
-                img = torch.nn.functional.interpolate(img[None], scale_factor=scale, mode='bilinear',
-                                                      align_corners=False)[0]
+                img = ops.ScaledImage(img, scale)  # resampled inside the stem pack kernel
             out.append(img)
         return out
 

@@ -67,7 +67,10 @@ class DistillationBox(nn.Module):
                              "which are outside the B200 hot path")
         student = self._unwrap(student_model)
         self.require_adjustment = isinstance(student, KeypointRCNN)
+        teacher_min = self._unwrap(teacher_model).transform.min_size
+        teacher_min = teacher_min if isinstance(teacher_min, (list, tuple)) else (teacher_min,)
         self.use_cuda_graph = use_cuda_graph
+        self.max_resident_plans = len(teacher_min) if self.require_adjustment else 1
         self.flat = None
         self._plans = {}
         self.last_terms = None
@@ -89,7 +92,14 @@ class DistillationBox(nn.Module):
                             image_mean=student.transform.image_mean, image_std=student.transform.image_std)
             if self.use_cuda_graph:
                 plan.capture()
-            self._plans = {key: plan}  # one resident shape at a time (activations are large)
+            # Resident shapes: one for fixed-size training; the Keypoint multi-scale path draws the
+            # padded shape from six (min_size choices x fixed aspect), so keep those plans (and their
+            # CUDA graphs) alive -- a few GB each out of 180 GB -- instead of rebuilding per step.
+            while len(self._plans) >= self.max_resident_plans:
+                self._plans.pop(next(iter(self._plans)))
+            self._plans[key] = plan
+        else:
+            self._plans[key] = self._plans.pop(key)  # most recently used last
         return plan
 
     def forward(self, images, targets):

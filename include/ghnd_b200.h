@@ -103,6 +103,15 @@ int ghnd_nhwc16_to_nchw_f32(const void* src, int src_fmt, float* dst, int N, int
 int ghnd_stem_pack_image(const float* img_chw, int H, int W, const float* mean, const float* std_,
                          void* dst, int dst_fmt, int n_index, int Hp, int Wp, void* stream);
 
+/* The same with GeneralizedRCNNTransform.resize fused in (src/models/org/rcnn.py:29-45: normalize ->
+ * interpolate(scale_factor, bilinear, align_corners=False) -> batch_images zero pad): the H x W
+ * source is resampled to Ho x Wo (= floor(H*scale), floor(W*scale)) while packing.  rscale_* is the
+ * source step per output pixel, (float)(1.0/scale_factor) as ATen derives it when scale_factor is
+ * given; tap indices/weights follow ATen's upsample_bilinear2d.  One image per call. */
+int ghnd_stem_pack_image_resized(const float* img_chw, int H, int W, int Ho, int Wo, float rscale_h,
+                                 float rscale_w, const float* mean, const float* std_, void* dst,
+                                 int dst_fmt, int n_index, int Hp, int Wp, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Wide convolutions: implicit GEMM on tcgen05 tensor cores (TMA-fed, TMEM accumulators).
  * Replaces nn.Conv2d (+FrozenBatchNorm2d +ReLU +residual) forward and its autograd dgrad:

@@ -63,14 +63,57 @@ IMAGE_MEAN = (0.485, 0.456, 0.406)
 IMAGE_STD = (0.229, 0.224, 0.225)
 
 
-def transform_batch(images, size_divisible=32):
-    """normalize + zero-pad to a common size rounded up to 32 (torchvision
-    GeneralizedRCNNTransform.normalize / batch_images); resize must be the identity for these
-    inputs (true when min side == 800 / max side == 1333, or for the small test images when the
-    caller passes already-sized images; see tests)."""
+def resize_scale(h, w, size, max_size):
+    """Scale factor of CustomRCNNTransform.resize (src/models/org/rcnn.py:29-42): min side -> `size`
+    unless that pushes the max side over `max_size`."""
+    mn, mx = float(min(h, w)), float(max(h, w))
+    scale = size / mn
+    if mx * scale > max_size:
+        scale = max_size / mx
+    return scale
+
+
+def bilinear_resize_np(img, scale):
+    """interpolate(img[None], scale_factor=scale, mode='bilinear', align_corners=False)[0]
+    (rcnn.py:43-44) restated in numpy fp32 after ATen's upsample_bilinear2d: output size
+    floor(double(in)*scale); source index rscale*(dst+0.5)-0.5 clamped at 0 with rscale =
+    float(1/scale) (the scale factor is passed through, not recomputed from the sizes); second tap =
+    first + (first < in-1); value = h0*(w0*a + w1*b) + h1*(w0*c + w1*d)."""
+    import math
+    x = np.asarray(img, dtype=np.float32)
+    _, h, w = x.shape
+    ho, wo = int(math.floor(float(h) * scale)), int(math.floor(float(w) * scale))
+    rs = np.float32(1.0 / scale)
+
+    def taps(n_out, n_in):
+        src = rs * (np.arange(n_out, dtype=np.float32) + np.float32(0.5)) - np.float32(0.5)
+        src = np.maximum(src, np.float32(0)).astype(np.float32)
+        i0 = np.minimum(src.astype(np.int64), n_in - 1)
+        i1 = i0 + (i0 < n_in - 1)
+        l1 = (src - i0.astype(np.float32)).astype(np.float32)
+        return i0, i1, (np.float32(1) - l1).astype(np.float32), l1
+
+    h0, h1, hl0, hl1 = taps(ho, h)
+    w0, w1, wl0, wl1 = taps(wo, w)
+    top = wl0[None, None, :] * x[:, h0][:, :, w0] + wl1[None, None, :] * x[:, h0][:, :, w1]
+    bot = wl0[None, None, :] * x[:, h1][:, :, w0] + wl1[None, None, :] * x[:, h1][:, :, w1]
+    return (hl0[None, :, None] * top + hl1[None, :, None] * bot).astype(np.float32)
+
+
+def transform_batch(images, size_divisible=32, sizes=None, max_size=1333):
+    """normalize -> resize -> zero-pad to a common size rounded up to 32 (rcnn.py:65-82;
+    torchvision GeneralizedRCNNTransform.normalize / batch_images).  `sizes` = per-image target min
+    side (fixed_sizes of DistillationBox, tool.py:44-49, or min_size[-1] in eval); None = the images
+    are already at network scale (resize is the identity: interpolate with scale_factor 1)."""
     mean = torch.tensor(IMAGE_MEAN, dtype=torch.float32)[:, None, None]
     std = torch.tensor(IMAGE_STD, dtype=torch.float32)[:, None, None]
     imgs = [(im - mean) / std for im in images]
+    if sizes is not None:
+        scaled = []
+        for im, size in zip(imgs, sizes):
+            sc = resize_scale(im.shape[1], im.shape[2], size, max_size)
+            scaled.append(im if sc == 1.0 else torch.from_numpy(bilinear_resize_np(im.numpy(), sc)))
+        imgs = scaled
     hmax = max(im.shape[1] for im in imgs)
     wmax = max(im.shape[2] for im in imgs)
     hp = (hmax + size_divisible - 1) // size_divisible * size_divisible
@@ -214,11 +257,13 @@ def trainable_names(student_sd, prefix="backbone.body."):
     return names
 
 
-def distill_step(teacher_sd, student_sd, images, levels=("layer1", "layer2", "layer3", "layer4")):
+def distill_step(teacher_sd, student_sd, images, levels=("layer1", "layer2", "layer3", "layer4"),
+                 sizes=None, max_size=1333):
     """One DistillationBox.forward + backward (tool.py:40-61, mimic_runner.py:51-53).
     Returns loss, per-level terms, teacher/student features, grads of the trainable tensors and the
-    updated BN running stats."""
-    x = transform_batch(images)
+    updated BN running stats.  `sizes` = the per-image fixed_sizes of the Keypoint path
+    (tool.py:44-49); both models see the same resized batch."""
+    x = transform_batch(images, sizes=sizes, max_size=max_size)
     with torch.no_grad():
         t_feats = backbone_features(x, teacher_sd, student=False)
     names = trainable_names(student_sd)

@@ -71,6 +71,14 @@ def model_config(kind, bch=3, min_size=96, max_size=128):
     return cfg
 
 
+def keypoint_config(kind, min_size=(64, 96, 128), max_size=192):
+    cfg = model_config(kind, min_size=min_size, max_size=max_size)
+    cfg["name"] = "keypoint_rcnn"
+    cfg["params"]["num_classes"] = 2
+    cfg["params"]["num_keypoints"] = 17
+    return cfg
+
+
 def criterion_config(levels=LEVELS):
     terms = {lv: {"ts_modules": ["backbone.body." + lv, "backbone.body." + lv],
                   "criterion": {"type": "MSELoss", "params": {"reduction": "sum"}}, "factor": 1.0}
@@ -305,3 +313,78 @@ def test_layer1_module_eval_and_train(env):
     assert rel(xg.grad, grads[0]) <= 0.15
     got = dict(layer.named_parameters())
     check_grads({n: got[n[len("backbone.body.layer1."):]].grad for n in names}, dict(zip(names, grads[1:])))
+
+
+def test_keypoint_multi_scale_step(env):
+    """BASELINE config 4: Keypoint R-CNN draws a per-image `fixed_sizes` (tool.py:44-49) so the batch
+    goes through a real bilinear resize -- fused into the stem pack kernel here.  Same gates as the
+    fixed-size step (features <= 1e-2, loss <= 1e-3) against the oracle run on the same sizes; the
+    plan cache keeps one plan per padded shape."""
+    import random
+    from hnd_ghnd_object_detectors_b200.tool import DistillationBox
+    from hnd_ghnd_object_detectors_b200 import ops
+    models, mu = env["models"], env["module_util"]
+    dev = torch.device("cuda")
+    teacher = models.get_model(keypoint_config("teacher"), dev)
+    student = models.get_model(keypoint_config("student"), dev)
+    teacher.load_state_dict({k: v for k, v in env["t_sd"].items() if k.startswith("backbone.body.")}, strict=False)
+    student.load_state_dict({k: v for k, v in env["s_sd"].items() if k.startswith("backbone.body.")}, strict=False)
+    mu.freeze_module_params(teacher)
+    for path in keypoint_config("student")["frozen_modules"]:
+        mu.freeze_module_params(mu.get_module(student, path))
+    assert len(mu.get_updatable_param_names(student)) == 25
+    teacher.eval()
+    student.train()
+    teacher.distill_backbone_only = student.distill_backbone_only = True
+    box = DistillationBox(teacher, student, criterion_config())
+    assert box.require_adjustment and box.max_resident_plans == 3
+    g = torch.Generator().manual_seed(77)
+    host = [torch.rand(3, 90, 120, generator=g), torch.rand(3, 96, 100, generator=g)]
+    images = [im.cuda() for im in host]
+    shapes = set()
+    for seed in (2, 5, 9, 4, 2):  # padded shapes 64x96, 128x192, 128x160, 96x128, 64x96 again
+        random.seed(seed)
+        sizes = [random.choice(teacher.transform.min_size) for _ in images]
+        random.seed(seed)
+        student.zero_grad()
+        loss = box(images, targets_for(images))
+        loss.backward()
+        ref = O.distill_step(env["t_sd"], env["s_sd"], host, sizes=sizes, max_size=192)
+        assert abs(loss.item() - float(ref["loss"])) <= 1e-3 * float(ref["loss"]), (sizes, loss.item(), float(ref["loss"]))
+        plan = list(box._plans.values())[-1]
+        shapes.add((plan.Hp, plan.Wp))
+        for lv in LEVELS:
+            assert tuple(plan.feat_t[lv].shape[1:3]) == tuple(ref["teacher"][lv].shape[2:]), (lv, sizes)
+            assert rel(ops.to_nchw_f32(plan.feat_t[lv]), ref["teacher"][lv]) <= 1e-2, (lv, sizes)
+            assert rel(ops.to_nchw_f32(plan.feat_s[lv]), ref["student"][lv]) <= 1e-2, (lv, sizes)
+        got = {n: p.grad.detach().cpu() for n, p in student.named_parameters() if p.requires_grad}
+        check_grads(got, ref["grads"])
+    assert len(shapes) == 4 and len(box._plans) == 3  # LRU: the oldest shape was evicted
+
+
+def test_mask_rcnn_uses_the_same_hot_path(env):
+    """BASELINE config 3: Mask R-CNN differs from Faster R-CNN only in roi_heads, which
+    distill_backbone_only never executes -- same loss bits for the same backbone weights."""
+    from hnd_ghnd_object_detectors_b200.tool import DistillationBox
+    models, mu = env["models"], env["module_util"]
+    dev = torch.device("cuda")
+    losses = []
+    for name in ("faster_rcnn", "mask_rcnn"):
+        pair = []
+        for kind, sd in (("teacher", env["t_sd"]), ("student", env["s_sd"])):
+            cfg = model_config(kind)
+            cfg["name"] = name
+            m = models.get_model(cfg, dev)
+            m.load_state_dict({k: v for k, v in sd.items() if k.startswith("backbone.body.")}, strict=False)
+            pair.append(m)
+        teacher, student = pair
+        mu.freeze_module_params(teacher)
+        for path in model_config("student")["frozen_modules"]:
+            mu.freeze_module_params(mu.get_module(student, path))
+        teacher.eval()
+        student.train()
+        teacher.distill_backbone_only = student.distill_backbone_only = True
+        box = DistillationBox(teacher, student, criterion_config())
+        images = [im.cuda() for im in small_images()]
+        losses.append(box(images, targets_for(images)).item())
+    assert losses[0] == losses[1], losses

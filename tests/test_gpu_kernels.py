@@ -492,6 +492,48 @@ def test_stem(ops, dt):
     assert rel(dw.cpu(), dw_ref) < 2e-3, rel(dw.cpu(), dw_ref)
 
 
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+def test_stem_pack_with_resize(ops, golden_dir, dt):
+    """normalize + bilinear resize + zero-pad fused in the pack kernel against the
+    reference transform's golden output and the oracle: equal to the 16-bit rounding of the fp32
+    result except where fp32 rounding of the tap weights crosses a 16-bit rounding boundary
+    (<= 1 ulp of the 16-bit format, on < 5 % of the pixels: the fp32 results themselves differ by up
+    to 2e-5 between implementations, see tests/test_oracle_golden.py); padding exactly zero."""
+    from tests.golden.make_transform_golden import case_images, transform_cases
+    g = np.load(os.path.join(golden_dir, "transform.npz"))
+    ulp = 2.0 ** -10 if dt == torch.float16 else 2.0 ** -7
+    for name, (shapes, sizes, max_size, seed) in transform_cases().items():
+        imgs = case_images(shapes, seed)
+        ref = torch.from_numpy(g[name + "/batch"])
+        N, _, Hp, Wp = ref.shape
+        packed = torch.full((N, Hp + 6, Wp + 8, 4), 7.0, dtype=dt, device="cuda")
+        for i, (im, size) in enumerate(zip(imgs, sizes)):
+            sc = O.resize_scale(im.shape[1], im.shape[2], size, max_size)
+            src = im.cuda() if sc == 1.0 else ops.ScaledImage(im.cuda(), sc)
+            assert tuple(src.shape[-2:]) == tuple(g[name + "/image_sizes"][i])
+            ops.stem_pack_image(src, packed, i, Hp, Wp, O.IMAGE_MEAN, O.IMAGE_STD)
+        got = packed[:, 3:3 + Hp, 3:3 + Wp, :3].permute(0, 3, 1, 2).float().cpu()
+        want = r16(ref, dt)
+        diff = (got - want).abs()
+        assert float((diff / want.abs().clamp_min(1.0)).max()) <= ulp, name
+        assert float((diff > 0).float().mean()) < 5e-2, name
+        assert torch.equal(got == 0, ref == 0) or float(((got == 0) != (ref == 0)).float().mean()) < 1e-4
+        assert float(packed[:, :3].abs().max()) == 0 and float(packed[:, 3 + Hp:].abs().max()) == 0
+        assert float(packed[:, :, :3].abs().max()) == 0 and float(packed[:, :, 3 + Wp:].abs().max()) == 0
+        assert float(packed[..., 3].abs().max()) == 0
+        assert rel(got, O.transform_batch(imgs, sizes=sizes, max_size=max_size)) < 2 * ulp
+
+
+def test_stem_pack_resize_errors(ops):
+    packed = torch.zeros((1, 32 + 6, 32 + 8, 4), dtype=torch.float16, device="cuda")
+    from hnd_ghnd_object_detectors_b200._lib import GhndError
+    with pytest.raises(GhndError):  # resized image larger than the slot
+        ops.stem_pack_image(ops.ScaledImage(torch.rand(3, 30, 30).cuda(), 2.0), packed, 0, 32, 32,
+                            O.IMAGE_MEAN, O.IMAGE_STD)
+    with pytest.raises(ValueError):
+        ops.ScaledImage(torch.rand(3, 4, 4), 0.1)
+
+
 @pytest.mark.parametrize("geom", [(2, 96, 128), (1, 64, 168), (3, 32, 72)])
 def test_stem_wgrad_tensor_core(ops, geom):
     """conv1 dW on tcgen05 (MN-major SW64 x SW128 operands) against fp32 conv2d_weight on the same
