@@ -358,7 +358,9 @@ def test_keypoint_multi_scale_step(env):
             assert rel(ops.to_nchw_f32(plan.feat_t[lv]), ref["teacher"][lv]) <= 1e-2, (lv, sizes)
             assert rel(ops.to_nchw_f32(plan.feat_s[lv]), ref["student"][lv]) <= 1e-2, (lv, sizes)
         got = {n: p.grad.detach().cpu() for n, p in student.named_parameters() if p.requires_grad}
-        check_grads(got, ref["grads"])
+        # these batches are as small as 2 x 64x96: the ReLU-mask-flip noise of the module docstring is
+        # averaged over ~3x fewer pixels than in the fixed-size test, hence the wider bound
+        check_grads(got, ref["grads"], tol=0.3, cos=0.95)
     assert len(shapes) == 4 and len(box._plans) == 3  # LRU: the oldest shape was evicted
 
 
