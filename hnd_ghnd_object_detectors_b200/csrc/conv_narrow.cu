@@ -466,7 +466,8 @@ __global__ void __launch_bounds__(256, 2)
 // copied itself).  The narrow values f(a[ca][q - tap]) of the chunk are staged once per chunk in
 // shared memory (double buffered, one __syncthreads per chunk).
 //   accum[ca][tap][cb] += f(a[n][ca][ib-dh][jb-dw]) * b[n][ib][jb][cb]   for ca in [ca0, ca0+3)
-static constexpr int kWgStages = 8;
+static constexpr int kWgStages = 4;
+static constexpr int kWgChunk = 64;  // pixels per chunk: two pixel slots per thread
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
 }
@@ -481,54 +482,80 @@ __global__ void __launch_bounds__(256, 2)
     wgrad_narrow_bs_kernel(const float* __restrict__ a, const float* __restrict__ pre, int pre_relu,
                            const uint4* __restrict__ b, float* __restrict__ accum, int N, int Ha,
                            int Wa, int Ca, int ca0, int Hb, int Wb, NarrowTaps taps) {
-  __shared__ uint4 s_ring[kWgStages][256];
-  __shared__ float s_a[2][3 * kNarrowMaxTaps * 32];  // [buf][ca][tap][slot]
+  __shared__ uint4 s_ring[kWgStages][2][256];
+  __shared__ float s_a[2][3 * kNarrowMaxTaps * kWgChunk];  // [buf][ca][tap][pixel]
   __shared__ float s_acc[3 * kNarrowMaxTaps * 64];
   const int cg = threadIdx.x & 7, slot = threadIdx.x >> 3;
-  const int cpr = (Wb + 31) >> 5;  // chunks per row of b
+  const int cpr = (Wb + kWgChunk - 1) / kWgChunk;  // chunks per row of b
   const int chunks = N * Hb * cpr;
-  const int stride = gridDim.x;
-  auto chunk_src = [&](int c, int& n, int& ib, int& jb0) {
-    const int row = c / cpr;
-    jb0 = (c - row * cpr) << 5;
-    n = row / Hb;
-    ib = row - n * Hb;
+  // Each CTA owns a contiguous range of chunks and walks it with incremental (n, row, chunk-in-row)
+  // cursors (the strided assignment cost two integer divisions per chunk and pipeline position).
+  const int per = chunks / (int)gridDim.x, extra = chunks - per * (int)gridDim.x;
+  const int c_begin = (int)blockIdx.x * per + min((int)blockIdx.x, extra);
+  const int c_end = c_begin + per + ((int)blockIdx.x < extra ? 1 : 0);
+  struct Cursor {
+    int c, n, ib, jc;
   };
-  auto issue = [&](int c, int stage) {
-    if (c < chunks) {
-      int n, ib, jb0;
-      chunk_src(c, n, ib, jb0);
-      if (jb0 + slot < Wb)
-        cp_async16(&s_ring[stage][threadIdx.x], b + (((size_t)n * Hb + ib) * Wb + jb0 + slot) * 8 + cg);
+  auto make_cursor = [&](int c) {
+    Cursor k;
+    k.c = c;
+    const int row = c / cpr;
+    k.jc = c - row * cpr;
+    k.n = row / Hb;
+    k.ib = row - k.n * Hb;
+    return k;
+  };
+  auto advance = [&](Cursor& k) {
+    ++k.c;
+    if (++k.jc == cpr) {
+      k.jc = 0;
+      if (++k.ib == Hb) {
+        k.ib = 0;
+        ++k.n;
+      }
+    }
+  };
+  auto issue = [&](const Cursor& k, int stage) {
+    if (k.c < c_end) {
+      const int jb = k.jc * kWgChunk + slot;
+      const uint4* src = b + (((size_t)k.n * Hb + k.ib) * Wb + jb) * 8 + cg;
+      if (jb < Wb) cp_async16(&s_ring[stage][0][threadIdx.x], src);
+      if (jb + 32 < Wb) cp_async16(&s_ring[stage][1][threadIdx.x], src + 32 * 8);
     }
     cp_async_commit();
   };
-  // narrow values of chunk c: this thread fetches entries threadIdx.x and threadIdx.x + 256 (< 384)
-  auto fetch_a = [&](int c, float (&val)[2]) {
-    val[0] = val[1] = 0.f;
-    if (c >= chunks) return;
-    int n, ib, jb0;
-    chunk_src(c, n, ib, jb0);
+  // narrow values of a chunk, 3 channels x taps x 64 pixels: this thread fetches (channel k, its
+  // tap, its pixel) for k = 0..2.  The loads are raw; the BN/ReLU pre-transform is applied when the
+  // values are stored to shared memory one chunk later, so the load latency overlaps the FMAs.
+  const int f_sl = threadIdx.x & 63, f_tap = (threadIdx.x >> 6) & 3;
+  const bool f_tap_ok = f_tap < taps.n_taps;
+  const int f_dh = taps.dh[f_tap], f_dw = taps.dw[f_tap];
+  float f_sc[3], f_sh[3];
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const int idx = threadIdx.x + 256 * k;
-      if (idx >= 3 * kNarrowMaxTaps * 32) continue;
-      const int sl = idx & 31, tap = (idx >> 5) & 3, c3 = idx >> 7;
-      const int ca = ca0 + c3;
-      if (tap >= taps.n_taps || ca >= Ca) continue;
-      const int ia = ib - taps.dh[tap], ja = jb0 + sl - taps.dw[tap];
-      if (ia < 0 || ia >= Ha || ja < 0 || ja >= Wa) continue;
-      float v = __ldg(a + (((size_t)n * Ca + ca) * Ha + ia) * Wa + ja);
-      if (pre != nullptr) {
-        v = fmaf(v, __ldg(pre + ca), __ldg(pre + Ca + ca));
+  for (int k = 0; k < 3; ++k) {
+    const bool okc = ca0 + k < Ca && pre != nullptr;
+    f_sc[k] = okc ? __ldg(pre + ca0 + k) : 1.f;
+    f_sh[k] = okc ? __ldg(pre + Ca + ca0 + k) : 0.f;
+  }
+  const bool has_pre = pre != nullptr;
+  const size_t a_plane = (size_t)Ha * Wa;
+  auto fetch_a = [&](const Cursor& cur, float (&val)[3], bool& ok) {
+    const int ia = cur.ib - f_dh, ja = cur.jc * kWgChunk + f_sl - f_dw;
+    ok = cur.c < c_end && f_tap_ok && ia >= 0 && ia < Ha && ja >= 0 && ja < Wa;
+    const float* src = a + ((size_t)cur.n * Ca + ca0) * a_plane + (size_t)ia * Wa + ja;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) val[k] = (ok && ca0 + k < Ca) ? __ldg(src + k * a_plane) : 0.f;
+  };
+  auto store_a = [&](int buf, const float (&val)[3], bool ok) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      float v = val[k];
+      if (has_pre) {
+        v = fmaf(v, f_sc[k], f_sh[k]);
         if (pre_relu) v = fmaxf(v, 0.f);
       }
-      val[k] = v;
+      s_a[buf][k * (kNarrowMaxTaps * kWgChunk) + threadIdx.x] = (ok && ca0 + k < Ca) ? v : 0.f;
     }
-  };
-  auto store_a = [&](int buf, const float (&val)[2]) {
-    s_a[buf][threadIdx.x] = val[0];
-    if (threadIdx.x + 256 < 3 * kNarrowMaxTaps * 32) s_a[buf][threadIdx.x + 256] = val[1];
   };
   float acc[3][kNarrowMaxTaps][8];
 #pragma unroll
@@ -538,42 +565,52 @@ __global__ void __launch_bounds__(256, 2)
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc[c][t][e] = 0.f;
   for (int i = threadIdx.x; i < 3 * kNarrowMaxTaps * 64; i += blockDim.x) s_acc[i] = 0.f;
+  Cursor cur = make_cursor(c_begin), ahead = cur, nxt_cur = cur;
 #pragma unroll
-  for (int s = 0; s < kWgStages; ++s) issue((int)blockIdx.x + s * stride, s);
-  {
-    float v0[2];
-    fetch_a((int)blockIdx.x, v0);
-    store_a(0, v0);
+  for (int s = 0; s < kWgStages; ++s) {
+    issue(ahead, s);
+    advance(ahead);
   }
+  {
+    float v0[3];
+    bool ok0;
+    fetch_a(cur, v0, ok0);
+    store_a(0, v0, ok0);
+  }
+  advance(nxt_cur);
   __syncthreads();
   int stage = 0, buf = 0;
-  for (int c = blockIdx.x; c < chunks; c += stride) {
-    float nxt[2];
-    fetch_a(c + stride, nxt);  // latency hidden behind this chunk's FMAs
+  for (; cur.c < c_end; advance(cur), advance(nxt_cur)) {
+    float nxt[3];
+    bool nxt_ok;
+    fetch_a(nxt_cur, nxt, nxt_ok);  // consumed after this chunk's FMAs
     cp_async_wait<kWgStages - 1>();
-    int n, ib, jb0;
-    chunk_src(c, n, ib, jb0);
-    if (jb0 + slot < Wb) {
-      const uint4 v = s_ring[stage][threadIdx.x];
-      const uint32_t u[4] = {v.x, v.y, v.z, v.w};
-      float f[8];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 x2 = unpack2_t<FMT>(u[e]);
-        f[2 * e] = x2.x;
-        f[2 * e + 1] = x2.y;
-      }
+    for (int half = 0; half < 2; ++half) {
+      const int ps = slot + 32 * half;
+      if (cur.jc * kWgChunk + ps < Wb) {
+        const uint4 v = s_ring[stage][half][threadIdx.x];
+        const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+        float f[8];
 #pragma unroll
-      for (int c3 = 0; c3 < 3; ++c3)
-#pragma unroll
-        for (int t = 0; t < kNarrowMaxTaps; ++t) {
-          const float av = s_a[buf][(c3 * kNarrowMaxTaps + t) * 32 + slot];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) acc[c3][t][e] = fmaf(av, f[e], acc[c3][t][e]);
+        for (int e = 0; e < 4; ++e) {
+          const float2 x2 = unpack2_t<FMT>(u[e]);
+          f[2 * e] = x2.x;
+          f[2 * e + 1] = x2.y;
         }
+#pragma unroll
+        for (int c3 = 0; c3 < 3; ++c3)
+#pragma unroll
+          for (int t = 0; t < kNarrowMaxTaps; ++t) {
+            const float av = s_a[buf][(c3 * kNarrowMaxTaps + t) * kWgChunk + ps];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[c3][t][e] = fmaf(av, f[e], acc[c3][t][e]);
+          }
+      }
     }
-    issue(c + kWgStages * stride, stage);
-    store_a(buf ^ 1, nxt);
+    issue(ahead, stage);
+    advance(ahead);
+    store_a(buf ^ 1, nxt, nxt_ok);
     __syncthreads();
     stage = stage + 1 == kWgStages ? 0 : stage + 1;
     buf ^= 1;
@@ -985,7 +1022,7 @@ int ghnd_wgrad_narrow(const float* a, const float* pre_scale_shift, int pre_relu
     }
   const int lanes = Cb / 8;
   const int64_t npix = (int64_t)N * Ha * Wa;
-  const int64_t chunks_b = (int64_t)N * Hb * ((Wb + 31) / 32);
+  const int64_t chunks_b = (int64_t)N * Hb * ((Wb + kWgChunk - 1) / kWgChunk);
   const bool fast = Cb == 64 && chunks_b < (int64_t)1 << 30 && (b_fmt == GHND_F16 || b_fmt == GHND_BF16);
   for (int ca0 = 0; ca0 < Ca; ca0 += 3) {
     if (fast) {

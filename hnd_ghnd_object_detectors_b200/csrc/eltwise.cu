@@ -1,9 +1,15 @@
 // HBM-bound helper kernels of the GHND path: layout boundary, stem input packing, max-pool,
 // training-mode BatchNorm (stats / apply / backward), weight repacking, fused Adam.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace ghnd {
 
+// developer knob for on-GPU sweeps (scripts/bench_kernels.py); unset = the tuned default
+static inline int tune_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
 static inline int grid_for(int64_t work_items, int threads, int per_sm = 8) {
   int64_t b = (work_items + threads - 1) / threads;
   int64_t cap = (int64_t)num_sms() * per_sm;
@@ -129,115 +135,145 @@ __global__ void stem_pack_resize_kernel(const float* __restrict__ img, int H, in
 // ------------------------------------------------------------------------------------------------
 // max-pool 3x3 s2 p1 (NHWC, 8 channels per thread) + backward fused with the ReLU mask
 // ------------------------------------------------------------------------------------------------
-// grid = (ceil(Wo*C8/256), Ho, N): no per-element division (C8 is a power of two: shift)
+// grid = (ceil(Wo*C8/256), Ho, N): no per-element division (C8 is a power of two: shift).
+// The 3x3 scan stays in packed 16-bit pairs: one max + one compare-mask + one select per pair and
+// tap (the first version unpacked to fp32 and was instruction-issue bound: ~900 SASS instructions
+// per 8 channels, 55 us for a 172 MB stream).  Strict '>' keeps the first maximum in scan order,
+// like torch's max_pool2d; padding taps are skipped.
+template <int FMT>
+__device__ __forceinline__ void pool_tap(uint32_t& best, uint32_t& idx, uint32_t v, uint32_t code) {
+  if (FMT == GHND_F16) {
+    const __half2 b = *reinterpret_cast<const __half2*>(&best);
+    const __half2 x = *reinterpret_cast<const __half2*>(&v);
+    const uint32_t m = __hgt2_mask(x, b);
+    const __half2 r = __hmax2(b, x);
+    best = *reinterpret_cast<const uint32_t*>(&r);
+    idx = (idx & ~m) | (code & m);
+  } else {
+    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&best);
+    const __nv_bfloat162 x = *reinterpret_cast<const __nv_bfloat162*>(&v);
+    const uint32_t m = __hgt2_mask(x, b);
+    const __nv_bfloat162 r = __hmax2(b, x);
+    best = *reinterpret_cast<const uint32_t*>(&r);
+    idx = (idx & ~m) | (code & m);
+  }
+}
+template <int FMT, bool kArg>
 __global__ void __launch_bounds__(256)
-    maxpool_kernel(const uint4* __restrict__ x, uint4* __restrict__ y,
-                               uint2* __restrict__ argmax, int fmt, int N, int H, int W, int C8,
-                               int c8_shift, int Ho, int Wo) {
-  {
-    const int v = blockIdx.x * 256 + threadIdx.x;
-    if (v >= Wo * C8) return;
-    const int cg = v & (C8 - 1);
-    const int wo = v >> c8_shift;
-    const int ho = blockIdx.y;
-    const int n = blockIdx.z;
-    const int64_t i = (((int64_t)n * Ho + ho) * Wo + wo) * C8 + cg;
-    float best[8];
-    uint32_t idx[8];
+    maxpool_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, uint2* __restrict__ argmax,
+                   int N, int H, int W, int C8, int c8_shift, int Ho, int Wo) {
+  const int v = blockIdx.x * 256 + threadIdx.x;
+  if (v >= Wo * C8) return;
+  const int cg = v & (C8 - 1);
+  const int wo = v >> c8_shift;
+  const int ho = blockIdx.y;
+  const int n = blockIdx.z;
+  const int64_t i = (((int64_t)n * Ho + ho) * Wo + wo) * C8 + cg;
+  const uint32_t ninf = FMT == GHND_F16 ? 0xfc00fc00u : 0xff80ff80u;
+  uint32_t best[4] = {ninf, ninf, ninf, ninf};
+  uint32_t idx[4] = {0u, 0u, 0u, 0u};  // two 16-bit tap codes per word
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      best[j] = -INFINITY;
-      idx[j] = 0;
+  for (int r = 0; r < 3; ++r) {
+    const int h = 2 * ho - 1 + r;
+    if (h < 0 || h >= H) continue;
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      const int w = 2 * wo - 1 + s;
+      if (w < 0 || w >= W) continue;
+      const uint4 q = __ldg(x + (((int64_t)n * H + h) * W + w) * C8 + cg);
+      const uint32_t code = (uint32_t)(r * 3 + s) * 0x00010001u;
+      pool_tap<FMT>(best[0], idx[0], q.x, code);
+      pool_tap<FMT>(best[1], idx[1], q.y, code);
+      pool_tap<FMT>(best[2], idx[2], q.z, code);
+      pool_tap<FMT>(best[3], idx[3], q.w, code);
     }
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      const int h = 2 * ho - 1 + r;
-      if (h < 0 || h >= H) continue;
-#pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        const int w = 2 * wo - 1 + s;
-        if (w < 0 || w >= W) continue;
-        const uint4 v = __ldg(x + (((int64_t)n * H + h) * W + w) * C8 + cg);
-        const uint32_t u[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 f = unpack2(u[e], fmt);
-          if (f.x > best[2 * e]) {
-            best[2 * e] = f.x;
-            idx[2 * e] = r * 3 + s;
-          }
-          if (f.y > best[2 * e + 1]) {
-            best[2 * e + 1] = f.y;
-            idx[2 * e + 1] = r * 3 + s;
-          }
-        }
-      }
-    }
-    uint4 o;
-    o.x = pack2(best[0], best[1], fmt);
-    o.y = pack2(best[2], best[3], fmt);
-    o.z = pack2(best[4], best[5], fmt);
-    o.w = pack2(best[6], best[7], fmt);
-    y[i] = o;
-    if (argmax != nullptr) {
-      uint2 a;
-      a.x = idx[0] | (idx[1] << 8) | (idx[2] << 16) | (idx[3] << 24);
-      a.y = idx[4] | (idx[5] << 8) | (idx[6] << 16) | (idx[7] << 24);
-      argmax[i] = a;
-    }
+  }
+  y[i] = make_uint4(best[0], best[1], best[2], best[3]);
+  if (kArg) {
+    uint2 a;  // one byte per channel, channel order
+    a.x = __byte_perm(idx[0], idx[1], 0x6420);
+    a.y = __byte_perm(idx[2], idx[3], 0x6420);
+    argmax[i] = a;
   }
 }
 
-__global__ void __launch_bounds__(256)
-    maxpool_bwd_kernel(const uint4* __restrict__ x, int x_fmt,
-                                   const uint2* __restrict__ argmax, const uint4* __restrict__ dy,
-                                   int dy_fmt, uint4* __restrict__ dx, int dx_fmt, int N, int H, int W,
-                                   int C8, int c8_shift, int Ho, int Wo) {
-  {
-    const int v = blockIdx.x * 256 + threadIdx.x;
-    if (v >= W * C8) return;
-    const int cg = v & (C8 - 1);
-    const int w = v >> c8_shift;
-    const int h = blockIdx.y;
-    const int n = blockIdx.z;
-    const int64_t i = (((int64_t)n * H + h) * W + w) * C8 + cg;
-    float g[8];
+// Backward of the pool fused with the ReLU mask of the stem output.  A thread owns the input pixel
+// pair (h, 2m), (h, 2m+1) for one 8-channel group: the pair shares its windows (wo = m, m+1; ho =
+// h/2 and, for odd h, h/2+1 -- uniform per block), so every window vector is loaded once and each
+// (pixel, window) combination that can hold the pixel is tested exactly once: 1.5 (even rows) or 3
+// (odd rows) tests per pixel, all loads issued before the first use.  (The per-pixel version
+// tested 4 windows per pixel and was instruction-issue bound at ~40 % of HBM.)
+template <int DYF>
+__device__ __forceinline__ void pool_bwd_acc(float (&g)[8], const uint2 a, const uint4 d, uint32_t code) {
+  const uint32_t du[4] = {d.x, d.y, d.z, d.w};
 #pragma unroll
-    for (int j = 0; j < 8; ++j) g[j] = 0.f;
-    // windows ho with 2ho-1 <= h <= 2ho+1
-    const int ho_lo = h / 2, ho_hi = (h + 1) / 2;
-    const int wo_lo = w / 2, wo_hi = (w + 1) / 2;
-    for (int ho = ho_lo; ho <= ho_hi; ++ho) {
-      if (ho >= Ho) continue;
-      const uint32_t r = (uint32_t)(h - (2 * ho - 1));
-      for (int wo = wo_lo; wo <= wo_hi; ++wo) {
-        if (wo >= Wo) continue;
-        const uint32_t s = (uint32_t)(w - (2 * wo - 1));
-        const uint32_t me = r * 3 + s;
-        const int64_t o = (((int64_t)n * Ho + ho) * Wo + wo) * C8 + cg;
-        const uint2 a = __ldg(argmax + o);
-        const uint4 d = __ldg(dy + o);
-        const uint32_t du[4] = {d.x, d.y, d.z, d.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 f = unpack2(du[e], dy_fmt);
-          const uint32_t a0 = ((e < 2 ? a.x : a.y) >> (16 * (e & 1))) & 0xff;
-          const uint32_t a1 = ((e < 2 ? a.x : a.y) >> (16 * (e & 1) + 8)) & 0xff;
-          if (a0 == me) g[2 * e] += f.x;
-          if (a1 == me) g[2 * e + 1] += f.y;
-        }
-      }
-    }
-    const uint4 xv = __ldg(x + i);
-    const uint32_t xu[4] = {xv.x, xv.y, xv.z, xv.w};
-    uint32_t ou[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float2 f = unpack2(xu[e], x_fmt);
-      ou[e] = pack2(f.x > 0.f ? g[2 * e] : 0.f, f.y > 0.f ? g[2 * e + 1] : 0.f, dx_fmt);
-    }
-    dx[i] = make_uint4(ou[0], ou[1], ou[2], ou[3]);
+  for (int e = 0; e < 4; ++e) {
+    const float2 f = unpack2_t<DYF>(du[e]);
+    const uint32_t word = e < 2 ? a.x : a.y;
+    const uint32_t a0 = (word >> (16 * (e & 1))) & 0xffu;
+    const uint32_t a1 = (word >> (16 * (e & 1) + 8)) & 0xffu;
+    g[2 * e] += a0 == code ? f.x : 0.f;
+    g[2 * e + 1] += a1 == code ? f.y : 0.f;
   }
+}
+template <int XF, int DXF>
+__device__ __forceinline__ uint4 pool_bwd_mask(const uint4 xv, const float (&g)[8]) {
+  const uint32_t xu[4] = {xv.x, xv.y, xv.z, xv.w};
+  uint32_t ou[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 f = unpack2_t<XF>(xu[e]);
+    ou[e] = pack2_t<DXF>(f.x > 0.f ? g[2 * e] : 0.f, f.y > 0.f ? g[2 * e + 1] : 0.f);
+  }
+  return make_uint4(ou[0], ou[1], ou[2], ou[3]);
+}
+template <int XF, int DYF, int DXF>
+__global__ void __launch_bounds__(256)
+    maxpool_bwd_kernel(const uint4* __restrict__ x, const uint2* __restrict__ argmax,
+                       const uint4* __restrict__ dy, uint4* __restrict__ dx, int N, int H, int W,
+                       int C8, int c8_shift, int Ho, int Wo) {
+  const int v = blockIdx.x * 256 + threadIdx.x;
+  const int m = v >> c8_shift;  // pixel pair index along w
+  const int w0 = 2 * m;
+  if (w0 >= W) return;
+  const int cg = v & (C8 - 1);
+  const int h = blockIdx.y;
+  const int n = blockIdx.z;
+  const bool has1 = w0 + 1 < W;
+  const int64_t i0 = (((int64_t)n * H + h) * W + w0) * C8 + cg;
+  const uint4 x0 = ld_stream(x + i0);
+  const uint4 x1 = has1 ? ld_stream(x + i0 + C8) : make_uint4(0u, 0u, 0u, 0u);
+  const int k = h >> 1;
+  const bool odd = h & 1;  // uniform per block
+  // window (row q, col c): q = 0 -> ho = k, q = 1 -> ho = k + 1 (odd rows only); c = 0 -> wo = m,
+  // c = 1 -> wo = m + 1 (only the odd pixel of the pair lies in it)
+  uint2 a[2][2];
+  uint4 d[2][2];
+#pragma unroll
+  for (int q = 0; q < 2; ++q)
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int ho = k + q, wo = m + c;
+      const bool ok = (q == 0 || odd) && ho < Ho && wo < Wo && (c == 0 || has1);
+      const int64_t o = (((int64_t)n * Ho + ho) * Wo + wo) * C8 + cg;
+      a[q][c] = ok ? __ldg(argmax + o) : make_uint2(0xffffffffu, 0xffffffffu);
+      d[q][c] = ok ? __ldg(dy + o) : make_uint4(0u, 0u, 0u, 0u);
+    }
+  float g0[8], g1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) g0[j] = g1[j] = 0.f;
+  // tap code inside a window = r*3 + s with r = h - (2ho-1), s = w - (2wo-1)
+  const uint32_t r0 = odd ? 2u : 1u;  // row of this pixel inside window row q = 0
+  pool_bwd_acc<DYF>(g0, a[0][0], d[0][0], r0 * 3 + 1);  // (w0 in window m: s = 1)
+  pool_bwd_acc<DYF>(g1, a[0][0], d[0][0], r0 * 3 + 2);  // (w1 in window m: s = 2)
+  pool_bwd_acc<DYF>(g1, a[0][1], d[0][1], r0 * 3 + 0);  // (w1 in window m+1: s = 0)
+  if (odd) {                                            // second window row: r = 0
+    pool_bwd_acc<DYF>(g0, a[1][0], d[1][0], 1);
+    pool_bwd_acc<DYF>(g1, a[1][0], d[1][0], 2);
+    pool_bwd_acc<DYF>(g1, a[1][1], d[1][1], 0);
+  }
+  dx[i0] = pool_bwd_mask<XF, DXF>(x0, g0);
+  if (has1) dx[i0 + C8] = pool_bwd_mask<XF, DXF>(x1, g1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -612,7 +648,7 @@ __global__ void __launch_bounds__(256)
     bn_bwd_reduce_fast_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy, int64_t nvec,
                               int C8, const float* __restrict__ scale_shift,
                               const float* __restrict__ mean_invstd, double* __restrict__ sums) {
-  constexpr int U = 2;
+  constexpr int U = 4;
   extern __shared__ float sh[];  // [2*C]
   const int C = C8 * 8;
   const int cg = threadIdx.x % C8;
@@ -853,8 +889,17 @@ int ghnd_maxpool3x3s2(const void* x, void* y, void* argmax, int fmt, int N, int 
   int shift = 0;
   while ((1 << shift) < C8) ++shift;
   dim3 grid((unsigned)((Wo * C8 + 255) / 256), (unsigned)Ho, (unsigned)N);
-  maxpool_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)y, (uint2*)argmax, fmt,
-                                                         N, H, W, C8, shift, Ho, Wo);
+  cudaStream_t st = (cudaStream_t)stream;
+  const uint4* xp = (const uint4*)x;
+  uint4* yp = (uint4*)y;
+  uint2* ap = (uint2*)argmax;
+  if (fmt == GHND_F16) {
+    if (ap) maxpool_kernel<GHND_F16, true><<<grid, 256, 0, st>>>(xp, yp, ap, N, H, W, C8, shift, Ho, Wo);
+    else maxpool_kernel<GHND_F16, false><<<grid, 256, 0, st>>>(xp, yp, ap, N, H, W, C8, shift, Ho, Wo);
+  } else {
+    if (ap) maxpool_kernel<GHND_BF16, true><<<grid, 256, 0, st>>>(xp, yp, ap, N, H, W, C8, shift, Ho, Wo);
+    else maxpool_kernel<GHND_BF16, false><<<grid, 256, 0, st>>>(xp, yp, ap, N, H, W, C8, shift, Ho, Wo);
+  }
   GHND_LAUNCH_CHECK("maxpool_kernel");
   return GHND_OK;
 }
@@ -870,10 +915,24 @@ int ghnd_maxpool3x3s2_bwd(const void* x, int x_fmt, const void* argmax, const vo
                  "maxpool3x3s2_bwd: C/8 must be a power of two (C=%d)", C);
   int shift = 0;
   while ((1 << shift) < C8) ++shift;
-  dim3 grid((unsigned)((W * C8 + 255) / 256), (unsigned)H, (unsigned)N);
-  maxpool_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
-      (const uint4*)x, x_fmt, (const uint2*)argmax, (const uint4*)dy, dy_fmt, (uint4*)dx, dx_fmt, N, H,
-      W, C8, shift, Ho, Wo);
+  dim3 grid((unsigned)((((W + 1) / 2) * C8 + 255) / 256), (unsigned)H, (unsigned)N);
+  cudaStream_t st = (cudaStream_t)stream;
+#define GHND_POOL_BWD(XF, DYF, DXF)                                                                \
+  maxpool_bwd_kernel<XF, DYF, DXF><<<grid, 256, 0, st>>>((const uint4*)x, (const uint2*)argmax,    \
+                                                         (const uint4*)dy, (uint4*)dx, N, H, W, C8, \
+                                                         shift, Ho, Wo)
+  const int combo = (x_fmt == GHND_F16 ? 4 : 0) | (dy_fmt == GHND_F16 ? 2 : 0) | (dx_fmt == GHND_F16 ? 1 : 0);
+  switch (combo) {
+    case 0: GHND_POOL_BWD(GHND_BF16, GHND_BF16, GHND_BF16); break;
+    case 1: GHND_POOL_BWD(GHND_BF16, GHND_BF16, GHND_F16); break;
+    case 2: GHND_POOL_BWD(GHND_BF16, GHND_F16, GHND_BF16); break;
+    case 3: GHND_POOL_BWD(GHND_BF16, GHND_F16, GHND_F16); break;
+    case 4: GHND_POOL_BWD(GHND_F16, GHND_BF16, GHND_BF16); break;
+    case 5: GHND_POOL_BWD(GHND_F16, GHND_BF16, GHND_F16); break;
+    case 6: GHND_POOL_BWD(GHND_F16, GHND_F16, GHND_BF16); break;
+    default: GHND_POOL_BWD(GHND_F16, GHND_F16, GHND_F16); break;
+  }
+#undef GHND_POOL_BWD
   GHND_LAUNCH_CHECK("maxpool_bwd_kernel");
   return GHND_OK;
 }
@@ -972,7 +1031,9 @@ int ghnd_bn_bwd_reduce(const void* dy, int dy_fmt, const void* x, int x_fmt, int
     const int lanes = 256 / (C / 8);
     if (x_fmt == GHND_F16 && dy_fmt == GHND_BF16) {  // the engine's combination: fast path
       const int64_t nvec = npix * (C / 8);
-      const int grid = grid_for(nvec, 256 * 4, 6);
+      // 3 CTAs/SM x 8 warps x 8 x 16-byte loads in flight; fewer CTAs also means fewer same-address
+      // fp64 atomics in the tail (2*C per CTA)
+      const int grid = grid_for(nvec, 256 * 8, tune_int("GHND_BNRED_PER_SM", 3));
       if (relu)
         bn_bwd_reduce_fast_kernel<GHND_F16, GHND_BF16, true><<<grid, 256, 2 * C * sizeof(float), st>>>(
             (const uint4*)x, (const uint4*)dy, nvec, C / 8, scale_shift, mean_invstd, sums);

@@ -32,6 +32,39 @@ def _empty(shape, dtype, device):
     return torch.empty(shape, dtype=dtype, device=device)
 
 
+class SideStream(object):
+    """A second CUDA stream for the independent branches of a step (teacher forward next to the
+    student's stem/layer1 forward; weight repacking; the weight-gradient GEMMs next to the data-
+    gradient chain).  Every conv kernel is a persistent one-CTA-per-SM grid, so two of them never
+    share an SM -- what the second stream buys is the tail: when the CTAs of one kernel run out of
+    tiles, CTAs of the independent kernel start on the freed SMs instead of idling until the slowest
+    CTA is done.  Inside CUDA-graph capture the fork/join events become parallel graph branches.
+    Only allocation-free work may run here (all buffers are preallocated by the plans)."""
+
+    def __init__(self, device):
+        self.stream = torch.cuda.Stream(device=device)
+        self.dirty = False
+
+    def fork(self):
+        """Everything enqueued on the current stream so far happens-before later side work."""
+        self.stream.wait_stream(torch.cuda.current_stream())
+
+    def run(self, fn):
+        with torch.cuda.stream(self.stream):
+            fn()
+        self.dirty = True
+
+    def mark(self):
+        ev = torch.cuda.Event()
+        ev.record(self.stream)
+        return ev
+
+    def join(self):
+        if self.dirty:
+            torch.cuda.current_stream().wait_stream(self.stream)
+            self.dirty = False
+
+
 def fold_frozen_bn(bn):
     """FrozenBatchNorm2d -> per-channel (scale, shift) fp32 (tiny host-side tensor math)."""
     eps = float(getattr(bn, "eps", 1e-5))
@@ -242,6 +275,7 @@ class _WideUnit(object):
         K, C, R, S = conv.weight.shape
         pad = conv.padding[0]
         self.conv, self.relu, self.x, self.x_g = conv, relu, x, x_g
+        self.prepacked = False
         self.N, self.H, self.W, self.C, self.K, self.pad = N, H, W, C, K, pad
         self.Ho, self.Wo = H + 2 * pad - R + 1, W + 2 * pad - S + 1
         self.train = train
@@ -261,9 +295,20 @@ class _WideUnit(object):
             self.plan = ops.ConvPlan(CONV_FWD, N, H, W, C, K, R, S, 1, pad, x, self.w, self.out,
                                      bias=self.bn.scale_shift[K:], relu=relu)
 
+    def prepack(self):
+        """Repack this step's weights (forward [K][R][S][C] and transposed for the dgrad): depends on
+        the parameters only, so the plan runs it off the critical path at the start of the step."""
+        if not self.train:
+            return  # eval folds the BN scale into the weights inside forward()
+        ops.pack_weight(self.conv.weight, None, False, out=self.w)
+        if getattr(self, "wt", None) is not None:
+            ops.pack_weight(self.conv.weight, None, True, out=self.wt)
+        self.prepacked = True
+
     def forward(self):
         if self.train:
-            ops.pack_weight(self.conv.weight, None, False, out=self.w)
+            if not self.prepacked:
+                ops.pack_weight(self.conv.weight, None, False, out=self.w)
             self.plan.run()
             self.bn.finalize()
             ops.bn_apply(self.raw, self.out, self.bn.scale_shift, self.relu, y2=self.out_g)
@@ -289,16 +334,25 @@ class _WideUnit(object):
             self.wt = _empty((C, R, S, K), grad_dtype, dev)
             self.dgrad = ops.ConvPlan(CONV_DGRAD, N, H, W, C, K, R, S, 1, self.pad, self.g_raw, self.wt, g_x)
 
-    def backward(self):
+    def _wgrad(self):
+        self.wgrad.run()
+        ops.unpack_wgrad(self.dw_packed, self.dw)
+
+    def backward(self, side=None):
         bn = self.bn
         ops.bn_bwd_reduce(self.g_out, self.raw, bn.scale_shift, bn.mean_invstd, self.relu, bn.sums)
         ops.bn_bwd_apply(self.g_out, self.raw, self.g_raw, bn.bn.weight, bn.scale_shift, bn.mean_invstd,
                          self.relu, bn.sums, self.dgamma, self.dbeta)
-        self.wgrad.run()
-        ops.unpack_wgrad(self.dw_packed, self.dw)
+        if side is not None:  # dW next to the dgrad chain (reads g_raw / x_g only)
+            side.fork()
+            side.run(self._wgrad)
+        else:
+            self._wgrad()
         if self.dgrad is not None:
-            ops.pack_weight(self.conv.weight, None, True, out=self.wt)
+            if not self.prepacked:
+                ops.pack_weight(self.conv.weight, None, True, out=self.wt)
             self.dgrad.run()
+        self.prepacked = False
 
 
 class StudentLayer1Runner(object):
@@ -401,11 +455,18 @@ class StudentLayer1Runner(object):
         self.e1.plan_backward(self.g_e1out, self.g_e0out, grads, (e + "2.weight", e + "3.weight", e + "3.bias"), gd)
         self.e0.plan_backward(self.g_e0out, self.g_x, grads, (e + "0.weight", e + "1.weight", e + "1.bias"), gd)
 
-    def backward(self):
+    def wide_units(self):
+        return (self.e0, self.e1, self.e2, self.d4, self.d7, self.d9)
+
+    def prepack(self):
+        for u in self.wide_units():
+            u.prepack()
+
+    def backward(self, side=None):
         e, d = self.names
-        self.d9.backward()
-        self.d7.backward()
-        self.d4.backward()
+        self.d9.backward(side)
+        self.d7.backward(side)
+        self.d4.backward(side)
         # BN dec[3] (no ReLU) on raw3
         b3 = self.bn3
         ops.bn_bwd_reduce(self.g_act3, self.raw3, b3.scale_shift, b3.mean_invstd, False, b3.sums)
@@ -424,9 +485,9 @@ class StudentLayer1Runner(object):
         # enc7 (narrow-out conv)
         ops.wgrad_narrow(self.g_z, self.e2.out, self.gr[e + "7.weight"], True, 2, 2, 1, ws=self.wws)
         ops.conv_narrow_in(self.g_z, self.enc7.weight, 1, flip=True, y=self.g_e2out, ws=self.nws)
-        self.e2.backward()
-        self.e1.backward()
-        self.e0.backward()
+        self.e2.backward(side)
+        self.e1.backward(side)
+        self.e0.backward(side)
 
 
 def _same_frozen_layers(teacher_body, student_body, names):
@@ -558,6 +619,8 @@ class GhndPlan(object):
         self.s_l1.plan_backward(g, grads, "backbone.body.layer1.")
         self.graph = None
         self.step_count = 0
+        import os
+        self.side = SideStream(dev) if os.environ.get("GHND_SIDE_STREAM", "1") != "0" else None
 
     # ------------------------------------------------------------------------------------------
     def load_images(self, images):
@@ -568,12 +631,22 @@ class GhndPlan(object):
 
     def forward_backward(self):
         """Enqueue teacher fwd, student fwd, loss and student bwd on the current stream."""
-        self.t_stem.forward()
-        for name in LEVELS:
-            if name in self.t_layers:
-                self.t_layers[name].forward()
-        self.s_stem.forward()
-        self.s_l1.forward()
+        side = self.side
+        if side is not None:
+            # branch 1 (side): this step's weight repacking, then the whole teacher forward;
+            # branch 2 (main): student stem + layer1.  They meet at the (shared) frozen trunk.
+            side.fork()
+            side.run(self.s_l1.prepack)
+            packed = side.mark()
+            side.run(self._teacher_forward)
+            self.s_stem.forward()
+            torch.cuda.current_stream().wait_event(packed)
+            self.s_l1.forward()
+            side.join()
+        else:
+            self._teacher_forward()
+            self.s_stem.forward()
+            self.s_l1.forward()
         for name in LEVELS[1:]:
             if name in self.s_layers:
                 self.s_layers[name].forward()  # both models' images when the frozen trunk is shared
@@ -583,9 +656,17 @@ class GhndPlan(object):
         for name in reversed(LEVELS[1:]):
             if name in self.s_layers:
                 self.s_layers[name].backward()
-        self.s_l1.backward()
+        self.s_l1.backward(side)
         self.s_stem.backward(self.s_l1.g_x, self.flat.grads["backbone.body.conv1.weight"])
+        if side is not None:
+            side.join()
         return self.loss_out
+
+    def _teacher_forward(self):
+        self.t_stem.forward()
+        for name in LEVELS:
+            if name in self.t_layers:
+                self.t_layers[name].forward()
 
     def capture(self):
         """Capture forward_backward() into a CUDA graph (buffers and plans are static)."""
