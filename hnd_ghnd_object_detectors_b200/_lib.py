@@ -54,6 +54,7 @@ SIGNATURES = {
     "ghnd_device_check": (_I, []),
     "ghnd_quantize_u8_workspace_bytes": (_Z, [_L]),
     "ghnd_quantize_u8": (_I, [_P, _L, _I, _I, _P, _P, _P, _Z, _P]),
+    "ghnd_quantize_u8_minmax": (_I, [_P, _L, _I, _I, _P, _I, _P, _P, _P]),
     "ghnd_dequantize_u8": (_I, [_P, _L, _P, _P, _P]),
     "ghnd_sse_workspace_bytes": (_Z, []),
     "ghnd_sse_fwd_bwd": (_I, [POINTER(SseLevel), _I, _I, _I, _P, _P, _Z, _P]),
@@ -64,6 +65,7 @@ SIGNATURES = {
                                           POINTER(c_float), _P, _I, _I, _I, _I, _P]),
     "ghnd_conv_plan_create": (_I, [POINTER(ConvDesc), POINTER(c_void_p)]),
     "ghnd_conv_plan_run": (_I, [_P, _P]),
+    "ghnd_conv_plan_run_range": (_I, [_P, _I, _I, _P]),
     "ghnd_conv_plan_destroy": (None, [_P]),
     "ghnd_conv_plan_launches": (_I, [_P]),
     "ghnd_wgrad_plan_create": (_I, [POINTER(WgradDesc), POINTER(c_void_p)]),
@@ -73,6 +75,8 @@ SIGNATURES = {
     "ghnd_unpack_wgrad": (_I, [_P, _P, _I, _I, _I, _I, _F, _P]),
     "ghnd_conv_narrow_workspace_bytes": (_Z, [_I, _I, _I, _I]),
     "ghnd_conv_narrow_out": (_I, [_P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _Z, _P]),
+    "ghnd_conv_narrow_out_minmax": (_I, [_P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _Z, _P, _I,
+                                         POINTER(c_int), _P]),
     "ghnd_conv_narrow_in": (_I, [_P, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _Z, _P]),
     "ghnd_conv_narrow_out_dgrad": (_I, [_P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _Z, _P]),
     "ghnd_wgrad_narrow_workspace_bytes": (_Z, [_I, _I, _I, _I]),

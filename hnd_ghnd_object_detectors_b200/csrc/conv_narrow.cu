@@ -247,15 +247,21 @@ __device__ __forceinline__ void split16(float v, uint32_t& hi, uint32_t& lo) {
 }
 
 // out[n][co][i][j] (planar fp32) = sum_{tap,c} wt[tap][c][co] * in[n][i+dh][j+dw][c], 64 wide channels.
-// One warp = 16 consecutive (flattened) output pixels; lane (g,t) loads, for rows g and g+8 and
-// every tap, the two 16-byte pieces t and t+4 of the pixel row.  GEMM-K step (tap, s): lane t's
+// A CTA works on blocks of 8 output rows x 16 output columns: warp w owns row 8*ib + w, its 16
+// pixels are one m16 tile; lane (g,t) loads, for pixels g and g+8 and every tap, the two 16-byte
+// pieces t and t+4 of the pixel row.  Neighbouring rows / columns of a k2 conv share three of
+// their four taps: with the 2-D blocking those repeats hit L1 (the flat pixel order sent every
+// tap to L2: 4x the tensor in L2 traffic, ~25 % of HBM speed).  GEMM-K step (tap, s): lane t's
 // logical k {2t,2t+1 | 2t+8,2t+9} are channels base..base+3, base = 32*(s>>1) + 8t + 4*(s&1).
-template <int FMT, int NT>
+// kMinMax: also publish the CTA's min / max of the stored values (NaN-propagating like torch.min)
+// as partial[2*blockIdx.x .. +1] -- the quantizer's first pass, fused into the producer.
+template <int FMT, int NT, bool kMinMax>
 __global__ void __launch_bounds__(256, 2)
     narrow_out_mma_kernel(const uint4* __restrict__ in, const float* __restrict__ wt,
                           float* __restrict__ out, int N, int Hi, int Wi, int CN, int Ho, int Wo,
-                          NarrowTaps taps) {
+                          NarrowTaps taps, float* __restrict__ partial) {
   __shared__ uint4 s_b[16 * NT * 32];  // [k-step][n-tile][lane] = {b0 hi, b1 hi, b0 lo, b1 lo}
+  __shared__ float s_mm[16];
   for (int idx = threadIdx.x; idx < 16 * NT * 32; idx += blockDim.x) {
     const int l = idx & 31, nt = (idx >> 5) % NT, ks = idx / (32 * NT);
     const int g = l >> 2, t = l & 3;
@@ -272,33 +278,32 @@ __global__ void __launch_bounds__(256, 2)
                           lo[2] | (lo[3] << 16));
   }
   __syncthreads();
-  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const uint32_t npix = (uint32_t)N * Ho * Wo;
-  const uint32_t tiles = (npix + 15) >> 4;
-  for (uint32_t tile = blockIdx.x * 8 + (threadIdx.x >> 5); tile < tiles; tile += gridDim.x * 8) {
-    bool pv[2];
-    int pn[2], pi[2], pj[2];
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const uint32_t p = tile * 16 + g + 8 * r;
-      pv[r] = p < npix;
-      const uint32_t pp = pv[r] ? p : 0;
-      const uint32_t q = pp / (uint32_t)Wo;
-      pj[r] = (int)(pp - q * Wo);
-      pn[r] = (int)(q / (uint32_t)Ho);
-      pi[r] = (int)(q - (uint32_t)pn[r] * Ho);
-    }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const uint32_t JB = (uint32_t)(Wo + 15) >> 4, IB = (uint32_t)(Ho + 7) >> 3;
+  const uint32_t ctiles = (uint32_t)N * IB * JB;
+  float mn = INFINITY, mx = -INFINITY;
+  bool has_nan = false;
+  for (uint32_t ct = blockIdx.x; ct < ctiles; ct += gridDim.x) {
+    const uint32_t q = ct / JB, jb = ct - q * JB;
+    const uint32_t n = q / IB, ib = q - n * IB;
+    const int i = (int)(ib * 8) + warp;
+    const int j0 = (int)(jb * 16) + g;
+    const bool row_ok = i < Ho;
     uint4 v[kNarrowMaxTaps][2][2];
 #pragma unroll
-    for (int tap = 0; tap < kNarrowMaxTaps; ++tap)
+    for (int tap = 0; tap < kNarrowMaxTaps; ++tap) {
+      const int h = i + taps.dh[tap];
+      const bool hok = row_ok && tap < taps.n_taps && h >= 0 && h < Hi;
+      const uint32_t rowbase = ((uint32_t)((int)n * Hi + h) * (uint32_t)Wi) * 8u + (uint32_t)t;
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
-        const int h = pi[r] + taps.dh[tap], w = pj[r] + taps.dw[tap];
-        const bool ok = pv[r] && tap < taps.n_taps && h >= 0 && h < Hi && w >= 0 && w < Wi;
-        const uint4* src = in + (((size_t)pn[r] * Hi + h) * Wi + w) * 8 + t;
+        const int j = j0 + 8 * r, w = j + taps.dw[tap];
+        const bool ok = hok && j < Wo && w >= 0 && w < Wi;
+        const uint4* src = in + (rowbase + (uint32_t)w * 8u);
         v[tap][r][0] = ok ? __ldg(src) : make_uint4(0, 0, 0, 0);
         v[tap][r][1] = ok ? __ldg(src + 4) : make_uint4(0, 0, 0, 0);
       }
+    }
     float dhi[NT][4], dlo[NT][4];
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt)
@@ -326,19 +331,53 @@ __global__ void __launch_bounds__(256, 2)
         mma16816<FMT>(dlo[nt], a, b.z, b.w);
       }
     }
+    if (row_ok) {
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt)
+      for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int co = nt * 8 + 2 * t + e;
-        if (co < CN) {
+        for (int e = 0; e < 2; ++e) {
+          const int co = nt * 8 + 2 * t + e;
+          if (co < CN) {
+            float* dst = out + ((size_t)((int)n * CN + co) * Ho + i) * Wo;
 #pragma unroll
-          for (int r = 0; r < 2; ++r)
-            if (pv[r])
-              out[(((size_t)pn[r] * CN + co) * Ho + pi[r]) * Wo + pj[r]] =
-                  dhi[nt][2 * r + e] + dlo[nt][2 * r + e] * LoScale<FMT>::kDown;
+            for (int r = 0; r < 2; ++r) {
+              const int j = j0 + 8 * r;
+              if (j < Wo) {
+                const float val = dhi[nt][2 * r + e] + dlo[nt][2 * r + e] * LoScale<FMT>::kDown;
+                dst[j] = val;
+                if (kMinMax) {
+                  has_nan |= val != val;
+                  mn = fminf(mn, val);
+                  mx = fmaxf(mx, val);
+                }
+              }
+            }
+          }
         }
+    }
+  }
+  if (kMinMax) {
+    if (has_nan) mn = mx = __int_as_float(0x7fc00000);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float omn = __shfl_xor_sync(0xffffffffu, mn, o), omx = __shfl_xor_sync(0xffffffffu, mx, o);
+      mn = (mn != mn) ? mn : ((omn != omn) ? omn : fminf(mn, omn));
+      mx = (mx != mx) ? mx : ((omx != omx) ? omx : fmaxf(mx, omx));
+    }
+    if (lane == 0) {
+      s_mm[2 * warp] = mn;
+      s_mm[2 * warp + 1] = mx;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < 8; ++w) {
+        const float omn = s_mm[2 * w], omx = s_mm[2 * w + 1];
+        mn = (mn != mn) ? mn : ((omn != omn) ? omn : fminf(mn, omn));
+        mx = (mx != mx) ? mx : ((omx != omx) ? omx : fmaxf(mx, omx));
       }
+      partial[2 * blockIdx.x] = mn;
+      partial[2 * blockIdx.x + 1] = mx;
+    }
   }
 }
 
@@ -817,19 +856,29 @@ static int narrow_tile_blocks(int64_t npix) {
   if (b > cap) b = cap;
   return (int)(b < 1 ? 1 : b);
 }
-static void launch_narrow_out_mma(const void* in, int fmt, const float* wt, float* out, int N, int Hi,
-                                  int Wi, int CN, int Ho, int Wo, const NarrowTaps& taps,
-                                  cudaStream_t st) {
-  const int blocks = narrow_tile_blocks((int64_t)N * Ho * Wo);
-#define GHND_NO(FMT, NT)                                                                          \
-  narrow_out_mma_kernel<FMT, NT><<<blocks, 256, 0, st>>>((const uint4*)in, wt, out, N, Hi, Wi, CN, \
-                                                         Ho, Wo, taps)
+static int narrow_out_blocks(int N, int Ho, int Wo) {
+  const int64_t ctiles = (int64_t)N * ((Ho + 7) / 8) * ((Wo + 15) / 16);
+  const int64_t cap = (int64_t)num_sms() * 2;
+  return (int)(ctiles < cap ? ctiles : cap);
+}
+// returns the number of CTAs (= min/max partial pairs written when `partial` is given)
+static int launch_narrow_out_mma(const void* in, int fmt, const float* wt, float* out, int N, int Hi,
+                                 int Wi, int CN, int Ho, int Wo, const NarrowTaps& taps,
+                                 float* partial, cudaStream_t st) {
+  const int blocks = narrow_out_blocks(N, Ho, Wo);
+#define GHND_NO(FMT, NT, MM)                                                                        \
+  narrow_out_mma_kernel<FMT, NT, MM><<<blocks, 256, 0, st>>>((const uint4*)in, wt, out, N, Hi, Wi, \
+                                                             CN, Ho, Wo, taps, partial)
+#define GHND_NO_MM(FMT, NT) \
+  if (partial) GHND_NO(FMT, NT, true); else GHND_NO(FMT, NT, false)
   if (fmt == GHND_F16) {
-    if (CN <= 8) GHND_NO(GHND_F16, 1); else GHND_NO(GHND_F16, 2);
+    if (CN <= 8) { GHND_NO_MM(GHND_F16, 1); } else { GHND_NO_MM(GHND_F16, 2); }
   } else {
-    if (CN <= 8) GHND_NO(GHND_BF16, 1); else GHND_NO(GHND_BF16, 2);
+    if (CN <= 8) { GHND_NO_MM(GHND_BF16, 1); } else { GHND_NO_MM(GHND_BF16, 2); }
   }
+#undef GHND_NO_MM
 #undef GHND_NO
+  return blocks;
 }
 static void launch_narrow_in_mma(const float* in, const float* pre, int pre_relu, const float* wt,
                                  void* out, int fmt, int N, int Hi, int Wi, int CN, int Ho, int Wo,
@@ -865,9 +914,10 @@ size_t ghnd_conv_narrow_workspace_bytes(int C, int K, int R, int S) {
   return (size_t)C * K * R * S * sizeof(float);
 }
 
-int ghnd_conv_narrow_out(const void* x, int x_fmt, const float* w, float* y, int N, int H, int W,
-                         int C, int K, int R, int S, int pad, void* workspace,
-                         size_t workspace_bytes, void* stream) {
+static int conv_narrow_out_impl(const void* x, int x_fmt, const float* w, float* y, int N, int H,
+                                int W, int C, int K, int R, int S, int pad, void* workspace,
+                                size_t workspace_bytes, float* minmax_partial, int partial_capacity,
+                                int* n_partial, void* stream) {
   GHND_CHECK_ARG(x && w && y && workspace, "conv_narrow_out: null pointer");
   GHND_CHECK_ARG(pow2_lanes(C) && K >= 1 && K <= kNarrowMaxC && R * S <= kNarrowMaxTaps && R >= 1 &&
                      S >= 1,
@@ -888,9 +938,17 @@ int ghnd_conv_narrow_out(const void* x, int x_fmt, const float* w, float* y, int
     }
   const int lanes = C / 8;
   const int64_t npix = (int64_t)N * Ho * Wo;
-  if (narrow_fast_ok(C, K, npix) && (x_fmt == GHND_F16 || x_fmt == GHND_BF16))
-    launch_narrow_out_mma(x, x_fmt, (const float*)workspace, y, N, H, W, K, Ho, Wo, taps, st);
-  else if (K <= 3)
+  const bool fast = narrow_fast_ok(C, K, npix) && (x_fmt == GHND_F16 || x_fmt == GHND_BF16);
+  if (minmax_partial != nullptr) {
+    GHND_CHECK_ARG(fast && n_partial != nullptr && partial_capacity >= narrow_out_blocks(N, Ho, Wo),
+                   "conv_narrow_out_minmax: needs the 64-channel 16-bit path and %d partial pairs",
+                   narrow_out_blocks(N, Ho, Wo));
+  }
+  if (fast) {
+    const int blocks = launch_narrow_out_mma(x, x_fmt, (const float*)workspace, y, N, H, W, K, Ho, Wo,
+                                             taps, minmax_partial, st);
+    if (n_partial) *n_partial = blocks;
+  } else if (K <= 3)
     narrow_out_kernel<3><<<blocks_for_pixels(npix, 256 / lanes), 256,
                            (size_t)R * S * C * K * sizeof(float), st>>>(
         (const uint4*)x, x_fmt, (const float*)workspace, y, N, H, W, C, K, Ho, Wo, taps);
@@ -900,6 +958,22 @@ int ghnd_conv_narrow_out(const void* x, int x_fmt, const float* w, float* y, int
         (const uint4*)x, x_fmt, (const float*)workspace, y, N, H, W, C, K, Ho, Wo, taps);
   GHND_LAUNCH_CHECK("narrow_out_kernel");
   return GHND_OK;
+}
+
+int ghnd_conv_narrow_out(const void* x, int x_fmt, const float* w, float* y, int N, int H, int W,
+                         int C, int K, int R, int S, int pad, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  return conv_narrow_out_impl(x, x_fmt, w, y, N, H, W, C, K, R, S, pad, workspace, workspace_bytes,
+                              nullptr, 0, nullptr, stream);
+}
+
+int ghnd_conv_narrow_out_minmax(const void* x, int x_fmt, const float* w, float* y, int N, int H,
+                                int W, int C, int K, int R, int S, int pad, void* workspace,
+                                size_t workspace_bytes, float* minmax_partial, int partial_capacity,
+                                int* n_partial, void* stream) {
+  GHND_CHECK_ARG(minmax_partial && n_partial, "conv_narrow_out_minmax: null min/max buffer");
+  return conv_narrow_out_impl(x, x_fmt, w, y, N, H, W, C, K, R, S, pad, workspace, workspace_bytes,
+                              minmax_partial, partial_capacity, n_partial, stream);
 }
 
 int ghnd_conv_narrow_out_dgrad(const void* dy, int dy_fmt, const float* w, float* dx, int N, int H,
@@ -928,7 +1002,7 @@ int ghnd_conv_narrow_out_dgrad(const void* dy, int dy_fmt, const float* w, float
   const int lanes = K / 8;
   const int64_t npix = (int64_t)N * H * W;
   if (narrow_fast_ok(K, C, npix) && (dy_fmt == GHND_F16 || dy_fmt == GHND_BF16))
-    launch_narrow_out_mma(dy, dy_fmt, (const float*)workspace, dx, N, Ho, Wo, C, H, W, taps, st);
+    launch_narrow_out_mma(dy, dy_fmt, (const float*)workspace, dx, N, Ho, Wo, C, H, W, taps, nullptr, st);
   else if (C <= 3)
     narrow_out_kernel<3><<<blocks_for_pixels(npix, 256 / lanes), 256,
                            (size_t)R * S * C * K * sizeof(float), st>>>(

@@ -929,6 +929,22 @@ int ghnd_conv_plan_run(const ghnd_conv_plan_t* plan, void* stream) {
   return GHND_OK;
 }
 
+int ghnd_conv_plan_run_range(const ghnd_conv_plan_t* plan, int first, int count, void* stream) {
+  using namespace ghnd;
+  GHND_CHECK_ARG(plan != nullptr, "conv_plan_run_range: null plan");
+  GHND_CHECK_ARG(first >= 0 && count >= 0 && (size_t)(first + count) <= plan->launches.size(),
+                 "conv_plan_run_range: [%d, %d) outside the plan's %d launches", first, first + count,
+                 (int)plan->launches.size());
+  for (int i = first; i < first + count; ++i) {
+    const ConvLaunch& L = plan->launches[i];
+    if (L.p.stats != nullptr && i == 0)
+      GHND_CUDA(cudaMemsetAsync(L.p.stats, 0, (size_t)2 * L.p.cout * sizeof(double),
+                                (cudaStream_t)stream));
+    GHND_CUDA(launch_conv(L, (cudaStream_t)stream));
+  }
+  return GHND_OK;
+}
+
 int ghnd_conv_plan_launches(const ghnd_conv_plan_t* plan) {
   return plan ? (int)plan->launches.size() : 0;
 }

@@ -362,6 +362,28 @@ int ghnd_quantize_u8(const float* x, int64_t n, int num_bits, int scale_mode, ui
   return GHND_OK;
 }
 
+int ghnd_quantize_u8_minmax(const float* x, int64_t n, int num_bits, int scale_mode,
+                            const float* minmax_partial, int n_partial, uint8_t* q, void* qparams,
+                            void* stream) {
+  using namespace ghnd;
+  GHND_CHECK_ARG(x && q && qparams && minmax_partial, "quantize_u8_minmax: null pointer");
+  GHND_CHECK_ARG(n > 0 && n_partial > 0, "quantize_u8_minmax: empty tensor");
+  GHND_CHECK_ARG(num_bits >= 1 && num_bits <= 8, "quantize_u8_minmax: num_bits %d not in [1,8]", num_bits);
+  GHND_CHECK_ARG(scale_mode == GHND_QSCALE_DIV || scale_mode == GHND_QSCALE_RECIP,
+                 "quantize_u8_minmax: bad scale_mode %d", scale_mode);
+  const int vec_ok = ((((uintptr_t)x) & 15) == 0 && (((uintptr_t)q) & 15) == 0) ? 1 : 0;
+  const float qmax = (float)((1 << num_bits) - 1);
+  // one streaming pass: 4 B read + 1 B write per element; 16 elements per thread and iteration
+  int64_t blocks = (n / 16 + kQThreads - 1) / kQThreads;
+  const int64_t cap = (int64_t)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  quant_apply_kernel<<<(int)blocks, kQThreads, 0, (cudaStream_t)stream>>>(
+      x, n, vec_ok, minmax_partial, n_partial, qmax, 1.0f / qmax, scale_mode, q, (QParams*)qparams);
+  GHND_LAUNCH_CHECK("quant_apply_kernel");
+  return GHND_OK;
+}
+
 int ghnd_dequantize_u8(const uint8_t* q, int64_t n, const void* qparams, float* out,
                        void* stream) {
   using namespace ghnd;

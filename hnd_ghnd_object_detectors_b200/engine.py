@@ -150,18 +150,38 @@ class BottleneckRunner(object):
             self.bwd.append(ops.ConvPlan(CONV_DGRAD, N, H, W, cin, p, 1, 1, 1, 0, self.g_a1, self.c1.wt,
                                          g_x, residual=g_out, mask=x_b))
         else:
+            # the stride-2 downsample dgrad reaches only the even lattice of g_x, so it has to be the
+            # accumulating launch and stays behind the main branch
             self.bwd.append(ops.ConvPlan(CONV_DGRAD, N, H, W, cin, p, 1, 1, 1, 0, self.g_a1, self.c1.wt,
                                          g_x, residual=loss_grad_x, mask=x_b))
             self.bwd.append(ops.ConvPlan(CONV_DGRAD, N, H, W, cin, cout, 1, 1, s, 0, g_out, self.cd.wt,
                                          g_x, mask=x_b, accumulate=True))
 
-    def forward(self):
+    def forward(self, side=None):
+        if self.cd is not None and side is not None:
+            # [conv1, conv2, downsample, conv3]: the downsample conv only needs x
+            side.fork()
+            side.run(self.fwd[2].run)
+            self.fwd[0].run()
+            self.fwd[1].run()
+            side.join()
+            self.fwd[3].run()
+            return
         for p in self.fwd:
             p.run()
 
-    def backward(self):
+    def backward(self, side=None):
         for p in self.bwd:
-            p.run()
+            n = p.n_launches
+            if side is not None and n > 1 and p is self.bwd[1]:
+                # stride-2 3x3 dgrad = one small launch per output parity class, disjoint outputs:
+                # half of them on the second stream
+                side.fork()
+                side.run(lambda: p.run_range(n // 2, n - n // 2))
+                p.run_range(0, n // 2)
+                side.join()
+            else:
+                p.run()
 
 
 class FrozenLayerRunner(object):
@@ -179,9 +199,9 @@ class FrozenLayerRunner(object):
             x, H, W = r.out, r.Ho, r.Wo
         self.out, self.Ho, self.Wo = x, H, W
 
-    def forward(self):
+    def forward(self, side=None):
         for b in self.blocks:
-            b.forward()
+            b.forward(side)
 
     def plan_backward(self, g_out, g_x, loss_grad_x, grad_dtype):
         """g_out: masked gradient at this layer's output; g_x: buffer for the layer input's."""
@@ -196,9 +216,9 @@ class FrozenLayerRunner(object):
                 b.plan_backward(g, gx, None, grad_dtype)
                 g = gx
 
-    def backward(self):
+    def backward(self, side=None):
         for b in reversed(self.blocks):
-            b.backward()
+            b.backward(side)
 
 
 class StemRunner(object):
@@ -398,13 +418,19 @@ class StudentLayer1Runner(object):
         self.q = None  # set by forward_encoder_quantized
 
     # ---- forward ----
-    def forward_encoder(self):
+    def forward_encoder(self, minmax=None):
+        """minmax: fp32 buffer for the (min, max) partial pairs of z (the quantizer's first pass,
+        fused into the last encoder conv); the number of pairs is left in self.z_pairs."""
         if self.train and self._own_xg:
             ops.convert16(self.x, self.x_g)
         self.e0.forward()
         self.e1.forward()
         self.e2.forward()
-        ops.conv_narrow_out(self.e2.out, self.enc7.weight, 1, y=self.z, ws=self.nws)
+        if minmax is not None:
+            _, self.z_pairs = ops.conv_narrow_out(self.e2.out, self.enc7.weight, 1, y=self.z, ws=self.nws,
+                                                  minmax=minmax)
+        else:
+            ops.conv_narrow_out(self.e2.out, self.enc7.weight, 1, y=self.z, ws=self.nws)
         return self.z
 
     def forward_decoder(self, z=None):
@@ -649,13 +675,15 @@ class GhndPlan(object):
             self.s_l1.forward()
         for name in LEVELS[1:]:
             if name in self.s_layers:
-                self.s_layers[name].forward()  # both models' images when the frozen trunk is shared
+                # both models' images when the frozen trunk is shared (the teacher has been joined by
+                # then, so the side stream is free for the downsample convs)
+                self.s_layers[name].forward(side if self.shared else None)
         lv = [(self.feat_t[l], self.feat_s[l], self.loss_grads[l], self.factors[l], l == self.top)
               for l in self.levels]
         ops.sse_fwd_bwd(lv, self.grad_dtype, self.loss_out, self.sse_ws)
         for name in reversed(LEVELS[1:]):
             if name in self.s_layers:
-                self.s_layers[name].backward()
+                self.s_layers[name].backward(side)
         self.s_l1.backward(side)
         self.s_stem.backward(self.s_l1.g_x, self.flat.grads["backbone.body.conv1.weight"])
         if side is not None:
@@ -727,8 +755,8 @@ class EncodePlan(object):
         self.z = self.l1.z
         self.q = torch.empty(tuple(self.z.shape), dtype=torch.uint8, device=dev)
         self.qparams = torch.zeros(4, dtype=torch.int32, device=dev)
-        self.qws_bytes = _lib.load().ghnd_quantize_u8_workspace_bytes(self.z.numel())
-        self.qws = torch.zeros((self.qws_bytes,), dtype=torch.uint8, device=dev)  # barrier words start at 0
+        # the encoder's last conv publishes min / max of z, so the quantizer is one streaming pass
+        self.minmax = torch.zeros((2 * ops.MINMAX_CAPACITY,), dtype=torch.float32, device=dev)
         self.graph = None
 
     def load_images(self, images):
@@ -739,13 +767,12 @@ class EncodePlan(object):
     def forward(self):
         self.stem.refresh_weights()
         self.stem.forward()
-        self.l1.forward_encoder()
         if self.num_bits == 16:
+            self.l1.forward_encoder()
             return self.z
-        _lib.call("ghnd_quantize_u8", _lib.ptr(self.z), self.z.numel(), self.num_bits, self.scale_mode,
-                  _lib.ptr(self.q), _lib.ptr(self.qparams), _lib.ptr(self.qws), self.qws_bytes,
-                  _lib.stream_ptr())
-        ops._count(1)
+        self.l1.forward_encoder(minmax=self.minmax)
+        ops.quantize_u8_minmax(self.z, self.minmax, self.l1.z_pairs, self.num_bits, self.scale_mode,
+                               q=self.q, qparams=self.qparams)
         return self.q
 
     def capture(self):

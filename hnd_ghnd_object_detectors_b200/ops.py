@@ -54,6 +54,21 @@ def quantize_u8(x, num_bits=8, scale_mode=_lib.QSCALE_DIV):
     return q, qp
 
 
+def quantize_u8_minmax(x, minmax, n_pairs, num_bits=8, scale_mode=_lib.QSCALE_DIV, q=None, qparams=None):
+    """Single-pass quantizer for a tensor whose (min, max) partial pairs were published by its
+    producer (conv_narrow_out(..., minmax=...)).  Same bytes as quantize_u8."""
+    _need_cuda(x, minmax)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    if q is None:
+        q = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    if qparams is None:
+        qparams = torch.empty(4, dtype=torch.int32, device=x.device)
+    call("ghnd_quantize_u8_minmax", ptr(x), x.numel(), num_bits, scale_mode, ptr(minmax), int(n_pairs),
+         ptr(q), ptr(qparams), stream_ptr())
+    _count(1)
+    return q, qparams
+
+
 def dequantize_u8(q, qparams):
     _need_cuda(q, qparams)
     q = q.contiguous()
@@ -178,6 +193,12 @@ class ConvPlan(object):
         except _lib.GhndError as e:
             raise _lib.GhndError("%s [conv plan: %s]" % (e, self.desc))
         _count(self.n_launches)
+
+    def run_range(self, first, count, stream=None):
+        """Only launches [first, first+count): they write disjoint parts of dst, so the caller may
+        put them on different streams (parity classes of a stride-2 dgrad)."""
+        call("ghnd_conv_plan_run_range", self._h, int(first), int(count), stream_ptr(stream))
+        _count(count)
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -330,8 +351,13 @@ def _narrow_ws(c, k, r, s, device):
     return _ws(n, device), n
 
 
-def conv_narrow_out(x, w, pad, y=None, ws=None):
-    """x NHWC16 [N,H,W,C], w OIHW fp32 [K,C,R,S] -> y planar fp32 [N,K,Ho,Wo]."""
+MINMAX_CAPACITY = 1024  # (min, max) pairs a producer may publish (>= 2 x SM count)
+
+
+def conv_narrow_out(x, w, pad, y=None, ws=None, minmax=None):
+    """x NHWC16 [N,H,W,C], w OIHW fp32 [K,C,R,S] -> y planar fp32 [N,K,Ho,Wo].
+    minmax: optional fp32 [2*MINMAX_CAPACITY] buffer; the kernel then also writes per-CTA (min, max)
+    pairs of y into it and the call returns (y, number of pairs) -- input of quantize_u8_minmax."""
     n, h, wd, c = x.shape
     k, _, r, s = w.shape
     ho, wo = h + 2 * pad - r + 1, wd + 2 * pad - s + 1
@@ -339,6 +365,13 @@ def conv_narrow_out(x, w, pad, y=None, ws=None):
         y = torch.empty((n, k, ho, wo), dtype=torch.float32, device=x.device)
     if ws is None:
         ws = _narrow_ws(c, k, r, s, x.device)
+    if minmax is not None:
+        assert minmax.dtype == torch.float32 and minmax.numel() >= 2
+        n_pairs = ctypes.c_int(0)
+        call("ghnd_conv_narrow_out_minmax", ptr(x), fmt_of(x.dtype), ptr(w), ptr(y), n, h, wd, c, k, r, s,
+             pad, ptr(ws[0]), ws[1], ptr(minmax), minmax.numel() // 2, byref(n_pairs), stream_ptr())
+        _count(2)
+        return y, n_pairs.value
     call("ghnd_conv_narrow_out", ptr(x), fmt_of(x.dtype), ptr(w), ptr(y), n, h, wd, c, k, r, s, pad,
          ptr(ws[0]), ws[1], stream_ptr())
     _count(2)

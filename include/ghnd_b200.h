@@ -62,6 +62,15 @@ int ghnd_device_check(void);
 size_t ghnd_quantize_u8_workspace_bytes(int64_t n);
 int ghnd_quantize_u8(const float* x, int64_t n, int num_bits, int scale_mode, uint8_t* q,
                      void* qparams, void* workspace, size_t workspace_bytes, void* stream);
+/* The same quantizer as ONE streaming pass (4 B read + 1 B write per element) when the tensor's
+ * min / max are already known as `n_partial` (min, max) pairs -- written by the kernel that
+ * produced x (ghnd_conv_narrow_out_minmax: the encoder's last conv, src/models/mimic/
+ * split_rcnn.py:31-35 runs encoder then Quantizer back to back).  Folding the pairs, deriving
+ * scale / zero-point and quantizing follow the same operation order; results are bit-identical to
+ * ghnd_quantize_u8 on the same tensor.  No workspace. */
+int ghnd_quantize_u8_minmax(const float* x, int64_t n, int num_bits, int scale_mode,
+                            const float* minmax_partial, int n_partial, uint8_t* q, void* qparams,
+                            void* stream);
 /* out = scale * (float(q) - zero_point)   (tensor_util.py:21-22) */
 int ghnd_dequantize_u8(const uint8_t* q, int64_t n, const void* qparams, float* out, void* stream);
 
@@ -149,6 +158,9 @@ typedef struct ghnd_conv_desc {
 typedef struct ghnd_conv_plan ghnd_conv_plan_t;
 int ghnd_conv_plan_create(const ghnd_conv_desc_t* desc, ghnd_conv_plan_t** plan);
 int ghnd_conv_plan_run(const ghnd_conv_plan_t* plan, void* stream);
+/* Enqueue only launches [first, first+count) of the plan.  The launches of one plan write disjoint
+ * parts of dst (the parity classes of a stride-2 dgrad), so a caller may spread them over streams. */
+int ghnd_conv_plan_run_range(const ghnd_conv_plan_t* plan, int first, int count, void* stream);
 void ghnd_conv_plan_destroy(ghnd_conv_plan_t* plan);
 /* number of kernel launches one run of the plan enqueues (for gpu_launches accounting) */
 int ghnd_conv_plan_launches(const ghnd_conv_plan_t* plan);
@@ -189,6 +201,14 @@ size_t ghnd_conv_narrow_workspace_bytes(int C, int K, int R, int S);
 int ghnd_conv_narrow_out(const void* x, int x_fmt, const float* w, float* y, int N, int H, int W,
                          int C, int K, int R, int S, int pad, void* workspace,
                          size_t workspace_bytes, void* stream);
+/* The same conv that also publishes per-CTA (min, max) pairs of the stored fp32 outputs
+ * (NaN-propagating like torch.min / torch.max): minmax_partial[2*i], [2*i+1] for i < *n_partial,
+ * *n_partial <= partial_capacity (2 * SM count pairs always suffice).  64-channel 16-bit input only.
+ * Feeds ghnd_quantize_u8_minmax. */
+int ghnd_conv_narrow_out_minmax(const void* x, int x_fmt, const float* w, float* y, int N, int H,
+                                int W, int C, int K, int R, int S, int pad, void* workspace,
+                                size_t workspace_bytes, float* minmax_partial, int partial_capacity,
+                                int* n_partial, void* stream);
 /* flip=0: y[n][ho][wo][k] = sum_{r,s,c} w[k][c][r][s] * f(x[n][c][ho+r-pad][wo+s-pad]),
  *   f(v) = pre_scale_shift ? (v*scale[c]+shift[c], then max(.,0) if pre_relu) : v
  *   (decoder BN0+ReLU fused; zero padding is applied AFTER f).  w: OIHW [K][C][R][S].

@@ -105,6 +105,37 @@ def test_quantizer_vs_oracle_and_torch_cuda(ops, shape):
     assert torch.equal(deq, float(so) * (q.float() - zo))
 
 
+@pytest.mark.parametrize("geom", [(2, 13, 29, 3), (1, 40, 67, 6), (3, 9, 16, 12)])
+def test_narrow_out_minmax_feeds_single_pass_quantizer(ops, geom):
+    """The encoder's last conv publishes (min, max) partial pairs of the tensor it writes; the
+    one-pass quantizer fed with them must give the same bytes / scale / zero-point as the two-pass
+    quantizer on that tensor, which in turn is bit-exact against the oracle (both scale modes)."""
+    from hnd_ghnd_object_detectors_b200 import _lib
+    N, H, W, bch = geom
+    g = torch.Generator().manual_seed(N * 100 + bch)
+    x = ops.to_nhwc16(torch.randn(N, 64, H, W, generator=g).cuda(), torch.float16)
+    w = (torch.randn(bch, 64, 2, 2, generator=g) * 0.2).cuda()
+    mm = torch.zeros(2 * ops.MINMAX_CAPACITY, device="cuda")
+    z, pairs = ops.conv_narrow_out(x, w, 1, minmax=mm)
+    z_plain = ops.conv_narrow_out(x, w, 1)
+    torch.cuda.synchronize()
+    assert torch.equal(z, z_plain) and 1 <= pairs <= ops.MINMAX_CAPACITY
+    part = mm[:2 * pairs].view(pairs, 2).cpu()
+    assert float(part[:, 0].min()) == float(z.min()) and float(part[:, 1].max()) == float(z.max())
+    for mode, name in ((_lib.QSCALE_DIV, "div"), (_lib.QSCALE_RECIP, "recip")):
+        q1, qp1 = ops.quantize_u8_minmax(z, mm, pairs, 8, mode)
+        q2, qp2 = ops.quantize_u8(z, 8, mode)
+        assert torch.equal(q1, q2) and torch.equal(qp1, qp2)
+        qo, so, zo = O.quantize_tensor_np(z.cpu().numpy(), 8, scale_mode=name)
+        assert np.array_equal(q1.cpu().numpy(), qo) and int(qp1[1]) == zo
+    # NaN propagates like torch.min / torch.max (zero-point marker INT_MIN = the reference raises)
+    xb = x.clone()
+    xb[0, 1, 2, 5] = float("nan")
+    zb, pairs_b = ops.conv_narrow_out(xb, w, 1, minmax=mm)
+    _, qpb = ops.quantize_u8_minmax(zb, mm, pairs_b)
+    assert int(qpb[1]) == -2 ** 31
+
+
 def test_quantizer_errors(ops):
     from hnd_ghnd_object_detectors_b200 import _lib
     with pytest.raises(_lib.GhndError):
