@@ -96,6 +96,8 @@ SIGNATURES = {
     "ghnd_bn_finalize": (_I, [_P, _L, _I, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P]),
     "ghnd_bn_eval_params": (_I, [_I, _P, _P, _P, _P, _F, _P, _P]),
     "ghnd_bn_apply": (_I, [_P, _I, _P, _I, _P, _I, _L, _I, _P, _I, _P]),
+    "ghnd_bn_finalize_apply": (_I, [_P, _I, _P, _I, _P, _I, _L, _I, _I, _P, _L, _P, _P, _F, _F, _P, _P, _P, _P,
+                                    _P, _P]),
     "ghnd_convert16": (_I, [_P, _I, _P, _I, _L, _P]),
     "ghnd_bn_bwd_reduce": (_I, [_P, _I, _P, _I, _I, _I, _L, _I, _P, _P, _I, _P, _P]),
     "ghnd_bn_bwd_apply": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _L, _I, _P, _P, _P, _I, _P, _P, _P, _P]),

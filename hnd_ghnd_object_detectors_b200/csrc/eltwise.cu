@@ -545,18 +545,68 @@ __global__ void bn_param_grads_kernel(const double* __restrict__ sums, int C,
 // same 8-channel group, so its per-channel constants live in registers, the loop carries no
 // division, formats are compile-time, and several 16-byte loads are in flight per thread.
 // ------------------------------------------------------------------------------------------------
+// Optional "finalize" job of the apply kernel (training forward): derive scale / shift from the
+// batch sums in the prologue -- every thread for its own 8 channels, same fp64 formulas as
+// bn_finalize_kernel -- while block 0 also publishes scale_shift / mean_invstd for the backward pass
+// and updates the running statistics.  Saves one tiny launch per BatchNorm on the critical path.
+struct BnFin {
+  const double* sums;  // nullptr: plain apply with the given scale_shift
+  double count;
+  const float* gamma;
+  const float* beta;
+  float eps, momentum;
+  float* running_mean;
+  float* running_var;
+  int64_t* nbt;
+  float* scale_shift_out;
+  float* mean_invstd_out;
+};
 template <int XF, int YF, int Y2F, bool RELU>
 __global__ void __launch_bounds__(256)
     bn_apply_fast_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, uint4* __restrict__ y2,
-                         int64_t nvec, int C8, const float* __restrict__ scale_shift) {
+                         int64_t nvec, int C8, const float* __restrict__ scale_shift, const BnFin fin) {
   constexpr int U = 4;
   const int cg = threadIdx.x % C8;
   const int C = C8 * 8;
   float sc[8], sh[8];
+  if (fin.sums != nullptr) {
+    // one thread per channel does the fp64 math, the block shares the result through shared memory
+    __shared__ float s_ss[2 * 2048];
+    const bool publish = blockIdx.x == 0;
+    if (publish && threadIdx.x == 0 && fin.nbt != nullptr) *fin.nbt += 1;
+    for (int c = threadIdx.x; c < C; c += 256) {
+      const double mean = fin.sums[c] / fin.count;
+      double var = fin.sums[C + c] / fin.count - mean * mean;  // biased
+      if (var < 0.0) var = 0.0;
+      const float invstd = (float)(1.0 / sqrt(var + (double)fin.eps));
+      const float g = fin.gamma ? __ldg(fin.gamma + c) : 1.f, b = fin.beta ? __ldg(fin.beta + c) : 0.f;
+      const float scv = g * invstd, shv = b - (float)mean * scv;
+      s_ss[c] = scv;
+      s_ss[C + c] = shv;
+      if (publish) {
+        fin.scale_shift_out[c] = scv;
+        fin.scale_shift_out[C + c] = shv;
+        fin.mean_invstd_out[c] = (float)mean;
+        fin.mean_invstd_out[C + c] = invstd;
+        if (fin.running_mean != nullptr) {
+          const double unbiased = fin.count > 1.0 ? var * fin.count / (fin.count - 1.0) : var;
+          fin.running_mean[c] = (1.f - fin.momentum) * fin.running_mean[c] + fin.momentum * (float)mean;
+          fin.running_var[c] = (1.f - fin.momentum) * fin.running_var[c] + fin.momentum * (float)unbiased;
+        }
+      }
+    }
+    __syncthreads();
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    sc[j] = __ldg(scale_shift + cg * 8 + j);
-    sh[j] = __ldg(scale_shift + C + cg * 8 + j);
+    for (int j = 0; j < 8; ++j) {
+      sc[j] = s_ss[cg * 8 + j];
+      sh[j] = s_ss[C + cg * 8 + j];
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sc[j] = __ldg(scale_shift + cg * 8 + j);
+      sh[j] = __ldg(scale_shift + C + cg * 8 + j);
+    }
   }
   const int64_t stride = (int64_t)gridDim.x * 256;
   int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
@@ -594,10 +644,17 @@ __global__ void __launch_bounds__(256)
                              uint4* __restrict__ dx, int64_t nvec, int C8, float inv_count,
                              const float* __restrict__ scale_shift,
                              const float* __restrict__ mean_invstd,
-                             const double* __restrict__ sums) {
+                             const double* __restrict__ sums, float* __restrict__ dgamma,
+                             float* __restrict__ dbeta) {
   constexpr int U = 2;
   const int cg = threadIdx.x % C8;
   const int C = C8 * 8;
+  // parameter gradients are the two sums themselves: block 0 copies them out (was a separate launch)
+  if (blockIdx.x == 0)
+    for (int c = threadIdx.x; c < C; c += 256) {
+      if (dbeta != nullptr) dbeta[c] = (float)sums[c];
+      if (dgamma != nullptr) dgamma[c] = (float)sums[C + c];
+    }
   // dx = sc*(g' - mg - xhat*mgx) with xhat = (x-mu)*is  ==  sc*g' + x*k1 + k0
   float sc[8], sf[8], k1[8], k0[8];
 #pragma unroll
@@ -706,26 +763,27 @@ static bool fast_c8(int C) { return C >= 8 && C % 8 == 0 && C / 8 <= 256 && 256 
 
 template <int XF, int YF, int Y2F>
 static void launch_bn_apply_fast3(const uint4* x, uint4* y, uint4* y2, int64_t nvec, int C8,
-                                  const float* ss, int relu, int grid, cudaStream_t st) {
-  if (relu) bn_apply_fast_kernel<XF, YF, Y2F, true><<<grid, 256, 0, st>>>(x, y, y2, nvec, C8, ss);
-  else bn_apply_fast_kernel<XF, YF, Y2F, false><<<grid, 256, 0, st>>>(x, y, y2, nvec, C8, ss);
+                                  const float* ss, int relu, int grid, const BnFin& fin, cudaStream_t st) {
+  if (relu) bn_apply_fast_kernel<XF, YF, Y2F, true><<<grid, 256, 0, st>>>(x, y, y2, nvec, C8, ss, fin);
+  else bn_apply_fast_kernel<XF, YF, Y2F, false><<<grid, 256, 0, st>>>(x, y, y2, nvec, C8, ss, fin);
 }
 template <int XF, int YF>
 static void launch_bn_apply_fast2(int y2_fmt, const uint4* x, uint4* y, uint4* y2, int64_t nvec, int C8,
-                                  const float* ss, int relu, int grid, cudaStream_t st) {
-  if (y2 == nullptr) launch_bn_apply_fast3<XF, YF, -1>(x, y, y2, nvec, C8, ss, relu, grid, st);
-  else if (y2_fmt == GHND_F16) launch_bn_apply_fast3<XF, YF, GHND_F16>(x, y, y2, nvec, C8, ss, relu, grid, st);
-  else launch_bn_apply_fast3<XF, YF, GHND_BF16>(x, y, y2, nvec, C8, ss, relu, grid, st);
+                                  const float* ss, int relu, int grid, const BnFin& fin, cudaStream_t st) {
+  if (y2 == nullptr) launch_bn_apply_fast3<XF, YF, -1>(x, y, y2, nvec, C8, ss, relu, grid, fin, st);
+  else if (y2_fmt == GHND_F16) launch_bn_apply_fast3<XF, YF, GHND_F16>(x, y, y2, nvec, C8, ss, relu, grid, fin, st);
+  else launch_bn_apply_fast3<XF, YF, GHND_BF16>(x, y, y2, nvec, C8, ss, relu, grid, fin, st);
 }
 static void launch_bn_apply_fast(int x_fmt, int y_fmt, int y2_fmt, const uint4* x, uint4* y, uint4* y2,
-                                 int64_t nvec, int C8, const float* ss, int relu, cudaStream_t st) {
+                                 int64_t nvec, int C8, const float* ss, int relu, const BnFin& fin,
+                                 cudaStream_t st) {
   const int grid = grid_for(nvec, 256 * 4, 8);
   if (x_fmt == GHND_F16) {
-    if (y_fmt == GHND_F16) launch_bn_apply_fast2<GHND_F16, GHND_F16>(y2_fmt, x, y, y2, nvec, C8, ss, relu, grid, st);
-    else launch_bn_apply_fast2<GHND_F16, GHND_BF16>(y2_fmt, x, y, y2, nvec, C8, ss, relu, grid, st);
+    if (y_fmt == GHND_F16) launch_bn_apply_fast2<GHND_F16, GHND_F16>(y2_fmt, x, y, y2, nvec, C8, ss, relu, grid, fin, st);
+    else launch_bn_apply_fast2<GHND_F16, GHND_BF16>(y2_fmt, x, y, y2, nvec, C8, ss, relu, grid, fin, st);
   } else {
-    if (y_fmt == GHND_F16) launch_bn_apply_fast2<GHND_BF16, GHND_F16>(y2_fmt, x, y, y2, nvec, C8, ss, relu, grid, st);
-    else launch_bn_apply_fast2<GHND_BF16, GHND_BF16>(y2_fmt, x, y, y2, nvec, C8, ss, relu, grid, st);
+    if (y_fmt == GHND_F16) launch_bn_apply_fast2<GHND_BF16, GHND_F16>(y2_fmt, x, y, y2, nvec, C8, ss, relu, grid, fin, st);
+    else launch_bn_apply_fast2<GHND_BF16, GHND_BF16>(y2_fmt, x, y, y2, nvec, C8, ss, relu, grid, fin, st);
   }
 }
 
@@ -994,13 +1052,49 @@ int ghnd_bn_apply(const void* x, int x_fmt, void* y, int y_fmt, void* y2, int y2
                      C % 8 == 0 && (y2 == nullptr || fmt16(y2_fmt)),
                  "bn_apply: bad argument");
   const int64_t nvec = npix * (C / 8);
-  if (fast_c8(C))
+  if (fast_c8(C)) {
+    BnFin none;
+    memset(&none, 0, sizeof(none));
     launch_bn_apply_fast(x_fmt, y_fmt, y2_fmt, (const uint4*)x, (uint4*)y, (uint4*)y2, nvec, C / 8,
-                         scale_shift, relu, (cudaStream_t)stream);
-  else
+                         scale_shift, relu, none, (cudaStream_t)stream);
+  } else
     bn_apply_kernel<<<grid_for(nvec, 256 * 2), 256, 0, (cudaStream_t)stream>>>(
         (const uint4*)x, x_fmt, (uint4*)y, y_fmt, (uint4*)y2, y2_fmt, nvec, C / 8, scale_shift, relu);
   GHND_LAUNCH_CHECK("bn_apply_kernel");
+  return GHND_OK;
+}
+
+int ghnd_bn_finalize_apply(const void* x, int x_fmt, void* y, int y_fmt, void* y2, int y2_fmt,
+                           int64_t npix, int C, int relu, const double* sums, int64_t count,
+                           const float* gamma, const float* beta, float eps, float momentum,
+                           float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                           float* scale_shift, float* mean_invstd, void* stream) {
+  GHND_CHECK_ARG(sums && scale_shift && mean_invstd && count > 0, "bn_finalize_apply: bad argument");
+  GHND_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr),
+                 "bn_finalize_apply: running_mean/var must both be given or both be null");
+  if (!fast_c8(C)) {  // generic widths: the two separate kernels
+    int rc = ghnd_bn_finalize(sums, count, C, gamma, beta, eps, momentum, running_mean, running_var,
+                              num_batches_tracked, scale_shift, mean_invstd, stream);
+    if (rc != GHND_OK) return rc;
+    return ghnd_bn_apply(x, x_fmt, y, y_fmt, y2, y2_fmt, npix, C, scale_shift, relu, stream);
+  }
+  GHND_CHECK_ARG(x && y && fmt16(x_fmt) && fmt16(y_fmt) && npix > 0 && (y2 == nullptr || fmt16(y2_fmt)),
+                 "bn_finalize_apply: bad tensor argument");
+  BnFin fin;
+  fin.sums = sums;
+  fin.count = (double)count;
+  fin.gamma = gamma;
+  fin.beta = beta;
+  fin.eps = eps;
+  fin.momentum = momentum;
+  fin.running_mean = running_mean;
+  fin.running_var = running_var;
+  fin.nbt = num_batches_tracked;
+  fin.scale_shift_out = scale_shift;
+  fin.mean_invstd_out = mean_invstd;
+  launch_bn_apply_fast(x_fmt, y_fmt, y2_fmt, (const uint4*)x, (uint4*)y, (uint4*)y2, npix * (C / 8), C / 8,
+                       nullptr, relu, fin, (cudaStream_t)stream);
+  GHND_LAUNCH_CHECK("bn_apply_fast_kernel(finalize)");
   return GHND_OK;
 }
 
@@ -1072,11 +1166,13 @@ int ghnd_bn_bwd_apply(const void* dy, int dy_fmt, const void* x, int x_fmt, void
       if (relu)
         bn_bwd_apply_fast_kernel<GHND_F16, GHND_BF16, true><<<grid, 256, 0, st>>>(
             (const uint4*)dy, (const uint4*)x, (uint4*)dx, nvec, C / 8, (float)inv_count, scale_shift,
-            mean_invstd, sums);
+            mean_invstd, sums, dgamma, dbeta);
       else
         bn_bwd_apply_fast_kernel<GHND_F16, GHND_BF16, false><<<grid, 256, 0, st>>>(
             (const uint4*)dy, (const uint4*)x, (uint4*)dx, nvec, C / 8, (float)inv_count, scale_shift,
-            mean_invstd, sums);
+            mean_invstd, sums, dgamma, dbeta);
+      GHND_LAUNCH_CHECK("bn_bwd_apply_fast_kernel");
+      return GHND_OK;  // dgamma / dbeta written by the kernel's block 0
     } else {
       bn_bwd_apply_nhwc_kernel<<<grid_for(nvec, 256 * 2), 256, 6 * C * sizeof(float), st>>>(
           (const uint4*)dy, dy_fmt, (const uint4*)x, x_fmt, (uint4*)dx, dx_fmt, nvec, C / 8, inv_count,

@@ -281,6 +281,13 @@ class _BN(object):
                         0.1 if bn.momentum is None else bn.momentum, bn.running_mean, bn.running_var,
                         bn.num_batches_tracked, self.scale_shift, self.mean_invstd)
 
+    def finalize_apply(self, x, y, relu, y2=None):
+        """finalize() fused into the normalising pass over x (one launch)."""
+        bn = self.bn
+        ops.bn_finalize_apply(x, y, relu, self.sums, self.count, bn.weight, bn.bias, bn.eps,
+                              0.1 if bn.momentum is None else bn.momentum, bn.running_mean, bn.running_var,
+                              bn.num_batches_tracked, self.scale_shift, self.mean_invstd, y2=y2)
+
     def eval_params(self):
         bn = self.bn
         ops.bn_eval_params(self.C, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps,
@@ -330,8 +337,7 @@ class _WideUnit(object):
             if not self.prepacked:
                 ops.pack_weight(self.conv.weight, None, False, out=self.w)
             self.plan.run()
-            self.bn.finalize()
-            ops.bn_apply(self.raw, self.out, self.bn.scale_shift, self.relu, y2=self.out_g)
+            self.bn.finalize_apply(self.raw, self.out, self.relu, y2=self.out_g)
         else:
             self.bn.eval_params()
             ops.pack_weight(self.conv.weight, self.bn.scale_shift[:self.K], False, out=self.w)
@@ -444,10 +450,10 @@ class StudentLayer1Runner(object):
                            ws=self.nws)
         if self.train:
             ops.bn_stats(self.raw3, self.bn3.sums)
-            self.bn3.finalize()
+            self.bn3.finalize_apply(self.raw3, self.act3, False, y2=self.act3_g)
         else:
             self.bn3.eval_params()
-        ops.bn_apply(self.raw3, self.act3, self.bn3.scale_shift, False, y2=self.act3_g)
+            ops.bn_apply(self.raw3, self.act3, self.bn3.scale_shift, False, y2=self.act3_g)
         self.d4.forward()
         self.d7.forward()
         self.d9.forward()

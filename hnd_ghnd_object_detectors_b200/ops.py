@@ -523,6 +523,18 @@ def bn_apply(x, y, scale_shift, relu, y2=None):
     return y
 
 
+def bn_finalize_apply(x, y, relu, sums, count, gamma, beta, eps, momentum, running_mean, running_var, nbt,
+                      scale_shift, mean_invstd, y2=None):
+    """bn_finalize + bn_apply in one launch (training forward); see ghnd_bn_finalize_apply."""
+    n, h, w, c = x.shape
+    call("ghnd_bn_finalize_apply", ptr(x), fmt_of(x.dtype), ptr(y), fmt_of(y.dtype), ptr(y2),
+         fmt_of(y2.dtype) if y2 is not None else 0, n * h * w, c, int(bool(relu)), ptr(sums), int(count),
+         ptr(gamma), ptr(beta), float(eps), float(momentum), ptr(running_mean), ptr(running_var), ptr(nbt),
+         ptr(scale_shift), ptr(mean_invstd), stream_ptr())
+    _count()
+    return y
+
+
 def convert16(x, y):
     call("ghnd_convert16", ptr(x), fmt_of(x.dtype), ptr(y), fmt_of(y.dtype), x.numel(), stream_ptr())
     _count()
@@ -553,7 +565,7 @@ def bn_bwd_apply(dy, x, dx, gamma, scale_shift, mean_invstd, relu, sums, dgamma,
         call("ghnd_bn_bwd_apply", ptr(dy), fmt_of(dy.dtype), ptr(x), fmt_of(x.dtype), ptr(dx),
              fmt_of(dx.dtype), 0, n, h * w, c, ptr(gamma), ptr(scale_shift), ptr(mean_invstd),
              int(bool(relu)), ptr(sums), ptr(dgamma), ptr(dbeta), stream_ptr())
-    _count(2)
+    _count(2 if planar else 1)
     return dx
 
 

@@ -297,6 +297,15 @@ int ghnd_bn_eval_params(int C, const float* gamma, const float* beta, const floa
  * gradients. */
 int ghnd_bn_apply(const void* x, int x_fmt, void* y, int y_fmt, void* y2, int y2_fmt, int64_t npix,
                   int C, const float* scale_shift, int relu, void* stream);
+/* ghnd_bn_finalize + ghnd_bn_apply as ONE launch (training forward of nn.BatchNorm2d,
+ * src/models/mimic/resnet_layer.py:43-64): every thread derives scale / shift of its channels from
+ * the batch sums; block 0 also writes scale_shift / mean_invstd (for the backward kernels) and
+ * updates running_mean / running_var / num_batches_tracked exactly like ghnd_bn_finalize. */
+int ghnd_bn_finalize_apply(const void* x, int x_fmt, void* y, int y_fmt, void* y2, int y2_fmt,
+                           int64_t npix, int C, int relu, const double* sums, int64_t count,
+                           const float* gamma, const float* beta, float eps, float momentum,
+                           float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                           float* scale_shift, float* mean_invstd, void* stream);
 /* 16-bit format conversion (fp16 <-> bf16), n elements (multiple of 8) */
 int ghnd_convert16(const void* x, int x_fmt, void* y, int y_fmt, int64_t n, void* stream);
 /* backward, pass 1: sums[2C] = { sum g', sum g'*xhat } with g' = dy * (relu ? (x*scale+shift>0):1) */

@@ -395,6 +395,16 @@ def test_bn_train_fwd_bwd(ops, C, relu):
     back = torch.empty_like(yd)
     assert rel(ops.convert16(yd2, back).float(), yd2.float()) < 1e-3
     assert rel(rmd.cpu(), rm) < 1e-5 and rel(rvd.cpu(), rv) < 1e-5 and int(nbt) == 1
+    # the one-launch finalize+apply must reproduce the two-launch sequence bit for bit
+    ss2, mi2 = torch.empty_like(ss), torch.empty_like(mi)
+    rm2, rv2 = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    nbt2 = torch.zeros((), dtype=torch.long, device="cuda")
+    yf, yf2 = torch.empty_like(yd), torch.empty_like(yd2)
+    ops.bn_finalize_apply(xd, yf, relu, sums, N * H * W, gamma.cuda(), beta.cuda(), 1e-5, 0.1, rm2, rv2, nbt2,
+                          ss2, mi2, y2=yf2)
+    assert torch.equal(yf, yd) and torch.equal(yf2, yd2)
+    assert torch.equal(ss2, ss) and torch.equal(mi2, mi)
+    assert torch.equal(rm2, rmd) and torch.equal(rv2, rvd) and int(nbt2) == 1
     dyd = ops.to_nhwc16(dy.cuda(), torch.bfloat16)
     dxd = torch.empty((N, H, W, C), dtype=torch.bfloat16, device="cuda")
     dg, db = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
