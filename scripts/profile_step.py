@@ -3,6 +3,7 @@
 the step in launch order (description, launches, FLOPs) so the ncu launch list can be joined to
 layers by scripts/join_launches.py.  Usage: python scripts/profile_step.py [batch]"""
 import json, os, sys
+os.environ.setdefault("GHND_SIDE_STREAM", "0")  # ncu serialises kernels anyway; keeps plan runs in one ordered stream
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import bench
