@@ -397,3 +397,52 @@ def test_mask_rcnn_uses_the_same_hot_path(env):
         losses.append(box(images, targets_for(images)).item())
     # same kernels on the same tensors; fp32/fp64 atomics make the last digits run-dependent
     assert abs(losses[0] - losses[1]) <= 1e-4 * abs(losses[0]), losses
+
+
+def test_full_size_step_properties(env):
+    """BASELINE configs[1] geometry (800x1333, batch 2 to keep the test short): the loss must equal
+    the factor-weighted sum of its per-level terms, every term must agree with torch's own fp64
+    reduction of the plan's feature tensors (checksum of the loss kernel at full size), all 25
+    gradients finite and non-zero, BN running statistics updated, and a second identical step must
+    give the same loss to accumulation-order noise."""
+    from hnd_ghnd_object_detectors_b200.tool import DistillationBox
+    models, mu = env["models"], env["module_util"]
+    dev = torch.device("cuda")
+    teacher = models.get_model(model_config("teacher", min_size=800, max_size=1333), dev)
+    student = models.get_model(model_config("student", min_size=800, max_size=1333), dev)
+    teacher.load_state_dict(env["t_sd"], strict=False)
+    student.load_state_dict(env["s_sd"], strict=False)
+    mu.freeze_module_params(teacher)
+    for path in model_config("student")["frozen_modules"]:
+        mu.freeze_module_params(mu.get_module(student, path))
+    teacher.eval()
+    student.train()
+    teacher.distill_backbone_only = student.distill_backbone_only = True
+    box = DistillationBox(teacher, student, criterion_config())
+    g = torch.Generator().manual_seed(5)
+    images = [torch.rand(3, 800, 1333, generator=g).cuda() for _ in range(2)]
+    rm0 = student.backbone.body.layer1.decoder[10].running_mean.clone()
+    loss = box(images, targets_for(images))
+    loss.backward()
+    torch.cuda.synchronize()
+    plan = list(box._plans.values())[0]
+    assert (plan.Hp, plan.Wp) == (800, 1344)
+    terms = box.last_terms.double().cpu()
+    assert abs(float(terms[0]) - float(terms[1:].sum())) <= 1e-6 * float(terms[0])
+    assert abs(loss.item() - float(terms[0])) <= 1e-6 * float(terms[0])
+    for i, lv in enumerate(LEVELS):
+        t, s_ = plan.feat_t[lv], plan.feat_s[lv]
+        assert tuple(t.shape) == tuple(s_.shape) and t.shape[0] == 2
+        ref = float(((t.double() - s_.double()) ** 2).sum())
+        assert abs(float(terms[1 + i]) - ref) <= 1e-5 * ref, (lv, float(terms[1 + i]), ref)
+    n = 0
+    for name, p in student.named_parameters():
+        if p.requires_grad:
+            n += 1
+            assert p.grad is not None and bool(torch.isfinite(p.grad).all()), name
+            if not name.endswith(ZERO_GRADS):
+                assert float(p.grad.abs().max()) > 0, name
+    assert n == 25
+    assert not torch.equal(student.backbone.body.layer1.decoder[10].running_mean, rm0)
+    loss2 = box(images, targets_for(images))
+    assert abs(loss2.item() - loss.item()) <= 1e-4 * loss.item()

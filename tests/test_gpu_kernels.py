@@ -171,6 +171,59 @@ def test_sse_loss(ops, dtype):
     assert abs(float(out[0]) - tot) <= 1e-5 * tot
 
 
+def test_sse_loss_full_size_properties(ops):
+    """The loss kernel at the full GHND size (4 images of 800x1333: 129 M elements over the 4 levels)
+    through size-independent properties instead of a CPU oracle:
+      * known answer: student = teacher + c (c exactly representable) -> term = factor * c^2 * numel,
+        gradient = 2 * factor * c everywhere (ReLU mask on the top level: the student is > 0);
+      * linearity in the factor and additivity over levels;
+      * agreement with torch's own fp64 reduction of the same device tensors."""
+    N = 4
+    shapes = [(N, 200, 336, 256), (N, 100, 168, 512), (N, 50, 84, 1024), (N, 25, 42, 2048)]
+    cs = [0.5, -0.25, 1.0, 2.0]
+    factors = [1.0, 0.5, 2.0, 3.0]
+    g0 = torch.Generator(device="cuda").manual_seed(3)
+    levels, levels2 = [], []
+    for sh, c, f in zip(shapes, cs, factors):
+        t = (torch.rand(sh, device="cuda", generator=g0) * 4 + 3).half()  # in [3, 7): t + c > 0, exact in fp16
+        t = (t * 4).round() / 4  # multiples of 1/4 so that t + c is exact
+        s_ = (t + c).half()
+        g = torch.empty(sh, dtype=torch.bfloat16, device="cuda")
+        levels.append((t, s_, g, f, sh[-1] == 2048))
+        levels2.append((t, s_, None, 2 * f, sh[-1] == 2048))
+    out = ops.sse_fwd_bwd(levels).double().cpu()
+    out2 = ops.sse_fwd_bwd(levels2).double().cpu()
+    total = 0.0
+    for i, (sh, c, f) in enumerate(zip(shapes, cs, factors)):
+        numel = float(np.prod(sh))
+        want = f * c * c * numel
+        assert abs(float(out[1 + i]) - want) <= 1e-6 * want, (i, float(out[1 + i]), want)
+        assert abs(float(out2[1 + i]) - 2 * want) <= 1e-6 * want  # linear in the factor
+        g = levels[i][2]
+        assert float(g.float().min()) == float(g.float().max()) == 2 * f * c  # exact in bf16
+        t, s_ = levels[i][0], levels[i][1]
+        ref = float(((t.double() - s_.double()) ** 2).sum()) * f
+        assert abs(float(out[1 + i]) - ref) <= 1e-6 * ref
+        total += want
+    assert abs(float(out[0]) - total) <= 1e-6 * total  # additive over levels
+
+
+def test_quantizer_full_size_round_trip(ops):
+    """quantize -> dequantize at the largest encode batch (64 x 3 x 204 x 340): every element comes
+    back within half a quantization step (plus one fp32 ulp of the scaled value), the extremes map
+    to 0 and 255, and the bytes are monotone in the input -- properties that hold at any size."""
+    x = torch.randn(64, 3, 204, 340, device="cuda", generator=torch.Generator(device="cuda").manual_seed(9)) * 3
+    q, qp = ops.quantize_u8(x)
+    back = ops.dequantize_u8(q, qp)
+    scale = float(qp[0:1].view(torch.float32))
+    err = (back - x).abs().max().item()
+    assert err <= 0.5 * scale * (1 + 1e-4) + 1e-5, (err, scale)
+    assert int(q.min()) == 0 and int(q.max()) == 255
+    flat_x, flat_q = x.flatten()[:1 << 20], q.flatten()[:1 << 20]
+    order = torch.argsort(flat_x)
+    assert bool((flat_q[order][1:].int() - flat_q[order][:-1].int() >= 0).all())
+
+
 def test_layout_roundtrip(ops):
     x = torch.randn(2, 70, 9, 13).cuda()
     y = ops.to_nhwc16(x, torch.float16)
