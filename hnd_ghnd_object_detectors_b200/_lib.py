@@ -32,7 +32,8 @@ class ConvDesc(Structure):
                 ("src", c_void_p), ("src_fmt", c_int), ("weights", c_void_p), ("w_fmt", c_int),
                 ("dst", c_void_p), ("dst_fmt", c_int), ("bias", c_void_p), ("residual", c_void_p),
                 ("res_fmt", c_int), ("relu", c_int), ("mask", c_void_p), ("mask_fmt", c_int),
-                ("accumulate", c_int), ("stats", c_void_p)]
+                ("accumulate", c_int), ("stats", c_void_p), ("stats_mode", c_int),
+                ("mask_stats_only", c_int)]
 
 
 class WgradDesc(Structure):
@@ -101,6 +102,7 @@ SIGNATURES = {
     "ghnd_convert16": (_I, [_P, _I, _P, _I, _L, _P]),
     "ghnd_bn_bwd_reduce": (_I, [_P, _I, _P, _I, _I, _I, _L, _I, _P, _P, _I, _P, _P]),
     "ghnd_bn_bwd_apply": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _L, _I, _P, _P, _P, _I, _P, _P, _P, _P]),
+    "ghnd_bn_bwd_apply_fused_sums": (_I, [_P, _I, _P, _I, _P, _I, _I, _L, _I, _P, _P, _P, _I, _P, _P, _P, _P]),
     "ghnd_adam_step": (_I, [_P, _P, _P, _P, _L, c_double, c_double, c_double, c_double, c_double, c_double, _I, _P]),
 }
 

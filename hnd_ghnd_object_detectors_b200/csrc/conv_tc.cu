@@ -86,6 +86,8 @@ struct ConvKernelParams {
   int out_fmt, in0_fmt, in1_fmt;
   int relu;
   double* stats;    // optional [2*cout]: sum / sum of squares of the stored (rounded) output
+  int stats_mode;   // 1: sum of the output, sum of output * in1 operand (BN backward reductions)
+  int in1_mask;     // 0: the in1 operand is only read by the statistics
 };
 
 __device__ __forceinline__ int fd_ring_r(const ConvKernelParams& p, uint32_t cnt) {
@@ -205,6 +207,34 @@ __device__ __forceinline__ void epi_stats_rows(const uint8_t* base, int quarter,
       s1 += f.y;
       q0 = fmaf(f.x, f.x, q0);
       q1 = fmaf(f.y, f.y, q1);
+    }
+  }
+  atomicAdd(&sstat[ch + 2 * lane], s0);
+  atomicAdd(&sstat[ch + 2 * lane + 1], s1);
+  atomicAdd(&sstat[cout + ch + 2 * lane], q0);
+  atomicAdd(&sstat[cout + ch + 2 * lane + 1], q1);
+}
+
+// BN-backward variant: sum of the staged output g and of g * a, a = the in1 operand tile (same
+// swizzled layout, its own 16-bit format).
+template <int FMT, int AFMT>
+__device__ __forceinline__ void epi_stats2_rows(const uint8_t* base, const uint8_t* abase, int quarter,
+                                                int lane, uint32_t valid, float* sstat, int ch,
+                                                int cout) {
+  float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 8
+  for (int i = 0; i < 32; ++i) {
+    const int r = quarter * 32 + i;
+    const uint32_t off = r * 128 + ((((lane >> 2) ^ (r & 7))) << 4) + ((lane & 3) << 2);
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(base + off);
+    const uint32_t a = *reinterpret_cast<const uint32_t*>(abase + off);
+    if ((valid >> i) & 1u) {
+      const float2 f = unpack2_t<FMT>(w);
+      const float2 g = unpack2_t<AFMT>(a);
+      s0 += f.x;
+      s1 += f.y;
+      q0 = fmaf(f.x, g.x, q0);
+      q1 = fmaf(f.y, g.y, q1);
     }
   }
   atomicAdd(&sstat[ch + 2 * lane], s0);
@@ -475,8 +505,8 @@ __global__ void __launch_bounds__(kConvThreads, 1)
 #pragma unroll
           for (int j = 0; j < 64; ++j) v[j] = fmaxf(v[j], 0.f);
         }
-        if (p.has_in1) {
-          const uint8_t* m_base = in_base + p.has_in0 * kChunkBytes;
+        const uint8_t* m_base = in_base + p.has_in0 * kChunkBytes;
+        if (p.has_in1 && p.in1_mask) {
           if (p.in1_fmt == GHND_F16) epi_mask_rows<GHND_F16>(v, m_base, row);
           else epi_mask_rows<GHND_BF16>(v, m_base, row);
         }
@@ -484,7 +514,9 @@ __global__ void __launch_bounds__(kConvThreads, 1)
           if (p.in0_fmt == GHND_F16) epi_add_rows<GHND_F16>(v, in_base, row);
           else epi_add_rows<GHND_BF16>(v, in_base, row);
         }
-        if (n_in > 0) mbar_arrive(&iempty_bar[slot]);  // operand buffer consumed
+        // operand buffer consumed (the BN-backward statistics still read the in1 tile below)
+        const bool late_release = p.stats != nullptr && p.stats_mode == 1;
+        if (n_in > 0 && !late_release) mbar_arrive(&iempty_bar[slot]);
         // ---- stage the 64-channel rows and store them with one TMA tensor store ----
         if (etid == 0) bulk_wait_read<0>();  // the store that used this staging buffer has drained
         named_bar_sync(bar_id, kEpiGroupThreads);
@@ -497,10 +529,24 @@ __global__ void __launch_bounds__(kConvThreads, 1)
           bulk_commit();
         }
         if (p.stats != nullptr) {
-          if (p.out_fmt == GHND_F16)
+          if (p.stats_mode == 1) {
+            if (p.out_fmt == GHND_F16) {
+              if (p.in1_fmt == GHND_F16)
+                epi_stats2_rows<GHND_F16, GHND_F16>(o_base, m_base, quarter, lane, valid, sstat, ch, p.cout);
+              else
+                epi_stats2_rows<GHND_F16, GHND_BF16>(o_base, m_base, quarter, lane, valid, sstat, ch, p.cout);
+            } else {
+              if (p.in1_fmt == GHND_F16)
+                epi_stats2_rows<GHND_BF16, GHND_F16>(o_base, m_base, quarter, lane, valid, sstat, ch, p.cout);
+              else
+                epi_stats2_rows<GHND_BF16, GHND_BF16>(o_base, m_base, quarter, lane, valid, sstat, ch, p.cout);
+            }
+            mbar_arrive(&iempty_bar[slot]);  // now the operand buffer may be refilled
+          } else if (p.out_fmt == GHND_F16) {
             epi_stats_rows<GHND_F16>(o_base, quarter, lane, valid, sstat, ch, p.cout);
-          else
+          } else {
             epi_stats_rows<GHND_BF16>(o_base, quarter, lane, valid, sstat, ch, p.cout);
+          }
         }
       }
     }
@@ -700,6 +746,8 @@ static int finish_launch(ConvLaunch* L, const ghnd_conv_desc_t* d, int gemm_cin,
   p.out_fmt = d->dst_fmt;
   p.relu = d->relu;
   p.stats = d->stats;
+  p.stats_mode = d->stats != nullptr ? d->stats_mode : 0;
+  p.in1_mask = (d->mask != nullptr && !(d->stats != nullptr && d->stats_mode == 1 && d->mask_stats_only)) ? 1 : 0;
   // shared-memory split: >= 3 pipeline stages first, then the operand ring (deep enough to keep
   // ~64 KB of residual / mask loads in flight per SM), the rest goes to more stages
   const int fixed = 2 * kChunkBytes + (d->bias ? gemm_cout * 4 : 0) + (d->stats ? gemm_cout * 8 : 0);
@@ -789,8 +837,16 @@ int ghnd_conv_plan_create(const ghnd_conv_desc_t* d, ghnd_conv_plan_t** out) {
                  "mixed f16 x bf16 operands on sm_100a)");
   GHND_CHECK_ARG(!d->residual || fmt_ok(d->res_fmt), "conv: bad residual format");
   GHND_CHECK_ARG(!d->mask || fmt_ok(d->mask_fmt), "conv: bad mask format");
-  GHND_CHECK_ARG(d->stats == nullptr || (d->kind == GHND_CONV_FWD && d->stride == 1 && d->K <= 1024),
-                 "conv: fused statistics need a stride-1 forward conv with K <= 1024");
+  GHND_CHECK_ARG(d->stats == nullptr || d->stats_mode == 0 || d->stats_mode == 1, "conv: bad stats_mode %d",
+                 d->stats_mode);
+  GHND_CHECK_ARG(d->stats == nullptr || d->stats_mode != 0 ||
+                     (d->kind == GHND_CONV_FWD && d->stride == 1 && d->K <= 1024),
+                 "conv: fused output statistics need a stride-1 forward conv with K <= 1024");
+  GHND_CHECK_ARG(d->stats == nullptr || d->stats_mode != 1 ||
+                     (d->stride == 1 && d->mask != nullptr && !d->accumulate &&
+                      (d->kind == GHND_CONV_FWD ? d->K : d->C) <= 1024),
+                 "conv: BN-backward statistics need a stride-1 launch with a mask operand, no "
+                 "accumulate and <= 1024 output channels");
   GHND_CHECK_ARG(((uintptr_t)d->src % 16) == 0 && ((uintptr_t)d->weights % 16) == 0 &&
                      ((uintptr_t)d->dst % 16) == 0 && ((uintptr_t)d->residual % 16) == 0 &&
                      ((uintptr_t)d->mask % 16) == 0 && ((uintptr_t)d->bias % 16) == 0,

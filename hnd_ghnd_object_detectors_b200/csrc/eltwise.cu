@@ -645,15 +645,25 @@ __global__ void __launch_bounds__(256)
                              const float* __restrict__ scale_shift,
                              const float* __restrict__ mean_invstd,
                              const double* __restrict__ sums, float* __restrict__ dgamma,
-                             float* __restrict__ dbeta) {
+                             float* __restrict__ dbeta, int sums_mode) {
   constexpr int U = 2;
   const int cg = threadIdx.x % C8;
   const int C = C8 * 8;
+  // sum g'*xhat of channel c.  sums_mode 0: sums[C+c] is that sum.  sums_mode 1 (reductions fused
+  // into the producing dgrad, which only sees the post-BN activation a = sc*x + sf): sums[C+c] =
+  // sum g'*a, and (x - mu)*is = (a - sf - mu*sc) * is/sc, all in fp64 (the two terms cancel).
+  auto sum_gxhat = [&](int c) -> double {
+    const double s2 = sums[C + c];
+    if (sums_mode == 0) return s2;
+    const double scd = (double)__ldg(scale_shift + c), sfd = (double)__ldg(scale_shift + C + c);
+    const double mud = (double)__ldg(mean_invstd + c), isd = (double)__ldg(mean_invstd + C + c);
+    return (isd / scd) * (s2 - (sfd + mud * scd) * sums[c]);
+  };
   // parameter gradients are the two sums themselves: block 0 copies them out (was a separate launch)
   if (blockIdx.x == 0)
     for (int c = threadIdx.x; c < C; c += 256) {
       if (dbeta != nullptr) dbeta[c] = (float)sums[c];
-      if (dgamma != nullptr) dgamma[c] = (float)sums[C + c];
+      if (dgamma != nullptr) dgamma[c] = (float)sum_gxhat(c);
     }
   // dx = sc*(g' - mg - xhat*mgx) with xhat = (x-mu)*is  ==  sc*g' + x*k1 + k0
   float sc[8], sf[8], k1[8], k0[8];
@@ -663,7 +673,7 @@ __global__ void __launch_bounds__(256)
     sc[j] = __ldg(scale_shift + c);
     sf[j] = __ldg(scale_shift + C + c);
     const float mu = __ldg(mean_invstd + c), is = __ldg(mean_invstd + C + c);
-    const float mg = (float)sums[c] * inv_count, mgx = (float)sums[C + c] * inv_count;
+    const float mg = (float)sums[c] * inv_count, mgx = (float)sum_gxhat(c) * inv_count;
     k1[j] = -sc[j] * is * mgx;
     k0[j] = sc[j] * (mu * is * mgx - mg);
   }
@@ -1144,12 +1154,16 @@ int ghnd_bn_bwd_reduce(const void* dy, int dy_fmt, const void* x, int x_fmt, int
   return GHND_OK;
 }
 
-int ghnd_bn_bwd_apply(const void* dy, int dy_fmt, const void* x, int x_fmt, void* dx, int dx_fmt,
-                      int planar, int N, int64_t hw, int C, const float* gamma,
-                      const float* scale_shift, const float* mean_invstd, int relu,
-                      const double* sums, float* dgamma, float* dbeta, void* stream) {
+static int bn_bwd_apply_impl(const void* dy, int dy_fmt, const void* x, int x_fmt, void* dx, int dx_fmt,
+                             int planar, int N, int64_t hw, int C, const float* gamma,
+                             const float* scale_shift, const float* mean_invstd, int relu,
+                             const double* sums, float* dgamma, float* dbeta, int sums_mode,
+                             void* stream) {
   GHND_CHECK_ARG(dy && x && dx && scale_shift && mean_invstd && sums && N > 0 && hw > 0,
                  "bn_bwd_apply: bad argument");
+  GHND_CHECK_ARG(sums_mode == 0 || (sums_mode == 1 && !planar && x_fmt == GHND_F16 &&
+                                    dy_fmt == GHND_BF16 && dx_fmt == GHND_BF16),
+                 "bn_bwd_apply: sums_mode 1 needs the NHWC f16-activation / bf16-gradient path");
   GHND_CHECK_ARG(bn_geom_ok(planar, C), "bn_bwd_apply: unsupported channel count %d", C);
   cudaStream_t st = (cudaStream_t)stream;
   const double inv_count = 1.0 / ((double)N * (double)hw);
@@ -1166,11 +1180,11 @@ int ghnd_bn_bwd_apply(const void* dy, int dy_fmt, const void* x, int x_fmt, void
       if (relu)
         bn_bwd_apply_fast_kernel<GHND_F16, GHND_BF16, true><<<grid, 256, 0, st>>>(
             (const uint4*)dy, (const uint4*)x, (uint4*)dx, nvec, C / 8, (float)inv_count, scale_shift,
-            mean_invstd, sums, dgamma, dbeta);
+            mean_invstd, sums, dgamma, dbeta, sums_mode);
       else
         bn_bwd_apply_fast_kernel<GHND_F16, GHND_BF16, false><<<grid, 256, 0, st>>>(
             (const uint4*)dy, (const uint4*)x, (uint4*)dx, nvec, C / 8, (float)inv_count, scale_shift,
-            mean_invstd, sums, dgamma, dbeta);
+            mean_invstd, sums, dgamma, dbeta, sums_mode);
       GHND_LAUNCH_CHECK("bn_bwd_apply_fast_kernel");
       return GHND_OK;  // dgamma / dbeta written by the kernel's block 0
     } else {
@@ -1185,6 +1199,23 @@ int ghnd_bn_bwd_apply(const void* dy, int dy_fmt, const void* x, int x_fmt, void
     GHND_LAUNCH_CHECK("bn_param_grads_kernel");
   }
   return GHND_OK;
+}
+
+int ghnd_bn_bwd_apply(const void* dy, int dy_fmt, const void* x, int x_fmt, void* dx, int dx_fmt,
+                      int planar, int N, int64_t hw, int C, const float* gamma,
+                      const float* scale_shift, const float* mean_invstd, int relu,
+                      const double* sums, float* dgamma, float* dbeta, void* stream) {
+  return bn_bwd_apply_impl(dy, dy_fmt, x, x_fmt, dx, dx_fmt, planar, N, hw, C, gamma, scale_shift,
+                           mean_invstd, relu, sums, dgamma, dbeta, 0, stream);
+}
+
+int ghnd_bn_bwd_apply_fused_sums(const void* dy, int dy_fmt, const void* x, int x_fmt, void* dx,
+                                 int dx_fmt, int N, int64_t hw, int C, const float* gamma,
+                                 const float* scale_shift, const float* mean_invstd, int relu,
+                                 const double* sums, float* dgamma, float* dbeta, void* stream) {
+  GHND_CHECK_ARG(fast_c8(C), "bn_bwd_apply_fused_sums: unsupported channel count %d", C);
+  return bn_bwd_apply_impl(dy, dy_fmt, x, x_fmt, dx, dx_fmt, 0, N, hw, C, gamma, scale_shift,
+                           mean_invstd, relu, sums, dgamma, dbeta, 1, stream);
 }
 
 int ghnd_pack_weight(const float* w_oihw, const float* scale_o, int O, int I, int R, int S,

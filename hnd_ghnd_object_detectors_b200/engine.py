@@ -22,6 +22,15 @@ import torch
 from . import _lib, ops
 from ._lib import CONV_DGRAD, CONV_FWD
 
+import os
+
+# GHND_FUSE_BN_REDUCE=1: take the BN-backward reductions inside the producing dgrad's epilogue
+# (ConvPlan stats_mode 1) instead of a separate bn_bwd_reduce pass.  Off by default: an A/B on the
+# B200 gave the same step time (655.5 vs 655.6 img/s) -- the small streaming reduce kernels already
+# run concurrently with the persistent tensor-core kernels of the second stream -- and the fused
+# form divides by gamma (undefined for a channel whose gamma is exactly 0).
+FUSE_BN_REDUCE = os.environ.get("GHND_FUSE_BN_REDUCE", "0") == "1"
+
 LEVELS = ("layer1", "layer2", "layer3", "layer4")
 PLANES = {"layer1": 64, "layer2": 128, "layer3": 256, "layer4": 512}
 IMAGE_MEAN = (0.485, 0.456, 0.406)
@@ -303,6 +312,7 @@ class _WideUnit(object):
         pad = conv.padding[0]
         self.conv, self.relu, self.x, self.x_g = conv, relu, x, x_g
         self.prepacked = False
+        self.reduce_fused = False
         self.N, self.H, self.W, self.C, self.K, self.pad = N, H, W, C, K, pad
         self.Ho, self.Wo = H + 2 * pad - R + 1, W + 2 * pad - S + 1
         self.train = train
@@ -343,9 +353,12 @@ class _WideUnit(object):
             ops.pack_weight(self.conv.weight, self.bn.scale_shift[:self.K], False, out=self.w)
             self.plan.run()
 
-    def plan_backward(self, g_out, g_x, grads, names, grad_dtype):
+    def plan_backward(self, g_out, g_x, grads, names, grad_dtype, below=None):
         """g_out: gradient w.r.t. self.out; g_x: gradient buffer for the input (None: not needed);
-        grads: dict name -> fp32 grad view; names = (conv.weight, bn.weight, bn.bias)."""
+        grads: dict name -> fp32 grad view; names = (conv.weight, bn.weight, bn.bias).
+        below = (activation, relu, sums): the BatchNorm whose output is this unit's input.  Its
+        backward reductions (sum g', sum g'*activation) are then taken in this unit's dgrad epilogue
+        (the activation tile doubles as the ReLU mask), and `below` skips its bn_bwd_reduce pass."""
         dev = g_out.device
         N, H, W, C, K = self.N, self.H, self.W, self.C, self.K
         R, S = self.conv.weight.shape[2:]
@@ -358,7 +371,12 @@ class _WideUnit(object):
         self.dgrad = None
         if g_x is not None:
             self.wt = _empty((C, R, S, K), grad_dtype, dev)
-            self.dgrad = ops.ConvPlan(CONV_DGRAD, N, H, W, C, K, R, S, 1, self.pad, self.g_raw, self.wt, g_x)
+            if below is not None and FUSE_BN_REDUCE:
+                act, relu, sums = below
+                self.dgrad = ops.ConvPlan(CONV_DGRAD, N, H, W, C, K, R, S, 1, self.pad, self.g_raw, self.wt,
+                                          g_x, mask=act, stats=sums, stats_mode=1, mask_stats_only=not relu)
+            else:
+                self.dgrad = ops.ConvPlan(CONV_DGRAD, N, H, W, C, K, R, S, 1, self.pad, self.g_raw, self.wt, g_x)
 
     def _wgrad(self):
         self.wgrad.run()
@@ -366,9 +384,10 @@ class _WideUnit(object):
 
     def backward(self, side=None):
         bn = self.bn
-        ops.bn_bwd_reduce(self.g_out, self.raw, bn.scale_shift, bn.mean_invstd, self.relu, bn.sums)
+        if not self.reduce_fused:  # else: the dgrad that produced g_out already left the sums
+            ops.bn_bwd_reduce(self.g_out, self.raw, bn.scale_shift, bn.mean_invstd, self.relu, bn.sums)
         ops.bn_bwd_apply(self.g_out, self.raw, self.g_raw, bn.bn.weight, bn.scale_shift, bn.mean_invstd,
-                         self.relu, bn.sums, self.dgamma, self.dbeta)
+                         self.relu, bn.sums, self.dgamma, self.dbeta, fused_sums=self.reduce_fused)
         if side is not None:  # dW next to the dgrad chain (reads g_raw / x_g only)
             side.fork()
             side.run(self._wgrad)
@@ -471,9 +490,16 @@ class StudentLayer1Runner(object):
         e, d = prefix + "encoder.encoder.", prefix + "decoder."
         g = lambda u: _empty((N, u.H, u.W, u.C), gd, dev)
         self.g_d7out, self.g_d4out, self.g_act3 = g(self.d9), g(self.d7), g(self.d4)
-        self.d9.plan_backward(g_out, self.g_d7out, grads, (d + "9.weight", d + "10.weight", d + "10.bias"), gd)
-        self.d7.plan_backward(self.g_d7out, self.g_d4out, grads, (d + "7.weight", d + "8.weight", d + "8.bias"), gd)
-        self.d4.plan_backward(self.g_d4out, self.g_act3, grads, (d + "4.weight", d + "5.weight", d + "5.bias"), gd)
+        def below(u):  # the BN under a unit's input, for the fused backward reductions
+            return (u.out, u.relu, u.bn.sums)
+        fuse = FUSE_BN_REDUCE
+        self.d9.plan_backward(g_out, self.g_d7out, grads, (d + "9.weight", d + "10.weight", d + "10.bias"), gd,
+                              below=below(self.d7))
+        self.d7.plan_backward(self.g_d7out, self.g_d4out, grads, (d + "7.weight", d + "8.weight", d + "8.bias"), gd,
+                              below=below(self.d4))
+        self.d4.plan_backward(self.g_d4out, self.g_act3, grads, (d + "4.weight", d + "5.weight", d + "5.bias"), gd,
+                              below=(self.act3, False, self.bn3.sums))
+        self.d7.reduce_fused = self.d4.reduce_fused = self.bn3_reduce_fused = fuse
         self.g_raw3 = _empty((N, self.H3, self.W3, 64), gd, dev)
         self.g_zact = _empty(tuple(self.z.shape), torch.float32, dev)  # grad wrt relu(bn0(z))
         self.g_z = _empty(tuple(self.z.shape), torch.float32, dev)
@@ -483,9 +509,12 @@ class StudentLayer1Runner(object):
         self.names = (e, d)
         self.g_e2out, self.g_e1out, self.g_e0out = g_like(self.e2, gd, dev), g_like(self.e1, gd, dev), g_like(self.e0, gd, dev)
         self.g_x = _empty((N, self.H, self.W, 64), gd, dev) if need_gx else None
-        self.e2.plan_backward(self.g_e2out, self.g_e1out, grads, (e + "5.weight", e + "6.weight", e + "6.bias"), gd)
-        self.e1.plan_backward(self.g_e1out, self.g_e0out, grads, (e + "2.weight", e + "3.weight", e + "3.bias"), gd)
+        self.e2.plan_backward(self.g_e2out, self.g_e1out, grads, (e + "5.weight", e + "6.weight", e + "6.bias"), gd,
+                              below=below(self.e1))
+        self.e1.plan_backward(self.g_e1out, self.g_e0out, grads, (e + "2.weight", e + "3.weight", e + "3.bias"), gd,
+                              below=below(self.e0))
         self.e0.plan_backward(self.g_e0out, self.g_x, grads, (e + "0.weight", e + "1.weight", e + "1.bias"), gd)
+        self.e1.reduce_fused = self.e0.reduce_fused = fuse
 
     def wide_units(self):
         return (self.e0, self.e1, self.e2, self.d4, self.d7, self.d9)
@@ -501,9 +530,11 @@ class StudentLayer1Runner(object):
         self.d4.backward(side)
         # BN dec[3] (no ReLU) on raw3
         b3 = self.bn3
-        ops.bn_bwd_reduce(self.g_act3, self.raw3, b3.scale_shift, b3.mean_invstd, False, b3.sums)
+        if not self.bn3_reduce_fused:
+            ops.bn_bwd_reduce(self.g_act3, self.raw3, b3.scale_shift, b3.mean_invstd, False, b3.sums)
         ops.bn_bwd_apply(self.g_act3, self.raw3, self.g_raw3, b3.bn.weight, b3.scale_shift, b3.mean_invstd,
-                         False, b3.sums, self.gr[d + "3.weight"], self.gr[d + "3.bias"])
+                         False, b3.sums, self.gr[d + "3.weight"], self.gr[d + "3.bias"],
+                         fused_sums=self.bn3_reduce_fused)
         # dec2 (narrow-in conv on relu(bn0(z)))
         bz = self.bnz
         ops.wgrad_narrow(self.z, self.g_raw3, self.gr[d + "2.weight"], False, 2, 2, 0, pre=bz.scale_shift,

@@ -159,7 +159,8 @@ class ConvPlan(object):
     """ghnd_conv_plan: tcgen05 implicit-GEMM conv forward / dgrad bound to fixed buffers."""
 
     def __init__(self, kind, N, H, W, C, K, R, S, stride, pad, src, weights, dst, bias=None,
-                 residual=None, relu=False, mask=None, accumulate=False, stats=None):
+                 residual=None, relu=False, mask=None, accumulate=False, stats=None, stats_mode=0,
+                 mask_stats_only=False):
         d = _lib.ConvDesc()
         d.kind = kind
         d.N, d.H, d.W, d.C, d.K, d.R, d.S, d.stride, d.pad = N, H, W, C, K, R, S, stride, pad
@@ -176,6 +177,8 @@ class ConvPlan(object):
         if stats is not None:
             assert stats.dtype == torch.float64 and stats.numel() >= 2 * (K if kind == _lib.CONV_FWD else C)
         d.stats = stats.data_ptr() if stats is not None else None
+        d.stats_mode = int(stats_mode)
+        d.mask_stats_only = int(bool(mask_stats_only))
         self._keep = (src, weights, dst, bias, residual, mask, stats)  # buffers must outlive the plan
         self.desc = "%s N%d %dx%d C%d K%d %dx%d s%d p%d%s%s%s%s" % (
             "fwd" if kind == _lib.CONV_FWD else "dgrad", N, H, W, C, K, R, S, stride, pad,
@@ -554,7 +557,18 @@ def bn_bwd_reduce(dy, x, scale_shift, mean_invstd, relu, sums, planar=False):
     return sums
 
 
-def bn_bwd_apply(dy, x, dx, gamma, scale_shift, mean_invstd, relu, sums, dgamma, dbeta, planar=False):
+def bn_bwd_apply(dy, x, dx, gamma, scale_shift, mean_invstd, relu, sums, dgamma, dbeta, planar=False,
+                 fused_sums=False):
+    """fused_sums: `sums` = (sum g', sum g'*activation) written by the producing dgrad launch
+    (ConvPlan(stats_mode=1)) instead of by bn_bwd_reduce."""
+    if fused_sums:
+        assert not planar
+        n, h, w, c = x.shape
+        call("ghnd_bn_bwd_apply_fused_sums", ptr(dy), fmt_of(dy.dtype), ptr(x), fmt_of(x.dtype), ptr(dx),
+             fmt_of(dx.dtype), n, h * w, c, ptr(gamma), ptr(scale_shift), ptr(mean_invstd),
+             int(bool(relu)), ptr(sums), ptr(dgamma), ptr(dbeta), stream_ptr())
+        _count(1)
+        return dx
     if planar:
         n, c, h, w = x.shape
         call("ghnd_bn_bwd_apply", ptr(dy), 0, ptr(x), 0, ptr(dx), 0, 1, n, h * w, c, ptr(gamma),

@@ -154,6 +154,14 @@ typedef struct ghnd_conv_desc {
   int mask_fmt;
   int accumulate;
   double* stats; /* optional: [2*channels] sum / sum-of-squares of the stored (rounded) output */
+  /* stats_mode 1 (needs `mask`): stats = sum of dst, sum of dst * mask-operand per channel -- the two
+   * reductions of the BatchNorm backward of the layer that produced the mask operand (its
+   * post-BN/ReLU activation `a`): sum g' and sum g'*a, from which bn_bwd_apply (sums_mode 1) recovers
+   * sum g'*xhat = (sum g'*a - beta * sum g') / gamma.  Lets a dgrad launch absorb the separate
+   * bn_bwd_reduce pass over (g, x) of the previous layer. */
+  int stats_mode;
+  /* 1: the mask operand only feeds the statistics (layer without ReLU); 0: it also masks dst */
+  int mask_stats_only;
 } ghnd_conv_desc_t;
 typedef struct ghnd_conv_plan ghnd_conv_plan_t;
 int ghnd_conv_plan_create(const ghnd_conv_desc_t* desc, ghnd_conv_plan_t** plan);
@@ -318,6 +326,14 @@ int ghnd_bn_bwd_apply(const void* dy, int dy_fmt, const void* x, int x_fmt, void
                       int planar, int N, int64_t hw, int C, const float* gamma,
                       const float* scale_shift, const float* mean_invstd, int relu,
                       const double* sums, float* dgamma, float* dbeta, void* stream);
+/* The same when `sums` were produced by a conv launch with stats_mode 1 (sum g', sum g'*a with a =
+ * the layer's post-BN activation): sum g'*xhat is recovered as (is/sc) * (sum g'*a - (sf + mu*sc) * sum g')
+ * in fp64.  NHWC f16 activations / bf16 gradients only.  Undefined for gamma == 0 (a carries no
+ * information about xhat then). */
+int ghnd_bn_bwd_apply_fused_sums(const void* dy, int dy_fmt, const void* x, int x_fmt, void* dx,
+                                 int dx_fmt, int N, int64_t hw, int C, const float* gamma,
+                                 const float* scale_shift, const float* mean_invstd, int relu,
+                                 const double* sums, float* dgamma, float* dbeta, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused multi-tensor Adam over one flat fp32 parameter/gradient buffer
