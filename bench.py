@@ -164,7 +164,7 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 def conv_plans(plan):
     """Every tcgen05 conv plan (forward / dgrad / stem) one GHND step runs, in no particular order."""
-    out = [plan.t_stem.plan, plan.s_stem.plan]
+    out = [plan.stem2.plan] if plan.stem2 is not None else [plan.t_stem.plan, plan.s_stem.plan]
     for r in list(plan.t_layers.values()) + list(plan.s_layers.values()):
         for b in r.blocks:
             out += list(b.fwd) + list(b.bwd)
@@ -411,9 +411,12 @@ def run_cuda(args):
         units = [l1.e0, l1.e1, l1.e2, l1.d4, l1.d7, l1.d9]
         raw_elems = float(sum(u.raw.numel() for u in units))
         raw3 = float(l1.raw3.numel())
-        conv_elems, pool_elems = float(plan.s_stem.conv.numel()), float(plan.s_stem.out.numel())
+        pool_elems = float(plan.s_stem.out.numel())
+        conv_elems = 4.0 * pool_elems  # one model's 64-channel conv1 output (2x2 the pooled size)
         streaming = {
-            "bn_apply (x -> y f16 + bf16 copy, 6 B/elem)": ("ghnd_bn_apply", 6.0 * (raw_elems + raw3)),
+            "bn_finalize_apply (x -> y f16 [+ bf16 copy where a tensor-core dW reads it], 4-6 B/elem)":
+                ("ghnd_bn_finalize_apply",
+                 sum(u.raw.numel() * (6.0 if u.out_g is not None else 4.0) for u in units) + 6.0 * raw3),
             "bn_bwd_reduce (g, x -> sums, 4 B/elem)": ("ghnd_bn_bwd_reduce", 4.0 * (raw_elems + raw3)),
             "bn_bwd_apply (g, x -> dx, 6 B/elem)": ("ghnd_bn_bwd_apply", 6.0 * (raw_elems + raw3)),
             "maxpool 3x3 s2 fwd, teacher + student (2 B in, 2 B out, +1 B argmax)":

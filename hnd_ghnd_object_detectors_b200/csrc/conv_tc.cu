@@ -1022,9 +1022,17 @@ extern "C" {
 int ghnd_stem_conv_plan_create(const void* x_packed, int x_fmt, const void* w_packed, int w_fmt,
                                const float* bias, void* y, int y_fmt, int N, int Hp, int Wp,
                                ghnd_stem_plan_t** out) {
+  return ghnd_stem_conv_plan_create_k(x_packed, x_fmt, w_packed, w_fmt, bias, y, y_fmt, N, Hp, Wp, 64,
+                                      out);
+}
+
+int ghnd_stem_conv_plan_create_k(const void* x_packed, int x_fmt, const void* w_packed, int w_fmt,
+                                 const float* bias, void* y, int y_fmt, int N, int Hp, int Wp, int K,
+                                 ghnd_stem_plan_t** out) {
   using namespace ghnd;
   GHND_CHECK_ARG(out && x_packed && w_packed && y, "stem_conv_plan_create: null argument");
   *out = nullptr;
+  GHND_CHECK_ARG(K == 64 || K == 128 || K == 256, "stem conv: K=%d output channels unsupported", K);
   GHND_CHECK_ARG(N > 0 && Hp > 0 && Wp > 0 && Hp % 2 == 0 && Wp % 8 == 0,
                  "stem conv: padded size must be even x multiple of 8 (Hp=%d Wp=%d)", Hp, Wp);
   GHND_CHECK_ARG(fmt_ok(x_fmt) && fmt_ok(w_fmt) && fmt_ok(y_fmt), "stem conv: bad format");
@@ -1066,7 +1074,7 @@ int ghnd_stem_conv_plan_create(const void* x_packed, int x_fmt, const void* w_pa
       p.taps[r] = ConvTap{(int16_t)((r - ph) / 2), 0, (int16_t)ph, (int16_t)r};
     }
     const IoGeom g{N, Ho, Wo, 1, 4, 0, q};
-    if (rc == GHND_OK) rc = finish_launch(&L, &d, 32, 64, w_packed, 7, g, 32);
+    if (rc == GHND_OK) rc = finish_launch(&L, &d, 32, K, w_packed, 7, g, 32);
     if (rc == GHND_OK) plan->launches.push_back(L);
   }
   if (rc == GHND_OK) rc = set_conv_attr();

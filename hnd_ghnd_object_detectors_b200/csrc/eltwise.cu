@@ -161,7 +161,7 @@ __device__ __forceinline__ void pool_tap(uint32_t& best, uint32_t& idx, uint32_t
 template <int FMT, bool kArg>
 __global__ void __launch_bounds__(256)
     maxpool_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, uint2* __restrict__ argmax,
-                   int N, int H, int W, int C8, int c8_shift, int Ho, int Wo) {
+                   int N, int H, int W, int C8, int c8_shift, int Ho, int Wo, int XC8, int xoff8) {
   const int v = blockIdx.x * 256 + threadIdx.x;
   if (v >= Wo * C8) return;
   const int cg = v & (C8 - 1);
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(256)
     for (int s = 0; s < 3; ++s) {
       const int w = 2 * wo - 1 + s;
       if (w < 0 || w >= W) continue;
-      const uint4 q = __ldg(x + (((int64_t)n * H + h) * W + w) * C8 + cg);
+      const uint4 q = __ldg(x + (((int64_t)n * H + h) * W + w) * XC8 + xoff8 + cg);
       const uint32_t code = (uint32_t)(r * 3 + s) * 0x00010001u;
       pool_tap<FMT>(best[0], idx[0], q.x, code);
       pool_tap<FMT>(best[1], idx[1], q.y, code);
@@ -231,7 +231,7 @@ template <int XF, int DYF, int DXF>
 __global__ void __launch_bounds__(256)
     maxpool_bwd_kernel(const uint4* __restrict__ x, const uint2* __restrict__ argmax,
                        const uint4* __restrict__ dy, uint4* __restrict__ dx, int N, int H, int W,
-                       int C8, int c8_shift, int Ho, int Wo) {
+                       int C8, int c8_shift, int Ho, int Wo, int XC8, int xoff8) {
   const int v = blockIdx.x * 256 + threadIdx.x;
   const int m = v >> c8_shift;  // pixel pair index along w
   const int w0 = 2 * m;
@@ -241,8 +241,9 @@ __global__ void __launch_bounds__(256)
   const int n = blockIdx.z;
   const bool has1 = w0 + 1 < W;
   const int64_t i0 = (((int64_t)n * H + h) * W + w0) * C8 + cg;
-  const uint4 x0 = ld_stream(x + i0);
-  const uint4 x1 = has1 ? ld_stream(x + i0 + C8) : make_uint4(0u, 0u, 0u, 0u);
+  const int64_t ix0 = (((int64_t)n * H + h) * W + w0) * XC8 + xoff8 + cg;
+  const uint4 x0 = ld_stream(x + ix0);
+  const uint4 x1 = has1 ? ld_stream(x + ix0 + XC8) : make_uint4(0u, 0u, 0u, 0u);
   const int k = h >> 1;
   const bool odd = h & 1;  // uniform per block
   // window (row q, col c): q = 0 -> ho = k, q = 1 -> ho = k + 1 (odd rows only); c = 0 -> wo = m,
@@ -948,8 +949,18 @@ int ghnd_stem_pack_image_resized(const float* img_chw, int H, int W, int Ho, int
 
 int ghnd_maxpool3x3s2(const void* x, void* y, void* argmax, int fmt, int N, int H, int W, int C,
                       void* stream) {
+  return ghnd_maxpool3x3s2_strided(x, C, 0, y, argmax, fmt, N, H, W, C, stream);
+}
+
+int ghnd_maxpool3x3s2_strided(const void* x, int x_channels, int x_channel_offset, void* y, void* argmax,
+                              int fmt, int N, int H, int W, int C, void* stream) {
   GHND_CHECK_ARG(x && y && fmt16(fmt) && N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0,
                  "maxpool3x3s2: bad argument");
+  GHND_CHECK_ARG(x_channels % 8 == 0 && x_channel_offset % 8 == 0 && x_channel_offset >= 0 &&
+                     x_channel_offset + C <= x_channels,
+                 "maxpool3x3s2: channels [%d, %d) outside the %d-channel input", x_channel_offset,
+                 x_channel_offset + C, x_channels);
+  const int XC8 = x_channels / 8, xoff8 = x_channel_offset / 8;
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
   const int C8 = C / 8;
   GHND_CHECK_ARG((C8 & (C8 - 1)) == 0 && Ho <= 65535 && N <= 65535,
@@ -962,11 +973,11 @@ int ghnd_maxpool3x3s2(const void* x, void* y, void* argmax, int fmt, int N, int 
   uint4* yp = (uint4*)y;
   uint2* ap = (uint2*)argmax;
   if (fmt == GHND_F16) {
-    if (ap) maxpool_kernel<GHND_F16, true><<<grid, 256, 0, st>>>(xp, yp, ap, N, H, W, C8, shift, Ho, Wo);
-    else maxpool_kernel<GHND_F16, false><<<grid, 256, 0, st>>>(xp, yp, ap, N, H, W, C8, shift, Ho, Wo);
+    if (ap) maxpool_kernel<GHND_F16, true><<<grid, 256, 0, st>>>(xp, yp, ap, N, H, W, C8, shift, Ho, Wo, XC8, xoff8);
+    else maxpool_kernel<GHND_F16, false><<<grid, 256, 0, st>>>(xp, yp, ap, N, H, W, C8, shift, Ho, Wo, XC8, xoff8);
   } else {
-    if (ap) maxpool_kernel<GHND_BF16, true><<<grid, 256, 0, st>>>(xp, yp, ap, N, H, W, C8, shift, Ho, Wo);
-    else maxpool_kernel<GHND_BF16, false><<<grid, 256, 0, st>>>(xp, yp, ap, N, H, W, C8, shift, Ho, Wo);
+    if (ap) maxpool_kernel<GHND_BF16, true><<<grid, 256, 0, st>>>(xp, yp, ap, N, H, W, C8, shift, Ho, Wo, XC8, xoff8);
+    else maxpool_kernel<GHND_BF16, false><<<grid, 256, 0, st>>>(xp, yp, ap, N, H, W, C8, shift, Ho, Wo, XC8, xoff8);
   }
   GHND_LAUNCH_CHECK("maxpool_kernel");
   return GHND_OK;
@@ -974,8 +985,19 @@ int ghnd_maxpool3x3s2(const void* x, void* y, void* argmax, int fmt, int N, int 
 
 int ghnd_maxpool3x3s2_bwd(const void* x, int x_fmt, const void* argmax, const void* dy, int dy_fmt,
                           void* dx, int dx_fmt, int N, int H, int W, int C, void* stream) {
+  return ghnd_maxpool3x3s2_bwd_strided(x, x_fmt, C, 0, argmax, dy, dy_fmt, dx, dx_fmt, N, H, W, C, stream);
+}
+
+int ghnd_maxpool3x3s2_bwd_strided(const void* x, int x_fmt, int x_channels, int x_channel_offset,
+                                  const void* argmax, const void* dy, int dy_fmt, void* dx, int dx_fmt,
+                                  int N, int H, int W, int C, void* stream) {
   GHND_CHECK_ARG(x && argmax && dy && dx && fmt16(x_fmt) && fmt16(dy_fmt) && fmt16(dx_fmt),
                  "maxpool3x3s2_bwd: bad argument");
+  GHND_CHECK_ARG(x_channels % 8 == 0 && x_channel_offset % 8 == 0 && x_channel_offset >= 0 &&
+                     x_channel_offset + C <= x_channels,
+                 "maxpool3x3s2_bwd: channels [%d, %d) outside the %d-channel input", x_channel_offset,
+                 x_channel_offset + C, x_channels);
+  const int XC8 = x_channels / 8, xoff8 = x_channel_offset / 8;
   GHND_CHECK_ARG(N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "maxpool3x3s2_bwd: bad geometry");
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
   const int C8 = C / 8;
@@ -988,7 +1010,7 @@ int ghnd_maxpool3x3s2_bwd(const void* x, int x_fmt, const void* argmax, const vo
 #define GHND_POOL_BWD(XF, DYF, DXF)                                                                \
   maxpool_bwd_kernel<XF, DYF, DXF><<<grid, 256, 0, st>>>((const uint4*)x, (const uint2*)argmax,    \
                                                          (const uint4*)dy, (uint4*)dx, N, H, W, C8, \
-                                                         shift, Ho, Wo)
+                                                         shift, Ho, Wo, XC8, xoff8)
   const int combo = (x_fmt == GHND_F16 ? 4 : 0) | (dy_fmt == GHND_F16 ? 2 : 0) | (dx_fmt == GHND_F16 ? 1 : 0);
   switch (combo) {
     case 0: GHND_POOL_BWD(GHND_BF16, GHND_BF16, GHND_BF16); break;

@@ -230,22 +230,55 @@ class FrozenLayerRunner(object):
             b.backward(side)
 
 
-class StemRunner(object):
-    """conv1 7x7 s2 + FrozenBN + ReLU (tcgen05 implicit GEMM) -> MaxPool 3x3 s2."""
+class DualStemConv(object):
+    """The teacher's and the student's conv1 as ONE K=128 GEMM over the shared packed image (teacher
+    = channels 0-63, student = 64-127).  The stem is bounded by its im2col traffic (every input
+    pixel travels ~12x through L2 -> shared memory; the tensor pipe is ~16 % busy), which does not
+    depend on the number of output channels -- so the second model's conv1 is almost free."""
 
-    def __init__(self, body, packed, N, Hp, Wp, act_dtype, grad_dtype, trainable):
+    def __init__(self, teacher_body, student_body, packed, N, Hp, Wp, act_dtype):
+        dev = packed.device
+        self.student_body = student_body
+        t_scale, t_shift = fold_frozen_bn(teacher_body.bn1)
+        self.s_scale, s_shift = fold_frozen_bn(student_body.bn1)
+        self.w = _empty((128, 7, 32), act_dtype, dev)
+        self.bias = torch.cat([t_shift, s_shift]).contiguous()
+        self.conv = _empty((N, Hp // 2, Wp // 2, 128), act_dtype, dev)
+        self.plan = ops.StemPlan(packed, self.w, self.bias, self.conv, N, Hp, Wp)
+        ops.stem_pack_weight(teacher_body.conv1.weight, t_scale, out=self.w[:64])  # frozen: once
+        self.refresh_student()
+
+    def refresh_student(self):
+        ops.stem_pack_weight(self.student_body.conv1.weight, self.s_scale, out=self.w[64:])
+
+    def forward(self):
+        self.refresh_student()  # conv1.weight is trainable
+        self.plan.run()
+
+
+class StemRunner(object):
+    """conv1 7x7 s2 + FrozenBN + ReLU (tcgen05 implicit GEMM) -> MaxPool 3x3 s2.
+    shared = (DualStemConv, channel offset): the conv is done by the two-stem GEMM and this runner
+    only pools (and back-propagates through) its 64-channel half."""
+
+    def __init__(self, body, packed, N, Hp, Wp, act_dtype, grad_dtype, trainable, shared=None):
         dev = packed.device
         self.body, self.packed = body, packed
         self.N, self.Hp, self.Wp = N, Hp, Wp
         self.trainable = trainable
+        self.shared = shared
         self.scale, self.shift = fold_frozen_bn(body.bn1)
-        self.w = _empty((64, 7, 32), act_dtype, dev)
-        self.conv = _empty((N, Hp // 2, Wp // 2, 64), act_dtype, dev)
         self.Ho, self.Wo = (Hp // 2 + 1) // 2, (Wp // 2 + 1) // 2
         self.out = _empty((N, self.Ho, self.Wo, 64), act_dtype, dev)
         self.argmax = _empty((N, self.Ho, self.Wo, 64), torch.uint8, dev) if trainable else None
-        self.plan = ops.StemPlan(packed, self.w, self.shift, self.conv, N, Hp, Wp)
-        self.refresh_weights()
+        if shared is not None:
+            self.conv, self.c_off, self.plan, self.w = shared[0].conv, shared[1], None, None
+        else:
+            self.c_off = 0
+            self.w = _empty((64, 7, 32), act_dtype, dev)
+            self.conv = _empty((N, Hp // 2, Wp // 2, 64), act_dtype, dev)
+            self.plan = ops.StemPlan(packed, self.w, self.shift, self.conv, N, Hp, Wp)
+            self.refresh_weights()
         if trainable:
             self.g_conv = _empty((N, Hp // 2, Wp // 2, 64), grad_dtype, dev)
             self.ws = _empty((_lib.load().ghnd_stem_wgrad_workspace_bytes(),), torch.uint8, dev)
@@ -255,17 +288,19 @@ class StemRunner(object):
             self.wgrad = None
 
     def refresh_weights(self):
-        ops.stem_pack_weight(self.body.conv1.weight, self.scale, out=self.w)
+        if self.shared is None:
+            ops.stem_pack_weight(self.body.conv1.weight, self.scale, out=self.w)
 
     def forward(self):
-        if self.trainable:
-            self.refresh_weights()
-        self.plan.run()
-        ops.maxpool3x3s2(self.conv, self.out, self.argmax)
+        if self.shared is None:
+            if self.trainable:
+                self.refresh_weights()
+            self.plan.run()
+        ops.maxpool3x3s2(self.conv, self.out, self.argmax, channels=64, channel_offset=self.c_off)
 
     def backward(self, g_out, dw):
         """g_out: gradient w.r.t. the pooled output; dw: fp32 OIHW view for conv1.weight.grad."""
-        ops.maxpool3x3s2_bwd(self.conv, self.argmax, g_out, self.g_conv)
+        ops.maxpool3x3s2_bwd(self.conv, self.argmax, g_out, self.g_conv, channel_offset=self.c_off)
         if self.packed_g is not self.packed:
             ops.convert16(self.packed, self.packed_g)
         if self.wgrad is None or self.wgrad_dw is not dw:
@@ -306,7 +341,8 @@ class _BN(object):
 class _WideUnit(object):
     """conv(k2) -> BatchNorm(batch stats) [-> ReLU] of the student's layer1, forward + backward."""
 
-    def __init__(self, conv, bn, relu, x, x_g, N, H, W, act_dtype, grad_dtype, train, out=None):
+    def __init__(self, conv, bn, relu, x, x_g, N, H, W, act_dtype, grad_dtype, train, out=None,
+                 need_out_g=True):
         dev = x.device
         K, C, R, S = conv.weight.shape
         pad = conv.padding[0]
@@ -322,7 +358,9 @@ class _WideUnit(object):
         assert tuple(self.out.shape) == (N, self.Ho, self.Wo, K)
         if train:
             self.raw = _empty((N, self.Ho, self.Wo, K), act_dtype, dev)
-            self.out_g = _empty((N, self.Ho, self.Wo, K), grad_dtype, dev)  # bf16 copy for wgrad
+            # bf16 copy of the activation for the NEXT unit's weight-gradient GEMM (skipped when no
+            # tensor-core dW reads it: the layer's last unit, and e2 whose consumer is the narrow dW)
+            self.out_g = _empty((N, self.Ho, self.Wo, K), grad_dtype, dev) if need_out_g else None
             # batch statistics of the stored conv output are accumulated by the conv epilogue
             self.plan = ops.ConvPlan(CONV_FWD, N, H, W, C, K, R, S, 1, pad, x, self.w, self.raw,
                                      stats=self.bn.sums)
@@ -417,11 +455,12 @@ class StudentLayer1Runner(object):
         else:
             self._own_xg = False
         self.x_g = x_g
-        mk = lambda conv, bn, relu, xin, xin_g, h, w: _WideUnit(conv, bn, relu, xin, xin_g, N, h, w,
-                                                              act_dtype, grad_dtype, train)
+        mk = lambda conv, bn, relu, xin, xin_g, h, w, og=True: _WideUnit(conv, bn, relu, xin, xin_g, N, h, w,
+                                                                       act_dtype, grad_dtype, train,
+                                                                       need_out_g=og)
         self.e0 = mk(enc[0], enc[1], False, x, x_g, H, W)
         self.e1 = mk(enc[2], enc[3], True, self.e0.out, self.e0.out_g, self.e0.Ho, self.e0.Wo)
-        self.e2 = mk(enc[5], enc[6], False, self.e1.out, self.e1.out_g, self.e1.Ho, self.e1.Wo)
+        self.e2 = mk(enc[5], enc[6], False, self.e1.out, self.e1.out_g, self.e1.Ho, self.e1.Wo, False)
         self.enc7, self.bn0, self.dec2 = enc[7], dec[0], dec[2]
         self.bch = enc[7].weight.shape[0]
         self.Hz, self.Wz = self.e2.Ho + 1, self.e2.Wo + 1
@@ -437,7 +476,7 @@ class StudentLayer1Runner(object):
         self.d4 = mk(dec[4], dec[5], True, self.act3, self.act3_g, self.H3, self.W3)
         self.d7 = mk(dec[7], dec[8], False, self.d4.out, self.d4.out_g, self.d4.Ho, self.d4.Wo)
         self.d9 = _WideUnit(dec[9], dec[10], True, self.d7.out, self.d7.out_g, N, self.d7.Ho, self.d7.Wo,
-                            act_dtype, grad_dtype, train, out=out)
+                            act_dtype, grad_dtype, train, out=out, need_out_g=False)
         self.out = self.d9.out
         assert (self.d9.Ho, self.d9.Wo) == (H, W)
         self.q = None  # set by forward_encoder_quantized
@@ -622,7 +661,12 @@ class GhndPlan(object):
             share_frozen_trunk = bool(upper) and _same_frozen_layers(teacher_body, student_body, upper)
         self.shared = bool(share_frozen_trunk) and bool(upper)
         # ---- teacher (forward only) ----
-        self.t_stem = StemRunner(teacher_body, self.packed, N, Hp, Wp, act_dtype, grad_dtype, False)
+        # both conv1's as one K=128 GEMM over the shared image (GHND_DUAL_STEM=0: two K=64 GEMMs)
+        self.stem2 = None
+        if os.environ.get("GHND_DUAL_STEM", "1") != "0":
+            self.stem2 = DualStemConv(teacher_body, student_body, self.packed, N, Hp, Wp, act_dtype)
+        self.t_stem = StemRunner(teacher_body, self.packed, N, Hp, Wp, act_dtype, grad_dtype, False,
+                                 shared=(self.stem2, 0) if self.stem2 else None)
         H1, W1 = self.t_stem.Ho, self.t_stem.Wo
         self.trunk_in = _empty((2 * N, H1, W1, 256), act_dtype, dev) if self.shared else None
         self.t_layers = {}
@@ -639,7 +683,8 @@ class GhndPlan(object):
         self.flat = flat if flat is not None else FlatParams(
             [("backbone.body." + n, p) for n, p in student_body.named_parameters()])
         grads = self.flat.grads
-        self.s_stem = StemRunner(student_body, self.packed, N, Hp, Wp, act_dtype, grad_dtype, True)
+        self.s_stem = StemRunner(student_body, self.packed, N, Hp, Wp, act_dtype, grad_dtype, True,
+                                 shared=(self.stem2, 64) if self.stem2 else None)
         self.s_l1 = StudentLayer1Runner(student_body.layer1, self.s_stem.out, N, self.s_stem.Ho,
                                         self.s_stem.Wo, act_dtype, grad_dtype, True,
                                         out=self.trunk_in[N:] if self.shared else None)
@@ -682,7 +727,6 @@ class GhndPlan(object):
         self.s_l1.plan_backward(g, grads, "backbone.body.layer1.")
         self.graph = None
         self.step_count = 0
-        import os
         self.side = SideStream(dev) if os.environ.get("GHND_SIDE_STREAM", "1") != "0" else None
 
     # ------------------------------------------------------------------------------------------
@@ -701,12 +745,17 @@ class GhndPlan(object):
             side.fork()
             side.run(self.s_l1.prepack)
             packed = side.mark()
+            if self.stem2 is not None:
+                self.stem2.forward()  # both conv1's; the two pools + layer1's then run side by side
+                side.fork()
             side.run(self._teacher_forward)
             self.s_stem.forward()
             torch.cuda.current_stream().wait_event(packed)
             self.s_l1.forward()
             side.join()
         else:
+            if self.stem2 is not None:
+                self.stem2.forward()
             self._teacher_forward()
             self.s_stem.forward()
             self.s_l1.forward()

@@ -242,14 +242,19 @@ class WgradPlan(object):
 
 
 class StemPlan(object):
+    """conv1 7x7 s2 + folded FrozenBN + ReLU.  y [N,Hp/2,Wp/2,K] with K = 64 (one stem) or 128 (two
+    stems over the same packed image as one GEMM: weights [K][7][32], bias [K])."""
+
     def __init__(self, x_packed, w_packed, bias, y, N, Hp, Wp):
+        K = y.shape[-1]
+        assert w_packed.shape[0] == K and bias.numel() == K
         self._keep = (x_packed, w_packed, bias, y)
-        self.desc = "stem N%d %dx%d" % (N, Hp, Wp)
+        self.desc = "stem N%d %dx%d" % (N, Hp, Wp) + ("" if K == 64 else " K%d" % K)
         self.n_launches = 4
-        self.flops = 2.0 * N * (Hp // 2) * (Wp // 2) * 64 * 147
+        self.flops = 2.0 * N * (Hp // 2) * (Wp // 2) * K * 147
         self._h = c_void_p()
-        call("ghnd_stem_conv_plan_create", ptr(x_packed), fmt_of(x_packed.dtype), ptr(w_packed),
-             fmt_of(w_packed.dtype), ptr(bias), ptr(y), fmt_of(y.dtype), N, Hp, Wp, byref(self._h))
+        call("ghnd_stem_conv_plan_create_k", ptr(x_packed), fmt_of(x_packed.dtype), ptr(w_packed),
+             fmt_of(w_packed.dtype), ptr(bias), ptr(y), fmt_of(y.dtype), N, Hp, Wp, K, byref(self._h))
 
     def run(self, stream=None):
         call("ghnd_stem_conv_plan_run", self._h, stream_ptr(stream))
@@ -432,20 +437,26 @@ def wgrad_narrow(a, b, dw, a_is_output, R, S, pad, pre=None, pre_relu=False, ws=
 # ------------------------------------------------------------------------------------------------
 # stem helpers
 # ------------------------------------------------------------------------------------------------
-def maxpool3x3s2(x, y=None, argmax=None):
-    n, h, w, c = x.shape
+def maxpool3x3s2(x, y=None, argmax=None, channels=None, channel_offset=0):
+    """channels / channel_offset: pool only channels [offset, offset+channels) of x (one half of the
+    two-stem conv output); y / argmax are compact `channels`-wide tensors."""
+    n, h, w, xc = x.shape
+    c = xc if channels is None else channels
     ho, wo = (h + 1) // 2, (w + 1) // 2
     if y is None:
         y = torch.empty((n, ho, wo, c), dtype=x.dtype, device=x.device)
-    call("ghnd_maxpool3x3s2", ptr(x), ptr(y), ptr(argmax), fmt_of(x.dtype), n, h, w, c, stream_ptr())
+    call("ghnd_maxpool3x3s2_strided", ptr(x), xc, channel_offset, ptr(y), ptr(argmax), fmt_of(x.dtype), n, h, w,
+         c, stream_ptr())
     _count()
     return y
 
 
-def maxpool3x3s2_bwd(x, argmax, dy, dx):
-    n, h, w, c = x.shape
-    call("ghnd_maxpool3x3s2_bwd", ptr(x), fmt_of(x.dtype), ptr(argmax), ptr(dy), fmt_of(dy.dtype), ptr(dx),
-         fmt_of(dx.dtype), n, h, w, c, stream_ptr())
+def maxpool3x3s2_bwd(x, argmax, dy, dx, channel_offset=0):
+    """x may be wider than dx (two-stem conv output): its channels [offset, offset+C) are used."""
+    n, h, w, xc = x.shape
+    c = dx.shape[-1]
+    call("ghnd_maxpool3x3s2_bwd_strided", ptr(x), fmt_of(x.dtype), xc, channel_offset, ptr(argmax), ptr(dy),
+         fmt_of(dy.dtype), ptr(dx), fmt_of(dx.dtype), n, h, w, c, stream_ptr())
     _count()
     return dx
 

@@ -254,6 +254,13 @@ typedef struct ghnd_stem_plan ghnd_stem_plan_t;
 int ghnd_stem_conv_plan_create(const void* x_packed, int x_fmt, const void* w_packed, int w_fmt,
                                const float* bias, void* y, int y_fmt, int N, int Hp, int Wp,
                                ghnd_stem_plan_t** plan);
+/* The same for K = 64 * m output channels: m stems that read the SAME packed image as one GEMM
+ * (weights [K][7][32], bias[K], y [N,Hp/2,Wp/2,K]).  The distillation step runs the teacher's and
+ * the student's conv1 this way (channels 0-63 / 64-127): the im2col traffic, which bounds the stem,
+ * is paid once. */
+int ghnd_stem_conv_plan_create_k(const void* x_packed, int x_fmt, const void* w_packed, int w_fmt,
+                                 const float* bias, void* y, int y_fmt, int N, int Hp, int Wp, int K,
+                                 ghnd_stem_plan_t** plan);
 int ghnd_stem_conv_plan_run(const ghnd_stem_plan_t* plan, void* stream);
 void ghnd_stem_plan_destroy(ghnd_stem_plan_t* plan);
 /* maxpool 3x3 s2 p1 on NHWC 16-bit: y[N][Ho][Wo][C], Ho=(H+1)/2; argmax (nullable) receives the
@@ -264,6 +271,13 @@ int ghnd_maxpool3x3s2(const void* x, void* y, void* argmax, int fmt, int N, int 
  * (h,w), zero where x (the post-ReLU conv output) is not > 0. */
 int ghnd_maxpool3x3s2_bwd(const void* x, int x_fmt, const void* argmax, const void* dy, int dy_fmt,
                           void* dx, int dx_fmt, int N, int H, int W, int C, void* stream);
+/* Strided-input variants: x holds x_channels channels per pixel and the pool works on the C channels
+ * starting at x_channel_offset (multiples of 8) -- one half of the two-stem conv output. */
+int ghnd_maxpool3x3s2_strided(const void* x, int x_channels, int x_channel_offset, void* y, void* argmax,
+                              int fmt, int N, int H, int W, int C, void* stream);
+int ghnd_maxpool3x3s2_bwd_strided(const void* x, int x_fmt, int x_channels, int x_channel_offset,
+                                  const void* argmax, const void* dy, int dy_fmt, void* dx, int dx_fmt,
+                                  int N, int H, int W, int C, void* stream);
 /* dW of conv1: dw[k][c][r][s] = scale[k] * sum g[n][ho][wo][k] * xpacked[n][2ho+r][2wo+s][c]
  * (fp32 OIHW [64][3][7][7]); SIMT register-tiled, split over pixels, fp32 atomics into workspace. */
 size_t ghnd_stem_wgrad_workspace_bytes(void);

@@ -644,6 +644,50 @@ def test_stem(ops, dt):
     assert rel(dw.cpu(), dw_ref) < 2e-3, rel(dw.cpu(), dw_ref)
 
 
+def test_stem_two_models_one_gemm(ops):
+    """Teacher + student conv1 as one K=128 stem GEMM over the shared packed image: each 64-channel
+    half must equal the stand-alone K=64 stem bit for bit, and the strided max-pool forward /
+    backward on a half must equal the compact kernels on the stand-alone tensor."""
+    torch.manual_seed(21)
+    dt = torch.float16
+    imgs = [torch.rand(3, 96, 128), torch.rand(3, 80, 120)]
+    N, Hp, Wp = 2, 96, 128
+    packed = torch.empty((N, Hp + 6, Wp + 8, 4), dtype=dt, device="cuda")
+    for i, im in enumerate(imgs):
+        ops.stem_pack_image(im.cuda(), packed, i, Hp, Wp, O.IMAGE_MEAN, O.IMAGE_STD)
+    ws = [(torch.randn(64, 3, 7, 7) * 0.1).cuda() for _ in range(2)]
+    scales = [(torch.rand(64) + 0.5).cuda() for _ in range(2)]
+    biases = [(torch.randn(64) * 0.2).cuda() for _ in range(2)]
+    w2 = torch.empty((128, 7, 32), dtype=dt, device="cuda")
+    singles = []
+    for k in range(2):
+        wk = ops.stem_pack_weight(ws[k], scales[k], dt)
+        ops.stem_pack_weight(ws[k], scales[k], out=w2[64 * k:64 * (k + 1)])
+        y = torch.zeros((N, Hp // 2, Wp // 2, 64), dtype=dt, device="cuda")
+        ops.StemPlan(packed, wk, biases[k], y, N, Hp, Wp).run()
+        singles.append(y)
+    y2 = torch.zeros((N, Hp // 2, Wp // 2, 128), dtype=dt, device="cuda")
+    ops.StemPlan(packed, w2, torch.cat(biases).contiguous(), y2, N, Hp, Wp).run()
+    torch.cuda.synchronize()
+    for k in range(2):
+        assert torch.equal(y2[..., 64 * k:64 * (k + 1)], singles[k]), k
+    am1 = torch.empty((N, Hp // 4, Wp // 4, 64), dtype=torch.uint8, device="cuda")
+    am2 = torch.empty_like(am1)
+    p1 = ops.maxpool3x3s2(singles[1], argmax=am1)
+    p2 = ops.maxpool3x3s2(y2, argmax=am2, channels=64, channel_offset=64)
+    assert torch.equal(p1, p2) and torch.equal(am1, am2)
+    assert torch.equal(ops.maxpool3x3s2(y2, channels=64, channel_offset=0), ops.maxpool3x3s2(singles[0]))
+    dy = torch.randn(p1.shape, device="cuda").to(torch.bfloat16)
+    dx1 = torch.empty(singles[1].shape, dtype=torch.bfloat16, device="cuda")
+    dx2 = torch.empty_like(dx1)
+    ops.maxpool3x3s2_bwd(singles[1], am1, dy, dx1)
+    ops.maxpool3x3s2_bwd(y2, am2, dy, dx2, channel_offset=64)
+    assert torch.equal(dx1, dx2)
+    from hnd_ghnd_object_detectors_b200._lib import GhndError
+    with pytest.raises(GhndError):
+        ops.maxpool3x3s2(y2, channels=64, channel_offset=96)
+
+
 @pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
 def test_stem_pack_with_resize(ops, golden_dir, dt):
     """normalize + bilinear resize + zero-pad fused in the pack kernel against the
