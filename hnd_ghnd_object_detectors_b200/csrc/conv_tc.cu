@@ -88,6 +88,10 @@ struct ConvKernelParams {
   double* stats;    // optional [2*cout]: sum / sum of squares of the stored (rounded) output
   int stats_mode;   // 1: sum of the output, sum of output * in1 operand (BN backward reductions)
   int in1_mask;     // 0: the in1 operand is only read by the statistics
+  // stem "halo" mode: the im2col operand of ALL filter rows of a tile is one TMA box of
+  // 2*th+5 image rows (read at row shifts by the MMA descriptors) and the weights stay resident
+  int halo;
+  int w_res_bytes;  // n_taps * b_bytes of resident weights behind the pipeline stages
 };
 
 __device__ __forceinline__ int fd_ring_r(const ConvKernelParams& p, uint32_t cnt) {
@@ -145,6 +149,30 @@ __device__ __forceinline__ void umma_unit(uint32_t d_tmem, uint32_t a_lo, uint32
         "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc)
         : "memory");
   }
+}
+
+// Two K=16 steps with separate high words for A and B (different stride-byte-offsets).
+__device__ __forceinline__ void umma_unit2_ab(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi,
+                                              uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      ".reg .b64 da, db;\n\t"
+      ".reg .b32 a, b;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "setp.eq.b32 q, 0, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "add.u32 a, %1, 2;\n\t"
+      "add.u32 b, %3, 2;\n\t"
+      "mov.b64 da, {a, %2};\n\t"
+      "mov.b64 db, {b, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, q;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 
 // v[0..63] += the 64 channels of `row` of a swizzled 16-bit operand tile
@@ -250,7 +278,8 @@ __global__ void __launch_bounds__(kConvThreads, 1)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~(uintptr_t)1023);
   const int n_in = p.has_in0 + p.has_in1;
-  uint8_t* epi_out = smem + (size_t)p.n_stages * p.stage_bytes;            // [2 groups][kChunkBytes]
+  uint8_t* wres = smem + (size_t)p.n_stages * p.stage_bytes;               // halo mode: resident weights
+  uint8_t* epi_out = wres + (p.halo ? p.w_res_bytes : 0);                  // [2 groups][kChunkBytes]
   uint8_t* epi_in = epi_out + 2 * kChunkBytes;                             // [ring][n_in][kChunkBytes]
   float* sbias = reinterpret_cast<float*>(epi_in + (size_t)p.ring * n_in * kChunkBytes);  // [cout]
   float* sstat = sbias + (p.bias != nullptr ? p.cout : 0);                 // [2*cout] when stats
@@ -261,7 +290,8 @@ __global__ void __launch_bounds__(kConvThreads, 1)
   uint64_t* tempty_bar = tfull_bar + 2;             // [2]
   uint64_t* ifull_bar = tempty_bar + 2;             // [kMaxRing]
   uint64_t* iempty_bar = ifull_bar + kMaxRing;      // [kMaxRing]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(iempty_bar + kMaxRing);
+  uint64_t* wfull_bar = iempty_bar + kMaxRing;      // [1] resident weights have landed (halo mode)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull_bar + 1);
 
   // warp index through a shuffle so that the compiler treats the role branches as warp-uniform
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -283,6 +313,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
       mbar_init(&ifull_bar[i], 1);
       mbar_init(&iempty_bar[i], kEpiGroupThreads);
     }
+    mbar_init(wfull_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -300,7 +331,74 @@ __global__ void __launch_bounds__(kConvThreads, 1)
   const int upst = p.units_per_stage;
   const int n_chunks = p.block_n >> 6;
 
-  if (warp == 0) {
+  if (warp == 0 && p.halo) {
+    // ===================== TMA producer, stem halo mode ==========================================
+    // weights once; then ONE box per tile: 2*th+5 image rows x tw column slots x 64 B
+    if (elect_one()) {
+      mbar_arrive_expect_tx(wfull_bar, (uint32_t)p.w_res_bytes);
+      for (int r = 0; r < p.n_taps; ++r)
+        tma_load_2d(wres + (size_t)r * p.b_bytes, &p.tmap_b, wfull_bar, p.taps[r].wk * p.cin, 0);
+    }
+    __syncwarp();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      int img, rem, h0, w0;
+      fd_divmod(p.fd_tiles_per_img, tile, img, rem);
+      fd_divmod(p.fd_tiles_w, rem, h0, w0);
+      h0 *= p.th;
+      w0 *= p.tw;
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)p.a_box_bytes);
+        tma_load_4d(smem + (size_t)stage * p.stage_bytes, &p.tmap_a[0], &full_bar[stage], 0, w0, 2 * h0,
+                    img);
+      }
+      __syncwarp();
+      if (++stage == p.n_stages) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+  } else if (warp == 1 && p.halo) {
+    // ===================== MMA issuer, stem halo mode ============================================
+    // filter row r reads the halo tile at a shift of r image rows (r * tw * 64 B); output rows are
+    // two image rows apart (SBO of A = 2 * tw * 64 B).  tw == 8: one 8-row swizzle atom per image row,
+    // so every shift is a multiple of the 512-byte SWIZZLE_64B period.
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t w_base = smem_u32(wres);
+    const uint32_t row_pitch = (uint32_t)p.tw * 64u;
+    const uint32_t a_hi = ((2u * row_pitch) >> 4) | (1u << 14) | ((uint32_t)UMMA_SW64 << 29);
+    const uint32_t b_hi = (512u >> 4) | (1u << 14) | ((uint32_t)UMMA_SW64 << 29);
+    mbar_wait(wfull_bar, 0);
+    tc_fence_after();
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      mbar_wait(&tempty_bar[buf], (((uint32_t)it >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.block_n);
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sa = smem_base + (uint32_t)(stage * p.stage_bytes);
+        for (int r = 0; r < p.n_taps; ++r) {
+          const uint32_t a_lo = (((sa + (uint32_t)r * row_pitch) >> 4) & 0x3fffu) | (1u << 16);
+          const uint32_t b_lo = (((w_base + (uint32_t)(r * p.b_bytes)) >> 4) & 0x3fffu) | (1u << 16);
+          umma_unit2_ab(d_tmem, a_lo, a_hi, b_lo, b_hi, p.idesc, (uint32_t)(r != 0));
+        }
+        umma_commit(&empty_bar[stage]);  // the halo tile may be overwritten when these retire
+        umma_commit(&tfull_bar[buf]);    // accumulator complete -> epilogue
+      }
+      __syncwarp();
+      if (++stage == p.n_stages) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+  } else if (warp == 0) {
     // ===================== TMA producer (whole warp converged, one elected lane issues) ==========
     int stage = 0;
     uint32_t phase = 0;
@@ -675,7 +773,8 @@ struct IoGeom {
 // Shared-memory plan of one launch: [stages][2 staging tiles][operand ring][bias][stats][barriers].
 
 static int finish_launch(ConvLaunch* L, const ghnd_conv_desc_t* d, int gemm_cin, int gemm_cout,
-                         const void* weights, int total_taps, const IoGeom& g, int kblock = 64) {
+                         const void* weights, int total_taps, const IoGeom& g, int kblock = 64,
+                         int force_block_n = 0) {
   ConvKernelParams& p = L->p;
   p.cin = gemm_cin;
   p.cout = gemm_cout;
@@ -692,7 +791,9 @@ static int finish_launch(ConvLaunch* L, const ghnd_conv_desc_t* d, int gemm_cin,
   if (d->residual != nullptr || d->accumulate) p.has_in0 = 1;
   if (d->mask != nullptr) p.has_in1 = 1;
   const int n_in = p.has_in0 + p.has_in1;
-  p.block_n = pick_block_n(gemm_cout, m_tiles, n_units, p.n_taps, row_bytes, n_in, d->bias != nullptr);
+  p.block_n = force_block_n ? force_block_n
+                            : pick_block_n(gemm_cout, m_tiles, n_units, p.n_taps, row_bytes, n_in,
+                                           d->bias != nullptr);
   p.b_bytes = p.block_n * row_bytes;
   p.n_tiles_n = gemm_cout / p.block_n;
   p.total_tiles = m_tiles * p.n_tiles_n;
@@ -745,6 +846,8 @@ static int finish_launch(ConvLaunch* L, const ghnd_conv_desc_t* d, int gemm_cin,
   p.bias = d->bias;
   p.out_fmt = d->dst_fmt;
   p.relu = d->relu;
+  p.halo = 0;
+  p.w_res_bytes = 0;
   p.stats = d->stats;
   p.stats_mode = d->stats != nullptr ? d->stats_mode : 0;
   p.in1_mask = (d->mask != nullptr && !(d->stats != nullptr && d->stats_mode == 1 && d->mask_stats_only)) ? 1 : 0;
@@ -1056,6 +1159,43 @@ int ghnd_stem_conv_plan_create_k(const void* x_packed, int x_fmt, const void* w_
     memset(&L, 0, sizeof(L));
     ConvKernelParams& p = L.p;
     p.n_img = N;
+    static const bool no_halo = getenv("GHND_NO_STEM_HALO") != nullptr;  // A/B + debugging switch
+    if (!no_halo && J >= 8 && K <= 256) {
+      // halo mode: tile = 16 output rows x 8 column slots; one TMA box of 37 image rows per tile,
+      // weights resident in shared memory (see the kernel's halo branches)
+      p.th = 16;
+      p.tw = 8;
+      p.tiles_h = (Ho + p.th - 1) / p.th;
+      p.tiles_w = (J + p.tw - 1) / p.tw;
+      const int halo_rows = 2 * p.th + 5;
+      const uint8_t* base = static_cast<const uint8_t*>(x_packed) + (size_t)q * 8 * 2;
+      uint64_t dims[4] = {32, (uint64_t)J, (uint64_t)rows, (uint64_t)N};
+      uint64_t str[4] = {2, 64, (uint64_t)RP * 2, (uint64_t)rows * RP * 2};
+      uint32_t box[4] = {32, (uint32_t)p.tw, (uint32_t)halo_rows, 1};
+      rc = encode_tmap(&p.tmap_a[0], 2, 4, const_cast<uint8_t*>(base), dims, str, box, 64);
+      for (int i = 1; i < 4; ++i) p.tmap_a[i] = p.tmap_a[0];
+      p.n_taps = 7;
+      for (int r = 0; r < 7; ++r) p.taps[r] = ConvTap{(int16_t)r, 0, 0, (int16_t)r};
+      const IoGeom g{N, Ho, Wo, 1, 4, 0, q};
+      if (rc == GHND_OK) rc = finish_launch(&L, &d, 32, K, w_packed, 7, g, 32, K);
+      if (rc == GHND_OK) {
+        p.halo = 1;
+        p.w_res_bytes = 7 * p.b_bytes;
+        p.a_box_bytes = halo_rows * p.tw * 64;
+        p.stage_bytes = (p.a_box_bytes + 1023) / 1024 * 1024;
+        const int fixed = 2 * kChunkBytes + (bias ? K * 4 : 0);
+        int stages = (kSmemBudget - fixed - p.w_res_bytes) / p.stage_bytes;
+        if (stages > kMaxStages) stages = kMaxStages;
+        if (stages < 2) {
+          set_error("stem conv: shared memory budget leaves %d halo stages", stages);
+          rc = GHND_ERR_UNSUPPORTED;
+        }
+        p.n_stages = stages;
+        L.smem = (size_t)p.n_stages * p.stage_bytes + (size_t)p.w_res_bytes + (size_t)fixed + 1024 + 512;
+      }
+      if (rc == GHND_OK) plan->launches.push_back(L);
+      continue;
+    }
     choose_tile(Ho, J, &p.th, &p.tw);
     p.tiles_h = (Ho + p.th - 1) / p.th;
     p.tiles_w = (J + p.tw - 1) / p.tw;
