@@ -92,6 +92,8 @@ struct ConvKernelParams {
   // 2*th+5 image rows (read at row shifts by the MMA descriptors) and the weights stay resident
   int halo;
   int w_res_bytes;  // n_taps * b_bytes of resident weights behind the pipeline stages
+  int epi_bufs;     // output staging tiles per epilogue group (2: the TMA store of chunk i drains
+                    // while chunk i+1 is staged)
 };
 
 __device__ __forceinline__ int fd_ring_r(const ConvKernelParams& p, uint32_t cnt) {
@@ -280,7 +282,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
   const int n_in = p.has_in0 + p.has_in1;
   uint8_t* wres = smem + (size_t)p.n_stages * p.stage_bytes;               // halo mode: resident weights
   uint8_t* epi_out = wres + (p.halo ? p.w_res_bytes : 0);                  // [2 groups][kChunkBytes]
-  uint8_t* epi_in = epi_out + 2 * kChunkBytes;                             // [ring][n_in][kChunkBytes]
+  uint8_t* epi_in = epi_out + (size_t)2 * p.epi_bufs * kChunkBytes;        // [ring][n_in][kChunkBytes]
   float* sbias = reinterpret_cast<float*>(epi_in + (size_t)p.ring * n_in * kChunkBytes);  // [cout]
   float* sstat = sbias + (p.bias != nullptr ? p.cout : 0);                 // [2*cout] when stats
   uint64_t* bars = reinterpret_cast<uint64_t*>(sstat + (p.stats != nullptr ? 2 * p.cout : 0));
@@ -531,7 +533,8 @@ __global__ void __launch_bounds__(kConvThreads, 1)
     const int row = quarter * 32 + lane;
     const int etid = threadIdx.x - (kEpiWarp0 + 4 * group) * 32;
     const int bar_id = 1 + group;
-    uint8_t* o_base = epi_out + (size_t)group * kChunkBytes;
+    uint8_t* const o_base0 = epi_out + (size_t)group * p.epi_bufs * kChunkBytes;
+    uint32_t n_staged = 0;  // chunks staged by this group so far (selects the staging tile)
     // bias / statistics scratch are only needed here: fill them off the producer/MMA critical path
     if (p.bias != nullptr)
       for (int i = threadIdx.x - kEpiWarp0 * 32; i < p.cout; i += kEpiThreads) sbias[i] = __ldg(p.bias + i);
@@ -616,7 +619,15 @@ __global__ void __launch_bounds__(kConvThreads, 1)
         const bool late_release = p.stats != nullptr && p.stats_mode == 1;
         if (n_in > 0 && !late_release) mbar_arrive(&iempty_bar[slot]);
         // ---- stage the 64-channel rows and store them with one TMA tensor store ----
-        if (etid == 0) bulk_wait_read<0>();  // the store that used this staging buffer has drained
+        // the store that last used this staging tile has finished reading it
+        uint8_t* o_base = o_base0;
+        if (p.epi_bufs == 2) {
+          o_base += (size_t)(n_staged & 1u) * kChunkBytes;
+          if (etid == 0) bulk_wait_read<1>();
+        } else {
+          if (etid == 0) bulk_wait_read<0>();
+        }
+        ++n_staged;
         named_bar_sync(bar_id, kEpiGroupThreads);
         if (p.out_fmt == GHND_F16) epi_stage_rows<GHND_F16>(v, o_base, row);
         else epi_stage_rows<GHND_BF16>(v, o_base, row);
@@ -725,6 +736,16 @@ static const int kSmemBudget = 227 * 1024 - 1024 /*align*/ - 512 /*barriers + tm
 //   the epilogue          (~600 clk per 64-channel chunk, two groups in parallel),
 //   HBM                   (unique bytes at ~6.2 TB/s),
 // plus 10 % of the non-dominant terms; a shallow (depth-2) operand ring costs another 8 %.
+// output staging tiles per epilogue group (GHND_EPI_BUFS=1|2 overrides)
+static int epi_bufs_default() {
+  static const int v = [] {
+    const char* e = getenv("GHND_EPI_BUFS");
+    const int n = e ? atoi(e) : 1;  // A/B on the B200: the second tile costs pipeline stages, no gain
+    return n == 2 ? 2 : 1;
+  }();
+  return v;
+}
+
 static int pick_block_n(int cout, int m_tiles, int n_units, int n_taps, int row_bytes, int n_in,
                         bool has_bias) {
   const int sms = num_sms();
@@ -742,7 +763,7 @@ static int pick_block_n(int cout, int m_tiles, int n_units, int n_taps, int row_
     const double tiles = (double)m_tiles * (cout / bn);
     const double waves = (double)((int64_t)(tiles + sms - 1) / sms);
     const double stage = 128.0 * row_bytes + (double)bn * row_bytes;
-    const int fixed = 2 * kChunkBytes + (has_bias ? cout * 4 : 0);
+    const int fixed = 2 * epi_bufs_default() * kChunkBytes + (has_bias ? cout * 4 : 0);
     const bool ring2 = n_in > 0 && (kSmemBudget - fixed - 3 * (int)stage) / (n_in * kChunkBytes) < 4;
     const double per_tile = n_units * stage + (double)n_in * bn * 256.0;
     const double t_ing = waves * per_tile / (40.0 * clk);
@@ -853,7 +874,19 @@ static int finish_launch(ConvLaunch* L, const ghnd_conv_desc_t* d, int gemm_cin,
   p.in1_mask = (d->mask != nullptr && !(d->stats != nullptr && d->stats_mode == 1 && d->mask_stats_only)) ? 1 : 0;
   // shared-memory split: >= 3 pipeline stages first, then the operand ring (deep enough to keep
   // ~64 KB of residual / mask loads in flight per SM), the rest goes to more stages
-  const int fixed = 2 * kChunkBytes + (d->bias ? gemm_cout * 4 : 0) + (d->stats ? gemm_cout * 8 : 0);
+  // Two staging tiles per epilogue group when the pipeline keeps >= 3 stages (and the operand ring
+  // its 4 slots) next to them; otherwise one.
+  p.epi_bufs = epi_bufs_default();
+  if (p.epi_bufs == 2) {
+    const int fixed2 = 4 * kChunkBytes + (d->bias ? gemm_cout * 4 : 0) + (d->stats ? gemm_cout * 8 : 0);
+    const int ring2 = n_in > 0 ? ((kSmemBudget - fixed2 - 3 * p.stage_bytes) / (n_in * kChunkBytes) >= 4 ? 4 : 2) : 0;
+    const int ring1 = n_in > 0 ? ((kSmemBudget - (fixed2 - 2 * kChunkBytes) - 3 * p.stage_bytes) /
+                                              (n_in * kChunkBytes) >= 4 ? 4 : 2) : 0;
+    const int stages2 = (kSmemBudget - fixed2 - ring2 * n_in * kChunkBytes) / p.stage_bytes;
+    if (stages2 < 3 || ring2 < ring1) p.epi_bufs = 1;
+  }
+  const int fixed = 2 * p.epi_bufs * kChunkBytes + (d->bias ? gemm_cout * 4 : 0) +
+                    (d->stats ? gemm_cout * 8 : 0);
   const int stages_per_tile = (n_units + p.units_per_stage - 1) / p.units_per_stage;
   int ring = 0;
   if (n_in > 0) {
@@ -1183,7 +1216,7 @@ int ghnd_stem_conv_plan_create_k(const void* x_packed, int x_fmt, const void* w_
         p.w_res_bytes = 7 * p.b_bytes;
         p.a_box_bytes = halo_rows * p.tw * 64;
         p.stage_bytes = (p.a_box_bytes + 1023) / 1024 * 1024;
-        const int fixed = 2 * kChunkBytes + (bias ? K * 4 : 0);
+        const int fixed = 2 * p.epi_bufs * kChunkBytes + (bias ? K * 4 : 0);
         int stages = (kSmemBudget - fixed - p.w_res_bytes) / p.stage_bytes;
         if (stages > kMaxStages) stages = kMaxStages;
         if (stages < 2) {
