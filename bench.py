@@ -420,9 +420,9 @@ def run_cuda(args):
             "bn_bwd_reduce (g, x -> sums, 4 B/elem)": ("ghnd_bn_bwd_reduce", 4.0 * (raw_elems + raw3)),
             "bn_bwd_apply (g, x -> dx, 6 B/elem)": ("ghnd_bn_bwd_apply", 6.0 * (raw_elems + raw3)),
             "maxpool 3x3 s2 fwd, teacher + student (2 B in, 2 B out, +1 B argmax)":
-                ("ghnd_maxpool3x3s2", 4.0 * conv_elems + 5.0 * pool_elems),
+                ("ghnd_maxpool3x3s2_strided", 4.0 * conv_elems + 5.0 * pool_elems),
             "maxpool bwd + ReLU mask (x, dx 2 B/elem; dy + argmax 3 B/pooled elem)":
-                ("ghnd_maxpool3x3s2_bwd", 4.0 * conv_elems + 3.0 * pool_elems),
+                ("ghnd_maxpool3x3s2_bwd_strided", 4.0 * conv_elems + 3.0 * pool_elems),
         }
         for label, (name, nbytes) in streaming.items():
             if name in ep and ep[name][0] > 0:
