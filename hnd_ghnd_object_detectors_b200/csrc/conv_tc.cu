@@ -92,6 +92,9 @@ struct ConvKernelParams {
   // 2*th+5 image rows (read at row shifts by the MMA descriptors) and the weights stay resident
   int halo;
   int w_res_bytes;  // n_taps * b_bytes of resident weights behind the pipeline stages
+  int epi_debug;    // what-if switches for profiling ONLY (results become wrong): 1 = no TMA store,
+                    // 2 = no proxy fence, 4 = no tcgen05.ld, 8 = no bias/ReLU/operand math
+  int epi_prefetch; // issue the next chunk's tcgen05.ld as soon as the current chunk is staged
   int epi_bufs;     // output staging tiles per epilogue group (2: the TMA store of chunk i drains
                     // while chunk i+1 is staged)
 };
@@ -543,6 +546,14 @@ __global__ void __launch_bounds__(kConvThreads, 1)
     named_bar_sync(3, kEpiThreads);
     int it = 0;
     uint32_t cnt0 = 0;  // global chunk counter at the start of the tile
+    // Accumulator registers of the chunk being processed.  Once a chunk is staged in shared memory
+    // they are dead, so the NEXT chunk's tcgen05.ld is issued right there (pre = true) and its
+    // latency overlaps the proxy fence, the barrier, the TMA store and the statistics of the
+    // current chunk instead of heading the next iteration (ncu: 36 % of the epilogue's stall
+    // samples were the wait for tcgen05.ld).
+    uint32_t r[64];
+    bool pre = false;
+    const bool prefetch_on = p.epi_prefetch != 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it, cnt0 += n_chunks) {
       const int buf = it & 1;
       const uint32_t use = (uint32_t)it >> 1;
@@ -572,9 +583,11 @@ __global__ void __launch_bounds__(kConvThreads, 1)
       const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * p.block_n);
       for (int c = c_first; c < n_chunks; c += 2) {
         const uint32_t cnt = cnt0 + (uint32_t)c;
-        uint32_t r[64];
-        tmem_ld32(t_addr + (uint32_t)(c * 64), r);
-        tmem_ld32(t_addr + (uint32_t)(c * 64 + 32), r + 32);
+        if (!pre && !(p.epi_debug & 4)) {
+          tmem_ld32(t_addr + (uint32_t)(c * 64), r);
+          tmem_ld32(t_addr + (uint32_t)(c * 64 + 32), r + 32);
+        }
+        pre = false;
         tmem_ld_wait();
         if (c == c_last) {  // accumulator fully read by this thread: hand TMEM back to the MMA warp
           tc_fence_before();
@@ -584,7 +597,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
         float v[64];
 #pragma unroll
         for (int j = 0; j < 64; ++j) v[j] = __uint_as_float(r[j]);
-        if (p.bias != nullptr) {
+        if (p.bias != nullptr && !(p.epi_debug & 8)) {
           const float4* b4 = reinterpret_cast<const float4*>(sbias + ch);
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
@@ -631,9 +644,33 @@ __global__ void __launch_bounds__(kConvThreads, 1)
         named_bar_sync(bar_id, kEpiGroupThreads);
         if (p.out_fmt == GHND_F16) epi_stage_rows<GHND_F16>(v, o_base, row);
         else epi_stage_rows<GHND_BF16>(v, o_base, row);
-        fence_proxy_async();
+        if (prefetch_on) {
+          if (c + 2 < n_chunks) {  // this group's next chunk of the same accumulator
+            tmem_ld32(t_addr + (uint32_t)((c + 2) * 64), r);
+            tmem_ld32(t_addr + (uint32_t)((c + 2) * 64 + 32), r + 32);
+            pre = true;
+          } else if (tile + (int)gridDim.x < p.total_tiles) {
+            // first chunk of the next tile, if this group has one there and that accumulator is
+            // already complete (never wait here: the MMA warp may still need our own release)
+            const int c_next = (int)(((cnt0 + (uint32_t)n_chunks) ^ (uint32_t)group) & 1u);
+            if (c_next < n_chunks) {
+              const int nbuf = buf ^ 1;
+              const uint32_t nuse = (uint32_t)(it + 1) >> 1;
+              const bool ready = mbar_try_wait(&tfull_bar[nbuf], nuse & 1u);
+              if (__all_sync(0xffffffffu, ready)) {
+                tc_fence_after();
+                const uint32_t n_addr =
+                    tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(nbuf * p.block_n);
+                tmem_ld32(n_addr + (uint32_t)(c_next * 64), r);
+                tmem_ld32(n_addr + (uint32_t)(c_next * 64 + 32), r + 32);
+                pre = true;
+              }
+            }
+          }
+        }
+        if (!(p.epi_debug & 2)) fence_proxy_async();
         named_bar_sync(bar_id, kEpiGroupThreads);
-        if (etid == 0) {
+        if (etid == 0 && !(p.epi_debug & 1)) {
           tma_store_4d(&p.tmap_out, o_base, ch, w0, h0, img);
           bulk_commit();
         }
@@ -869,6 +906,15 @@ static int finish_launch(ConvLaunch* L, const ghnd_conv_desc_t* d, int gemm_cin,
   p.relu = d->relu;
   p.halo = 0;
   p.w_res_bytes = 0;
+  {
+    static const bool pf = [] {
+      const char* e = getenv("GHND_EPI_PREFETCH");  // A/B on the B200: no gain, off by default
+      return e != nullptr && atoi(e) != 0;
+    }();
+    p.epi_prefetch = pf ? 1 : 0;
+    const char* dbg = getenv("GHND_EPI_DEBUG");
+    p.epi_debug = dbg ? atoi(dbg) : 0;
+  }
   p.stats = d->stats;
   p.stats_mode = d->stats != nullptr ? d->stats_mode : 0;
   p.in1_mask = (d->mask != nullptr && !(d->stats != nullptr && d->stats_mode == 1 && d->mask_stats_only)) ? 1 : 0;

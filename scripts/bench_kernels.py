@@ -74,6 +74,31 @@ def rnd(shape, dtype):
 
 f16, bf16 = torch.float16, torch.bfloat16
 
+if want("stem") or want("conv"):
+    # the two-model stem (K=128, halo mode) and two output-heavy 1x1 convs of the frozen trunk
+    from hnd_ghnd_object_detectors_b200 import _lib
+    Hp, Wp = 800, 1344
+    packed = rnd((N, Hp + 6, Wp + 8, 4), f16)
+    w2 = rnd((128, 7, 32), f16)
+    bias2 = torch.randn(128, device=dev)
+    y2 = torch.empty((N, Hp // 2, Wp // 2, 128), dtype=f16, device=dev)
+    sp = ops.StemPlan(packed, w2, bias2, y2, N, Hp, Wp)
+    us = timed(sp.run)
+    print("%-46s %8.1f us %9.1f MB out %7.1f TFLOP/s" % ("stem K=128 (4 launches)", us, y2.numel() * 2 / 1e6,
+                                                          sp.flops / us / 1e6), flush=True)
+    for (n, h, w, c, k, res) in [(N, 200, 336, 64, 256, True), (2 * N, 100, 168, 128, 512, True),
+                                 (2 * N, 50, 84, 256, 1024, True), (N, 200, 336, 64, 256, False)]:
+        x = rnd((n, h, w, c), f16)
+        wt = rnd((k, 1, 1, c), f16)
+        b = torch.randn(k, device=dev)
+        r_ = rnd((n, h, w, k), f16) if res else None
+        y = torch.empty((n, h, w, k), dtype=f16, device=dev)
+        cp = ops.ConvPlan(_lib.CONV_FWD, n, h, w, c, k, 1, 1, 1, 0, x, wt, y, bias=b, residual=r_, relu=True)
+        us = timed(cp.run)
+        nbytes = x.numel() * 2 + y.numel() * 2 * (2 if res else 1)
+        print("%-46s %8.1f us %9.1f MB %8.1f GB/s %7.1f TFLOP/s" % (cp.desc[:46], us, nbytes / 1e6,
+                                                                     nbytes / us / 1e3, cp.flops / us / 1e6), flush=True)
+
 if want("maxpool"):
     x = rnd((N, 400, 672, 64), f16).relu_()
     y = torch.empty((N, 200, 336, 64), dtype=f16, device=dev)
