@@ -92,6 +92,8 @@ struct ConvKernelParams {
   // 2*th+5 image rows (read at row shifts by the MMA descriptors) and the weights stay resident
   int halo;
   int w_res_bytes;  // n_taps * b_bytes of resident weights behind the pipeline stages
+  int epi_half;     // f16 outputs without mask / statistics: bias, residual and ReLU in packed half2
+                    // after ONE fp32 -> f16 conversion of the accumulator (half the epilogue math)
   int epi_debug;    // what-if switches for profiling ONLY (results become wrong): 1 = no TMA store,
                     // 2 = no proxy fence, 4 = no tcgen05.ld, 8 = no bias/ReLU/operand math
   int epi_prefetch; // issue the next chunk's tcgen05.ld as soon as the current chunk is staged
@@ -274,6 +276,45 @@ __device__ __forceinline__ void epi_stats2_rows(const uint8_t* base, const uint8
   atomicAdd(&sstat[ch + 2 * lane + 1], s1);
   atomicAdd(&sstat[cout + ch + 2 * lane], q0);
   atomicAdd(&sstat[cout + ch + 2 * lane + 1], q1);
+}
+
+// Packed-half2 epilogue of one accumulator row (64 channels): h = f16(acc); h += bias; h += residual;
+// ReLU -> 32 packed registers.  bias16: 64 halves (128 B) of this chunk; res: swizzled residual tile
+// or nullptr.  The caller releases the operand slot, then stages h (epi_stage_packed).
+__device__ __forceinline__ void epi_half_rows(const uint32_t* r, const uint8_t* bias16,
+                                              const uint8_t* res, int relu, uint32_t* out, int row) {
+  const __half2 zero = __float2half2_rn(0.f);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    __half2 h[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      h[e] = __floats2half2_rn(__uint_as_float(r[8 * j + 2 * e]), __uint_as_float(r[8 * j + 2 * e + 1]));
+    if (bias16 != nullptr) {
+      const uint4 b = *reinterpret_cast<const uint4*>(bias16 + j * 16);
+      const __half2* bh = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) h[e] = __hadd2(h[e], bh[e]);
+    }
+    if (res != nullptr) {
+      const uint4 q = *reinterpret_cast<const uint4*>(res + swz_off(row, j));
+      const __half2* qh = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) h[e] = __hadd2(h[e], qh[e]);
+    }
+    if (relu) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) h[e] = __hmax2(h[e], zero);
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) out[4 * j + e] = *reinterpret_cast<const uint32_t*>(&h[e]);
+  }
+}
+__device__ __forceinline__ void epi_stage_packed(const uint32_t* h, uint8_t* stage, int row) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<uint4*>(stage + swz_off(row, j)) =
+        make_uint4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
 }
 
 __global__ void __launch_bounds__(kConvThreads, 1)
@@ -539,8 +580,15 @@ __global__ void __launch_bounds__(kConvThreads, 1)
     uint8_t* const o_base0 = epi_out + (size_t)group * p.epi_bufs * kChunkBytes;
     uint32_t n_staged = 0;  // chunks staged by this group so far (selects the staging tile)
     // bias / statistics scratch are only needed here: fill them off the producer/MMA critical path
-    if (p.bias != nullptr)
-      for (int i = threadIdx.x - kEpiWarp0 * 32; i < p.cout; i += kEpiThreads) sbias[i] = __ldg(p.bias + i);
+    if (p.bias != nullptr) {
+      if (p.epi_half) {
+        __half* hb = reinterpret_cast<__half*>(sbias);
+        for (int i = threadIdx.x - kEpiWarp0 * 32; i < p.cout; i += kEpiThreads)
+          hb[i] = __float2half_rn(__ldg(p.bias + i));
+      } else {
+        for (int i = threadIdx.x - kEpiWarp0 * 32; i < p.cout; i += kEpiThreads) sbias[i] = __ldg(p.bias + i);
+      }
+    }
     if (p.stats != nullptr)
       for (int i = threadIdx.x - kEpiWarp0 * 32; i < 2 * p.cout; i += kEpiThreads) sstat[i] = 0.f;
     named_bar_sync(3, kEpiThreads);
@@ -594,6 +642,33 @@ __global__ void __launch_bounds__(kConvThreads, 1)
           mbar_arrive(&tempty_bar[buf]);
         }
         const int ch = n_tile * p.block_n + c * 64;
+        if (p.epi_half) {
+          // ---- packed-half2 path: f16 output, optional bias / f16 residual / ReLU ----
+          const int slot = fd_ring_r(p, cnt);
+          const uint8_t* in_base = epi_in + (size_t)slot * n_in * kChunkBytes;
+          if (n_in > 0) mbar_wait(&ifull_bar[slot], (uint32_t)fd_div(p.fd_ring, (int)cnt) & 1u);
+          uint32_t hp[32];
+          epi_half_rows(r, p.bias != nullptr ? reinterpret_cast<const uint8_t*>(sbias) + ch * 2 : nullptr,
+                        p.has_in0 ? in_base : nullptr, p.relu, hp, row);
+          if (n_in > 0) mbar_arrive(&iempty_bar[slot]);  // operand buffer consumed
+          uint8_t* o_base = o_base0;
+          if (p.epi_bufs == 2) {
+            o_base += (size_t)(n_staged & 1u) * kChunkBytes;
+            if (etid == 0) bulk_wait_read<1>();
+          } else {
+            if (etid == 0) bulk_wait_read<0>();
+          }
+          ++n_staged;
+          named_bar_sync(bar_id, kEpiGroupThreads);
+          epi_stage_packed(hp, o_base, row);
+          fence_proxy_async();
+          named_bar_sync(bar_id, kEpiGroupThreads);
+          if (etid == 0) {
+            tma_store_4d(&p.tmap_out, o_base, ch, w0, h0, img);
+            bulk_commit();
+          }
+          continue;
+        }
         float v[64];
 #pragma unroll
         for (int j = 0; j < 64; ++j) v[j] = __uint_as_float(r[j]);
@@ -914,6 +989,14 @@ static int finish_launch(ConvLaunch* L, const ghnd_conv_desc_t* d, int gemm_cin,
     p.epi_prefetch = pf ? 1 : 0;
     const char* dbg = getenv("GHND_EPI_DEBUG");
     p.epi_debug = dbg ? atoi(dbg) : 0;
+    static const bool half_ok = [] {
+      const char* e = getenv("GHND_EPI_HALF");
+      return e == nullptr || atoi(e) != 0;
+    }();
+    p.epi_half = (half_ok && d->dst_fmt == GHND_F16 && d->mask == nullptr && d->stats == nullptr &&
+                  !d->accumulate && (d->residual == nullptr || d->res_fmt == GHND_F16) &&
+                  p.epi_debug == 0 && !p.epi_prefetch)
+                     ? 1 : 0;
   }
   p.stats = d->stats;
   p.stats_mode = d->stats != nullptr ? d->stats_mode : 0;
