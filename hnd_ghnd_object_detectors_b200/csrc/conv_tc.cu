@@ -751,17 +751,8 @@ __global__ void __launch_bounds__(kConvThreads, 1)
         }
         if (p.stats != nullptr) {
           if (p.stats_mode == 1) {
-            if (p.out_fmt == GHND_F16) {
-              if (p.in1_fmt == GHND_F16)
-                epi_stats2_rows<GHND_F16, GHND_F16>(o_base, m_base, quarter, lane, valid, sstat, ch, p.cout);
-              else
-                epi_stats2_rows<GHND_F16, GHND_BF16>(o_base, m_base, quarter, lane, valid, sstat, ch, p.cout);
-            } else {
-              if (p.in1_fmt == GHND_F16)
-                epi_stats2_rows<GHND_BF16, GHND_F16>(o_base, m_base, quarter, lane, valid, sstat, ch, p.cout);
-              else
-                epi_stats2_rows<GHND_BF16, GHND_BF16>(o_base, m_base, quarter, lane, valid, sstat, ch, p.cout);
-            }
+            // bf16 gradient out, f16 activation operand (the only combination the plans accept)
+            epi_stats2_rows<GHND_BF16, GHND_F16>(o_base, m_base, quarter, lane, valid, sstat, ch, p.cout);
             mbar_arrive(&iempty_bar[slot]);  // now the operand buffer may be refilled
           } else if (p.out_fmt == GHND_F16) {
             epi_stats_rows<GHND_F16>(o_base, quarter, lane, valid, sstat, ch, p.cout);
@@ -1107,6 +1098,9 @@ int ghnd_conv_plan_create(const ghnd_conv_desc_t* d, ghnd_conv_plan_t** out) {
   GHND_CHECK_ARG(d->stats == nullptr || d->stats_mode != 0 ||
                      (d->kind == GHND_CONV_FWD && d->stride == 1 && d->K <= 1024),
                  "conv: fused output statistics need a stride-1 forward conv with K <= 1024");
+  GHND_CHECK_ARG(d->stats == nullptr || d->stats_mode != 1 ||
+                     (d->dst_fmt == GHND_BF16 && d->mask_fmt == GHND_F16),
+                 "conv: BN-backward statistics need a bf16 output and an f16 mask operand");
   GHND_CHECK_ARG(d->stats == nullptr || d->stats_mode != 1 ||
                      (d->stride == 1 && d->mask != nullptr && !d->accumulate &&
                       (d->kind == GHND_CONV_FWD ? d->K : d->C) <= 1024),
