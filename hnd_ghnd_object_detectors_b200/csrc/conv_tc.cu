@@ -317,6 +317,11 @@ __device__ __forceinline__ void epi_stage_packed(const uint32_t* h, uint8_t* sta
         make_uint4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
 }
 
+// HALF / HALO select the epilogue (packed half2 vs fp32) and the operand pipeline (stem halo vs
+// im2col units) at COMPILE time: each instantiation carries only its own paths.  The kernel is
+// sensitive to code size (a build with all variants in one 7.2k-instruction kernel lost 10-20 % on
+// the epilogue-bound layers against a 5.1k-instruction build, same algorithm).
+template <bool HALF, bool HALO>
 __global__ void __launch_bounds__(kConvThreads, 1)
     conv_tc_kernel(const __grid_constant__ ConvKernelParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -325,7 +330,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
                                              ~(uintptr_t)1023);
   const int n_in = p.has_in0 + p.has_in1;
   uint8_t* wres = smem + (size_t)p.n_stages * p.stage_bytes;               // halo mode: resident weights
-  uint8_t* epi_out = wres + (p.halo ? p.w_res_bytes : 0);                  // [2 groups][kChunkBytes]
+  uint8_t* epi_out = wres + (HALO ? p.w_res_bytes : 0);                  // [2 groups][kChunkBytes]
   uint8_t* epi_in = epi_out + (size_t)2 * p.epi_bufs * kChunkBytes;        // [ring][n_in][kChunkBytes]
   float* sbias = reinterpret_cast<float*>(epi_in + (size_t)p.ring * n_in * kChunkBytes);  // [cout]
   float* sstat = sbias + (p.bias != nullptr ? p.cout : 0);                 // [2*cout] when stats
@@ -377,7 +382,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
   const int upst = p.units_per_stage;
   const int n_chunks = p.block_n >> 6;
 
-  if (warp == 0 && p.halo) {
+  if (HALO && warp == 0) {
     // ===================== TMA producer, stem halo mode ==========================================
     // weights once; then ONE box per tile: 2*th+5 image rows x tw column slots x 64 B
     if (elect_one()) {
@@ -406,7 +411,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
         phase ^= 1;
       }
     }
-  } else if (warp == 1 && p.halo) {
+  } else if (HALO && warp == 1) {
     // ===================== MMA issuer, stem halo mode ============================================
     // filter row r reads the halo tile at a shift of r image rows (r * tw * 64 B); output rows are
     // two image rows apart (SBO of A = 2 * tw * 64 B).  tw == 8: one 8-row swizzle atom per image row,
@@ -444,7 +449,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
         phase ^= 1;
       }
     }
-  } else if (warp == 0) {
+  } else if (!HALO && warp == 0) {
     // ===================== TMA producer (whole warp converged, one elected lane issues) ==========
     int stage = 0;
     uint32_t phase = 0;
@@ -489,7 +494,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (!HALO && warp == 1) {
     // ===================== MMA issuer (whole warp converged, one elected lane issues) ============
     int stage = 0;
     uint32_t phase = 0;
@@ -581,7 +586,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
     uint32_t n_staged = 0;  // chunks staged by this group so far (selects the staging tile)
     // bias / statistics scratch are only needed here: fill them off the producer/MMA critical path
     if (p.bias != nullptr) {
-      if (p.epi_half) {
+      if (HALF) {
         __half* hb = reinterpret_cast<__half*>(sbias);
         for (int i = threadIdx.x - kEpiWarp0 * 32; i < p.cout; i += kEpiThreads)
           hb[i] = __float2half_rn(__ldg(p.bias + i));
@@ -642,7 +647,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
           mbar_arrive(&tempty_bar[buf]);
         }
         const int ch = n_tile * p.block_n + c * 64;
-        if (p.epi_half) {
+        if (HALF) {
           // ---- packed-half2 path: f16 output, optional bias / f16 residual / ReLU ----
           const int slot = fd_ring_r(p, cnt);
           const uint8_t* in_base = epi_in + (size_t)slot * n_in * kChunkBytes;
@@ -1050,7 +1055,12 @@ static cudaError_t launch_conv(const ConvLaunch& L, cudaStream_t st) {
   static const bool no_pdl = getenv("GHND_NO_PDL") != nullptr;  // debugging switch
   cfg.attrs = attr;
   cfg.numAttrs = no_pdl ? 0 : 1;
-  return cudaLaunchKernelEx(&cfg, conv_tc_kernel, L.p);
+  if (L.p.epi_half) {
+    if (L.p.halo) return cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, true>, L.p);
+    return cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, false>, L.p);
+  }
+  if (L.p.halo) return cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, true>, L.p);
+  return cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, false>, L.p);
 }
 
 static bool fmt_ok(int f) { return f == GHND_F16 || f == GHND_BF16; }
@@ -1058,8 +1068,17 @@ static bool fmt_ok(int f) { return f == GHND_F16 || f == GHND_BF16; }
 static int set_conv_attr() {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<false, false>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               227 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               227 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               227 * 1024);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_tc_kernel)");
     attr_set = true;
   }
