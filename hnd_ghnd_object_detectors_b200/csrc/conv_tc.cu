@@ -321,7 +321,8 @@ __device__ __forceinline__ void epi_stage_packed(const uint32_t* h, uint8_t* sta
 // im2col units) at COMPILE time: each instantiation carries only its own paths.  The kernel is
 // sensitive to code size (a build with all variants in one 7.2k-instruction kernel lost 10-20 % on
 // the epilogue-bound layers against a 5.1k-instruction build, same algorithm).
-template <bool HALF, bool HALO>
+// STATS: the launch accumulates per-channel statistics (kept out of the other instantiations)
+template <bool HALF, bool HALO, bool STATS>
 __global__ void __launch_bounds__(kConvThreads, 1)
     conv_tc_kernel(const __grid_constant__ ConvKernelParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -334,7 +335,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
   uint8_t* epi_in = epi_out + (size_t)2 * p.epi_bufs * kChunkBytes;        // [ring][n_in][kChunkBytes]
   float* sbias = reinterpret_cast<float*>(epi_in + (size_t)p.ring * n_in * kChunkBytes);  // [cout]
   float* sstat = sbias + (p.bias != nullptr ? p.cout : 0);                 // [2*cout] when stats
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sstat + (p.stats != nullptr ? 2 * p.cout : 0));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sstat + (STATS ? 2 * p.cout : 0));
   uint64_t* full_bar = bars;                        // [kMaxStages]
   uint64_t* empty_bar = full_bar + kMaxStages;      // [kMaxStages]
   uint64_t* tfull_bar = empty_bar + kMaxStages;     // [2]
@@ -594,7 +595,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
         for (int i = threadIdx.x - kEpiWarp0 * 32; i < p.cout; i += kEpiThreads) sbias[i] = __ldg(p.bias + i);
       }
     }
-    if (p.stats != nullptr)
+    if (STATS)
       for (int i = threadIdx.x - kEpiWarp0 * 32; i < 2 * p.cout; i += kEpiThreads) sstat[i] = 0.f;
     named_bar_sync(3, kEpiThreads);
     int it = 0;
@@ -617,7 +618,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
       h0 *= p.th;
       w0 *= p.tw;
       uint32_t valid = 0xffffffffu;
-      if (p.stats != nullptr) {
+      if (STATS) {
         int rh, rw;
         fd_divmod(p.fd_tw, row, rh, rw);
         valid = __ballot_sync(0xffffffffu, rh < p.th && h0 + rh < p.lim_h && w0 + rw < p.lim_w);
@@ -709,7 +710,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
           else epi_add_rows<GHND_BF16>(v, in_base, row);
         }
         // operand buffer consumed (the BN-backward statistics still read the in1 tile below)
-        const bool late_release = p.stats != nullptr && p.stats_mode == 1;
+        const bool late_release = STATS && p.stats_mode == 1;
         if (n_in > 0 && !late_release) mbar_arrive(&iempty_bar[slot]);
         // ---- stage the 64-channel rows and store them with one TMA tensor store ----
         // the store that last used this staging tile has finished reading it
@@ -754,7 +755,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
           tma_store_4d(&p.tmap_out, o_base, ch, w0, h0, img);
           bulk_commit();
         }
-        if (p.stats != nullptr) {
+        if (STATS) {
           if (p.stats_mode == 1) {
             // bf16 gradient out, f16 activation operand (the only combination the plans accept)
             epi_stats2_rows<GHND_BF16, GHND_F16>(o_base, m_base, quarter, lane, valid, sstat, ch, p.cout);
@@ -768,7 +769,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
       }
     }
     if (etid == 0) bulk_wait_all();
-    if (p.stats != nullptr) {
+    if (STATS) {
       named_bar_sync(3, kEpiThreads);  // both groups: all shared-memory partial sums are in
       for (int i = threadIdx.x - kEpiWarp0 * 32; i < 2 * p.cout; i += kEpiThreads)
         atomicAdd(p.stats + i, (double)sstat[i]);
@@ -1055,12 +1056,13 @@ static cudaError_t launch_conv(const ConvLaunch& L, cudaStream_t st) {
   static const bool no_pdl = getenv("GHND_NO_PDL") != nullptr;  // debugging switch
   cfg.attrs = attr;
   cfg.numAttrs = no_pdl ? 0 : 1;
-  if (L.p.epi_half) {
-    if (L.p.halo) return cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, true>, L.p);
-    return cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, false>, L.p);
+  if (L.p.epi_half) {  // never with statistics
+    if (L.p.halo) return cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, true, false>, L.p);
+    return cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, false, false>, L.p);
   }
-  if (L.p.halo) return cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, true>, L.p);
-  return cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, false>, L.p);
+  if (L.p.halo) return cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, true, false>, L.p);
+  if (L.p.stats != nullptr) return cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, false, true>, L.p);
+  return cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, false, false>, L.p);
 }
 
 static bool fmt_ok(int f) { return f == GHND_F16 || f == GHND_BF16; }
@@ -1068,17 +1070,17 @@ static bool fmt_ok(int f) { return f == GHND_F16 || f == GHND_BF16; }
 static int set_conv_attr() {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<false, false>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(conv_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               227 * 1024);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(conv_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               227 * 1024);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(conv_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               227 * 1024);
+    cudaError_t e = cudaSuccess;
+#define GHND_SET_SMEM(...)                                                                        \
+  if (e == cudaSuccess)                                                                           \
+    e = cudaFuncSetAttribute(conv_tc_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                             227 * 1024)
+    GHND_SET_SMEM(false, false, false);
+    GHND_SET_SMEM(false, false, true);
+    GHND_SET_SMEM(false, true, false);
+    GHND_SET_SMEM(true, false, false);
+    GHND_SET_SMEM(true, true, false);
+#undef GHND_SET_SMEM
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_tc_kernel)");
     attr_set = true;
   }
