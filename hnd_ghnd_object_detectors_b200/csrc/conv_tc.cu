@@ -278,36 +278,77 @@ __device__ __forceinline__ void epi_stats2_rows(const uint8_t* base, const uint8
   atomicAdd(&sstat[cout + ch + 2 * lane + 1], q1);
 }
 
-// Packed-half2 epilogue of one accumulator row (64 channels): h = f16(acc); h += bias; h += residual;
-// ReLU -> 32 packed registers.  bias16: 64 halves (128 B) of this chunk; res: swizzled residual tile
-// or nullptr.  The caller releases the operand slot, then stages h (epi_stage_packed).
-__device__ __forceinline__ void epi_half_rows(const uint32_t* r, const uint8_t* bias16,
-                                              const uint8_t* res, int relu, uint32_t* out, int row) {
-  const __half2 zero = __float2half2_rn(0.f);
+// Packed 16-bit-pair helpers on raw 32-bit words (FMT = GHND_F16 or GHND_BF16)
+template <int FMT>
+__device__ __forceinline__ uint32_t h2_add(uint32_t a, uint32_t b) {
+  if (FMT == GHND_F16) {
+    const __half2 r = __hadd2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&r);
+  }
+  const __nv_bfloat162 r =
+      __hadd2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+template <int FMT>
+__device__ __forceinline__ uint32_t h2_relu(uint32_t a) {
+  if (FMT == GHND_F16) {
+    const __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&a), __float2half2_rn(0.f));
+    return *reinterpret_cast<const uint32_t*>(&r);
+  }
+  const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a), __float2bfloat162_rn(0.f));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+
+// Packed epilogue of one accumulator row (64 channels), all arithmetic in the OUTPUT format after one
+// fp32 -> 16-bit conversion of the accumulator:
+//   h = cvt(acc); h += bias; h += in0 (residual, !in0_post); ReLU; h &= (mask > 0); h += in0 (in0_post)
+// bias16: 64 values (128 B) of this chunk in the output format; in0: swizzled operand tile in the
+// output format; mask: swizzled f16 tile (the forward activation).
+template <int FMT>
+__device__ __forceinline__ void epi_half_rows(const uint32_t* r, const uint8_t* bias16, const uint8_t* in0,
+                                              int in0_post, const uint8_t* mask, int relu, uint32_t* out,
+                                              int row) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    __half2 h[4];
+    uint32_t h[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e)
-      h[e] = __floats2half2_rn(__uint_as_float(r[8 * j + 2 * e]), __uint_as_float(r[8 * j + 2 * e + 1]));
+      h[e] = pack2_t<FMT>(__uint_as_float(r[8 * j + 2 * e]), __uint_as_float(r[8 * j + 2 * e + 1]));
     if (bias16 != nullptr) {
       const uint4 b = *reinterpret_cast<const uint4*>(bias16 + j * 16);
-      const __half2* bh = reinterpret_cast<const __half2*>(&b);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) h[e] = __hadd2(h[e], bh[e]);
+      h[0] = h2_add<FMT>(h[0], b.x);
+      h[1] = h2_add<FMT>(h[1], b.y);
+      h[2] = h2_add<FMT>(h[2], b.z);
+      h[3] = h2_add<FMT>(h[3], b.w);
     }
-    if (res != nullptr) {
-      const uint4 q = *reinterpret_cast<const uint4*>(res + swz_off(row, j));
-      const __half2* qh = reinterpret_cast<const __half2*>(&q);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) h[e] = __hadd2(h[e], qh[e]);
+    uint4 q = make_uint4(0u, 0u, 0u, 0u);
+    if (in0 != nullptr) q = *reinterpret_cast<const uint4*>(in0 + swz_off(row, j));
+    if (in0 != nullptr && !in0_post) {
+      h[0] = h2_add<FMT>(h[0], q.x);
+      h[1] = h2_add<FMT>(h[1], q.y);
+      h[2] = h2_add<FMT>(h[2], q.z);
+      h[3] = h2_add<FMT>(h[3], q.w);
     }
     if (relu) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) h[e] = __hmax2(h[e], zero);
+      for (int e = 0; e < 4; ++e) h[e] = h2_relu<FMT>(h[e]);
+    }
+    if (FMT == GHND_BF16 && mask != nullptr) {  // data gradients: ReLU mask from the f16 activation
+      const uint4 m = *reinterpret_cast<const uint4*>(mask + swz_off(row, j));
+      const __half2 z = __float2half2_rn(0.f);
+      h[0] &= __hgt2_mask(*reinterpret_cast<const __half2*>(&m.x), z);
+      h[1] &= __hgt2_mask(*reinterpret_cast<const __half2*>(&m.y), z);
+      h[2] &= __hgt2_mask(*reinterpret_cast<const __half2*>(&m.z), z);
+      h[3] &= __hgt2_mask(*reinterpret_cast<const __half2*>(&m.w), z);
+    }
+    if (in0 != nullptr && in0_post) {
+      h[0] = h2_add<FMT>(h[0], q.x);
+      h[1] = h2_add<FMT>(h[1], q.y);
+      h[2] = h2_add<FMT>(h[2], q.z);
+      h[3] = h2_add<FMT>(h[3], q.w);
     }
 #pragma unroll
-    for (int e = 0; e < 4; ++e) out[4 * j + e] = *reinterpret_cast<const uint32_t*>(&h[e]);
+    for (int e = 0; e < 4; ++e) out[4 * j + e] = h[e];
   }
 }
 __device__ __forceinline__ void epi_stage_packed(const uint32_t* h, uint8_t* stage, int row) {
@@ -317,12 +358,12 @@ __device__ __forceinline__ void epi_stage_packed(const uint32_t* h, uint8_t* sta
         make_uint4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
 }
 
-// HALF / HALO select the epilogue (packed half2 vs fp32) and the operand pipeline (stem halo vs
+// EPI (0 fp32, 1 packed f16, 2 packed bf16 + mask) / HALO select the epilogue and the operand pipeline (stem halo vs
 // im2col units) at COMPILE time: each instantiation carries only its own paths.  The kernel is
 // sensitive to code size (a build with all variants in one 7.2k-instruction kernel lost 10-20 % on
 // the epilogue-bound layers against a 5.1k-instruction build, same algorithm).
 // STATS: the launch accumulates per-channel statistics (kept out of the other instantiations)
-template <bool HALF, bool HALO, bool STATS>
+template <int EPI, bool HALO, bool STATS>
 __global__ void __launch_bounds__(kConvThreads, 1)
     conv_tc_kernel(const __grid_constant__ ConvKernelParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -587,10 +628,10 @@ __global__ void __launch_bounds__(kConvThreads, 1)
     uint32_t n_staged = 0;  // chunks staged by this group so far (selects the staging tile)
     // bias / statistics scratch are only needed here: fill them off the producer/MMA critical path
     if (p.bias != nullptr) {
-      if (HALF) {
-        __half* hb = reinterpret_cast<__half*>(sbias);
+      if (EPI != 0) {
+        uint16_t* hb = reinterpret_cast<uint16_t*>(sbias);
         for (int i = threadIdx.x - kEpiWarp0 * 32; i < p.cout; i += kEpiThreads)
-          hb[i] = __float2half_rn(__ldg(p.bias + i));
+          hb[i] = float_to_h16(__ldg(p.bias + i), p.out_fmt);
       } else {
         for (int i = threadIdx.x - kEpiWarp0 * 32; i < p.cout; i += kEpiThreads) sbias[i] = __ldg(p.bias + i);
       }
@@ -648,14 +689,22 @@ __global__ void __launch_bounds__(kConvThreads, 1)
           mbar_arrive(&tempty_bar[buf]);
         }
         const int ch = n_tile * p.block_n + c * 64;
-        if (HALF) {
+        if (EPI != 0) {
           // ---- packed-half2 path: f16 output, optional bias / f16 residual / ReLU ----
           const int slot = fd_ring_r(p, cnt);
           const uint8_t* in_base = epi_in + (size_t)slot * n_in * kChunkBytes;
           if (n_in > 0) mbar_wait(&ifull_bar[slot], (uint32_t)fd_div(p.fd_ring, (int)cnt) & 1u);
           uint32_t hp[32];
-          epi_half_rows(r, p.bias != nullptr ? reinterpret_cast<const uint8_t*>(sbias) + ch * 2 : nullptr,
-                        p.has_in0 ? in_base : nullptr, p.relu, hp, row);
+          {
+            const uint8_t* b16 = p.bias != nullptr ? reinterpret_cast<const uint8_t*>(sbias) + ch * 2 : nullptr;
+            const uint8_t* i0 = p.has_in0 ? in_base : nullptr;
+            if (EPI == 1) {
+              epi_half_rows<GHND_F16>(r, b16, i0, 0, nullptr, p.relu, hp, row);
+            } else {
+              const uint8_t* mk = (p.has_in1 && p.in1_mask) ? in_base + p.has_in0 * kChunkBytes : nullptr;
+              epi_half_rows<GHND_BF16>(r, b16, i0, p.in0_post, mk, p.relu, hp, row);
+            }
+          }
           if (n_in > 0) mbar_arrive(&iempty_bar[slot]);  // operand buffer consumed
           uint8_t* o_base = o_base0;
           if (p.epi_bufs == 2) {
@@ -986,14 +1035,22 @@ static int finish_launch(ConvLaunch* L, const ghnd_conv_desc_t* d, int gemm_cin,
     p.epi_prefetch = pf ? 1 : 0;
     const char* dbg = getenv("GHND_EPI_DEBUG");
     p.epi_debug = dbg ? atoi(dbg) : 0;
-    static const bool half_ok = [] {
+    // epi_half: 0 fp32 epilogue; 1 packed f16 (forward: bias / f16 residual / ReLU); 2 packed bf16 (data
+    // gradients: bf16 residual or accumulate, ReLU mask from the f16 activation).  GHND_EPI_HALF=0|1|2
+    // caps the level.
+    static const int half_level = [] {
       const char* e = getenv("GHND_EPI_HALF");
-      return e == nullptr || atoi(e) != 0;
+      return e == nullptr ? 2 : atoi(e);
     }();
-    p.epi_half = (half_ok && d->dst_fmt == GHND_F16 && d->mask == nullptr && d->stats == nullptr &&
-                  !d->accumulate && (d->residual == nullptr || d->res_fmt == GHND_F16) &&
-                  p.epi_debug == 0 && !p.epi_prefetch)
-                     ? 1 : 0;
+    p.epi_half = 0;
+    if (d->stats == nullptr && p.epi_debug == 0 && !p.epi_prefetch) {
+      if (half_level >= 1 && d->dst_fmt == GHND_F16 && d->mask == nullptr && !d->accumulate &&
+          (d->residual == nullptr || d->res_fmt == GHND_F16))
+        p.epi_half = 1;
+      else if (half_level >= 2 && d->dst_fmt == GHND_BF16 && (d->mask == nullptr || d->mask_fmt == GHND_F16) &&
+               (d->residual == nullptr || d->res_fmt == GHND_BF16))
+        p.epi_half = 2;
+    }
   }
   p.stats = d->stats;
   p.stats_mode = d->stats != nullptr ? d->stats_mode : 0;
@@ -1056,13 +1113,14 @@ static cudaError_t launch_conv(const ConvLaunch& L, cudaStream_t st) {
   static const bool no_pdl = getenv("GHND_NO_PDL") != nullptr;  // debugging switch
   cfg.attrs = attr;
   cfg.numAttrs = no_pdl ? 0 : 1;
-  if (L.p.epi_half) {  // never with statistics
-    if (L.p.halo) return cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, true, false>, L.p);
-    return cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, false, false>, L.p);
+  if (L.p.epi_half == 1) {  // packed epilogues never carry statistics
+    if (L.p.halo) return cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, true, false>, L.p);
+    return cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, false, false>, L.p);
   }
-  if (L.p.halo) return cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, true, false>, L.p);
-  if (L.p.stats != nullptr) return cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, false, true>, L.p);
-  return cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, false, false>, L.p);
+  if (L.p.epi_half == 2 && !L.p.halo) return cudaLaunchKernelEx(&cfg, conv_tc_kernel<2, false, false>, L.p);
+  if (L.p.halo) return cudaLaunchKernelEx(&cfg, conv_tc_kernel<0, true, false>, L.p);
+  if (L.p.stats != nullptr) return cudaLaunchKernelEx(&cfg, conv_tc_kernel<0, false, true>, L.p);
+  return cudaLaunchKernelEx(&cfg, conv_tc_kernel<0, false, false>, L.p);
 }
 
 static bool fmt_ok(int f) { return f == GHND_F16 || f == GHND_BF16; }
@@ -1075,11 +1133,12 @@ static int set_conv_attr() {
   if (e == cudaSuccess)                                                                           \
     e = cudaFuncSetAttribute(conv_tc_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                              227 * 1024)
-    GHND_SET_SMEM(false, false, false);
-    GHND_SET_SMEM(false, false, true);
-    GHND_SET_SMEM(false, true, false);
-    GHND_SET_SMEM(true, false, false);
-    GHND_SET_SMEM(true, true, false);
+    GHND_SET_SMEM(0, false, false);
+    GHND_SET_SMEM(0, false, true);
+    GHND_SET_SMEM(0, true, false);
+    GHND_SET_SMEM(1, false, false);
+    GHND_SET_SMEM(1, true, false);
+    GHND_SET_SMEM(2, false, false);
 #undef GHND_SET_SMEM
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_tc_kernel)");
     attr_set = true;
