@@ -722,6 +722,8 @@ __global__ void __launch_bounds__(kConvThreads, 1)
             tma_store_4d(&p.tmap_out, o_base, ch, w0, h0, img);
             bulk_commit();
           }
+          if (STATS && EPI == 1)  // plain sum / sum of squares of the staged f16 tile (stats_mode 0)
+            epi_stats_rows<GHND_F16>(o_base, quarter, lane, valid, sstat, ch, p.cout);
           continue;
         }
         float v[64];
@@ -1043,11 +1045,12 @@ static int finish_launch(ConvLaunch* L, const ghnd_conv_desc_t* d, int gemm_cin,
       return e == nullptr ? 2 : atoi(e);
     }();
     p.epi_half = 0;
-    if (d->stats == nullptr && p.epi_debug == 0 && !p.epi_prefetch) {
+    const bool plain_stats = d->stats == nullptr || d->stats_mode == 0;
+    if (plain_stats && p.epi_debug == 0 && !p.epi_prefetch) {
       if (half_level >= 1 && d->dst_fmt == GHND_F16 && d->mask == nullptr && !d->accumulate &&
           (d->residual == nullptr || d->res_fmt == GHND_F16))
         p.epi_half = 1;
-      else if (half_level >= 2 && d->dst_fmt == GHND_BF16 && (d->mask == nullptr || d->mask_fmt == GHND_F16) &&
+      else if (d->stats == nullptr && half_level >= 2 && d->dst_fmt == GHND_BF16 && (d->mask == nullptr || d->mask_fmt == GHND_F16) &&
                (d->residual == nullptr || d->res_fmt == GHND_BF16))
         p.epi_half = 2;
     }
@@ -1113,8 +1116,9 @@ static cudaError_t launch_conv(const ConvLaunch& L, cudaStream_t st) {
   static const bool no_pdl = getenv("GHND_NO_PDL") != nullptr;  // debugging switch
   cfg.attrs = attr;
   cfg.numAttrs = no_pdl ? 0 : 1;
-  if (L.p.epi_half == 1) {  // packed epilogues never carry statistics
-    if (L.p.halo) return cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, true, false>, L.p);
+  if (L.p.epi_half == 1) {
+    if (L.p.halo) return cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, true, false>, L.p);  // stem: no stats
+    if (L.p.stats != nullptr) return cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, false, true>, L.p);
     return cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, false, false>, L.p);
   }
   if (L.p.epi_half == 2 && !L.p.halo) return cudaLaunchKernelEx(&cfg, conv_tc_kernel<2, false, false>, L.p);
@@ -1137,6 +1141,7 @@ static int set_conv_attr() {
     GHND_SET_SMEM(0, false, true);
     GHND_SET_SMEM(0, true, false);
     GHND_SET_SMEM(1, false, false);
+    GHND_SET_SMEM(1, false, true);
     GHND_SET_SMEM(1, true, false);
     GHND_SET_SMEM(2, false, false);
 #undef GHND_SET_SMEM
