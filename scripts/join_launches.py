@@ -4,7 +4,19 @@ import csv, json, sys
 rows = [l for l in open(sys.argv[1]) if l.startswith('"')]
 r = list(csv.reader(rows)); hdr, r = r[0], r[1:]
 ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
-launches = [(x[ki].split("(")[0], float(x[vi].replace(",", "")) / 1e3) for x in r]
+import re
+
+
+def kname(full):
+    """'void conv_tc_kernel<1, 0, 0>(ghnd::ConvKernelParams)' -> 'conv_tc_kernel' (the template
+    instantiations of one kernel share a launch queue)."""
+    n = full.split("(")[0]
+    n = re.sub(r"^void\s+", "", n)
+    n = re.sub(r"<.*$", "", n)
+    return n.split("::")[-1]
+
+
+launches = [(kname(x[ki]), float(x[vi].replace(",", "")) / 1e3) for x in r]
 ops = json.load(open(sys.argv[2]))
 queues = {}
 for name, us in launches:
