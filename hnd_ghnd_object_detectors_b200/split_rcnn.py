@@ -90,7 +90,10 @@ class RcnnTail(nn.Module):
             self._plans = {key: (l1, layers)}
         return self._plans[key]
 
-    def forward(self, z, tensors_shape, image_sizes, original_image_sizes, targets=None):
+    def backbone_features(self, z, targets=None):
+        """Server half of split computing up to the body outputs (split_rcnn.py:186-189):
+        Dequantizer -> layer1.decoder (eval BN folded) -> layer2-4 on the CUDA kernels; NCHW fp32
+        tensors keyed '0'..'3' like IntermediateLayerGetter's return_layers."""
         if self.bottleneck_transformer is not None:
             z, _ = self.bottleneck_transformer(z, targets)
         z = z.float().contiguous()
@@ -100,8 +103,13 @@ class RcnnTail(nn.Module):
         for i, r in enumerate(layers):
             r.forward()
             feats[str(i + 1)] = ops.to_nchw_f32(r.out)
+        return feats
+
+    def forward(self, z, tensors_shape, image_sizes, original_image_sizes, targets=None):
+        feats = self.backbone_features(z, targets)
         features = self.model.backbone.fpn(feats)
-        image_list = ImageList(torch.empty(tuple(tensors_shape), device=z.device), [tuple(s) for s in image_sizes])
+        image_list = ImageList(torch.empty(tuple(tensors_shape), device=feats['0'].device),
+                               [tuple(s) for s in image_sizes])
         proposals, proposal_losses = self.model.rpn(image_list, features, targets)
         detections, detector_losses = self.model.roi_heads(features, proposals, image_list.image_sizes, targets)
         detections = self.model.transform.postprocess(detections, image_list.image_sizes, original_image_sizes)

@@ -280,6 +280,36 @@ def test_encode_head_bytes(env, golden_dir):
     assert np.array_equal(qz.tensor.cpu().numpy(), qo) and zo == qz.zero_point
 
 
+def test_tail_decode_matches_oracle(env):
+    """SURVEY 8(f)2, the server half of split computing (split_rcnn.py:162-191): the head's quantized
+    bottleneck goes through Dequantizer -> layer1.decoder (eval BN) -> layer2-4.  Checked against the
+    oracle fed with the SAME bytes (dequantize_tensor_np -> student_decoder_forward ->
+    frozen_layer_forward): per-level relative L2 <= 1e-2."""
+    from hnd_ghnd_object_detectors_b200.split_rcnn import split_rcnn_model
+    models = env["models"]
+    student = models.get_model(model_config("student"), torch.device("cuda"))
+    student.load_state_dict(env["s_sd"], strict=False)
+    student.eval()
+    head, tail = split_rcnn_model(student, 8)
+    images = [im.cuda() for im in small_images()]
+    qz, tshape, image_sizes, orig = head(images)
+    feats = tail.backbone_features(qz)
+    z = O.dequantize_tensor_np(qz.tensor.cpu().numpy(), float(qz.scale), qz.zero_point)
+    with torch.no_grad():
+        x = O.student_decoder_forward(torch.from_numpy(z), env["s_sd"], "backbone.body.layer1", training=False)
+        assert rel(feats["0"], x) <= 1e-2, rel(feats["0"], x)
+        for i, name in enumerate(("layer2", "layer3", "layer4")):
+            x = O.frozen_layer_forward(x, env["s_sd"], name)
+            assert tuple(feats[str(i + 1)].shape) == tuple(x.shape)
+            assert rel(feats[str(i + 1)], x) <= 1e-2, (name, rel(feats[str(i + 1)], x))
+    # the whole tail (FPN / RPN / RoI heads are torchvision modules fed by those features) runs
+    tail.eval()
+    with torch.no_grad():
+        detections = tail(qz, tshape, image_sizes, orig)
+    assert isinstance(detections, list) and len(detections) == len(images)
+    assert all(set(d.keys()) >= {"boxes", "labels", "scores"} for d in detections)
+
+
 def test_layer1_module_eval_and_train(env):
     """Bottleneck4LargeResNet as a stand-alone nn.Module (NCHW fp32 in/out), eval with the
     quantize/dequantize transformer spliced in (base.py:50-58) and train with autograd."""
