@@ -85,6 +85,50 @@ def test_error_behaviour_matches_reference():
     assert transformer.get_bottleneck_transformer({"order": [], "components": {}}) is None
 
 
+def test_resize_decisions_match_reference_transform(golden_dir):
+    """CustomRCNN._scaled_images decides each image's scale factor like CustomRCNNTransform.resize
+    (src/models/org/rcnn.py:29-42): fixed_sizes > random.choice(min_size) in training > min_size[-1]
+    in eval, capped so the long side stays <= max_size; identity scale returns the tensor itself,
+    otherwise an ops.ScaledImage whose geometry equals what the reference transform produced
+    (tests/golden/transform.npz, generated from the unmodified reference)."""
+    import numpy as np
+    import os
+    import random
+    from hnd_ghnd_object_detectors_b200 import models, ops
+    from oracle import ghnd_oracle as O
+    from tests.golden.make_transform_golden import case_images, transform_cases
+    g = np.load(os.path.join(golden_dir, "transform.npz"))
+    for name, (shapes, sizes, max_size, seed) in transform_cases().items():
+        cfg = {"name": "keypoint_rcnn", "ckpt": "/nonexistent",
+               "backbone": {"name": "resnet50", "params": {"pretrained": False, "freeze_layers": True}},
+               "params": {"num_classes": 2, "pretrained": False, "num_keypoints": 17,
+                          "min_size": tuple(sorted(set(sizes))), "max_size": max_size}}
+        model = models.get_model(cfg, "cpu")
+        imgs = case_images(shapes, seed)
+        out = model._scaled_images(imgs, fixed_sizes=sizes)
+        for im, o, size, (h, w) in zip(imgs, out, sizes, g[name + "/image_sizes"]):
+            sc = O.resize_scale(im.shape[1], im.shape[2], size, max_size)
+            assert tuple(o.shape[-2:]) == (int(h), int(w)), name
+            if sc == 1.0:
+                assert o is im
+            else:
+                assert isinstance(o, ops.ScaledImage) and o.src is im and abs(o.scale - sc) < 1e-12
+        # eval: the largest configured scale (rcnn.py:38-40); training: one of the configured scales
+        model.eval()
+        ev = model._scaled_images(imgs, None)
+        want = [O.resize_scale(im.shape[1], im.shape[2], max(sizes), max_size) for im in imgs]
+        for o, im, sc in zip(ev, imgs, want):
+            assert (o is im) if sc == 1.0 else abs(o.scale - sc) < 1e-12
+        model.train()
+        random.seed(3)
+        tr = model._scaled_images(imgs, None)
+        random.seed(3)
+        picks = [random.choice(model.transform.min_size) for _ in imgs]
+        for o, im, size in zip(tr, imgs, picks):
+            sc = O.resize_scale(im.shape[1], im.shape[2], size, max_size)
+            assert (o is im) if sc == 1.0 else abs(o.scale - sc) < 1e-12
+
+
 def test_no_cpu_fallback():
     from hnd_ghnd_object_detectors_b200 import _lib, resnet_layer, tensor_util
     with pytest.raises(_lib.GhndError):
