@@ -930,8 +930,8 @@ class BodyPlan(object):
             l1 = self.body.layer1
             z = self.l1.forward_encoder()
             if (not l1.training) and l1.bottleneck_transformer is not None and l1.use_bottleneck_transformer:
-                z, _ = l1.bottleneck_transformer(z, None)  # base.py:55-57
-                z = z.to(self.packed.device).contiguous()
+                from .resnet_layer import apply_bottleneck_transformer
+                z = apply_bottleneck_transformer(l1, z).contiguous()  # base.py:55-57
             self.l1.forward_decoder(z)
         else:
             self.l1.forward()

@@ -7,8 +7,12 @@ distill :62-106, main :124-151) on the B200 CUDA path.
 What is the same: YAML schema (with !join), --json deep-merge, teacher/student construction,
 frozen_modules, Adam + MultiStepLR + epoch-0 warm-up, best-checkpoint format and keys.
 What differs: DistributedDataParallel is replaced by one flat-buffer NCCL all-reduce + fused Adam
-(parallel.py); COCO loading and COCO evaluation (pycocotools; SURVEY.md "out of scope") are used
-only if available -- `dataset.name: synthetic` gives random images so the loop runs anywhere.
+(parallel.py; rank 0's parameters and BN buffers are broadcast at start like DDP's constructor does);
+COCO loading and COCO mAP (pycocotools; SURVEY.md "out of scope") are not re-implemented --
+`dataset.name: synthetic` gives random images so both entry points run anywhere: `-distill` trains,
+and the evaluation entry point (mimic_runner.py:109-121,148-151) runs the full detector forward of the
+teacher and of the student (with the quantize/dequantize splice under -transform_bottleneck) and
+reports model time, detections and the bottleneck's bytes on the wire instead of mAP.
 """
 import argparse
 import datetime
@@ -92,9 +96,9 @@ def distill_model(distillation_box, data_loader, optimizer, log_freq, device, ep
         loss = distillation_box(images, targets)
         optimizer.zero_grad()
         loss.backward()
-        if distillation_box.flat is not None and optimizer.flat is None:
+        if optimizer.flat is None:
             optimizer.attach(distillation_box.flat)
-        parallel.allreduce_flat_grad(distillation_box.flat)
+        parallel.allreduce_flat_grad(distillation_box.flat)  # p.grad are views of this buffer
         optimizer.step()
         if lr_scheduler is not None:
             lr_scheduler.step()
@@ -112,19 +116,24 @@ def distill(teacher_model, student_model, train_data_loader, val_data_loader, de
     """mimic_runner.py:62-106."""
     train_config = config['train']
     distillation_box = DistillationBox(teacher_model, student_model, train_config['criterion'])
+    flat = distillation_box.flatten_parameters()
+    if parallel.world_size() > 1:
+        # DistributedDataParallel's constructor broadcasts rank 0's parameters and buffers
+        parallel.broadcast_flat_params(flat)
+        parallel.broadcast_buffers(student_model)
     ckpt_file_path = config['student_model']['ckpt']
     optim_config = train_config['optimizer']
     if optim_config['type'].lower() != 'adam':
         raise ValueError("optimizer `{}`: the fused CUDA path implements Adam".format(optim_config['type']))
     optimizer = FusedAdam([p for p in student_model.parameters() if p.requires_grad],
-                          grad_scale=1.0 / parallel.world_size(), **optim_config['params'])
+                          grad_scale=1.0 / parallel.world_size(), flat=flat, **optim_config['params'])
     scheduler_config = train_config['scheduler']
     scheduler_cls = getattr(torch.optim.lr_scheduler, scheduler_config['type'])
     lr_scheduler = scheduler_cls(optimizer, **scheduler_config['params'])
     best_val = 0.0
     import os
     if os.path.exists(ckpt_file_path):
-        best_val, _, _ = load_ckpt(ckpt_file_path, optimizer=None, lr_scheduler=lr_scheduler)
+        best_val, _, _ = load_ckpt(ckpt_file_path, optimizer=optimizer, lr_scheduler=lr_scheduler)
     start_time = time.time()
     for epoch in range(train_config['num_epochs']):
         teacher_model.eval()
@@ -136,7 +145,8 @@ def distill(teacher_model, student_model, train_data_loader, val_data_loader, de
                              device, epoch)
         student_model.distill_backbone_only = False
         student_model.backbone.body.layer1.use_bottleneck_transformer = args.transform_bottleneck
-        # COCO mAP evaluation (main_util.evaluate) is outside the hot path: keep the latest student
+        # COCO mAP (main_util.evaluate + pycocotools) is outside the hot path: the latest student is
+        # kept instead of the best-mAP one
         save_ckpt(student_model, optimizer, lr_scheduler, best_val, config, args, ckpt_file_path)
         lr_scheduler.step()
     if distributed:
@@ -144,6 +154,57 @@ def distill(teacher_model, student_model, train_data_loader, val_data_loader, de
     total_time = time.time() - start_time
     print('Training time {}'.format(str(datetime.timedelta(seconds=int(total_time)))))
     return distillation_box
+
+
+def evaluate_model(model, data_loader, device, max_batches=None):
+    """main_util.evaluate (src/utils/main_util.py:76-113) without the COCO scorer: eval-mode forward of
+    the full detector per batch, model time by CUDA-synchronised wall clock like the reference,
+    detections moved to the host.  Returns a dict of averaged stats."""
+    from . import file_util
+    model.eval()
+    n_img, n_det, t_model, wire = 0, 0, 0.0, []
+    layer1 = model.backbone.body.layer1
+    log_wire = getattr(layer1, 'use_bottleneck_transformer', False) and \
+        getattr(layer1, 'bottleneck_transformer', None) is not None
+    if log_wire:
+        layer1.data_logging = True
+    with torch.no_grad():
+        for it, (images, targets) in enumerate(data_loader):
+            if max_batches is not None and it >= max_batches:
+                break
+            images = [img.to(device) for img in images]
+            torch.cuda.synchronize()
+            t0 = time.time()
+            outputs = model(images)
+            outputs = [{k: v.to('cpu') for k, v in t.items()} for t in outputs]
+            t_model += time.time() - t0
+            n_img += len(images)
+            n_det += sum(len(o['boxes']) for o in outputs)
+            if log_wire and getattr(layer1, 'last_bottleneck', None) is not None:
+                wire.append(file_util.get_binary_object_size(layer1.last_bottleneck) / len(images))
+    if log_wire:
+        layer1.data_logging = False
+    stats = {'images': n_img, 'detections': n_det, 'model_time': t_model / max(n_img, 1)}
+    if wire:
+        stats['bottleneck_kb_per_image'] = sum(wire) / len(wire)
+    print('Averaged stats: model_time: {:.4f} s/img  detections/img: {:.1f}{}'.format(
+        stats['model_time'], n_det / max(n_img, 1),
+        '  bottleneck: {:.1f} KB/img'.format(stats['bottleneck_kb_per_image']) if wire else ''))
+    return stats
+
+
+def evaluate(teacher_model, student_model, test_data_loader, device, student_only, use_bottleneck_transformer):
+    """mimic_runner.py:109-121."""
+    teacher_model.distill_backbone_only = False
+    student_model.distill_backbone_only = False
+    student_model.backbone.body.layer1.use_bottleneck_transformer = use_bottleneck_transformer
+    results = {}
+    if not student_only:
+        print('[Teacher model]')
+        results['teacher'] = evaluate_model(teacher_model, test_data_loader, device)
+    print('\n[Student model]')
+    results['student'] = evaluate_model(student_model, test_data_loader, device)
+    return results
 
 
 def main(args):
@@ -168,8 +229,11 @@ def main(args):
         distill(teacher_model, student_model, train_loader, val_loader, device, distributed,
                 distill_backbone_only, config, args)
         load_ckpt(config['student_model']['ckpt'], model=student_model)
+    results = evaluate(teacher_model, student_model, val_loader, device, args.skip_teacher_eval,
+                       args.transform_bottleneck)
     if distributed:
         dist.destroy_process_group()
+    return results
 
 
 if __name__ == '__main__':

@@ -26,6 +26,13 @@ def broadcast_flat_params(flat, src=0):
         dist.broadcast(flat.flat, src=src)
 
 
+def broadcast_buffers(module, src=0):
+    """BN running statistics etc. of rank `src` to every rank (DDP broadcasts buffers too)."""
+    if world_size() > 1:
+        for b in module.buffers():
+            dist.broadcast(b, src=src)
+
+
 def shard_indices(n_items, rank, world):
     """DistributedSampler-style partition (data_util.py:28-30): item i goes to rank i % world, padded
     so that every rank gets the same count."""

@@ -27,7 +27,7 @@ from .resnet_layer import get_mimic_layers
 MODEL_URL_DICT = {
     'fasterrcnn_resnet50_fpn_coco': 'https://download.pytorch.org/models/fasterrcnn_resnet50_fpn_coco-258fb6c6.pth',
     'maskrcnn_resnet50_fpn_coco': 'https://download.pytorch.org/models/maskrcnn_resnet50_fpn_coco-bf2d0c1e.pth',
-    'keypointrcnn_resnet50_fpn_coco': 'https://download.pytorch.org/models/keypointrcnn_resnet50_fpn_coco-9f466800.pth',
+    'keypointrcnn_resnet50_fpn_coco': 'https://download.pytorch.org/models/keypointrcnn_resnet50_fpn_coco-fc266e95.pth',
 }
 
 
@@ -85,16 +85,40 @@ class CustomRCNN(nn.Module):
         imgs = self._scaled_images(images, fixed_sizes)
         hp = round_up(max(i.shape[1] for i in imgs), 32)
         wp = round_up(max(i.shape[2] for i in imgs), 32)
-        key = (len(imgs), hp, wp)
+        # A BodyPlan bakes in layer1's train/eval mode and packs the frozen weights once: key it on the
+        # mode and on a version of the body's tensors so train()/eval()/load_state_dict() rebuild it.
+        body = self.backbone.body
+        l1_train = bool(getattr(body.layer1, "training", False))
+        version = sum(int(t._version) for t in body.state_dict(keep_vars=True).values())
+        key = (len(imgs), hp, wp, l1_train, version)
         plan = self._feature_plans.get(key)
         if plan is None:
-            plan = BodyPlan(self.backbone.body, len(imgs), hp, wp, act_dtype=self.act_dtype,
+            plan = BodyPlan(body, len(imgs), hp, wp, act_dtype=self.act_dtype,
                             image_mean=self.transform.image_mean, image_std=self.transform.image_std)
             self._feature_plans = {key: plan}
         feats = plan.run(imgs)
         image_sizes = [tuple(i.shape[-2:]) for i in imgs]
         return OrderedDict((str(i), ops.to_nchw_f32(feats[l])) for i, l in enumerate(levels) if l in feats), \
             image_sizes, (len(imgs), 3, hp, wp)
+
+    @staticmethod
+    def _resize_targets(targets, original_sizes, new_sizes):
+        """What GeneralizedRCNNTransform.resize does to the targets next to the image
+        (rcnn.py:46-62): boxes / keypoints scaled by the per-axis ratios, masks resampled."""
+        from torchvision.models.detection.transform import resize_boxes, resize_keypoints
+        out = []
+        for t, (h, w), (nh, nw) in zip(targets, original_sizes, new_sizes):
+            if (h, w) == (nh, nw):
+                out.append(t)
+                continue
+            t = dict(t)
+            t["boxes"] = resize_boxes(t["boxes"], (h, w), (nh, nw))
+            if "keypoints" in t:
+                t["keypoints"] = resize_keypoints(t["keypoints"], (h, w), (nh, nw))
+            if "masks" in t:
+                t["masks"] = torch.nn.functional.interpolate(t["masks"][None].float(), size=(nh, nw))[0].byte()
+            out.append(t)
+        return out
 
     def forward(self, images, targets=None, fixed_sizes=None):
         if self.training and targets is None:
@@ -107,6 +131,8 @@ class CustomRCNN(nn.Module):
             return body_feats  # rcnn.py:109-110 (the reference also runs a discarded FPN here)
         features = self.backbone.fpn(body_feats)
         image_list = ImageList(torch.empty(tshape, device=images[0].device), image_sizes)
+        if targets is not None and self.training:
+            targets = self._resize_targets(targets, original_image_sizes, image_sizes)
         proposals, proposal_losses = self.rpn(image_list, features, targets)
         detections, detector_losses = self.roi_heads(features, proposals, image_list.image_sizes, targets)
         detections = self.transform.postprocess(detections, image_list.image_sizes, original_image_sizes)

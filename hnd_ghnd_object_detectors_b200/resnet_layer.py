@@ -13,6 +13,25 @@ from torch import nn
 from . import _lib, ops
 
 
+def apply_bottleneck_transformer(layer1, z):
+    """base.py:55-57: z, _ = bottleneck_transformer(z, target=None); z = z.to(device).  When
+    `layer1.data_logging` is set the first wire object of the chain (e.g. the QuantizedTensor between
+    Quantizer and Dequantizer) is kept in `layer1.last_bottleneck` for byte accounting."""
+    device = z.device
+    tr = layer1.bottleneck_transformer
+    if getattr(layer1, 'data_logging', False) and hasattr(tr, 'transforms'):
+        layer1.last_bottleneck = None
+        for t in tr.transforms:
+            z, _ = t(z, None)
+            if layer1.last_bottleneck is None and not isinstance(z, torch.Tensor):
+                layer1.last_bottleneck = z
+        if layer1.last_bottleneck is None:
+            layer1.last_bottleneck = z
+    else:
+        z, _ = tr(z, target=None)
+    return z.to(device)
+
+
 class ExtEncoder(nn.Module):
     """base.py:7-26.  The neural-filter classifier (ext_classifier) is out of scope."""
 
@@ -61,7 +80,9 @@ class BottleneckBase4Ext(nn.Module):
         self.encoder = encoder
         self.decoder = decoder
         self.bottleneck_transformer = bottleneck_transformer
-        self.data_logging = False
+        from .transformer import DataLogger
+        self.data_logging = isinstance(bottleneck_transformer, DataLogger)
+        self.last_bottleneck = None
         self.uses_ext_encoder = False
         self.use_bottleneck_transformer = False
         self._runners = {}
@@ -105,9 +126,7 @@ class BottleneckBase4Ext(nn.Module):
         ops.to_nhwc16_into(x, runner.x)
         z = runner.forward_encoder()
         if not self.training and self.bottleneck_transformer is not None and self.use_bottleneck_transformer:
-            device = z.device
-            z, _ = self.bottleneck_transformer(z, target=None)  # base.py:55-57
-            z = z.to(device)
+            z = apply_bottleneck_transformer(self, z)  # base.py:55-57
         return ops.to_nchw_f32(runner.forward_decoder(z.contiguous()))
 
     def get_ext_classifier(self):

@@ -30,12 +30,16 @@ class _GradInjector(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
+        # The fused backward wrote every gradient into the flat buffer during forward(); here they
+        # are scaled by the incoming gradient with ONE in-place multiply and each `p.grad` is made a
+        # VIEW of that buffer, so the data-parallel all-reduce of `flat.grad` and the fused Adam see
+        # exactly what autograd users see (no per-tensor copies, no 25 multiplies).  Gradients are
+        # assigned, not accumulated: the plan overwrites the buffer every step.
         flat = ctx.box.flat
-        grads = []
+        flat.grad.mul_(g)
         for p_name in flat.names:
-            gv = flat.grads[p_name]
-            grads.append(gv * g)
-        return (None, None) + tuple(grads)
+            flat.params[p_name].grad = flat.grads[p_name]
+        return (None, None) + (None,) * len(flat.names)
 
 
 def _level_of(path):
@@ -70,7 +74,10 @@ class DistillationBox(nn.Module):
         teacher_min = self._unwrap(teacher_model).transform.min_size
         teacher_min = teacher_min if isinstance(teacher_min, (list, tuple)) else (teacher_min,)
         self.use_cuda_graph = use_cuda_graph
-        self.max_resident_plans = len(teacher_min) if self.require_adjustment else 1
+        # Resident shapes (one GhndPlan + CUDA graph each, a few GB out of 180 GB): real COCO batches
+        # pad to a handful of shapes and the Keypoint path draws from six scales, so keep an LRU of
+        # several plans for every model type instead of rebuilding on each shape change.
+        self.max_resident_plans = max(len(teacher_min), 4)
         self.flat = None
         self._plans = {}
         self.last_terms = None
@@ -79,22 +86,27 @@ class DistillationBox(nn.Module):
     def _unwrap(model):
         return model.module if isinstance(model, (DataParallel, DistributedDataParallel)) else model
 
+    def flatten_parameters(self):
+        """Move the trainable student tensors into ONE flat fp32 buffer (engine.FlatParams): a single
+        all-reduce and a single fused Adam kernel cover them.  Called lazily by the first forward; the
+        runner calls it up front to broadcast rank 0's parameters and attach the optimizer."""
+        if self.flat is None:
+            student = self._unwrap(self.student_model)
+            named = [("backbone.body." + k, p) for k, p in student.backbone.body.named_parameters()]
+            self.flat = FlatParams(named)
+        return self.flat
+
     def _plan(self, n, hp, wp):
         key = (n, hp, wp)
         plan = self._plans.get(key)
         if plan is None:
             teacher, student = self._unwrap(self.teacher_model), self._unwrap(self.student_model)
-            if self.flat is None:
-                named = [("backbone.body." + k, p) for k, p in student.backbone.body.named_parameters()]
-                self.flat = FlatParams(named)
+            self.flatten_parameters()
             plan = GhndPlan(teacher.backbone.body, student.backbone.body, n, hp, wp, levels=self.levels,
                             factors=self.factors, flat=self.flat,
                             image_mean=student.transform.image_mean, image_std=student.transform.image_std)
             if self.use_cuda_graph:
                 plan.capture()
-            # Resident shapes: one for fixed-size training; the Keypoint multi-scale path draws the
-            # padded shape from six (min_size choices x fixed aspect), so keep those plans (and their
-            # CUDA graphs) alive -- a few GB each out of 180 GB -- instead of rebuilding per step.
             while len(self._plans) >= self.max_resident_plans:
                 self._plans.pop(next(iter(self._plans)))
             self._plans[key] = plan
@@ -115,7 +127,12 @@ class DistillationBox(nn.Module):
         hp = round_up(max(i.shape[1] for i in imgs), 32)
         wp = round_up(max(i.shape[2] for i in imgs), 32)
         plan = self._plan(len(imgs), hp, wp)
+        # stale views of the flat gradient buffer (left by the previous backward) are dropped before
+        # the plan rewrites it, so a later zero_grad(set_to_none=False) cannot wipe the new gradients
+        params = [self.flat.params[n] for n in self.flat.names]
+        for n, p in zip(self.flat.names, params):
+            if p.grad is not None and p.grad.data_ptr() == self.flat.grads[n].data_ptr():
+                p.grad = None
         out = plan.step(imgs)
         self.last_terms = out
-        params = [self.flat.params[n] for n in self.flat.names]
         return _GradInjector.apply(out[0], self, *params)

@@ -1,7 +1,7 @@
 """Bottleneck transformers -- drop-in mirror of src/structure/transformer.py:22-29,131-174
-(Compose, Quantizer, Dequantizer, registry, get_bottleneck_transformer).  The JPEG codec and the
-DataLogger of the reference are analysis tools outside the hot path."""
-from . import tensor_util
+(Compose, Quantizer, Dequantizer, DataLogger :58-91, registry, get_bottleneck_transformer).  The JPEG
+codec of the reference is an analysis tool outside the hot path."""
+from . import file_util, tensor_util
 
 
 class Compose(object):
@@ -12,6 +12,36 @@ class Compose(object):
         for t in self.transforms:
             image, target = t(image, target)
         return image, target
+
+
+class DataLogger(object):
+    """transformer.py:58-91: records the bytes the bottleneck would occupy on the wire (pickled as-is,
+    as fp16 and 8-bit quantized) plus its C/H/W shape; passes z through unchanged."""
+
+    def __init__(self, num_bits=8):
+        self.num_bits4quant = num_bits
+        self.data_size_list = list()
+        self.fp16_data_size_list = list()
+        self.quantized_data_size_list = list()
+        self.tensor_shape_list = list()
+
+    def get_data(self):
+        return self.data_size_list.copy(), self.fp16_data_size_list, \
+            self.quantized_data_size_list.copy(), self.tensor_shape_list.copy()
+
+    def clear(self):
+        self.data_size_list.clear()
+        self.fp16_data_size_list.clear()
+        self.quantized_data_size_list.clear()
+        self.tensor_shape_list.clear()
+
+    def __call__(self, z, target):
+        data_size, fp16_data_size, quantized_data_size = file_util.bottleneck_wire_sizes(z, self.num_bits4quant)
+        self.data_size_list.append(data_size)
+        self.fp16_data_size_list.append(fp16_data_size)
+        self.quantized_data_size_list.append(quantized_data_size)
+        self.tensor_shape_list.append([0, 0, 0] if z is None else [z.shape[1], z.shape[2], z.shape[3]])
+        return z, target
 
 
 class Quantizer(object):

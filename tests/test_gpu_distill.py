@@ -373,7 +373,8 @@ def test_keypoint_multi_scale_step(env):
     student.train()
     teacher.distill_backbone_only = student.distill_backbone_only = True
     box = DistillationBox(teacher, student, criterion_config())
-    assert box.require_adjustment and box.max_resident_plans == 3
+    assert box.require_adjustment and box.max_resident_plans >= 3
+    box.max_resident_plans = 3  # exercise the LRU eviction with four shapes
     g = torch.Generator().manual_seed(77)
     host = [torch.rand(3, 90, 120, generator=g), torch.rand(3, 96, 100, generator=g)]
     images = [im.cuda() for im in host]

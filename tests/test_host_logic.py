@@ -204,3 +204,171 @@ def test_data_parallel_flat_allreduce_gloo():
     assert torch.equal(p0, p1)
     expect = torch.arange(p0.numel(), dtype=torch.float32) * 3
     assert torch.equal(g0, expect) and torch.equal(g1, expect)
+
+
+# ------------------------------------------------------------------------------------------------
+# data-parallel training semantics (the all-reduced gradient must be the one Adam uses)
+# ------------------------------------------------------------------------------------------------
+def _torch_adam_step(param, grad, m, v, lr, b1, b2, eps, wd, grad_scale, step):
+    """Stand-in for the ghnd_adam_step kernel in CPU tests of the HOST logic (same update rule)."""
+    g = grad * grad_scale
+    if wd:
+        g = g + wd * param
+    m.mul_(b1).add_(g, alpha=1 - b1)
+    v.mul_(b2).addcmul_(g, g, value=1 - b2)
+    bc1, bc2 = 1 - b1 ** step, 1 - b2 ** step
+    param.addcdiv_(m, (v.sqrt() / bc2 ** 0.5).add_(eps), value=-lr / bc1)
+
+
+class _FakeBox(object):
+    """What tool._GradInjector needs from a DistillationBox: the flat buffer the plan wrote into."""
+
+    def __init__(self, flat):
+        self.flat = flat
+
+
+def _train_worker(rank, world, port, q):
+    os.environ.update({"MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(port), "RANK": str(rank),
+                       "WORLD_SIZE": str(world)})
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from hnd_ghnd_object_detectors_b200 import ops, parallel
+    from hnd_ghnd_object_detectors_b200.engine import FlatParams
+    from hnd_ghnd_object_detectors_b200.optim import FusedAdam
+    from hnd_ghnd_object_detectors_b200.tool import _GradInjector
+    ops.adam_step = _torch_adam_step
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(100 + rank)  # ranks start from DIFFERENT parameters, like un-seeded processes
+    model = torch.nn.Sequential(torch.nn.Linear(5, 3), torch.nn.BatchNorm1d(3))
+    model[1].running_mean.fill_(float(rank))
+    flat = FlatParams(list(model.named_parameters()))
+    parallel.broadcast_flat_params(flat)
+    parallel.broadcast_buffers(model)
+    opt = FusedAdam([p for p in model.parameters()], lr=1e-2, grad_scale=1.0 / world, flat=flat)
+    box = _FakeBox(flat)
+    start = flat.flat.clone()
+    local = []
+    for step in range(3):
+        # the fused plan writes this rank's LOCAL gradient into the flat buffer during forward
+        flat.grad.copy_(torch.randn(flat.total, generator=torch.Generator().manual_seed(10 * step + rank)))
+        local.append(flat.grad.clone())
+        loss = _GradInjector.apply(torch.tensor(1.0 + rank), box, *[flat.params[n] for n in flat.names])
+        opt.zero_grad()       # mimic_runner.py:51-54 order
+        loss.backward()
+        for n in flat.names:  # p.grad is a VIEW of the flat gradient buffer
+            assert flat.params[n].grad.data_ptr() == flat.grads[n].data_ptr()
+        parallel.allreduce_flat_grad(flat)
+        opt.step()
+    q.put((rank, start, flat.flat.clone(), model[1].running_mean.clone(), local))
+    dist.destroy_process_group()
+
+
+def test_two_rank_training_keeps_replicas_identical():
+    """world_size 2, gloo: ranks begin with different random parameters and see different data; after
+    broadcast + 3 x (backward -> flat all-reduce -> fused Adam) both hold identical parameters, and
+    those equal single-process Adam on the rank-averaged gradient."""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_train_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=180) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+    (_, s0, p0, rm0, g0), (_, s1, p1, rm1, g1) = res
+    assert torch.equal(s0, s1) and torch.equal(rm0, rm1)      # broadcast at start
+    assert torch.equal(p0, p1) and not torch.equal(p0, s0)    # replicas stay identical and did move
+    ref, m, v = s0.clone(), torch.zeros_like(s0), torch.zeros_like(s0)
+    for step in range(3):
+        _torch_adam_step(ref, (g0[step] + g1[step]), m, v, 1e-2, 0.9, 0.999, 1e-8, 0, 0.5, step + 1)
+    assert torch.allclose(p0, ref, atol=1e-6)
+
+
+def test_grad_injector_scales_once_and_zero_grad_keeps_new_gradients():
+    from hnd_ghnd_object_detectors_b200.engine import FlatParams
+    from hnd_ghnd_object_detectors_b200.optim import FusedAdam
+    from hnd_ghnd_object_detectors_b200.tool import _GradInjector
+    w = torch.nn.Parameter(torch.randn(4, 3))
+    flat = FlatParams([("w", w)])
+    opt = FusedAdam([w], flat=flat)
+    box = _FakeBox(flat)
+    flat.grad.fill_(1.5)
+    loss = _GradInjector.apply(torch.tensor(2.0), box, w)
+    (3.0 * loss).backward()
+    assert w.grad.data_ptr() == flat.grads["w"].data_ptr() and torch.all(w.grad == 4.5)
+    # next step: the plan rewrites the buffer during forward, THEN the reference loop calls zero_grad
+    flat.grad.fill_(2.0)
+    loss = _GradInjector.apply(torch.tensor(2.0), box, w)
+    opt.zero_grad(set_to_none=False)
+    assert torch.all(flat.grad[:12] == 2.0)  # never wiped in place
+    loss.backward()
+    assert torch.all(w.grad == 2.0)
+
+
+def test_fused_adam_state_dict_is_torch_adam_format():
+    """Checkpoint resume (src/mimic_runner.py:75): moments and step count survive a save/load round
+    trip and are interchangeable with torch.optim.Adam."""
+    from hnd_ghnd_object_detectors_b200 import ops
+    from hnd_ghnd_object_detectors_b200.engine import FlatParams
+    from hnd_ghnd_object_detectors_b200.optim import FusedAdam
+    saved = ops.adam_step
+    ops.adam_step = _torch_adam_step
+    try:
+        torch.manual_seed(0)
+        ps = [torch.nn.Parameter(torch.randn(3, 5)), torch.nn.Parameter(torch.randn(7))]
+        ref_ps = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+        flat = FlatParams([("a", ps[0]), ("b", ps[1])])
+        opt = FusedAdam(ps, lr=1e-2, flat=flat)
+        ref = torch.optim.Adam(ref_ps, lr=1e-2)
+        grads = [[torch.randn_like(p) for p in ps] for _ in range(4)]
+        for k in range(2):
+            for p, r, g in zip(ps, ref_ps, grads[k]):
+                flat.grads["a" if p is ps[0] else "b"].copy_(g)
+                r.grad = g.clone()
+            opt.step()
+            ref.step()
+        sd = opt.state_dict()
+        assert set(sd["state"].keys()) == {0, 1} and int(sd["state"][0]["step"]) == 2
+        assert torch.allclose(sd["state"][0]["exp_avg"], ref.state_dict()["state"][0]["exp_avg"], atol=1e-7)
+        # resume into a fresh FusedAdam (flat) and into torch.optim.Adam: both continue identically
+        ps2 = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+        flat2 = FlatParams([("a", ps2[0]), ("b", ps2[1])])
+        opt2 = FusedAdam(ps2, lr=1e-2, flat=flat2)
+        opt2.load_state_dict(sd)
+        ps3 = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+        opt3 = torch.optim.Adam(ps3, lr=1e-2)
+        opt3.load_state_dict({k: v for k, v in sd.items() if k != "fused_step"})
+        for k in range(2, 4):
+            for i, n in enumerate(("a", "b")):
+                flat.grads[n].copy_(grads[k][i])
+                flat2.grads[n].copy_(grads[k][i])
+                ps3[i].grad = grads[k][i].clone()
+            opt.step()
+            opt2.step()
+            opt3.step()
+        for a, b, c in zip(ps, ps2, ps3):
+            assert torch.allclose(a, b, atol=1e-7) and torch.allclose(a, c, atol=1e-6)
+    finally:
+        ops.adam_step = saved
+
+
+def test_wire_format_sizes():
+    """file_util.get_binary_object_size (src/myutils/common/file_util.py:52-53) = KB of the pickle: the
+    8-bit QuantizedTensor of a b3ch bottleneck is ~1/4 of the fp32 tensor and ~1/2 of the fp16 one."""
+    import pickle
+    from hnd_ghnd_object_detectors_b200 import file_util
+    from hnd_ghnd_object_detectors_b200.tensor_util import QuantizedTensor
+    z = torch.randn(1, 3, 204, 340)
+    q = QuantizedTensor(tensor=torch.zeros(1, 3, 204, 340, dtype=torch.uint8), scale=torch.tensor(0.1), zero_point=7)
+    s32, s16, s8 = (file_util.get_binary_object_size(x) for x in (z, z.short(), q))
+    assert s32 == sys.getsizeof(pickle.dumps(z)) / 1024
+    n = z.numel()
+    assert 4 * n / 1024 < s32 < 4 * n / 1024 + 2 and 2 * n / 1024 < s16 < 2 * n / 1024 + 2
+    assert n / 1024 < s8 < n / 1024 + 2
+    assert file_util.get_binary_object_size(z, unit_size=1) == sys.getsizeof(pickle.dumps(z))
