@@ -1,0 +1,23 @@
+#!/bin/bash
+# One parameterised GPU trip (replaces the round-1 gpu_trip_*.sh one-shots).  Run under gpurun:
+#   gpurun --timeout 900 -- 'bash scripts/gpu.sh tests "tests/test_gpu_fullsize.py -s" bench "--steps 20 --warmup 5"'
+# Verbs (each followed by ONE quoted argument string):
+#   tests  <pytest args>      -> gpurun_out/tests_<n>.log      (python -m pytest -m gpu -q <args>)
+#   bench  <bench.py args>    -> gpurun_out/bench_<n>.log/.err
+#   py     <script + args>    -> gpurun_out/py_<n>.log
+#   launches <bench.py args>  -> gpurun_out/launches_<n>.csv   (ncu gpu__time_duration, never a bench value)
+#   ncu    "<kernel regex>|<skip>|<count>|<cmd>" -> gpurun_out/prof_<n>.ncu-rep (ncu --set full)
+mkdir -p gpurun_out
+n=0
+while [ $# -ge 2 ]; do
+  verb=$1; arg=$2; shift 2; n=$((n+1))
+  case $verb in
+    tests) timeout 1500 python -m pytest -m gpu -q -x $arg > gpurun_out/tests_$n.log 2>&1; echo "tests_$n rc=$?"; tail -5 gpurun_out/tests_$n.log ;;
+    bench) timeout 900 python bench.py $arg > gpurun_out/bench_$n.log 2> gpurun_out/bench_$n.err; echo "bench_$n rc=$?"; head -c 600 gpurun_out/bench_$n.log; echo ;;
+    py) timeout 900 python $arg > gpurun_out/py_$n.log 2>&1; echo "py_$n rc=$?"; tail -30 gpurun_out/py_$n.log ;;
+    launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_$n.csv python bench.py $arg > gpurun_out/launches_$n.log 2>&1; echo "launches_$n rc=$?" ;;
+    ncu) IFS='|' read -r rx skip cnt cmd <<< "$arg"
+         timeout 1200 ncu --set full --clock-control none --import-source on -k regex:$rx -s $skip -c $cnt -f -o gpurun_out/prof_$n $cmd > gpurun_out/ncu_$n.log 2>&1; echo "ncu_$n rc=$?" ;;
+    *) echo "unknown verb $verb" ;;
+  esac
+done

@@ -2,11 +2,13 @@
 Bottleneck4LargeResNet, RcnnHead-style encode) against the CPU oracle and the golden fixtures.
 
 Tolerances (BASELINE.json north_star): per-level feature relative L2 <= 1e-2, loss relative error
-<= 1e-3.  Gradients are reported and bounded at 0.15 relative L2 / 0.985 cosine: a 16-bit forward
-flips the ReLU mask of the ~0.2% of activations that sit within rounding distance of zero, and each
-flipped element changes its gradient by O(|g|), i.e. relative L2 ~ sqrt(flipped fraction) ~ 2-8%
-(measured by scripts/debug_grads.py: 2.4% already at the loss gradient of layer1, before any
-backward kernel has run).  Kernel-level backward parity is pinned tightly in test_gpu_kernels.py."""
+<= 1e-3.  End-to-end gradients are gated at <= 1e-2 relative L2 against the storage-precision
+emulation of the oracle (oracle/ghnd_oracle16.py: the fp32 oracle's graph and autograd with fp16
+activations / bf16 gradients rounded at exactly the tensors the engine stores) and REPORTED against
+the fp32 oracle: a 16-bit forward flips the ReLU mask of the ~0.2% of activations that sit within
+rounding distance of zero, which moves the fp32-oracle distance to 5-10% -- the emulation reproduces
+that on the CPU with none of the CUDA code, so what is left against it is accumulation order.
+Kernel-level backward parity is pinned tightly in test_gpu_kernels.py."""
 import copy
 import os
 
@@ -17,6 +19,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 from oracle import ghnd_oracle as O  # checker only
+from oracle import ghnd_oracle16 as O16
 from oracle import weights
 from tests.golden.make_golden import small_images
 
@@ -39,10 +42,10 @@ def cosine(a, b):
 ZERO_GRADS = ("decoder.3.bias", "decoder.8.bias")
 
 
-def check_grads(got, ref, tol=0.15, cos=0.985, tiny_tol=None):
-    """tiny_tol: separate relative-L2 bound for the few-element tensors (the bch-channel BN
-    gamma/beta of the bottleneck): each element is a heavily cancelling sum over all pixels, so on
-    small batches the mask-flip noise is a large fraction of the (small) total."""
+def check_grads(got, ref, emu, tol=1e-2, tiny_tol=None):
+    """got vs `emu` (storage-precision emulation, oracle16) gated at `tol` relative L2; got vs `ref`
+    (fp32 oracle) reported.  tiny_tol: separate bound for the few-element tensors (the bch-channel BN
+    gamma/beta of the bottleneck): each element is a heavily cancelling sum over all pixels."""
     scale = max(float(v.norm()) for v in ref.values())
     report = {}
     for n, r in ref.items():
@@ -50,11 +53,11 @@ def check_grads(got, ref, tol=0.15, cos=0.985, tiny_tol=None):
         if n.endswith(ZERO_GRADS):
             assert float(g.norm()) <= 1e-3 * scale, (n, float(g.norm()), scale)
             continue
-        report[n] = (round(rel(g, r), 4), round(cosine(g, r), 5))
-        if tiny_tol is not None and r.numel() < 16:
-            assert report[n][0] <= tiny_tol, (n, report[n])
-            continue
-        assert report[n][0] <= tol and report[n][1] >= cos, (n, report[n])
+        report[n] = (float("%.3g" % rel(g, emu[n])), float("%.3g" % rel(g, r)), round(cosine(g, r), 5))
+    print("grad (rel L2 vs emulation, rel L2 vs fp32 oracle, cosine vs fp32 oracle):", report)
+    for n, rep in report.items():
+        bound = tiny_tol if (tiny_tol is not None and ref[n].numel() < 16) else tol
+        assert rep[0] <= bound, (n, rep)
     return report
 
 
@@ -132,7 +135,12 @@ def oracle_step(env):
     return O.distill_step(env["t_sd"], env["s_sd"], small_images())
 
 
-def test_ghnd_step_matches_oracle_and_golden(env, oracle_step, golden_dir):
+@pytest.fixture(scope="module")
+def oracle16_step(env):
+    return O16.distill_step16(env["t_sd"], env["s_sd"], small_images())
+
+
+def test_ghnd_step_matches_oracle_and_golden(env, oracle_step, oracle16_step, golden_dir):
     from hnd_ghnd_object_detectors_b200.tool import DistillationBox
     from hnd_ghnd_object_detectors_b200 import ops
     teacher, student = build_pair(env)
@@ -156,8 +164,7 @@ def test_ghnd_step_matches_oracle_and_golden(env, oracle_step, golden_dir):
     # backward through the reference-style API
     loss.backward()
     params = dict(student.named_parameters())
-    rep = check_grads({n: params[n].grad for n in oracle_step["grads"]}, oracle_step["grads"])
-    print("grad (rel L2, cosine):", rep)
+    check_grads({n: params[n].grad for n in oracle_step["grads"]}, oracle_step["grads"], oracle16_step["grads"])
     # BN running statistics after one training step (nn.BatchNorm2d momentum update)
     bufs = dict(student.named_buffers())
     for k, v in oracle_step["bn_update"].items():
@@ -202,7 +209,8 @@ def test_hnd_layer1_only(env):
     assert abs(loss.item() - float(res["loss"])) <= 1e-3 * float(res["loss"])
     loss.backward()
     params = dict(student.named_parameters())
-    check_grads({n: params[n].grad for n in res["grads"]}, res["grads"])
+    emu = O16.distill_step16(env["t_sd"], env["s_sd"], small_images(), levels=("layer1",))
+    check_grads({n: params[n].grad for n in res["grads"]}, res["grads"], emu["grads"])
 
 
 def test_unshared_frozen_trunk(env):
@@ -222,7 +230,8 @@ def test_unshared_frozen_trunk(env):
     assert abs(loss.item() - float(res["loss"])) <= 1e-3 * float(res["loss"])
     loss.backward()
     params = dict(student.named_parameters())
-    check_grads({n: params[n].grad for n in res["grads"]}, res["grads"])
+    emu = O16.distill_step16(env["t_sd"], s_sd, small_images())
+    check_grads({n: params[n].grad for n in res["grads"]}, res["grads"], emu["grads"])
 
 
 def test_shared_frozen_trunk_is_detected(env):
@@ -346,9 +355,18 @@ def test_layer1_module_eval_and_train(env):
     ro = O.student_layer1_forward(xr, sd2, training=True)
     assert rel(out, ro) <= 1e-2
     grads = torch.autograd.grad(ro, [xr] + [sd2[n] for n in names], gy.cpu())
-    assert rel(xg.grad, grads[0]) <= 0.15
+    # the same step on the engine's storage points (fp16 input / activations, bf16 gradients)
+    sd3 = {k: v.clone() for k, v in env["s_sd"].items()}
+    for n in names:
+        sd3[n].requires_grad_(True)
+    x16 = O16.r16(x).requires_grad_(True)
+    ro16 = O16.G(O16.student_layer1_16(x16, sd3, training=True))
+    grads16 = torch.autograd.grad(ro16, [x16] + [sd3[n] for n in names], gy.cpu())
+    print("dx rel L2 vs emulation %.3g, vs fp32 oracle %.3g" % (rel(xg.grad, grads16[0]), rel(xg.grad, grads[0])))
+    assert rel(xg.grad, grads16[0]) <= 1e-2
     got = dict(layer.named_parameters())
-    check_grads({n: got[n[len("backbone.body.layer1."):]].grad for n in names}, dict(zip(names, grads[1:])))
+    check_grads({n: got[n[len("backbone.body.layer1."):]].grad for n in names}, dict(zip(names, grads[1:])),
+                dict(zip(names, grads16[1:])))
 
 
 def test_keypoint_multi_scale_step(env):
@@ -395,9 +413,8 @@ def test_keypoint_multi_scale_step(env):
             assert rel(ops.to_nchw_f32(plan.feat_t[lv]), ref["teacher"][lv]) <= 1e-2, (lv, sizes)
             assert rel(ops.to_nchw_f32(plan.feat_s[lv]), ref["student"][lv]) <= 1e-2, (lv, sizes)
         got = {n: p.grad.detach().cpu() for n, p in student.named_parameters() if p.requires_grad}
-        # these batches are as small as 2 x 64x96: the ReLU-mask-flip noise of the module docstring is
-        # averaged over ~3x fewer pixels than in the fixed-size test, hence the wider bound
-        check_grads(got, ref["grads"], tol=0.3, cos=0.95, tiny_tol=0.75)
+        emu = O16.distill_step16(env["t_sd"], env["s_sd"], host, sizes=sizes, max_size=192)
+        check_grads(got, ref["grads"], emu["grads"])
     assert len(shapes) == 4 and len(box._plans) == 3  # LRU: the oldest shape was evicted
 
 

@@ -1,0 +1,304 @@
+"""GPU parity at BASELINE.json's geometry (3x800x1333 -> padded 800x1344) and of the reference-facing
+entry points that the distillation fast path bypasses.
+
+* GHND step, one image and a batch of two, through DistillationBox vs the fp32 oracle (loss <= 1e-3,
+  per-level relative L2 <= 1e-2) and vs the storage-precision emulation of the same oracle
+  (oracle/ghnd_oracle16.py: gradients <= 1e-2 relative L2; the distance to the fp32 oracle is printed
+  next to it -- that one is dominated by ReLU masks moved by 16-bit storage, which the emulation
+  reproduces on the CPU without any of the CUDA code).
+* RcnnHead (config 1: batch 2 at 800x1333) vs O.encode_head: bytes bit-exact for the same z, end-to-end
+  byte-difference histogram printed.
+* CustomRCNN.forward with distill_backbone_only (src/models/org/rcnn.py:102-110) in train and eval
+  mode, and the eval-time quantize/dequantize splice (src/models/mimic/base.py:50-58) through BodyPlan.
+* mimic_runner.main on a reference-schema YAML with `dataset.name: synthetic`: -distill for a few
+  steps, checkpoint with optimizer state, resume, evaluation entry point with -transform_bottleneck.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import ghnd_oracle as O  # checker only
+from oracle import ghnd_oracle16 as O16
+from oracle import weights
+from tests.test_gpu_distill import (LEVELS, ZERO_GRADS, build_pair, cosine, criterion_config, env,  # noqa: F401
+                                    model_config, rel, targets_for)
+
+
+def full_images(n, seed=5):
+    g = torch.Generator().manual_seed(seed)
+    return [torch.rand(3, 800, 1333, generator=g) for _ in range(n)]
+
+
+def grad_report(got, ref16, ref32):
+    """{name: (rel L2 vs emulation, rel L2 vs fp32 oracle)}; zero-gradient tensors in absolute terms."""
+    scale = max(float(v.norm()) for v in ref32.values())
+    rep = {}
+    for n in ref32:
+        g = got[n].detach().float().cpu()
+        if n.endswith(ZERO_GRADS):
+            assert float(g.norm()) <= 1e-3 * scale, (n, float(g.norm()), scale)
+            continue
+        rep[n] = (rel(g, ref16[n]), rel(g, ref32[n]))
+    return rep
+
+
+def build_full_pair(env_, min_size=800, max_size=1333):
+    models, mu = env_["models"], env_["module_util"]
+    dev = torch.device("cuda")
+    teacher = models.get_model(model_config("teacher", min_size=min_size, max_size=max_size), dev)
+    student = models.get_model(model_config("student", min_size=min_size, max_size=max_size), dev)
+    teacher.load_state_dict(env_["t_sd"], strict=False)
+    student.load_state_dict(env_["s_sd"], strict=False)
+    mu.freeze_module_params(teacher)
+    for path in model_config("student")["frozen_modules"]:
+        mu.freeze_module_params(mu.get_module(student, path))
+    teacher.eval()
+    student.train()
+    teacher.distill_backbone_only = student.distill_backbone_only = True
+    return teacher, student
+
+
+@pytest.mark.parametrize("batch", [1, 2])
+def test_ghnd_step_at_800x1333_matches_oracle(env, batch):
+    from hnd_ghnd_object_detectors_b200 import ops
+    from hnd_ghnd_object_detectors_b200.tool import DistillationBox
+    teacher, student = build_full_pair(env)
+    box = DistillationBox(teacher, student, criterion_config())
+    host = full_images(batch)
+    images = [im.cuda() for im in host]
+    loss = box(images, targets_for(images))
+    loss.backward()
+    torch.cuda.synchronize()
+    plan = list(box._plans.values())[0]
+    assert (plan.N, plan.Hp, plan.Wp) == (batch, 800, 1344)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    ref = O.distill_step(env["t_sd"], env["s_sd"], host)
+    emu = O16.distill_step16(env["t_sd"], env["s_sd"], host)
+    err = abs(loss.item() - float(ref["loss"])) / float(ref["loss"])
+    print("batch %d loss %.6g oracle %.6g rel %.2e (emulation %.6g)" % (batch, loss.item(), float(ref["loss"]), err,
+                                                                    float(emu["loss"])))
+    assert err <= 1e-3
+    assert abs(loss.item() - float(emu["loss"])) <= 2e-4 * float(emu["loss"])
+    for i, lv in enumerate(LEVELS):
+        t, s_ = ops.to_nchw_f32(plan.feat_t[lv]), ops.to_nchw_f32(plan.feat_s[lv])
+        assert tuple(t.shape) == tuple(ref["teacher"][lv].shape)
+        rt, rs = rel(t, ref["teacher"][lv]), rel(s_, ref["student"][lv])
+        et, es = rel(t, emu["teacher"][lv]), rel(s_, emu["student"][lv])
+        print("%s rel L2 vs fp32 oracle: teacher %.2e student %.2e | vs emulation: %.2e %.2e" % (lv, rt, rs, et, es))
+        assert rt <= 1e-2 and rs <= 1e-2, lv
+        assert et <= 2e-3 and es <= 2e-3, lv
+        term = float(box.last_terms[1 + i])
+        assert abs(term - float(ref["per_level"][lv])) <= 2e-3 * float(ref["per_level"][lv]), lv
+    params = dict(student.named_parameters())
+    rep = grad_report({n: params[n].grad for n in ref["grads"]}, emu["grads"], ref["grads"])
+    for n, (e16, e32) in rep.items():
+        print("grad %-50s vs emulation %.2e   vs fp32 oracle %.2e" % (n, e16, e32))
+    worst = max(v[0] for v in rep.values())
+    assert worst <= 1e-2, rep
+
+
+def test_rcnn_head_at_800x1333_batch2(env):
+    """BASELINE config 1 geometry: Faster R-CNN b3ch head forward + 8-bit quantize, batch 2."""
+    from hnd_ghnd_object_detectors_b200.split_rcnn import split_rcnn_model
+    models = env["models"]
+    student = models.get_model(model_config("student", min_size=800, max_size=1333), torch.device("cuda"))
+    student.load_state_dict(env["s_sd"], strict=False)
+    student.eval()
+    head, _tail = split_rcnn_model(student, 8)
+    host = full_images(2, seed=9)
+    qz, tshape, image_sizes, orig = head([im.cuda() for im in host])
+    q_ref, scale_ref, zp_ref, z_ref, shape_ref = O.encode_head(host, env["s_sd"], 8)
+    assert tuple(tshape) == tuple(shape_ref) == (2, 3, 800, 1344)
+    assert tuple(qz.tensor.shape) == (2, 3, 204, 340) and qz.tensor.dtype == torch.uint8
+    z = head.plan.z.cpu()
+    print("z rel L2 vs oracle %.2e" % rel(z, z_ref))
+    assert rel(z, z_ref) <= 1e-2
+    # the quantizer: bit-exact for the SAME z
+    qo, so, zo = O.quantize_tensor_np(z.numpy(), 8)
+    got = qz.tensor.cpu().numpy()
+    assert np.array_equal(got, qo) and zo == qz.zero_point and float(qz.scale) == float(so)
+    # end to end (fp16 convolutions may move a value across a rounding boundary)
+    diff = np.abs(got.astype(np.int32) - q_ref.astype(np.int32))
+    hist = np.bincount(diff.reshape(-1), minlength=4)
+    print("end-to-end byte |diff| histogram:", hist[:6].tolist(), "of", diff.size,
+          "zp %d/%d scale %.6g/%.6g" % (qz.zero_point, zp_ref, float(qz.scale), float(scale_ref)))
+    assert abs(qz.zero_point - zp_ref) <= 1 and abs(float(qz.scale) - float(scale_ref)) <= 2e-3 * float(scale_ref)
+    assert diff.max() <= 2 and (diff > 0).mean() < 0.10
+
+
+def test_custom_rcnn_forward_distill_short_circuit(env):
+    """student(images, targets) with distill_backbone_only=True (rcnn.py:102-110): the body features of
+    the bottleneck-injected ResNet-50, train mode (batch statistics, running stats updated) and eval
+    mode without / with the 8-bit splice (base.py:50-58), all through engine.BodyPlan."""
+    teacher, student = build_pair(env)
+    from tests.golden.make_golden import small_images
+    host = small_images()
+    images = [im.cuda() for im in host]
+    x = O.transform_batch(host)
+    # ---- train mode ----
+    rm0 = student.backbone.body.layer1.decoder[10].running_mean.clone()
+    feats = student(images, targets_for(images))
+    assert list(feats.keys()) == ["0", "1", "2", "3"]
+    upd = {}
+    with torch.no_grad():
+        ref = O.backbone_features(x, env["s_sd"], student=True, training=True, update=upd)
+    for i, lv in enumerate(LEVELS):
+        assert tuple(feats[str(i)].shape) == tuple(ref[lv].shape)
+        assert rel(feats[str(i)], ref[lv]) <= 1e-2, (lv, rel(feats[str(i)], ref[lv]))
+    assert not torch.equal(student.backbone.body.layer1.decoder[10].running_mean, rm0)
+    assert rel(student.backbone.body.layer1.decoder[10].running_mean,
+               upd["backbone.body.layer1.decoder.10.running_mean"]) < 2e-3
+    with pytest.raises(ValueError):
+        student(images)  # training mode needs targets (rcnn.py:103-104)
+    # ---- teacher (frozen ResNet-50 body) ----
+    tf = teacher(images)
+    with torch.no_grad():
+        tref = O.backbone_features(x, env["t_sd"], student=False)
+    for i, lv in enumerate(LEVELS):
+        assert rel(tf[str(i)], tref[lv]) <= 1e-2, lv
+    # ---- eval mode: same shape, the plan must be rebuilt for running-statistics BN ----
+    student.load_state_dict(env["s_sd"], strict=False)  # undo the running-stat update
+    student.eval()
+    fe = student(images)
+    with torch.no_grad():
+        ref_e = O.backbone_features(x, env["s_sd"], student=True, training=False)
+    for i, lv in enumerate(LEVELS):
+        assert rel(fe[str(i)], ref_e[lv]) <= 1e-2, (lv, rel(fe[str(i)], ref_e[lv]))
+    # ---- eval + -transform_bottleneck: quantize -> dequantize spliced between encoder and decoder ----
+    student.backbone.body.layer1.use_bottleneck_transformer = True
+    fq = student(images)
+    with torch.no_grad():
+        s = O.stem_forward(x, env["s_sd"])
+        l1 = O.student_layer1_forward(s, env["s_sd"], training=False, quantize_bits=8)
+        assert rel(fq["0"], l1) <= 2e-2, rel(fq["0"], l1)
+        cur = l1
+        for i, name in enumerate(("layer2", "layer3", "layer4")):
+            cur = O.frozen_layer_forward(cur, env["s_sd"], name)
+            assert rel(fq[str(i + 1)], cur) <= 2e-2, (name, rel(fq[str(i + 1)], cur))
+    assert rel(fq["0"], fe["0"]) > 1e-4  # the splice really ran
+    # ---- full detector forward (FPN / RPN / RoI heads are torchvision modules on those features) ----
+    student.distill_backbone_only = False
+    with torch.no_grad():
+        det = student(images)
+    assert isinstance(det, list) and len(det) == len(images) and set(det[0].keys()) >= {"boxes", "labels", "scores"}
+
+
+YAML = """
+dataset:
+    name: 'synthetic'
+    num_samples: 8
+    image_size: [96, 128]
+
+teacher_model:
+    name: &teacher_model_name 'faster_rcnn'
+    backbone:
+        name: &teacher_backbone_name 'resnet50'
+        params:
+            pretrained: False
+            freeze_layers: True
+    params:
+        num_classes: 91
+        pretrained: False
+        min_size: 96
+        max_size: 128
+    ckpt: !join ['{root}', '/org/', *teacher_model_name, '-backbone_', *teacher_backbone_name, '.pt']
+
+student_model:
+    name: &student_model_name 'faster_rcnn'
+    backbone:
+        name: &student_backbone_name 'custom_resnet50'
+        params:
+            pretrained: False
+            freeze_layers: False
+            layer1:
+                name: 'Bottleneck4LargeResNet'
+                bottleneck_channel: &bch 3
+    bottleneck_transformer:
+        order: ['quantizer', 'dequantizer']
+        components:
+            quantizer:
+                params:
+                    num_bits: 8
+            dequantizer:
+                params:
+                    num_bits: 8
+    params:
+        num_classes: 91
+        pretrained: False
+        min_size: 96
+        max_size: 128
+    distill_backbone_only: True
+    frozen_modules: ['backbone.body.layer2', 'backbone.body.layer3', 'backbone.body.layer4', 'backbone.fpn', 'rpn', 'roi_heads']
+    ckpt: !join ['{root}', '/ghnd/', *student_model_name, '-b', *bch, 'ch.pt']
+
+train:
+    num_epochs: 1
+    batch_size: 2
+    log_freq: 1
+    optimizer:
+        type: 'Adam'
+        params:
+            lr: 0.001
+    criterion:
+        type: 'general'
+        params:
+            org_loss_factor: 0.0
+        terms:
+            layer1:
+                ts_modules: ['backbone.body.layer1', 'backbone.body.layer1']
+                criterion:
+                    type: 'MSELoss'
+                    params:
+                        reduction: 'sum'
+                factor: 1.0
+            layer4:
+                ts_modules: ['backbone.body.layer4', 'backbone.body.layer4']
+                criterion:
+                    type: 'MSELoss'
+                    params:
+                        reduction: 'sum'
+                factor: 1.0
+    scheduler:
+        type: 'MultiStepLR'
+        params:
+            milestones: [5, 15]
+            gamma: 0.1
+
+test:
+    batch_size: 1
+"""
+
+
+def test_mimic_runner_main_distill_resume_and_eval(tmp_path, capsys):
+    """src/mimic_runner.py:124-151 end to end on synthetic data: -distill trains 4 steps and writes the
+    reference checkpoint layout (model / optimizer / lr_scheduler / best_value / config / args); a
+    second run resumes the Adam moments and step count; the evaluation entry point runs the teacher
+    and the student (quantized bottleneck under -transform_bottleneck) and reports wire bytes."""
+    from hnd_ghnd_object_detectors_b200 import mimic_runner
+    cfg_path = tmp_path / "ghnd.yaml"
+    cfg_path.write_text(YAML.replace("{root}", str(tmp_path)))
+    args = mimic_runner.get_argparser().parse_args(["--config", str(cfg_path), "-distill", "-transform_bottleneck"])
+    res = mimic_runner.main(args)
+    out = capsys.readouterr().out
+    assert "Updatable parameters" in out and "Epoch: [0]" in out and "[Student model]" in out
+    ckpt_path = tmp_path / "ghnd" / "faster_rcnn-b3ch.pt"
+    assert ckpt_path.exists()
+    ckpt = torch.load(str(ckpt_path), map_location="cpu", weights_only=False)
+    assert set(ckpt.keys()) >= {"model", "optimizer", "lr_scheduler", "best_value", "config", "args"}
+    st = ckpt["optimizer"]["state"]
+    assert len(st) == 25 and all(int(s["step"]) == 4 for s in st.values())
+    assert all(float(s["exp_avg_sq"].abs().sum()) > 0 for s in st.values())
+    assert res["student"]["images"] == 8 and res["teacher"]["images"] == 8
+    kb = res["student"]["bottleneck_kb_per_image"]
+    n_bytes = 3 * (96 // 4 + 4) * (128 // 4 + 4)  # b3ch bottleneck of a 96x128 image, one byte per value
+    assert n_bytes / 1024 < kb < n_bytes / 1024 + 2, kb
+    # resume: the optimizer continues from step 4
+    args2 = mimic_runner.get_argparser().parse_args(["--config", str(cfg_path), "-distill", "-skip_teacher_eval"])
+    res2 = mimic_runner.main(args2)
+    ckpt2 = torch.load(str(ckpt_path), map_location="cpu", weights_only=False)
+    assert all(int(s["step"]) == 8 for s in ckpt2["optimizer"]["state"].values())
+    assert "teacher" not in res2 and "bottleneck_kb_per_image" not in res2["student"]
