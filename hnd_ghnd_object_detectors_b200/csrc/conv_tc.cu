@@ -244,10 +244,19 @@ __device__ __forceinline__ void epi_stats_rows(const uint8_t* base, int quarter,
       q1 = fmaf(f.y, f.y, q1);
     }
   }
-  atomicAdd(&sstat[ch + 2 * lane], s0);
-  atomicAdd(&sstat[ch + 2 * lane + 1], s1);
-  atomicAdd(&sstat[cout + ch + 2 * lane], q0);
-  atomicAdd(&sstat[cout + ch + 2 * lane + 1], q1);
+  // `sstat` is PRIVATE to this warp and each lane owns its channel pair: plain read-modify-write.
+  // (Shared-memory float atomicAdd is a compare-and-swap spin loop in SASS -- ATOMS.CAST.SPIN --
+  // and eight warps hitting the same 64 addresses after every chunk made these launches the
+  // slowest tensor-core kernels of the step, 0.31-0.39 of their HBM bound.)
+  float2* a = reinterpret_cast<float2*>(sstat + ch + 2 * lane);
+  float2* b = reinterpret_cast<float2*>(sstat + cout + ch + 2 * lane);
+  float2 av = *a, bv = *b;
+  av.x += s0;
+  av.y += s1;
+  bv.x += q0;
+  bv.y += q1;
+  *a = av;
+  *b = bv;
 }
 
 // BN-backward variant: sum of the staged output g and of g * a, a = the in1 operand tile (same
@@ -272,10 +281,19 @@ __device__ __forceinline__ void epi_stats2_rows(const uint8_t* base, const uint8
       q1 = fmaf(f.y, g.y, q1);
     }
   }
-  atomicAdd(&sstat[ch + 2 * lane], s0);
-  atomicAdd(&sstat[ch + 2 * lane + 1], s1);
-  atomicAdd(&sstat[cout + ch + 2 * lane], q0);
-  atomicAdd(&sstat[cout + ch + 2 * lane + 1], q1);
+  // `sstat` is PRIVATE to this warp and each lane owns its channel pair: plain read-modify-write.
+  // (Shared-memory float atomicAdd is a compare-and-swap spin loop in SASS -- ATOMS.CAST.SPIN --
+  // and eight warps hitting the same 64 addresses after every chunk made these launches the
+  // slowest tensor-core kernels of the step, 0.31-0.39 of their HBM bound.)
+  float2* a = reinterpret_cast<float2*>(sstat + ch + 2 * lane);
+  float2* b = reinterpret_cast<float2*>(sstat + cout + ch + 2 * lane);
+  float2 av = *a, bv = *b;
+  av.x += s0;
+  av.y += s1;
+  bv.x += q0;
+  bv.y += q1;
+  *a = av;
+  *b = bv;
 }
 
 // Packed 16-bit-pair helpers on raw 32-bit words (FMT = GHND_F16 or GHND_BF16)
@@ -375,8 +393,8 @@ __global__ void __launch_bounds__(kConvThreads, 1)
   uint8_t* epi_out = wres + (HALO ? p.w_res_bytes : 0);                  // [2 groups][kChunkBytes]
   uint8_t* epi_in = epi_out + (size_t)2 * p.epi_bufs * kChunkBytes;        // [ring][n_in][kChunkBytes]
   float* sbias = reinterpret_cast<float*>(epi_in + (size_t)p.ring * n_in * kChunkBytes);  // [cout]
-  float* sstat = sbias + (p.bias != nullptr ? p.cout : 0);                 // [2*cout] when stats
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sstat + (STATS ? 2 * p.cout : 0));
+  float* sstat = sbias + (p.bias != nullptr ? p.cout : 0);                 // [8 epilogue warps][2*cout] when stats
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sstat + (STATS ? kEpiThreads / 32 * 2 * p.cout : 0));
   uint64_t* full_bar = bars;                        // [kMaxStages]
   uint64_t* empty_bar = full_bar + kMaxStages;      // [kMaxStages]
   uint64_t* tfull_bar = empty_bar + kMaxStages;     // [2]
@@ -637,7 +655,8 @@ __global__ void __launch_bounds__(kConvThreads, 1)
       }
     }
     if (STATS)
-      for (int i = threadIdx.x - kEpiWarp0 * 32; i < 2 * p.cout; i += kEpiThreads) sstat[i] = 0.f;
+      for (int i = threadIdx.x - kEpiWarp0 * 32; i < kEpiThreads / 32 * 2 * p.cout; i += kEpiThreads) sstat[i] = 0.f;
+    float* const wstat = sstat + (size_t)(warp - kEpiWarp0) * 2 * p.cout;  // this warp's private partial sums
     named_bar_sync(3, kEpiThreads);
     int it = 0;
     uint32_t cnt0 = 0;  // global chunk counter at the start of the tile
@@ -723,7 +742,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
             bulk_commit();
           }
           if (STATS && EPI == 1)  // plain sum / sum of squares of the staged f16 tile (stats_mode 0)
-            epi_stats_rows<GHND_F16>(o_base, quarter, lane, valid, sstat, ch, p.cout);
+            epi_stats_rows<GHND_F16>(o_base, quarter, lane, valid, wstat, ch, p.cout);
           continue;
         }
         float v[64];
@@ -809,12 +828,12 @@ __global__ void __launch_bounds__(kConvThreads, 1)
         if (STATS) {
           if (p.stats_mode == 1) {
             // bf16 gradient out, f16 activation operand (the only combination the plans accept)
-            epi_stats2_rows<GHND_BF16, GHND_F16>(o_base, m_base, quarter, lane, valid, sstat, ch, p.cout);
+            epi_stats2_rows<GHND_BF16, GHND_F16>(o_base, m_base, quarter, lane, valid, wstat, ch, p.cout);
             mbar_arrive(&iempty_bar[slot]);  // now the operand buffer may be refilled
           } else if (p.out_fmt == GHND_F16) {
-            epi_stats_rows<GHND_F16>(o_base, quarter, lane, valid, sstat, ch, p.cout);
+            epi_stats_rows<GHND_F16>(o_base, quarter, lane, valid, wstat, ch, p.cout);
           } else {
-            epi_stats_rows<GHND_BF16>(o_base, quarter, lane, valid, sstat, ch, p.cout);
+            epi_stats_rows<GHND_BF16>(o_base, quarter, lane, valid, wstat, ch, p.cout);
           }
         }
       }
@@ -822,8 +841,12 @@ __global__ void __launch_bounds__(kConvThreads, 1)
     if (etid == 0) bulk_wait_all();
     if (STATS) {
       named_bar_sync(3, kEpiThreads);  // both groups: all shared-memory partial sums are in
-      for (int i = threadIdx.x - kEpiWarp0 * 32; i < 2 * p.cout; i += kEpiThreads)
-        atomicAdd(p.stats + i, (double)sstat[i]);
+      for (int i = threadIdx.x - kEpiWarp0 * 32; i < 2 * p.cout; i += kEpiThreads) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < kEpiThreads / 32; ++w) t += sstat[(size_t)w * 2 * p.cout + i];
+        atomicAdd(p.stats + i, (double)t);
+      }
     }
   }
 
@@ -1067,7 +1090,7 @@ static int finish_launch(ConvLaunch* L, const ghnd_conv_desc_t* d, int gemm_cin,
   // its 4 slots) next to them; otherwise one.
   p.epi_bufs = epi_bufs_default();
   if (p.epi_bufs == 2) {
-    const int fixed2 = 4 * kChunkBytes + (d->bias ? gemm_cout * 4 : 0) + (d->stats ? gemm_cout * 8 : 0);
+    const int fixed2 = 4 * kChunkBytes + (d->bias ? gemm_cout * 4 : 0) + (d->stats ? gemm_cout * 8 * (kEpiThreads / 32) : 0);
     const int ring2 = n_in > 0 ? ((kSmemBudget - fixed2 - 3 * p.stage_bytes) / (n_in * kChunkBytes) >= 4 ? 4 : 2) : 0;
     const int ring1 = n_in > 0 ? ((kSmemBudget - (fixed2 - 2 * kChunkBytes) - 3 * p.stage_bytes) /
                                               (n_in * kChunkBytes) >= 4 ? 4 : 2) : 0;
@@ -1075,7 +1098,7 @@ static int finish_launch(ConvLaunch* L, const ghnd_conv_desc_t* d, int gemm_cin,
     if (stages2 < 3 || ring2 < ring1) p.epi_bufs = 1;
   }
   const int fixed = 2 * p.epi_bufs * kChunkBytes + (d->bias ? gemm_cout * 4 : 0) +
-                    (d->stats ? gemm_cout * 8 : 0);
+                    (d->stats ? gemm_cout * 8 * (kEpiThreads / 32) : 0);
   const int stages_per_tile = (n_units + p.units_per_stage - 1) / p.units_per_stage;
   int ring = 0;
   if (n_in > 0) {
@@ -1184,16 +1207,16 @@ int ghnd_conv_plan_create(const ghnd_conv_desc_t* d, ghnd_conv_plan_t** out) {
   GHND_CHECK_ARG(d->stats == nullptr || d->stats_mode == 0 || d->stats_mode == 1, "conv: bad stats_mode %d",
                  d->stats_mode);
   GHND_CHECK_ARG(d->stats == nullptr || d->stats_mode != 0 ||
-                     (d->kind == GHND_CONV_FWD && d->stride == 1 && d->K <= 1024),
-                 "conv: fused output statistics need a stride-1 forward conv with K <= 1024");
+                     (d->kind == GHND_CONV_FWD && d->stride == 1 && d->K <= 256),
+                 "conv: fused output statistics need a stride-1 forward conv with K <= 256");
   GHND_CHECK_ARG(d->stats == nullptr || d->stats_mode != 1 ||
                      (d->dst_fmt == GHND_BF16 && d->mask_fmt == GHND_F16),
                  "conv: BN-backward statistics need a bf16 output and an f16 mask operand");
   GHND_CHECK_ARG(d->stats == nullptr || d->stats_mode != 1 ||
                      (d->stride == 1 && d->mask != nullptr && !d->accumulate &&
-                      (d->kind == GHND_CONV_FWD ? d->K : d->C) <= 1024),
+                      (d->kind == GHND_CONV_FWD ? d->K : d->C) <= 256),
                  "conv: BN-backward statistics need a stride-1 launch with a mask operand, no "
-                 "accumulate and <= 1024 output channels");
+                 "accumulate and <= 256 output channels");
   GHND_CHECK_ARG(((uintptr_t)d->src % 16) == 0 && ((uintptr_t)d->weights % 16) == 0 &&
                      ((uintptr_t)d->dst % 16) == 0 && ((uintptr_t)d->residual % 16) == 0 &&
                      ((uintptr_t)d->mask % 16) == 0 && ((uintptr_t)d->bias % 16) == 0,
