@@ -7,7 +7,11 @@
 Workload (N=1): Faster R-CNN ResNet-50-FPN b3ch GHND distillation step -- teacher forward, student
 forward, 4-level SSE loss, student backward, gradient all-reduce (N>1), fused Adam -- on 4 synthetic
 3x800x1333 images per GPU (config/ghnd/faster_rcnn-backbone_resnet50-b3ch.yaml: batch_size 4),
-random-init weights.  One JSON line is printed by rank 0.
+random-init weights.  One JSON line is printed by rank 0.  Beside the headline it carries the other
+BASELINE.json configs: `config1` (head + 8-bit quantize: CPU reference leg and the CUDA path, batch 2),
+`config4` (Keypoint R-CNN, batch 8 per GPU, all-800 and random-scale seed 0; N=1 and N=8 runs),
+`encode` (config 5: batch 1..64 sweep), and an informational `stock_torch_cuda` leg (the oracle port
+of the same step run by stock PyTorch/cuDNN on the same B200, fp32 and TF32).
 """
 import argparse
 import json
@@ -98,10 +102,13 @@ class ClockSampler(object):
 
 def ncu_traffic():
     """DRAM bytes of the conv family from the committed ncu capture (profiles/), if present."""
-    path = os.path.join(ROOT, "profiles", "r1_conv_dram_traffic.json")
-    if os.path.isfile(path):
-        with open(path) as f:
-            return json.load(f)
+    for name in ("r2_conv_dram_traffic.json", "r1_conv_dram_traffic.json"):
+        path = os.path.join(ROOT, "profiles", name)
+        if os.path.isfile(path):
+            with open(path) as f:
+                d = json.load(f)
+            d["file"] = "profiles/" + name
+            return d
     return {}
 
 
@@ -118,37 +125,76 @@ def measured_peaks():
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port of the reference algorithm on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_step_fn(sample_batch):
+CPU_SAMPLE_BATCH = 2  # the reference arm steps on 2 images
+
+
+def cpu_step_fn(sample_batch, device="cpu", tf32=False):
+    """One step of the reference algorithm (oracle port, stock torch ops): teacher forward, student
+    forward + backward through autograd, 4-level MSE(sum) loss, Adam over the 25 trainable tensors
+    (src/distillation/tool.py:40-61, src/mimic_runner.py:51-54).  device="cuda": the same Python on the
+    GPU through cuDNN/ATen ("stock PyTorch on the same box")."""
+    import torch
+    from oracle import ghnd_oracle as O
+    from oracle import weights
+    if device == "cpu":
+        torch.set_num_threads(os.cpu_count() or 1)
+    else:
+        torch.backends.cudnn.allow_tf32 = bool(tf32)
+        torch.backends.cuda.matmul.allow_tf32 = bool(tf32)
+    t_sd, s_sd = weights.teacher_student(3, seed=0)
+    t_sd = {k: v.to(device) for k, v in t_sd.items()}
+    s_sd = {k: v.to(device) for k, v in s_sd.items()}
+    g = torch.Generator().manual_seed(0)
+    images = [torch.rand(3, IMG_H, IMG_W, generator=g).to(device) for _ in range(sample_batch)]
+    state = {"step": 0, "m": {}, "v": {}}
+
+    def step():
+        res = O.distill_step(t_sd, s_sd, images)
+        state["step"] += 1
+        for n, gr in res["grads"].items():
+            m = state["m"].get(n, torch.zeros_like(gr))
+            v = state["v"].get(n, torch.zeros_like(gr))
+            s_sd[n], state["m"][n], state["v"][n] = O.adam_step(s_sd[n], gr, m, v, state["step"])
+        return float(res["loss"])
+    return step
+
+
+def cpu_encode_fn(sample_batch):
+    """BASELINE config 1: Faster R-CNN b3ch head forward + 8-bit quantize on the host cores."""
     import torch
     from oracle import ghnd_oracle as O
     from oracle import weights
     torch.set_num_threads(os.cpu_count() or 1)
-    t_sd, s_sd = weights.teacher_student(3, seed=0)
+    _, s_sd = weights.teacher_student(3, seed=0)
     g = torch.Generator().manual_seed(0)
     images = [torch.rand(3, IMG_H, IMG_W, generator=g) for _ in range(sample_batch)]
 
     def step():
-        res = O.distill_step(t_sd, s_sd, images)
-        return float(res["loss"])
+        return O.encode_head(images, s_sd, 8)[1]
     return step
+
+
+def time_host(fn, warmup, steps):
+    for _ in range(warmup):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fn()
+    return (time.perf_counter() - t0) / steps
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample_batch = 1
+    sample_batch = CPU_SAMPLE_BATCH
     step = cpu_step_fn(sample_batch)
-    for _ in range(args.warmup):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()
-    dt = time.perf_counter() - t0
+    dt = time_host(step, args.warmup, args.steps) * args.steps
     val = sample_batch * args.steps / dt
     cores = os.cpu_count() or 1
-    sample = ("each step = oracle port (torch CPU fp32, oracle/ghnd_oracle.py distill_step) of the same "
-              "GHND step on %d image of 3x800x1333" % sample_batch)
+    sample = ("each step = oracle port (torch CPU fp32, oracle/ghnd_oracle.py distill_step + adam_step) of the "
+              "same GHND step (teacher fwd, student fwd/bwd, 4-level loss, Adam) on %d images of 3x800x1333, "
+              "%d torch threads" % (sample_batch, cores))
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -209,15 +255,42 @@ def time_entry_points(fn):
     return out
 
 
-def encode_sweep(dev, batches, iters=10):
-    """Config 5: Keypoint R-CNN b3ch split-computing head (stem + layer1 encoder + 8-bit quantizer),
-    images/s per batch size, inputs resident in HBM; also the quantizer's achieved HBM GB/s."""
+def flush_l2(dev, _buf={}):
+    """Write a buffer larger than the 126 MB L2 so the next kernel starts cold."""
     import torch
-    from hnd_ghnd_object_detectors_b200 import models
+    if "b" not in _buf:
+        _buf["b"] = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    _buf["b"].zero_()
+
+
+def time_cold(fn, dev, iters=5):
+    """Median CUDA-event time (s) of fn() with an L2 flush before every call."""
+    import torch
+    ts = []
+    for _ in range(iters + 1):
+        flush_l2(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e-3)
+    ts = sorted(ts[1:])
+    return ts[len(ts) // 2]
+
+
+def encode_sweep(dev, batches, iters=10, model_name="keypoint_rcnn"):
+    """Config 5: Keypoint R-CNN b3ch split-computing head (stem + layer1 encoder + 8-bit quantizer),
+    images/s per batch size, inputs resident in HBM; also achieved HBM GB/s of the bottleneck-side
+    kernels at the largest batch (cold L2): the encoder's last conv (64 -> bch, narrow_out), the
+    one-pass quantizer fed by its min/max, the stand-alone quantizer and the dequantizer."""
+    import torch
+    from hnd_ghnd_object_detectors_b200 import models, ops
     from hnd_ghnd_object_detectors_b200.split_rcnn import split_rcnn_model
     cfg = model_config(True)
-    cfg["name"] = "keypoint_rcnn"
-    cfg["params"] = {"num_classes": 2, "pretrained": False, "num_keypoints": 17}
+    cfg["name"] = model_name
+    if model_name == "keypoint_rcnn":
+        cfg["params"] = {"num_classes": 2, "pretrained": False, "num_keypoints": 17}
     torch.manual_seed(0)
     import contextlib
     with contextlib.redirect_stdout(sys.stderr):
@@ -226,7 +299,7 @@ def encode_sweep(dev, batches, iters=10):
     out = {}
     g = torch.Generator().manual_seed(5)
     pool = [torch.rand(3, IMG_H, IMG_W, generator=g).to(dev) for _ in range(4)]
-    quant_gbs = None
+    kernels = {}
     for b in batches:
         images = [pool[i % len(pool)] for i in range(b)]
         head(images)  # builds + captures the fixed-shape plan
@@ -242,16 +315,129 @@ def encode_sweep(dev, batches, iters=10):
         torch.cuda.synchronize()
         out[str(b)] = b * iters / (e0.elapsed_time(e1) * 1e-3)
         if b == batches[-1]:
-            plan_graph, plan.graph = plan.graph, None
-            try:
-                t = time_entry_points(plan.run)
-            finally:
-                plan.graph = plan_graph
-            # one streaming pass: min / max arrive from the encoder's last conv
-            if "ghnd_quantize_u8_minmax" in t:
-                quant_gbs = 5.0 * plan.z.numel() / t["ghnd_quantize_u8_minmax"][0] / 1e9
+            z, l1 = plan.z, plan.l1
+            nz = float(z.numel())
+            wide = float(l1.e2.out.numel())
+            t = time_cold(lambda: ops.quantize_u8_minmax(z, plan.minmax, l1.z_pairs, 8, plan.scale_mode, q=plan.q,
+                                                         qparams=plan.qparams), dev)
+            kernels["quant_apply (one-pass 8-bit quantizer of the encode path, min/max from the encoder's last conv; 5 B/elem, batch %d)" % b] = 5.0 * nz / t
+            t = time_cold(lambda: ops.quantize_u8(z, 8), dev)
+            kernels["quantize_u8 (stand-alone quantize_tensor: min/max + quantize in one persistent launch; 5 B/elem compulsory, batch %d)" % b] = 5.0 * nz / t
+            q, qp = ops.quantize_u8(z, 8)
+            t = time_cold(lambda: ops.dequantize_u8(q, qp), dev)
+            kernels["dequantize_u8 (1 B in, 4 B out per elem, batch %d)" % b] = 5.0 * nz / t
+            t = time_cold(lambda: ops.conv_narrow_out(l1.e2.out, l1.enc7.weight, 1, y=z, ws=l1.nws, minmax=plan.minmax), dev)
+            kernels["narrow_out (encoder's last conv 64 -> bch k2 + min/max; 2 B/elem of the 64-ch input + 4 B/elem of z, batch %d)" % b] = (2.0 * wide + 4.0 * nz) / t
         head.plan = None
-    return out, quant_gbs
+    return out, kernels
+
+
+def config4_bench(dev, world, steps=10, warmup=3):
+    """BASELINE config 4: Keypoint R-CNN b3ch GHND distillation, 8 images per GPU.  The Keypoint path
+    draws a per-image `fixed_sizes` from min_size = (640..800) (src/distillation/tool.py:44-49), so
+    every step is a bilinear resize + a padded shape picked by the largest image of the batch; the
+    box keeps one plan + CUDA graph per padded shape.  Two runs: all images at 800 (one shape) and
+    random scales with random.seed(0).  Through the public API (DistillationBox -> backward -> flat
+    all-reduce -> FusedAdam), images resident on the device."""
+    import contextlib
+    import random
+    import torch
+    import torch.distributed as dist
+    from hnd_ghnd_object_detectors_b200 import models, module_util, parallel
+    from hnd_ghnd_object_detectors_b200.optim import FusedAdam
+    from hnd_ghnd_object_detectors_b200.tool import DistillationBox
+    batch = 8
+    rank = int(os.environ.get("RANK", "0"))
+
+    def cfg(student):
+        c = model_config(student)
+        c["name"] = "keypoint_rcnn"
+        c["params"] = {"num_classes": 2, "pretrained": False, "num_keypoints": 17}
+        return c
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(sys.stderr):
+        teacher = models.get_model(cfg(False), dev)
+        student = models.get_model(cfg(True), dev)
+    student.load_state_dict(teacher.state_dict(), strict=False)
+    module_util.freeze_module_params(teacher)
+    for path in cfg(True)["frozen_modules"]:
+        module_util.freeze_module_params(module_util.get_module(student, path))
+    teacher.eval()
+    student.train()
+    teacher.distill_backbone_only = student.distill_backbone_only = True
+    g = torch.Generator().manual_seed(4000 + rank)
+    images = [torch.rand(3, IMG_H, IMG_W, generator=g).to(dev) for _ in range(batch)]
+    targets = [{"boxes": torch.tensor([[10., 10., 100., 100.]], device=dev), "labels": torch.tensor([1], device=dev)}
+               for _ in range(batch)]
+    all_sizes = tuple(teacher.transform.min_size)
+    out = {"workload": "Keypoint R-CNN ResNet-50-FPN b3ch GHND distillation, %d synthetic 3x800x1333 images per GPU, "
+                       "per-image fixed_sizes from %s, public API loop, images resident on the device" % (batch, list(all_sizes)),
+           "per_gpu_batch": batch, "n_gpus": world}
+    for mode, sizes in (("all_800", (800,)), ("random_scale_seed0", all_sizes)):
+        teacher.transform.min_size = sizes
+        box = DistillationBox(teacher, student, criterion_config())
+        flat = box.flatten_parameters()
+        opt = FusedAdam([p for p in student.parameters() if p.requires_grad], lr=1e-3, grad_scale=1.0 / world, flat=flat)
+        random.seed(0)
+
+        def step():
+            loss = box(images, targets)
+            opt.zero_grad()
+            loss.backward()
+            parallel.allreduce_flat_grad(flat)
+            opt.step()
+        # warm-up: visit (build + capture) every padded shape the seeded sequence will need
+        state = random.getstate()
+        for _ in range(warmup + steps):
+            step()
+        random.setstate(state)
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            step()
+        b.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms = float(ms.item())
+        out[mode] = {"value": batch * world * steps / (ms * 1e-3), "unit": "images/s", "ms_per_step": ms / steps,
+                     "steps": steps, "padded_shapes": sorted("%dx%d" % (k[1], k[2]) for k in box._plans)}
+        del box, opt
+        torch.cuda.empty_cache()
+    teacher.transform.min_size = all_sizes
+    return out
+
+
+def stock_torch_cuda(dev):
+    """Informational: the oracle port of the same GHND step (stock torch ops -> cuDNN/ATen, autograd,
+    per-tensor Adam math) on the same B200, fp32 and TF32, 4 images per step."""
+    import torch
+    out = {}
+    for name, tf32 in (("fp32", False), ("tf32", True)):
+        step = cpu_step_fn(PER_GPU_BATCH, device=str(dev), tf32=tf32)
+        step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n = 3
+        e0.record()
+        for _ in range(n):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        out[name] = {"value": PER_GPU_BATCH * n / (e0.elapsed_time(e1) * 1e-3), "unit": "images/s"}
+        del step
+        torch.cuda.empty_cache()
+    torch.backends.cudnn.allow_tf32 = True
+    out["what"] = ("oracle/ghnd_oracle.py distill_step + adam_step with every tensor on cuda: stock PyTorch %s "
+                   "(cuDNN/ATen kernels, autograd), %d images of 3x800x1333 per step, 1 warm-up + 3 timed steps; "
+                   "not this repo's kernels" % (torch.__version__, PER_GPU_BATCH))
+    return out
 
 
 def run_cuda(args):
@@ -300,7 +486,9 @@ def run_cuda(args):
     loss = box(dev_images, targets)
     opt.attach(box.flat)
     plan = list(box._plans.values())[0]
+    plan_shared, plan_side = bool(plan.shared), plan.side is not None
     torch.cuda.synchronize()
+    from hnd_ghnd_object_detectors_b200 import parallel
 
     dbg = {"n": 0}
 
@@ -311,8 +499,7 @@ def run_cuda(args):
                 torch.cuda.synchronize()
                 print("step %d loss %s" % (dbg["n"], plan.loss_out.tolist()), file=sys.stderr, flush=True)
         plan.step()  # images already packed in HBM; graph replay of fwd + loss + bwd
-        if world > 1:
-            dist.all_reduce(box.flat.grad)
+        parallel.allreduce_flat_grad(box.flat)
         opt.step()
 
     # end-to-end: the loop a user writes with the package's public API (mimic_runner.distill_model):
@@ -333,10 +520,9 @@ def run_cuda(args):
     def e2e_step():
         imgs, _ = next(e2e_state["iter"])
         l = box(imgs, targets)
-        opt.zero_grad(set_to_none=True)
-        l.backward()
-        if world > 1:
-            dist.all_reduce(box.flat.grad)
+        opt.zero_grad()
+        l.backward()                            # p.grad become views of the flat gradient buffer
+        parallel.allreduce_flat_grad(box.flat)  # one NCCL all-reduce (N > 1)
         opt.step()
         v = e2e_state["reader"].push(l)  # device -> host read of a step's loss, one per step
         if v is not None:
@@ -374,9 +560,13 @@ def run_cuda(args):
     value = images_per_step * args.steps / (ms * 1e-3)
     e2e_value = images_per_step * e2e_steps / (ms_e2e * 1e-3)
 
-    roof = cpu = hbm_kernels = encode = None
+    roof = cpu = hbm_kernels = encode = config1 = stock = None
     if rank == 0:
         peaks = measured_peaks()
+        hbm = peaks["hbm_gbs"]
+
+        def entry(gbs):
+            return {"achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm}
         # per-kernel timing pass: single stream (the side-stream branches would overlap the spans)
         side, plan.side = plan.side, None
         try:
@@ -389,23 +579,26 @@ def run_cuda(args):
         flops = conv_flops_per_step(plan)
         achieved = flops / conv_s / 1e12
         ncu = ncu_traffic()
+        traffic = ncu.get("conv_tc_dram_bytes_per_step")
+        note = ncu.get("note")
+        if traffic is not None and ncu.get("launches") not in (None, n_conv):
+            note = "STALE (%s launches captured, this build runs %d): %s" % (ncu.get("launches"), n_conv, note)
         roof = {"bound": "tensor",
                 "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv fwd/dgrad + stem, %d launches/step; "
                           "achieved = algorithmic FLOPs of all launches / summed CUDA-event time)" % n_conv,
                 "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["bf16_tflops_sustained"],
-                "traffic": ncu.get("conv_tc_dram_bytes_per_step"),
-                "traffic_note": ncu.get("note"),
+                "traffic": traffic, "traffic_note": note, "traffic_file": ncu.get("file"),
                 "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
                 "conv_share_of_step": conv_s / sum(t for t, _ in ep.values()),
-                "flops_per_step": flops}
+                "flops_per_step": flops,
+                "whole_step_tflops": value / world * 701.8e9 / 1e12,
+                "whole_step_frac": value / world * 701.8e9 / 1e12 / peaks["bf16_tflops_sustained"]}
         # memory-bound kernels of the path against the measured copy bandwidth
         sse_bytes = 6.0 * sum(t.numel() for t in plan.feat_s.values())
         hbm_kernels = {}
         if "ghnd_sse_fwd_bwd" in ep:
-            gbs = sse_bytes / ep["ghnd_sse_fwd_bwd"][0] / 1e9
-            hbm_kernels["sse_kernel (4-level loss fwd+bwd, 6 B/elem)"] = {
-                "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"]}
+            hbm_kernels["sse_kernel (4-level loss fwd+bwd, 6 B/elem)"] = entry(sse_bytes / ep["ghnd_sse_fwd_bwd"][0] / 1e9)
         # the other streaming kernels of the step: algorithmic bytes from the plan's tensors
         l1 = plan.s_l1
         units = [l1.e0, l1.e1, l1.e2, l1.d4, l1.d7, l1.d9]
@@ -413,43 +606,65 @@ def run_cuda(args):
         raw3 = float(l1.raw3.numel())
         pool_elems = float(plan.s_stem.out.numel())
         conv_elems = 4.0 * pool_elems  # one model's 64-channel conv1 output (2x2 the pooled size)
+        nz = float(l1.z.numel())
+        wide_e2, wide_r3 = float(l1.e2.out.numel()), raw3
         streaming = {
             "bn_finalize_apply (x -> y f16 [+ bf16 copy where a tensor-core dW reads it], 4-6 B/elem)":
                 ("ghnd_bn_finalize_apply",
                  sum(u.raw.numel() * (6.0 if u.out_g is not None else 4.0) for u in units) + 6.0 * raw3),
-            "bn_bwd_reduce (g, x -> sums, 4 B/elem)": ("ghnd_bn_bwd_reduce", 4.0 * (raw_elems + raw3)),
-            "bn_bwd_apply (g, x -> dx, 6 B/elem)": ("ghnd_bn_bwd_apply", 6.0 * (raw_elems + raw3)),
+            "bn_bwd_reduce (g, x -> sums, 4 B/elem)": ("ghnd_bn_bwd_reduce", 4.0 * (raw_elems + raw3) + 8.0 * nz),
+            "bn_bwd_apply (g, x -> dx, 6 B/elem)": ("ghnd_bn_bwd_apply", 6.0 * (raw_elems + raw3) + 12.0 * nz),
             "maxpool 3x3 s2 fwd, teacher + student (2 B in, 2 B out, +1 B argmax)":
                 ("ghnd_maxpool3x3s2_strided", 4.0 * conv_elems + 5.0 * pool_elems),
             "maxpool bwd + ReLU mask (x, dx 2 B/elem; dy + argmax 3 B/pooled elem)":
                 ("ghnd_maxpool3x3s2_bwd_strided", 4.0 * conv_elems + 3.0 * pool_elems),
+            # the bottleneck side (north_star (b)): wide 64-channel 16-bit tensor <-> planar fp32 bch tensor
+            "narrow_out fwd (enc7: 64 -> bch k2 p1; 2 B/elem wide in + 4 B/elem z out)":
+                ("ghnd_conv_narrow_out", 2.0 * wide_e2 + 4.0 * nz),
+            "narrow_in (dec2 fwd bch -> 64 with BN+ReLU prologue, and enc7 dgrad; 4 B/elem planar in + 2 B/elem wide out, 2 launches)":
+                ("ghnd_conv_narrow_in", 4.0 * nz + 2.0 * wide_r3 + 4.0 * nz + 2.0 * wide_e2),
+            "narrow_out dgrad (dec2: 64 -> bch; 2 B/elem wide in + 4 B/elem out)":
+                ("ghnd_conv_narrow_out_dgrad", 2.0 * wide_r3 + 4.0 * nz),
+            "wgrad_narrow (dec2 + enc7 dW; wide 2 B/elem + planar 4 B/elem, 2 launches)":
+                ("ghnd_wgrad_narrow", 2.0 * wide_r3 + 4.0 * nz + 2.0 * wide_e2 + 4.0 * nz),
         }
         for label, (name, nbytes) in streaming.items():
             if name in ep and ep[name][0] > 0:
-                gbs = nbytes / ep[name][0] / 1e9
-                hbm_kernels[label] = {"achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                                      "frac": gbs / peaks["hbm_gbs"]}
+                hbm_kernels[label] = entry(nbytes / ep[name][0] / 1e9)
         breakdown = {k: round(v[0] * 1e3, 4) for k, v in sorted(ep.items(), key=lambda kv: -kv[1][0])}
         roof["entry_point_ms_per_step"] = breakdown
         if world == 1 and not args.no_encode:
-            sweep, qgbs = encode_sweep(dev, [1, 2, 4, 8, 16, 32, 64] if args.encode_sweep else [8, 64])
+            sweep, kern = encode_sweep(dev, [8, 64] if args.short_encode else [1, 2, 4, 8, 16, 32, 64])
             encode = {"metric": "head_quant_encode_images_per_sec", "unit": "images/s",
-                      "workload": "Keypoint R-CNN b3ch RcnnHead (stem + layer1 encoder + 8-bit quantize), "
-                                  "synthetic 3x800x1333, inputs resident in HBM", "by_batch": sweep}
-            if qgbs is not None:
-                hbm_kernels["quant_apply (8-bit quantizer, one pass, min/max fused into the encoder's last conv; 5 B/elem, batch %s)" % ("64")] = {
-                    "achieved": qgbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": qgbs / peaks["hbm_gbs"]}
+                      "workload": "BASELINE config 5: Keypoint R-CNN b3ch RcnnHead (stem + layer1 encoder + 8-bit "
+                                  "quantize), synthetic 3x800x1333, inputs resident in HBM, one scale/zero-point "
+                                  "per call", "by_batch": sweep}
+            for label, bps in kern.items():
+                hbm_kernels[label] = entry(bps / 1e9)
+            # config 1 on the CUDA path: Faster R-CNN head + quantize at batch 2
+            f_sweep, _ = encode_sweep(dev, [2], model_name="faster_rcnn")
+            config1 = {"workload": "BASELINE config 1: Faster R-CNN b3ch head forward + 8-bit quantize, batch 2, "
+                                   "synthetic 3x800x1333", "cuda": {"value": f_sweep["2"], "unit": "images/s"}}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        step = cpu_step_fn(1)
-        step()
-        t0 = time.perf_counter()
         n = 2
-        for _ in range(n):
-            step()
-        dt = (time.perf_counter() - t0) / n
-        cpu = {"value": 1.0 / dt, "unit": "images/s", "cores": os.cpu_count() or 1, "kind": "port",
-               "sample": "oracle port (torch CPU fp32) of the same GHND step, 1 image of 3x800x1333 per "
-                         "step, 1 warm-up + %d timed steps" % n}
+        dt = time_host(cpu_step_fn(CPU_SAMPLE_BATCH), 1, n)
+        cores = os.cpu_count() or 1
+        cpu = {"value": CPU_SAMPLE_BATCH / dt, "unit": "images/s", "cores": cores, "kind": "port",
+               "sample": "oracle port (torch CPU fp32, autograd + Adam) of the same GHND step on %d images of "
+                         "3x800x1333 per step, %d torch threads, 1 warm-up + %d timed steps" % (CPU_SAMPLE_BATCH, cores, n)}
+        dt1 = time_host(cpu_encode_fn(2), 1, 3)
+        if config1 is None:
+            config1 = {"workload": "BASELINE config 1"}
+        config1["cpu"] = {"value": 2.0 / dt1, "unit": "images/s", "cores": cores, "kind": "port",
+                          "sample": "oracle port (torch CPU fp32 + numpy quantizer) of RcnnHead on 2 images of "
+                                    "3x800x1333, 1 warm-up + 3 timed calls"}
+        if not args.no_stock_torch:
+            stock = stock_torch_cuda(dev)
+    config4 = None
+    if (world in (1, 8) and not args.no_config4) or args.config4:
+        del box, plan
+        torch.cuda.empty_cache()
+        config4 = config4_bench(dev, world)
     if rank == 0:
         h2d = sum(h.numel() * 4 for h in host_images)
         line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
@@ -460,15 +675,19 @@ def run_cuda(args):
                 "config": {"workload": WORKLOAD, "global_batch": images_per_step, "per_gpu_batch": PER_GPU_BATCH,
                            "parallelism": "dp%d" % world,
                            "l2": "per-step working set (several GB of activations) exceeds the 126 MB L2",
-                           "shared_frozen_trunk": bool(plan.shared),
-                           "cuda_graph": True, "side_stream": plan.side is not None},
+                           "shared_frozen_trunk": plan_shared,
+                           "cuda_graph": True, "side_stream": plan_side,
+                           "device_resident_value": "`value` replays the step on images already packed in HBM "
+                                                    "(the stem-pack kernel of the 4 inputs is not in it); `e2e` "
+                                                    "includes the H2D copy and the packing"},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": 4, "steps": e2e_steps,
-                        "api": "DevicePrefetcher(pinned host images) -> DistillationBox -> backward -> FusedAdam -> "
-                               "AsyncScalarReader(loss), i.e. mimic_runner.distill_model's loop"},
+                        "api": "DevicePrefetcher(pinned host images) -> DistillationBox -> backward -> flat all-reduce "
+                               "-> FusedAdam -> AsyncScalarReader(loss), i.e. mimic_runner.distill_model's loop"},
                 "gpu_launches": launches, "roofline": roof, "roofline_hbm_kernels": hbm_kernels,
-                "encode": encode, "cpu_baseline": cpu,
+                "encode": encode, "config1": config1, "config4": config4, "cpu_baseline": cpu,
+                "stock_torch_cuda": stock,
                 "loss": float(loss.item())}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -483,7 +702,11 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-encode", action="store_true", help="skip the split-computing head line")
-    ap.add_argument("--encode-sweep", action="store_true", help="encode path at batch 1..64 (config 5)")
+    ap.add_argument("--short-encode", action="store_true", help="encode path at batch 8 and 64 only")
+    ap.add_argument("--encode-sweep", action="store_true", help="(default now) encode path at batch 1..64")
+    ap.add_argument("--no-config4", action="store_true", help="skip the Keypoint batch-8 line (config 4)")
+    ap.add_argument("--config4", action="store_true", help="run config 4 at any N (default: N=1 and N=8)")
+    ap.add_argument("--no-stock-torch", action="store_true", help="skip the stock-PyTorch-on-cuda leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -103,6 +103,10 @@ SIGNATURES = {
     "ghnd_bn_finalize_apply": (_I, [_P, _I, _P, _I, _P, _I, _L, _I, _I, _P, _L, _P, _P, _F, _F, _P, _P, _P, _P,
                                     _P, _P]),
     "ghnd_convert16": (_I, [_P, _I, _P, _I, _L, _P]),
+    "ghnd_upsample_add": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "ghnd_adaptive_avgpool_nhwc16": (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _I, _P]),
+    "ghnd_small_conv_f32": (_I, [_P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "ghnd_avgpool_linear": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P, _P]),
     "ghnd_bn_bwd_reduce": (_I, [_P, _I, _P, _I, _I, _I, _L, _I, _P, _P, _I, _P, _P]),
     "ghnd_bn_bwd_apply": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _L, _I, _P, _P, _P, _I, _P, _P, _P, _P]),
     "ghnd_bn_bwd_apply_fused_sums": (_I, [_P, _I, _P, _I, _P, _I, _I, _L, _I, _P, _P, _P, _I, _P, _P, _P, _P]),

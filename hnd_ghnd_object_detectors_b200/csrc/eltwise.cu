@@ -280,6 +280,41 @@ __global__ void __launch_bounds__(256)
 // ------------------------------------------------------------------------------------------------
 // BatchNorm (training): statistics, finalize, apply, backward
 // ------------------------------------------------------------------------------------------------
+// Block-level fold of per-thread channel partials (a[8] = sums, b[8] = second sums of the 8 channels of
+// group cg = tid % C8) into `sums`, for C8 a power of two <= 32 and 256 threads: lanes of a warp that
+// share a group are combined by xor-shuffles, every warp writes its totals into its OWN row of sh
+// (plain stores), the block adds the 8 rows and issues ONE fp64 atomic per channel.  The previous
+// version did 16 shared-memory float atomicAdds per thread: those are compare-and-swap spin loops in
+// SASS (ATOMS.CAST.SPIN) with 8-32 threads per address -- the fixed ~15 us tail of the reduce kernels.
+// sh: [8 warps][2*C] floats.  Requires C8 in {1, 2, 4, 8, 16, 32} (C <= 256).
+__device__ __forceinline__ void block_channel_fold(float (&a)[8], float (&b)[8], int C8, float* sh,
+                                                   double* __restrict__ sums) {
+  const int C = C8 * 8;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int o = C8; o < 32; o <<= 1) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      a[j] += __shfl_xor_sync(0xffffffffu, a[j], o);
+      b[j] += __shfl_xor_sync(0xffffffffu, b[j], o);
+    }
+  }
+  float* row = sh + (size_t)warp * 2 * C;
+  if (lane < C8) {
+    const int cg = threadIdx.x % C8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      row[cg * 8 + j] = a[j];
+      row[C + cg * 8 + j] = b[j];
+    }
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < 2 * C; k += 256) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sh[(size_t)w * 2 * C + k];
+    atomicAdd(&sums[k], (double)t);
+  }
+}
 // NHWC 16-bit: thread owns one 8-channel group and strides over pixels
 template <bool kBwd>
 __global__ void __launch_bounds__(256)
@@ -287,13 +322,16 @@ __global__ void __launch_bounds__(256)
                           int dy_fmt, int64_t npix, int C, const float* __restrict__ scale_shift,
                           const float* __restrict__ mean_invstd, int relu,
                           double* __restrict__ sums) {
-  extern __shared__ float sh[];  // [2*C]
+  extern __shared__ float sh[];  // [2*C], or [8 warps][2*C] on the fold path
   const int C8 = C >> 3;
   const int lanes = blockDim.x / C8;  // pixel lanes per block
   const int cg = threadIdx.x % C8;
   const int lane = threadIdx.x / C8;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
-  __syncthreads();
+  const bool fold = C8 <= 32 && (C8 & (C8 - 1)) == 0 && blockDim.x == 256;  // host sizes sh to match
+  if (!fold) {
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
+    __syncthreads();
+  }
   float a[8], b[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) a[j] = b[j] = 0.f;
@@ -338,11 +376,17 @@ __global__ void __launch_bounds__(256)
         }
       }
     }
+    if (!fold) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      atomicAdd(&sh[cg * 8 + j], a[j]);
-      atomicAdd(&sh[C + cg * 8 + j], b[j]);
+      for (int j = 0; j < 8; ++j) {
+        atomicAdd(&sh[cg * 8 + j], a[j]);
+        atomicAdd(&sh[C + cg * 8 + j], b[j]);
+      }
     }
+  }
+  if (fold) {  // all 256 threads are pixel lanes here (256 % C8 == 0)
+    block_channel_fold(a, b, C8, sh, sums);
+    return;
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&sums[i], (double)sh[i]);
@@ -710,6 +754,7 @@ __global__ void __launch_bounds__(256)
   for (; i < nvec; i += stride) one(ld_stream(x + i), ld_stream(dy + i), i);
 }
 
+
 // backward reduction: sums[c] += sum g', sums[C+c] += sum g'*xhat
 template <int XF, int GF, bool RELU>
 __global__ void __launch_bounds__(256)
@@ -717,11 +762,9 @@ __global__ void __launch_bounds__(256)
                               int C8, const float* __restrict__ scale_shift,
                               const float* __restrict__ mean_invstd, double* __restrict__ sums) {
   constexpr int U = 4;
-  extern __shared__ float sh[];  // [2*C]
+  extern __shared__ float sh[];  // [8 warps][2*C]
   const int C = C8 * 8;
   const int cg = threadIdx.x % C8;
-  for (int i = threadIdx.x; i < 2 * C; i += 256) sh[i] = 0.f;
-  __syncthreads();
   float sc[8], sf[8], mu[8], is[8], a[8], b[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -761,15 +804,13 @@ __global__ void __launch_bounds__(256)
     for (int k = 0; k < U; ++k) one(xv[k], dv[k]);
   }
   for (; i < nvec; i += stride) one(ld_stream(x + i), ld_stream(dy + i));
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    atomicAdd(&sh[cg * 8 + j], a[j]);
-    atomicAdd(&sh[C + cg * 8 + j], b[j]);
-  }
-  __syncthreads();
-  for (int k = threadIdx.x; k < 2 * C; k += 256) atomicAdd(&sums[k], (double)sh[k]);
+  block_channel_fold(a, b, C8, sh, sums);
 }
 
+static size_t bn_reduce_smem(int C) {  // bn_reduce_nhwc_kernel: [8 warps][2*C] on its fold path
+  const int c8 = C / 8;
+  return (size_t)((c8 <= 32 && (c8 & (c8 - 1)) == 0) ? 16 : 2) * C * sizeof(float);
+}
 static bool fast_c8(int C) { return C >= 8 && C % 8 == 0 && C / 8 <= 256 && 256 % (C / 8) == 0; }
 
 template <int XF, int YF, int Y2F>
@@ -810,6 +851,38 @@ __global__ void __launch_bounds__(256)
     for (int e = 0; e < 4; ++e) {
       const float2 f = unpack2(u[e], x_fmt);
       o[e] = pack2(f.x, f.y, y_fmt);
+    }
+    y[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// FPN top-down step: y = lateral + nearest-upsample(coarse), NHWC 16-bit, 8 channels per
+// thread.  torchvision FeaturePyramidNetwork: F.interpolate(last_inner, size=lateral.shape[-2:],
+// mode="nearest") -> source index floor(dst * in / out) (= dst/2 for the exact 2x of /32-padded maps).
+// ------------------------------------------------------------------------------------------------
+template <int FMT>
+__global__ void __launch_bounds__(256)
+    upsample_add_kernel(const uint4* __restrict__ fine, const uint4* __restrict__ coarse,
+                        uint4* __restrict__ y, int H, int W, int Hc, int Wc, int C8, int64_t nvec) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t t = i;
+    const int cg = (int)(t % C8);
+    t /= C8;
+    const int w = (int)(t % W);
+    t /= W;
+    const int h = (int)(t % H);
+    const int n = (int)(t / H);
+    const int hc = (int)(((int64_t)h * Hc) / H), wc = (int)(((int64_t)w * Wc) / W);
+    const uint4 a = ld_stream(fine + i);
+    const uint4 b = __ldg(coarse + (((int64_t)n * Hc + hc) * Wc + wc) * C8 + cg);
+    const uint32_t au[4] = {a.x, a.y, a.z, a.w}, bu[4] = {b.x, b.y, b.z, b.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = unpack2_t<FMT>(au[e]), g = unpack2_t<FMT>(bu[e]);
+      o[e] = pack2_t<FMT>(f.x + g.x, f.y + g.y);
     }
     y[i] = make_uint4(o[0], o[1], o[2], o[3]);
   }
@@ -1047,7 +1120,7 @@ int ghnd_bn_stats(const void* x, int fmt, int planar, int N, int64_t hw, int C, 
     GHND_CHECK_ARG(fmt16(fmt), "bn_stats: bad format");
     const int64_t npix = (int64_t)N * hw;
     const int lanes = 256 / (C / 8);
-    bn_reduce_nhwc_kernel<false><<<grid_for(npix, lanes * 8, 4), 256, 2 * C * sizeof(float), st>>>(
+    bn_reduce_nhwc_kernel<false><<<grid_for(npix, lanes * 8, 4), 256, bn_reduce_smem(C), st>>>(
         (const uint4*)x, fmt, nullptr, 0, npix, C, nullptr, nullptr, 0, sums);
   }
   GHND_LAUNCH_CHECK("bn_reduce_kernel");
@@ -1130,6 +1203,23 @@ int ghnd_bn_finalize_apply(const void* x, int x_fmt, void* y, int y_fmt, void* y
   return GHND_OK;
 }
 
+int ghnd_upsample_add(const void* fine, const void* coarse, void* y, int fmt, int N, int H, int W, int Hc,
+                      int Wc, int C, void* stream) {
+  GHND_CHECK_ARG(fine && coarse && y && fmt16(fmt), "upsample_add: bad argument");
+  GHND_CHECK_ARG(N > 0 && H > 0 && W > 0 && Hc > 0 && Wc > 0 && Hc <= H && Wc <= W && C > 0 && C % 8 == 0,
+                 "upsample_add: bad geometry N=%d %dx%d <- %dx%d C=%d", N, H, W, Hc, Wc, C);
+  const int64_t nvec = (int64_t)N * H * W * (C / 8);
+  const int grid = grid_for(nvec, 256, 16);
+  if (fmt == GHND_F16)
+    upsample_add_kernel<GHND_F16><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        (const uint4*)fine, (const uint4*)coarse, (uint4*)y, H, W, Hc, Wc, C / 8, nvec);
+  else
+    upsample_add_kernel<GHND_BF16><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        (const uint4*)fine, (const uint4*)coarse, (uint4*)y, H, W, Hc, Wc, C / 8, nvec);
+  GHND_LAUNCH_CHECK("upsample_add_kernel");
+  return GHND_OK;
+}
+
 int ghnd_convert16(const void* x, int x_fmt, void* y, int y_fmt, int64_t n, void* stream) {
   GHND_CHECK_ARG(x && y && fmt16(x_fmt) && fmt16(y_fmt) && n > 0 && n % 8 == 0,
                  "convert16: bad argument (n must be a positive multiple of 8)");
@@ -1155,19 +1245,20 @@ int ghnd_bn_bwd_reduce(const void* dy, int dy_fmt, const void* x, int x_fmt, int
     GHND_CHECK_ARG(fmt16(dy_fmt) && fmt16(x_fmt), "bn_bwd_reduce: bad format");
     const int64_t npix = (int64_t)N * hw;
     const int lanes = 256 / (C / 8);
-    if (x_fmt == GHND_F16 && dy_fmt == GHND_BF16) {  // the engine's combination: fast path
+    const int c8 = C / 8;
+    if (x_fmt == GHND_F16 && dy_fmt == GHND_BF16 && c8 <= 32 && (c8 & (c8 - 1)) == 0) {  // the engine's combination: fast path
       const int64_t nvec = npix * (C / 8);
       // 3 CTAs/SM x 8 warps x 8 x 16-byte loads in flight; fewer CTAs also means fewer same-address
       // fp64 atomics in the tail (2*C per CTA)
       const int grid = grid_for(nvec, 256 * 8, tune_int("GHND_BNRED_PER_SM", 3));
       if (relu)
-        bn_bwd_reduce_fast_kernel<GHND_F16, GHND_BF16, true><<<grid, 256, 2 * C * sizeof(float), st>>>(
+        bn_bwd_reduce_fast_kernel<GHND_F16, GHND_BF16, true><<<grid, 256, 16 * C * sizeof(float), st>>>(
             (const uint4*)x, (const uint4*)dy, nvec, C / 8, scale_shift, mean_invstd, sums);
       else
-        bn_bwd_reduce_fast_kernel<GHND_F16, GHND_BF16, false><<<grid, 256, 2 * C * sizeof(float), st>>>(
+        bn_bwd_reduce_fast_kernel<GHND_F16, GHND_BF16, false><<<grid, 256, 16 * C * sizeof(float), st>>>(
             (const uint4*)x, (const uint4*)dy, nvec, C / 8, scale_shift, mean_invstd, sums);
     } else {
-      bn_reduce_nhwc_kernel<true><<<grid_for(npix, lanes * 8, 4), 256, 2 * C * sizeof(float), st>>>(
+      bn_reduce_nhwc_kernel<true><<<grid_for(npix, lanes * 8, 4), 256, bn_reduce_smem(C), st>>>(
           (const uint4*)x, x_fmt, (const uint4*)dy, dy_fmt, npix, C, scale_shift, mean_invstd, relu,
           sums);
     }

@@ -887,6 +887,24 @@ class EncodePlan(object):
             self.forward()
         return self.q, self.qparams
 
+    def run_filtered(self, images, ext_encoder):
+        """RcnnHead with a neural filter (split_rcnn.py:30-35): stem -> filter -> [stop | encoder +
+        quantizer].  The decision is a host-side branch (the reference returns None from Python), so
+        this path runs eagerly: one D2H read of the 2 filter probabilities."""
+        self.load_images(images)
+        self.stem.refresh_weights()
+        self.stem.forward()
+        skip, ext_z = ext_encoder.filter_decision(self.stem.out)
+        if skip:
+            return None, ext_z
+        if self.num_bits == 16:
+            self.l1.forward_encoder()
+            return (self.z, None), ext_z
+        self.l1.forward_encoder(minmax=self.minmax)
+        ops.quantize_u8_minmax(self.z, self.minmax, self.l1.z_pairs, self.num_bits, self.scale_mode,
+                               q=self.q, qparams=self.qparams)
+        return (self.q, self.qparams), ext_z
+
 
 class BodyPlan(object):
     """Forward-only backbone body (stem -> layer1..4) for a fixed shape: the teacher's frozen
@@ -905,6 +923,7 @@ class BodyPlan(object):
         x, H, W = self.stem.out, self.stem.Ho, self.stem.Wo
         self.student = isinstance(body.layer1, BottleneckBase4Ext)
         self.feats = {}
+        self.skipped, self.ext_z = False, None
         if self.student:
             self.l1_train = bool(body.layer1.training)
             self.l1 = StudentLayer1Runner(body.layer1, x, N, H, W, act_dtype, torch.bfloat16, self.l1_train)
@@ -926,8 +945,14 @@ class BodyPlan(object):
             ops.stem_pack_image(im, self.packed, i, self.Hp, self.Wp, self.mean, self.std)
         self.stem.refresh_weights()
         self.stem.forward()
+        self.skipped, self.ext_z = False, None
         if self.student:
             l1 = self.body.layer1
+            if getattr(l1, "uses_ext_encoder", False) and not l1.training:
+                # neural filter on the stem output (base.py:13-16): may stop inference here
+                self.skipped, self.ext_z = l1.encoder.filter_decision(self.stem.out)
+                if self.skipped:
+                    return self.feats
             z = self.l1.forward_encoder()
             if (not l1.training) and l1.bottleneck_transformer is not None and l1.use_bottleneck_transformer:
                 from .resnet_layer import apply_bottleneck_transformer
@@ -938,3 +963,51 @@ class BodyPlan(object):
         for r in self.layers:
             r.forward()
         return self.feats
+
+
+class FpnPlan(object):
+    """BackboneWithFPN.fpn forward on the conv kernels: torchvision
+    FeaturePyramidNetwork.forward reached through src/models/org/rcnn.py:399-414 (called at :108 and
+    :127) -- 1x1 lateral convs (+bias), top-down nearest-upsample + add, 3x3 output convs (+bias), all
+    on the tcgen05 implicit-GEMM ConvPlan; the upsample-add is one streaming kernel per level.
+    `feats`: the body's NHWC 16-bit outputs, finest first (layer1..layer4).  Outputs stay NHWC 16-bit
+    in self.out (finest first); extra blocks (LastLevelMaxPool = a stride-2 subsample) are left to the
+    caller."""
+
+    def __init__(self, fpn, feats, act_dtype=torch.float16):
+        from torch import nn
+        _lib.check(_lib.load().ghnd_device_check(), "ghnd_device_check")
+
+        def conv_of(blk):  # torchvision >= 0.13 wraps each conv in Conv2dNormActivation
+            return blk[0] if isinstance(blk, nn.Sequential) else blk
+        assert len(feats) == len(fpn.inner_blocks) == len(fpn.layer_blocks)
+        self.feats = list(feats)
+        self.lat, self.out, self.inner, self.outer = [], [], [], []
+        self._keep = []
+        for i, x in enumerate(self.feats):
+            n, h, w, c = x.shape
+            ci, co = conv_of(fpn.inner_blocks[i]), conv_of(fpn.layer_blocks[i])
+            K = ci.weight.shape[0]
+            if ci.weight.shape[2:] != (1, 1) or co.weight.shape[2:] != (3, 3) or co.padding[0] != 1:
+                raise ValueError("FpnPlan expects 1x1 lateral and 3x3/p1 output convolutions")
+            wi = ops.pack_weight(ci.weight, None, False, act_dtype)
+            wo = ops.pack_weight(co.weight, None, False, act_dtype)
+            bi = ci.bias.detach().float().contiguous() if ci.bias is not None else None
+            bo = co.bias.detach().float().contiguous() if co.bias is not None else None
+            lat = _empty((n, h, w, K), act_dtype, x.device)
+            po = _empty((n, h, w, K), act_dtype, x.device)
+            self.inner.append(ops.ConvPlan(CONV_FWD, n, h, w, c, K, 1, 1, 1, 0, x, wi, lat, bias=bi))
+            self.outer.append(ops.ConvPlan(CONV_FWD, n, h, w, K, K, 3, 3, 1, 1, lat, wo, po, bias=bo))
+            self.lat.append(lat)
+            self.out.append(po)
+            self._keep += [wi, wo, bi, bo]
+        self.flops = sum(p.flops for p in self.inner + self.outer)
+
+    def run(self):
+        top = len(self.feats) - 1
+        for i in range(top, -1, -1):
+            self.inner[i].run()
+            if i < top:  # last_inner = inner_lateral + interpolate(last_inner, nearest)
+                ops.upsample_add(self.lat[i], self.lat[i + 1], out=self.lat[i])
+            self.outer[i].run()
+        return self.out

@@ -55,8 +55,10 @@ def get_model(model_config, device, strict=True, bottleneck_transformer=None):
             bottleneck_transformer = get_bottleneck_transformer(model_config['bottleneck_transformer'])
         model = rcnn.get_model(model_name, backbone_config=backbone_config, strict=strict,
                                bottleneck_transformer=bottleneck_transformer, **model_params_config)
-        if 'ext_config' in backbone_config:
-            raise NotImplementedError("ext_config (neural filter) is outside the B200 hot path")
+        if 'ext_config' in backbone_config:  # __init__.py:49-52: the filter has its own checkpoint
+            ext_config = backbone_config['ext_config']
+            load_ckpt(ext_config['ckpt'], model=model.get_ext_classifier())
+            strict = False
     else:
         raise ValueError('model_name `{}` is not expected'.format(model_name))
     load_ckpt(ckpt_file_path, model=model, strict=strict)

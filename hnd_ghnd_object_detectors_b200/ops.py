@@ -555,6 +555,56 @@ def convert16(x, y):
     return y
 
 
+def upsample_add(fine, coarse, out=None):
+    """out = fine + nearest_upsample(coarse), NHWC 16-bit (the FPN top-down step)."""
+    _need_cuda(fine, coarse)
+    n, h, w, c = fine.shape
+    _, hc, wc, _ = coarse.shape
+    if out is None:
+        out = torch.empty_like(fine)
+    call("ghnd_upsample_add", ptr(fine), ptr(coarse), ptr(out), fmt_of(fine.dtype), n, h, w, hc, wc, c, stream_ptr())
+    _count()
+    return out
+
+
+def adaptive_avgpool_nhwc16(x, oh, ow, out=None):
+    """NHWC 16-bit [N,H,W,C] -> NHWC fp32 [N,oh,ow,C] (nn.AdaptiveAvgPool2d)."""
+    _need_cuda(x)
+    n, h, w, c = x.shape
+    if out is None:
+        out = torch.empty((n, oh, ow, c), dtype=torch.float32, device=x.device)
+    call("ghnd_adaptive_avgpool_nhwc16", ptr(x), fmt_of(x.dtype), n, h, w, c, ptr(out), oh, ow, stream_ptr())
+    _count()
+    return out
+
+
+def small_conv_f32(x, w_rsck, scale, shift, relu, stride, out=None):
+    """NHWC fp32 conv without padding + per-channel scale/shift (+ReLU); w_rsck [R,S,C,K] fp32."""
+    _need_cuda(x, w_rsck)
+    n, h, w, c = x.shape
+    r, s, _, k = w_rsck.shape
+    ho, wo = (h - r) // stride + 1, (w - s) // stride + 1
+    if out is None:
+        out = torch.empty((n, ho, wo, k), dtype=torch.float32, device=x.device)
+    call("ghnd_small_conv_f32", ptr(x), ptr(w_rsck), ptr(scale), ptr(shift), int(bool(relu)), ptr(out), n, h, w, c, k,
+         r, s, stride, stream_ptr())
+    _count()
+    return out
+
+
+def avgpool_linear(x, oh, ow, lw, lb, softmax, out=None):
+    """NHWC fp32 [N,H,W,C] -> AdaptiveAvgPool2d(oh,ow) -> flatten (NCHW order) -> Linear -> [softmax]."""
+    _need_cuda(x, lw)
+    n, h, w, c = x.shape
+    n_out = lw.shape[0]
+    if out is None:
+        out = torch.empty((n, n_out), dtype=torch.float32, device=x.device)
+    call("ghnd_avgpool_linear", ptr(x), n, h, w, c, oh, ow, ptr(lw), ptr(lb), n_out, int(bool(softmax)), ptr(out),
+         stream_ptr())
+    _count()
+    return out
+
+
 def bn_bwd_reduce(dy, x, scale_shift, mean_invstd, relu, sums, planar=False):
     if planar:
         n, c, h, w = x.shape

@@ -78,28 +78,50 @@ class CustomRCNN(nn.Module):
             out.append(img)
         return out
 
-    def backbone_features(self, images, fixed_sizes=None, levels=("layer1", "layer2", "layer3", "layer4")):
-        """Forward-only body features (eval-mode BN) as NCHW fp32 tensors, keyed '0'..'3' like
-        IntermediateLayerGetter's return_layers (rcnn.py:405)."""
+    def _run_body(self, images, fixed_sizes=None):
+        """Transform + body (stem -> layer1..4) on the CUDA kernels -> (BodyPlan holding the NHWC
+        16-bit features, image sizes after resizing, padded batch shape)."""
         from .engine import BodyPlan
         imgs = self._scaled_images(images, fixed_sizes)
         hp = round_up(max(i.shape[1] for i in imgs), 32)
         wp = round_up(max(i.shape[2] for i in imgs), 32)
         # A BodyPlan bakes in layer1's train/eval mode and packs the frozen weights once: key it on the
-        # mode and on a version of the body's tensors so train()/eval()/load_state_dict() rebuild it.
+        # mode and on a version of the backbone's tensors so train()/eval()/load_state_dict() rebuild it.
         body = self.backbone.body
         l1_train = bool(getattr(body.layer1, "training", False))
-        version = sum(int(t._version) for t in body.state_dict(keep_vars=True).values())
+        version = sum(int(t._version) for t in self.backbone.state_dict(keep_vars=True).values())
         key = (len(imgs), hp, wp, l1_train, version)
         plan = self._feature_plans.get(key)
         if plan is None:
             plan = BodyPlan(body, len(imgs), hp, wp, act_dtype=self.act_dtype,
                             image_mean=self.transform.image_mean, image_std=self.transform.image_std)
             self._feature_plans = {key: plan}
-        feats = plan.run(imgs)
+        plan.run(imgs)
         image_sizes = [tuple(i.shape[-2:]) for i in imgs]
+        return plan, image_sizes, (len(imgs), 3, hp, wp)
+
+    def backbone_features(self, images, fixed_sizes=None, levels=("layer1", "layer2", "layer3", "layer4")):
+        """Forward-only body features (eval-mode BN) as NCHW fp32 tensors, keyed '0'..'3' like
+        IntermediateLayerGetter's return_layers (rcnn.py:405)."""
+        plan, image_sizes, tshape = self._run_body(images, fixed_sizes)
+        feats = plan.feats
         return OrderedDict((str(i), ops.to_nchw_f32(feats[l])) for i, l in enumerate(levels) if l in feats), \
-            image_sizes, (len(imgs), 3, hp, wp)
+            image_sizes, tshape
+
+    def fpn_features(self, plan):
+        """BackboneWithFPN.fpn on the body plan's NHWC features through engine.FpnPlan (tcgen05 convs);
+        returns the reference's OrderedDict {'0','1','2','3','pool'} of NCHW fp32 maps for the
+        torchvision RPN / RoI heads."""
+        from .engine import FpnPlan, LEVELS
+        fp = getattr(plan, "fpn_plan", None)
+        if fp is None:
+            fp = plan.fpn_plan = FpnPlan(self.backbone.fpn, [plan.feats[l] for l in LEVELS], act_dtype=self.act_dtype)
+        names = [str(i) for i in range(len(fp.out))]
+        results = [ops.to_nchw_f32(t) for t in fp.run()]
+        extra = self.backbone.fpn.extra_blocks
+        if extra is not None:  # LastLevelMaxPool: a stride-2 subsample of the coarsest map
+            results, names = extra(results, [None] * len(results), names)
+        return OrderedDict(zip(names, results))
 
     @staticmethod
     def _resize_targets(targets, original_sizes, new_sizes):
@@ -120,16 +142,31 @@ class CustomRCNN(nn.Module):
             out.append(t)
         return out
 
+    def train_ext(self):
+        raise _lib.GhndError("training the neural filter (ext_runner.py) is outside the B200 hot path")
+
+    def get_ext_classifier(self):
+        """rcnn.py:99-100."""
+        layer1 = self.backbone.body.layer1
+        return layer1.get_ext_classifier() if hasattr(layer1, "get_ext_classifier") else None
+
     def forward(self, images, targets=None, fixed_sizes=None):
         if self.training and targets is None:
             raise ValueError("In training mode, targets should be passed")
         if not images[0].is_cuda:
             raise _lib.GhndError("CustomRCNN runs its backbone on CUDA only (no CPU fallback)")
         original_image_sizes = [img.shape[-2:] for img in images]
-        body_feats, image_sizes, tshape = self.backbone_features(images, fixed_sizes)
+        plan, image_sizes, tshape = self._run_body(images, fixed_sizes)
+        if plan.skipped:  # rcnn.py:115-124: the neural filter found nothing of interest (eval, batch 1)
+            _, ch, height, width = tshape
+            pred_dict = {'boxes': torch.empty(0, 4), 'labels': torch.empty(0, dtype=torch.int64),
+                         'scores': torch.empty(0), 'masks': torch.zeros(100, ch, height, width),
+                         'keypoints': torch.empty(0, 17, 3), 'keypoints_scores': torch.empty(0, 17)}
+            return [pred_dict]
         if self.distill_backbone_only:
-            return body_feats  # rcnn.py:109-110 (the reference also runs a discarded FPN here)
-        features = self.backbone.fpn(body_feats)
+            # rcnn.py:109-110 (the reference also runs a discarded FPN here)
+            return OrderedDict((str(i), ops.to_nchw_f32(f)) for i, f in enumerate(plan.feats.values()))
+        features = self.fpn_features(plan)
         image_list = ImageList(torch.empty(tshape, device=images[0].device), image_sizes)
         if targets is not None and self.training:
             targets = self._resize_targets(targets, original_image_sizes, image_sizes)
@@ -222,8 +259,9 @@ def get_model(model_name, pretrained, num_classes=91, backbone_config=None, cust
         backbone_params_config['pretrained'] = False
     if custom_backbone is None:
         base_backbone = get_base_backbone(backbone_name, backbone_config, bottleneck_transformer)
-        if backbone_config.get('ext_config', None) is not None:
-            raise NotImplementedError("ext_config (neural filter) is outside the B200 hot path")
+        # ext_config (neural filter, rcnn.py:432-435): the reference swaps in ExtBackboneWithFPN; here the
+        # filter hangs on layer1.encoder.ext_classifier (same state_dict keys) and CustomRCNN.forward
+        # consults it on the CUDA path
         backbone = get_fpn_backbone(base_backbone, backbone_params_config['freeze_layers'])
     else:
         backbone = custom_backbone

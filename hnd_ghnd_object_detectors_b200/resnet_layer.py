@@ -33,18 +33,25 @@ def apply_bottleneck_transformer(layer1, z):
 
 
 class ExtEncoder(nn.Module):
-    """base.py:7-26.  The neural-filter classifier (ext_classifier) is out of scope."""
+    """base.py:7-26: the encoder stack plus the optional neural filter `ext_classifier`
+    (models/ext/classifier.py) that decides from the stem output whether an image is worth encoding:
+    in eval mode with batch 1, `ext_z[0][1] < threshold` stops inference before the encoder runs."""
 
     def __init__(self, encoder, ext_classifier=None, ext_config=None):
         super().__init__()
-        if ext_classifier is not None or ext_config is not None:
-            raise NotImplementedError("ext_config (neural filter, models/ext) is outside the B200 hot path")
         self.encoder = encoder
-        self.ext_classifier = None
-        self.threshold = None
+        self.ext_classifier = ext_classifier
+        self.threshold = ext_config['threshold'] if ext_config is not None else None
 
     def forward(self, x):
         raise _lib.GhndError("ExtEncoder is executed by its parent Bottleneck4LargeResNet")
+
+    def filter_decision(self, x_nhwc16):
+        """forward_with_ext's test (base.py:13-16) on the NHWC 16-bit stem output: returns (skip, ext_z);
+        skip is True when the filter says nothing of interest is in the (single) image."""
+        ext_z = self.ext_classifier.forward_nhwc16(x_nhwc16)
+        skip = (not self.training) and ext_z.shape[0] == 1 and bool(ext_z[0][1] < self.threshold)
+        return skip, ext_z
 
     def get_ext_classifier(self):
         return self.ext_classifier
@@ -83,7 +90,7 @@ class BottleneckBase4Ext(nn.Module):
         from .transformer import DataLogger
         self.data_logging = isinstance(bottleneck_transformer, DataLogger)
         self.last_bottleneck = None
-        self.uses_ext_encoder = False
+        self.uses_ext_encoder = isinstance(encoder, ExtEncoder) and encoder.ext_classifier is not None
         self.use_bottleneck_transformer = False
         self._runners = {}
         self.act_dtype = torch.float16
@@ -120,17 +127,28 @@ class BottleneckBase4Ext(nn.Module):
 
     def forward(self, x):
         self._check(x)
+        if self.uses_ext_encoder and self.training:
+            raise _lib.GhndError("training with the neural filter attached (ext_runner.py) is outside the "
+                                 "B200 hot path")
         if self.training and torch.is_grad_enabled():
             return _Layer1Function.apply(self, x, *list(self.parameters()))
         runner = self._runner(x.shape, train=self.training)
         ops.to_nhwc16_into(x, runner.x)
+        ext_z = None
+        if self.uses_ext_encoder:  # base.py:38-48 forward_ext: returns (decoder output or None, ext_z)
+            skip, ext_z = self.encoder.filter_decision(runner.x)
+            if skip:
+                if self.data_logging:
+                    self.bottleneck_transformer(None, target=None)
+                return None, ext_z
         z = runner.forward_encoder()
         if not self.training and self.bottleneck_transformer is not None and self.use_bottleneck_transformer:
             z = apply_bottleneck_transformer(self, z)  # base.py:55-57
-        return ops.to_nchw_f32(runner.forward_decoder(z.contiguous()))
+        out = ops.to_nchw_f32(runner.forward_decoder(z.contiguous()))
+        return (out, ext_z) if self.uses_ext_encoder else out
 
     def get_ext_classifier(self):
-        return None
+        return self.encoder.get_ext_classifier() if isinstance(self.encoder, ExtEncoder) else None
 
 
 def _make_encoder_decoder(bottleneck_channel):
@@ -168,7 +186,9 @@ class Bottleneck4LargeResNet(BottleneckBase4Ext):
         if not 1 <= int(bottleneck_channel) <= 16:
             raise ValueError("bottleneck_channel %r not supported (1..16)" % (bottleneck_channel,))
         encoder, decoder = _make_encoder_decoder(int(bottleneck_channel))
-        super().__init__(encoder=ExtEncoder(encoder, None, ext_config), decoder=decoder,
+        from .classifier import Ext4ResNet
+        ext = Ext4ResNet(64) if ext_config is not None else None  # resnet_layer.py:66
+        super().__init__(encoder=ExtEncoder(encoder, ext, ext_config), decoder=decoder,
                          bottleneck_transformer=bottleneck_transformer)
         self.bottleneck_channel = int(bottleneck_channel)
         # custom/resnet.py:55-60 applies this init to every conv / norm, injected layers included

@@ -52,9 +52,17 @@ class RcnnHead(nn.Module):
                                    image_mean=self.transform.image_mean, image_std=self.transform.image_std,
                                    scale_mode=tensor_util._scale_mode())
             self.plan_key = key
-            if self.use_cuda_graph:
+            if self.use_cuda_graph and not getattr(self.model.backbone.body.layer1, "uses_ext_encoder", False):
                 self.plan.capture()
-        q, qp = self.plan.run(imgs)
+        layer1 = self.model.backbone.body.layer1
+        if getattr(layer1, "uses_ext_encoder", False):
+            res, _ext_z = self.plan.run_filtered(imgs, layer1.encoder)
+            if res is None:
+                # Stop inference since it is decided that there is no object we are interested in
+                return None
+            q, qp = res
+        else:
+            q, qp = self.plan.run(imgs)
         tshape = torch.Size((len(imgs), 3, hp, wp))
         if self.num_bits is None:
             return self.plan.z, tshape, image_sizes, original_image_sizes
@@ -87,7 +95,9 @@ class RcnnTail(nn.Module):
                 r = FrozenLayerRunner(getattr(body, name), cur, n, ch, cw, torch.float16, torch.bfloat16, False)
                 layers.append(r)
                 cur, ch, cw = r.out, r.Ho, r.Wo
-            self._plans = {key: (l1, layers)}
+            from .engine import FpnPlan
+            fpn = FpnPlan(self.model.backbone.fpn, [l1.out] + [r.out for r in layers])
+            self._plans = {key: (l1, layers, fpn)}
         return self._plans[key]
 
     def backbone_features(self, z, targets=None):
@@ -97,18 +107,34 @@ class RcnnTail(nn.Module):
         if self.bottleneck_transformer is not None:
             z, _ = self.bottleneck_transformer(z, targets)
         z = z.float().contiguous()
-        l1, layers = self._plan(z)
+        l1, layers, _ = self._run_body(z)
         feats = OrderedDict()
-        feats['0'] = ops.to_nchw_f32(l1.forward_decoder(z))
+        feats['0'] = ops.to_nchw_f32(l1.out)
         for i, r in enumerate(layers):
-            r.forward()
             feats[str(i + 1)] = ops.to_nchw_f32(r.out)
         return feats
 
+    def _run_body(self, z):
+        z = z.float().contiguous()
+        plan = self._plan(z)
+        plan[0].forward_decoder(z)
+        for r in plan[1]:
+            r.forward()
+        return plan
+
     def forward(self, z, tensors_shape, image_sizes, original_image_sizes, targets=None):
-        feats = self.backbone_features(z, targets)
-        features = self.model.backbone.fpn(feats)
-        image_list = ImageList(torch.empty(tuple(tensors_shape), device=feats['0'].device),
+        """split_rcnn.py:186-212: dequantize -> decoder -> layer2-4 -> FPN on the CUDA kernels, then the
+        torchvision RPN / RoI heads."""
+        if self.bottleneck_transformer is not None:
+            z, _ = self.bottleneck_transformer(z, targets)
+        _, _, fpn = self._run_body(z)
+        names = [str(i) for i in range(len(fpn.out))]
+        results = [ops.to_nchw_f32(t) for t in fpn.run()]
+        extra = self.model.backbone.fpn.extra_blocks
+        if extra is not None:
+            results, names = extra(results, [None] * len(results), names)
+        features = OrderedDict(zip(names, results))
+        image_list = ImageList(torch.empty(tuple(tensors_shape), device=results[0].device),
                                [tuple(s) for s in image_sizes])
         proposals, proposal_losses = self.model.rpn(image_list, features, targets)
         detections, detector_losses = self.model.roi_heads(features, proposals, image_list.image_sizes, targets)

@@ -328,6 +328,12 @@ int ghnd_bn_finalize_apply(const void* x, int x_fmt, void* y, int y_fmt, void* y
                            const float* gamma, const float* beta, float eps, float momentum,
                            float* running_mean, float* running_var, int64_t* num_batches_tracked,
                            float* scale_shift, float* mean_invstd, void* stream);
+/* FPN top-down step: y = fine + nearest_upsample(coarse) on NHWC 16-bit tensors (fine/y [N,H,W,C],
+ * coarse [N,Hc,Wc,C]; source index floor(dst*in/out)).  Replaces F.interpolate(mode="nearest") + add in
+ * torchvision's FeaturePyramidNetwork.forward, reached from the reference through
+ * BackboneWithFPN.fpn (src/models/org/rcnn.py:399-414, called at :108,:127). */
+int ghnd_upsample_add(const void* fine, const void* coarse, void* y, int fmt, int N, int H, int W, int Hc,
+                      int Wc, int C, void* stream);
 /* 16-bit format conversion (fp16 <-> bf16), n elements (multiple of 8) */
 int ghnd_convert16(const void* x, int x_fmt, void* y, int y_fmt, int64_t n, void* stream);
 /* backward, pass 1: sums[2C] = { sum g', sum g'*xhat } with g' = dy * (relu ? (x*scale+shift>0):1) */
@@ -358,6 +364,20 @@ int ghnd_bn_bwd_apply_fused_sums(const void* dy, int dy_fmt, const void* x, int 
 int ghnd_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                    double lr, double beta1, double beta2, double eps, double weight_decay,
                    double grad_scale, int step, void* stream);
+
+/* ---- neural-filter head Ext4ResNet (src/models/ext/classifier.py:16-37), inference ----------------
+ * ghnd_adaptive_avgpool_nhwc16: nn.AdaptiveAvgPool2d((OH,OW)) of an NHWC 16-bit tensor [N,H,W,C] into
+ *   NHWC fp32 [N,OH,OW,C] (bin i = [floor(i*H/OH), ceil((i+1)*H/OH)), classifier.py:20).
+ * ghnd_small_conv_f32: nn.Conv2d (no padding) + folded eval BatchNorm + optional ReLU on NHWC fp32
+ *   tensors, weights repacked [R][S][C][K]; y = act(scale[k]*conv + shift[k]) (classifier.py:21-29).
+ * ghnd_avgpool_linear: AdaptiveAvgPool2d((OH,OW)) -> flatten(1) in NCHW order -> nn.Linear -> optional
+ *   softmax(dim=1) (classifier.py:30-37); lw is the Linear weight [n_out][C*OH*OW], out [N][n_out]. */
+int ghnd_adaptive_avgpool_nhwc16(const void* x, int fmt, int N, int H, int W, int C, float* y, int OH, int OW,
+                                 void* stream);
+int ghnd_small_conv_f32(const float* x, const float* w_rsck, const float* scale, const float* shift, int relu,
+                        float* y, int N, int H, int W, int C, int K, int R, int S, int stride, void* stream);
+int ghnd_avgpool_linear(const float* x, int N, int H, int W, int C, int OH, int OW, const float* lw, const float* lb,
+                        int n_out, int softmax, float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -105,20 +105,21 @@ def transform_batch(images, size_divisible=32, sizes=None, max_size=1333):
     torchvision GeneralizedRCNNTransform.normalize / batch_images).  `sizes` = per-image target min
     side (fixed_sizes of DistillationBox, tool.py:44-49, or min_size[-1] in eval); None = the images
     are already at network scale (resize is the identity: interpolate with scale_factor 1)."""
-    mean = torch.tensor(IMAGE_MEAN, dtype=torch.float32)[:, None, None]
-    std = torch.tensor(IMAGE_STD, dtype=torch.float32)[:, None, None]
+    dev = images[0].device  # the bench's "stock torch on the same B200" leg runs this port on cuda
+    mean = torch.tensor(IMAGE_MEAN, dtype=torch.float32, device=dev)[:, None, None]
+    std = torch.tensor(IMAGE_STD, dtype=torch.float32, device=dev)[:, None, None]
     imgs = [(im - mean) / std for im in images]
     if sizes is not None:
         scaled = []
         for im, size in zip(imgs, sizes):
             sc = resize_scale(im.shape[1], im.shape[2], size, max_size)
-            scaled.append(im if sc == 1.0 else torch.from_numpy(bilinear_resize_np(im.numpy(), sc)))
+            scaled.append(im if sc == 1.0 else torch.from_numpy(bilinear_resize_np(im.cpu().numpy(), sc)).to(dev))
         imgs = scaled
     hmax = max(im.shape[1] for im in imgs)
     wmax = max(im.shape[2] for im in imgs)
     hp = (hmax + size_divisible - 1) // size_divisible * size_divisible
     wp = (wmax + size_divisible - 1) // size_divisible * size_divisible
-    out = torch.zeros(len(imgs), 3, hp, wp, dtype=torch.float32)
+    out = torch.zeros(len(imgs), 3, hp, wp, dtype=torch.float32, device=dev)
     for i, im in enumerate(imgs):
         out[i, :, :im.shape[1], :im.shape[2]] = im
     return out
@@ -303,5 +304,5 @@ def encode_head(images, student_sd, num_bits=8):
     with torch.no_grad():
         z = student_encoder_forward(stem_forward(x, student_sd), student_sd, "backbone.body.layer1",
                                     training=False)
-    q, scale, zp = quantize_tensor_np(z.numpy(), num_bits)
+    q, scale, zp = quantize_tensor_np(z.cpu().numpy(), num_bits)
     return q, scale, zp, z, tuple(x.shape)

@@ -302,3 +302,112 @@ def test_mimic_runner_main_distill_resume_and_eval(tmp_path, capsys):
     ckpt2 = torch.load(str(ckpt_path), map_location="cpu", weights_only=False)
     assert all(int(s["step"]) == 8 for s in ckpt2["optimizer"]["state"].values())
     assert "teacher" not in res2 and "bottleneck_kb_per_image" not in res2["student"]
+
+
+@pytest.mark.parametrize("size", ["small", "800x1333"])
+def test_fpn_forward_on_conv_kernels(env, size):
+    """BackboneWithFPN.fpn (rcnn.py:399-414) through engine.FpnPlan -- 1x1 laterals,
+    nearest-upsample-add, 3x3 output convs on the tcgen05 conv kernel -- against torchvision's own
+    FeaturePyramidNetwork (fp32, TF32 off) fed with the SAME body features: <= 1e-2 relative L2 per
+    level, same keys ('0'..'3','pool') and shapes."""
+    from collections import OrderedDict
+    from hnd_ghnd_object_detectors_b200 import ops
+    from tests.golden.make_golden import small_images
+    if size == "small":
+        _, student = build_pair(env)
+        host = small_images()
+    else:
+        _, student = build_full_pair(env)
+        host = full_images(1, seed=3)
+    student.eval()
+    torch.manual_seed(11)
+    with torch.no_grad():
+        for p in student.backbone.fpn.parameters():
+            if p.dim() == 1:
+                p.normal_(0.0, 0.2)  # the default zero biases would hide a missing bias add
+    images = [im.cuda() for im in host]
+    plan, image_sizes, tshape = student._run_body(images)
+    got = student.fpn_features(plan)
+    body = OrderedDict((str(i), ops.to_nchw_f32(f)) for i, f in enumerate(plan.feats.values()))
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            ref = student.backbone.fpn(body)
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    assert list(got.keys()) == list(ref.keys()) == ["0", "1", "2", "3", "pool"]
+    for k in ref:
+        assert tuple(got[k].shape) == tuple(ref[k].shape), k
+        r = rel(got[k], ref[k])
+        print("fpn level %s %s rel L2 %.2e" % (k, tuple(ref[k].shape), r))
+        assert r <= 1e-2, (k, r)
+    # the full detector forward consumes these maps
+    student.distill_backbone_only = False
+    with torch.no_grad():
+        det = student(images)
+    assert len(det) == len(images) and set(det[0].keys()) >= {"boxes", "labels", "scores"}
+
+
+def test_neural_filter_head(env):
+    """Ext4ResNet (src/models/ext/classifier.py:16-37) on the CUDA kernels vs the same
+    nn modules run by torch (fp32) on the fp16-rounded input; then the filter's place in the split
+    model: batch-1 inference stops before the encoder when P(object) < threshold (base.py:13-16,
+    split_rcnn.py:30-35, rcnn.py:115-124)."""
+    from hnd_ghnd_object_detectors_b200.classifier import Ext4ResNet
+    from hnd_ghnd_object_detectors_b200.split_rcnn import split_rcnn_model
+    torch.manual_seed(21)
+    m = Ext4ResNet(64).cuda().eval()
+    with torch.no_grad():
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.running_mean.normal_(0, 0.2)
+                mod.running_var.uniform_(0.5, 1.5)
+                mod.weight.uniform_(0.7, 1.3)
+                mod.bias.normal_(0, 0.2)
+    x = torch.randn(3, 64, 200, 336, device="cuda").relu()
+    got = m(x)
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            ref = m.linear(m.extractor(x.half().float()).flatten(1)).softmax(dim=1)
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    print("filter probabilities", got.tolist(), ref.tolist())
+    assert tuple(got.shape) == (3, 2) and float((got - ref).abs().max()) <= 1e-4
+    assert float((got.sum(dim=1) - 1).abs().max()) <= 1e-5
+    with pytest.raises(Exception):
+        m.train()(x)  # training the filter is outside the hot path: must fail loudly, not fall back
+    # ---- inside the split model ----
+    models = env["models"]
+    cfg = model_config("student")
+    cfg["backbone"]["ext_config"] = {"backbone_frozen": True, "threshold": 0.5, "ckpt": "/nonexistent/ext.pt"}
+    model = models.get_model(cfg, torch.device("cuda"))
+    model.load_state_dict(env["s_sd"], strict=False)
+    model.eval()
+    assert model.get_ext_classifier() is model.backbone.body.layer1.encoder.ext_classifier
+    head, tail = split_rcnn_model(model, 8)
+    from tests.golden.make_golden import small_images
+    img = [small_images()[0].cuda()]
+    enc = model.backbone.body.layer1.encoder
+    probs = []
+    for thr, expect_skip in ((2.0, True), (-1.0, False)):  # P(object) in [0,1]: always / never below
+        enc.threshold = thr
+        out = head(img)
+        assert (out is None) == expect_skip
+        model.distill_backbone_only = False
+        with torch.no_grad():
+            det = model(img)
+        assert len(det) == 1 and "boxes" in det[0]
+        if expect_skip:
+            assert det[0]["boxes"].shape == (0, 4) and det[0]["masks"].shape[0] == 100
+        else:
+            qz, tshape, sizes, orig = out
+            assert qz.tensor.dtype == torch.uint8
+            with torch.no_grad():
+                assert len(tail(qz, tshape, sizes, orig)) == 1
+    # two images: the filter never stops a batch (base.py:15 `ext_z.shape[0] == 1`)
+    enc.threshold = 2.0
+    two = [im.cuda() for im in small_images()]
+    assert head(two) is not None
