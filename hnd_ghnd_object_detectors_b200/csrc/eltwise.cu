@@ -190,6 +190,17 @@ __global__ void __launch_bounds__(256)
   }
   y[i] = make_uint4(best[0], best[1], best[2], best[3]);
   if (kArg) {
+    // The backward pass routes dy to the argmax tap AND applies the ReLU mask of the pooled tensor's
+    // producer; at the argmax the producer's value IS the pooled value, so the mask is folded in here:
+    // a non-positive maximum gets tap code 0xff ("no tap") and the backward kernel never has to re-read
+    // the (4x larger) pre-pool tensor.
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      uint32_t pos;
+      if (FMT == GHND_F16) pos = __hgt2_mask(*reinterpret_cast<const __half2*>(&best[e]), __float2half2_rn(0.f));
+      else pos = __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&best[e]), __float2bfloat162_rn(0.f));
+      idx[e] = (idx[e] & pos) | (0x00ff00ffu & ~pos);
+    }
     uint2 a;  // one byte per channel, channel order
     a.x = __byte_perm(idx[0], idx[1], 0x6420);
     a.y = __byte_perm(idx[2], idx[3], 0x6420);
@@ -197,7 +208,8 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// Backward of the pool fused with the ReLU mask of the stem output.  A thread owns the input pixel
+// Backward of the pool fused with the ReLU mask of the stem output (carried by the argmax codes, see
+// maxpool_kernel).  A thread owns the input pixel
 // pair (h, 2m), (h, 2m+1) for one 8-channel group: the pair shares its windows (wo = m, m+1; ho =
 // h/2 and, for odd h, h/2+1 -- uniform per block), so every window vector is loaded once and each
 // (pixel, window) combination that can hold the pixel is tested exactly once: 1.5 (even rows) or 3
@@ -216,16 +228,10 @@ __device__ __forceinline__ void pool_bwd_acc(float (&g)[8], const uint2 a, const
     g[2 * e + 1] += a1 == code ? f.y : 0.f;
   }
 }
-template <int XF, int DXF>
-__device__ __forceinline__ uint4 pool_bwd_mask(const uint4 xv, const float (&g)[8]) {
-  const uint32_t xu[4] = {xv.x, xv.y, xv.z, xv.w};
-  uint32_t ou[4];
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const float2 f = unpack2_t<XF>(xu[e]);
-    ou[e] = pack2_t<DXF>(f.x > 0.f ? g[2 * e] : 0.f, f.y > 0.f ? g[2 * e + 1] : 0.f);
-  }
-  return make_uint4(ou[0], ou[1], ou[2], ou[3]);
+template <int DXF>
+__device__ __forceinline__ uint4 pool_bwd_pack(const float (&g)[8]) {
+  return make_uint4(pack2_t<DXF>(g[0], g[1]), pack2_t<DXF>(g[2], g[3]), pack2_t<DXF>(g[4], g[5]),
+                    pack2_t<DXF>(g[6], g[7]));
 }
 template <int XF, int DYF, int DXF>
 __global__ void __launch_bounds__(256)
@@ -241,9 +247,7 @@ __global__ void __launch_bounds__(256)
   const int n = blockIdx.z;
   const bool has1 = w0 + 1 < W;
   const int64_t i0 = (((int64_t)n * H + h) * W + w0) * C8 + cg;
-  const int64_t ix0 = (((int64_t)n * H + h) * W + w0) * XC8 + xoff8 + cg;
-  const uint4 x0 = ld_stream(x + ix0);
-  const uint4 x1 = has1 ? ld_stream(x + ix0 + XC8) : make_uint4(0u, 0u, 0u, 0u);
+  // x (the pre-pool tensor) is not read: its ReLU mask travels inside the argmax codes (0xff = masked)
   const int k = h >> 1;
   const bool odd = h & 1;  // uniform per block
   // window (row q, col c): q = 0 -> ho = k, q = 1 -> ho = k + 1 (odd rows only); c = 0 -> wo = m,
@@ -273,8 +277,8 @@ __global__ void __launch_bounds__(256)
     pool_bwd_acc<DYF>(g1, a[1][0], d[1][0], 2);
     pool_bwd_acc<DYF>(g1, a[1][1], d[1][1], 0);
   }
-  dx[i0] = pool_bwd_mask<XF, DXF>(x0, g0);
-  if (has1) dx[i0 + C8] = pool_bwd_mask<XF, DXF>(x1, g1);
+  dx[i0] = pool_bwd_pack<DXF>(g0);
+  if (has1) dx[i0 + C8] = pool_bwd_pack<DXF>(g1);
 }
 
 // ------------------------------------------------------------------------------------------------

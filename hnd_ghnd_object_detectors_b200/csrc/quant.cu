@@ -104,11 +104,46 @@ __device__ __forceinline__ uint32_t quant1(float v, float zpf, float scale, floa
   t = t < 0.0f ? 0.0f : (t > qmax ? qmax : t);
   return (uint32_t)(int)rintf(t) & 0xffu;
 }
-__device__ __forceinline__ uint32_t quant4(uint4 v, float zpf, float scale, float qmax) {
-  return quant1(__uint_as_float(v.x), zpf, scale, qmax) |
-         (quant1(__uint_as_float(v.y), zpf, scale, qmax) << 8) |
-         (quant1(__uint_as_float(v.z), zpf, scale, qmax) << 16) |
-         (quant1(__uint_as_float(v.w), zpf, scale, qmax) << 24);
+// Exact-result fast path.  The IEEE division per element (~20 issue slots with its slow path) kept the
+// quantizer at 30-40 % of HBM.  Here t' = zp + x * RN(1/scale) replaces t = zp + RN(x / scale): for a
+// quotient inside [-256, 512] the two differ by < 1.3e-4 (3 roundings of 2^-24 relative on |q| <= 512,
+// plus half an ulp of the sum), quotients outside clamp to the same end.  The byte is
+// round-half-even(clamp(t)); it can only differ from the reference's when t' lies within that error
+// of a rounding boundary k + 0.5, so a 4-element vector whose t' comes within kQuantGuard = 2^-11 of a
+// boundary (0.1 % of elements) is redone with the reference's exact sequence.  Rounding and the
+// float -> byte conversion use the 1.5 * 2^23 magic constant (round-half-even in the FADD itself, the
+// integer sits in the low mantissa byte): no F2I / FRND on the conversion pipe.
+static constexpr float kQuantMagic = 12582912.0f;  // 1.5 * 2^23
+static constexpr float kQuantGuard = 0.5f - 0.00048828125f;
+struct QFast {
+  float zpf, scale, rscale, qmax;
+  bool ok;  // scale is a normal number with a finite reciprocal: the error bound above holds
+};
+__device__ __forceinline__ QFast make_qfast(float zpf, float scale, float qmax) {
+  QFast f;
+  f.zpf = zpf;
+  f.scale = scale;
+  f.qmax = qmax;
+  f.rscale = __frcp_rn(scale);
+  f.ok = scale >= 1e-30f && scale <= 1e30f;
+  return f;
+}
+__device__ __forceinline__ uint32_t quant4(uint4 v, const QFast& f) {
+  const float x[4] = {__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w)};
+  uint32_t m[4];
+  bool near = !f.ok;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    float t = __fadd_rn(f.zpf, __fmul_rn(x[e], f.rscale));
+    t = fminf(fmaxf(t, 0.0f), f.qmax);            // NaN -> 0, like (int)rintf(NaN) & 0xff
+    const float r = __fadd_rn(t, kQuantMagic);    // low mantissa byte = round-half-even(t)
+    m[e] = __float_as_uint(r);
+    near |= fabsf(__fsub_rn(t, __fsub_rn(r, kQuantMagic))) > kQuantGuard;
+  }
+  if (near)
+    return quant1(x[0], f.zpf, f.scale, f.qmax) | (quant1(x[1], f.zpf, f.scale, f.qmax) << 8) |
+           (quant1(x[2], f.zpf, f.scale, f.qmax) << 16) | (quant1(x[3], f.zpf, f.scale, f.qmax) << 24);
+  return __byte_perm(__byte_perm(m[0], m[1], 0x0040), __byte_perm(m[2], m[3], 0x0040), 0x5410);
 }
 
 // pass 2: every block folds the partials (L2 resident), derives scale / zero-point, quantizes.
@@ -133,6 +168,7 @@ __global__ void __launch_bounds__(kQThreads)
     qp->mx = mx;
   }
   const float zpf = (float)zp;
+  const QFast qf = make_qfast(zpf, scale, qmax);
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
   int64_t done = 0;
@@ -144,10 +180,10 @@ __global__ void __launch_bounds__(kQThreads)
       uint4 a = ld_stream(x4 + 4 * i), b = ld_stream(x4 + 4 * i + 1), c = ld_stream(x4 + 4 * i + 2),
             d = ld_stream(x4 + 4 * i + 3);
       uint4 o;
-      o.x = quant4(a, zpf, scale, qmax);
-      o.y = quant4(b, zpf, scale, qmax);
-      o.z = quant4(c, zpf, scale, qmax);
-      o.w = quant4(d, zpf, scale, qmax);
+      o.x = quant4(a, qf);
+      o.y = quant4(b, qf);
+      o.z = quant4(c, qf);
+      o.w = quant4(d, qf);
       st_stream(q16 + i, o);
     }
     done = n16 << 4;
@@ -242,11 +278,11 @@ __global__ void __launch_bounds__(kQFThreads, 1)
   int zp;
   derive_qparams(mn, mx, qmax, inv_range, scale_mode, scale, zp);
   const float zpf = (float)zp;
+  const QFast qf = make_qfast(zpf, scale, qmax);
 #pragma unroll 4
-  for (int i = threadIdx.x; i < res; i += kQFThreads) q4[i] = quant4(s_x[i], zpf, scale, qmax);
+  for (int i = threadIdx.x; i < res; i += kQFThreads) q4[i] = quant4(s_x[i], qf);
 #pragma unroll 4
-  for (int i = res + threadIdx.x; i < len; i += kQFThreads)
-    q4[i] = quant4(ld_stream(x4 + i), zpf, scale, qmax);
+  for (int i = res + threadIdx.x; i < len; i += kQFThreads) q4[i] = quant4(ld_stream(x4 + i), qf);
   if (blockIdx.x == 0)
     for (int64_t i = (nvec << 2) + threadIdx.x; i < n; i += kQFThreads)
       q[i] = (uint8_t)quant1(x[i], zpf, scale, qmax);
@@ -274,7 +310,12 @@ __global__ void __launch_bounds__(kQThreads)
   const float scale = qp->scale;
   const float zpf = (float)qp->zero_point;
   // scale * (q.float() - zero_point)   tensor_util.py:22
-  auto dq = [&](uint32_t b) -> float { return __fmul_rn(scale, __fsub_rn((float)b, zpf)); };
+  // (float)b - zp without I2F: bits 0x4b000000 | b are the float 2^23 + b; 2^23 + zp is exact, so is the
+  // difference (both integers below 2^24) -- identical to __fsub_rn((float)b, zpf)
+  const float zp_magic = 8388608.0f + zpf;
+  auto dq = [&](uint32_t b) -> float {
+    return __fmul_rn(scale, __fsub_rn(__uint_as_float(0x4b000000u | b), zp_magic));
+  };
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
   int64_t done = 0;

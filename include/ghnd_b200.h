@@ -264,11 +264,13 @@ int ghnd_stem_conv_plan_create_k(const void* x_packed, int x_fmt, const void* w_
 int ghnd_stem_conv_plan_run(const ghnd_stem_plan_t* plan, void* stream);
 void ghnd_stem_plan_destroy(ghnd_stem_plan_t* plan);
 /* maxpool 3x3 s2 p1 on NHWC 16-bit: y[N][Ho][Wo][C], Ho=(H+1)/2; argmax (nullable) receives the
- * window position 0..8 of the first maximum, one byte per output element. */
+ * window position 0..8 of the first maximum, one byte per output element -- or 0xff when that maximum is
+ * not > 0: the ReLU mask of x's producer, folded in so that the backward pass need not re-read x. */
 int ghnd_maxpool3x3s2(const void* x, void* y, void* argmax, int fmt, int N, int H, int W, int C,
                       void* stream);
 /* backward of relu+maxpool: dx[n][h][w][c] = sum of dy over the pool windows whose argmax is
- * (h,w), zero where x (the post-ReLU conv output) is not > 0. */
+ * (h,w), zero where x (the post-ReLU conv output) is not > 0.  The mask arrives through the argmax
+ * codes (0xff); x / x_fmt are kept in the signature for geometry checks only and are not read. */
 int ghnd_maxpool3x3s2_bwd(const void* x, int x_fmt, const void* argmax, const void* dy, int dy_fmt,
                           void* dx, int dx_fmt, int N, int H, int W, int C, void* stream);
 /* Strided-input variants: x holds x_channels channels per pixel and the pool works on the C channels

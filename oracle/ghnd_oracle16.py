@@ -21,9 +21,17 @@ exactly the tensors the engine stores (engine.py / conv_tc.cu epilogues):
     around it stay fp32 (planar fp32 tensors, fp32-split mma.sync operands)
   * loss gradient = bf16(2 * factor * (s - t)), masked by s > 0 on the top level (sse.cu)
 
-With the forward rounded like the engine's, both sides take the same ReLU masks, and the remaining
-difference is accumulation order: the GPU tests gate end-to-end gradients at <= 1e-2 relative L2
-against this emulation and REPORT the distance to the fp32 oracle next to it.
+Free-running, the emulation agrees with the engine to ~1e-5 per kernel, but 16-bit rounding is chaotic
+along a deep chain: a 1-ulp difference in 0.2 % of one layer's outputs (accumulation order) re-rounds a few
+per cent of the next layer's, and after ~6 convolutions two CORRECT implementations sit at the fp16
+rounding floor from each other (relative L2 ~1e-3, measured at 800x1333 with scripts/debug/emu_vs_engine.py).
+Their ReLU masks then differ in the same ~0.2 % of positions as against the fp32 oracle, so end-to-end
+gradients differ by percents no matter how exact the backward kernels are.  To test the BACKWARD at step
+level the emulation can therefore be teacher-forced: `force` maps storage points to the tensors the engine
+actually stored in its forward pass; the emulated forward takes those VALUES (hence the engine's masks,
+arg-maxima and BatchNorm statistics) while autograd still differentiates the oracle's graph.  The GPU tests
+gate gradients at <= 1e-2 relative L2 against the forced emulation and REPORT the distances to the
+free-running emulation and to the fp32 oracle next to it.
 Reference lines restated: the same as ghnd_oracle.py (tool.py:40-61, resnet_layer.py:42-65,
 custom/resnet.py:26-30,96-99, loss.py:25-34)."""
 import torch
@@ -62,6 +70,28 @@ class _G(torch.autograd.Function):
 
 Q, G = _Q.apply, _G.apply
 
+# teacher forcing (see the module docstring): storage-point name -> tensor stored by the engine (NCHW fp32)
+_FORCE = {}
+
+
+def _forced(x, key):
+    """Value of the engine's stored tensor, gradient of the emulated one."""
+    f = _FORCE.get(key)
+    if f is None:
+        return x
+    assert f.shape == x.shape, (key, tuple(f.shape), tuple(x.shape))
+    return f + (x - x.detach())
+
+
+def _forced_relu(pre, key):
+    """ReLU whose output value AND mask are the engine's stored post-ReLU tensor."""
+    f = _FORCE.get(key)
+    if f is None:
+        return F.relu(pre)
+    assert f.shape == pre.shape, (key, tuple(f.shape), tuple(pre.shape))
+    m = (f > 0).to(pre.dtype)
+    return f + (pre * m - (pre * m).detach())
+
 
 class _Conv(torch.autograd.Function):
     """y = conv(x, fp16(w)); dx = conv_T(g, bf16(w)); dw = corr(xg, g) with xg = the bf16 copy of x."""
@@ -94,19 +124,20 @@ def _frozen_scale_shift(sd, prefix):
     return scale, b - rm * scale
 
 
-def frozen_conv(x, sd, conv, bn, stride=1, pad=0, relu=True, residual=None, xg=None):
-    """conv + folded FrozenBN through the packed-half2 epilogue (conv_tc.cu epi_half_rows)."""
+def frozen_conv(x, sd, conv, bn, stride=1, pad=0, relu=True, residual=None, xg=None, name=None):
+    """conv + folded FrozenBN through the packed-half2 epilogue (conv_tc.cu epi_half_rows).
+    `name`: storage point of the result for teacher forcing."""
     scale, shift = _frozen_scale_shift(sd, bn)
     h = Q(conv16(x, sd[conv + ".weight"] * scale[:, None, None, None], stride, pad, xg))
     h = Q(h + r16(shift)[None, :, None, None])
     if residual is not None:
         h = Q(h + residual)
-    return F.relu(h) if relu else h
+    return _forced_relu(h, name) if relu else _forced(h, name)
 
 
 def stem16(x16, sd, prefix="backbone.body."):
     """packed fp16 image -> conv1 (+FrozenBN, ReLU) -> max-pool; conv1's dW uses the bf16 image copy."""
-    c = frozen_conv(x16, sd, prefix + "conv1", prefix + "bn1", 2, 3, True, xg=rbf(x16))
+    c = frozen_conv(x16, sd, prefix + "conv1", prefix + "bn1", 2, 3, True, xg=rbf(x16), name=prefix + "conv1")
     return F.max_pool2d(G(c), kernel_size=3, stride=2, padding=1)
 
 
@@ -117,13 +148,14 @@ def bottleneck16(x, sd, prefix, stride):
     ds = (prefix + ".downsample.0.weight") in sd
     x0 = G(x)                       # the stored gradient w.r.t. x (after the last accumulating launch)
     xi = G(x0) if ds else x0        # downsample blocks: inner sum rbf(rbf(acc_conv1) + loss_grad) first
-    a1 = frozen_conv(G(xi), sd, prefix + ".conv1", prefix + ".bn1")
-    a2 = frozen_conv(G(a1), sd, prefix + ".conv2", prefix + ".bn2", stride, 1)
+    a1 = frozen_conv(G(xi), sd, prefix + ".conv1", prefix + ".bn1", name=prefix + ".a1")
+    a2 = frozen_conv(G(a1), sd, prefix + ".conv2", prefix + ".bn2", stride, 1, name=prefix + ".a2")
     if ds:
-        idn = frozen_conv(G(x0), sd, prefix + ".downsample.0", prefix + ".downsample.1", stride, 0, relu=False)
+        idn = frozen_conv(G(x0), sd, prefix + ".downsample.0", prefix + ".downsample.1", stride, 0, relu=False,
+                          name=prefix + ".idn")
     else:
         idn = xi
-    out = frozen_conv(G(a2), sd, prefix + ".conv3", prefix + ".bn3", relu=True, residual=idn)
+    out = frozen_conv(G(a2), sd, prefix + ".conv3", prefix + ".bn3", relu=True, residual=idn, name=prefix + ".out")
     return out, xi
 
 
@@ -155,11 +187,11 @@ def _wide_unit(x, xg, sd, conv, bn, pad, relu, training=True):
         h = Q(conv16(x, sd[conv + ".weight"] * sc[:, None, None, None], 1, pad))
         h = Q(h + r16(sd[bn + ".bias"] - rm * sc)[None, :, None, None])
         return (F.relu(h) if relu else h), None
-    raw = G(Q(conv16(G(x), sd[conv + ".weight"], 1, pad, xg)))
+    raw = G(_forced(Q(conv16(G(x), sd[conv + ".weight"], 1, pad, xg)), conv + ".raw"))
     a = _bn_train(raw, sd, bn)
     if relu:
         a = F.relu(a)
-    return Q(a), rbf(a.detach())
+    return _forced(Q(a), conv + ".out"), rbf(a.detach())
 
 
 def student_layer1_16(x, sd, prefix="backbone.body.layer1", training=True):
@@ -171,11 +203,11 @@ def student_layer1_16(x, sd, prefix="backbone.body.layer1", training=True):
     z = F.conv2d(G(y) if training else y, sd[e + "7.weight"], None, 1, 1)      # fp32 planar bottleneck
     bn = _bn_train if training else _bn_eval
     a = F.relu(bn(z, sd, d + "0"))
-    raw3 = Q(F.conv2d(a, sd[d + "2.weight"]))
+    raw3 = _forced(Q(F.conv2d(a, sd[d + "2.weight"])), d + "2.raw")
     if training:
         raw3 = G(raw3)
     a3 = bn(raw3, sd, d + "3")
-    y, yg = Q(a3), rbf(a3.detach())
+    y, yg = _forced(Q(a3), d + "2.out"), rbf(a3.detach())
     y, yg = _wide_unit(y, yg, sd, d + "4", d + "5", 0, True, training)
     y, yg = _wide_unit(y, yg, sd, d + "7", d + "8", 0, False, training)
     y, _ = _wide_unit(y, yg, sd, d + "9", d + "10", 0, True, training)
@@ -201,11 +233,30 @@ def backbone_features16(x16, sd, student, training=False, prefix="backbone.body.
 
 
 def distill_step16(teacher_sd, student_sd, images, levels=("layer1", "layer2", "layer3", "layer4"),
-                   sizes=None, max_size=1333):
-    """One GHND step with the engine's storage precision; same return layout as O.distill_step."""
+                   sizes=None, max_size=1333, force=None, teacher_feats=None):
+    """One GHND step with the engine's storage precision; same return layout as O.distill_step.
+    force / teacher_feats: teacher forcing with the tensors the engine stored (module docstring);
+    keys of `force` are the storage-point names used above (e.g. 'backbone.body.layer2.0.a1',
+    'backbone.body.layer1.decoder.9.raw', 'backbone.body.conv1')."""
+    _FORCE.clear()
+    if force:
+        _FORCE.update(force)
+    try:
+        return _distill_step16(teacher_sd, student_sd, images, levels, sizes, max_size, teacher_feats)
+    finally:
+        _FORCE.clear()
+
+
+def _distill_step16(teacher_sd, student_sd, images, levels, sizes, max_size, teacher_feats):
     x16 = r16(O.transform_batch(images, sizes=sizes, max_size=max_size))
-    with torch.no_grad():
-        t_feats, _ = backbone_features16(x16, teacher_sd, student=False)
+    if teacher_feats is not None:
+        t_feats = teacher_feats
+    else:
+        saved = dict(_FORCE)
+        _FORCE.clear()  # the storage-point names are the student's
+        with torch.no_grad():
+            t_feats, _ = backbone_features16(x16, teacher_sd, student=False)
+        _FORCE.update(saved)
     names = O.trainable_names(student_sd)
     sd = dict(student_sd)
     leaves = {}

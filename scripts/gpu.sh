@@ -6,13 +6,23 @@
 #   bench  <bench.py args>    -> gpurun_out/bench_<n>.log/.err
 #   py     <script + args>    -> gpurun_out/py_<n>.log
 #   launches <bench.py args>  -> gpurun_out/launches_<n>.csv   (ncu gpu__time_duration, never a bench value)
+#   perlayer <batch>          -> gpurun_out/per_layer_<n>.txt + launch_summary_<n>.txt (one eager step under ncu)
+#   traffic  <batch>          -> gpurun_out/conv_dram_traffic_<n>.json (dram bytes of the conv_tc launches; copy to
+#                                profiles/r2_conv_dram_traffic.json -- bench.py's roofline.traffic reads it)
 #   ncu    "<kernel regex>|<skip>|<count>|<cmd>" -> gpurun_out/prof_<n>.ncu-rep (ncu --set full)
 mkdir -p gpurun_out
 n=0
 while [ $# -ge 2 ]; do
   verb=$1; arg=$2; shift 2; n=$((n+1))
   case $verb in
-    tests) timeout 1500 python -m pytest -m gpu -q -x $arg > gpurun_out/tests_$n.log 2>&1; echo "tests_$n rc=$?"; tail -5 gpurun_out/tests_$n.log ;;
+    tests) eval "timeout 1500 python -m pytest -m gpu -q -x $arg" > gpurun_out/tests_$n.log 2>&1; echo "tests_$n rc=$?"; tail -5 gpurun_out/tests_$n.log ;;
+    perlayer) # ncu launch list of ONE eager step joined with the plan runs -> per-layer table (arg = batch)
+         timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_$n.csv python scripts/profile_step.py $arg > gpurun_out/perlayer_$n.log 2>&1; echo "perlayer_$n rc=$?"
+         python scripts/join_launches.py gpurun_out/launches_$n.csv gpurun_out/step_ops.json > gpurun_out/per_layer_$n.txt 2>&1
+         python scripts/summarize_launches.py gpurun_out/launches_$n.csv 40 > gpurun_out/launch_summary_$n.txt 2>&1; tail -1 gpurun_out/launch_summary_$n.txt ;;
+    traffic) # DRAM bytes of every conv_tc_kernel launch of one eager step -> roofline.traffic (arg = batch)
+         timeout 1200 ncu --profile-from-start off --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:conv_tc --csv --log-file gpurun_out/conv_traffic_$n.csv python scripts/profile_step.py $arg > gpurun_out/traffic_$n.log 2>&1; echo "traffic_$n rc=$?"
+         python scripts/conv_traffic.py gpurun_out/conv_traffic_$n.csv gpurun_out/conv_dram_traffic_$n.json; cat gpurun_out/conv_dram_traffic_$n.json ;;
     bench) timeout 900 python bench.py $arg > gpurun_out/bench_$n.log 2> gpurun_out/bench_$n.err; echo "bench_$n rc=$?"; head -c 600 gpurun_out/bench_$n.log; echo ;;
     py) timeout 900 python $arg > gpurun_out/py_$n.log 2>&1; echo "py_$n rc=$?"; tail -30 gpurun_out/py_$n.log ;;
     launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_$n.csv python bench.py $arg > gpurun_out/launches_$n.log 2>&1; echo "launches_$n rc=$?" ;;

@@ -3,9 +3,9 @@ entry points that the distillation fast path bypasses.
 
 * GHND step, one image and a batch of two, through DistillationBox vs the fp32 oracle (loss <= 1e-3,
   per-level relative L2 <= 1e-2) and vs the storage-precision emulation of the same oracle
-  (oracle/ghnd_oracle16.py: gradients <= 1e-2 relative L2; the distance to the fp32 oracle is printed
-  next to it -- that one is dominated by ReLU masks moved by 16-bit storage, which the emulation
-  reproduces on the CPU without any of the CUDA code).
+  (oracle/ghnd_oracle16.py), teacher-forced with the engine's stored forward tensors: all 25 gradients
+  <= 1e-2 relative L2; the distances to the free-running emulation and to the fp32 oracle are printed
+  next to it -- those are dominated by ReLU masks moved by 16-bit storage.
 * RcnnHead (config 1: batch 2 at 800x1333) vs O.encode_head: bytes bit-exact for the same z, end-to-end
   byte-difference histogram printed.
 * CustomRCNN.forward with distill_backbone_only (src/models/org/rcnn.py:102-110) in train and eval
@@ -24,26 +24,13 @@ pytestmark = pytest.mark.gpu
 from oracle import ghnd_oracle as O  # checker only
 from oracle import ghnd_oracle16 as O16
 from oracle import weights
-from tests.test_gpu_distill import (LEVELS, ZERO_GRADS, build_pair, cosine, criterion_config, env,  # noqa: F401
-                                    model_config, rel, targets_for)
+from tests.test_gpu_distill import (LEVELS, ZERO_GRADS, build_pair, check_grads, cosine, criterion_config, env,  # noqa: F401
+                                    forced_step, model_config, rel, targets_for)
 
 
 def full_images(n, seed=5):
     g = torch.Generator().manual_seed(seed)
     return [torch.rand(3, 800, 1333, generator=g) for _ in range(n)]
-
-
-def grad_report(got, ref16, ref32):
-    """{name: (rel L2 vs emulation, rel L2 vs fp32 oracle)}; zero-gradient tensors in absolute terms."""
-    scale = max(float(v.norm()) for v in ref32.values())
-    rep = {}
-    for n in ref32:
-        g = got[n].detach().float().cpu()
-        if n.endswith(ZERO_GRADS):
-            assert float(g.norm()) <= 1e-3 * scale, (n, float(g.norm()), scale)
-            continue
-        rep[n] = (rel(g, ref16[n]), rel(g, ref32[n]))
-    return rep
 
 
 def build_full_pair(env_, min_size=800, max_size=1333):
@@ -90,15 +77,12 @@ def test_ghnd_step_at_800x1333_matches_oracle(env, batch):
         et, es = rel(t, emu["teacher"][lv]), rel(s_, emu["student"][lv])
         print("%s rel L2 vs fp32 oracle: teacher %.2e student %.2e | vs emulation: %.2e %.2e" % (lv, rt, rs, et, es))
         assert rt <= 1e-2 and rs <= 1e-2, lv
-        assert et <= 2e-3 and es <= 2e-3, lv
+        assert et <= 3e-3 and es <= 3e-3, lv  # two 16-bit implementations: the fp16 rounding floor
         term = float(box.last_terms[1 + i])
         assert abs(term - float(ref["per_level"][lv])) <= 2e-3 * float(ref["per_level"][lv]), lv
     params = dict(student.named_parameters())
-    rep = grad_report({n: params[n].grad for n in ref["grads"]}, emu["grads"], ref["grads"])
-    for n, (e16, e32) in rep.items():
-        print("grad %-50s vs emulation %.2e   vs fp32 oracle %.2e" % (n, e16, e32))
-    worst = max(v[0] for v in rep.values())
-    assert worst <= 1e-2, rep
+    forced = forced_step(plan, env["t_sd"], env["s_sd"], host)
+    check_grads({n: params[n].grad for n in ref["grads"]}, ref["grads"], emu["grads"], forced["grads"])
 
 
 def test_rcnn_head_at_800x1333_batch2(env):
