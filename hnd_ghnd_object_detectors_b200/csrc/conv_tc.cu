@@ -724,7 +724,16 @@ __global__ void __launch_bounds__(kConvThreads, 1)
               epi_half_rows<GHND_BF16>(r, b16, i0, p.in0_post, mk, p.relu, hp, row);
             }
           }
-          if (n_in > 0) mbar_arrive(&iempty_bar[slot]);  // operand buffer consumed
+          if (n_in > 0) {
+            // The operand tile was read through the generic proxy (ld.shared) and will be OVERWRITTEN by
+            // the async proxy (the loader warp's next TMA load): a cross-proxy write-after-read.  The
+            // mbarrier orders the two warps but not the two proxies -- without this fence a late TMA
+            // write could land before these reads were performed (seen as a few corrupted 64-channel
+            // rows in the "+res" 1x1 convs, only when another kernel shared the GPU: graph replay with
+            // the side stream, scripts/debug/race_hunt.py).
+            fence_proxy_async();
+            mbar_arrive(&iempty_bar[slot]);  // operand buffer consumed
+          }
           uint8_t* o_base = o_base0;
           if (p.epi_bufs == 2) {
             o_base += (size_t)(n_staged & 1u) * kChunkBytes;
@@ -781,7 +790,10 @@ __global__ void __launch_bounds__(kConvThreads, 1)
         }
         // operand buffer consumed (the BN-backward statistics still read the in1 tile below)
         const bool late_release = STATS && p.stats_mode == 1;
-        if (n_in > 0 && !late_release) mbar_arrive(&iempty_bar[slot]);
+        if (n_in > 0 && !late_release) {
+          fence_proxy_async();  // generic-proxy reads before the async-proxy refill (see the packed path)
+          mbar_arrive(&iempty_bar[slot]);
+        }
         // ---- stage the 64-channel rows and store them with one TMA tensor store ----
         // the store that last used this staging tile has finished reading it
         uint8_t* o_base = o_base0;
@@ -829,6 +841,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
           if (p.stats_mode == 1) {
             // bf16 gradient out, f16 activation operand (the only combination the plans accept)
             epi_stats2_rows<GHND_BF16, GHND_F16>(o_base, m_base, quarter, lane, valid, wstat, ch, p.cout);
+            fence_proxy_async();
             mbar_arrive(&iempty_bar[slot]);  // now the operand buffer may be refilled
           } else if (p.out_fmt == GHND_F16) {
             epi_stats_rows<GHND_F16>(o_base, quarter, lane, valid, wstat, ch, p.cout);

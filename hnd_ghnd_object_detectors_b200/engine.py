@@ -142,6 +142,7 @@ class BottleneckRunner(object):
         mask(x>0) * (dL/dx [+ loss_grad_x]) i.e. the same convention for the producer of x.
         All gradient tensors have batch bwd_n; the saved activations are sliced to those images."""
         dev = g_out.device
+        self.g_out, self.g_x = g_out, g_x  # kept for inspection (tests / debugging)
         N, H, W, Ho, Wo = self.bwd_n, self.H, self.W, self.Ho, self.Wo
         p, cin, cout, s = self.planes, self.cin, self.cout, self.stride
         o = self.N - N
@@ -748,7 +749,10 @@ class GhndPlan(object):
             if self.stem2 is not None:
                 self.stem2.forward()  # both conv1's; the two pools + layer1's then run side by side
                 side.fork()
-            side.run(self._teacher_forward)
+            if os.environ.get("GHND_TEACHER_SIDE", "1") != "0":
+                side.run(self._teacher_forward)
+            else:
+                self._teacher_forward()
             self.s_stem.forward()
             torch.cuda.current_stream().wait_event(packed)
             self.s_l1.forward()

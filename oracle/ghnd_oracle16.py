@@ -72,11 +72,23 @@ Q, G = _Q.apply, _G.apply
 
 # teacher forcing (see the module docstring): storage-point name -> tensor stored by the engine (NCHW fp32)
 _FORCE = {}
+_GRADS = None      # set to a dict to capture the gradient arriving at every named storage point
+_FORCE_GRAD = {}   # storage-point name -> gradient tensor that REPLACES the emulated one there
+
+
+def _capture(t, key):
+    if key and t.requires_grad:
+        if _GRADS is not None:
+            t.register_hook(lambda g, k=key: _GRADS.__setitem__(k, g.detach().clone()))
+        if key in _FORCE_GRAD:
+            t.register_hook(lambda g, k=key: _FORCE_GRAD[k].to(g.dtype))
+    return t
 
 
 def _forced(x, key):
     """Value of the engine's stored tensor, gradient of the emulated one."""
     f = _FORCE.get(key)
+    _capture(x, key)
     if f is None:
         return x
     assert f.shape == x.shape, (key, tuple(f.shape), tuple(x.shape))
@@ -86,6 +98,7 @@ def _forced(x, key):
 def _forced_relu(pre, key):
     """ReLU whose output value AND mask are the engine's stored post-ReLU tensor."""
     f = _FORCE.get(key)
+    _capture(pre, key)
     if f is None:
         return F.relu(pre)
     assert f.shape == pre.shape, (key, tuple(f.shape), tuple(pre.shape))
@@ -233,18 +246,27 @@ def backbone_features16(x16, sd, student, training=False, prefix="backbone.body.
 
 
 def distill_step16(teacher_sd, student_sd, images, levels=("layer1", "layer2", "layer3", "layer4"),
-                   sizes=None, max_size=1333, force=None, teacher_feats=None):
+                   sizes=None, max_size=1333, force=None, teacher_feats=None, force_grad=None, capture=None):
     """One GHND step with the engine's storage precision; same return layout as O.distill_step.
     force / teacher_feats: teacher forcing with the tensors the engine stored (module docstring);
     keys of `force` are the storage-point names used above (e.g. 'backbone.body.layer2.0.a1',
-    'backbone.body.layer1.decoder.9.raw', 'backbone.body.conv1')."""
+    'backbone.body.layer1.decoder.9.raw', 'backbone.body.conv1').  force_grad: the same for stored
+    GRADIENTS (the backward continues from the engine's tensor at that point); capture: a dict that
+    receives the emulated gradient at every named storage point."""
+    global _GRADS
     _FORCE.clear()
+    _FORCE_GRAD.clear()
     if force:
         _FORCE.update(force)
+    if force_grad:
+        _FORCE_GRAD.update(force_grad)
+    _GRADS = capture
     try:
         return _distill_step16(teacher_sd, student_sd, images, levels, sizes, max_size, teacher_feats)
     finally:
         _FORCE.clear()
+        _FORCE_GRAD.clear()
+        _GRADS = None
 
 
 def _distill_step16(teacher_sd, student_sd, images, levels, sizes, max_size, teacher_feats):

@@ -73,32 +73,58 @@ def layer1_forward_tensors(l1, prefix):
     return f
 
 
+L1_OUT = "backbone.body.layer1.decoder.9.out"
+
+
 def forced_step(plan, t_sd, s_sd, host_images, **kw):
-    """The emulated step teacher-forced with the tensors `plan` holds from its last forward."""
+    """The emulated step teacher-forced with the tensors `plan` holds from its last forward + backward.
+    Two backward passes over the forced forward:
+      * the whole chain (loss -> 39 frozen-conv data gradients -> layer1 -> stem): its gradient at
+        layer1's output is compared with the engine's stored one ("trunk" gate), its 25 parameter
+        gradients are reported ("chain");
+      * layer1 + stem continued from the ENGINE's stored gradient at layer1's output: the 25 parameter
+        gradients that are gated.
+    Why two: every stored gradient is rounded to bf16 (2^-9), and a 2e-5 accumulation-order difference
+    in the first data gradient re-rounds ~2 % of the next one's elements -- measured per stage with
+    scripts/debug/grad_chain.py the distance grows by ~4e-4 per convolution and reaches 0.75 % after the
+    trunk and ~1 % at conv1 for ANY two correct implementations; cutting the chain at layer1's output
+    keeps each gated segment well inside 1e-2.
+    Returns (gated grads, chain grads, relative L2 of the engine's gradient at layer1's output)."""
     force, t_feats = engine_forward_tensors(plan)
-    return O16.distill_step16(t_sd, s_sd, host_images, force=force, teacher_feats=t_feats, **kw)
+    cap = {}
+    chain = O16.distill_step16(t_sd, s_sd, host_images, force=force, teacher_feats=t_feats, capture=cap, **kw)
+    if plan.s_layers:  # GHND: the engine's gradient w.r.t. layer1's output (ReLU mask already applied)
+        g_l1 = nchw_cpu(plan.s_layers["layer2"].blocks[0].g_x)
+        m = (force[L1_OUT] > 0).float()
+        trunk_rel = rel(g_l1, cap[L1_OUT] * m)
+        cut = O16.distill_step16(t_sd, s_sd, host_images, force=force, teacher_feats=t_feats,
+                                 force_grad={L1_OUT: g_l1}, **kw)
+        return cut["grads"], chain["grads"], trunk_rel
+    return chain["grads"], chain["grads"], 0.0  # HND: the loss gradient IS the gradient at layer1's output
 
 
-def check_grads(got, ref, emu, forced=None, tol=1e-2, tiny_tol=None):
-    """got vs `forced` (teacher-forced storage-precision emulation; falls back to `emu`) gated at `tol`
-    relative L2; got vs `emu` (free-running emulation) and `ref` (fp32 oracle) reported.  tiny_tol:
-    separate bound for the few-element tensors (the bch-channel BN gamma/beta of the bottleneck): each
-    element is a heavily cancelling sum over all pixels."""
+def check_grads(got, ref, emu, forced=None, tol=1e-2, tiny_tol=5e-2):
+    """got vs the teacher-forced emulation gated at `tol` relative L2 (`forced` = forced_step's result;
+    falls back to `emu`); got vs the whole forced chain, the free-running emulation `emu` and the fp32
+    oracle `ref` reported.  tiny_tol: bound for the <= 256-element tensors (BatchNorm gamma / beta): each
+    element is a heavily cancelling sum over all pixels, so the same per-pixel noise is a larger fraction."""
     scale = max(float(v.norm()) for v in ref.values())
-    gate = forced if forced is not None else emu
+    gate, chain, trunk_rel = forced if forced is not None else (emu, emu, 0.0)
     report = {}
     for n, r in ref.items():
         g = got[n]
         if n.endswith(ZERO_GRADS):
             assert float(g.norm()) <= 1e-3 * scale, (n, float(g.norm()), scale)
             continue
-        report[n] = (float("%.3g" % rel(g, gate[n])), float("%.3g" % rel(g, emu[n])), float("%.3g" % rel(g, r)),
-                     round(cosine(g, r), 5))
-    print("grad (rel L2 vs forced emulation [gated], vs free emulation, vs fp32 oracle, cosine vs fp32 oracle):")
+        report[n] = tuple(float("%.3g" % rel(g, x[n])) for x in (gate, chain, emu, ref)) + (round(cosine(g, r), 5),)
+    print("gradient at layer1's output vs forced emulation (trunk backward): rel L2 %.3g" % trunk_rel)
+    print("parameter gradients, rel L2 vs: forced emulation from layer1's output [GATED], forced whole chain, "
+          "free-running emulation, fp32 oracle; cosine vs fp32 oracle")
     for n, rep in report.items():
         print("   %-52s %s" % (n, rep))
+    assert trunk_rel <= tol, trunk_rel
     for n, rep in report.items():
-        bound = tiny_tol if (tiny_tol is not None and ref[n].numel() < 16) else tol
+        bound = tiny_tol if ref[n].numel() <= 256 else tol
         assert rep[0] <= bound, (n, rep)
     return report
 
@@ -208,7 +234,7 @@ def test_ghnd_step_matches_oracle_and_golden(env, oracle_step, oracle16_step, go
     params = dict(student.named_parameters())
     forced = forced_step(plan, env["t_sd"], env["s_sd"], small_images())
     check_grads({n: params[n].grad for n in oracle_step["grads"]}, oracle_step["grads"], oracle16_step["grads"],
-                forced["grads"])
+                forced)
     # BN running statistics after one training step (nn.BatchNorm2d momentum update)
     bufs = dict(student.named_buffers())
     for k, v in oracle_step["bn_update"].items():
@@ -255,7 +281,7 @@ def test_hnd_layer1_only(env):
     params = dict(student.named_parameters())
     emu = O16.distill_step16(env["t_sd"], env["s_sd"], small_images(), levels=("layer1",))
     forced = forced_step(list(box._plans.values())[0], env["t_sd"], env["s_sd"], small_images(), levels=("layer1",))
-    check_grads({n: params[n].grad for n in res["grads"]}, res["grads"], emu["grads"], forced["grads"])
+    check_grads({n: params[n].grad for n in res["grads"]}, res["grads"], emu["grads"], forced)
 
 
 def test_unshared_frozen_trunk(env):
@@ -277,7 +303,7 @@ def test_unshared_frozen_trunk(env):
     params = dict(student.named_parameters())
     emu = O16.distill_step16(env["t_sd"], s_sd, small_images())
     forced = forced_step(plan, env["t_sd"], s_sd, small_images())
-    check_grads({n: params[n].grad for n in res["grads"]}, res["grads"], emu["grads"], forced["grads"])
+    check_grads({n: params[n].grad for n in res["grads"]}, res["grads"], emu["grads"], forced)
 
 
 def test_shared_frozen_trunk_is_detected(env):
@@ -423,7 +449,7 @@ def test_layer1_module_eval_and_train(env):
     assert rel(xg.grad, gradsf[0]) <= 1e-2
     got = dict(layer.named_parameters())
     check_grads({n: got[n[len("backbone.body.layer1."):]].grad for n in names}, dict(zip(names, grads[1:])),
-                dict(zip(names, grads16[1:])), dict(zip(names, gradsf[1:])))
+                dict(zip(names, grads16[1:])), (dict(zip(names, gradsf[1:])), dict(zip(names, gradsf[1:])), 0.0))
 
 
 def test_keypoint_multi_scale_step(env):
@@ -472,7 +498,7 @@ def test_keypoint_multi_scale_step(env):
         got = {n: p.grad.detach().cpu() for n, p in student.named_parameters() if p.requires_grad}
         emu = O16.distill_step16(env["t_sd"], env["s_sd"], host, sizes=sizes, max_size=192)
         forced = forced_step(plan, env["t_sd"], env["s_sd"], host, sizes=sizes, max_size=192)
-        check_grads(got, ref["grads"], emu["grads"], forced["grads"])
+        check_grads(got, ref["grads"], emu["grads"], forced)
     assert len(shapes) == 4 and len(box._plans) == 3  # LRU: the oldest shape was evicted
 
 

@@ -82,7 +82,7 @@ def test_ghnd_step_at_800x1333_matches_oracle(env, batch):
         assert abs(term - float(ref["per_level"][lv])) <= 2e-3 * float(ref["per_level"][lv]), lv
     params = dict(student.named_parameters())
     forced = forced_step(plan, env["t_sd"], env["s_sd"], host)
-    check_grads({n: params[n].grad for n in ref["grads"]}, ref["grads"], emu["grads"], forced["grads"])
+    check_grads({n: params[n].grad for n in ref["grads"]}, ref["grads"], emu["grads"], forced)
 
 
 def test_rcnn_head_at_800x1333_batch2(env):
@@ -395,3 +395,28 @@ def test_neural_filter_head(env):
     enc.threshold = 2.0
     two = [im.cuda() for im in small_images()]
     assert head(two) is not None
+
+
+def test_graph_replay_with_side_stream_is_bit_reproducible(env):
+    """The teacher path has no atomics: every run must give bit-identical features, eager or as a CUDA
+    graph whose parallel branches (side stream) really overlap on the GPU.  Regression test for a
+    cross-proxy write-after-read on the conv kernel's epilogue-operand ring (generic-proxy reads of the
+    residual tile vs the async-proxy TMA refill): a few 64-channel rows of the "+res" 1x1 convs came out
+    corrupted in graph mode only, invisible in the loss (2e-5) and found by the 800x1333 parity test."""
+    from hnd_ghnd_object_detectors_b200.tool import DistillationBox
+    images = [im.cuda() for im in full_images(1)]
+    ref = None
+    for graph in (False, True):
+        teacher, student = build_full_pair(env)
+        box = DistillationBox(teacher, student, criterion_config(), use_cuda_graph=graph)
+        for it in range(5):
+            box(images, targets_for(images))
+            torch.cuda.synchronize()
+            plan = list(box._plans.values())[0]
+            cur = {lv: plan.feat_t[lv].clone() for lv in plan.levels}
+            cur.update({"t.l1.%d" % b: blk.out.clone() for b, blk in enumerate(plan.t_layers["layer1"].blocks)})
+            if ref is None:
+                ref = cur
+            for k in ref:
+                assert torch.equal(cur[k], ref[k]), (graph, it, k, int((cur[k] != ref[k]).sum()))
+        del box
