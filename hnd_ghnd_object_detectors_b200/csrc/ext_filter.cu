@@ -124,8 +124,8 @@ using namespace ghnd;
 int ghnd_adaptive_avgpool_nhwc16(const void* x, int fmt, int N, int H, int W, int C, float* y, int OH, int OW,
                                  void* stream) {
   GHND_CHECK_ARG(x && y && (fmt == GHND_F16 || fmt == GHND_BF16), "adaptive_avgpool: bad argument");
-  GHND_CHECK_ARG(N > 0 && N <= 65535 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && OH > 0 && OW > 0 && OH <= H &&
-                     OW <= W,
+  // OH > H (the pool up-samples a small map by repeating bins) is legal in nn.AdaptiveAvgPool2d too
+  GHND_CHECK_ARG(N > 0 && N <= 65535 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && OH > 0 && OW > 0,
                  "adaptive_avgpool: bad geometry N=%d %dx%d C=%d -> %dx%d", N, H, W, C, OH, OW);
   dim3 grid((unsigned)OH, (unsigned)N);
   if (fmt == GHND_F16)
@@ -162,7 +162,7 @@ int ghnd_small_conv_f32(const float* x, const float* w_rsck, const float* scale,
 int ghnd_avgpool_linear(const float* x, int N, int H, int W, int C, int OH, int OW, const float* lw, const float* lb,
                         int n_out, int softmax, float* out, void* stream) {
   GHND_CHECK_ARG(x && lw && out, "avgpool_linear: null argument");
-  GHND_CHECK_ARG(N > 0 && H > 0 && W > 0 && C > 0 && OH > 0 && OW > 0 && OH <= H && OW <= W && n_out > 0 && n_out <= 64,
+  GHND_CHECK_ARG(N > 0 && H > 0 && W > 0 && C > 0 && OH > 0 && OW > 0 && n_out > 0 && n_out <= 64,
                  "avgpool_linear: bad geometry");
   const size_t smem = ((size_t)C * OH * OW + n_out) * sizeof(float);
   GHND_CHECK_ARG(smem <= 48 * 1024, "avgpool_linear: %zu bytes of pooled features exceed shared memory", smem);

@@ -173,20 +173,23 @@ __global__ void __launch_bounds__(kQThreads)
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
   int64_t done = 0;
   if (vec_ok) {
-    const int64_t n16 = n >> 4;
+    // lane-contiguous accesses: a warp reads 512 contiguous bytes per load instruction and writes 128
+    // contiguous bytes per store (the first version gave every lane its own 64-byte run: each 32-byte
+    // sector was requested by two different instructions and, with L1 allocation off, fetched twice)
+    const int64_t n4 = n >> 2;
     const uint4* x4 = reinterpret_cast<const uint4*>(x);
-    uint4* q16 = reinterpret_cast<uint4*>(q);
-    for (int64_t i = tid; i < n16; i += nthreads) {
-      uint4 a = ld_stream(x4 + 4 * i), b = ld_stream(x4 + 4 * i + 1), c = ld_stream(x4 + 4 * i + 2),
-            d = ld_stream(x4 + 4 * i + 3);
-      uint4 o;
-      o.x = quant4(a, qf);
-      o.y = quant4(b, qf);
-      o.z = quant4(c, qf);
-      o.w = quant4(d, qf);
-      st_stream(q16 + i, o);
+    uint32_t* q4 = reinterpret_cast<uint32_t*>(q);
+    int64_t i = tid;
+    for (; i + 3 * nthreads < n4; i += 4 * nthreads) {
+      const uint4 a = ld_stream(x4 + i), b = ld_stream(x4 + i + nthreads), c = ld_stream(x4 + i + 2 * nthreads),
+                  d = ld_stream(x4 + i + 3 * nthreads);
+      q4[i] = quant4(a, qf);
+      q4[i + nthreads] = quant4(b, qf);
+      q4[i + 2 * nthreads] = quant4(c, qf);
+      q4[i + 3 * nthreads] = quant4(d, qf);
     }
-    done = n16 << 4;
+    for (; i < n4; i += nthreads) q4[i] = quant4(ld_stream(x4 + i), qf);
+    done = n4 << 2;
   }
   for (int64_t i = done + tid; i < n; i += nthreads) q[i] = (uint8_t)quant1(x[i], zpf, scale, qmax);
 }
@@ -320,23 +323,25 @@ __global__ void __launch_bounds__(kQThreads)
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
   int64_t done = 0;
   if (vec_ok) {
-    const int64_t n16 = n >> 4;
-    const uint4* q16 = reinterpret_cast<const uint4*>(q);
+    // lane-contiguous: a warp reads 128 contiguous bytes and writes 512 contiguous bytes per instruction
+    const int64_t n4 = n >> 2;
+    const uint32_t* q4 = reinterpret_cast<const uint32_t*>(q);
     uint4* o4 = reinterpret_cast<uint4*>(out);
-    for (int64_t i = tid; i < n16; i += nthreads) {
-      uint4 v = ld_stream(q16 + i);
-      uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint4 o;
-        o.x = __float_as_uint(dq(w[j] & 0xff));
-        o.y = __float_as_uint(dq((w[j] >> 8) & 0xff));
-        o.z = __float_as_uint(dq((w[j] >> 16) & 0xff));
-        o.w = __float_as_uint(dq(w[j] >> 24));
-        st_stream(o4 + 4 * i + j, o);
-      }
+    auto dq4 = [&](uint32_t w) -> uint4 {
+      return make_uint4(__float_as_uint(dq(w & 0xff)), __float_as_uint(dq((w >> 8) & 0xff)),
+                        __float_as_uint(dq((w >> 16) & 0xff)), __float_as_uint(dq(w >> 24)));
+    };
+    int64_t i = tid;
+    for (; i + 3 * nthreads < n4; i += 4 * nthreads) {
+      const uint32_t a = __ldg(q4 + i), b = __ldg(q4 + i + nthreads), c = __ldg(q4 + i + 2 * nthreads),
+                     d = __ldg(q4 + i + 3 * nthreads);
+      st_stream(o4 + i, dq4(a));
+      st_stream(o4 + i + nthreads, dq4(b));
+      st_stream(o4 + i + 2 * nthreads, dq4(c));
+      st_stream(o4 + i + 3 * nthreads, dq4(d));
     }
-    done = n16 << 4;
+    for (; i < n4; i += nthreads) st_stream(o4 + i, dq4(__ldg(q4 + i)));
+    done = n4 << 2;
   }
   for (int64_t i = done + tid; i < n; i += nthreads) out[i] = dq(q[i]);
 }

@@ -372,6 +372,7 @@ def test_neural_filter_head(env):
     model.eval()
     assert model.get_ext_classifier() is model.backbone.body.layer1.encoder.ext_classifier
     head, tail = split_rcnn_model(model, 8)
+    tail.eval()
     from tests.golden.make_golden import small_images
     img = [small_images()[0].cuda()]
     enc = model.backbone.body.layer1.encoder
