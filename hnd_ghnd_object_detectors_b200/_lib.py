@@ -14,7 +14,8 @@ CONV_FWD, CONV_DGRAD = 0, 1
 SSE_MAX_LEVELS = 8
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "libghnd_b200.so")
+# GHND_LIB_PATH: load another build of the same ABI (same-box A/B of kernel changes; scripts/gpu.sh ab)
+LIB_PATH = os.environ.get("GHND_LIB_PATH") or os.path.join(_PKG_DIR, "libghnd_b200.so")
 
 
 class GhndError(RuntimeError):

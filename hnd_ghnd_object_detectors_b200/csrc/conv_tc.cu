@@ -40,6 +40,7 @@ static constexpr int kBlockM = 128;
 static constexpr int kMaxTaps = 9;
 static constexpr int kMaxStages = 8;
 static constexpr int kMaxRing = 4;
+static constexpr int kMaxASlots = 4;
 static constexpr int kChunkBytes = kBlockM * 128;  // one [128 rows][64 ch] 16-bit staging tile
 // GEMM-K per "unit": 64 x 16-bit = 128 B rows (SWIZZLE_128B) for the wide convs, or
 // 32 x 16-bit = 64 B rows (SWIZZLE_64B) for the stem whose im2col row is 7 px x 4 ch (+4 zero).
@@ -99,6 +100,17 @@ struct ConvKernelParams {
   int epi_prefetch; // issue the next chunk's tcgen05.ld as soon as the current chunk is staged
   int epi_bufs;     // output staging tiles per epilogue group (2: the TMA store of chunk i drains
                     // while chunk i+1 is staged)
+  // conv "halo" mode (MODE 2; stride-1 convs with more than one tap): per 64-channel chunk ONE dense TMA
+  // box of (th+R-1) x (tw+S-1) pixels; every tap is an MMA descriptor at a row shift of that tile
+  // (tw == 8: one 8-row swizzle group per output row, group stride = halo row pitch).  Cuts the
+  // L2 -> shared-memory traffic of the A operand by n_taps x (th*tw)/(halo pixels): 3.3x for 2x2, 6.2x for
+  // 3x3.  b_resident: the whole weight slab of this CTA's n-tile stays in shared memory.
+  int a_halo_bytes;   // halo tile bytes rounded up to 1024
+  int a_slots;        // depth of the halo ring
+  int halo_w;         // halo row pitch in pixels (tw + S - 1)
+  int org_dh, org_dw; // offset of the halo box origin from the tile origin
+  int tap_off[kMaxTaps];  // byte offset of tap t's first row inside the halo tile
+  int b_resident;
 };
 
 __device__ __forceinline__ int fd_ring_r(const ConvKernelParams& p, uint32_t cnt) {
@@ -180,6 +192,14 @@ __device__ __forceinline__ void umma_unit2_ab(uint32_t d_tmem, uint32_t a_lo, ui
       "}\n" ::"r"(d_tmem),
       "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+
+// Four K=16 steps (one 64-channel unit) with separate high words for A and B.
+__device__ __forceinline__ void umma_unit4_ab(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi,
+                                              uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                              uint32_t accumulate) {
+  umma_unit2_ab(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
+  umma_unit2_ab(d_tmem, a_lo + 4, a_hi, b_lo + 4, b_hi, idesc, 1u);
 }
 
 // v[0..63] += the 64 channels of `row` of a swizzled 16-bit operand tile
@@ -381,16 +401,23 @@ __device__ __forceinline__ void epi_stage_packed(const uint32_t* h, uint8_t* sta
 // sensitive to code size (a build with all variants in one 7.2k-instruction kernel lost 10-20 % on
 // the epilogue-bound layers against a 5.1k-instruction build, same algorithm).
 // STATS: the launch accumulates per-channel statistics (kept out of the other instantiations)
-template <int EPI, bool HALO, bool STATS>
+template <int EPI, int MODE, bool STATS>
 __global__ void __launch_bounds__(kConvThreads, 1)
     conv_tc_kernel(const __grid_constant__ ConvKernelParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  // 1024-byte alignment for the 128B swizzle atoms
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~(uintptr_t)1023);
+  constexpr bool HALO = MODE == 1;   // stem halo mode
+  constexpr bool CHALO = MODE == 2;  // conv halo mode
+  // 1024-byte alignment for the 128B swizzle atoms comes from the declaration; every pointer below is
+  // derived from this array by plain arithmetic so that ptxas keeps the accesses in the shared state
+  // space (LDS / STS).  The first version rounded the base up through uintptr_t: the casts hid the
+  // address space and EVERY epilogue access became a generic LD.E / ST.E (ncu source page, round 2).
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if (smem_u32(smem_raw) & 1023u) __trap();
   const int n_in = p.has_in0 + p.has_in1;
-  uint8_t* wres = smem + (size_t)p.n_stages * p.stage_bytes;               // halo mode: resident weights
-  uint8_t* epi_out = wres + (HALO ? p.w_res_bytes : 0);                  // [2 groups][kChunkBytes]
+  // MODE 2: [a_slots halo tiles] precede the (B-only) pipeline stages / the resident weights
+  uint8_t* stages0 = smem + (CHALO ? (size_t)p.a_slots * p.a_halo_bytes : 0);
+  uint8_t* wres = stages0 + (size_t)p.n_stages * p.stage_bytes;            // halo modes: resident weights
+  uint8_t* epi_out = wres + ((HALO || CHALO) ? p.w_res_bytes : 0);       // [2 groups][kChunkBytes]
   uint8_t* epi_in = epi_out + (size_t)2 * p.epi_bufs * kChunkBytes;        // [ring][n_in][kChunkBytes]
   float* sbias = reinterpret_cast<float*>(epi_in + (size_t)p.ring * n_in * kChunkBytes);  // [cout]
   float* sstat = sbias + (p.bias != nullptr ? p.cout : 0);                 // [8 epilogue warps][2*cout] when stats
@@ -401,8 +428,10 @@ __global__ void __launch_bounds__(kConvThreads, 1)
   uint64_t* tempty_bar = tfull_bar + 2;             // [2]
   uint64_t* ifull_bar = tempty_bar + 2;             // [kMaxRing]
   uint64_t* iempty_bar = ifull_bar + kMaxRing;      // [kMaxRing]
-  uint64_t* wfull_bar = iempty_bar + kMaxRing;      // [1] resident weights have landed (halo mode)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull_bar + 1);
+  uint64_t* wfull_bar = iempty_bar + kMaxRing;      // [1] resident weights have landed (halo modes)
+  uint64_t* afull_bar = wfull_bar + 1;              // [kMaxASlots] conv halo tiles
+  uint64_t* aempty_bar = afull_bar + kMaxASlots;    // [kMaxASlots]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty_bar + kMaxASlots);
 
   // warp index through a shuffle so that the compiler treats the role branches as warp-uniform
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -425,6 +454,10 @@ __global__ void __launch_bounds__(kConvThreads, 1)
       mbar_init(&iempty_bar[i], kEpiGroupThreads);
     }
     mbar_init(wfull_bar, 1);
+    for (int i = 0; i < kMaxASlots; ++i) {
+      mbar_init(&afull_bar[i], 1);
+      mbar_init(&aempty_bar[i], 1);
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -509,7 +542,127 @@ __global__ void __launch_bounds__(kConvThreads, 1)
         phase ^= 1;
       }
     }
-  } else if (!HALO && warp == 0) {
+  } else if (CHALO && warp == 0) {
+    // ===================== TMA producer, conv halo mode ==========================================
+    // per tile and 64-channel chunk: one halo box; then (unless the weights are resident) this chunk's
+    // B tiles, tap by tap, through the stage ring.  Loads are issued in the order the MMA warp consumes.
+    const int n_tile0 = (int)blockIdx.x - fd_div(p.fd_tiles_n, (int)blockIdx.x) * (int)p.fd_tiles_n.d;
+    if (p.b_resident) {
+      if (elect_one()) {
+        mbar_arrive_expect_tx(wfull_bar, (uint32_t)p.w_res_bytes);
+        for (int t = 0; t < p.n_taps; ++t)
+          for (int kc = 0; kc < k_chunks; ++kc)
+            tma_load_2d(wres + (size_t)(t * k_chunks + kc) * p.b_bytes, &p.tmap_b, wfull_bar,
+                        p.taps[t].wk * p.cin + kc * p.kblock, n_tile0 * p.block_n);
+      }
+      __syncwarp();
+    }
+    int stage = 0, aslot = 0;
+    uint32_t phase = 0, aphase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      int n_tile, m_tile, img, rem, h0, w0;
+      fd_divmod(p.fd_tiles_n, tile, m_tile, n_tile);
+      fd_divmod(p.fd_tiles_per_img, m_tile, img, rem);
+      fd_divmod(p.fd_tiles_w, rem, h0, w0);
+      h0 *= p.th;
+      w0 *= p.tw;
+      for (int kc = 0; kc < k_chunks; ++kc) {
+        mbar_wait(&aempty_bar[aslot], aphase ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&afull_bar[aslot], (uint32_t)p.a_box_bytes);
+          tma_load_4d(smem + (size_t)aslot * p.a_halo_bytes, &p.tmap_a[0], &afull_bar[aslot], kc * p.kblock,
+                      w0 + p.org_dw, h0 + p.org_dh, img);
+        }
+        __syncwarp();
+        if (++aslot == p.a_slots) {
+          aslot = 0;
+          aphase ^= 1;
+        }
+        if (!p.b_resident) {
+          for (int t0 = 0; t0 < p.n_taps; t0 += upst) {
+            const int nu = min(upst, p.n_taps - t0);
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (elect_one()) {
+              uint8_t* sb = stages0 + (size_t)stage * p.stage_bytes;
+              mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(nu * p.b_bytes));
+              for (int j = 0; j < nu; ++j)
+                tma_load_2d(sb + j * p.b_bytes, &p.tmap_b, &full_bar[stage],
+                            p.taps[t0 + j].wk * p.cin + kc * p.kblock, n_tile * p.block_n);
+            }
+            __syncwarp();
+            if (++stage == p.n_stages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (CHALO && warp == 1) {
+    // ===================== MMA issuer, conv halo mode ============================================
+    // tap (r, s) reads the chunk's halo tile at a shift of (r * halo_w + s) rows of 128 B; output row i of
+    // the th x 8 tile is the 8-row group i, groups are halo_w rows apart (SBO of A).
+    int stage = 0, aslot = 0, it = 0;
+    uint32_t phase = 0, aphase = 0;
+    const uint32_t a_base = smem_u32(smem), s_base = smem_u32(stages0), w_base = smem_u32(wres);
+    const uint32_t a_hi = (((uint32_t)p.halo_w * 128u) >> 4) | (1u << 14) | ((uint32_t)UMMA_SW128 << 29);
+    const uint32_t b_hi = (1024u >> 4) | (1u << 14) | ((uint32_t)UMMA_SW128 << 29);
+    if (p.b_resident) {
+      mbar_wait(wfull_bar, 0);
+      tc_fence_after();
+    }
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      mbar_wait(&tempty_bar[buf], (((uint32_t)it >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.block_n);
+      for (int kc = 0; kc < k_chunks; ++kc) {
+        mbar_wait(&afull_bar[aslot], aphase);
+        tc_fence_after();
+        const uint32_t a_tile = a_base + (uint32_t)(aslot * p.a_halo_bytes);
+        if (p.b_resident) {
+          if (elect_one()) {
+            for (int t = 0; t < p.n_taps; ++t) {
+              const uint32_t a_lo = (((a_tile + (uint32_t)p.tap_off[t]) >> 4) & 0x3fffu) | (1u << 16);
+              const uint32_t b_lo =
+                  (((w_base + (uint32_t)((t * k_chunks + kc) * p.b_bytes)) >> 4) & 0x3fffu) | (1u << 16);
+              umma_unit4_ab(d_tmem, a_lo, a_hi, b_lo, b_hi, p.idesc, (uint32_t)((kc | t) != 0));
+            }
+            umma_commit(&aempty_bar[aslot]);
+          }
+          __syncwarp();
+        } else {
+          for (int t0 = 0; t0 < p.n_taps; t0 += upst) {
+            const int nu = min(upst, p.n_taps - t0);
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t sb = s_base + (uint32_t)(stage * p.stage_bytes);
+              for (int j = 0; j < nu; ++j) {
+                const int t = t0 + j;
+                const uint32_t a_lo = (((a_tile + (uint32_t)p.tap_off[t]) >> 4) & 0x3fffu) | (1u << 16);
+                const uint32_t b_lo = (((sb + (uint32_t)(j * p.b_bytes)) >> 4) & 0x3fffu) | (1u << 16);
+                umma_unit4_ab(d_tmem, a_lo, a_hi, b_lo, b_hi, p.idesc, (uint32_t)((kc | t) != 0));
+              }
+              umma_commit(&empty_bar[stage]);
+              if (t0 + nu >= p.n_taps) umma_commit(&aempty_bar[aslot]);
+            }
+            __syncwarp();
+            if (++stage == p.n_stages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+        if (++aslot == p.a_slots) {
+          aslot = 0;
+          aphase ^= 1;
+        }
+      }
+      if (elect_one()) umma_commit(&tfull_bar[buf]);  // accumulator complete -> epilogue
+      __syncwarp();
+    }
+  } else if (!HALO && !CHALO && warp == 0) {
     // ===================== TMA producer (whole warp converged, one elected lane issues) ==========
     int stage = 0;
     uint32_t phase = 0;
@@ -554,7 +707,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
         }
       }
     }
-  } else if (!HALO && warp == 1) {
+  } else if (!HALO && !CHALO && warp == 1) {
     // ===================== MMA issuer (whole warp converged, one elected lane issues) ============
     int stage = 0;
     uint32_t phase = 0;
@@ -878,6 +1031,9 @@ struct ConvLaunch {
   ConvKernelParams p;
   int grid;
   size_t smem;
+  // A-operand source tensor [src_n][src_h][src_w][gemm_cin] (conv halo mode re-encodes its tensor map)
+  const void* src;
+  int src_n, src_h, src_w;
 };
 
 }  // namespace ghnd
@@ -923,7 +1079,7 @@ static int make_lattice_map(CUtensorMap* m, const void* base, int N, int H, int 
   return encode_tmap(m, 2, 4, const_cast<uint8_t*>(b), dims, str, box, inner * 2);
 }
 
-static const int kSmemBudget = 227 * 1024 - 1024 /*align*/ - 512 /*barriers + tmem slot*/;
+static const int kSmemBudget = 227 * 1024 - 512 /*barriers + tmem slot*/;  // aligned by declaration: no slack
 
 // Tile-N choice from a cost model fitted to a forced-block_n sweep of every conv of the GHND step
 // on B200 (scripts/gpu_bn_sweep.sh, profiles/r1_summary.md): a launch is bound by the slowest of
@@ -992,9 +1148,125 @@ struct IoGeom {
 
 // Shared-memory plan of one launch: [stages][2 staging tiles][operand ring][bias][stats][barriers].
 
+// Conv halo mode planning (after the generic fields are set): returns true when the launch was switched
+// to MODE 2.  Requires stride-1 taps on ONE view, th x 8 tiles, a packed epilogue.
+static bool plan_conv_halo(ConvLaunch* L, const ghnd_conv_desc_t* d, int gemm_cin, int gemm_cout, int n_in,
+                           int fixed_no_stages) {
+  ConvKernelParams& p = L->p;
+  static const bool off = [] {
+    const char* e = getenv("GHND_CONV_HALO");
+    return e != nullptr && atoi(e) == 0;
+  }();
+  if (off || p.n_taps < 2 || p.tw != 8 || p.kblock != 64 || p.epi_half == 0) return false;
+  int dh0 = p.taps[0].dh, dh1 = dh0, dw0 = p.taps[0].dw, dw1 = dw0;
+  for (int t = 0; t < p.n_taps; ++t) {
+    if (p.taps[t].map != 0) return false;
+    dh0 = p.taps[t].dh < dh0 ? p.taps[t].dh : dh0;
+    dh1 = p.taps[t].dh > dh1 ? p.taps[t].dh : dh1;
+    dw0 = p.taps[t].dw < dw0 ? p.taps[t].dw : dw0;
+    dw1 = p.taps[t].dw > dw1 ? p.taps[t].dw : dw1;
+  }
+  const int hh = p.th + (dh1 - dh0), hw = p.tw + (dw1 - dw0);
+  if (hw > 256 || hh > 256) return false;
+  const int k_chunks = gemm_cin / 64;
+  const int a_box = hh * hw * 128;
+  const int a_halo = (a_box + 1023) / 1024 * 1024;
+  // tile width: the largest N whose whole weight slab stays resident next to two halo tiles; else the
+  // cost model's N with the weights streamed tap by tap
+  const int ring_bytes = p.ring * n_in * kChunkBytes;
+  const int avail = kSmemBudget - fixed_no_stages - (n_in > 0 ? ring_bytes : 0);
+  int bn_res = 0;
+  for (int bn = 256; bn >= 64; bn >>= 1) {
+    if (gemm_cout % bn != 0) continue;
+    if (p.n_taps * k_chunks * bn * 128 + 2 * a_halo <= avail) {
+      bn_res = bn;
+      break;
+    }
+  }
+  if (const char* force = getenv("GHND_BLOCK_N")) {
+    const int bn = atoi(force);
+    if ((bn == 64 || bn == 128 || bn == 256) && gemm_cout % bn == 0)
+      bn_res = (p.n_taps * k_chunks * bn * 128 + 2 * a_halo <= avail) ? bn : 0, p.block_n = bn;
+  }
+  static const bool no_res = getenv("GHND_CONV_HALO_NO_RESIDENT") != nullptr;  // A/B switch
+  if (no_res) bn_res = 0;
+  // Measured on the B200 (profiles/r2_summary.md): the mode pays when the weights are resident and the CTA
+  // keeps (nearly) the whole output width -- the small-C convs whose shared-memory ingest was dominated by
+  // re-fetched weights and 4x / 9x re-fetched pixels (3x3 C64->K64 -27 %, 2x2 C256->K64 -24 %, its dgrad
+  // -22 %, 3x3 C128->K128 -12 %).  It LOSES on the deep convs: with the weights streamed the 16x8 tiling
+  // (74 % full on a 50x84 map, one more wave) costs more than the saved A traffic (3x3 C256->K256 +44 %),
+  // and a resident slab that forces four N=64 tiles per pixel block leaves only two halo slots in flight
+  // (2x2 C256->K256 +44 %).  GHND_CONV_HALO_ALL=1 lifts the restriction (A/B switch).
+  static const bool halo_all = getenv("GHND_CONV_HALO_ALL") != nullptr;
+  if (!halo_all && (bn_res == 0 || gemm_cout / bn_res > 2)) return false;
+  if (bn_res) p.block_n = bn_res;
+  p.b_bytes = p.block_n * 128;
+  p.n_tiles_n = gemm_cout / p.block_n;
+  const int m_tiles = p.n_img * p.tiles_h * p.tiles_w;
+  p.total_tiles = m_tiles * p.n_tiles_n;
+  p.fd_tiles_n = make_fastdiv(p.n_tiles_n);
+  p.idesc = make_idesc(d->src_fmt, d->w_fmt, 0, 0, kBlockM, p.block_n);
+  // the weight map's box follows block_n
+  {
+    const int total_taps = d->R * d->S;
+    uint64_t dims[2] = {(uint64_t)total_taps * gemm_cin, (uint64_t)gemm_cout};
+    uint64_t str[2] = {2, (uint64_t)total_taps * gemm_cin * 2};
+    uint32_t box[2] = {64u, (uint32_t)p.block_n};
+    if (encode_tmap(&p.tmap_b, 2, 2, const_cast<void*>(d->weights), dims, str, box, 128) != GHND_OK) return false;
+  }
+  {  // A: one dense box of hh x hw pixels x 64 channels (out-of-bounds rows / columns zero-filled)
+    uint64_t dims[4] = {(uint64_t)gemm_cin, (uint64_t)L->src_w, (uint64_t)L->src_h, (uint64_t)L->src_n};
+    uint64_t str[4] = {2, (uint64_t)gemm_cin * 2, (uint64_t)L->src_w * gemm_cin * 2,
+                       (uint64_t)L->src_h * L->src_w * gemm_cin * 2};
+    uint32_t box[4] = {64u, (uint32_t)hw, (uint32_t)hh, 1u};
+    if (encode_tmap(&p.tmap_a[0], 2, 4, const_cast<void*>(L->src), dims, str, box, 128) != GHND_OK) return false;
+    for (int i = 1; i < 4; ++i) p.tmap_a[i] = p.tmap_a[0];
+  }
+  p.a_box_bytes = a_box;
+  p.a_halo_bytes = a_halo;
+  p.halo_w = hw;
+  p.org_dh = dh0;
+  p.org_dw = dw0;
+  for (int t = 0; t < p.n_taps; ++t) p.tap_off[t] = ((p.taps[t].dh - dh0) * hw + (p.taps[t].dw - dw0)) * 128;
+  int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  if (bn_res) {
+    p.b_resident = 1;
+    p.w_res_bytes = p.n_taps * k_chunks * p.b_bytes;
+    p.n_stages = 0;
+    p.stage_bytes = 0;
+    p.units_per_stage = 1;
+    int slots = (avail - p.w_res_bytes) / a_halo;
+    p.a_slots = slots > kMaxASlots ? kMaxASlots : slots;
+    grid -= grid % p.n_tiles_n;  // every CTA keeps ONE n-tile (its resident weights)
+    if (grid < p.n_tiles_n) return false;
+  } else {
+    p.b_resident = 0;
+    p.w_res_bytes = 0;
+    // >= ~256 tensor-pipe cycles of B per stage, at most all taps of a chunk
+    const int unit_cycles = 4 * (p.block_n / 2);
+    int u = (256 + unit_cycles - 1) / unit_cycles;
+    if (u > p.n_taps) u = p.n_taps;
+    if (u < 1) u = 1;
+    p.units_per_stage = u;
+    p.stage_bytes = u * p.b_bytes;
+    p.a_slots = k_chunks >= 2 ? 3 : 2;
+    int stages = (avail - p.a_slots * a_halo) / p.stage_bytes;
+    if (stages < 2) {
+      p.a_slots = 2;
+      stages = (avail - p.a_slots * a_halo) / p.stage_bytes;
+    }
+    if (stages < 2) return false;
+    p.n_stages = stages > kMaxStages ? kMaxStages : stages;
+  }
+  L->grid = grid;
+  L->smem = (size_t)p.a_slots * a_halo + (size_t)p.n_stages * p.stage_bytes + (size_t)p.w_res_bytes +
+            (size_t)fixed_no_stages + (size_t)(n_in > 0 ? ring_bytes : 0) + 512;
+  return true;
+}
+
 static int finish_launch(ConvLaunch* L, const ghnd_conv_desc_t* d, int gemm_cin, int gemm_cout,
                          const void* weights, int total_taps, const IoGeom& g, int kblock = 64,
-                         int force_block_n = 0) {
+                         int force_block_n = 0, bool try_halo = false) {
   ConvKernelParams& p = L->p;
   p.cin = gemm_cin;
   p.cout = gemm_cout;
@@ -1135,7 +1407,10 @@ static int finish_launch(ConvLaunch* L, const ghnd_conv_desc_t* d, int gemm_cin,
   p.n_stages = stages;
   L->grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   L->smem = (size_t)p.n_stages * p.stage_bytes + (size_t)fixed + (size_t)ring * n_in * kChunkBytes +
-            1024 /*align*/ + 512 /*barriers*/;
+            512 /*barriers*/;
+  p.a_halo_bytes = 0;
+  p.b_resident = 0;
+  if (try_halo) plan_conv_halo(L, d, gemm_cin, gemm_cout, n_in, fixed);
   return GHND_OK;
 }
 
@@ -1155,15 +1430,20 @@ static cudaError_t launch_conv(const ConvLaunch& L, cudaStream_t st) {
   static const bool no_pdl = getenv("GHND_NO_PDL") != nullptr;  // debugging switch
   cfg.attrs = attr;
   cfg.numAttrs = no_pdl ? 0 : 1;
-  if (L.p.epi_half == 1) {
-    if (L.p.halo) return cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, true, false>, L.p);  // stem: no stats
-    if (L.p.stats != nullptr) return cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, false, true>, L.p);
-    return cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, false, false>, L.p);
+  if (L.p.a_halo_bytes > 0) {  // conv halo mode (MODE 2): packed epilogues only
+    if (L.p.epi_half == 2) return cudaLaunchKernelEx(&cfg, conv_tc_kernel<2, 2, false>, L.p);
+    if (L.p.stats != nullptr) return cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, 2, true>, L.p);
+    return cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, 2, false>, L.p);
   }
-  if (L.p.epi_half == 2 && !L.p.halo) return cudaLaunchKernelEx(&cfg, conv_tc_kernel<2, false, false>, L.p);
-  if (L.p.halo) return cudaLaunchKernelEx(&cfg, conv_tc_kernel<0, true, false>, L.p);
-  if (L.p.stats != nullptr) return cudaLaunchKernelEx(&cfg, conv_tc_kernel<0, false, true>, L.p);
-  return cudaLaunchKernelEx(&cfg, conv_tc_kernel<0, false, false>, L.p);
+  if (L.p.epi_half == 1) {
+    if (L.p.halo) return cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, 1, false>, L.p);  // stem: no stats
+    if (L.p.stats != nullptr) return cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, 0, true>, L.p);
+    return cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, 0, false>, L.p);
+  }
+  if (L.p.epi_half == 2 && !L.p.halo) return cudaLaunchKernelEx(&cfg, conv_tc_kernel<2, 0, false>, L.p);
+  if (L.p.halo) return cudaLaunchKernelEx(&cfg, conv_tc_kernel<0, 1, false>, L.p);
+  if (L.p.stats != nullptr) return cudaLaunchKernelEx(&cfg, conv_tc_kernel<0, 0, true>, L.p);
+  return cudaLaunchKernelEx(&cfg, conv_tc_kernel<0, 0, false>, L.p);
 }
 
 static bool fmt_ok(int f) { return f == GHND_F16 || f == GHND_BF16; }
@@ -1176,13 +1456,16 @@ static int set_conv_attr() {
   if (e == cudaSuccess)                                                                           \
     e = cudaFuncSetAttribute(conv_tc_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                              227 * 1024)
-    GHND_SET_SMEM(0, false, false);
-    GHND_SET_SMEM(0, false, true);
-    GHND_SET_SMEM(0, true, false);
-    GHND_SET_SMEM(1, false, false);
-    GHND_SET_SMEM(1, false, true);
-    GHND_SET_SMEM(1, true, false);
-    GHND_SET_SMEM(2, false, false);
+    GHND_SET_SMEM(0, 0, false);
+    GHND_SET_SMEM(0, 0, true);
+    GHND_SET_SMEM(0, 1, false);
+    GHND_SET_SMEM(1, 0, false);
+    GHND_SET_SMEM(1, 0, true);
+    GHND_SET_SMEM(1, 1, false);
+    GHND_SET_SMEM(2, 0, false);
+    GHND_SET_SMEM(1, 2, false);
+    GHND_SET_SMEM(1, 2, true);
+    GHND_SET_SMEM(2, 2, false);
 #undef GHND_SET_SMEM
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_tc_kernel)");
     attr_set = true;
@@ -1243,10 +1526,13 @@ int ghnd_conv_plan_create(const ghnd_conv_desc_t* d, ghnd_conv_plan_t** out) {
   const int taps_total = d->R * d->S;
 
   if (d->kind == GHND_CONV_FWD) {
+   bool halo_failed = false;
+   for (int pass = 0; pass < 2; ++pass) {  // pass 0 tries the conv halo geometry, pass 1 is the generic tiling
     ConvLaunch L;
     memset(&L, 0, sizeof(L));
     ConvKernelParams& p = L.p;
     IoGeom g;
+    bool want_halo = false;
     const bool flat = (d->R == 1 && d->S == 1 && d->stride == 1 && d->pad == 0);
     if (flat) {
       const int64_t npix = (int64_t)d->N * d->H * d->W;
@@ -1263,6 +1549,12 @@ int ghnd_conv_plan_create(const ghnd_conv_desc_t* d, ghnd_conv_plan_t** out) {
     } else {
       p.n_img = d->N;
       choose_tile(Ho, Wo, &p.th, &p.tw);
+      // conv halo mode (stride 1, several taps): th x 8 tiles, see plan_conv_halo
+      want_halo = d->stride == 1 && taps_total > 1 && Wo >= 8 && Ho >= 4;
+      if (want_halo && !halo_failed) {
+        p.th = Ho < 16 ? Ho : 16;
+        p.tw = 8;
+      }
       p.tiles_h = (Ho + p.th - 1) / p.th;
       p.tiles_w = (Wo + p.tw - 1) / p.tw;
       g = IoGeom{d->N, Ho, Wo, 1, 1, 0, 0};
@@ -1291,16 +1583,29 @@ int ghnd_conv_plan_create(const ghnd_conv_desc_t* d, ghnd_conv_plan_t** out) {
         }
       p.n_taps = nt;
     }
-    if (rc == GHND_OK) rc = finish_launch(&L, d, d->C, d->K, d->weights, taps_total, g);
+    L.src = d->src;
+    L.src_n = d->N;
+    L.src_h = d->H;
+    L.src_w = d->W;
+    const bool try_halo = want_halo && !halo_failed;
+    if (rc == GHND_OK) rc = finish_launch(&L, d, d->C, d->K, d->weights, taps_total, g, 64, 0, try_halo);
+    if (rc == GHND_OK && try_halo && L.p.a_halo_bytes == 0) {
+      halo_failed = true;  // not eligible (epilogue kind / shared memory): rebuild with the generic tiling
+      continue;
+    }
     if (rc == GHND_OK) plan->launches.push_back(L);
+    break;
+   }
   } else {
     // DGRAD: src = dy [N,Ho,Wo,K], dst = dx [N,H,W,C], weights [C][R][S][K]
     const int sub = d->stride;
+    bool halo_failed = false;
     for (int ph = 0; ph < sub && rc == GHND_OK; ++ph) {
       for (int pw = 0; pw < sub && rc == GHND_OK; ++pw) {
         ConvLaunch L;
         memset(&L, 0, sizeof(L));
         ConvKernelParams& p = L.p;
+        bool want_halo = false;
         // dx rows h = sub*i + ph, i in [0, hi)
         const int hi = (d->H - ph + sub - 1) / sub;
         const int wi = (d->W - pw + sub - 1) / sub;
@@ -1336,13 +1641,30 @@ int ghnd_conv_plan_create(const ghnd_conv_desc_t* d, ghnd_conv_plan_t** out) {
         } else {
           p.n_img = d->N;
           choose_tile(hi, wi, &p.th, &p.tw);
+          // stride-1 dgrad with several taps: conv halo geometry first (th x 8 tiles)
+          want_halo = sub == 1 && nt > 1 && wi >= 8 && hi >= 4;
+          if (want_halo && !halo_failed) {
+            p.th = hi < 16 ? hi : 16;
+            p.tw = 8;
+          }
           p.tiles_h = (hi + p.th - 1) / p.th;
           p.tiles_w = (wi + p.tw - 1) / p.tw;
           g = IoGeom{d->N, d->H, d->W, sub, sub, ph, pw};
           rc = make_lattice_map(&p.tmap_a[0], d->src, d->N, Ho, Wo, d->K, 1, 1, 0, 0, p.th, p.tw);
         }
         for (int i = 1; i < 4 && rc == GHND_OK; ++i) p.tmap_a[i] = p.tmap_a[0];
-        if (rc == GHND_OK) rc = finish_launch(&L, d, d->K, d->C, d->weights, taps_total, g);
+        L.src = d->src;
+        L.src_n = d->N;
+        L.src_h = Ho;
+        L.src_w = Wo;
+        const bool try_halo = want_halo && !halo_failed;
+        if (rc == GHND_OK) rc = finish_launch(&L, d, d->K, d->C, d->weights, taps_total, g, 64, 0, try_halo);
+        if (rc == GHND_OK && try_halo && L.p.a_halo_bytes == 0) {
+          halo_failed = true;  // rebuild this parity class with the generic tiling
+          --pw;
+          continue;
+        }
+        halo_failed = false;
         if (rc == GHND_OK) plan->launches.push_back(L);
       }
     }
@@ -1471,7 +1793,7 @@ int ghnd_stem_conv_plan_create_k(const void* x_packed, int x_fmt, const void* w_
           rc = GHND_ERR_UNSUPPORTED;
         }
         p.n_stages = stages;
-        L.smem = (size_t)p.n_stages * p.stage_bytes + (size_t)p.w_res_bytes + (size_t)fixed + 1024 + 512;
+        L.smem = (size_t)p.n_stages * p.stage_bytes + (size_t)p.w_res_bytes + (size_t)fixed + 512;
       }
       if (rc == GHND_OK) plan->launches.push_back(L);
       continue;

@@ -60,9 +60,10 @@ __device__ __forceinline__ void umma_pair_stem(uint32_t d_tmem, uint32_t a_lo, u
 
 __global__ void __launch_bounds__(kSwtThreads, 1)
     stem_wgrad_tc_kernel(const __grid_constant__ StemWgradParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~(uintptr_t)1023);
+  // aligned by declaration; plain pointer arithmetic keeps the shared state space (LDS/STS, not generic)
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if (smem_u32(smem_raw) & 1023u) __trap();
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kSwtStages * kSwtStage);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kSwtStages;

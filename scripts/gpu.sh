@@ -6,6 +6,7 @@
 #   bench  <bench.py args>    -> gpurun_out/bench_<n>.log/.err
 #   py     <script + args>    -> gpurun_out/py_<n>.log
 #   launches <bench.py args>  -> gpurun_out/launches_<n>.csv   (ncu gpu__time_duration, never a bench value)
+#   ab <bench.py args>        -> same-box A/B: hnd_ghnd_object_detectors_b200/libghnd_b200_base.so vs the current build
 #   perlayer <batch>          -> gpurun_out/per_layer_<n>.txt + launch_summary_<n>.txt (one eager step under ncu)
 #   traffic  <batch>          -> gpurun_out/conv_dram_traffic_<n>.json (dram bytes of the conv_tc launches; copy to
 #                                profiles/r2_conv_dram_traffic.json -- bench.py's roofline.traffic reads it)
@@ -28,6 +29,14 @@ while [ $# -ge 2 ]; do
     launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_$n.csv python bench.py $arg > gpurun_out/launches_$n.log 2>&1; echo "launches_$n rc=$?" ;;
     ncu) IFS='|' read -r rx skip cnt cmd <<< "$arg"
          timeout 1200 ncu --set full --clock-control none --import-source on -k regex:$rx -s $skip -c $cnt -f -o gpurun_out/prof_$n $cmd > gpurun_out/ncu_$n.log 2>&1; echo "ncu_$n rc=$?" ;;
+    ab) # same-box A/B of two builds of the library: libghnd_b200_base.so (A) vs libghnd_b200.so (B), alternating
+         for rep in 1 2; do
+           for v in base new; do
+             if [ $v = base ]; then export GHND_LIB_PATH=$PWD/hnd_ghnd_object_detectors_b200/libghnd_b200_base.so; else unset GHND_LIB_PATH; fi
+             timeout 600 python bench.py --no-cpu-baseline --no-encode --no-config4 $arg > gpurun_out/ab_${n}_${v}_$rep.log 2> gpurun_out/ab_${n}_${v}_$rep.err
+             python -c "import json,sys; d=json.loads(open('gpurun_out/ab_${n}_${v}_$rep.log').read().strip().splitlines()[-1]); print('$v $rep: %.1f img/s  e2e %.1f  conv frac %.3f  clocks %s' % (d['value'], d['e2e']['value'], d['roofline']['frac'], d['clocks']['sm_mhz']))"
+           done
+         done; unset GHND_LIB_PATH ;;
     *) echo "unknown verb $verb" ;;
   esac
 done

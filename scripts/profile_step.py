@@ -48,7 +48,21 @@ def wrap(cls, kernel):
     cls.run = run
 wrap(ops.ConvPlan, "conv_tc_kernel"); wrap(ops.StemPlan, "conv_tc_kernel"); wrap(ops.WgradPlan, "wgrad_tc_kernel")
 top = int(os.environ.get("GHND_PROFILE_TOP", "0"))
-if top:
+want = os.environ.get("GHND_PROFILE_DESC")  # ';'-separated substrings of plan descriptions to profile (first run each)
+if want:
+    box(images, targets)
+    torch.cuda.synchronize()
+    selected = set()
+    for w in want.split(";"):
+        for t in trace:
+            if w in t["desc"]:
+                selected.add(t["desc"])
+                break
+    print("selected:", sorted(selected))
+    del trace[:]
+    box(images, targets)
+    torch.cuda.synchronize()
+elif top:
     # GHND_PROFILE_TOP=K: profile only the first run of the K distinct plan shapes with the most FLOPs
     # (for `ncu --set full`, which replays every profiled kernel ~40 times)
     box(images, targets)
