@@ -111,6 +111,11 @@ SIGNATURES = {
     "ghnd_bn_bwd_reduce": (_I, [_P, _I, _P, _I, _I, _I, _L, _I, _P, _P, _I, _P, _P]),
     "ghnd_bn_bwd_apply": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _L, _I, _P, _P, _P, _I, _P, _P, _P, _P]),
     "ghnd_bn_bwd_apply_fused_sums": (_I, [_P, _I, _P, _I, _P, _I, _I, _L, _I, _P, _P, _P, _I, _P, _P, _P, _P]),
+    "ghnd_comm_unique_id": (_I, [_P]),
+    "ghnd_comm_init_from_unique_id": (_I, [_P, _I, _I, POINTER(c_void_p)]),
+    "ghnd_comm_allreduce_flat": (_I, [_P, _P, _L, _P]),
+    "ghnd_comm_broadcast_flat": (_I, [_P, _P, _L, _I, _P]),
+    "ghnd_comm_destroy": (None, [_P]),
     "ghnd_adam_step": (_I, [_P, _P, _P, _P, _L, c_double, c_double, c_double, c_double, c_double, c_double, _I, _P]),
 }
 

@@ -381,6 +381,20 @@ int ghnd_small_conv_f32(const float* x, const float* w_rsck, const float* scale,
 int ghnd_avgpool_linear(const float* x, int N, int H, int W, int C, int OH, int OW, const float* lw, const float* lb,
                         int n_out, int softmax, float* out, void* stream);
 
+/* ---- data-parallel exchange (src/mimic_runner.py:141-143: DistributedDataParallel; src/utils/main_util.py:43-62)
+ * One process per GPU.  Rank 0 makes a 128-byte NCCL unique id (ghnd_comm_unique_id), ships it to the other
+ * ranks by any side channel (the Python runner uses torch.distributed's store), every rank calls
+ * ghnd_comm_init_from_unique_id on its own device.  ghnd_comm_allreduce_flat: in-place SUM over ranks of
+ * the flat fp32 gradient buffer (the 1/world factor is FusedAdam's grad_scale); ghnd_comm_broadcast_flat:
+ * rank `root`'s flat parameter buffer to everyone (what DDP's constructor does).  NCCL over NVLink 5 /
+ * NVSwitch, enqueued on `stream`; libnccl.so.2 is resolved with dlopen at first use. */
+typedef struct ghnd_comm ghnd_comm_t;
+int ghnd_comm_unique_id(void* id128);
+int ghnd_comm_init_from_unique_id(const void* id128, int world_size, int rank, ghnd_comm_t** comm);
+int ghnd_comm_allreduce_flat(ghnd_comm_t* comm, float* buf, int64_t n, void* stream);
+int ghnd_comm_broadcast_flat(ghnd_comm_t* comm, float* buf, int64_t n, int root, void* stream);
+void ghnd_comm_destroy(ghnd_comm_t* comm);
+
 #ifdef __cplusplus
 }
 #endif
