@@ -319,18 +319,23 @@ def flush_l2(dev, _buf={}):
     _buf["b"].zero_()
 
 
-def time_cold(fn, dev, iters=5):
-    """Median CUDA-event time (s) of fn() with an L2 flush before every call."""
+def time_cold(fns, dev, iters=5):
+    """Median CUDA-event time (s) PER CALL of the closures in `fns`, launched back to back after an L2
+    flush.  The closures do the same work on DISTINCT buffers whose total exceeds the L2, so every call
+    streams from HBM while the ~5 us of launch + event overhead of a lone short kernel is amortised."""
     import torch
+    if callable(fns):
+        fns = [fns]
     ts = []
     for _ in range(iters + 1):
         flush_l2(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        fn()
+        for fn in fns:
+            fn()
         e1.record()
         torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1) * 1e-3)
+        ts.append(e0.elapsed_time(e1) * 1e-3 / len(fns))
     ts = sorted(ts[1:])
     return ts[len(ts) // 2]
 
@@ -374,16 +379,25 @@ def encode_sweep(dev, batches, iters=10, model_name="keypoint_rcnn"):
             z, l1 = plan.z, plan.l1
             nz = float(z.numel())
             wide = float(l1.e2.out.numel())
-            t = time_cold(lambda: ops.quantize_u8_minmax(z, plan.minmax, l1.z_pairs, 8, plan.scale_mode, q=plan.q,
-                                                         qparams=plan.qparams), dev)
+            # four buffer sets (4 x 66 MB > L2): back-to-back launches stay HBM-cold
+            zs = [z] + [z.clone() for _ in range(3)]
+            qs = [plan.q] + [torch.empty_like(plan.q) for _ in range(3)]
+            qps = [plan.qparams] + [torch.empty_like(plan.qparams) for _ in range(3)]
+            t = time_cold([lambda i=i: ops.quantize_u8_minmax(zs[i], plan.minmax, l1.z_pairs, 8, plan.scale_mode,
+                                                              q=qs[i], qparams=qps[i]) for i in range(4)], dev)
             kernels["quant_apply (one-pass 8-bit quantizer of the encode path, min/max from the encoder's last conv; 5 B/elem, batch %d)" % b] = 5.0 * nz / t
-            t = time_cold(lambda: ops.quantize_u8(z, 8), dev)
+            qws = ops.quantize_ws(z.numel(), dev)
+            t = time_cold([lambda i=i: ops.quantize_u8(zs[i], 8, q=qs[i], qparams=qps[i], ws=qws) for i in range(4)], dev)
             kernels["quantize_u8 (stand-alone quantize_tensor: min/max + quantize in one persistent launch; 5 B/elem compulsory, batch %d)" % b] = 5.0 * nz / t
             q, qp = ops.quantize_u8(z, 8)
-            t = time_cold(lambda: ops.dequantize_u8(q, qp), dev)
+            qq = [q] + [q.clone() for _ in range(3)]
+            t = time_cold([lambda i=i: ops.dequantize_u8(qq[i], qp, out=zs[i]) for i in range(4)], dev)
             kernels["dequantize_u8 (1 B in, 4 B out per elem, batch %d)" % b] = 5.0 * nz / t
-            t = time_cold(lambda: ops.conv_narrow_out(l1.e2.out, l1.enc7.weight, 1, y=z, ws=l1.nws, minmax=plan.minmax), dev)
+            xs = [l1.e2.out] + [l1.e2.out.clone() for _ in range(3)]
+            t = time_cold([lambda i=i: ops.conv_narrow_out(xs[i], l1.enc7.weight, 1, y=zs[i], ws=l1.nws,
+                                                           minmax=plan.minmax) for i in range(4)], dev)
             kernels["narrow_out (encoder's last conv 64 -> bch k2 + min/max; 2 B/elem of the 64-ch input + 4 B/elem of z, batch %d)" % b] = (2.0 * wide + 4.0 * nz) / t
+            del zs, qs, qq, xs
         head.plan = None
     return out, kernels
 

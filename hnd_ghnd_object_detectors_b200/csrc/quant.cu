@@ -152,6 +152,20 @@ __global__ void __launch_bounds__(kQThreads)
                        const float* __restrict__ partial, int n_partial, float qmax,
                        float inv_range, int scale_mode, uint8_t* __restrict__ q,
                        QParams* __restrict__ qp) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  // first batch of loads in flight while the block folds the min/max partials (the prologue is ~10 % of
+  // this 15-20 us kernel: every block starts with it)
+  const int64_t n4 = vec_ok ? (n >> 2) : 0;
+  const uint4* x4 = reinterpret_cast<const uint4*>(x);
+  uint4 pa = make_uint4(0, 0, 0, 0), pb = pa, pc = pa, pd = pa;
+  const bool pre = tid + 3 * nthreads < n4;
+  if (pre) {
+    pa = ld_stream(x4 + tid);
+    pb = ld_stream(x4 + tid + nthreads);
+    pc = ld_stream(x4 + tid + 2 * nthreads);
+    pd = ld_stream(x4 + tid + 3 * nthreads);
+  }
   float mn = INFINITY, mx = -INFINITY;
   for (int i = threadIdx.x; i < n_partial; i += blockDim.x) {
     mn = nan_min(mn, partial[2 * i]);
@@ -169,17 +183,20 @@ __global__ void __launch_bounds__(kQThreads)
   }
   const float zpf = (float)zp;
   const QFast qf = make_qfast(zpf, scale, qmax);
-  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
   int64_t done = 0;
   if (vec_ok) {
     // lane-contiguous accesses: a warp reads 512 contiguous bytes per load instruction and writes 128
     // contiguous bytes per store (the first version gave every lane its own 64-byte run: each 32-byte
     // sector was requested by two different instructions and, with L1 allocation off, fetched twice)
-    const int64_t n4 = n >> 2;
-    const uint4* x4 = reinterpret_cast<const uint4*>(x);
     uint32_t* q4 = reinterpret_cast<uint32_t*>(q);
     int64_t i = tid;
+    if (pre) {
+      q4[i] = quant4(pa, qf);
+      q4[i + nthreads] = quant4(pb, qf);
+      q4[i + 2 * nthreads] = quant4(pc, qf);
+      q4[i + 3 * nthreads] = quant4(pd, qf);
+      i += 4 * nthreads;
+    }
     for (; i + 3 * nthreads < n4; i += 4 * nthreads) {
       const uint4 a = ld_stream(x4 + i), b = ld_stream(x4 + i + nthreads), c = ld_stream(x4 + i + 2 * nthreads),
                   d = ld_stream(x4 + i + 3 * nthreads);

@@ -38,20 +38,28 @@ def _ws(nbytes, device):
 # ------------------------------------------------------------------------------------------------
 # quantizer
 # ------------------------------------------------------------------------------------------------
-def quantize_u8(x, num_bits=8, scale_mode=_lib.QSCALE_DIV):
+def quantize_ws(n, device):
+    """Zeroed workspace of ghnd_quantize_u8 (its grid-barrier words must be zero on entry; the kernel
+    re-arms them on exit, so one workspace serves any number of calls on one stream)."""
+    return torch.zeros(_lib.load().ghnd_quantize_u8_workspace_bytes(n), dtype=torch.uint8, device=device)
+
+
+def quantize_u8(x, num_bits=8, scale_mode=_lib.QSCALE_DIV, q=None, qparams=None, ws=None):
     """-> (q uint8 like x, qparams: 16-byte device tensor {scale f32, zp i32, min f32, max f32})."""
     _need_cuda(x)
     if x.dtype != torch.float32:
         x = x.float()
     x = x.contiguous()
-    q = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
-    qp = torch.empty(4, dtype=torch.int32, device=x.device)
+    if q is None:
+        q = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    if qparams is None:
+        qparams = torch.empty(4, dtype=torch.int32, device=x.device)
     n = x.numel()
-    wsz = _lib.load().ghnd_quantize_u8_workspace_bytes(n)
-    ws = torch.zeros(wsz, dtype=torch.uint8, device=x.device)  # barrier words must start at zero
-    call("ghnd_quantize_u8", ptr(x), n, num_bits, scale_mode, ptr(q), ptr(qp), ptr(ws), wsz, stream_ptr())
+    if ws is None:
+        ws = quantize_ws(n, x.device)
+    call("ghnd_quantize_u8", ptr(x), n, num_bits, scale_mode, ptr(q), ptr(qparams), ptr(ws), ws.numel(), stream_ptr())
     _count(1)
-    return q, qp
+    return q, qparams
 
 
 def quantize_u8_minmax(x, minmax, n_pairs, num_bits=8, scale_mode=_lib.QSCALE_DIV, q=None, qparams=None):
@@ -69,10 +77,11 @@ def quantize_u8_minmax(x, minmax, n_pairs, num_bits=8, scale_mode=_lib.QSCALE_DI
     return q, qparams
 
 
-def dequantize_u8(q, qparams):
+def dequantize_u8(q, qparams, out=None):
     _need_cuda(q, qparams)
     q = q.contiguous()
-    out = torch.empty(q.shape, dtype=torch.float32, device=q.device)
+    if out is None:
+        out = torch.empty(q.shape, dtype=torch.float32, device=q.device)
     if q.numel():
         call("ghnd_dequantize_u8", ptr(q), q.numel(), ptr(qparams), ptr(out), stream_ptr())
         _count(1)
