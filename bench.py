@@ -559,6 +559,8 @@ def run_cuda(args):
     plan_shared, plan_side = bool(plan.shared), plan.side is not None
     torch.cuda.synchronize()
     from hnd_ghnd_object_detectors_b200 import parallel
+    parallel.broadcast_flat_params(box.flat)  # every rank starts from rank 0's student (DDP semantics)
+    parallel.broadcast_buffers(student)
 
     dbg = {"n": 0}
 
@@ -734,7 +736,10 @@ def run_cuda(args):
     if (world in (1, 8) and not args.no_config4) or args.config4:
         del box, plan
         torch.cuda.empty_cache()
-        config4 = config4_bench(dev, world)
+        try:
+            config4 = config4_bench(dev, world)
+        except Exception as e:  # the headline line must survive a failure of the secondary workload
+            config4 = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
     if rank == 0:
         h2d = sum(h.numel() * 4 for h in host_images)
         line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
