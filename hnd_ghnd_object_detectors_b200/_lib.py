@@ -88,6 +88,10 @@ SIGNATURES = {
     "ghnd_stem_conv_plan_create_k": (_I, [_P, _I, _P, _I, _P, _P, _I, _I, _I, _I, _I, POINTER(c_void_p)]),
     "ghnd_stem_conv_plan_run": (_I, [_P, _P]),
     "ghnd_stem_plan_destroy": (None, [_P]),
+    "ghnd_stem_pool_plan_create": (_I, [_P, _I, _P, _I, _P, _I, POINTER(c_void_p), POINTER(c_void_p), _I, _I, _I, _I,
+                                        POINTER(c_void_p)]),
+    "ghnd_stem_pool_plan_run": (_I, [_P, _P]),
+    "ghnd_stem_pool_plan_destroy": (None, [_P]),
     "ghnd_maxpool3x3s2": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "ghnd_maxpool3x3s2_strided": (_I, [_P, _I, _I, _P, _P, _I, _I, _I, _I, _I, _P]),
     "ghnd_maxpool3x3s2_bwd": (_I, [_P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P]),

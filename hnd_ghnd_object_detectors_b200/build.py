@@ -7,7 +7,7 @@ from concurrent.futures import ThreadPoolExecutor
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libghnd_b200.so")
-SOURCES = ["api.cu", "quant.cu", "sse.cu", "eltwise.cu", "conv_narrow.cu", "conv_tc.cu", "wgrad_tc.cu", "stem_wgrad_tc.cu", "ext_filter.cu", "comm.cu"]
+SOURCES = ["api.cu", "quant.cu", "sse.cu", "eltwise.cu", "conv_narrow.cu", "conv_tc.cu", "wgrad_tc.cu", "stem_wgrad_tc.cu", "stem_pool_tc.cu", "ext_filter.cu", "comm.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default",
               # 128: "loop is not reachable" in template instantiations that compile a path out

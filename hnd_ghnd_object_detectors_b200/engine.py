@@ -231,11 +231,17 @@ class FrozenLayerRunner(object):
             b.backward(side)
 
 
+def _stem_pool_fused():
+    """conv1 and the max-pool as one kernel (the conv output never reaches HBM); GHND_STEM_POOL=0 keeps
+    the two-kernel path (conv GEMM, then pool) for A/B runs and as the bitwise reference in the tests."""
+    return os.environ.get("GHND_STEM_POOL", "1") != "0"
+
+
 class DualStemConv(object):
-    """The teacher's and the student's conv1 as ONE K=128 GEMM over the shared packed image (teacher
-    = channels 0-63, student = 64-127).  The stem is bounded by its im2col traffic (every input
-    pixel travels ~12x through L2 -> shared memory; the tensor pipe is ~16 % busy), which does not
-    depend on the number of output channels -- so the second model's conv1 is almost free."""
+    """The teacher's and the student's conv1 over the shared packed image (teacher = channels 0-63,
+    student = 64-127 of the packed weights).  Fused mode: ONE stem+pool kernel writes both pooled maps
+    (and the student's argmax codes).  Otherwise one K=128 GEMM writes both conv outputs and the two
+    StemRunners pool their halves."""
 
     def __init__(self, teacher_body, student_body, packed, N, Hp, Wp, act_dtype):
         dev = packed.device
@@ -244,8 +250,16 @@ class DualStemConv(object):
         self.s_scale, s_shift = fold_frozen_bn(student_body.bn1)
         self.w = _empty((128, 7, 32), act_dtype, dev)
         self.bias = torch.cat([t_shift, s_shift]).contiguous()
-        self.conv = _empty((N, Hp // 2, Wp // 2, 128), act_dtype, dev)
-        self.plan = ops.StemPlan(packed, self.w, self.bias, self.conv, N, Hp, Wp)
+        self.fused = _stem_pool_fused()
+        if self.fused:
+            Ho, Wo = (Hp // 2 + 1) // 2, (Wp // 2 + 1) // 2
+            self.conv = None
+            self.outs = [_empty((N, Ho, Wo, 64), act_dtype, dev) for _ in range(2)]
+            self.argmax = [None, _empty((N, Ho, Wo, 64), torch.uint8, dev)]
+            self.plan = ops.StemPoolPlan(packed, self.w, self.bias, self.outs, self.argmax, N, Hp, Wp)
+        else:
+            self.conv = _empty((N, Hp // 2, Wp // 2, 128), act_dtype, dev)
+            self.plan = ops.StemPlan(packed, self.w, self.bias, self.conv, N, Hp, Wp)
         ops.stem_pack_weight(teacher_body.conv1.weight, t_scale, out=self.w[:64])  # frozen: once
         self.refresh_student()
 
@@ -258,9 +272,9 @@ class DualStemConv(object):
 
 
 class StemRunner(object):
-    """conv1 7x7 s2 + FrozenBN + ReLU (tcgen05 implicit GEMM) -> MaxPool 3x3 s2.
-    shared = (DualStemConv, channel offset): the conv is done by the two-stem GEMM and this runner
-    only pools (and back-propagates through) its 64-channel half."""
+    """conv1 7x7 s2 + FrozenBN + ReLU -> MaxPool 3x3 s2 (tcgen05 implicit GEMM; one fused kernel unless
+    GHND_STEM_POOL=0).  shared = (DualStemConv, channel offset): the conv (fused mode: and the pool) is
+    done by the two-stem kernel and this runner only owns the backward pass of its 64-channel half."""
 
     def __init__(self, body, packed, N, Hp, Wp, act_dtype, grad_dtype, trainable, shared=None):
         dev = packed.device
@@ -270,15 +284,24 @@ class StemRunner(object):
         self.shared = shared
         self.scale, self.shift = fold_frozen_bn(body.bn1)
         self.Ho, self.Wo = (Hp // 2 + 1) // 2, (Wp // 2 + 1) // 2
-        self.out = _empty((N, self.Ho, self.Wo, 64), act_dtype, dev)
-        self.argmax = _empty((N, self.Ho, self.Wo, 64), torch.uint8, dev) if trainable else None
+        self.fused = shared[0].fused if shared is not None else _stem_pool_fused()
+        if shared is not None and self.fused:
+            self.out, self.argmax = shared[0].outs[shared[1] // 64], shared[0].argmax[shared[1] // 64]
+            assert (self.argmax is not None) == bool(trainable)
+        else:
+            self.out = _empty((N, self.Ho, self.Wo, 64), act_dtype, dev)
+            self.argmax = _empty((N, self.Ho, self.Wo, 64), torch.uint8, dev) if trainable else None
         if shared is not None:
             self.conv, self.c_off, self.plan, self.w = shared[0].conv, shared[1], None, None
         else:
             self.c_off = 0
             self.w = _empty((64, 7, 32), act_dtype, dev)
-            self.conv = _empty((N, Hp // 2, Wp // 2, 64), act_dtype, dev)
-            self.plan = ops.StemPlan(packed, self.w, self.shift, self.conv, N, Hp, Wp)
+            if self.fused:
+                self.conv = None
+                self.plan = ops.StemPoolPlan(packed, self.w, self.shift, [self.out], [self.argmax], N, Hp, Wp)
+            else:
+                self.conv = _empty((N, Hp // 2, Wp // 2, 64), act_dtype, dev)
+                self.plan = ops.StemPlan(packed, self.w, self.shift, self.conv, N, Hp, Wp)
             self.refresh_weights()
         if trainable:
             self.g_conv = _empty((N, Hp // 2, Wp // 2, 64), grad_dtype, dev)
@@ -297,7 +320,8 @@ class StemRunner(object):
             if self.trainable:
                 self.refresh_weights()
             self.plan.run()
-        ops.maxpool3x3s2(self.conv, self.out, self.argmax, channels=64, channel_offset=self.c_off)
+        if not self.fused:
+            ops.maxpool3x3s2(self.conv, self.out, self.argmax, channels=64, channel_offset=self.c_off)
 
     def backward(self, g_out, dw):
         """g_out: gradient w.r.t. the pooled output; dw: fp32 OIHW view for conv1.weight.grad."""

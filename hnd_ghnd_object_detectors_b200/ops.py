@@ -279,6 +279,43 @@ class StemPlan(object):
             self._h = None
 
 
+class StemPoolPlan(object):
+    """conv1 + folded FrozenBN + ReLU + MaxPool 3x3 s2 p1 in one kernel: the conv output stays in shared
+    memory.  ys: one pooled [N,Ho,Wo,64] tensor per model (1 or 2 models over the same packed image,
+    weights [64*m][7][32], bias [64*m]); argmaxes: matching uint8 tensors or None entries."""
+
+    def __init__(self, x_packed, w_packed, bias, ys, argmaxes, N, Hp, Wp):
+        m = len(ys)
+        assert w_packed.shape[0] == 64 * m and bias.numel() == 64 * m
+        argmaxes = list(argmaxes) if argmaxes is not None else [None] * m
+        ho, wo = (Hp // 2 + 1) // 2, (Wp // 2 + 1) // 2
+        for y, a in zip(ys, argmaxes):
+            assert tuple(y.shape) == (N, ho, wo, 64) and y.is_contiguous() and y.dtype == x_packed.dtype
+            assert a is None or (tuple(a.shape) == (N, ho, wo, 64) and a.dtype == torch.uint8 and a.is_contiguous())
+        self._keep = (x_packed, w_packed, bias, list(ys), argmaxes)
+        self.desc = "stem+pool N%d %dx%d" % (N, Hp, Wp) + ("" if m == 1 else " x%d" % m)
+        self.n_launches = 1
+        self.flops = 2.0 * N * (Hp // 2) * (Wp // 2) * 64 * m * 147
+        yp = (c_void_p * m)(*[ptr(y) for y in ys])
+        ap = (c_void_p * m)(*[ptr(a) for a in argmaxes])
+        self._h = c_void_p()
+        call("ghnd_stem_pool_plan_create", ptr(x_packed), fmt_of(x_packed.dtype), ptr(w_packed),
+             fmt_of(w_packed.dtype), ptr(bias), m, yp, ap, fmt_of(x_packed.dtype), N, Hp, Wp, byref(self._h))
+
+    def run(self, stream=None):
+        call("ghnd_stem_pool_plan_run", self._h, stream_ptr(stream))
+        _count()
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                _lib.load().ghnd_stem_pool_plan_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+
 # ------------------------------------------------------------------------------------------------
 # weights
 # ------------------------------------------------------------------------------------------------
@@ -461,7 +498,11 @@ def maxpool3x3s2(x, y=None, argmax=None, channels=None, channel_offset=0):
 
 
 def maxpool3x3s2_bwd(x, argmax, dy, dx, channel_offset=0):
-    """x may be wider than dx (two-stem conv output): its channels [offset, offset+C) are used."""
+    """x may be wider than dx (two-stem conv output): its channels [offset, offset+C) are used.  x only
+    supplies geometry (the ReLU mask travels in the argmax codes); None = the geometry of dx, for the
+    fused stem+pool path where the pool's input never exists."""
+    if x is None:
+        x, channel_offset = dx, 0
     n, h, w, xc = x.shape
     c = dx.shape[-1]
     call("ghnd_maxpool3x3s2_bwd_strided", ptr(x), fmt_of(x.dtype), xc, channel_offset, ptr(argmax), ptr(dy),

@@ -263,6 +263,19 @@ int ghnd_stem_conv_plan_create_k(const void* x_packed, int x_fmt, const void* w_
                                  ghnd_stem_plan_t** plan);
 int ghnd_stem_conv_plan_run(const ghnd_stem_plan_t* plan, void* stream);
 void ghnd_stem_plan_destroy(ghnd_stem_plan_t* plan);
+/* conv1 + FrozenBN + ReLU + MaxPool 3x3 s2 p1 as ONE kernel (src/models/custom/resnet.py:26-30,96-99 --
+ * `self.conv1 .. self.maxpool` of the backbone body): conv1's [N][Hp/2][Wp/2][64] output is pooled in
+ * shared memory and never written.  n_models (1 or 2) stems read the SAME packed image (weights
+ * [64*n_models][7][32], bias[64*n_models]; the distillation step runs teacher + student this way);
+ * y[m] receives model m's pooled map [N][Ho][Wo][64] (Ho = (Hp/2+1)/2), argmax[m] (array or entries
+ * nullable) the window codes of ghnd_maxpool3x3s2 (0xff where the maximum is not > 0).  Bit-identical
+ * to ghnd_stem_conv_plan_* followed by ghnd_maxpool3x3s2_strided. */
+typedef struct ghnd_stem_pool_plan ghnd_stem_pool_plan_t;
+int ghnd_stem_pool_plan_create(const void* x_packed, int x_fmt, const void* w_packed, int w_fmt,
+                               const float* bias, int n_models, void* const* y, void* const* argmax,
+                               int y_fmt, int N, int Hp, int Wp, ghnd_stem_pool_plan_t** plan);
+int ghnd_stem_pool_plan_run(const ghnd_stem_pool_plan_t* plan, void* stream);
+void ghnd_stem_pool_plan_destroy(ghnd_stem_pool_plan_t* plan);
 /* maxpool 3x3 s2 p1 on NHWC 16-bit: y[N][Ho][Wo][C], Ho=(H+1)/2; argmax (nullable) receives the
  * window position 0..8 of the first maximum, one byte per output element -- or 0xff when that maximum is
  * not > 0: the ReLU mask of x's producer, folded in so that the backward pass need not re-read x. */

@@ -690,6 +690,51 @@ def test_stem_two_models_one_gemm(ops):
         ops.maxpool3x3s2(y2, channels=64, channel_offset=96)
 
 
+@pytest.mark.parametrize("geom", [(2, 96, 128), (1, 64, 168), (3, 32, 72), (1, 224, 456), (1, 8, 16), (2, 30, 40)])
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+def test_stem_pool_fused_is_bitwise_the_two_kernel_path(ops, geom, dt):
+    """conv1 + ReLU + max-pool as one kernel (conv output pooled in shared memory, patches of 16x32
+    conv outputs overlapping by the pool halo) against the conv GEMM followed by the pool kernel:
+    pooled maps and argmax codes (with the folded ReLU mask) equal bit for bit, one and two models,
+    ragged sizes where the last patch hangs over the border."""
+    N, Hp, Wp = geom
+    torch.manual_seed(Hp * 7 + Wp)
+    packed = torch.zeros((N, Hp + 6, Wp + 8, 4), dtype=dt, device="cuda")
+    for i in range(N):
+        ops.stem_pack_image(torch.rand(3, Hp - (i % 2) * 1, Wp - (i % 2) * 3).cuda(), packed, i, Hp, Wp,
+                            O.IMAGE_MEAN, O.IMAGE_STD)
+    ws = [(torch.randn(64, 3, 7, 7) * 0.1).cuda() for _ in range(2)]
+    scales = [(torch.rand(64) + 0.5).cuda() for _ in range(2)]
+    biases = [(torch.randn(64) * 0.2).cuda() for _ in range(2)]
+    w2 = torch.empty((128, 7, 32), dtype=dt, device="cuda")
+    Hc, Wc = Hp // 2, Wp // 2
+    Ho, Wo = (Hc + 1) // 2, (Wc + 1) // 2
+    want = []
+    for k in range(2):
+        ops.stem_pack_weight(ws[k], scales[k], out=w2[64 * k:64 * (k + 1)])
+        y = torch.zeros((N, Hc, Wc, 64), dtype=dt, device="cuda")
+        ops.StemPlan(packed, w2[64 * k:64 * (k + 1)], biases[k], y, N, Hp, Wp).run()
+        am = torch.full((N, Ho, Wo, 64), 77, dtype=torch.uint8, device="cuda")
+        want.append((ops.maxpool3x3s2(y, argmax=am), am))
+    for models in ([0], [1], [0, 1]):
+        m = len(models)
+        w = w2 if m == 2 else w2[64 * models[0]:64 * (models[0] + 1)]
+        b = torch.cat([biases[k] for k in models]).contiguous()
+        ys = [torch.full((N, Ho, Wo, 64), 5.0, dtype=dt, device="cuda") for _ in models]
+        ams = [torch.full((N, Ho, Wo, 64), 99, dtype=torch.uint8, device="cuda") if k == 1 else None for k in models]
+        plan = ops.StemPoolPlan(packed, w, b, ys, ams, N, Hp, Wp)
+        plan.run()
+        plan.run()  # idempotent (buffers alternate inside, nothing carried between runs)
+        torch.cuda.synchronize()
+        for y, am, k in zip(ys, ams, models):
+            assert torch.equal(y, want[k][0]), (models, k)
+            if am is not None:
+                assert torch.equal(am, want[k][1]), (models, k)
+    from hnd_ghnd_object_detectors_b200._lib import GhndError
+    with pytest.raises(GhndError):  # formats must agree
+        ops.StemPoolPlan(packed, w2.to(torch.bfloat16 if dt == torch.float16 else torch.float16), b, ys, None, N, Hp, Wp)
+
+
 @pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
 def test_stem_pack_with_resize(ops, golden_dir, dt):
     """normalize + bilinear resize + zero-pad fused in the pack kernel against the
