@@ -73,19 +73,19 @@ __device__ __forceinline__ void sp_pool_tap(uint32_t& best, uint32_t& idx, uint3
     idx = (idx & ~m) | (code & m);
   }
 }
+// Bias + ReLU + conversion of one channel pair, with the rounding of conv_tc.cu's epilogue for the same output
+// format: f16 -> packed (h = cvt(acc); h += bias16; max(h, 0)); bf16 -> fp32 (cvt(max(acc + bias, 0))).
+// `bias` points at the pair's bias: one packed f16 word, or two floats.
 template <int FMT>
-__device__ __forceinline__ uint32_t sp_bias_relu(float a, float b, uint32_t bias2) {
-  // h = cvt(acc); h += bias; ReLU -- all in the output format, like conv_tc.cu's packed epilogue
-  uint32_t h = pack2_t<FMT>(a, b);
+__device__ __forceinline__ uint32_t sp_bias_relu(float a, float b, const uint32_t* bias) {
   if (FMT == GHND_F16) {
-    __half2 r = __hadd2(*reinterpret_cast<const __half2*>(&h), *reinterpret_cast<const __half2*>(&bias2));
+    const uint32_t h = pack2_t<FMT>(a, b);
+    __half2 r = __hadd2(*reinterpret_cast<const __half2*>(&h), *reinterpret_cast<const __half2*>(bias));
     r = __hmax2(r, __float2half2_rn(0.f));
     return *reinterpret_cast<const uint32_t*>(&r);
   }
-  __nv_bfloat162 r =
-      __hadd2(*reinterpret_cast<const __nv_bfloat162*>(&h), *reinterpret_cast<const __nv_bfloat162*>(&bias2));
-  r = __hmax2(r, __float2bfloat162_rn(0.f));
-  return *reinterpret_cast<const uint32_t*>(&r);
+  const float2 bf = *reinterpret_cast<const float2*>(bias);
+  return pack2_t<FMT>(fmaxf(a + bf.x, 0.f), fmaxf(b + bf.y, 0.f));
 }
 
 // Two K=16 steps with separate high words for A and B (see conv_tc.cu).
@@ -118,8 +118,10 @@ __global__ void __launch_bounds__(kSpThreads, 1)
   if (smem_u32(smem) & 1023u) __trap();
   uint8_t* wres = smem + (size_t)p.n_stages * kSpStageBytes;      // [n_models][7][64 x 64 B]
   uint8_t* tile = wres + (size_t)p.n_models * 7 * kSpWBytes;      // [16][32][128 B], swizzled
-  uint32_t* sbias = reinterpret_cast<uint32_t*>(tile + kSpTileBytes);  // [n_models][32] packed pairs
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sbias + 64);
+  // bias per channel pair: one packed f16 word, or two floats (bf16 output: fp32 epilogue) -- see sp_bias_relu
+  constexpr int kBw = FMT == GHND_F16 ? 1 : 2;
+  uint32_t* sbias = reinterpret_cast<uint32_t*>(tile + kSpTileBytes);  // [n_models][32 pairs][kBw]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sbias + 128);
   uint64_t* afull = bars;                     // [kSpMaxStages]
   uint64_t* aempty = afull + kSpMaxStages;    // [kSpMaxStages]
   uint64_t* tfull = aempty + kSpMaxStages;    // [2]
@@ -226,8 +228,14 @@ __global__ void __launch_bounds__(kSpThreads, 1)
     const int half = (warp - 2) >> 2; // which two column classes this warp moves
     const int i_row = quarter * 4 + (lane >> 3);  // conv row of this thread's accumulator lane
     const int jj = lane & 7;                      // column slot
-    for (int i = et; i < p.n_models * 32; i += kSpEpiThreads)
-      sbias[i] = pack2(__ldg(p.bias + 2 * i), __ldg(p.bias + 2 * i + 1), p.fmt);
+    for (int i = et; i < p.n_models * 32; i += kSpEpiThreads) {
+      if (FMT == GHND_F16) {
+        sbias[i] = pack2_t<FMT>(__ldg(p.bias + 2 * i), __ldg(p.bias + 2 * i + 1));
+      } else {
+        sbias[2 * i] = __float_as_uint(__ldg(p.bias + 2 * i));
+        sbias[2 * i + 1] = __float_as_uint(__ldg(p.bias + 2 * i + 1));
+      }
+    }
     named_bar_sync(1, kSpEpiThreads);
     int it = 0;
     for (int job = blockIdx.x; job < p.total_jobs; job += gridDim.x, ++it) {
@@ -241,7 +249,7 @@ __global__ void __launch_bounds__(kSpThreads, 1)
       mbar_wait(&tfull[buf], ((uint32_t)it >> 1) & 1u);
       tc_fence_after();
       // ---- phase A: accumulators -> bias + ReLU -> swizzled 16-bit tile ----
-      const uint32_t* bm = sbias + m * 32;
+      const uint32_t* bm = sbias + m * 32 * kBw;
 #pragma unroll 1
       for (int qq = 0; qq < 2; ++qq) {
         const int q = 2 * half + qq;
@@ -256,10 +264,10 @@ __global__ void __launch_bounds__(kSpThreads, 1)
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           uint4 o;
-          o.x = sp_bias_relu<FMT>(__uint_as_float(r[8 * j]), __uint_as_float(r[8 * j + 1]), bm[4 * j]);
-          o.y = sp_bias_relu<FMT>(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]), bm[4 * j + 1]);
-          o.z = sp_bias_relu<FMT>(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]), bm[4 * j + 2]);
-          o.w = sp_bias_relu<FMT>(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]), bm[4 * j + 3]);
+          o.x = sp_bias_relu<FMT>(__uint_as_float(r[8 * j]), __uint_as_float(r[8 * j + 1]), bm + (4 * j + 0) * kBw);
+          o.y = sp_bias_relu<FMT>(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]), bm + (4 * j + 1) * kBw);
+          o.z = sp_bias_relu<FMT>(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]), bm + (4 * j + 2) * kBw);
+          o.w = sp_bias_relu<FMT>(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]), bm + (4 * j + 3) * kBw);
           *reinterpret_cast<uint4*>(px + ((j ^ key) << 4)) = o;
         }
       }
@@ -387,7 +395,7 @@ int ghnd_stem_pool_plan_create(const void* x_packed, int x_fmt, const void* w_pa
     delete plan;
     return rc;
   }
-  const int fixed = n_models * 7 * kSpWBytes + kSpTileBytes + 256 /*bias*/ + 512 /*barriers*/;
+  const int fixed = n_models * 7 * kSpWBytes + kSpTileBytes + 512 /*bias*/ + 512 /*barriers*/;
   int stages = (227 * 1024 - fixed) / kSpStageBytes;
   if (stages > kSpMaxStages) stages = kSpMaxStages;
   if (stages < 4) {

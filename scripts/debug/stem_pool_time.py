@@ -2,6 +2,8 @@
 at the distillation batch and the single stem at the encode batch."""
 import sys
 import torch
+import os
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 from hnd_ghnd_object_detectors_b200 import ops
 
 dt = torch.float16
