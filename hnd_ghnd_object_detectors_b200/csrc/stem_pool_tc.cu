@@ -15,7 +15,7 @@
 //   * a job = (model, patch): the four classes of a patch go to four 64-column TMEM accumulators; two
 //     such sets (2 x 256 columns) alternate between consecutive jobs, so the MMAs of job i+1 run under
 //     the epilogue of job i.
-//   * epilogue: 8 warps move the accumulators (bias + ReLU in packed half2, as the un-fused epilogue)
+//   * epilogue: 16 warps move the accumulators (bias + ReLU in packed half2, as the un-fused epilogue)
 //     into a swizzled [16][32][64 ch] 16-bit tile in shared memory, then pool 7 x 14 outputs from it
 //     (packed half2 max / compare-mask / select, first maximum in scan order like torch) and store
 //     pooled rows (+ argmax bytes, 0xff where the maximum is not > 0) with 128-byte-per-pixel coalescing.
@@ -31,8 +31,8 @@
 
 namespace ghnd {
 
-static constexpr int kSpThreads = 320;      // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue + pool
-static constexpr int kSpEpiThreads = 256;
+static constexpr int kSpThreads = 576;      // warp 0 TMA, warp 1 MMA, warps 2..17 epilogue + pool
+static constexpr int kSpEpiThreads = 512;   // 16 warps = 4 TMEM lane quarters x 4 column classes
 static constexpr int kSpMaxStages = 8;
 static constexpr int kSpRows = 16, kSpCols = 32;          // conv patch
 static constexpr int kSpPoolRows = 7, kSpPoolCols = 14;   // pooled outputs per patch
@@ -55,6 +55,16 @@ struct StemPoolParams {
   uint32_t idesc;
 };
 
+template <int FMT>
+__device__ __forceinline__ uint32_t sp_max2(uint32_t a, uint32_t b) {
+  if (FMT == GHND_F16) {
+    const __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&r);
+  }
+  const __nv_bfloat162 r =
+      __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
 template <int FMT>
 __device__ __forceinline__ void sp_pool_tap(uint32_t& best, uint32_t& idx, uint32_t v, uint32_t code) {
   if (FMT == GHND_F16) {
@@ -222,12 +232,16 @@ __global__ void __launch_bounds__(kSpThreads, 1)
       }
     }
   } else {
-    // ===================== epilogue + pool: 8 warps =====================
-    const int et = threadIdx.x - 64;  // 0..255
+    // ===================== epilogue + pool: 16 warps =====================
+    // Two warps per scheduler could not hide the LDS / TMEM latencies of this section (ncu: 34 % issue
+    // slots, 7 cycles per issued instruction); 16 warps also give every (lane quarter, class) its own warp.
+    const int et = threadIdx.x - 64;  // 0..511
     const int quarter = warp & 3;     // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2; // which two column classes this warp moves
+    const int q = (warp - 2) >> 2;    // column class this warp moves out of TMEM
     const int i_row = quarter * 4 + (lane >> 3);  // conv row of this thread's accumulator lane
     const int jj = lane & 7;                      // column slot
+    const int x_col = 4 * jj + ((q + 1) & 3);     // column inside the patch
+    const uint32_t ninf = FMT == GHND_F16 ? 0xfc00fc00u : 0xff80ff80u;
     for (int i = et; i < p.n_models * 32; i += kSpEpiThreads) {
       if (FMT == GHND_F16) {
         sbias[i] = pack2_t<FMT>(__ldg(p.bias + 2 * i), __ldg(p.bias + 2 * i + 1));
@@ -248,27 +262,31 @@ __global__ void __launch_bounds__(kSpThreads, 1)
       const int r_base = 2 * ph0 - 1, c_base = 2 * pw0 - 1;
       mbar_wait(&tfull[buf], ((uint32_t)it >> 1) & 1u);
       tc_fence_after();
-      // ---- phase A: accumulators -> bias + ReLU -> swizzled 16-bit tile ----
-      const uint32_t* bm = sbias + m * 32 * kBw;
-#pragma unroll 1
-      for (int qq = 0; qq < 2; ++qq) {
-        const int q = 2 * half + qq;
+      // ---- phase A: accumulators -> bias + ReLU -> swizzled 16-bit tile; -inf outside the image, so
+      //      that the pool below needs no border tests ----
+      {
+        const uint32_t* bm = sbias + m * 32 * kBw;
         uint32_t r[64];
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * 256 + q * 64);
         tmem_ld32(taddr, r);
         tmem_ld32(taddr + 32, r + 32);
         tmem_ld_wait();
-        const int x = 4 * jj + ((q + 1) & 3);  // column inside the patch
         const int key = (i_row + jj) & 7;
-        uint8_t* px = tile + (size_t)(i_row * kSpCols + x) * 128;
+        uint8_t* px = tile + (size_t)(i_row * kSpCols + x_col) * 128;
+        const bool inside = (unsigned)(r_base + i_row) < (unsigned)p.Hc && (unsigned)(c_base + x_col) < (unsigned)p.Wc;
+        if (inside) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          uint4 o;
-          o.x = sp_bias_relu<FMT>(__uint_as_float(r[8 * j]), __uint_as_float(r[8 * j + 1]), bm + (4 * j + 0) * kBw);
-          o.y = sp_bias_relu<FMT>(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]), bm + (4 * j + 1) * kBw);
-          o.z = sp_bias_relu<FMT>(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]), bm + (4 * j + 2) * kBw);
-          o.w = sp_bias_relu<FMT>(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]), bm + (4 * j + 3) * kBw);
-          *reinterpret_cast<uint4*>(px + ((j ^ key) << 4)) = o;
+          for (int j = 0; j < 8; ++j) {
+            uint4 o;
+            o.x = sp_bias_relu<FMT>(__uint_as_float(r[8 * j]), __uint_as_float(r[8 * j + 1]), bm + (4 * j + 0) * kBw);
+            o.y = sp_bias_relu<FMT>(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]), bm + (4 * j + 1) * kBw);
+            o.z = sp_bias_relu<FMT>(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]), bm + (4 * j + 2) * kBw);
+            o.w = sp_bias_relu<FMT>(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]), bm + (4 * j + 3) * kBw);
+            *reinterpret_cast<uint4*>(px + ((j ^ key) << 4)) = o;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(px + (j << 4)) = make_uint4(ninf, ninf, ninf, ninf);
         }
       }
       tc_fence_before();
@@ -277,46 +295,54 @@ __global__ void __launch_bounds__(kSpThreads, 1)
       // ---- phase B: 3x3 s2 max-pool of the tile -> 7 x 14 pooled pixels ----
       uint4* yo = reinterpret_cast<uint4*>(p.y[m]);
       uint2* ao = reinterpret_cast<uint2*>(p.argmax[m]);
-      const uint32_t ninf = FMT == GHND_F16 ? 0xfc00fc00u : 0xff80ff80u;
       for (int item = et; item < kSpPoolRows * kSpPoolCols * 8; item += kSpEpiThreads) {
         const int cg = item & 7, pix = item >> 3;
         const int a = pix / kSpPoolCols, b = pix - a * kSpPoolCols;
         const int ph = ph0 + a, pw = pw0 + b;
         if (ph >= p.Ho || pw >= p.Wo) continue;
-        uint32_t best[4] = {ninf, ninf, ninf, ninf};
-        uint32_t idx[4] = {0u, 0u, 0u, 0u};
+        uint4 v[9];
 #pragma unroll
-        for (int dr = 0; dr < 3; ++dr) {
-          const int i = 2 * a + dr;
-          if (r_base + i < 0 || r_base + i >= p.Hc) continue;
+        for (int dr = 0; dr < 3; ++dr)
 #pragma unroll
           for (int ds = 0; ds < 3; ++ds) {
-            const int x = 2 * b + ds;
-            if (c_base + x < 0 || c_base + x >= p.Wc) continue;
+            const int i = 2 * a + dr, x = 2 * b + ds;
             const int key = (i + (x >> 2)) & 7;
-            const uint4 v = *reinterpret_cast<const uint4*>(tile + (size_t)(i * kSpCols + x) * 128 + ((cg ^ key) << 4));
-            const uint32_t code = (uint32_t)(dr * 3 + ds) * 0x00010001u;
-            sp_pool_tap<FMT>(best[0], idx[0], v.x, code);
-            sp_pool_tap<FMT>(best[1], idx[1], v.y, code);
-            sp_pool_tap<FMT>(best[2], idx[2], v.z, code);
-            sp_pool_tap<FMT>(best[3], idx[3], v.w, code);
+            v[dr * 3 + ds] = *reinterpret_cast<const uint4*>(tile + (size_t)(i * kSpCols + x) * 128 + ((cg ^ key) << 4));
           }
-        }
         const int64_t o = (((int64_t)img * p.Ho + ph) * p.Wo + pw) * 8 + cg;
-        yo[o] = make_uint4(best[0], best[1], best[2], best[3]);
-        if (ao != nullptr) {
+        uint32_t best[4] = {ninf, ninf, ninf, ninf};
+        if (ao == nullptr) {  // no argmax wanted (frozen model): plain maximum
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {  // fold the ReLU mask into the code (see maxpool_kernel)
-            uint32_t pos;
-            if (FMT == GHND_F16) pos = __hgt2_mask(*reinterpret_cast<const __half2*>(&best[e]), __float2half2_rn(0.f));
-            else pos = __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&best[e]), __float2bfloat162_rn(0.f));
-            idx[e] = (idx[e] & pos) | (0x00ff00ffu & ~pos);
+          for (int tpi = 0; tpi < 9; ++tpi) {
+            best[0] = sp_max2<FMT>(best[0], v[tpi].x);
+            best[1] = sp_max2<FMT>(best[1], v[tpi].y);
+            best[2] = sp_max2<FMT>(best[2], v[tpi].z);
+            best[3] = sp_max2<FMT>(best[3], v[tpi].w);
           }
-          uint2 am;
-          am.x = __byte_perm(idx[0], idx[1], 0x6420);
-          am.y = __byte_perm(idx[2], idx[3], 0x6420);
-          ao[o] = am;
+          yo[o] = make_uint4(best[0], best[1], best[2], best[3]);
+          continue;
         }
+        uint32_t idx[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int tpi = 0; tpi < 9; ++tpi) {
+          const uint32_t code = (uint32_t)tpi * 0x00010001u;
+          sp_pool_tap<FMT>(best[0], idx[0], v[tpi].x, code);
+          sp_pool_tap<FMT>(best[1], idx[1], v[tpi].y, code);
+          sp_pool_tap<FMT>(best[2], idx[2], v[tpi].z, code);
+          sp_pool_tap<FMT>(best[3], idx[3], v[tpi].w, code);
+        }
+        yo[o] = make_uint4(best[0], best[1], best[2], best[3]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {  // fold the ReLU mask into the code (see maxpool_kernel)
+          uint32_t pos;
+          if (FMT == GHND_F16) pos = __hgt2_mask(*reinterpret_cast<const __half2*>(&best[e]), __float2half2_rn(0.f));
+          else pos = __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&best[e]), __float2bfloat162_rn(0.f));
+          idx[e] = (idx[e] & pos) | (0x00ff00ffu & ~pos);
+        }
+        uint2 am;
+        am.x = __byte_perm(idx[0], idx[1], 0x6420);
+        am.y = __byte_perm(idx[2], idx[3], 0x6420);
+        ao[o] = am;
       }
       named_bar_sync(1, kSpEpiThreads);  // the tile may be overwritten by the next job's phase A
     }
