@@ -1,6 +1,7 @@
 """Debug: where does the engine's forward leave the storage-precision emulation (oracle16)?
 Compares intermediate teacher tensors of a GhndPlan with the emulation, stage by stage."""
 import os, sys
+os.environ.setdefault("GHND_STEM_POOL", "0")  # this script looks at conv1's output, which only the un-fused stem stores
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import ghnd_oracle as O, ghnd_oracle16 as E, weights

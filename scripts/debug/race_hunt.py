@@ -1,5 +1,6 @@
 """Debug: which teacher tensor is first corrupted when the step runs as a CUDA graph with the side stream?"""
 import os, sys
+os.environ.setdefault("GHND_STEM_POOL", "0")  # this script looks at conv1's output, which only the un-fused stem stores
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import weights

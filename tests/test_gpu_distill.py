@@ -48,12 +48,28 @@ def nchw_cpu(t):
     return t.float().permute(0, 3, 1, 2).contiguous().cpu()
 
 
+def student_conv1_output(plan):
+    """The student's conv1 (+FrozenBN, ReLU) output [N,Hp/2,Wp/2,64].  The fused stem+pool kernel never
+    stores it: recompute it with the stand-alone stem GEMM from the plan's own packed image and packed
+    weights (tests/test_gpu_kernels.py proves the fused kernel pools exactly this tensor)."""
+    from hnd_ghnd_object_detectors_b200 import ops
+    if plan.stem2 is not None and plan.stem2.conv is not None:
+        return plan.stem2.conv[..., 64:]
+    if plan.stem2 is None and plan.s_stem.conv is not None:
+        return plan.s_stem.conv
+    w, b = (plan.stem2.w[64:], plan.stem2.bias[64:].contiguous()) if plan.stem2 is not None else (plan.s_stem.w, plan.s_stem.shift)
+    y = torch.empty((plan.N, plan.Hp // 2, plan.Wp // 2, 64), dtype=plan.packed.dtype, device=plan.packed.device)
+    ops.StemPlan(plan.packed, w.contiguous(), b, y, plan.N, plan.Hp, plan.Wp).run()
+    torch.cuda.synchronize()
+    return y
+
+
 def engine_forward_tensors(plan):
     """What a GhndPlan stored in its forward pass, keyed by oracle16's storage-point names (teacher
     forcing): student conv1 output, every layer1 unit's raw / normalised tensor, every student-side
     Bottleneck activation of the (possibly shared, 2N-batch) frozen trunk; plus the teacher features."""
     N, p = plan.N, "backbone.body."
-    f = {p + "conv1": nchw_cpu(plan.stem2.conv[..., 64:] if plan.stem2 is not None else plan.s_stem.conv)}
+    f = {p + "conv1": nchw_cpu(student_conv1_output(plan))}
     f.update(layer1_forward_tensors(plan.s_l1, p + "layer1"))
     for name, r in plan.s_layers.items():
         for b, blk in enumerate(r.blocks):
