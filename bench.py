@@ -646,7 +646,7 @@ def run_cuda(args):
         finally:
             plan.side = side
         conv_s = sum(ep.get(k, (0.0, 0))[0] for k in ("ghnd_conv_plan_run", "ghnd_conv_plan_run_range",
-                                                      "ghnd_stem_conv_plan_run"))
+                                                      "ghnd_stem_conv_plan_run", "ghnd_stem_pool_plan_run"))
         n_conv = sum(p.n_launches for p in conv_plans(plan))
         flops = conv_flops_per_step(plan)
         achieved = flops / conv_s / 1e12
@@ -656,7 +656,7 @@ def run_cuda(args):
         if traffic is not None and ncu.get("launches") not in (None, n_conv):
             note = "STALE (%s launches captured, this build runs %d): %s" % (ncu.get("launches"), n_conv, note)
         roof = {"bound": "tensor",
-                "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv fwd/dgrad + stem, %d launches/step; "
+                "kernel": "conv_tc_kernel + stem_pool_kernel (tcgen05 implicit-GEMM conv fwd/dgrad, conv1 fused with its max-pool; %d launches/step; "
                           "achieved = algorithmic FLOPs of all launches / summed CUDA-event time)" % n_conv,
                 "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["bf16_tflops_sustained"],

@@ -22,7 +22,7 @@ while [ $# -ge 2 ]; do
          python scripts/join_launches.py gpurun_out/launches_$n.csv gpurun_out/step_ops.json > gpurun_out/per_layer_$n.txt 2>&1
          python scripts/summarize_launches.py gpurun_out/launches_$n.csv 40 > gpurun_out/launch_summary_$n.txt 2>&1; tail -1 gpurun_out/launch_summary_$n.txt ;;
     traffic) # DRAM bytes of every conv_tc_kernel launch of one eager step -> roofline.traffic (arg = batch)
-         timeout 1200 ncu --profile-from-start off --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:conv_tc --csv --log-file gpurun_out/conv_traffic_$n.csv python scripts/profile_step.py $arg > gpurun_out/traffic_$n.log 2>&1; echo "traffic_$n rc=$?"
+         timeout 1200 ncu --profile-from-start off --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k "regex:conv_tc|stem_pool" --csv --log-file gpurun_out/conv_traffic_$n.csv python scripts/profile_step.py $arg > gpurun_out/traffic_$n.log 2>&1; echo "traffic_$n rc=$?"
          python scripts/conv_traffic.py gpurun_out/conv_traffic_$n.csv gpurun_out/conv_dram_traffic_$n.json; cat gpurun_out/conv_dram_traffic_$n.json ;;
     bench) timeout 900 python bench.py $arg > gpurun_out/bench_$n.log 2> gpurun_out/bench_$n.err; echo "bench_$n rc=$?"; head -c 600 gpurun_out/bench_$n.log; echo ;;
     py) timeout 900 python $arg > gpurun_out/py_$n.log 2>&1; echo "py_$n rc=$?"; tail -30 gpurun_out/py_$n.log ;;
