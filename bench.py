@@ -385,19 +385,33 @@ def encode_sweep(dev, batches, iters=10, model_name="keypoint_rcnn"):
             qps = [plan.qparams] + [torch.empty_like(plan.qparams) for _ in range(3)]
             t = time_cold([lambda i=i: ops.quantize_u8_minmax(zs[i], plan.minmax, l1.z_pairs, 8, plan.scale_mode,
                                                               q=qs[i], qparams=qps[i]) for i in range(4)], dev)
-            kernels["quant_apply (one-pass 8-bit quantizer of the encode path, min/max from the encoder's last conv; 5 B/elem, batch %d)" % b] = 5.0 * nz / t
+            kernels["quant_apply (one-pass 8-bit quantizer of the encode path, min/max from the encoder's last conv; 5 B/elem, batch %d)" % b] = (5.0 * nz / t, 0.8)
             qws = ops.quantize_ws(z.numel(), dev)
             t = time_cold([lambda i=i: ops.quantize_u8(zs[i], 8, q=qs[i], qparams=qps[i], ws=qws) for i in range(4)], dev)
-            kernels["quantize_u8 (stand-alone quantize_tensor: min/max + quantize in one persistent launch; 5 B/elem compulsory, batch %d)" % b] = 5.0 * nz / t
+            kernels["quantize_u8 (stand-alone quantize_tensor: min/max + quantize in one persistent launch; 5 B/elem compulsory, batch %d)" % b] = (5.0 * nz / t, 0.8)
             q, qp = ops.quantize_u8(z, 8)
             qq = [q] + [q.clone() for _ in range(3)]
             t = time_cold([lambda i=i: ops.dequantize_u8(qq[i], qp, out=zs[i]) for i in range(4)], dev)
-            kernels["dequantize_u8 (1 B in, 4 B out per elem, batch %d)" % b] = 5.0 * nz / t
+            kernels["dequantize_u8 (1 B in, 4 B out per elem, batch %d)" % b] = (5.0 * nz / t, 0.2)
             xs = [l1.e2.out] + [l1.e2.out.clone() for _ in range(3)]
             t = time_cold([lambda i=i: ops.conv_narrow_out(xs[i], l1.enc7.weight, 1, y=zs[i], ws=l1.nws,
                                                            minmax=plan.minmax) for i in range(4)], dev)
-            kernels["narrow_out (encoder's last conv 64 -> bch k2 + min/max; 2 B/elem of the 64-ch input + 4 B/elem of z, batch %d)" % b] = (2.0 * wide + 4.0 * nz) / t
+            kernels["narrow_out (encoder's last conv 64 -> bch k2 + min/max; 2 B/elem of the 64-ch input + 4 B/elem of z, batch %d)" % b] = ((2.0 * wide + 4.0 * nz) / t, 2.0 * wide / (2.0 * wide + 4.0 * nz))
             del zs, qs, qq, xs
+            # The batch-64 tensor is 53 MB: a launch's fixed cost (~8 us of launch, prologue, ramp and tail; a
+            # torch copy of the same size has ~4 us and reaches 0.7 of the copy peak) weighs as much as the
+            # streaming.  The same kernels on a 16x larger tensor show the streaming rate by itself.
+            big = torch.randn(16 * z.numel(), device=dev)
+            bq, bqp = torch.empty(big.numel(), dtype=torch.uint8, device=dev), torch.empty_like(plan.qparams)
+            mm = torch.stack([big.min(), big.max()]).contiguous()
+            t = time_cold(lambda: ops.quantize_u8_minmax(big, mm, 1, 8, plan.scale_mode, q=bq, qparams=bqp), dev)
+            kernels["quant_apply, streaming rate (same kernel, 16x the batch-%d tensor = %.0f MB of fp32)" % (b, big.numel() * 4e-6)] = (5.0 * big.numel() / t, 0.8)
+            bws = ops.quantize_ws(big.numel(), dev)
+            t = time_cold(lambda: ops.quantize_u8(big, 8, q=bq, qparams=bqp, ws=bws), dev)
+            kernels["quantize_u8 stand-alone, streaming rate (two passes above 20 M elements: 9 B/elem of traffic for 5 B/elem compulsory; 16x tensor)"] = (5.0 * big.numel() / t, 0.8)
+            t = time_cold(lambda: ops.dequantize_u8(bq, bqp, out=big), dev)
+            kernels["dequantize_u8, streaming rate (16x tensor)"] = (5.0 * big.numel() / t, 0.2)
+            del big, bq
         head.plan = None
     return out, kernels
 
@@ -637,8 +651,17 @@ def run_cuda(args):
         peaks = measured_peaks()
         hbm = peaks["hbm_gbs"]
 
-        def entry(gbs):
-            return {"achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm}
+        def entry(gbs, read_share=None):
+            """frac: against the measured COPY bandwidth (MEASURED_PEAKS.json).  HBM on this part is
+            directional (profiles/r2_hbm_directional.txt: read-only 5777, write-only 3872, copy 6441 GB/s),
+            so a kernel with read share r of its bytes cannot stream faster than
+            1 / max(r/5777, (1-r)/3872, 1/6441) GB/s; frac_directional is measured against that."""
+            e = {"achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm}
+            if read_share is not None:
+                lim = 1.0 / max(read_share / 5777.0, (1.0 - read_share) / 3872.0, 1.0 / 6441.0)
+                e.update({"read_share": round(read_share, 3), "directional_peak": round(lim, 1),
+                          "frac_directional": gbs / lim})
+            return e
         # per-kernel timing pass: single stream (the side-stream branches would overlap the spans)
         side, plan.side = plan.side, None
         try:
@@ -670,8 +693,8 @@ def run_cuda(args):
         sse_bytes = 6.0 * sum(t.numel() for t in plan.feat_s.values())
         hbm_kernels = {}
         if "ghnd_sse_fwd_bwd" in ep:
-            hbm_kernels["sse_kernel (4-level loss fwd+bwd, 6 B/elem)"] = entry(sse_bytes / ep["ghnd_sse_fwd_bwd"][0] / 1e9)
-        # the other streaming kernels of the step: algorithmic bytes from the plan's tensors
+            hbm_kernels["sse_kernel (4-level loss fwd+bwd, 6 B/elem)"] = entry(sse_bytes / ep["ghnd_sse_fwd_bwd"][0] / 1e9, 4.0 / 6.0)
+        # the other streaming kernels of the step: algorithmic (read, write) bytes from the plan's tensors
         l1 = plan.s_l1
         units = [l1.e0, l1.e1, l1.e2, l1.d4, l1.d7, l1.d9]
         raw_elems = float(sum(u.raw.numel() for u in units))
@@ -682,27 +705,28 @@ def run_cuda(args):
         wide_e2, wide_r3 = float(l1.e2.out.numel()), raw3
         streaming = {
             "bn_finalize_apply (x -> y f16 [+ bf16 copy where a tensor-core dW reads it], 4-6 B/elem)":
-                ("ghnd_bn_finalize_apply",
-                 sum(u.raw.numel() * (6.0 if u.out_g is not None else 4.0) for u in units) + 6.0 * raw3),
-            "bn_bwd_reduce (g, x -> sums, 4 B/elem)": ("ghnd_bn_bwd_reduce", 4.0 * (raw_elems + raw3) + 8.0 * nz),
-            "bn_bwd_apply (g, x -> dx, 6 B/elem)": ("ghnd_bn_bwd_apply", 6.0 * (raw_elems + raw3) + 12.0 * nz),
+                ("ghnd_bn_finalize_apply", 2.0 * (raw_elems + raw3),
+                 sum(u.raw.numel() * (4.0 if u.out_g is not None else 2.0) for u in units) + 4.0 * raw3),
+            "bn_bwd_reduce (g, x -> sums, 4 B/elem)": ("ghnd_bn_bwd_reduce", 4.0 * (raw_elems + raw3) + 8.0 * nz, 0.0),
+            "bn_bwd_apply (g, x -> dx, 6 B/elem)":
+                ("ghnd_bn_bwd_apply", 4.0 * (raw_elems + raw3) + 8.0 * nz, 2.0 * (raw_elems + raw3) + 4.0 * nz),
             "maxpool 3x3 s2 fwd, teacher + student (2 B in, 2 B out, +1 B argmax)":
-                ("ghnd_maxpool3x3s2_strided", 4.0 * conv_elems + 5.0 * pool_elems),
-            "maxpool bwd + ReLU mask (x, dx 2 B/elem; dy + argmax 3 B/pooled elem)":
-                ("ghnd_maxpool3x3s2_bwd_strided", 4.0 * conv_elems + 3.0 * pool_elems),
+                ("ghnd_maxpool3x3s2_strided", 4.0 * conv_elems, 5.0 * pool_elems),
+            "maxpool bwd + ReLU mask (dx 2 B/elem written; dy + argmax 3 B/pooled elem read)":
+                ("ghnd_maxpool3x3s2_bwd_strided", 3.0 * pool_elems, 2.0 * conv_elems),
             # the bottleneck side (north_star (b)): wide 64-channel 16-bit tensor <-> planar fp32 bch tensor
             "narrow_out fwd (enc7: 64 -> bch k2 p1; 2 B/elem wide in + 4 B/elem z out)":
-                ("ghnd_conv_narrow_out", 2.0 * wide_e2 + 4.0 * nz),
+                ("ghnd_conv_narrow_out", 2.0 * wide_e2, 4.0 * nz),
             "narrow_in (dec2 fwd bch -> 64 with BN+ReLU prologue, and enc7 dgrad; 4 B/elem planar in + 2 B/elem wide out, 2 launches)":
-                ("ghnd_conv_narrow_in", 4.0 * nz + 2.0 * wide_r3 + 4.0 * nz + 2.0 * wide_e2),
+                ("ghnd_conv_narrow_in", 8.0 * nz, 2.0 * wide_r3 + 2.0 * wide_e2),
             "narrow_out dgrad (dec2: 64 -> bch; 2 B/elem wide in + 4 B/elem out)":
-                ("ghnd_conv_narrow_out_dgrad", 2.0 * wide_r3 + 4.0 * nz),
+                ("ghnd_conv_narrow_out_dgrad", 2.0 * wide_r3, 4.0 * nz),
             "wgrad_narrow (dec2 + enc7 dW; wide 2 B/elem + planar 4 B/elem, 2 launches)":
-                ("ghnd_wgrad_narrow", 2.0 * wide_r3 + 4.0 * nz + 2.0 * wide_e2 + 4.0 * nz),
+                ("ghnd_wgrad_narrow", 2.0 * wide_r3 + 4.0 * nz + 2.0 * wide_e2 + 4.0 * nz, 0.0),
         }
-        for label, (name, nbytes) in streaming.items():
+        for label, (name, rd, wr) in streaming.items():
             if name in ep and ep[name][0] > 0:
-                hbm_kernels[label] = entry(nbytes / ep[name][0] / 1e9)
+                hbm_kernels[label] = entry((rd + wr) / ep[name][0] / 1e9, rd / (rd + wr))
         breakdown = {k: round(v[0] * 1e3, 4) for k, v in sorted(ep.items(), key=lambda kv: -kv[1][0])}
         roof["entry_point_ms_per_step"] = breakdown
         if world == 1 and not args.no_encode:
@@ -711,8 +735,8 @@ def run_cuda(args):
                       "workload": "BASELINE config 5: Keypoint R-CNN b3ch RcnnHead (stem + layer1 encoder + 8-bit "
                                   "quantize), synthetic 3x800x1333, inputs resident in HBM, one scale/zero-point "
                                   "per call", "by_batch": sweep}
-            for label, bps in kern.items():
-                hbm_kernels[label] = entry(bps / 1e9)
+            for label, (bps, rshare) in kern.items():
+                hbm_kernels[label] = entry(bps / 1e9, rshare)
             # config 1 on the CUDA path: Faster R-CNN head + quantize at batch 2
             f_sweep, _ = encode_sweep(dev, [2], model_name="faster_rcnn")
             config1 = {"workload": "BASELINE config 1: Faster R-CNN b3ch head forward + 8-bit quantize, batch 2, "

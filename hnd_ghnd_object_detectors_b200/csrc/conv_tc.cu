@@ -111,6 +111,7 @@ struct ConvKernelParams {
   int org_dh, org_dw; // offset of the halo box origin from the tile origin
   int tap_off[kMaxTaps];  // byte offset of tap t's first row inside the halo tile
   int b_resident;
+  int pdl_late_wait;  // independent of the previous launch (see launch_conv): wait for it at the END
 };
 
 __device__ __forceinline__ int fd_ring_r(const ConvKernelParams& p, uint32_t cnt) {
@@ -467,7 +468,11 @@ __global__ void __launch_bounds__(kConvThreads, 1)
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
   // Programmatic dependent launch: everything above overlapped the previous kernel's tail; from
   // here on global memory written by it is read, so wait for its completion + flush.
-  asm volatile("griddepcontrol.wait;" ::: "memory");
+  // pdl_late_wait: this launch shares no data with the one before it in the stream (parity classes 2..4 of a
+  // stride-2 dgrad: same inputs, disjoint outputs), and that one waited for everything earlier before it let
+  // this one start -- so the launches of the plan run side by side on the SMs.  The wait moves to the end of
+  // the kernel, which keeps completion transitive: whoever waits for this launch has waited for all of them.
+  if (!p.pdl_late_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   const int k_chunks = p.cin / p.kblock;
@@ -1022,6 +1027,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+  if (p.pdl_late_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1665,7 +1671,12 @@ int ghnd_conv_plan_create(const ghnd_conv_desc_t* d, ghnd_conv_plan_t** out) {
           continue;
         }
         halo_failed = false;
-        if (rc == GHND_OK) plan->launches.push_back(L);
+        if (rc == GHND_OK) {
+          // parity classes after the first: concurrent with their predecessor (disjoint lattice outputs)
+          static const bool serial = getenv("GHND_S2_SERIAL") != nullptr;  // A/B switch
+          if (sub > 1 && !serial && !plan->launches.empty()) L.p.pdl_late_wait = 1;
+          plan->launches.push_back(L);
+        }
       }
     }
   }

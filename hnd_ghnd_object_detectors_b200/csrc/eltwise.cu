@@ -65,10 +65,11 @@ __global__ void nhwc_to_nchw_kernel(const uint16_t* __restrict__ src, int fmt,
 __global__ void stem_pack_kernel(const float* __restrict__ img, int H, int W, float m0, float m1,
                                  float m2, float s0, float s1, float s2, uint2* __restrict__ dst,
                                  int fmt, int rows, int cols) {
-  const int64_t total = (int64_t)rows * cols;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int r = (int)(i / cols), c = (int)(i - (int64_t)r * cols);
+  // grid (column blocks, rows): no per-pixel division (the flat-index version spent ~100 instructions per
+  // pixel on a 64-bit i / cols and ran at 1.1 TB/s)
+  const int r = blockIdx.y;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < cols; c += gridDim.x * blockDim.x) {
+    const int64_t i = (int64_t)r * cols + c;
     const int h = r - 3, w = c - 3;
     uint2 o = make_uint2(0u, 0u);
     if (h >= 0 && h < H && w >= 0 && w < W) {
@@ -94,11 +95,10 @@ __global__ void stem_pack_resize_kernel(const float* __restrict__ img, int H, in
                                         float rh, float rw, float m0, float m1, float m2, float s0,
                                         float s1, float s2, uint2* __restrict__ dst, int fmt,
                                         int rows, int cols) {
-  const int64_t total = (int64_t)rows * cols;
   const int64_t hw = (int64_t)H * W;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int r = (int)(i / cols), c = (int)(i - (int64_t)r * cols);
+  const int r = blockIdx.y;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < cols; c += gridDim.x * blockDim.x) {
+    const int64_t i = (int64_t)r * cols + c;
     const int h = r - 3, w = c - 3;
     uint2 o = make_uint2(0u, 0u);
     if (h >= 0 && h < Ho && w >= 0 && w < Wo) {
@@ -1000,7 +1000,8 @@ int ghnd_stem_pack_image(const float* img_chw, int H, int W, const float* mean, 
                  "stem_pack_image: bad geometry H=%d W=%d Hp=%d Wp=%d", H, W, Hp, Wp);
   const int rows = Hp + 6, cols = Wp + 8;
   uint2* d = (uint2*)dst + (int64_t)n_index * rows * cols;
-  stem_pack_kernel<<<grid_for((int64_t)rows * cols, 256), 256, 0, (cudaStream_t)stream>>>(
+  GHND_CHECK_ARG(rows <= 65535, "stem_pack_image: %d rows exceed the grid", rows);
+  stem_pack_kernel<<<dim3((unsigned)((cols + 255) / 256), (unsigned)rows), 256, 0, (cudaStream_t)stream>>>(
       img_chw, H, W, mean[0], mean[1], mean[2], std_[0], std_[1], std_[2], d, dst_fmt, rows, cols);
   GHND_LAUNCH_CHECK("stem_pack_kernel");
   return GHND_OK;
@@ -1017,7 +1018,8 @@ int ghnd_stem_pack_image_resized(const float* img_chw, int H, int W, int Ho, int
                  Wo, Hp, Wp);
   const int rows = Hp + 6, cols = Wp + 8;
   uint2* d = (uint2*)dst + (int64_t)n_index * rows * cols;
-  stem_pack_resize_kernel<<<grid_for((int64_t)rows * cols, 256), 256, 0, (cudaStream_t)stream>>>(
+  GHND_CHECK_ARG(rows <= 65535, "stem_pack_image_resized: %d rows exceed the grid", rows);
+  stem_pack_resize_kernel<<<dim3((unsigned)((cols + 255) / 256), (unsigned)rows), 256, 0, (cudaStream_t)stream>>>(
       img_chw, H, W, Ho, Wo, rscale_h, rscale_w, mean[0], mean[1], mean[2], std_[0], std_[1], std_[2],
       d, dst_fmt, rows, cols);
   GHND_LAUNCH_CHECK("stem_pack_resize_kernel");

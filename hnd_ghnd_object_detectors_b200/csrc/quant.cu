@@ -2,6 +2,7 @@
 // Arithmetic follows src/myutils/pytorch/tensor_util.py:8-22 of the reference operation by
 // operation with explicit round-to-nearest intrinsics (no FMA contraction, no fast division).
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -10,12 +11,17 @@ namespace ghnd {
 static constexpr int kQThreads = 256;
 static constexpr int kQMaxBlocks = 1024;
 
-// torch.min/max propagate NaN
+// torch.min/max propagate NaN: min.NaN / max.NaN do exactly that in ONE instruction (FMNMX.NAN; the
+// compare-and-select form was 4-5 instructions per element and made the min/max passes issue-bound)
 __device__ __forceinline__ float nan_min(float a, float b) {
-  return (a != a) ? a : ((b != b) ? b : fminf(a, b));
+  float r;
+  asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
 }
 __device__ __forceinline__ float nan_max(float a, float b) {
-  return (a != a) ? a : ((b != b) ? b : fmaxf(a, b));
+  float r;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
 }
 
 __device__ __forceinline__ void block_minmax(float& mn, float& mx) {
@@ -105,16 +111,18 @@ __device__ __forceinline__ uint32_t quant1(float v, float zpf, float scale, floa
   return (uint32_t)(int)rintf(t) & 0xffu;
 }
 // Exact-result fast path.  The IEEE division per element (~20 issue slots with its slow path) kept the
-// quantizer at 30-40 % of HBM.  Here t' = zp + x * RN(1/scale) replaces t = zp + RN(x / scale): for a
-// quotient inside [-256, 512] the two differ by < 1.3e-4 (3 roundings of 2^-24 relative on |q| <= 512,
-// plus half an ulp of the sum), quotients outside clamp to the same end.  The byte is
-// round-half-even(clamp(t)); it can only differ from the reference's when t' lies within that error
-// of a rounding boundary k + 0.5, so a 4-element vector whose t' comes within kQuantGuard = 2^-11 of a
-// boundary (0.1 % of elements) is redone with the reference's exact sequence.  Rounding and the
-// float -> byte conversion use the 1.5 * 2^23 magic constant (round-half-even in the FADD itself, the
-// integer sits in the low mantissa byte): no F2I / FRND on the conversion pipe.
+// quantizer at 30-40 % of HBM.  Here t' = RN(zp + x * RN(1/scale)) (one FFMA) replaces the reference's
+// t = RN(zp + RN(x / scale)).  For a quotient inside [-256, 512]: |x*r - x/scale| <= 512 * 2^-24 = 3.1e-5,
+// the reference's quotient rounding <= 2^-16, the two final roundings <= 2^-16 each -> |t' - t| < 7.7e-5;
+// quotients outside clamp to the same end.  The byte is round-half-even(clamp(t)); it can only differ from
+// the reference's when t' lies within that error of a rounding boundary k + 0.5, so an element whose t'
+// comes within kQuantGuard = 2^-12 (3x the bound) of a boundary -- 0.05 % of elements -- is redone with the
+// reference's exact sequence.  Rounding and the float -> byte conversion use the 1.5 * 2^23 magic constant
+// (round-half-even in the FADD itself, the integer sits in the low mantissa byte): no F2I / FRND on the
+// conversion pipe.  ~34 instructions per 4 elements: 4 x (FFMA, 2 FMNMX, 3 FADD) + |d| maximum, one
+// compare and one branch per vector, 3 PRMT.
 static constexpr float kQuantMagic = 12582912.0f;  // 1.5 * 2^23
-static constexpr float kQuantGuard = 0.5f - 0.00048828125f;
+static constexpr float kQuantGuard = 0.5f - 0.000244140625f;
 struct QFast {
   float zpf, scale, rscale, qmax;
   bool ok;  // scale is a normal number with a finite reciprocal: the error bound above holds
@@ -131,19 +139,36 @@ __device__ __forceinline__ QFast make_qfast(float zpf, float scale, float qmax) 
 __device__ __forceinline__ uint32_t quant4(uint4 v, const QFast& f) {
   const float x[4] = {__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w)};
   uint32_t m[4];
-  bool near = !f.ok;
+  float d[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
-    float t = __fadd_rn(f.zpf, __fmul_rn(x[e], f.rscale));
+    float t = __fmaf_rn(x[e], f.rscale, f.zpf);
     t = fminf(fmaxf(t, 0.0f), f.qmax);            // NaN -> 0, like (int)rintf(NaN) & 0xff
     const float r = __fadd_rn(t, kQuantMagic);    // low mantissa byte = round-half-even(t)
     m[e] = __float_as_uint(r);
-    near |= fabsf(__fsub_rn(t, __fsub_rn(r, kQuantMagic))) > kQuantGuard;
+    d[e] = fabsf(__fsub_rn(t, __fsub_rn(r, kQuantMagic)));  // distance to the nearest integer, exact
   }
-  if (near)
-    return quant1(x[0], f.zpf, f.scale, f.qmax) | (quant1(x[1], f.zpf, f.scale, f.qmax) << 8) |
-           (quant1(x[2], f.zpf, f.scale, f.qmax) << 16) | (quant1(x[3], f.zpf, f.scale, f.qmax) << 24);
+  if (!f.ok || fmaxf(fmaxf(d[0], d[1]), fmaxf(d[2], d[3])) > kQuantGuard) {  // rare: redo the doubtful elements
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (!f.ok || d[e] > kQuantGuard) m[e] = quant1(x[e], f.zpf, f.scale, f.qmax);
+  }
   return __byte_perm(__byte_perm(m[0], m[1], 0x0040), __byte_perm(m[2], m[3], 0x0040), 0x5410);
+}
+
+// grid-stride quantization of 4-element vectors [first, n4), four loads in flight per thread
+template <typename I>
+__device__ __forceinline__ void quant_stream(const uint4* __restrict__ x4, uint32_t* __restrict__ q4, I i,
+                                             const I nthreads, const I n4, const QFast& qf) {
+  for (; i + 3 * nthreads < n4; i += 4 * nthreads) {
+    const uint4 a = ld_stream(x4 + i), b = ld_stream(x4 + i + nthreads), c = ld_stream(x4 + i + 2 * nthreads),
+                d = ld_stream(x4 + i + 3 * nthreads);
+    q4[i] = quant4(a, qf);
+    q4[i + nthreads] = quant4(b, qf);
+    q4[i + 2 * nthreads] = quant4(c, qf);
+    q4[i + 3 * nthreads] = quant4(d, qf);
+  }
+  for (; i < n4; i += nthreads) q4[i] = quant4(ld_stream(x4 + i), qf);
 }
 
 // pass 2: every block folds the partials (L2 resident), derives scale / zero-point, quantizes.
@@ -158,13 +183,12 @@ __global__ void __launch_bounds__(kQThreads)
   // this 15-20 us kernel: every block starts with it)
   const int64_t n4 = vec_ok ? (n >> 2) : 0;
   const uint4* x4 = reinterpret_cast<const uint4*>(x);
-  uint4 pa = make_uint4(0, 0, 0, 0), pb = pa, pc = pa, pd = pa;
-  const bool pre = tid + 3 * nthreads < n4;
+  constexpr int kPre = 4;  // 64 B per thread in flight across the prologue (8 measured no faster, 60 registers)
+  uint4 pv[kPre];
+  const bool pre = tid + (kPre - 1) * nthreads < n4;
   if (pre) {
-    pa = ld_stream(x4 + tid);
-    pb = ld_stream(x4 + tid + nthreads);
-    pc = ld_stream(x4 + tid + 2 * nthreads);
-    pd = ld_stream(x4 + tid + 3 * nthreads);
+#pragma unroll
+    for (int k = 0; k < kPre; ++k) pv[k] = ld_stream(x4 + tid + k * nthreads);
   }
   float mn = INFINITY, mx = -INFINITY;
   for (int i = threadIdx.x; i < n_partial; i += blockDim.x) {
@@ -189,23 +213,14 @@ __global__ void __launch_bounds__(kQThreads)
     // contiguous bytes per store (the first version gave every lane its own 64-byte run: each 32-byte
     // sector was requested by two different instructions and, with L1 allocation off, fetched twice)
     uint32_t* q4 = reinterpret_cast<uint32_t*>(q);
-    int64_t i = tid;
     if (pre) {
-      q4[i] = quant4(pa, qf);
-      q4[i + nthreads] = quant4(pb, qf);
-      q4[i + 2 * nthreads] = quant4(pc, qf);
-      q4[i + 3 * nthreads] = quant4(pd, qf);
-      i += 4 * nthreads;
+#pragma unroll
+      for (int k = 0; k < kPre; ++k) q4[tid + k * nthreads] = quant4(pv[k], qf);
     }
-    for (; i + 3 * nthreads < n4; i += 4 * nthreads) {
-      const uint4 a = ld_stream(x4 + i), b = ld_stream(x4 + i + nthreads), c = ld_stream(x4 + i + 2 * nthreads),
-                  d = ld_stream(x4 + i + 3 * nthreads);
-      q4[i] = quant4(a, qf);
-      q4[i + nthreads] = quant4(b, qf);
-      q4[i + 2 * nthreads] = quant4(c, qf);
-      q4[i + 3 * nthreads] = quant4(d, qf);
-    }
-    for (; i < n4; i += nthreads) q4[i] = quant4(ld_stream(x4 + i), qf);
+    const int64_t first = pre ? tid + kPre * nthreads : tid;
+    // 32-bit indices whenever they fit (the 64-bit index arithmetic was ~10 % of the issued instructions)
+    if (n4 + 4 * nthreads < (int64_t)0x7fffffff) quant_stream<int>(x4, q4, (int)first, (int)nthreads, (int)n4, qf);
+    else quant_stream<int64_t>(x4, q4, first, nthreads, n4, qf);
     done = n4 << 2;
   }
   for (int64_t i = done + tid; i < n; i += nthreads) q[i] = (uint8_t)quant1(x[i], zpf, scale, qmax);
@@ -397,7 +412,15 @@ int ghnd_quantize_u8(const float* x, int64_t n, int num_bits, int scale_mode, ui
   const int blocks = quant_blocks(n);
   const float qmax = (float)((1 << num_bits) - 1);
   const float inv_range = 1.0f / qmax;  // torch CUDA: a / cpu_scalar == a * (1/scalar) in fp32
-  if (vec_ok && n >= 4096) {
+  // Above ~20 M elements a CTA's slice no longer fits its shared memory (the rest is re-read) and two
+  // full-occupancy passes are faster than one launch of 148 CTAs (B200: 89 vs 115 us at 53 M elements,
+  // 310 vs 453 us at 213 M; 33.5 vs 31.6 us at 13 M).  GHND_QUANT_TWO_PASS=1|0 forces either.
+  static const int two_pass_env = [] {
+    const char* e = getenv("GHND_QUANT_TWO_PASS");
+    return e == nullptr ? -1 : atoi(e);
+  }();
+  const bool two_pass = two_pass_env >= 0 ? two_pass_env != 0 : n > (int64_t)20 << 20;
+  if (vec_ok && n >= 4096 && !two_pass) {
     // single persistent launch; workspace = [2 * kQMaxBlocks floats of partials][4 barrier words]
     static bool attr_set = false;
     if (!attr_set) {

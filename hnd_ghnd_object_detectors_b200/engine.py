@@ -183,7 +183,7 @@ class BottleneckRunner(object):
     def backward(self, side=None):
         for p in self.bwd:
             n = p.n_launches
-            if side is not None and n > 1 and p is self.bwd[1]:
+            if side is not None and n > 1 and p is self.bwd[1] and os.environ.get("GHND_S2_SIDE", "0") == "1":
                 # stride-2 3x3 dgrad = one small launch per output parity class, disjoint outputs:
                 # half of them on the second stream
                 side.fork()
