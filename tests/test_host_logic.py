@@ -267,20 +267,36 @@ def test_two_rank_training_keeps_replicas_identical():
     """world_size 2, gloo: ranks begin with different random parameters and see different data; after
     broadcast + 3 x (backward -> flat all-reduce -> fused Adam) both hold identical parameters, and
     those equal single-process Adam on the rank-averaged gradient."""
+    import queue
     import socket
     import torch.multiprocessing as mp
-    s = socket.socket()
-    s.bind(("127.0.0.1", 0))
-    port = s.getsockname()[1]
-    s.close()
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    procs = [ctx.Process(target=_train_worker, args=(r, 2, port, q)) for r in range(2)]
-    for p in procs:
-        p.start()
-    res = sorted([q.get(timeout=180) for _ in procs], key=lambda t: t[0])
-    for p in procs:
-        p.join(timeout=60)
+    res = None
+    for attempt in range(3):  # the rendezvous port is picked, released and re-bound: retry a lost race
+        s = socket.socket()
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+        s.close()
+        ctx = mp.get_context("spawn")
+        q = ctx.Queue()
+        procs = [ctx.Process(target=_train_worker, args=(r, 2, port, q)) for r in range(2)]
+        for p in procs:
+            p.start()
+        got, waited = [], 0
+        while len(got) < 2 and waited < 180:
+            try:
+                got.append(q.get(timeout=5))
+            except queue.Empty:
+                waited += 5
+                if not any(p.is_alive() for p in procs):  # a worker died without reporting
+                    break
+        res = sorted(got, key=lambda t: t[0]) if len(got) == 2 else None
+        for p in procs:
+            p.join(timeout=60)
+            if p.is_alive():
+                p.kill()
+        if res is not None:
+            break
+    assert res is not None, "2-rank gloo workers did not report"
     (_, s0, p0, rm0, g0), (_, s1, p1, rm1, g1) = res
     assert torch.equal(s0, s1) and torch.equal(rm0, rm1)      # broadcast at start
     assert torch.equal(p0, p1) and not torch.equal(p0, s0)    # replicas stay identical and did move
