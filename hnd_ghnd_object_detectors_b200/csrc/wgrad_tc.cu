@@ -2,15 +2,23 @@
 //
 //   dw[k][tap][c] = sum_{pixels} dy[pixel][k] * x[pixel + tap_offset][c]
 //
-// Both operands are read straight out of the NHWC tensors by TMA as [32 pixels][64 channels]
-// 128B-swizzled boxes, i.e. they sit in shared memory "MN-major" (channel contiguous, the GEMM
-// reduction axis = pixel is the strided one); the instruction descriptor's a_major/b_major bits
-// select that layout, so no transpose pass is needed.
+// Both operands are read straight out of the NHWC tensors by TMA as 128B-swizzled [pixels][64 channels]
+// boxes, i.e. they sit in shared memory "MN-major" (channel contiguous, the GEMM reduction axis = pixel
+// is the strided one); the instruction descriptor's a_major/b_major bits select that layout, so no
+// transpose pass is needed.  A pipeline stage reduces over 2 image rows x 32 pixels of dy:
+//   dy box  {64 ch, 32 px, 2 rows}                              =  8 KB per 64 channels
+//   x  box  {64 ch, 32+S-1 px (rounded up to 8), 2+R-1 rows}    = 15 KB per 64 channels for 2x2 taps
+// ONE x box serves every tap: tap (r, s) is the same box read through a descriptor whose start address is
+// shifted by (r * box width + s) pixels = that many 128-byte rows (the 128B swizzle is a function of the
+// absolute shared-memory address, so a shifted start stays consistent with what TMA wrote).  The first
+// version loaded one shifted x box per tap (5-10 boxes of 4 KB per 32 pixels): 2.5x the L2 -> SM traffic
+// and ~4x the TMA issues, 1.8 TB/s on the 64-channel dWs.
 //
 // One CTA owns a 128 (rows operand) x NB (cols operand, <=128) output block for ALL taps (<=4):
 // the accumulators fill TMEM (4 x 128 columns).  The pixel axis is split over CTAs; every CTA adds
 // its partial block into the fp32 dw with red.global.add.f32 (dw is zeroed by the plan first).
-// Zero padding of x and the ragged right edge of dy both come from TMA out-of-bounds zero fill.
+// Zero padding of x and the ragged right / bottom edge of dy both come from TMA out-of-bounds zero fill.
+#include <stdlib.h>
 #include <vector>
 
 #include "common.cuh"
@@ -18,13 +26,17 @@
 namespace ghnd {
 
 static constexpr int kWgThreads = 224;  // warp0/6 TMA producers, warp1 MMA, warps 2..5 epilogue
-static constexpr int kWgPix = 32;                  // pixels (GEMM-K) per pipeline stage
-static constexpr int kWgBox = kWgPix * 128;        // bytes of one [32 px][64 ch] box = 4 KB
+static constexpr int kWgPix = 32;                  // dy pixels along W per box row
+static constexpr int kWgRows = 2;                  // dy rows per box: a stage reduces over 2 x 32 pixels
+static constexpr int kWgDyBox = kWgRows * kWgPix * 128;  // bytes of one dy box = 8 KB
 static constexpr int kWgMaxTaps = 4;
 
 struct WgradParams {
-  CUtensorMap tmap_row;   // rows operand tensor (GEMM M): box {64, 32, 1, 1}
+  CUtensorMap tmap_row;   // rows operand tensor (GEMM M): dy box {64, 32, 2, 1} or x box {64, xw, xr, 1}
   CUtensorMap tmap_col;   // cols operand tensor (GEMM N)
+  int xw;                 // x box width in pixels (32 + S - 1, rounded up to 8)
+  int x_box_bytes;        // xw * (2 + R - 1) * 128
+  int debug;              // GHND_WGRAD_DEBUG: 1 = no MMAs, 2 = no TMA loads, 4 = no epilogue (timing experiments)
   int rows_is_dy;         // 1: rows = dy channels (k), cols = x channels (c); 0: swapped
   int n_taps, S;
   int pad;
@@ -35,10 +47,10 @@ struct WgradParams {
   int col_boxes;          // nb / 64
   int splits;             // CTAs per output block (pixel-axis split)
   int n_img, ho, wo;      // dy geometry
+  int hp;                 // row pairs per image = ceil(ho / 2)
   int tiles_w;            // ceil(wo / 32)
-  int total_pix_tiles;    // n_img * ho * tiles_w
+  int total_pix_tiles;    // n_img * hp * tiles_w
   int stage_bytes, n_stages;
-  int tap_dh[kWgMaxTaps], tap_dw[kWgMaxTaps];  // x offset of every tap (already minus pad)
   FastDiv fd_tiles_per_img, fd_tiles_w;
   uint32_t idesc;
   float* dw;              // [K][taps][C]
@@ -46,7 +58,7 @@ struct WgradParams {
 };
 
 
-// the two K=16 MMAs of one 32-pixel stage for one tap (second descriptor = +2048 B)
+// two K=16 MMAs (32 pixels) of a stage for one tap (second descriptor = +2048 B); a stage issues two such pairs
 __device__ __forceinline__ void umma_pair_wg(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo,
                                              uint32_t desc_hi, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -107,64 +119,40 @@ __global__ void __launch_bounds__(kWgThreads, 1)
   const int n_chunk = block - m_tile * p.n_chunks;
   const int t_begin = (int)(((int64_t)p.total_pix_tiles * split) / p.splits);
   const int t_end = (int)(((int64_t)p.total_pix_tiles * (split + 1)) / p.splits);
-  const int a_bytes = p.row_boxes * kWgBox;
-  const int b_tap_bytes = p.col_boxes * kWgBox;
+  // stage = [rows operand boxes][cols operand boxes]; the dy side has 8 KB boxes, the x side x_box_bytes
+  const int row_box = p.rows_is_dy ? kWgDyBox : p.x_box_bytes;
+  const int col_box = p.rows_is_dy ? p.x_box_bytes : kWgDyBox;
+  const int a_bytes = p.row_boxes * row_box;
 
   if (warp == 0 || warp == 6) {
-    // Two TMA producer warps (whole warp converged, one elected lane issues).  A single thread
-    // issuing all ~10 small boxes of a stage was the bottleneck of this kernel (ncu: MMA warp
-    // starved while the producer never waited for a free slot), so the taps are split in halves.
-    const int pw = warp == 0 ? 0 : 1;
-    const int tap_lo = pw == 0 ? 0 : (p.n_taps + 1) / 2;
-    const int tap_hi = pw == 0 ? (p.n_taps + 1) / 2 : p.n_taps;
+    // Two TMA producer warps (whole warp converged, one elected lane issues): warp 0 loads the rows operand,
+    // warp 6 the cols operand of every stage; each posts its own byte count on the stage's barrier.
+    const bool is_rows = warp == 0;
+    const bool is_dy = is_rows == (p.rows_is_dy != 0);
+    const CUtensorMap* map = is_rows ? &p.tmap_row : &p.tmap_col;
+    const int n_box = is_rows ? p.row_boxes : p.col_boxes;
+    const int box_bytes = is_rows ? row_box : col_box;
+    const int ch0 = is_rows ? m_tile * 128 : n_chunk * p.nb;
+    const int off = is_dy ? 0 : -p.pad;  // x box origin = dy position - pad
     int stage = 0;
     uint32_t phase = 0;
     // (img, h, wt) of the first tile by multiply-high division, then carried incrementally
     int img, rem, h, wt;
     fd_divmod(p.fd_tiles_per_img, t_begin, img, rem);
     fd_divmod(p.fd_tiles_w, rem, h, wt);
-    // bytes this warp posts per stage: its taps of the shifted operand (+ the unshifted one for pw 0)
-    const uint32_t shifted_bytes = (uint32_t)((tap_hi - tap_lo) * (p.rows_is_dy ? b_tap_bytes : a_bytes));
-    const uint32_t fixed_bytes = pw == 0 ? (uint32_t)(p.rows_is_dy ? a_bytes : b_tap_bytes) : 0u;
     for (int t = t_begin; t < t_end; ++t) {
-      const int w0 = wt * kWgPix;
       mbar_wait(&empty_bar[stage], phase ^ 1);
       if (elect_one()) {
-        uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
-        uint8_t* sb = sa + a_bytes;
-        mbar_arrive_expect_tx(&full_bar[stage], shifted_bytes + fixed_bytes);
-        if (p.rows_is_dy) {
-          // rows operand = dy (unshifted), cols operand = x shifted per tap
-          if (pw == 0)
-            for (int b = 0; b < p.row_boxes; ++b)
-              tma_load_4d(sa + b * kWgBox, &p.tmap_row, &full_bar[stage], m_tile * 128 + b * 64, w0, h,
-                          img);
-          for (int tap = tap_lo; tap < tap_hi; ++tap) {
-            const int dh = p.tap_dh[tap], dw = p.tap_dw[tap];
-            for (int b = 0; b < p.col_boxes; ++b)
-              tma_load_4d(sb + tap * b_tap_bytes + b * kWgBox, &p.tmap_col, &full_bar[stage],
-                          n_chunk * p.nb + b * 64, w0 + dw, h + dh, img);
-          }
-        } else {
-          // rows = x channels: A region holds n_taps shifted x tiles, B region the single dy tile
-          for (int tap = tap_lo; tap < tap_hi; ++tap) {
-            const int dh = p.tap_dh[tap], dw = p.tap_dw[tap];
-            for (int b = 0; b < p.row_boxes; ++b)
-              tma_load_4d(sa + tap * a_bytes + b * kWgBox, &p.tmap_row, &full_bar[stage],
-                          m_tile * 128 + b * 64, w0 + dw, h + dh, img);
-          }
-          if (pw == 0) {
-            uint8_t* sd = sa + p.n_taps * a_bytes;
-            for (int b = 0; b < p.col_boxes; ++b)
-              tma_load_4d(sd + b * kWgBox, &p.tmap_col, &full_bar[stage], n_chunk * p.nb + b * 64, w0,
-                          h, img);
-          }
-        }
+        uint8_t* dst = smem + (size_t)stage * p.stage_bytes + (is_rows ? 0 : a_bytes);
+        mbar_arrive_expect_tx(&full_bar[stage], (p.debug & 2) ? 0u : (uint32_t)(n_box * box_bytes));
+        for (int b = 0; b < n_box && !(p.debug & 2); ++b)
+          tma_load_4d(dst + b * box_bytes, map, &full_bar[stage], ch0 + b * 64, wt * kWgPix + off,
+                      kWgRows * h + off, img);
       }
       __syncwarp();
       if (++wt == p.tiles_w) {
         wt = 0;
-        if (++h == p.ho) {
+        if (++h == p.hp) {
           h = 0;
           ++img;
         }
@@ -181,28 +169,31 @@ __global__ void __launch_bounds__(kWgThreads, 1)
     uint32_t phase = 0;
     const uint32_t smem_base = smem_u32(smem);
     // rows operand with a single 64-channel box: rows 64..127 alias rows 0..63 (LBO = 0)
-    const uint32_t a_lbo = p.row_boxes == 2 ? kWgBox : 0;
-    const uint32_t b_lbo = kWgBox;
+    const uint32_t a_lbo = p.row_boxes == 2 ? (uint32_t)row_box : 0u;
+    const uint32_t b_lbo = (uint32_t)col_box;
     const uint32_t desc_hi = (1024u >> 4) | (1u << 14) | ((uint32_t)UMMA_SW128 << 29);
     for (int t = t_begin; t < t_end; ++t) {
       mbar_wait(&full_bar[stage], phase);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t sa = smem_base + (uint32_t)(stage * p.stage_bytes);
-        for (int tap = 0; tap < p.n_taps; ++tap) {
-          uint32_t a_addr, b_addr;
-          if (p.rows_is_dy) {
-            a_addr = sa;
-            b_addr = sa + a_bytes + tap * b_tap_bytes;
-          } else {
-            a_addr = sa + tap * a_bytes;
-            b_addr = sa + p.n_taps * a_bytes;
+        const uint32_t sb = sa + (uint32_t)a_bytes;
+        const uint32_t dy_base = p.rows_is_dy ? sa : sb, x_base = p.rows_is_dy ? sb : sa;
+        for (int tap = 0; tap < p.n_taps && !(p.debug & 1); ++tap) {
+          const int tr = tap / p.S, ts = tap - tr * p.S;
+#pragma unroll
+          for (int r = 0; r < kWgRows; ++r) {
+            // dy row r of the stage against x row r + tr, shifted by ts pixels (128 B per pixel)
+            const uint32_t dy_addr = dy_base + (uint32_t)(r * kWgPix * 128);
+            const uint32_t x_addr = x_base + (uint32_t)(((r + tr) * p.xw + ts) * 128);
+            const uint32_t a_addr = p.rows_is_dy ? dy_addr : x_addr;
+            const uint32_t b_addr = p.rows_is_dy ? x_addr : dy_addr;
+            const uint32_t a_lo = ((a_addr >> 4) & 0x3fffu) | ((a_lbo >> 4) << 16);
+            const uint32_t b_lo = ((b_addr >> 4) & 0x3fffu) | ((b_lbo >> 4) << 16);
+            // 16 pixels = two 8-row swizzle groups = 2048 B -> +128 in (addr >> 4)
+            umma_pair_wg(tmem_base + (uint32_t)(tap * 128), a_lo, b_lo, desc_hi, p.idesc,
+                         (uint32_t)(t != t_begin || r != 0));
           }
-          const uint32_t a_lo = ((a_addr >> 4) & 0x3fffu) | ((a_lbo >> 4) << 16);
-          const uint32_t b_lo = ((b_addr >> 4) & 0x3fffu) | ((b_lbo >> 4) << 16);
-          // 16 pixels = two 8-row swizzle groups = 2048 B -> +128 in (addr >> 4)
-          umma_pair_wg(tmem_base + (uint32_t)(tap * 128), a_lo, b_lo, desc_hi, p.idesc,
-                       (uint32_t)(t != t_begin));
         }
         umma_commit(&empty_bar[stage]);
       }
@@ -217,7 +208,7 @@ __global__ void __launch_bounds__(kWgThreads, 1)
   } else if (warp < 6) {
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
-    if (t_end > t_begin) {
+    if (t_end > t_begin && !(p.debug & 4)) {
       mbar_wait(done_bar, 0);
       tc_fence_after();
       const int taps = p.n_taps;
@@ -307,24 +298,28 @@ int ghnd_wgrad_plan_create(const ghnd_wgrad_desc_t* d, ghnd_wgrad_plan_t** out) 
   p.ho = Ho;
   p.wo = Wo;
   p.tiles_w = (Wo + kWgPix - 1) / kWgPix;
-  p.total_pix_tiles = d->N * Ho * p.tiles_w;
-  p.fd_tiles_per_img = make_fastdiv(Ho * p.tiles_w);
+  p.hp = (Ho + kWgRows - 1) / kWgRows;
+  p.total_pix_tiles = d->N * p.hp * p.tiles_w;
+  p.fd_tiles_per_img = make_fastdiv(p.hp * p.tiles_w);
   p.fd_tiles_w = make_fastdiv(p.tiles_w);
-  for (int tap = 0; tap < p.n_taps; ++tap) {
-    p.tap_dh[tap] = tap / d->S - d->pad;
-    p.tap_dw[tap] = tap % d->S - d->pad;
-  }
   const int blocks = p.m_tiles * p.n_chunks;
   int splits = num_sms() / blocks;
   if (splits < 1) splits = 1;
   if (splits > p.total_pix_tiles) splits = p.total_pix_tiles;
   p.splits = splits;
-  // stage: rows operand boxes + cols operand boxes; the shifted (x) side is replicated per tap
-  const int row_bytes = p.row_boxes * kWgBox, col_bytes = p.col_boxes * kWgBox;
-  p.stage_bytes = p.rows_is_dy ? row_bytes + p.n_taps * col_bytes : p.n_taps * row_bytes + col_bytes;
+  // stage: rows operand boxes + cols operand boxes (dy: 8 KB, x: one halo box serving every tap)
+  p.xw = (kWgPix + d->S - 1 + 7) / 8 * 8;
+  p.x_box_bytes = p.xw * (kWgRows + d->R - 1) * 128;
+  const int row_bytes = p.row_boxes * (p.rows_is_dy ? kWgDyBox : p.x_box_bytes);
+  const int col_bytes = p.col_boxes * (p.rows_is_dy ? p.x_box_bytes : kWgDyBox);
+  p.stage_bytes = row_bytes + col_bytes;
   int stages = (200 * 1024) / p.stage_bytes;
-  if (stages > 8) stages = 8;
+  if (stages > 12) stages = 12;
   p.n_stages = stages;
+  {
+    const char* e = getenv("GHND_WGRAD_DEBUG");
+    p.debug = e ? atoi(e) : 0;
+  }
   const int a_fmt = p.rows_is_dy ? d->dy_fmt : d->x_fmt;
   const int b_fmt = p.rows_is_dy ? d->x_fmt : d->dy_fmt;
   p.idesc = make_idesc(a_fmt, b_fmt, 1, 1, 128, p.nb);
@@ -332,15 +327,16 @@ int ghnd_wgrad_plan_create(const ghnd_wgrad_desc_t* d, ghnd_wgrad_plan_t** out) 
   p.K = d->K;
   p.C = d->C;
 
-  uint32_t box[4] = {64, (uint32_t)kWgPix, 1, 1};
+  uint32_t box_dy[4] = {64, (uint32_t)kWgPix, (uint32_t)kWgRows, 1};
+  uint32_t box_x[4] = {64, (uint32_t)p.xw, (uint32_t)(kWgRows + d->R - 1), 1};
   uint64_t dims_dy[4] = {(uint64_t)d->K, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)d->N};
   uint64_t str_dy[4] = {2, (uint64_t)d->K * 2, (uint64_t)Wo * d->K * 2, (uint64_t)Ho * Wo * d->K * 2};
   uint64_t dims_x[4] = {(uint64_t)d->C, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N};
   uint64_t str_x[4] = {2, (uint64_t)d->C * 2, (uint64_t)d->W * d->C * 2,
                        (uint64_t)d->H * d->W * d->C * 2};
   CUtensorMap map_dy, map_x;
-  int rc = encode_tmap(&map_dy, 2, 4, const_cast<void*>(d->dy), dims_dy, str_dy, box, 128);
-  if (rc == GHND_OK) rc = encode_tmap(&map_x, 2, 4, const_cast<void*>(d->x), dims_x, str_x, box, 128);
+  int rc = encode_tmap(&map_dy, 2, 4, const_cast<void*>(d->dy), dims_dy, str_dy, box_dy, 128);
+  if (rc == GHND_OK) rc = encode_tmap(&map_x, 2, 4, const_cast<void*>(d->x), dims_x, str_x, box_x, 128);
   if (rc != GHND_OK) {
     delete plan;
     return rc;
