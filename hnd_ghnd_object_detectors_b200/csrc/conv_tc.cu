@@ -112,6 +112,11 @@ struct ConvKernelParams {
   int tap_off[kMaxTaps];  // byte offset of tap t's first row inside the halo tile
   int b_resident;
   int pdl_late_wait;  // independent of the previous launch (see launch_conv): wait for it at the END
+  int mc;             // launched as clusters of 2 CTAs that work on the SAME n-tile of two neighbouring m-tiles
+                      // (generic mode).  1: each CTA fetches half of every weight tile and TMA-multicasts it to
+                      // both (measured neutral: the SM still ingests the whole tile); 2: CTA pair, ONE M=256
+                      // cta_group::2 MMA over both CTAs, each holds only its half of the weight tile (b_bytes)
+  int m_tiles;        // real m-tiles (mc: total_tiles counts m-tile PAIRS x n-tiles)
 };
 
 __device__ __forceinline__ int fd_ring_r(const ConvKernelParams& p, uint32_t cnt) {
@@ -193,6 +198,138 @@ __device__ __forceinline__ void umma_unit2_ab(uint32_t d_tmem, uint32_t a_lo, ui
       "}\n" ::"r"(d_tmem),
       "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+
+// 2-D TMA load multicast to the CTAs of the cluster named by `mask`: data and the barrier's complete_tx land at
+// the same shared-memory offsets in every destination CTA.
+__device__ __forceinline__ void tma_load_2d_mc(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, "
+      "{%3, %4}], [%2], %5;" ::"r"(smem_u32(smem)),
+      "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+// tcgen05.commit arriving on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
+// ---- CTA pair (cta_group::2): one M=256 MMA spans both CTAs of a cluster; each CTA supplies its own 128 rows of
+// A and HALF of the weight tile, so the weight bytes every SM ingests are halved.  Only the leader (rank 0)
+// issues MMAs; both CTAs' TMA loads complete on the LEADER's full barrier; commits are multicast. ----
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem, const CUtensorMap* m, uint32_t bar_addr, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, "
+      "%4}], [%2];" ::"r"(smem_u32(smem)),
+      "l"(m), "r"(bar_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2sm(void* smem, const CUtensorMap* m, uint32_t bar_addr, int c0, int c1,
+                                                int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, "
+      "%4, %5, %6}], [%2];" ::"r"(smem_u32(smem)),
+      "l"(m), "r"(bar_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_addr) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// umma_unit with cta_group::2 (see umma_unit)
+template <int KSTEPS>
+__device__ __forceinline__ void umma_unit_2sm(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
+                                              uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      ".reg .b64 da, db;\n\t"
+      ".reg .b32 a, b;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "setp.eq.b32 q, 0, 0;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t"
+      "add.u32 a, %1, 2;\n\t"
+      "add.u32 b, %2, 2;\n\t"
+      "mov.b64 da, {a, %3};\n\t"
+      "mov.b64 db, {b, %3};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, q;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+  if (KSTEPS == 4) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        ".reg .b64 da, db;\n\t"
+        ".reg .b32 a, b;\n\t"
+        "setp.eq.b32 q, 0, 0;\n\t"
+        "add.u32 a, %1, 4;\n\t"
+        "add.u32 b, %2, 4;\n\t"
+        "mov.b64 da, {a, %3};\n\t"
+        "mov.b64 db, {b, %3};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, q;\n\t"
+        "add.u32 a, %1, 6;\n\t"
+        "add.u32 b, %2, 6;\n\t"
+        "mov.b64 da, {a, %3};\n\t"
+        "mov.b64 db, {b, %3};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, q;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// Persistent tile loop.  Plain: tile = blockIdx.x, += gridDim.x, (m_tile, n_tile) = divmod(tile, n_tiles_n).
+// mc: the CTA pair {2j, 2j+1} walks pair-tiles j, j + gridDim.x/2, ...; CTA rank r takes m-tile 2*m_pair + r.  A
+// pair whose second m-tile does not exist repeats the last one (dup: everything but the store / statistics),
+// so that both CTAs run the same sequence of pipeline stages.
+struct TileWalk {
+  int first, step, rank;
+};
+template <typename P>
+__device__ __forceinline__ TileWalk tile_walk(const P& p) {
+  TileWalk w;
+  w.first = p.mc ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  w.step = p.mc ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  w.rank = (int)(blockIdx.x & 1u);
+  return w;
+}
+template <typename P>
+__device__ __forceinline__ bool tile_decode(const P& p, const TileWalk& w, int tile, int& m_tile, int& n_tile) {
+  fd_divmod(p.fd_tiles_n, tile, m_tile, n_tile);
+  if (!p.mc) return false;
+  m_tile = 2 * m_tile + w.rank;
+  if (m_tile < p.m_tiles) return false;
+  m_tile = p.m_tiles - 1;
+  return true;
 }
 
 // Four K=16 steps (one 64-channel unit) with separate high words for A and B.
@@ -402,7 +539,7 @@ __device__ __forceinline__ void epi_stage_packed(const uint32_t* h, uint8_t* sta
 // sensitive to code size (a build with all variants in one 7.2k-instruction kernel lost 10-20 % on
 // the epilogue-bound layers against a 5.1k-instruction build, same algorithm).
 // STATS: the launch accumulates per-channel statistics (kept out of the other instantiations)
-template <int EPI, int MODE, bool STATS>
+template <int EPI, int MODE, bool STATS, bool PAIR = false>
 __global__ void __launch_bounds__(kConvThreads, 1)
     conv_tc_kernel(const __grid_constant__ ConvKernelParams p) {
   constexpr bool HALO = MODE == 1;   // stem halo mode
@@ -444,11 +581,11 @@ __global__ void __launch_bounds__(kConvThreads, 1)
     prefetch_tmap(&p.tmap_out);
     for (int i = 0; i < p.n_stages; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], p.mc == 1 ? 2 : 1);  // mc 1: a stage is free when BOTH CTAs' MMAs have read it
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], kEpiThreads);
+      mbar_init(&tempty_bar[i], PAIR ? 2 * kEpiThreads : kEpiThreads);  // pair: both CTAs' epilogues
     }
     for (int i = 0; i < kMaxRing; ++i) {
       mbar_init(&ifull_bar[i], 1);
@@ -461,10 +598,15 @@ __global__ void __launch_bounds__(kConvThreads, 1)
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (warp == 1) {
+    if (PAIR) tmem_alloc_2sm(tmem_slot, 512);
+    else tmem_alloc(tmem_slot, 512);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (p.mc) cluster_sync_all();  // the peer's barriers are initialised before anything is multicast to them
+  const TileWalk walk = tile_walk(p);
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
   // Programmatic dependent launch: everything above overlapped the previous kernel's tail; from
   // here on global memory written by it is read, so wait for its completion + flush.
@@ -671,9 +813,10 @@ __global__ void __launch_bounds__(kConvThreads, 1)
     // ===================== TMA producer (whole warp converged, one elected lane issues) ==========
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    const int b_half = p.b_bytes >> 1;
+    for (int tile = walk.first; tile < p.total_tiles; tile += walk.step) {
       int n_tile, m_tile, img, rem, h0, w0;
-      fd_divmod(p.fd_tiles_n, tile, m_tile, n_tile);
+      tile_decode(p, walk, tile, m_tile, n_tile);
       fd_divmod(p.fd_tiles_per_img, m_tile, img, rem);
       fd_divmod(p.fd_tiles_w, rem, h0, w0);
       h0 *= p.th;
@@ -685,18 +828,41 @@ __global__ void __launch_bounds__(kConvThreads, 1)
         if (elect_one()) {
           uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
           uint8_t* sb = sa + upst * p.a_bytes;
-          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(nu * (p.a_box_bytes + p.b_bytes)));
           int tt = t, kk = kc;
+          if (PAIR) {
+            // pair: both CTAs' bytes complete on the LEADER's barrier; only the leader posts the expectation
+            const uint32_t lead_bar = mapa_u32(smem_u32(&full_bar[stage]), 0u);
+            if (walk.rank == 0)
+              mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(2 * nu * (p.a_box_bytes + p.b_bytes)));
+            for (int j = 0; j < nu; ++j) {
+              const ConvTap tap = p.taps[tt];
+              tma_load_4d_2sm(sa + j * p.a_bytes, &p.tmap_a[tap.map], lead_bar, kk * p.kblock, w0 + tap.dw,
+                              h0 + tap.dh, img);
+              tma_load_2d_2sm(sb + j * p.b_bytes, &p.tmap_b, lead_bar, tap.wk * p.cin + kk * p.kblock,
+                              n_tile * p.block_n + walk.rank * (p.block_n >> 1));
+              if (++kk == k_chunks) {
+                kk = 0;
+                ++tt;
+              }
+            }
+          } else {
+          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(nu * (p.a_box_bytes + p.b_bytes)));
           for (int j = 0; j < nu; ++j) {
             const ConvTap tap = p.taps[tt];
             tma_load_4d(sa + j * p.a_bytes, &p.tmap_a[tap.map], &full_bar[stage], kk * p.kblock,
                         w0 + tap.dw, h0 + tap.dh, img);
-            tma_load_2d(sb + j * p.b_bytes, &p.tmap_b, &full_bar[stage],
-                        tap.wk * p.cin + kk * p.kblock, n_tile * p.block_n);
+            if (p.mc)  // this CTA's half of the weight tile, to both CTAs (tmap_b's box is block_n / 2 rows)
+              tma_load_2d_mc(sb + j * p.b_bytes + walk.rank * b_half, &p.tmap_b, &full_bar[stage],
+                             tap.wk * p.cin + kk * p.kblock, n_tile * p.block_n + walk.rank * (p.block_n >> 1),
+                             (uint16_t)3);
+            else
+              tma_load_2d(sb + j * p.b_bytes, &p.tmap_b, &full_bar[stage],
+                          tap.wk * p.cin + kk * p.kblock, n_tile * p.block_n);
             if (++kk == k_chunks) {
               kk = 0;
               ++tt;
             }
+          }
           }
         }
         __syncwarp();
@@ -723,7 +889,10 @@ __global__ void __launch_bounds__(kConvThreads, 1)
                                                                          : (uint32_t)UMMA_SW64)
                                                         << 29);
     const uint32_t a_step = (uint32_t)p.a_bytes >> 4, b_step = (uint32_t)p.b_bytes >> 4;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    constexpr bool pair = PAIR;
+    // pair: the leader issues the M=256 MMAs for both CTAs; the peer's MMA warp only owns its TMEM allocation
+    for (int tile = (pair && walk.rank != 0) ? p.total_tiles : walk.first; tile < p.total_tiles;
+         tile += walk.step, ++it) {
       const int buf = it & 1;
       mbar_wait(&tempty_bar[buf], (((uint32_t)it >> 1) & 1u) ^ 1u);
       tc_fence_after();
@@ -737,7 +906,13 @@ __global__ void __launch_bounds__(kConvThreads, 1)
           // descriptor low word: start address >> 4 | LBO(16 B) << 16
           uint32_t a_lo = ((sa >> 4) & 0x3fffu) | (1u << 16);
           uint32_t b_lo = (((sa + (uint32_t)(upst * p.a_bytes)) >> 4) & 0x3fffu) | (1u << 16);
-          if (p.kblock == 64) {
+          if (pair) {  // kblock == 64 (host)
+            for (int j = 0; j < nu; ++j) {
+              umma_unit_2sm<4>(d_tmem, a_lo, b_lo, desc_hi, p.idesc, (uint32_t)((u + j) != 0));
+              a_lo += a_step;
+              b_lo += b_step;
+            }
+          } else if (p.kblock == 64) {
             for (int j = 0; j < nu; ++j) {
               umma_unit<4>(d_tmem, a_lo, b_lo, desc_hi, p.idesc, (uint32_t)((u + j) != 0));
               a_lo += a_step;
@@ -750,7 +925,10 @@ __global__ void __launch_bounds__(kConvThreads, 1)
               b_lo += b_step;
             }
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          // frees the smem slot when these MMAs retire (mc: in both CTAs -- the peer's multicast writes it too)
+          if (pair) umma_commit_2sm(&empty_bar[stage], (uint16_t)3);
+          else if (p.mc) umma_commit_mc(&empty_bar[stage], (uint16_t)3);
+          else umma_commit(&empty_bar[stage]);
         }
         __syncwarp();
         if (++stage == p.n_stages) {
@@ -758,7 +936,10 @@ __global__ void __launch_bounds__(kConvThreads, 1)
           phase ^= 1;
         }
       }
-      if (elect_one()) umma_commit(&tfull_bar[buf]);  // accumulator complete -> epilogue
+      if (elect_one()) {  // accumulator complete -> epilogue (pair: of both CTAs)
+        if (pair) umma_commit_2sm(&tfull_bar[buf], (uint16_t)3);
+        else umma_commit(&tfull_bar[buf]);
+      }
       __syncwarp();
     }
   } else if (warp == 2) {
@@ -767,9 +948,9 @@ __global__ void __launch_bounds__(kConvThreads, 1)
       uint32_t cnt = 0;
       int slot = 0;
       uint32_t rphase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int tile = walk.first; tile < p.total_tiles; tile += walk.step) {
         int n_tile, m_tile, img, rem, h0, w0;
-        fd_divmod(p.fd_tiles_n, tile, m_tile, n_tile);
+        tile_decode(p, walk, tile, m_tile, n_tile);
         fd_divmod(p.fd_tiles_per_img, m_tile, img, rem);
         fd_divmod(p.fd_tiles_w, rem, h0, w0);
         h0 *= p.th;
@@ -826,11 +1007,11 @@ __global__ void __launch_bounds__(kConvThreads, 1)
     uint32_t r[64];
     bool pre = false;
     const bool prefetch_on = p.epi_prefetch != 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it, cnt0 += n_chunks) {
+    for (int tile = walk.first; tile < p.total_tiles; tile += walk.step, ++it, cnt0 += n_chunks) {
       const int buf = it & 1;
       const uint32_t use = (uint32_t)it >> 1;
       int n_tile, m_tile, img, rem, h0, w0;
-      fd_divmod(p.fd_tiles_n, tile, m_tile, n_tile);
+      const bool dup = tile_decode(p, walk, tile, m_tile, n_tile);  // mc: repeated tile, nothing is stored
       fd_divmod(p.fd_tiles_per_img, m_tile, img, rem);
       fd_divmod(p.fd_tiles_w, rem, h0, w0);
       h0 *= p.th;
@@ -850,7 +1031,8 @@ __global__ void __launch_bounds__(kConvThreads, 1)
       tc_fence_after();
       if (c_last < 0) {  // nothing to read from this accumulator: release our share right away
         tc_fence_before();
-        mbar_arrive(&tempty_bar[buf]);
+        if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[buf]), 0u));  // the leader's barrier
+          else mbar_arrive(&tempty_bar[buf]);
       }
       const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * p.block_n);
       for (int c = c_first; c < n_chunks; c += 2) {
@@ -863,7 +1045,8 @@ __global__ void __launch_bounds__(kConvThreads, 1)
         tmem_ld_wait();
         if (c == c_last) {  // accumulator fully read by this thread: hand TMEM back to the MMA warp
           tc_fence_before();
-          mbar_arrive(&tempty_bar[buf]);
+          if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[buf]), 0u));  // the leader's barrier
+          else mbar_arrive(&tempty_bar[buf]);
         }
         const int ch = n_tile * p.block_n + c * 64;
         if (EPI != 0) {
@@ -904,7 +1087,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
           epi_stage_packed(hp, o_base, row);
           fence_proxy_async();
           named_bar_sync(bar_id, kEpiGroupThreads);
-          if (etid == 0) {
+          if (etid == 0 && !dup) {
             tma_store_4d(&p.tmap_out, o_base, ch, w0, h0, img);
             bulk_commit();
           }
@@ -970,7 +1153,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
             tmem_ld32(t_addr + (uint32_t)((c + 2) * 64), r);
             tmem_ld32(t_addr + (uint32_t)((c + 2) * 64 + 32), r + 32);
             pre = true;
-          } else if (tile + (int)gridDim.x < p.total_tiles) {
+          } else if (tile + walk.step < p.total_tiles) {
             // first chunk of the next tile, if this group has one there and that accumulator is
             // already complete (never wait here: the MMA warp may still need our own release)
             const int c_next = (int)(((cnt0 + (uint32_t)n_chunks) ^ (uint32_t)group) & 1u);
@@ -991,7 +1174,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
         }
         if (!(p.epi_debug & 2)) fence_proxy_async();
         named_bar_sync(bar_id, kEpiGroupThreads);
-        if (etid == 0 && !(p.epi_debug & 1)) {
+        if (etid == 0 && !(p.epi_debug & 1) && !dup) {
           tma_store_4d(&p.tmap_out, o_base, ch, w0, h0, img);
           bulk_commit();
         }
@@ -1023,9 +1206,11 @@ __global__ void __launch_bounds__(kConvThreads, 1)
 
   tc_fence_before();
   __syncthreads();
+  if (p.mc) cluster_sync_all();  // no CTA leaves while its peer may still arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (PAIR) tmem_dealloc_2sm(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
   }
   if (p.pdl_late_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
@@ -1416,7 +1601,56 @@ static int finish_launch(ConvLaunch* L, const ghnd_conv_desc_t* d, int gemm_cin,
             512 /*barriers*/;
   p.a_halo_bytes = 0;
   p.b_resident = 0;
-  if (try_halo) plan_conv_halo(L, d, gemm_cin, gemm_cout, n_in, fixed);
+  p.mc = 0;
+  p.m_tiles = m_tiles;
+  if (try_halo && plan_conv_halo(L, d, gemm_cin, gemm_cout, n_in, fixed)) return GHND_OK;
+  // CTA pairs (generic mode).  The trunk convs re-read their block_n x K weight slab for every m-tile, and that
+  // ingest (L2 -> SM) bounds most of them.  Two CTAs of a cluster take the same n-tile of two neighbouring
+  // m-tiles in lock step:
+  //   GHND_CONV_PAIR=1 (mc 2): ONE cta_group::2 MMA (M = 256) spans the pair, each CTA loads and holds only HALF
+  //     of every weight tile -- the weight bytes per SM are halved, and the smaller stages deepen the pipeline;
+  //   GHND_CONV_MC=1   (mc 1): cta_group::1 MMAs, each CTA fetches half of the tile and TMA-multicasts it to both.
+  //     Measured neutral on the B200 (712.6 vs 711.9 img/s): every SM still ingests the whole tile.
+  // Not with fused statistics (a repeated tile would count twice) and not below one pair per SM pair.
+  static const int mc_env = [] {
+    const char* e = getenv("GHND_CONV_MC");
+    return e == nullptr ? 0 : atoi(e);
+  }();
+  // Per-layer A/B on the B200 (profiles/r2_summary.md): the pair wins where the K loop dominates the tile
+  // (K >= 1024: 3x3 convs, the 1x1 reductions of layers 3-4, the 2x2 C256 dgrad: -8 .. -24 %) and loses where
+  // the tile is epilogue-bound (1x1 expansions with a residual, K <= 512: +20 .. +69 %, the MMAs of the next
+  // tile wait for BOTH CTAs' epilogues) -> default: pairs for launches with K >= 1024.  GHND_CONV_PAIR=0 off,
+  // 1 = every eligible launch with at least one pair per SM pair, 2 = every eligible launch.
+  static const int pair_env = [] {
+    const char* e = getenv("GHND_CONV_PAIR");
+    return e == nullptr ? -1 : atoi(e);
+  }();
+  // (K = 512: the masked data-gradient launches gain 9 .. 17 %, the forward ones lose 4 .. 19 %)
+  const int k_total = n_units * kblock;
+  const bool pair_auto = k_total >= 1024 || (k_total >= 512 && d->mask != nullptr && d->dst_fmt == GHND_BF16);
+  const int pair_want = pair_env >= 0 ? pair_env : (pair_auto ? 1 : 0);
+  const int want = pair_want ? pair_want : mc_env;
+  if (want != 0 && !p.halo && kblock == 64 && d->stats == nullptr && p.block_n >= 128 && m_tiles >= 2 &&
+      num_sms() % 2 == 0 && (want == 2 || (int64_t)((m_tiles + 1) / 2) * p.n_tiles_n >= num_sms() / 2)) {
+    uint32_t hbox[2] = {(uint32_t)kblock, (uint32_t)(p.block_n / 2)};
+    if (encode_tmap(&p.tmap_b, 2, 2, const_cast<void*>(weights), dims, str, hbox, row_bytes) == GHND_OK) {
+      p.mc = pair_want ? 2 : 1;
+      p.total_tiles = ((m_tiles + 1) / 2) * p.n_tiles_n;
+      L->grid = 2 * p.total_tiles < num_sms() ? 2 * p.total_tiles : num_sms();
+      if (p.mc == 2) {
+        p.b_bytes = (p.block_n / 2) * row_bytes;  // this CTA's half of a weight tile
+        p.stage_bytes = p.units_per_stage * (p.a_bytes + p.b_bytes);
+        int st2 = (kSmemBudget - fixed - ring * n_in * kChunkBytes) / p.stage_bytes;
+        if (st2 > kMaxStages) st2 = kMaxStages;
+        p.n_stages = st2;
+        L->smem = (size_t)p.n_stages * p.stage_bytes + (size_t)fixed + (size_t)ring * n_in * kChunkBytes + 512;
+        p.idesc = make_idesc(d->src_fmt, d->w_fmt, 0, 0, 2 * kBlockM, p.block_n);
+      }
+    } else {
+      rc = encode_tmap(&p.tmap_b, 2, 2, const_cast<void*>(weights), dims, str, box, row_bytes);
+      if (rc != GHND_OK) return rc;
+    }
+  }
   return GHND_OK;
 }
 
@@ -1430,12 +1664,28 @@ static cudaError_t launch_conv(const ConvLaunch& L, cudaStream_t st) {
   cfg.blockDim = dim3(kConvThreads, 1, 1);
   cfg.dynamicSmemBytes = L.smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
   static const bool no_pdl = getenv("GHND_NO_PDL") != nullptr;  // debugging switch
+  int na = 0;
+  if (!no_pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (L.p.mc) {  // CTA pairs sharing their weight tiles (see finish_launch)
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = no_pdl ? 0 : 1;
+  cfg.numAttrs = na;
+  if (L.p.mc == 2) {  // CTA pair: the instantiations with cta_group::2 instructions (cluster launches only)
+    if (L.p.epi_half == 1) return cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, 0, false, true>, L.p);
+    if (L.p.epi_half == 2) return cudaLaunchKernelEx(&cfg, conv_tc_kernel<2, 0, false, true>, L.p);
+    return cudaLaunchKernelEx(&cfg, conv_tc_kernel<0, 0, false, true>, L.p);
+  }
   if (L.p.a_halo_bytes > 0) {  // conv halo mode (MODE 2): packed epilogues only
     if (L.p.epi_half == 2) return cudaLaunchKernelEx(&cfg, conv_tc_kernel<2, 2, false>, L.p);
     if (L.p.stats != nullptr) return cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, 2, true>, L.p);
@@ -1472,6 +1722,9 @@ static int set_conv_attr() {
     GHND_SET_SMEM(1, 2, false);
     GHND_SET_SMEM(1, 2, true);
     GHND_SET_SMEM(2, 2, false);
+    GHND_SET_SMEM(0, 0, false, true);
+    GHND_SET_SMEM(1, 0, false, true);
+    GHND_SET_SMEM(2, 0, false, true);
 #undef GHND_SET_SMEM
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_tc_kernel)");
     attr_set = true;
