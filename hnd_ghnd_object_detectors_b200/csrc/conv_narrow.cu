@@ -3,6 +3,8 @@
 // The wide side of each conv is an NHWC 16-bit tensor (one 128-byte pixel row per 64 channels,
 // read/written as 8 lanes x 16 B so a warp touches 4 whole pixels = 512 contiguous bytes); the
 // narrow side is the planar fp32 bottleneck tensor the quantizer works on.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ghnd {
@@ -355,6 +357,177 @@ __global__ void __launch_bounds__(256, 2)
           }
         }
     }
+  }
+  if (kMinMax) {
+    if (has_nan) mn = mx = __int_as_float(0x7fc00000);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float omn = __shfl_xor_sync(0xffffffffu, mn, o), omx = __shfl_xor_sync(0xffffffffu, mx, o);
+      mn = (mn != mn) ? mn : ((omn != omn) ? omn : fminf(mn, omn));
+      mx = (mx != mx) ? mx : ((omx != omx) ? omx : fmaxf(mx, omx));
+    }
+    if (lane == 0) {
+      s_mm[2 * warp] = mn;
+      s_mm[2 * warp + 1] = mx;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < 8; ++w) {
+        const float omn = s_mm[2 * w], omx = s_mm[2 * w + 1];
+        mn = (mn != mn) ? mn : ((omn != omn) ? omn : fminf(mn, omn));
+        mx = (mx != mx) ? mx : ((omx != omx) ? omx : fmaxf(mx, omx));
+      }
+      partial[2 * blockIdx.x] = mn;
+      partial[2 * blockIdx.x + 1] = mx;
+    }
+  }
+}
+
+// The same conv with the wide tensor staged through shared memory by TMA (sm_100a):
+// a CTA works on blocks of 8 output rows x 16 output columns; ONE tensor-map box of (8 + dh span) x (16 + dw
+// span) pixels x 64 channels (128B-swizzled, out-of-bounds = the conv's zero padding) feeds all taps of all
+// eight warps, double buffered so that the box of block k+1 is in flight while block k is multiplied.  A
+// fragments come from `ldmatrix.x4` (conflict-free on the swizzled rows): 16 ldmatrix + 32 mma.sync per
+// 16-pixel row instead of 64 predicated 16-byte global loads (ncu of the direct-load kernel: 41 % of the issue
+// slots, 4.7 warps stalled on the long scoreboard per issue, 1.7 TB/s).  GEMM-K step (tap, s) = channels
+// 16s .. 16s+15 of that tap in natural order.
+static constexpr int kNoStages = 4;
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&a)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3])
+               : "r"(addr));
+}
+// Weights keep fp32 accuracy as hi + lo/kUp 16-bit halves.  Both halves of a channel sit in NEIGHBOURING columns
+// of one n8 tile (column 2c = hi, 2c+1 = lo of channel 4*nt + c), so ONE mma.sync per k-step yields both partial
+// sums in the same thread (the mma.sync rate, not memory, paced the first TMA version: 32 HMMA per 16 pixels
+// for 3 useful output channels).  NT = ceil(CN / 4) n-tiles.
+template <int FMT, int NT, bool kMinMax>
+__global__ void __launch_bounds__(256, 2)
+    narrow_out_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ w_oihw, int wmode,
+                          float* __restrict__ out, int N, int CN, int Ho, int Wo, NarrowTaps taps, int bw,
+                          int dh0, int dw0, int tile_bytes, int box_bytes, float* __restrict__ partial) {
+  extern __shared__ __align__(1024) uint8_t dsm[];  // [kNoStages][tile_bytes]
+  __shared__ uint2 s_b[16 * NT * 32];  // [k-step][n-tile][lane] = {b0, b1}
+  __shared__ float s_mm[16];
+  __shared__ uint64_t s_bar[kNoStages];
+  if (smem_u32(dsm) & 1023u) __trap();
+  for (int idx = threadIdx.x; idx < 16 * NT * 32; idx += blockDim.x) {
+    const int l = idx & 31, nt = (idx >> 5) % NT, ks = idx / (32 * NT);
+    const int g = l >> 2, t = l & 3;
+    const int tap = ks >> 2, sx = ks & 3;
+    const int co = nt * 4 + (g >> 1), part = g & 1;
+    uint32_t h[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {  // b0 = k {2t, 2t+1}, b1 = k {2t+8, 2t+9}
+      const int c = 16 * sx + 2 * t + (e & 1) + (e >> 1) * 8;
+      // straight from the OIHW tensor (no weight-table launch): wmode 0 = this conv's own weight [CN][64][R][S],
+      // wmode 1 = data gradient of the bch -> 64 conv, weight [64][CN][R][S]
+      const int wi = (wmode == 0 ? (co * 64 + c) : (c * CN + co)) * taps.n_taps + tap;
+      const float w = (co < CN && tap < taps.n_taps) ? __ldg(w_oihw + wi) : 0.f;
+      uint32_t hi, lo;
+      split16<FMT>(w, hi, lo);
+      h[e] = part ? lo : hi;
+    }
+    s_b[idx] = make_uint2(h[0] | (h[1] << 16), h[2] | (h[3] << 16));
+  }
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmap);
+    for (int b = 0; b < kNoStages; ++b) mbar_init(&s_bar[b], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const uint32_t JB = (uint32_t)(Wo + 15) >> 4, IB = (uint32_t)(Ho + 7) >> 3;
+  const uint32_t ctiles = (uint32_t)N * IB * JB;
+  auto issue = [&](uint32_t ct, int buf) {
+    const uint32_t q = ct / JB, jb = ct - q * JB;
+    const uint32_t n = q / IB, ib = q - n * IB;
+    mbar_arrive_expect_tx(&s_bar[buf], (uint32_t)box_bytes);
+    tma_load_4d(dsm + (size_t)buf * tile_bytes, &tmap, &s_bar[buf], 0, (int)(jb * 16) + dw0, (int)(ib * 8) + dh0,
+                (int)n);
+  };
+  // kNoStages - 1 boxes in flight per CTA (with one box ahead the kernel ran at the TMA round trip: 1.7 us
+  // per block and CTA, 2.9 TB/s)
+  if (threadIdx.x == 0)
+    for (int b = 0; b < kNoStages - 1; ++b)
+      if (blockIdx.x + (uint32_t)b * gridDim.x < ctiles) issue(blockIdx.x + (uint32_t)b * gridDim.x, b);
+  // per-lane ldmatrix row: matrix mi = lane >> 3 (pixels +8 for odd mi, channels +8 for mi >= 2), row lane & 7.
+  // The byte offset of every k-step's row inside a buffer depends on (warp, lane, tap, s) only: computed once
+  // (the first version rebuilt them per block: ~270 of its 320 instructions per 16-pixel row were index
+  // arithmetic, 38 % of the issue slots).  With one n-tile the B fragments live in registers, too.
+  const int lm_px = ((lane >> 3) & 1) * 8 + (lane & 7), lm_ch = lane >> 4;
+  uint32_t aoff[16];
+  uint2 breg[NT == 1 ? 16 : 1];
+#pragma unroll
+  for (int ks = 0; ks < 16; ++ks) {
+    const int tap = ks >> 2, sx = ks & 3;
+    const int tdh = tap < taps.n_taps ? taps.dh[tap] : taps.dh[0], tdw = tap < taps.n_taps ? taps.dw[tap] : taps.dw[0];
+    const int px = (warp + tdh - dh0) * bw + (tdw - dw0) + lm_px;
+    aoff[ks] = (uint32_t)(px * 128 + (((2 * sx + lm_ch) ^ (px & 7)) << 4));
+    if (NT == 1) breg[ks] = s_b[ks * 32 + lane];
+  }
+  float mn = INFINITY, mx = -INFINITY;
+  bool has_nan = false;
+  const int n_taps = taps.n_taps;
+  int k = 0;
+  for (uint32_t ct = blockIdx.x; ct < ctiles; ct += gridDim.x, ++k) {
+    const int buf = k % kNoStages;
+    // the buffer of block k - 1 was released by the barrier that ended it: refill it with block k + kNoStages - 1
+    if (threadIdx.x == 0 && ct + (uint32_t)(kNoStages - 1) * gridDim.x < ctiles)
+      issue(ct + (uint32_t)(kNoStages - 1) * gridDim.x, (k + kNoStages - 1) % kNoStages);
+    const uint32_t q = ct / JB, jb = ct - q * JB;
+    const uint32_t n = q / IB, ib = q - n * IB;
+    const int i = (int)(ib * 8) + warp;
+    const int j0 = (int)(jb * 16) + g;
+    const bool row_ok = i < Ho;
+    mbar_wait(&s_bar[buf], ((uint32_t)(k / kNoStages)) & 1u);
+    const uint32_t tile = smem_u32(dsm) + (uint32_t)(buf * tile_bytes);
+    float d[NT][4], d2[NT][4];  // two accumulator sets: even / odd k-steps (halves the mma dependency chain)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) d[nt][e] = d2[nt][e] = 0.f;
+    if (row_ok) {
+#pragma unroll
+      for (int ks = 0; ks < 16; ++ks) {
+        if ((ks >> 2) < n_taps) {  // uniform
+          uint32_t a[4];
+          ldmatrix_x4(a, tile + aoff[ks]);
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) {
+            const uint2 b = NT == 1 ? breg[ks] : s_b[(ks * NT + nt) * 32 + lane];
+            if (ks & 1) mma16816<FMT>(d2[nt], a, b.x, b.y);
+            else mma16816<FMT>(d[nt], a, b.x, b.y);
+          }
+        }
+      }
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) d[nt][e] += d2[nt][e];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const int co = nt * 4 + t;  // this thread's columns 2t / 2t+1 = hi / lo sums of channel co
+        if (co < CN) {
+          float* dst = out + ((size_t)((int)n * CN + co) * Ho + i) * Wo;
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const int j = j0 + 8 * r;
+            if (j < Wo) {
+              const float val = d[nt][2 * r] + d[nt][2 * r + 1] * LoScale<FMT>::kDown;
+              dst[j] = val;
+              if (kMinMax) {
+                has_nan |= val != val;
+                mn = fminf(mn, val);
+                mx = fmaxf(mx, val);
+              }
+            }
+          }
+        }
+      }
+    }
+    fence_proxy_async();  // generic-proxy reads of this buffer before the TMA refill two blocks later
+    __syncthreads();
   }
   if (kMinMax) {
     if (has_nan) mn = mx = __int_as_float(0x7fc00000);
@@ -862,10 +1035,62 @@ static int narrow_out_blocks(int N, int Ho, int Wo) {
   return (int)(ctiles < cap ? ctiles : cap);
 }
 // returns the number of CTAs (= min/max partial pairs written when `partial` is given)
-static int launch_narrow_out_mma(const void* in, int fmt, const float* wt, float* out, int N, int Hi,
-                                 int Wi, int CN, int Ho, int Wo, const NarrowTaps& taps,
+static int launch_narrow_out_mma(const void* in, int fmt, const float* w_oihw, int wmode, int R, int S, float* wt,
+                                 float* out, int N, int Hi, int Wi, int CN, int Ho, int Wo, const NarrowTaps& taps,
                                  float* partial, cudaStream_t st) {
   const int blocks = narrow_out_blocks(N, Ho, Wo);
+  // TMA-staged kernel (GHND_NARROW_TMA=0: the direct-load kernel)
+  static const bool tma_off = [] {
+    const char* e = getenv("GHND_NARROW_TMA");
+    return e != nullptr && atoi(e) == 0;
+  }();
+  if (!tma_off && taps.n_taps >= 1) {
+    int dh0 = taps.dh[0], dh1 = dh0, dw0 = taps.dw[0], dw1 = dw0;
+    for (int t = 1; t < taps.n_taps; ++t) {
+      dh0 = taps.dh[t] < dh0 ? taps.dh[t] : dh0;
+      dh1 = taps.dh[t] > dh1 ? taps.dh[t] : dh1;
+      dw0 = taps.dw[t] < dw0 ? taps.dw[t] : dw0;
+      dw1 = taps.dw[t] > dw1 ? taps.dw[t] : dw1;
+    }
+    const int bw = 16 + dw1 - dw0, bh = 8 + dh1 - dh0;
+    const int box_bytes = bw * bh * 128, tile_bytes = (box_bytes + 1023) / 1024 * 1024;
+    CUtensorMap tmap;
+    uint64_t dims[4] = {64, (uint64_t)Wi, (uint64_t)Hi, (uint64_t)N};
+    uint64_t str[4] = {2, 128, (uint64_t)Wi * 128, (uint64_t)Hi * Wi * 128};
+    uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)bh, 1};
+    if (bw <= 256 && bh <= 256 && kNoStages * tile_bytes <= 100 * 1024 &&
+        encode_tmap(&tmap, 2, 4, const_cast<void*>(in), dims, str, box, 128) == GHND_OK) {
+      const size_t smem = (size_t)kNoStages * tile_bytes;
+#define GHND_NOT(FMT, NT, MM)                                                                                  \
+  do {                                                                                                         \
+    static bool attr = false;                                                                                  \
+    if (!attr) {                                                                                               \
+      cudaFuncSetAttribute(narrow_out_tma_kernel<FMT, NT, MM>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                           100 * 1024);                                                                        \
+      attr = true;                                                                                             \
+    }                                                                                                          \
+    narrow_out_tma_kernel<FMT, NT, MM><<<blocks, 256, smem, st>>>(tmap, w_oihw, wmode, out, N, CN, Ho, Wo, taps, \
+                                                                  bw, dh0, dw0, tile_bytes, box_bytes,          \
+                                                                  partial);                                     \
+  } while (0)
+#define GHND_NOT_MM(FMT, NT) \
+  if (partial) GHND_NOT(FMT, NT, true); else GHND_NOT(FMT, NT, false)
+      const int nt = (CN + 3) / 4;  // four channels (hi, lo column pairs) per n8 tile
+      if (fmt == GHND_F16) {
+        if (nt == 1) { GHND_NOT_MM(GHND_F16, 1); } else if (nt == 2) { GHND_NOT_MM(GHND_F16, 2); }
+        else if (nt == 3) { GHND_NOT_MM(GHND_F16, 3); } else { GHND_NOT_MM(GHND_F16, 4); }
+      } else {
+        if (nt == 1) { GHND_NOT_MM(GHND_BF16, 1); } else if (nt == 2) { GHND_NOT_MM(GHND_BF16, 2); }
+        else if (nt == 3) { GHND_NOT_MM(GHND_BF16, 3); } else { GHND_NOT_MM(GHND_BF16, 4); }
+      }
+#undef GHND_NOT_MM
+#undef GHND_NOT
+      return blocks;
+    }
+  }
+  // direct-load kernel: needs the [tap][c][co] weight table
+  if (wmode == 0) narrow_wtable_kernel<<<4, 256, 0, st>>>(w_oihw, wt, CN, 64, R, S, 0);
+  else narrow_wtable_kernel<<<4, 256, 0, st>>>(w_oihw, wt, 64, CN, R, S, 1);
 #define GHND_NO(FMT, NT, MM)                                                                        \
   narrow_out_mma_kernel<FMT, NT, MM><<<blocks, 256, 0, st>>>((const uint4*)in, wt, out, N, Hi, Wi, \
                                                              CN, Ho, Wo, taps, partial)
@@ -927,8 +1152,6 @@ static int conv_narrow_out_impl(const void* x, int x_fmt, const float* w, float*
   const int Ho = H + 2 * pad - R + 1, Wo = W + 2 * pad - S + 1;
   GHND_CHECK_ARG(Ho > 0 && Wo > 0, "conv_narrow_out: empty output");
   cudaStream_t st = (cudaStream_t)stream;
-  narrow_wtable_kernel<<<4, 256, 0, st>>>(w, (float*)workspace, K, C, R, S, 0);
-  GHND_LAUNCH_CHECK("narrow_wtable_kernel");
   NarrowTaps taps;
   taps.n_taps = R * S;
   for (int r = 0; r < R; ++r)
@@ -939,13 +1162,17 @@ static int conv_narrow_out_impl(const void* x, int x_fmt, const float* w, float*
   const int lanes = C / 8;
   const int64_t npix = (int64_t)N * Ho * Wo;
   const bool fast = narrow_fast_ok(C, K, npix) && (x_fmt == GHND_F16 || x_fmt == GHND_BF16);
+  if (!fast) {  // the fast path builds its weight fragments itself (or its own table)
+    narrow_wtable_kernel<<<4, 256, 0, st>>>(w, (float*)workspace, K, C, R, S, 0);
+    GHND_LAUNCH_CHECK("narrow_wtable_kernel");
+  }
   if (minmax_partial != nullptr) {
     GHND_CHECK_ARG(fast && n_partial != nullptr && partial_capacity >= narrow_out_blocks(N, Ho, Wo),
                    "conv_narrow_out_minmax: needs the 64-channel 16-bit path and %d partial pairs",
                    narrow_out_blocks(N, Ho, Wo));
   }
   if (fast) {
-    const int blocks = launch_narrow_out_mma(x, x_fmt, (const float*)workspace, y, N, H, W, K, Ho, Wo,
+    const int blocks = launch_narrow_out_mma(x, x_fmt, w, 0, R, S, (float*)workspace, y, N, H, W, K, Ho, Wo,
                                              taps, minmax_partial, st);
     if (n_partial) *n_partial = blocks;
   } else if (K <= 3)
@@ -989,9 +1216,6 @@ int ghnd_conv_narrow_out_dgrad(const void* dy, int dy_fmt, const float* w, float
   const int Ho = H + 2 * pad - R + 1, Wo = W + 2 * pad - S + 1;
   GHND_CHECK_ARG(Ho > 0 && Wo > 0, "conv_narrow_out_dgrad: empty output");
   cudaStream_t st = (cudaStream_t)stream;
-  // table wt[tap][ci=k][co=c]
-  narrow_wtable_kernel<<<4, 256, 0, st>>>(w, (float*)workspace, K, C, R, S, 1);
-  GHND_LAUNCH_CHECK("narrow_wtable_kernel");
   NarrowTaps taps;
   taps.n_taps = R * S;
   for (int r = 0; r < R; ++r)
@@ -1001,8 +1225,13 @@ int ghnd_conv_narrow_out_dgrad(const void* dy, int dy_fmt, const float* w, float
     }
   const int lanes = K / 8;
   const int64_t npix = (int64_t)N * H * W;
-  if (narrow_fast_ok(K, C, npix) && (dy_fmt == GHND_F16 || dy_fmt == GHND_BF16))
-    launch_narrow_out_mma(dy, dy_fmt, (const float*)workspace, dx, N, Ho, Wo, C, H, W, taps, nullptr, st);
+  const bool dg_fast = narrow_fast_ok(K, C, npix) && (dy_fmt == GHND_F16 || dy_fmt == GHND_BF16);
+  if (!dg_fast) {  // table wt[tap][ci=k][co=c]
+    narrow_wtable_kernel<<<4, 256, 0, st>>>(w, (float*)workspace, K, C, R, S, 1);
+    GHND_LAUNCH_CHECK("narrow_wtable_kernel");
+  }
+  if (dg_fast)
+    launch_narrow_out_mma(dy, dy_fmt, w, 1, R, S, (float*)workspace, dx, N, Ho, Wo, C, H, W, taps, nullptr, st);
   else if (C <= 3)
     narrow_out_kernel<3><<<blocks_for_pixels(npix, 256 / lanes), 256,
                            (size_t)R * S * C * K * sizeof(float), st>>>(

@@ -424,11 +424,11 @@ def conv_narrow_out(x, w, pad, y=None, ws=None, minmax=None):
         n_pairs = ctypes.c_int(0)
         call("ghnd_conv_narrow_out_minmax", ptr(x), fmt_of(x.dtype), ptr(w), ptr(y), n, h, wd, c, k, r, s,
              pad, ptr(ws[0]), ws[1], ptr(minmax), minmax.numel() // 2, byref(n_pairs), stream_ptr())
-        _count(2)
+        _count(1)
         return y, n_pairs.value
     call("ghnd_conv_narrow_out", ptr(x), fmt_of(x.dtype), ptr(w), ptr(y), n, h, wd, c, k, r, s, pad,
          ptr(ws[0]), ws[1], stream_ptr())
-    _count(2)
+    _count(1)
     return y
 
 
@@ -463,7 +463,7 @@ def conv_narrow_out_dgrad(dy, w, pad, H, W, dx=None, ws=None):
         ws = _narrow_ws(c, k, r, s, dy.device)
     call("ghnd_conv_narrow_out_dgrad", ptr(dy), fmt_of(dy.dtype), ptr(w), ptr(dx), n, H, W, c, k, r, s, pad,
          ptr(ws[0]), ws[1], stream_ptr())
-    _count(2)
+    _count(1)
     return dx
 
 
