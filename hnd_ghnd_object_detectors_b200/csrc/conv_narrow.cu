@@ -672,6 +672,177 @@ __global__ void __launch_bounds__(256, 2)
   }
 }
 
+// ---- narrow-side halo of an 8 x 16 block through a cp.async ring (planar fp32 rows are not 16-byte aligned, so
+// no TMA): every thread copies up to three 4-byte elements per block, kHaloDepth blocks ahead; out-of-image
+// elements are zero-filled by the copy (src-size 0).  A lane then builds its MMA registers from the raw values:
+// f = BN/ReLU prologue, padding stays zero AFTER f (hence the validity flags), fp32 -> hi + lo/kUp 16-bit halves.
+static constexpr int kHaloDepth = 3;
+__device__ __forceinline__ void cp_async4_zfill(void* smem, const void* gmem, bool valid) {
+  const int sz = valid ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(smem)), "l"(gmem), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+// one packed (left, right) register pair: hi halves and lo halves of f(v0), f(v1)
+template <int FMT>
+__device__ __forceinline__ void narrow_pair(float v0, float v1, bool ok0, bool ok1, float sc, float sh, bool has_pre,
+                                            int pre_relu, uint32_t& hi, uint32_t& lo) {
+  if (has_pre) {
+    v0 = fmaf(v0, sc, sh);
+    v1 = fmaf(v1, sc, sh);
+    if (pre_relu) {
+      v0 = fmaxf(v0, 0.f);
+      v1 = fmaxf(v1, 0.f);
+    }
+  }
+  v0 = ok0 ? v0 : 0.f;
+  v1 = ok1 ? v1 : 0.f;
+  uint32_t h0, l0, h1, l1;
+  split16<FMT>(v0, h0, l0);
+  split16<FMT>(v1, h1, l1);
+  hi = h0 | (h1 << 16);
+  lo = l0 | (l1 << 16);
+}
+
+// The same conv for bch <= 4 and horizontally paired taps (k2 kernels), restructured like narrow_out_tma:
+// a CTA works on blocks of 8 output rows x 16 columns (warp = row), the narrow input halo of a block is
+// transformed (BN + ReLU prologue), split into hi / lo 16-bit halves and staged ONCE in shared memory -- every
+// word holds the PAIR (column c, c+1), and GEMM-K is ordered (channel, tap pair, left/right tap) so that an A
+// register is one LDS -- instead of 8 predicated scalar global loads + pre-transform + split per k-step and
+// lane; B fragments live in registers; no per-pixel divisions.  ~170 instead of ~450 instructions per 16 pixels.
+template <int FMT>
+__global__ void __launch_bounds__(256, 2)
+    narrow_in_pair_kernel(const float* __restrict__ in, const float* __restrict__ pre, int pre_relu,
+                          const float* __restrict__ w_oihw, int wmode, uint4* __restrict__ out, int N, int Hi,
+                          int Wi, int CN, int Ho, int Wo, NarrowTaps taps, int dhmin, int dwmin, int HR, int HC) {
+  extern __shared__ float s_raw[];  // [kHaloDepth + 1][4 ci][HR][HC + 1] raw fp32 halo ring
+  const int HCp = HC + 1, plane = 4 * HR * HCp;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  // tap of (pair p, half h): the pair's taps share dh and are one column apart; half 0 = the left one
+  auto tap_of = [&](int p, int h) { return taps.dw[2 * p] < taps.dw[2 * p + 1] ? 2 * p + h : 2 * p + 1 - h; };
+  // B fragments (weights, hi/lo): k = 4 ci + 2 p + h; column g of n-tile nn = channel 8 (g>>1) + 2 nn + (g&1)
+  // (+32 for nn >= 4), so that lane t ends up with channels 8t .. 8t+7 (and 32 + the same) of a pixel
+  uint4 breg[8];
+#pragma unroll
+  for (int nn = 0; nn < 8; ++nn) {
+    const int co = nn < 4 ? 8 * (g >> 1) + 2 * nn + (g & 1) : 32 + 8 * (g >> 1) + 2 * (nn - 4) + (g & 1);
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int kk = 2 * t + (e & 1) + (e >> 1) * 8;
+      const int ci = kk >> 2, p = (kk >> 1) & 1, h = kk & 1;
+      float w = 0.f;
+      if (ci < CN && 2 * p + 1 < taps.n_taps) {
+        const int tp = tap_of(p, h);
+        // wmode 0: forward weight [64][CN][R][S]; wmode 1: data gradient of the 64 -> bch conv, weight [CN][64][R][S]
+        w = __ldg(w_oihw + (wmode == 0 ? (co * CN + ci) : (ci * 64 + co)) * taps.n_taps + tp);
+      }
+      split16<FMT>(w, hi[e], lo[e]);
+    }
+    breg[nn] = make_uint4(hi[0] | (hi[1] << 16), hi[2] | (hi[3] << 16), lo[0] | (lo[1] << 16), lo[2] | (lo[3] << 16));
+  }
+  const uint32_t JB = (uint32_t)(Wo + 15) >> 4, IB = (uint32_t)(Ho + 7) >> 3;
+  const uint32_t ctiles = (uint32_t)N * IB * JB;
+  auto decode = [&](uint32_t ct, int& n, int& i0, int& j0) {
+    const uint32_t q = ct / JB, jb = ct - q * JB;
+    const uint32_t nn = q / IB, ib = q - nn * IB;
+    n = (int)nn;
+    i0 = (int)(ib * 8);
+    j0 = (int)(jb * 16);
+  };
+  const size_t plane_in = (size_t)Hi * Wi;
+  // element w of a halo: (ci, hr, hc) -> in[n][ci][i0 + dhmin + hr][j0 + dwmin + hc]
+  int e_ci[3], e_hr[3], e_hc[3];
+#pragma unroll
+  for (int u = 0; u < 3; ++u) {
+    const int w = threadIdx.x + 256 * u;
+    e_hc[u] = w % HCp;
+    e_hr[u] = (w / HCp) % HR;
+    e_ci[u] = w / (HCp * HR);
+  }
+  auto issue_halo = [&](uint32_t ct, int slot) {
+    if (ct < ctiles) {
+      int n, i0, j0;
+      decode(ct, n, i0, j0);
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {
+        const int w = threadIdx.x + 256 * u;
+        if (w < plane) {
+          const int ih = i0 + dhmin + e_hr[u], iw = j0 + dwmin + e_hc[u];
+          const bool ok = e_ci[u] < CN && ih >= 0 && ih < Hi && iw >= 0 && iw < Wi;
+          const float* src = ok ? in + ((size_t)n * CN + e_ci[u]) * plane_in + (size_t)ih * Wi + iw : in;
+          cp_async4_zfill(s_raw + (size_t)slot * plane + w, src, ok);
+        }
+      }
+    }
+    cp_async_commit_group();
+  };
+  // this lane's A values: k = 2t, 2t+1 -> channel t >> 1, pair t & 1 (k + 8: channel + 2); pixels g and g + 8
+  const bool has_pre = pre != nullptr;
+  const int pp = t & 1, cA = t >> 1, cB = cA + 2;
+  const bool pair_ok = 2 * pp + 1 < taps.n_taps;
+  const int pdh = pair_ok ? taps.dh[2 * pp] : 0;
+  const int pdw = pair_ok ? min(taps.dw[2 * pp], taps.dw[2 * pp + 1]) : 0;
+  const int ar = warp + pdh - dhmin, ac = g + pdw - dwmin;  // halo row / first column
+  const int awA = (cA * HR + ar) * HCp + ac, awB = (cB * HR + ar) * HCp + ac;
+  const bool okA = pair_ok && cA < CN, okB = pair_ok && cB < CN;
+  const float scA = (has_pre && cA < CN) ? __ldg(pre + cA) : 1.f, shA = (has_pre && cA < CN) ? __ldg(pre + CN + cA) : 0.f;
+  const float scB = (has_pre && cB < CN) ? __ldg(pre + cB) : 1.f, shB = (has_pre && cB < CN) ? __ldg(pre + CN + cB) : 0.f;
+#pragma unroll
+  for (int d = 0; d < kHaloDepth; ++d) issue_halo(blockIdx.x + (uint32_t)d * gridDim.x, d);
+  int k = 0;
+  for (uint32_t ct = blockIdx.x; ct < ctiles; ct += gridDim.x, ++k) {
+    cp_async_wait_group<kHaloDepth - 1>();
+    __syncthreads();  // block k's halo visible; everybody is done with block k - 1 (its slot is refilled next)
+    issue_halo(ct + (uint32_t)kHaloDepth * gridDim.x, (k + kHaloDepth) % (kHaloDepth + 1));
+    int n, i0, j0;
+    decode(ct, n, i0, j0);
+    const int i = i0 + warp;
+    const float* raw = s_raw + (size_t)(k % (kHaloDepth + 1)) * plane;
+    const int ih = i + pdh, iw = j0 + g + pdw;  // image position of the left value of pixel g's pair
+    const bool rok = ih >= 0 && ih < Hi;
+    bool cok[4];
+    cok[0] = rok && iw >= 0 && iw < Wi;
+    cok[1] = rok && iw + 1 >= 0 && iw + 1 < Wi;
+    cok[2] = rok && iw + 8 >= 0 && iw + 8 < Wi;
+    cok[3] = rok && iw + 9 >= 0 && iw + 9 < Wi;
+    uint32_t ahi[4], alo[4];
+    narrow_pair<FMT>(raw[awA], raw[awA + 1], okA && cok[0], okA && cok[1], scA, shA, has_pre, pre_relu, ahi[0], alo[0]);
+    narrow_pair<FMT>(raw[awA + 8], raw[awA + 9], okA && cok[2], okA && cok[3], scA, shA, has_pre, pre_relu, ahi[1], alo[1]);
+    narrow_pair<FMT>(raw[awB], raw[awB + 1], okB && cok[0], okB && cok[1], scB, shB, has_pre, pre_relu, ahi[2], alo[2]);
+    narrow_pair<FMT>(raw[awB + 8], raw[awB + 9], okB && cok[2], okB && cok[3], scB, shB, has_pre, pre_relu, ahi[3], alo[3]);
+    if (i < Ho) {
+      float dhi[8][4], dlo[8][4];
+#pragma unroll
+      for (int nn = 0; nn < 8; ++nn) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) dhi[nn][e] = dlo[nn][e] = 0.f;
+        mma16816<FMT>(dhi[nn], ahi, breg[nn].x, breg[nn].y);
+        mma16816<FMT>(dlo[nn], alo, breg[nn].x, breg[nn].y);
+        mma16816<FMT>(dlo[nn], ahi, breg[nn].z, breg[nn].w);
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int j = j0 + g + 8 * r;
+        uint32_t o[8];
+#pragma unroll
+        for (int nn = 0; nn < 8; ++nn)
+          o[nn] = pack2_t<FMT>(dhi[nn][2 * r] + dlo[nn][2 * r] * LoScale<FMT>::kDown,
+                               dhi[nn][2 * r + 1] + dlo[nn][2 * r + 1] * LoScale<FMT>::kDown);
+        if (j < Wo) {
+          uint4* dst = out + ((size_t)((size_t)n * Ho + i) * Wo + j) * 8 + t;
+          dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+          dst[4] = make_uint4(o[4], o[5], o[6], o[7]);
+        }
+      }
+    }
+  }
+  cp_async_wait_group<0>();
+}
+
 // Weight gradient, wide-tensor stationary: the CTA walks 32-pixel chunks of rows of b (NHWC, 64
 // ch); each thread owns one (pixel slot, 8-channel piece) whose 16 bytes arrive through a private
 // cp.async ring (kWgStages chunks in flight, no barrier needed: a thread reads only what it
@@ -845,6 +1016,165 @@ __global__ void __launch_bounds__(256, 2)
     const int cb = i & 63, t = (i >> 6) % kNarrowMaxTaps, c = i / (64 * kNarrowMaxTaps);
     if (t < taps.n_taps && ca0 + c < Ca)
       atomicAdd(accum + ((size_t)(ca0 + c) * taps.n_taps + t) * 64 + cb, s_acc[i]);
+  }
+}
+
+// The same weight gradient on mma.sync (sm_100a): GEMM M = (narrow channel, tap) = 4 x 4 rows, N = 64 wide
+// channels, K = pixels.  The wide tensor arrives as TMA boxes of 8 rows x 16 pixels x 64 channels (128B-swizzled,
+// 4-deep ring); `ldmatrix.x4.trans` turns its pixel-major rows into the k-major B fragments (pixels are the
+// reduction axis), four per 16 pixels.  The narrow operand f(a) is staged once per block in shared memory as
+// hi / lo 16-bit halves (fp32 accuracy), each word holding the PAIR (pixel p, p+1) so that an A register is one
+// LDS whatever the tap's column shift.  16 mma.sync + 4 ldmatrix + 8 LDS per 16 pixels and warp replace the
+// 384 fp32 FMAs per warp of the SIMT kernel (ncu: 20 M instructions, 57 % of the issue slots, 35 us).
+static constexpr int kWnStages = 4;
+static constexpr int kWnTile = 8 * 16 * 128;
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&b)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3])
+               : "r"(addr));
+}
+template <int FMT>
+__global__ void __launch_bounds__(256, 2)
+    wgrad_narrow_tma_kernel(const __grid_constant__ CUtensorMap tmap_b, const float* __restrict__ a,
+                            const float* __restrict__ pre, int pre_relu, float* __restrict__ accum, int N,
+                            int Ha, int Wa, int Ca, int ca0, int Hb, int Wb, NarrowTaps taps, int dhmax,
+                            int dwmax, int HR, int HC) {
+  extern __shared__ __align__(1024) uint8_t dsm[];  // [kWnStages][16 KB] wide tiles, then the narrow halo ring
+  if (smem_u32(dsm) & 1023u) __trap();
+  float* s_raw = reinterpret_cast<float*>(dsm + kWnStages * kWnTile);  // [kHaloDepth + 1][4 ca][HR][HC + 1]
+  __shared__ float s_red[16 * 64];
+  __shared__ uint64_t s_bar[kWnStages];
+  const int HCp = HC + 1, plane = 4 * HR * HCp;
+  for (int i = threadIdx.x; i < 16 * 64; i += blockDim.x) s_red[i] = 0.f;
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmap_b);
+    for (int b = 0; b < kWnStages; ++b) mbar_init(&s_bar[b], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const uint32_t JB = (uint32_t)(Wb + 15) >> 4, IB = (uint32_t)(Hb + 7) >> 3;
+  const uint32_t ctiles = (uint32_t)N * IB * JB;
+  auto decode = [&](uint32_t ct, int& n, int& i0, int& j0) {
+    const uint32_t q = ct / JB, jb = ct - q * JB;
+    const uint32_t nn = q / IB, ib = q - nn * IB;
+    n = (int)nn;
+    i0 = (int)(ib * 8);
+    j0 = (int)(jb * 16);
+  };
+  auto issue = [&](uint32_t ct, int buf) {
+    int n, i0, j0;
+    decode(ct, n, i0, j0);
+    mbar_arrive_expect_tx(&s_bar[buf], (uint32_t)kWnTile);
+    tma_load_4d(dsm + (size_t)buf * kWnTile, &tmap_b, &s_bar[buf], 0, j0, i0, n);
+  };
+  if (threadIdx.x == 0)
+    for (int b = 0; b < kWnStages - 1; ++b)
+      if (blockIdx.x + (uint32_t)b * gridDim.x < ctiles) issue(blockIdx.x + (uint32_t)b * gridDim.x, b);
+  // narrow halo element (ca, hr, hc) = a[n][ca0 + ca][i0 + hr - dhmax][j0 + hc - dwmax] (see issue_halo in
+  // narrow_in_pair_kernel)
+  const size_t a_plane = (size_t)Ha * Wa;
+  int e_ca[3], e_hr[3], e_hc[3];
+#pragma unroll
+  for (int u = 0; u < 3; ++u) {
+    const int w = threadIdx.x + 256 * u;
+    e_hc[u] = w % HCp;
+    e_hr[u] = (w / HCp) % HR;
+    e_ca[u] = w / (HCp * HR);
+  }
+  auto issue_halo = [&](uint32_t ct, int slot) {
+    if (ct < ctiles) {
+      int n, i0, j0;
+      decode(ct, n, i0, j0);
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {
+        const int w = threadIdx.x + 256 * u;
+        if (w < plane) {
+          const int ia = i0 + e_hr[u] - dhmax, ja = j0 + e_hc[u] - dwmax;
+          const bool ok = ca0 + e_ca[u] < Ca && ia >= 0 && ia < Ha && ja >= 0 && ja < Wa;
+          const float* src = ok ? a + ((size_t)n * Ca + ca0 + e_ca[u]) * a_plane + (size_t)ia * Wa + ja : a;
+          cp_async4_zfill(s_raw + (size_t)slot * plane + w, src, ok);
+        }
+      }
+    }
+    cp_async_commit_group();
+  };
+  // per-lane constants: A rows m = g and g + 8 -> channel m >> 2, tap m & 3; B row offsets
+  const bool has_pre = pre != nullptr;
+  const int tap = g & 3, cA = g >> 2, cB = cA + 2;
+  const bool tap_ok = tap < taps.n_taps;
+  const int tdh = tap_ok ? taps.dh[tap] : 0, tdw = tap_ok ? taps.dw[tap] : 0;
+  const int ar = warp - tdh + dhmax, ac = 2 * t - tdw + dwmax;
+  const int awA = (cA * HR + ar) * HCp + ac, awB = (cB * HR + ar) * HCp + ac;
+  const bool okA = tap_ok && ca0 + cA < Ca, okB = tap_ok && ca0 + cB < Ca;
+  const float scA = (has_pre && ca0 + cA < Ca) ? __ldg(pre + ca0 + cA) : 1.f;
+  const float shA = (has_pre && ca0 + cA < Ca) ? __ldg(pre + Ca + ca0 + cA) : 0.f;
+  const float scB = (has_pre && ca0 + cB < Ca) ? __ldg(pre + ca0 + cB) : 1.f;
+  const float shB = (has_pre && ca0 + cB < Ca) ? __ldg(pre + Ca + ca0 + cB) : 0.f;
+  uint32_t boff[4];
+  {
+    const int px = (lane & 7) + 8 * ((lane >> 3) & 1);
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      boff[q] = (uint32_t)((warp * 16 + px) * 128 + (((2 * q + (lane >> 4)) ^ (px & 7)) << 4));
+  }
+  float ahi[8][4], alo[8][4];
+#pragma unroll
+  for (int nn = 0; nn < 8; ++nn)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) ahi[nn][e] = alo[nn][e] = 0.f;
+#pragma unroll
+  for (int d = 0; d < kHaloDepth; ++d) issue_halo(blockIdx.x + (uint32_t)d * gridDim.x, d);
+  int k = 0;
+  for (uint32_t ct = blockIdx.x; ct < ctiles; ct += gridDim.x, ++k) {
+    const int buf = k % kWnStages;
+    cp_async_wait_group<kHaloDepth - 1>();
+    fence_proxy_async();  // generic-proxy reads of block k - 1's wide tile before its TMA refill below
+    __syncthreads();      // block k's halo visible; everybody is done with block k - 1
+    if (threadIdx.x == 0 && ct + (uint32_t)(kWnStages - 1) * gridDim.x < ctiles)
+      issue(ct + (uint32_t)(kWnStages - 1) * gridDim.x, (k + kWnStages - 1) % kWnStages);
+    issue_halo(ct + (uint32_t)kHaloDepth * gridDim.x, (k + kHaloDepth) % (kHaloDepth + 1));
+    int n, i0, j0;
+    decode(ct, n, i0, j0);
+    const float* raw = s_raw + (size_t)(k % (kHaloDepth + 1)) * plane;
+    const int ia = i0 + warp - tdh, ja = j0 + 2 * t - tdw;  // image position of A[.][k = 2t]
+    const bool rok = ia >= 0 && ia < Ha;
+    bool cok[4];
+    cok[0] = rok && ja >= 0 && ja < Wa;
+    cok[1] = rok && ja + 1 >= 0 && ja + 1 < Wa;
+    cok[2] = rok && ja + 8 >= 0 && ja + 8 < Wa;
+    cok[3] = rok && ja + 9 >= 0 && ja + 9 < Wa;
+    uint32_t fh[4], fl[4];  // a0 = (m g, k 2t..), a1 = (m g+8, k 2t..), a2 = (m g, k 2t+8..), a3 = (m g+8, k 2t+8..)
+    narrow_pair<FMT>(raw[awA], raw[awA + 1], okA && cok[0], okA && cok[1], scA, shA, has_pre, pre_relu, fh[0], fl[0]);
+    narrow_pair<FMT>(raw[awB], raw[awB + 1], okB && cok[0], okB && cok[1], scB, shB, has_pre, pre_relu, fh[1], fl[1]);
+    narrow_pair<FMT>(raw[awA + 8], raw[awA + 9], okA && cok[2], okA && cok[3], scA, shA, has_pre, pre_relu, fh[2], fl[2]);
+    narrow_pair<FMT>(raw[awB + 8], raw[awB + 9], okB && cok[2], okB && cok[3], scB, shB, has_pre, pre_relu, fh[3], fl[3]);
+    mbar_wait(&s_bar[buf], ((uint32_t)(k / kWnStages)) & 1u);
+    const uint32_t tile = smem_u32(dsm) + (uint32_t)(buf * kWnTile);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint32_t b[4];
+      ldmatrix_x4_trans(b, tile + boff[q]);
+      mma16816<FMT>(ahi[2 * q], fh, b[0], b[1]);
+      mma16816<FMT>(alo[2 * q], fl, b[0], b[1]);
+      mma16816<FMT>(ahi[2 * q + 1], fh, b[2], b[3]);
+      mma16816<FMT>(alo[2 * q + 1], fl, b[2], b[3]);
+    }
+  }
+  cp_async_wait_group<0>();
+  // D[m][n]: rows g / g + 8, columns 8 nn + 2t + {0, 1}; fold the warps in shared memory, one atomic per value
+#pragma unroll
+  for (int nn = 0; nn < 8; ++nn)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int m = g + 8 * (e >> 1), n = 8 * nn + 2 * t + (e & 1);
+      atomicAdd(&s_red[m * 64 + n], ahi[nn][e] + alo[nn][e] * LoScale<FMT>::kDown);
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 16 * 64; i += blockDim.x) {
+    const int n = i & 63, m = i >> 6, ca = m >> 2, tp = m & 3;
+    if (tp < taps.n_taps && ca0 + ca < Ca)
+      atomicAdd(accum + ((size_t)(ca0 + ca) * taps.n_taps + tp) * 64 + n, s_red[i]);
   }
 }
 
@@ -1261,6 +1591,46 @@ int ghnd_conv_narrow_in(const float* x, const float* pre_scale_shift, int pre_re
   NarrowTaps taps;
   taps.n_taps = R * S;
   int Ho, Wo;
+  {
+    // paired-tap kernel: bch <= 4, 64 wide channels, taps in horizontally adjacent pairs (S == 2)
+    static const bool pair_off = [] {
+      const char* e = getenv("GHND_NARROW_TMA");
+      return e != nullptr && atoi(e) == 0;
+    }();
+    const int ho = flip ? H - 2 * pad + R - 1 : H + 2 * pad - R + 1;
+    const int wo = flip ? W - 2 * pad + S - 1 : W + 2 * pad - S + 1;
+    if (!pair_off && K == 64 && C <= 4 && S == 2 && R <= 2 && ho > 0 && wo > 0 &&
+        (int64_t)N * ho * wo < (int64_t)1 << 30) {
+      int dhmin = 1 << 20, dhmax = -(1 << 20), dwmin = 1 << 20, dwmax = -(1 << 20);
+      for (int r = 0; r < R; ++r)
+        for (int s2 = 0; s2 < S; ++s2) {
+          const int dh = flip ? pad - r : r - pad, dw = flip ? pad - s2 : s2 - pad;
+          taps.dh[r * S + s2] = dh;
+          taps.dw[r * S + s2] = dw;
+          dhmin = dh < dhmin ? dh : dhmin;
+          dhmax = dh > dhmax ? dh : dhmax;
+          dwmin = dw < dwmin ? dw : dwmin;
+          dwmax = dw > dwmax ? dw : dwmax;
+        }
+      const int HR = 8 + dhmax - dhmin, HC = 16 + dwmax - dwmin;
+      const int64_t ctiles = (int64_t)N * ((ho + 7) / 8) * ((wo + 15) / 16);
+      int blocks = num_sms() * 2;
+      if (blocks > ctiles) blocks = (int)ctiles;
+      const size_t smem = (size_t)(kHaloDepth + 1) * 4 * HR * (HC + 1) * sizeof(float);
+      if (4 * HR * (HC + 1) <= 768) {
+        if (y_fmt == GHND_F16)
+          narrow_in_pair_kernel<GHND_F16><<<blocks, 256, smem, st>>>(x, pre_scale_shift, pre_relu, w, flip ? 1 : 0,
+                                                                    (uint4*)y, N, H, W, C, ho, wo, taps, dhmin, dwmin,
+                                                                    HR, HC);
+        else
+          narrow_in_pair_kernel<GHND_BF16><<<blocks, 256, smem, st>>>(x, pre_scale_shift, pre_relu, w, flip ? 1 : 0,
+                                                                     (uint4*)y, N, H, W, C, ho, wo, taps, dhmin, dwmin,
+                                                                     HR, HC);
+        GHND_LAUNCH_CHECK("narrow_in_pair_kernel");
+        return GHND_OK;
+      }
+    }
+  }
   if (!flip) {
     Ho = H + 2 * pad - R + 1;
     Wo = W + 2 * pad - S + 1;
@@ -1327,6 +1697,50 @@ int ghnd_wgrad_narrow(const float* a, const float* pre_scale_shift, int pre_relu
   const int64_t npix = (int64_t)N * Ha * Wa;
   const int64_t chunks_b = (int64_t)N * Hb * ((Wb + kWgChunk - 1) / kWgChunk);
   const bool fast = Cb == 64 && chunks_b < (int64_t)1 << 30 && (b_fmt == GHND_F16 || b_fmt == GHND_BF16);
+  static const bool tma_off = [] {
+    const char* e = getenv("GHND_NARROW_TMA");
+    return e != nullptr && atoi(e) == 0;
+  }();
+  if (fast && !tma_off) {
+    int dh0 = taps.dh[0], dh1 = dh0, dw0 = taps.dw[0], dw1 = dw0;
+    for (int t = 1; t < taps.n_taps; ++t) {
+      dh0 = taps.dh[t] < dh0 ? taps.dh[t] : dh0;
+      dh1 = taps.dh[t] > dh1 ? taps.dh[t] : dh1;
+      dw0 = taps.dw[t] < dw0 ? taps.dw[t] : dw0;
+      dw1 = taps.dw[t] > dw1 ? taps.dw[t] : dw1;
+    }
+    const int HR = 8 + dh1 - dh0, HC = 16 + dw1 - dw0;
+    CUtensorMap tmap;
+    uint64_t dims[4] = {64, (uint64_t)Wb, (uint64_t)Hb, (uint64_t)N};
+    uint64_t str[4] = {2, 128, (uint64_t)Wb * 128, (uint64_t)Hb * Wb * 128};
+    uint32_t box[4] = {64, 16, 8, 1};
+    if (4 * HR * (HC + 1) <= 768 && encode_tmap(&tmap, 2, 4, const_cast<void*>(b), dims, str, box, 128) == GHND_OK) {
+      const size_t smem = (size_t)kWnStages * kWnTile + (size_t)(kHaloDepth + 1) * 4 * HR * (HC + 1) * sizeof(float);
+      static bool attr = false;
+      if (!attr) {
+        cudaFuncSetAttribute(wgrad_narrow_tma_kernel<GHND_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        cudaFuncSetAttribute(wgrad_narrow_tma_kernel<GHND_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        attr = true;
+      }
+      const int64_t ctiles = (int64_t)N * ((Hb + 7) / 8) * ((Wb + 15) / 16);
+      int blocks = num_sms() * 2;
+      if (blocks > ctiles) blocks = (int)ctiles;
+      for (int ca0 = 0; ca0 < Ca; ca0 += 4) {
+        if (b_fmt == GHND_F16)
+          wgrad_narrow_tma_kernel<GHND_F16><<<blocks, 256, smem, st>>>(tmap, a, pre_scale_shift, pre_relu,
+                                                                      (float*)workspace, N, Ha, Wa, Ca, ca0, Hb, Wb,
+                                                                      taps, dh1, dw1, HR, HC);
+        else
+          wgrad_narrow_tma_kernel<GHND_BF16><<<blocks, 256, smem, st>>>(tmap, a, pre_scale_shift, pre_relu,
+                                                                       (float*)workspace, N, Ha, Wa, Ca, ca0, Hb, Wb,
+                                                                       taps, dh1, dw1, HR, HC);
+        GHND_LAUNCH_CHECK("wgrad_narrow_tma_kernel");
+      }
+      wgrad_narrow_finish_kernel<<<4, 256, 0, st>>>((const float*)workspace, dw_oihw, a_is_output, Ca, Cb, R, S);
+      GHND_LAUNCH_CHECK("wgrad_narrow_finish_kernel");
+      return GHND_OK;
+    }
+  }
   for (int ca0 = 0; ca0 < Ca; ca0 += 3) {
     if (fast) {
       int blocks = num_sms() * 2;
