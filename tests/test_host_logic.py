@@ -259,7 +259,10 @@ def _train_worker(rank, world, port, q):
             assert flat.params[n].grad.data_ptr() == flat.grads[n].data_ptr()
         parallel.allreduce_flat_grad(flat)
         opt.step()
-    q.put((rank, start, flat.flat.clone(), model[1].running_mean.clone(), local))
+    # numpy arrays travel through the queue by value (torch tensors are passed as shared-memory handles that
+    # die with this process: the parent then fails with FileNotFoundError if it reads after our exit)
+    q.put((rank, start.numpy(), flat.flat.detach().clone().numpy(), model[1].running_mean.clone().numpy(),
+           [g.numpy() for g in local]))
     dist.destroy_process_group()
 
 
@@ -297,7 +300,10 @@ def test_two_rank_training_keeps_replicas_identical():
         if res is not None:
             break
     assert res is not None, "2-rank gloo workers did not report"
-    (_, s0, p0, rm0, g0), (_, s1, p1, rm1, g1) = res
+    def to_t(r):
+        return (r[0], torch.from_numpy(r[1]), torch.from_numpy(r[2]), torch.from_numpy(r[3]),
+                [torch.from_numpy(g) for g in r[4]])
+    (_, s0, p0, rm0, g0), (_, s1, p1, rm1, g1) = [to_t(r) for r in res]
     assert torch.equal(s0, s1) and torch.equal(rm0, rm1)      # broadcast at start
     assert torch.equal(p0, p1) and not torch.equal(p0, s0)    # replicas stay identical and did move
     ref, m, v = s0.clone(), torch.zeros_like(s0), torch.zeros_like(s0)
