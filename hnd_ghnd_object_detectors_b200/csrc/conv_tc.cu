@@ -1455,6 +1455,8 @@ static bool plan_conv_halo(ConvLaunch* L, const ghnd_conv_desc_t* d, int gemm_ci
   return true;
 }
 
+static int max_conv_pairs();  // CTA pairs the device can hold at once (0: cluster launches unavailable)
+
 static int finish_launch(ConvLaunch* L, const ghnd_conv_desc_t* d, int gemm_cin, int gemm_cout,
                          const void* weights, int total_taps, const IoGeom& g, int kblock = 64,
                          int force_block_n = 0, bool try_halo = false) {
@@ -1631,7 +1633,8 @@ static int finish_launch(ConvLaunch* L, const ghnd_conv_desc_t* d, int gemm_cin,
   const int pair_want = pair_env >= 0 ? pair_env : (pair_auto ? 1 : 0);
   const int want = pair_want ? pair_want : mc_env;
   if (want != 0 && !p.halo && kblock == 64 && d->stats == nullptr && p.block_n >= 128 && m_tiles >= 2 &&
-      num_sms() % 2 == 0 && (want == 2 || (int64_t)((m_tiles + 1) / 2) * p.n_tiles_n >= num_sms() / 2)) {
+      num_sms() % 2 == 0 && (want == 2 || (int64_t)((m_tiles + 1) / 2) * p.n_tiles_n >= num_sms() / 2) &&
+      max_conv_pairs() > 0) {
     uint32_t hbox[2] = {(uint32_t)kblock, (uint32_t)(p.block_n / 2)};
     if (encode_tmap(&p.tmap_b, 2, 2, const_cast<void*>(weights), dims, str, hbox, row_bytes) == GHND_OK) {
       p.mc = pair_want ? 2 : 1;
@@ -1645,6 +1648,7 @@ static int finish_launch(ConvLaunch* L, const ghnd_conv_desc_t* d, int gemm_cin,
         p.n_stages = st2;
         L->smem = (size_t)p.n_stages * p.stage_bytes + (size_t)fixed + (size_t)ring * n_in * kChunkBytes + 512;
         p.idesc = make_idesc(d->src_fmt, d->w_fmt, 0, 0, 2 * kBlockM, p.block_n);
+        if (L->grid > 2 * max_conv_pairs()) L->grid = 2 * max_conv_pairs();
       }
     } else {
       rc = encode_tmap(&p.tmap_b, 2, 2, const_cast<void*>(weights), dims, str, box, row_bytes);
@@ -1730,6 +1734,33 @@ static int set_conv_attr() {
     attr_set = true;
   }
   return GHND_OK;
+}
+
+// As many CTA pairs as the device can hold at once (the persistent loop takes any even grid).  A device that
+// cannot co-schedule a pair of these CTAs (MIG slices, odd SM masks) keeps the single-CTA kernels.
+static int max_conv_pairs() {
+  static const int n_pairs = [] {
+    if (set_conv_attr() != GHND_OK) return 0;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(num_sms() & ~1), 1, 1);
+    cfg.blockDim = dim3(kConvThreads, 1, 1);
+    cfg.dynamicSmemBytes = 227 * 1024;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, conv_tc_kernel<1, 0, false, true>, &cfg) != cudaSuccess) {
+      cudaGetLastError();
+      return 0;
+    }
+    return n;
+  }();
+  return n_pairs;
 }
 
 }  // namespace ghnd

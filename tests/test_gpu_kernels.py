@@ -822,3 +822,17 @@ def test_adam(ops):
         ops.adam_step(pd, gs.cuda(), md, vd, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1.0, step)
     assert rel(pd.cpu(), p) < 1e-6
     assert rel(md.cpu(), m) < 1e-6 and rel(vd.cpu(), v) < 1e-6
+
+
+def test_switched_off_paths_still_pass():
+    """The A/B switches select the older kernels (direct-load / SIMT bottleneck-side kernels, un-fused stem +
+    pool, no CTA pairs, no conv halo mode).  They are read once per process, so the same kernel tests run again
+    in a child process with every switch off: the fall-back paths stay correct."""
+    import subprocess
+    import sys
+    env = dict(os.environ, GHND_NARROW_TMA="0", GHND_STEM_POOL="0", GHND_CONV_PAIR="0", GHND_CONV_HALO="0")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "tests/test_gpu_kernels.py", "-k",
+                        "test_narrow_convs or test_conv_fwd or test_conv_dgrad or test_stem or test_narrow_out_minmax"],
+                       cwd=root, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
