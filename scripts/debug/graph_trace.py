@@ -32,10 +32,44 @@ torch.cuda.synchronize()
 plan = next(iter(box._plans.values()))
 REPS = 4
 from torch.profiler import profile, ProfilerActivity
-with profile(activities=[ProfilerActivity.CUDA]) as prof:
-    for _ in range(REPS):
-        plan.step()
+E2E = len(sys.argv) > 2 and sys.argv[2] == "e2e"  # the public-API loop (host images, prefetcher, backward, Adam)
+if E2E:
+    from hnd_ghnd_object_detectors_b200.optim import FusedAdam
+    from hnd_ghnd_object_detectors_b200.prefetch import AsyncScalarReader, DevicePrefetcher
+    flat = box.flatten_parameters()
+    opt = FusedAdam([p for p in student.parameters() if p.requires_grad], lr=1e-3, flat=flat)
+    host_images = [im.cpu().pin_memory() for im in images]
+
+    class _Endless(object):
+        def __iter__(self):
+            while True:
+                yield host_images, None
+
+        def __len__(self):
+            return 1 << 30
+    it, reader = iter(DevicePrefetcher(_Endless(), dev)), AsyncScalarReader()
+
+    def one_step():
+        imgs, _ = next(it)
+        l = box(imgs, targets)
+        opt.zero_grad()
+        l.backward()
+        opt.step()
+        reader.push(l)
+    for _ in range(5):
+        one_step()
     torch.cuda.synchronize()
+    REPS = 6
+else:
+    one_step = plan.step
+import time
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    th = time.perf_counter()
+    for _ in range(REPS):
+        one_step()
+    th = time.perf_counter() - th
+    torch.cuda.synchronize()
+print("host loop time %.1f us per step (returns before the GPU is done unless the in-flight bound blocks)" % (th / REPS * 1e6))
 path = "gpurun_out/graph_trace.json"
 prof.export_chrome_trace(path)
 ev = [e for e in json.load(open(path))["traceEvents"] if e.get("cat") in ("kernel", "gpu_memset", "gpu_memcpy") and "dur" in e]
