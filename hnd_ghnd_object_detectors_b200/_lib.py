@@ -65,6 +65,8 @@ SIGNATURES = {
     "ghnd_stem_pack_image": (_I, [_P, _I, _I, POINTER(c_float), POINTER(c_float), _P, _I, _I, _I, _I, _P]),
     "ghnd_stem_pack_image_resized": (_I, [_P, _I, _I, _I, _I, c_float, c_float, POINTER(c_float),
                                           POINTER(c_float), _P, _I, _I, _I, _I, _P]),
+    "ghnd_stem_pack_images": (_I, [POINTER(c_void_p), POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int),
+                                   POINTER(c_float), _I, POINTER(c_float), POINTER(c_float), _P, _I, _I, _I, _I, _P]),
     "ghnd_conv_plan_create": (_I, [POINTER(ConvDesc), POINTER(c_void_p)]),
     "ghnd_conv_plan_run": (_I, [_P, _P]),
     "ghnd_conv_plan_run_range": (_I, [_P, _I, _I, _P]),

@@ -132,6 +132,63 @@ __global__ void stem_pack_resize_kernel(const float* __restrict__ img, int H, in
   }
 }
 
+// The whole batch in ONE launch (grid z = image): per-image source pointer, size and resize factor travel in
+// the kernel parameters.  rscale == 0: no resize.  Same arithmetic as the two single-image kernels above.
+static constexpr int kPackMaxImages = 16;
+struct PackBatch {
+  const float* img[kPackMaxImages];
+  int H[kPackMaxImages], W[kPackMaxImages], Ho[kPackMaxImages], Wo[kPackMaxImages];
+  float rh[kPackMaxImages], rw[kPackMaxImages];
+};
+__global__ void stem_pack_batch_kernel(const __grid_constant__ PackBatch b, float m0, float m1, float m2, float s0,
+                                       float s1, float s2, uint2* __restrict__ dst, int fmt, int rows, int cols,
+                                       int n_index0) {
+  const int z = blockIdx.z, r = blockIdx.y;
+  const float* __restrict__ img = b.img[z];
+  const int H = b.H[z], W = b.W[z], Ho = b.Ho[z], Wo = b.Wo[z];
+  const float rh = b.rh[z], rw = b.rw[z];
+  const bool resize = rh != 0.f;
+  const int64_t hw = (int64_t)H * W;
+  uint2* out = dst + (int64_t)(n_index0 + z) * rows * cols;
+  const float mean[3] = {m0, m1, m2}, sd[3] = {s0, s1, s2};
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < cols; c += gridDim.x * blockDim.x) {
+    const int h = r - 3, w = c - 3;
+    uint2 o = make_uint2(0u, 0u);
+    if (h >= 0 && h < Ho && w >= 0 && w < Wo) {
+      float v[3];
+      if (!resize) {
+        const int64_t at = (int64_t)h * W + w;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) v[ch] = __fdiv_rn(__fsub_rn(img[ch * hw + at], mean[ch]), sd[ch]);
+      } else {
+        float hr = __fsub_rn(__fmul_rn(rh, (float)h + 0.5f), 0.5f);
+        float wr = __fsub_rn(__fmul_rn(rw, (float)w + 0.5f), 0.5f);
+        hr = hr < 0.f ? 0.f : hr;
+        wr = wr < 0.f ? 0.f : wr;
+        int h1 = (int)hr, w1 = (int)wr;
+        h1 = h1 > H - 1 ? H - 1 : h1;
+        w1 = w1 > W - 1 ? W - 1 : w1;
+        const int hp = (h1 < H - 1) ? 1 : 0, wp = (w1 < W - 1) ? 1 : 0;
+        const float h1l = hr - (float)h1, h0l = 1.f - h1l;
+        const float w1l = wr - (float)w1, w0l = 1.f - w1l;
+        const int64_t a00 = (int64_t)h1 * W + w1, a01 = a00 + wp, a10 = a00 + (int64_t)hp * W, a11 = a10 + wp;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+          const float* p = img + ch * hw;
+          const float x00 = __fdiv_rn(__fsub_rn(p[a00], mean[ch]), sd[ch]);
+          const float x01 = __fdiv_rn(__fsub_rn(p[a01], mean[ch]), sd[ch]);
+          const float x10 = __fdiv_rn(__fsub_rn(p[a10], mean[ch]), sd[ch]);
+          const float x11 = __fdiv_rn(__fsub_rn(p[a11], mean[ch]), sd[ch]);
+          v[ch] = h0l * (w0l * x00 + w1l * x01) + h1l * (w0l * x10 + w1l * x11);
+        }
+      }
+      o.x = pack2(v[0], v[1], fmt);
+      o.y = pack2(v[2], 0.f, fmt);
+    }
+    out[(int64_t)r * cols + c] = o;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // max-pool 3x3 s2 p1 (NHWC, 8 channels per thread) + backward fused with the ReLU mask
 // ------------------------------------------------------------------------------------------------
@@ -1023,6 +1080,40 @@ int ghnd_stem_pack_image_resized(const float* img_chw, int H, int W, int Ho, int
       img_chw, H, W, Ho, Wo, rscale_h, rscale_w, mean[0], mean[1], mean[2], std_[0], std_[1], std_[2],
       d, dst_fmt, rows, cols);
   GHND_LAUNCH_CHECK("stem_pack_resize_kernel");
+  return GHND_OK;
+}
+
+int ghnd_stem_pack_images(const float* const* imgs_chw, const int* H, const int* W, const int* Ho, const int* Wo,
+                          const float* rscale, int n, const float* mean, const float* std_, void* dst, int dst_fmt,
+                          int n_index0, int Hp, int Wp, void* stream) {
+  GHND_CHECK_ARG(imgs_chw && H && W && Ho && Wo && rscale && mean && std_ && dst && fmt16(dst_fmt) && n > 0 &&
+                     n_index0 >= 0,
+                 "stem_pack_images: bad argument");
+  GHND_CHECK_ARG(Hp > 0 && Wp > 0 && Hp % 2 == 0 && Wp % 8 == 0 && Hp + 6 <= 65535, "stem_pack_images: bad slot %dx%d",
+                 Hp, Wp);
+  const int rows = Hp + 6, cols = Wp + 8;
+  for (int i0 = 0; i0 < n; i0 += kPackMaxImages) {
+    const int m = n - i0 < kPackMaxImages ? n - i0 : kPackMaxImages;
+    PackBatch b;
+    memset(&b, 0, sizeof(b));
+    for (int i = 0; i < m; ++i) {
+      const int k = i0 + i;
+      GHND_CHECK_ARG(imgs_chw[k] && H[k] > 0 && W[k] > 0 && Ho[k] > 0 && Wo[k] > 0 && Ho[k] <= Hp && Wo[k] <= Wp &&
+                         rscale[k] >= 0.f && (rscale[k] != 0.f || (Ho[k] == H[k] && Wo[k] == W[k])),
+                     "stem_pack_images: bad geometry of image %d (H=%d W=%d Ho=%d Wo=%d Hp=%d Wp=%d)", k, H[k], W[k],
+                     Ho[k], Wo[k], Hp, Wp);
+      b.img[i] = imgs_chw[k];
+      b.H[i] = H[k];
+      b.W[i] = W[k];
+      b.Ho[i] = Ho[k];
+      b.Wo[i] = Wo[k];
+      b.rh[i] = b.rw[i] = rscale[k];
+    }
+    stem_pack_batch_kernel<<<dim3((unsigned)((cols + 255) / 256), (unsigned)rows, (unsigned)m), 256, 0,
+                             (cudaStream_t)stream>>>(b, mean[0], mean[1], mean[2], std_[0], std_[1], std_[2],
+                                                     (uint2*)dst, dst_fmt, rows, cols, n_index0 + i0);
+    GHND_LAUNCH_CHECK("stem_pack_batch_kernel");
+  }
   return GHND_OK;
 }
 

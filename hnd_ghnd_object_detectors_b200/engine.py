@@ -758,8 +758,7 @@ class GhndPlan(object):
     def load_images(self, images):
         """images: list of N fp32 [3,H,W] CUDA tensors in [0,1] (already at network scale)."""
         assert len(images) == self.N, "plan was built for batch %d" % self.N
-        for i, im in enumerate(images):
-            ops.stem_pack_image(im, self.packed, i, self.Hp, self.Wp, self.mean, self.std)
+        ops.stem_pack_images(images, self.packed, self.Hp, self.Wp, self.mean, self.std)
 
     def forward_backward(self):
         """Enqueue teacher fwd, student fwd, loss and student bwd on the current stream."""
@@ -875,8 +874,7 @@ class EncodePlan(object):
 
     def load_images(self, images):
         assert len(images) == self.N
-        for i, im in enumerate(images):
-            ops.stem_pack_image(im, self.packed, i, self.Hp, self.Wp, self.mean, self.std)
+        ops.stem_pack_images(images, self.packed, self.Hp, self.Wp, self.mean, self.std)
 
     def forward(self):
         self.stem.refresh_weights()
@@ -969,8 +967,7 @@ class BodyPlan(object):
 
     def run(self, images):
         assert len(images) == self.N
-        for i, im in enumerate(images):
-            ops.stem_pack_image(im, self.packed, i, self.Hp, self.Wp, self.mean, self.std)
+        ops.stem_pack_images(images, self.packed, self.Hp, self.Wp, self.mean, self.std)
         self.stem.refresh_weights()
         self.stem.forward()
         self.skipped, self.ext_z = False, None

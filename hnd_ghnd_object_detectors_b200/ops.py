@@ -397,6 +397,29 @@ def stem_pack_image(img, dst, n_index, Hp, Wp, mean, std):
     _count()
 
 
+def stem_pack_images(imgs, dst, Hp, Wp, mean, std, n_index0=0):
+    """All images of a batch (fp32 [3,H,W] in [0,1], or ScaledImage) -> dst[n_index0 ...] in ONE launch."""
+    n = len(imgs)
+    m = (c_float * 3)(*[float(v) for v in mean])
+    s = (c_float * 3)(*[float(v) for v in std])
+    srcs, keep = [], []
+    H, W, Ho, Wo, rs = (ctypes.c_int * n)(), (ctypes.c_int * n)(), (ctypes.c_int * n)(), (ctypes.c_int * n)(), (c_float * n)()
+    for k, img in enumerate(imgs):
+        src = img.src if isinstance(img, ScaledImage) else img
+        _need_cuda(src, dst)
+        src = src.float().contiguous()
+        keep.append(src)
+        srcs.append(ptr(src))
+        H[k], W[k] = src.shape[1], src.shape[2]
+        Ho[k], Wo[k] = img.shape[1], img.shape[2]
+        # ATen: static_cast<float>(1.0 / scale_factor), same for both axes; 0 = no resize
+        rs[k] = 1.0 / img.scale if isinstance(img, ScaledImage) else 0.0
+    arr = (c_void_p * n)(*srcs)
+    call("ghnd_stem_pack_images", arr, H, W, Ho, Wo, rs, n, m, s, ptr(dst), fmt_of(dst.dtype), n_index0, Hp, Wp,
+         stream_ptr())
+    _count((n + 15) // 16)
+
+
 # ------------------------------------------------------------------------------------------------
 # narrow convs (planar fp32 bottleneck side <-> NHWC 16-bit wide side)
 # ------------------------------------------------------------------------------------------------

@@ -120,6 +120,13 @@ int ghnd_stem_pack_image(const float* img_chw, int H, int W, const float* mean, 
 int ghnd_stem_pack_image_resized(const float* img_chw, int H, int W, int Ho, int Wo, float rscale_h,
                                  float rscale_w, const float* mean, const float* std_, void* dst,
                                  int dst_fmt, int n_index, int Hp, int Wp, void* stream);
+/* The whole batch in ONE launch (the per-image calls above cost a launch each on the end-to-end path):
+ * image k = imgs_chw[k] of H[k] x W[k], written at H'[k] = Ho[k] x Wo[k] into slot n_index0 + k; rscale[k] = 0
+ * means no resize (then Ho = H, Wo = W), else the ATen source-index scale 1/scale_factor of
+ * ghnd_stem_pack_image_resized.  All arrays are HOST arrays of n entries. */
+int ghnd_stem_pack_images(const float* const* imgs_chw, const int* H, const int* W, const int* Ho, const int* Wo,
+                          const float* rscale, int n, const float* mean, const float* std_, void* dst, int dst_fmt,
+                          int n_index0, int Hp, int Wp, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Wide convolutions: implicit GEMM on tcgen05 tensor cores (TMA-fed, TMEM accumulators).

@@ -774,6 +774,29 @@ def test_stem_pack_with_resize(ops, golden_dir, dt):
         assert rel(got, O.transform_batch(imgs, sizes=sizes, max_size=max_size)) < 2 * ulp
 
 
+def test_stem_pack_images_batch_equals_per_image(ops):
+    """One launch for the whole batch (plain and resized images mixed, 18 images = two launches of <= 16) writes
+    exactly what the per-image entry points write."""
+    torch.manual_seed(3)
+    Hp, Wp = 96, 128
+    imgs = []
+    for k in range(18):
+        im = torch.rand(3, 40 + 3 * k, 50 + 4 * k).cuda()
+        if k % 3 == 1:
+            im = ops.ScaledImage(torch.rand(3, 30 + k, 44 + k).cuda(), 1.37 + 0.01 * k)
+        imgs.append(im)
+    for dt in (torch.float16, torch.bfloat16):
+        a = torch.full((18, Hp + 6, Wp + 8, 4), 3.0, dtype=dt, device="cuda")
+        b = torch.full_like(a, 5.0)
+        for i, im in enumerate(imgs):
+            ops.stem_pack_image(im, a, i, Hp, Wp, O.IMAGE_MEAN, O.IMAGE_STD)
+        ops.stem_pack_images(imgs, b, Hp, Wp, O.IMAGE_MEAN, O.IMAGE_STD)
+        assert torch.equal(a, b)
+    from hnd_ghnd_object_detectors_b200._lib import GhndError
+    with pytest.raises(GhndError):  # image larger than the slot
+        ops.stem_pack_images([torch.rand(3, 100, 100).cuda()], b, Hp, Wp, O.IMAGE_MEAN, O.IMAGE_STD)
+
+
 def test_stem_pack_resize_errors(ops):
     packed = torch.zeros((1, 32 + 6, 32 + 8, 4), dtype=torch.float16, device="cuda")
     from hnd_ghnd_object_detectors_b200._lib import GhndError
