@@ -388,18 +388,40 @@ template <int FMT>
 __device__ __forceinline__ void epi_stats_rows(const uint8_t* base, int quarter, int lane,
                                                uint32_t valid, float* sstat, int ch, int cout) {
   float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-#pragma unroll 8
-  for (int i = 0; i < 32; ++i) {
-    const int r = quarter * 32 + i;
-    const uint32_t w = *reinterpret_cast<const uint32_t*>(base + r * 128 +
-                                                          ((((lane >> 2) ^ (r & 7))) << 4) +
-                                                          ((lane & 3) << 2));
-    if ((valid >> i) & 1u) {
-      const float2 f = unpack2_t<FMT>(w);
+  // this lane's 4 bytes of row r: chunk (lane >> 2) ^ (r & 7); r & 7 == i & 7 (quarter * 32 is a multiple of 8)
+  const uint8_t* col = base + quarter * 32 * 128 + ((lane & 3) << 2);
+  const int chunk = lane >> 2;
+  if (valid == 0xffffffffu) {  // interior tile (uniform): no per-row predicate, two independent chains
+    float t0 = 0.f, t1 = 0.f, u0 = 0.f, u1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+      const float2 f = unpack2_t<FMT>(*reinterpret_cast<const uint32_t*>(col + i * 128 + ((chunk ^ (i & 7)) << 4)));
+      const float2 g =
+          unpack2_t<FMT>(*reinterpret_cast<const uint32_t*>(col + (i + 1) * 128 + ((chunk ^ ((i + 1) & 7)) << 4)));
       s0 += f.x;
       s1 += f.y;
       q0 = fmaf(f.x, f.x, q0);
       q1 = fmaf(f.y, f.y, q1);
+      t0 += g.x;
+      t1 += g.y;
+      u0 = fmaf(g.x, g.x, u0);
+      u1 = fmaf(g.y, g.y, u1);
+    }
+    s0 += t0;
+    s1 += t1;
+    q0 += u0;
+    q1 += u1;
+  } else {
+#pragma unroll 8
+    for (int i = 0; i < 32; ++i) {
+      const uint32_t w = *reinterpret_cast<const uint32_t*>(col + i * 128 + ((chunk ^ (i & 7)) << 4));
+      if ((valid >> i) & 1u) {
+        const float2 f = unpack2_t<FMT>(w);
+        s0 += f.x;
+        s1 += f.y;
+        q0 = fmaf(f.x, f.x, q0);
+        q1 = fmaf(f.y, f.y, q1);
+      }
     }
   }
   // `sstat` is PRIVATE to this warp and each lane owns its channel pair: plain read-modify-write.
