@@ -323,11 +323,19 @@ class StemRunner(object):
         if not self.fused:
             ops.maxpool3x3s2(self.conv, self.out, self.argmax, channels=64, channel_offset=self.c_off)
 
+    def convert_image(self):
+        """The packed image in the gradient format (operand of the tensor-core dW).  Depends on the image only:
+        the plan runs it on the side stream at the start of the step instead of in the backward tail."""
+        if self.trainable and self.packed_g is not self.packed:
+            ops.convert16(self.packed, self.packed_g)
+        self.image_converted = True
+
     def backward(self, g_out, dw):
         """g_out: gradient w.r.t. the pooled output; dw: fp32 OIHW view for conv1.weight.grad."""
         ops.maxpool3x3s2_bwd(self.conv, self.argmax, g_out, self.g_conv, channel_offset=self.c_off)
-        if self.packed_g is not self.packed:
+        if self.packed_g is not self.packed and not getattr(self, "image_converted", False):
             ops.convert16(self.packed, self.packed_g)
+        self.image_converted = False
         if self.wgrad is None or self.wgrad_dw is not dw:
             self.wgrad = ops.StemWgradPlan(self.packed_g, self.g_conv, self.scale, dw, self.N, self.Hp, self.Wp,
                                            ws=self.ws)
@@ -510,8 +518,9 @@ class StudentLayer1Runner(object):
     def forward_encoder(self, minmax=None):
         """minmax: fp32 buffer for the (min, max) partial pairs of z (the quantizer's first pass,
         fused into the last encoder conv); the number of pairs is left in self.z_pairs."""
-        if self.train and self._own_xg:
+        if self.train and self._own_xg and not getattr(self, "xg_converted", False):
             ops.convert16(self.x, self.x_g)
+        self.xg_converted = False
         self.e0.forward()
         self.e1.forward()
         self.e2.forward()
@@ -586,6 +595,13 @@ class StudentLayer1Runner(object):
     def prepack(self):
         for u in self.wide_units():
             u.prepack()
+
+    def convert_xg(self):
+        """The layer input in the gradient format (operand of enc.0's tensor-core dW, needed in the backward
+        pass only): the plan runs it on the side stream once the stem has produced the input."""
+        if self.train and self._own_xg:
+            ops.convert16(self.x, self.x_g)
+        self.xg_converted = True
 
     def backward(self, side=None):
         e, d = self.names
@@ -769,9 +785,12 @@ class GhndPlan(object):
             side.fork()
             side.run(self.s_l1.prepack)
             packed = side.mark()
+            side.run(self.s_stem.convert_image)  # bf16 copy of the packed image: off the backward tail
             if self.stem2 is not None:
                 self.stem2.forward()  # both conv1's; the two pools + layer1's then run side by side
                 side.fork()
+                if self.stem2.fused:  # the student's pooled output exists: its bf16 copy leaves the main chain
+                    side.run(self.s_l1.convert_xg)
             if os.environ.get("GHND_TEACHER_SIDE", "1") != "0":
                 side.run(self._teacher_forward)
             else:
