@@ -607,7 +607,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], PAIR ? 2 * kEpiThreads : kEpiThreads);  // pair: both CTAs' epilogues
+      mbar_init(&tempty_bar[i], PAIR ? 2 * (kEpiThreads / 32) : kEpiThreads);  // pair: both CTAs' epilogues
     }
     for (int i = 0; i < kMaxRing; ++i) {
       mbar_init(&ifull_bar[i], 1);
@@ -1053,8 +1053,12 @@ __global__ void __launch_bounds__(kConvThreads, 1)
       tc_fence_after();
       if (c_last < 0) {  // nothing to read from this accumulator: release our share right away
         tc_fence_before();
-        if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[buf]), 0u));  // the leader's barrier
-          else mbar_arrive(&tempty_bar[buf]);
+        if (PAIR) {  // one REMOTE arrival per warp on the leader's barrier (256 per tile and CTA cost more than
+          __syncwarp();  // the epilogue of a short tile)
+          if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[buf]), 0u));
+        } else {
+          mbar_arrive(&tempty_bar[buf]);
+        }
       }
       const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * p.block_n);
       for (int c = c_first; c < n_chunks; c += 2) {
@@ -1067,8 +1071,12 @@ __global__ void __launch_bounds__(kConvThreads, 1)
         tmem_ld_wait();
         if (c == c_last) {  // accumulator fully read by this thread: hand TMEM back to the MMA warp
           tc_fence_before();
-          if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[buf]), 0u));  // the leader's barrier
-          else mbar_arrive(&tempty_bar[buf]);
+          if (PAIR) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[buf]), 0u));
+          } else {
+            mbar_arrive(&tempty_bar[buf]);
+          }
         }
         const int ch = n_tile * p.block_n + c * 64;
         if (EPI != 0) {
