@@ -304,6 +304,12 @@ __device__ __forceinline__ void umma_unit_2sm(uint32_t d_tmem, uint32_t a_lo, ui
         : "memory");
   }
 }
+// One barrier arrival per WARP: every lane has done its part (and its fences) before the __syncwarp, lane 0 arrives.
+// (Per-thread arrivals were 128-256 shared-memory atomics on one word per chunk / tile.)
+__device__ __forceinline__ void mbar_arrive_warp(uint64_t* bar, int lane) {
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
+}
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -607,11 +613,11 @@ __global__ void __launch_bounds__(kConvThreads, 1)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], PAIR ? 2 * (kEpiThreads / 32) : kEpiThreads);  // pair: both CTAs' epilogues
+      mbar_init(&tempty_bar[i], PAIR ? 2 * (kEpiThreads / 32) : kEpiThreads / 32);  // pair: both CTAs' epilogues
     }
     for (int i = 0; i < kMaxRing; ++i) {
       mbar_init(&ifull_bar[i], 1);
-      mbar_init(&iempty_bar[i], kEpiGroupThreads);
+      mbar_init(&iempty_bar[i], kEpiGroupThreads / 32);
     }
     mbar_init(wfull_bar, 1);
     for (int i = 0; i < kMaxASlots; ++i) {
@@ -1057,7 +1063,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
           __syncwarp();  // the epilogue of a short tile)
           if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[buf]), 0u));
         } else {
-          mbar_arrive(&tempty_bar[buf]);
+          mbar_arrive_warp(&tempty_bar[buf], lane);
         }
       }
       const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * p.block_n);
@@ -1075,7 +1081,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[buf]), 0u));
           } else {
-            mbar_arrive(&tempty_bar[buf]);
+            mbar_arrive_warp(&tempty_bar[buf], lane);
           }
         }
         const int ch = n_tile * p.block_n + c * 64;
@@ -1103,7 +1109,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
             // rows in the "+res" 1x1 convs, only when another kernel shared the GPU: graph replay with
             // the side stream, scripts/debug/race_hunt.py).
             fence_proxy_async();
-            mbar_arrive(&iempty_bar[slot]);  // operand buffer consumed
+            mbar_arrive_warp(&iempty_bar[slot], lane);  // operand buffer consumed
           }
           uint8_t* o_base = o_base0;
           if (p.epi_bufs == 2) {
@@ -1163,7 +1169,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
         const bool late_release = STATS && p.stats_mode == 1;
         if (n_in > 0 && !late_release) {
           fence_proxy_async();  // generic-proxy reads before the async-proxy refill (see the packed path)
-          mbar_arrive(&iempty_bar[slot]);
+          mbar_arrive_warp(&iempty_bar[slot], lane);
         }
         // ---- stage the 64-channel rows and store them with one TMA tensor store ----
         // the store that last used this staging tile has finished reading it
@@ -1213,7 +1219,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
             // bf16 gradient out, f16 activation operand (the only combination the plans accept)
             epi_stats2_rows<GHND_BF16, GHND_F16>(o_base, m_base, quarter, lane, valid, wstat, ch, p.cout);
             fence_proxy_async();
-            mbar_arrive(&iempty_bar[slot]);  // now the operand buffer may be refilled
+            mbar_arrive_warp(&iempty_bar[slot], lane);  // now the operand buffer may be refilled
           } else if (p.out_fmt == GHND_F16) {
             epi_stats_rows<GHND_F16>(o_base, quarter, lane, valid, wstat, ch, p.cout);
           } else {

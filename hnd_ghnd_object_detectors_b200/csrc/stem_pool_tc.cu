@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(kSpThreads, 1)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], kSpEpiThreads);
+      mbar_init(&tempty[i], kSpEpiThreads / 32);  // one arrival per epilogue warp
     }
     mbar_init(wfull, 1);
     fence_barrier_init();
@@ -290,7 +290,8 @@ __global__ void __launch_bounds__(kSpThreads, 1)
         }
       }
       tc_fence_before();
-      mbar_arrive(&tempty[buf]);  // TMEM set free for the MMAs of the job after next
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[buf]);  // TMEM set free for the MMAs of the job after next
       named_bar_sync(1, kSpEpiThreads);
       // ---- phase B: 3x3 s2 max-pool of the tile -> 7 x 14 pooled pixels ----
       uint4* yo = reinterpret_cast<uint4*>(p.y[m]);
