@@ -2000,6 +2000,64 @@ int ghnd_conv_plan_create(const ghnd_conv_desc_t* d, ghnd_conv_plan_t** out) {
       }
     }
   }
+  // Stride-2 dgrad: the parity-class launches run side by side (pdl_late_wait), but each one asked for every SM,
+  // so the later ones only trickled onto SMs the earlier ones had left and every CTA saw about one tile
+  // (prologue + pipeline fill + a bare epilogue per tile).  Give each launch a share of the SMs in proportion to its
+  // work (tiles x taps): all of them are resident at once and every CTA streams several tiles through the
+  // mainloop / epilogue overlap.  GHND_S2_SHARE=0: the old full-width grids.
+  static const bool s2_share = [] {
+    const char* e = getenv("GHND_S2_SHARE");
+    return e == nullptr || atoi(e) != 0;
+  }();
+  if (rc == GHND_OK && s2_share && d->kind == GHND_CONV_DGRAD && d->stride > 1 && plan->launches.size() > 1) {
+    bool late = true;
+    for (size_t i = 1; i < plan->launches.size(); ++i) late = late && plan->launches[i].p.pdl_late_wait;
+    double total = 0.0;
+    std::vector<double> work;
+    for (const ConvLaunch& L : plan->launches) {
+      work.push_back((double)(L.p.mc ? 2 : 1) * L.p.total_tiles * L.p.n_taps);
+      total += work.back();
+    }
+    const int sms = num_sms();
+    // (a launch with several waves of tiles already keeps its CTAs busy: 200x336 C128 measured 48.6 -> 49.7 us)
+    bool small = true;
+    for (const ConvLaunch& L : plan->launches) small = small && L.p.total_tiles * (L.p.mc ? 2 : 1) < 2 * sms;
+    if (late && small && total > 0.0) {
+      int used = 0;
+      std::vector<int> grid(work.size());
+      for (size_t i = 0; i < work.size(); ++i) {
+        const ConvLaunch& L = plan->launches[i];
+        const int unit = L.p.mc ? 2 : 1;
+        int g = (int)(sms * work[i] / total) / unit * unit;
+        if (g < unit) g = unit;
+        if (g > L.grid) g = L.grid;
+        grid[i] = g;
+        used += g;
+      }
+      // SMs left by the rounding go to the launches with the most work per CTA
+      for (bool grew = true; grew && used < sms;) {
+        grew = false;
+        size_t best = work.size();
+        double load = 0.0;
+        for (size_t i = 0; i < work.size(); ++i) {
+          const int unit = plan->launches[i].p.mc ? 2 : 1;
+          if (grid[i] + unit > plan->launches[i].grid || used + unit > sms) continue;
+          if (work[i] / grid[i] > load) {
+            load = work[i] / grid[i];
+            best = i;
+          }
+        }
+        if (best < work.size()) {
+          const int unit = plan->launches[best].p.mc ? 2 : 1;
+          grid[best] += unit;
+          used += unit;
+          grew = true;
+        }
+      }
+      if (used <= sms)
+        for (size_t i = 0; i < work.size(); ++i) plan->launches[i].grid = grid[i];
+    }
+  }
   if (rc == GHND_OK) rc = set_conv_attr();
   if (rc != GHND_OK) {
     delete plan;

@@ -18,6 +18,21 @@ static inline int grid_for(int64_t work_items, int threads, int per_sm = 8) {
   return (int)b;
 }
 
+// A CTA of a streaming kernel can only join an SM that is running a tensor-core kernel of the other stream when
+// both want the SAME L1 / shared-memory split (the split of a busy SM cannot change).  The GEMM kernels run with the
+// maximum shared-memory carve-out, so the streaming BatchNorm kernels ask for it too (they read through
+// ld.global.nc.L1::no_allocate and do not need the L1).  GHND_STREAM_CARVEOUT=0: the driver's choice.
+template <auto kernel>  // the kernel is a template argument: one `done` flag per instantiation
+static inline void share_sm_with_gemm() {
+  static const bool on = tune_int("GHND_STREAM_CARVEOUT", 1) != 0;
+  static bool done = false;  // one flag per kernel instantiation
+  if (on && !done) {
+    cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         (int)cudaSharedmemCarveoutMaxShared);
+    done = true;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // NCHW fp32 <-> NHWC 16-bit (module boundary only; 32x32 smem transpose)
 // ------------------------------------------------------------------------------------------------
@@ -744,6 +759,89 @@ __global__ void __launch_bounds__(256)
   for (; i < nvec; i += stride) one(ld_stream(x + i), i);
 }
 
+// bn_apply_fast_kernel in the library-kernel shape (see bn_bwd_apply_light_kernel): 128-thread CTAs, 1024 vectors
+// each; the finalize prologue (fp64, one or two channels per thread) runs in every CTA, block 0 publishes.
+template <int XF, int YF, int Y2F, bool RELU>
+__global__ void __launch_bounds__(128, 8)
+    bn_apply_light_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, uint4* __restrict__ y2,
+                          int64_t nvec, int C8, const float* __restrict__ scale_shift, const BnFin fin) {
+  constexpr int U = 4, ROUNDS = 2;
+  const int C = C8 * 8;  // <= 256 (host)
+  __shared__ __align__(16) float s_ss[2][256];
+  const bool publish = blockIdx.x == 0;
+  if (fin.sums != nullptr) {
+    if (publish && threadIdx.x == 0 && fin.nbt != nullptr) *fin.nbt += 1;
+    for (int c = threadIdx.x; c < C; c += 128) {
+      const double mean = fin.sums[c] / fin.count;
+      double var = fin.sums[C + c] / fin.count - mean * mean;  // biased
+      if (var < 0.0) var = 0.0;
+      const float invstd = (float)(1.0 / sqrt(var + (double)fin.eps));
+      const float g = fin.gamma ? __ldg(fin.gamma + c) : 1.f, b = fin.beta ? __ldg(fin.beta + c) : 0.f;
+      const float scv = g * invstd, shv = b - (float)mean * scv;
+      s_ss[0][c] = scv;
+      s_ss[1][c] = shv;
+      if (publish) {
+        fin.scale_shift_out[c] = scv;
+        fin.scale_shift_out[C + c] = shv;
+        fin.mean_invstd_out[c] = (float)mean;
+        fin.mean_invstd_out[C + c] = invstd;
+        if (fin.running_mean != nullptr) {
+          const double unbiased = fin.count > 1.0 ? var * fin.count / (fin.count - 1.0) : var;
+          fin.running_mean[c] = (1.f - fin.momentum) * fin.running_mean[c] + fin.momentum * (float)mean;
+          fin.running_var[c] = (1.f - fin.momentum) * fin.running_var[c] + fin.momentum * (float)unbiased;
+        }
+      }
+    }
+  } else {
+    for (int c = threadIdx.x; c < C; c += 128) {
+      s_ss[0][c] = __ldg(scale_shift + c);
+      s_ss[1][c] = __ldg(scale_shift + C + c);
+    }
+  }
+  __syncthreads();
+  const int cg = threadIdx.x % C8;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const float4 a = *reinterpret_cast<const float4*>(&s_ss[0][cg * 8 + 4 * h]);
+    const float4 b = *reinterpret_cast<const float4*>(&s_ss[1][cg * 8 + 4 * h]);
+    sc[4 * h] = a.x, sc[4 * h + 1] = a.y, sc[4 * h + 2] = a.z, sc[4 * h + 3] = a.w;
+    sh[4 * h] = b.x, sh[4 * h + 1] = b.y, sh[4 * h + 2] = b.z, sh[4 * h + 3] = b.w;
+  }
+  auto one = [&](const uint4 v, int64_t at) {
+    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+    uint32_t o[4], o2[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = unpack2_t<XF>(u[e]);
+      float a = fmaf(f.x, sc[2 * e], sh[2 * e]);
+      float b = fmaf(f.y, sc[2 * e + 1], sh[2 * e + 1]);
+      if (RELU) {
+        a = fmaxf(a, 0.f);
+        b = fmaxf(b, 0.f);
+      }
+      o[e] = pack2_t<YF>(a, b);
+      if (Y2F >= 0) o2[e] = pack2_t<(Y2F >= 0 ? Y2F : 0)>(a, b);
+    }
+    y[at] = make_uint4(o[0], o[1], o[2], o[3]);
+    if (Y2F >= 0) y2[at] = make_uint4(o2[0], o2[1], o2[2], o2[3]);
+  };
+  int64_t i = (int64_t)blockIdx.x * (128 * U * ROUNDS) + threadIdx.x;
+#pragma unroll 1
+  for (int r = 0; r < ROUNDS; ++r, i += 128 * U) {
+    if (i + (U - 1) * 128 < nvec) {
+      uint4 v[U];
+#pragma unroll
+      for (int k = 0; k < U; ++k) v[k] = ld_stream(x + i + k * 128);
+#pragma unroll
+      for (int k = 0; k < U; ++k) one(v[k], i + k * 128);
+    } else {
+      for (int k = 0; k < U; ++k)
+        if (i + k * 128 < nvec) one(ld_stream(x + i + k * 128), i + k * 128);
+    }
+  }
+}
+
 template <int XF, int GF, bool RELU>
 __global__ void __launch_bounds__(256)
     bn_bwd_apply_fast_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x,
@@ -816,6 +914,90 @@ __global__ void __launch_bounds__(256)
 }
 
 
+// The same arithmetic as bn_bwd_apply_fast_kernel in the shape of a library copy kernel: MANY short-lived 128-thread
+// CTAs (1024 vectors each, <= 64 registers) instead of a persistent grid.  scripts/debug/coresidency.py: next to the
+// dW GEMM of the other stream (one 192-thread CTA per SM holding ~200 KB of shared memory) torch's copy kernel is
+// absorbed completely (GEMM + copy take as long as the GEMM alone), while the persistent 256-thread / 80-register
+// CTAs of the fast kernel mostly wait for the GEMM to finish: the block scheduler places small CTAs wherever
+// registers are left and late CTAs of a persistent grid still own their static share of the tensor.  The
+// per-channel constants are computed once per CTA (one or two channels per thread) and shared through 4 KB of smem.
+template <int XF, int GF, bool RELU>
+__global__ void __launch_bounds__(128, 8)
+    bn_bwd_apply_light_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x,
+                              uint4* __restrict__ dx, int64_t nvec, int C8, float inv_count,
+                              const float* __restrict__ scale_shift,
+                              const float* __restrict__ mean_invstd,
+                              const double* __restrict__ sums, float* __restrict__ dgamma,
+                              float* __restrict__ dbeta, int sums_mode) {
+  constexpr int U = 4, ROUNDS = 2;
+  const int C = C8 * 8;  // <= 256 (host)
+  __shared__ __align__(16) float s_k[4][256];  // sc, sf, k1, k0
+  for (int c = threadIdx.x; c < C; c += 128) {
+    const float scv = __ldg(scale_shift + c), sfv = __ldg(scale_shift + C + c);
+    const float mu = __ldg(mean_invstd + c), is = __ldg(mean_invstd + C + c);
+    const double s1 = sums[c];
+    double s2 = sums[C + c];
+    if (sums_mode != 0) s2 = ((double)is / (double)scv) * (s2 - ((double)sfv + (double)mu * (double)scv) * s1);
+    if (blockIdx.x == 0) {  // parameter gradients are the two sums themselves
+      if (dbeta != nullptr) dbeta[c] = (float)s1;
+      if (dgamma != nullptr) dgamma[c] = (float)s2;
+    }
+    const float mg = (float)s1 * inv_count, mgx = (float)s2 * inv_count;
+    s_k[0][c] = scv;
+    s_k[1][c] = sfv;
+    s_k[2][c] = -scv * is * mgx;
+    s_k[3][c] = scv * (mu * is * mgx - mg);
+  }
+  __syncthreads();
+  const int cg = threadIdx.x % C8;
+  float sc[8], sf[8], k1[8], k0[8];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const float4 a = *reinterpret_cast<const float4*>(&s_k[0][cg * 8 + 4 * h]);
+    const float4 b = *reinterpret_cast<const float4*>(&s_k[1][cg * 8 + 4 * h]);
+    const float4 c = *reinterpret_cast<const float4*>(&s_k[2][cg * 8 + 4 * h]);
+    const float4 d = *reinterpret_cast<const float4*>(&s_k[3][cg * 8 + 4 * h]);
+    sc[4 * h] = a.x, sc[4 * h + 1] = a.y, sc[4 * h + 2] = a.z, sc[4 * h + 3] = a.w;
+    sf[4 * h] = b.x, sf[4 * h + 1] = b.y, sf[4 * h + 2] = b.z, sf[4 * h + 3] = b.w;
+    k1[4 * h] = c.x, k1[4 * h + 1] = c.y, k1[4 * h + 2] = c.z, k1[4 * h + 3] = c.w;
+    k0[4 * h] = d.x, k0[4 * h + 1] = d.y, k0[4 * h + 2] = d.z, k0[4 * h + 3] = d.w;
+  }
+  auto one = [&](const uint4 xv, const uint4 dv, int64_t at) {
+    const uint32_t xu[4] = {xv.x, xv.y, xv.z, xv.w}, du[4] = {dv.x, dv.y, dv.z, dv.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = unpack2_t<XF>(xu[e]);
+      float2 g = unpack2_t<GF>(du[e]);
+      if (RELU) {
+        if (!(fmaf(f.x, sc[2 * e], sf[2 * e]) > 0.f)) g.x = 0.f;
+        if (!(fmaf(f.y, sc[2 * e + 1], sf[2 * e + 1]) > 0.f)) g.y = 0.f;
+      }
+      const float r0 = fmaf(sc[2 * e], g.x, fmaf(f.x, k1[2 * e], k0[2 * e]));
+      const float r1 = fmaf(sc[2 * e + 1], g.y, fmaf(f.y, k1[2 * e + 1], k0[2 * e + 1]));
+      o[e] = pack2_t<GF>(r0, r1);
+    }
+    dx[at] = make_uint4(o[0], o[1], o[2], o[3]);
+  };
+  int64_t i = (int64_t)blockIdx.x * (128 * U * ROUNDS) + threadIdx.x;
+#pragma unroll 1
+  for (int r = 0; r < ROUNDS; ++r, i += 128 * U) {
+    if (i + (U - 1) * 128 < nvec) {
+      uint4 xv[U], dv[U];
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        xv[k] = ld_stream(x + i + k * 128);
+        dv[k] = ld_stream(dy + i + k * 128);
+      }
+#pragma unroll
+      for (int k = 0; k < U; ++k) one(xv[k], dv[k], i + k * 128);
+    } else {
+      for (int k = 0; k < U; ++k)
+        if (i + k * 128 < nvec) one(ld_stream(x + i + k * 128), ld_stream(dy + i + k * 128), i + k * 128);
+    }
+  }
+}
+
 // backward reduction: sums[c] += sum g', sums[C+c] += sum g'*xhat
 template <int XF, int GF, bool RELU>
 __global__ void __launch_bounds__(256)
@@ -868,6 +1050,83 @@ __global__ void __launch_bounds__(256)
   block_channel_fold(a, b, C8, sh, sums);
 }
 
+// bn_bwd_reduce in the library-kernel shape (see bn_bwd_apply_light_kernel): 128-thread CTAs that each fold
+// 128 * 2 * rounds vectors and leave one fp64 atomic per channel sum.  (f - mu) is accumulated and invstd applied once
+// at the end, which keeps the per-thread constants to sc / sf / mu.  sh: [4 warps][2*C] floats.
+template <int XF, int GF, bool RELU>
+__global__ void __launch_bounds__(128, 7)
+    bn_bwd_reduce_light_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy, int64_t nvec,
+                               int C8, int rounds, const float* __restrict__ scale_shift,
+                               const float* __restrict__ mean_invstd, double* __restrict__ sums) {
+  constexpr int U = 2;
+  extern __shared__ float sh[];
+  const int C = C8 * 8;
+  const int cg = threadIdx.x % C8;
+  float sc[8], sf[8], mu[8], a[8], b[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = cg * 8 + j;
+    if (RELU) {
+      sc[j] = __ldg(scale_shift + c);
+      sf[j] = __ldg(scale_shift + C + c);
+    }
+    mu[j] = __ldg(mean_invstd + c);
+    a[j] = b[j] = 0.f;
+  }
+  auto one = [&](const uint4 xv, const uint4 dv) {
+    const uint32_t xu[4] = {xv.x, xv.y, xv.z, xv.w}, du[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = unpack2_t<XF>(xu[e]);
+      float2 g = unpack2_t<GF>(du[e]);
+      if (RELU) {
+        if (!(fmaf(f.x, sc[2 * e], sf[2 * e]) > 0.f)) g.x = 0.f;
+        if (!(fmaf(f.y, sc[2 * e + 1], sf[2 * e + 1]) > 0.f)) g.y = 0.f;
+      }
+      a[2 * e] += g.x;
+      a[2 * e + 1] += g.y;
+      b[2 * e] = fmaf(g.x, f.x - mu[2 * e], b[2 * e]);
+      b[2 * e + 1] = fmaf(g.y, f.y - mu[2 * e + 1], b[2 * e + 1]);
+    }
+  };
+  int64_t i = (int64_t)blockIdx.x * (128 * U) * rounds + threadIdx.x;
+#pragma unroll 1
+  for (int r = 0; r < rounds; ++r, i += 128 * U) {
+    if (i + 128 < nvec) {
+      const uint4 x0 = ld_stream(x + i), d0 = ld_stream(dy + i);
+      const uint4 x1 = ld_stream(x + i + 128), d1 = ld_stream(dy + i + 128);
+      one(x0, d0);
+      one(x1, d1);
+    } else if (i < nvec) {
+      one(ld_stream(x + i), ld_stream(dy + i));
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) b[j] *= __ldg(mean_invstd + C + cg * 8 + j);
+  // fold: lanes of one channel group, then the four warp rows, then one fp64 atomic per sum
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int o = C8; o < 32; o <<= 1) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      a[j] += __shfl_xor_sync(0xffffffffu, a[j], o);
+      b[j] += __shfl_xor_sync(0xffffffffu, b[j], o);
+    }
+  }
+  float* row = sh + (size_t)warp * 2 * C;
+  if (lane < C8) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      row[cg * 8 + j] = a[j];
+      row[C + cg * 8 + j] = b[j];
+    }
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < 2 * C; k += 128) {
+    const float t = (sh[k] + sh[2 * C + k]) + (sh[4 * C + k] + sh[6 * C + k]);
+    atomicAdd(&sums[k], (double)t);
+  }
+}
+
 static size_t bn_reduce_smem(int C) {  // bn_reduce_nhwc_kernel: [8 warps][2*C] on its fold path
   const int c8 = C / 8;
   return (size_t)((c8 <= 32 && (c8 & (c8 - 1)) == 0) ? 16 : 2) * C * sizeof(float);
@@ -877,6 +1136,17 @@ static bool fast_c8(int C) { return C >= 8 && C % 8 == 0 && C / 8 <= 256 && 256 
 template <int XF, int YF, int Y2F>
 static void launch_bn_apply_fast3(const uint4* x, uint4* y, uint4* y2, int64_t nvec, int C8,
                                   const float* ss, int relu, int grid, const BnFin& fin, cudaStream_t st) {
+  static const int light = tune_int("GHND_BN_LIGHT", 3);  // A/B switch: 0 = the persistent kernels
+  if ((light & 4) && C8 <= 32 && 128 % C8 == 0) {
+    const unsigned blocks = (unsigned)((nvec + 1023) / 1024);
+    share_sm_with_gemm<bn_apply_light_kernel<XF, YF, Y2F, true>>();
+    share_sm_with_gemm<bn_apply_light_kernel<XF, YF, Y2F, false>>();
+    if (relu) bn_apply_light_kernel<XF, YF, Y2F, true><<<blocks, 128, 0, st>>>(x, y, y2, nvec, C8, ss, fin);
+    else bn_apply_light_kernel<XF, YF, Y2F, false><<<blocks, 128, 0, st>>>(x, y, y2, nvec, C8, ss, fin);
+    return;
+  }
+  share_sm_with_gemm<bn_apply_fast_kernel<XF, YF, Y2F, true>>();
+  share_sm_with_gemm<bn_apply_fast_kernel<XF, YF, Y2F, false>>();
   if (relu) bn_apply_fast_kernel<XF, YF, Y2F, true><<<grid, 256, 0, st>>>(x, y, y2, nvec, C8, ss, fin);
   else bn_apply_fast_kernel<XF, YF, Y2F, false><<<grid, 256, 0, st>>>(x, y, y2, nvec, C8, ss, fin);
 }
@@ -890,7 +1160,7 @@ static void launch_bn_apply_fast2(int y2_fmt, const uint4* x, uint4* y, uint4* y
 static void launch_bn_apply_fast(int x_fmt, int y_fmt, int y2_fmt, const uint4* x, uint4* y, uint4* y2,
                                  int64_t nvec, int C8, const float* ss, int relu, const BnFin& fin,
                                  cudaStream_t st) {
-  const int grid = grid_for(nvec, 256 * 4, 8);
+  const int grid = grid_for(nvec, 256 * 4, tune_int("GHND_BNAPP_PER_SM", 8));
   if (x_fmt == GHND_F16) {
     if (y_fmt == GHND_F16) launch_bn_apply_fast2<GHND_F16, GHND_F16>(y2_fmt, x, y, y2, nvec, C8, ss, relu, grid, fin, st);
     else launch_bn_apply_fast2<GHND_F16, GHND_BF16>(y2_fmt, x, y, y2, nvec, C8, ss, relu, grid, fin, st);
@@ -1347,7 +1617,27 @@ int ghnd_bn_bwd_reduce(const void* dy, int dy_fmt, const void* x, int x_fmt, int
       const int64_t nvec = npix * (C / 8);
       // 3 CTAs/SM x 8 warps x 8 x 16-byte loads in flight; fewer CTAs also means fewer same-address
       // fp64 atomics in the tail (2*C per CTA)
+      static const int light = tune_int("GHND_BN_LIGHT", 3);  // A/B switch: 0 = the persistent kernels
+      if (light & 2) {
+        // ~8 CTAs per SM over the whole launch: enough of them to balance, few enough atomics (2*C per CTA)
+        int rounds = (int)(nvec / ((int64_t)256 * 8 * num_sms()));
+        rounds = rounds < 4 ? 4 : (rounds > 32 ? 32 : rounds);
+        const int64_t blocks = (nvec + (int64_t)256 * rounds - 1) / ((int64_t)256 * rounds);
+        const size_t smem = (size_t)8 * C * sizeof(float);
+        share_sm_with_gemm<bn_bwd_reduce_light_kernel<GHND_F16, GHND_BF16, true>>();
+        share_sm_with_gemm<bn_bwd_reduce_light_kernel<GHND_F16, GHND_BF16, false>>();
+        if (relu)
+          bn_bwd_reduce_light_kernel<GHND_F16, GHND_BF16, true><<<(unsigned)blocks, 128, smem, st>>>(
+              (const uint4*)x, (const uint4*)dy, nvec, C / 8, rounds, scale_shift, mean_invstd, sums);
+        else
+          bn_bwd_reduce_light_kernel<GHND_F16, GHND_BF16, false><<<(unsigned)blocks, 128, smem, st>>>(
+              (const uint4*)x, (const uint4*)dy, nvec, C / 8, rounds, scale_shift, mean_invstd, sums);
+        GHND_LAUNCH_CHECK("bn_bwd_reduce_light_kernel");
+        return GHND_OK;
+      }
       const int grid = grid_for(nvec, 256 * 8, tune_int("GHND_BNRED_PER_SM", 3));
+      share_sm_with_gemm<bn_bwd_reduce_fast_kernel<GHND_F16, GHND_BF16, true>>();
+      share_sm_with_gemm<bn_bwd_reduce_fast_kernel<GHND_F16, GHND_BF16, false>>();
       if (relu)
         bn_bwd_reduce_fast_kernel<GHND_F16, GHND_BF16, true><<<grid, 256, 16 * C * sizeof(float), st>>>(
             (const uint4*)x, (const uint4*)dy, nvec, C / 8, scale_shift, mean_invstd, sums);
@@ -1386,7 +1676,25 @@ static int bn_bwd_apply_impl(const void* dy, int dy_fmt, const void* x, int x_fm
     GHND_CHECK_ARG(fmt16(dy_fmt) && fmt16(x_fmt) && fmt16(dx_fmt), "bn_bwd_apply: bad format");
     const int64_t nvec = (int64_t)N * hw * (C / 8);
     if (x_fmt == GHND_F16 && dy_fmt == GHND_BF16 && dx_fmt == GHND_BF16) {  // engine's combination
-      const int grid = grid_for(nvec, 256 * 4, 6);
+      static const int light = tune_int("GHND_BN_LIGHT", 3);  // A/B switch: 0 = the persistent kernels
+      if ((light & 1) && C <= 256 && 128 % (C / 8) == 0) {
+        const int64_t blocks = (nvec + 1023) / 1024;
+        share_sm_with_gemm<bn_bwd_apply_light_kernel<GHND_F16, GHND_BF16, true>>();
+        share_sm_with_gemm<bn_bwd_apply_light_kernel<GHND_F16, GHND_BF16, false>>();
+        if (relu)
+          bn_bwd_apply_light_kernel<GHND_F16, GHND_BF16, true><<<(unsigned)blocks, 128, 0, st>>>(
+              (const uint4*)dy, (const uint4*)x, (uint4*)dx, nvec, C / 8, (float)inv_count, scale_shift,
+              mean_invstd, sums, dgamma, dbeta, sums_mode);
+        else
+          bn_bwd_apply_light_kernel<GHND_F16, GHND_BF16, false><<<(unsigned)blocks, 128, 0, st>>>(
+              (const uint4*)dy, (const uint4*)x, (uint4*)dx, nvec, C / 8, (float)inv_count, scale_shift,
+              mean_invstd, sums, dgamma, dbeta, sums_mode);
+        GHND_LAUNCH_CHECK("bn_bwd_apply_light_kernel");
+        return GHND_OK;
+      }
+      const int grid = grid_for(nvec, 256 * 4, tune_int("GHND_BNBWD_PER_SM", 6));
+      share_sm_with_gemm<bn_bwd_apply_fast_kernel<GHND_F16, GHND_BF16, true>>();
+      share_sm_with_gemm<bn_bwd_apply_fast_kernel<GHND_F16, GHND_BF16, false>>();
       if (relu)
         bn_bwd_apply_fast_kernel<GHND_F16, GHND_BF16, true><<<grid, 256, 0, st>>>(
             (const uint4*)dy, (const uint4*)x, (uint4*)dx, nvec, C / 8, (float)inv_count, scale_shift,

@@ -87,22 +87,18 @@ __global__ void __launch_bounds__(kSseThreads)
 __global__ void __launch_bounds__(256)
     sse_finalize_kernel(const float* __restrict__ partial, int blocks_per_level, SseArgs a,
                         float* __restrict__ loss_out) {
-  __shared__ double red[8];
+  // one warp per level (levels run side by side; the block used to walk them one after the other with two
+  // block barriers each: 9.9 us on the critical chain between the loss kernel and the first data gradient)
   __shared__ double lvl_sum[GHND_SSE_MAX_LEVELS];
-  for (int lvl = 0; lvl < a.n_levels; ++lvl) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int lvl = warp; lvl < a.n_levels; lvl += 8) {
     double acc = 0.0;
-    for (int i = threadIdx.x; i < blocks_per_level; i += blockDim.x)
+    for (int i = lane; i < blocks_per_level; i += 32)
       acc += (double)partial[(size_t)lvl * blocks_per_level + i];
     acc = warp_sum(acc);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double tot = 0.0;
-      for (int w = 0; w < 8; ++w) tot += red[w];
-      lvl_sum[lvl] = tot * (double)a.factor[lvl];
-    }
-    __syncthreads();
+    if (lane == 0) lvl_sum[lvl] = acc * (double)a.factor[lvl];
   }
+  __syncthreads();
   if (threadIdx.x == 0) {
     double tot = 0.0;
     for (int lvl = 0; lvl < a.n_levels; ++lvl) {

@@ -313,7 +313,9 @@ int ghnd_wgrad_plan_create(const ghnd_wgrad_desc_t* d, ghnd_wgrad_plan_t** out) 
   const int row_bytes = p.row_boxes * (p.rows_is_dy ? kWgDyBox : p.x_box_bytes);
   const int col_bytes = p.col_boxes * (p.rows_is_dy ? p.x_box_bytes : kWgDyBox);
   p.stage_bytes = row_bytes + col_bytes;
-  int stages = (200 * 1024) / p.stage_bytes;
+  int smem_kb = 200;
+  if (const char* e = getenv("GHND_WGRAD_SMEM_KB")) smem_kb = atoi(e);
+  int stages = (smem_kb * 1024) / p.stage_bytes;
   if (stages > 12) stages = 12;
   p.n_stages = stages;
   {
@@ -354,6 +356,10 @@ int ghnd_wgrad_plan_create(const ghnd_wgrad_desc_t* d, ghnd_wgrad_plan_t** out) 
       delete plan;
       return cuda_fail(e, "cudaFuncSetAttribute(wgrad_tc_kernel)");
     }
+    // keep the maximum shared-memory split whatever the ring needs, so that streaming kernels of the other
+    // stream (which ask for the same split) can join the SMs this kernel runs on
+    cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         (int)cudaSharedmemCarveoutMaxShared);
     attr_set = true;
   }
   *out = plan;

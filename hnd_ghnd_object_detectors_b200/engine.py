@@ -30,6 +30,8 @@ import os
 # run concurrently with the persistent tensor-core kernels of the second stream -- and the fused
 # form divides by gamma (undefined for a channel whose gamma is exactly 0).
 FUSE_BN_REDUCE = os.environ.get("GHND_FUSE_BN_REDUCE", "0") == "1"
+# A/B switch: the bottleneck-side dW launches on the side stream (default) or in the data-gradient chain
+NARROW_DW_SIDE = os.environ.get("GHND_NARROW_DW_SIDE", "1") != "0"
 
 LEVELS = ("layer1", "layer2", "layer3", "layer4")
 PLANES = {"layer1": 64, "layer2": 128, "layer3": 256, "layer4": 512}
@@ -617,8 +619,22 @@ class StudentLayer1Runner(object):
                          fused_sums=self.bn3_reduce_fused)
         # dec2 (narrow-in conv on relu(bn0(z)))
         bz = self.bnz
-        ops.wgrad_narrow(self.z, self.g_raw3, self.gr[d + "2.weight"], False, 2, 2, 0, pre=bz.scale_shift,
-                         pre_relu=True, ws=self.wws)
+        # the two bottleneck-side dW launches feed nothing on the data-gradient chain: like the wide dW GEMMs they
+        # run on the side stream (one after the other there, so they may share the workspace)
+        narrow_side = side if NARROW_DW_SIDE else None
+
+        def dw_dec2():
+            ops.wgrad_narrow(self.z, self.g_raw3, self.gr[d + "2.weight"], False, 2, 2, 0, pre=bz.scale_shift,
+                             pre_relu=True, ws=self.wws)
+
+        def dw_enc7():
+            ops.wgrad_narrow(self.g_z, self.e2.out, self.gr[e + "7.weight"], True, 2, 2, 1, ws=self.wws)
+
+        if narrow_side is not None:
+            narrow_side.fork()
+            narrow_side.run(dw_dec2)
+        else:
+            dw_dec2()
         ops.conv_narrow_out_dgrad(self.g_raw3, self.dec2.weight, 0, self.Hz, self.Wz, dx=self.g_zact,
                                   ws=self.nws)
         # BN dec[0] + ReLU on the planar bottleneck
@@ -626,7 +642,11 @@ class StudentLayer1Runner(object):
         ops.bn_bwd_apply(self.g_zact, self.z, self.g_z, bz.bn.weight, bz.scale_shift, bz.mean_invstd, True,
                          bz.sums, self.gr[d + "0.weight"], self.gr[d + "0.bias"], planar=True)
         # enc7 (narrow-out conv)
-        ops.wgrad_narrow(self.g_z, self.e2.out, self.gr[e + "7.weight"], True, 2, 2, 1, ws=self.wws)
+        if narrow_side is not None:
+            narrow_side.fork()
+            narrow_side.run(dw_enc7)
+        else:
+            dw_enc7()
         ops.conv_narrow_in(self.g_z, self.enc7.weight, 1, flip=True, y=self.g_e2out, ws=self.nws)
         self.e2.backward(side)
         self.e1.backward(side)

@@ -1,6 +1,6 @@
 #!/bin/bash
 # same-box A/B of an environment switch: ab_env.sh "VAR=a" "VAR=b" [reps]   (bench.py, device-resident step)
-B="python bench.py --steps 40 --warmup 5 --no-cpu-baseline --no-encode --no-config4 --no-stock-torch"
+B="python bench.py --steps ${STEPS:-40} --warmup 5 --no-cpu-baseline --no-encode --no-config4 --no-stock-torch"
 mkdir -p gpurun_out
 for rep in $(seq 1 ${3:-2}); do
   for v in "$1" "$2"; do

@@ -106,3 +106,13 @@ for g, at in gaps[1:9]:
     prev = max((e for e in ev if e["ts"] + e["dur"] <= at + 0.01), key=lambda e: e["ts"] + e["dur"])
     nxt = min((e for e in ev if e["ts"] >= at + g - 0.01), key=lambda e: e["ts"])
     print("  gap %.1f us between %s and %s" % (g, prev["name"][:50], nxt["name"][:50]))
+# chronological list of the LAST replay (stream, start offset, duration): the critical chain can be read off it
+per = len(ev) // REPS
+last = ev[-per:]
+base = last[0]["ts"]
+with open("gpurun_out/graph_timeline.txt", "w") as f:
+    for e in last:
+        a = e.get("args", {})
+        n = e["name"].split("(")[0].replace("void ", "").replace("ghnd::", "")
+        f.write("%9.1f %8.1f  s%-3s %s\n" % (e["ts"] - base, e["dur"], a.get("stream", "?"), n[:70]))
+print("timeline of the last replay: gpurun_out/graph_timeline.txt (%d events)" % per)
