@@ -18,10 +18,11 @@ static inline int grid_for(int64_t work_items, int threads, int per_sm = 8) {
   return (int)b;
 }
 
-// A CTA of a streaming kernel can only join an SM that is running a tensor-core kernel of the other stream when
-// both want the SAME L1 / shared-memory split (the split of a busy SM cannot change).  The GEMM kernels run with the
-// maximum shared-memory carve-out, so the streaming BatchNorm kernels ask for it too (they read through
-// ld.global.nc.L1::no_allocate and do not need the L1).  GHND_STREAM_CARVEOUT=0: the driver's choice.
+// The streaming BatchNorm kernels ask for the same (maximum) shared-memory split as the tensor-core kernels they run
+// next to, so that a CTA never has to wait for an SM to change its L1 / shared-memory split.  Measured neutral on the
+// B200 (scripts/debug/coresidency.py: 165 vs 169 us for dW GEMM + bn_bwd_reduce with and without) -- what decides
+// whether a streaming kernel shares the SMs with a GEMM is the size of its CTAs (bn_bwd_apply_light_kernel below).
+// GHND_STREAM_CARVEOUT=0: the driver's choice.
 template <auto kernel>  // the kernel is a template argument: one `done` flag per instantiation
 static inline void share_sm_with_gemm() {
   static const bool on = tune_int("GHND_STREAM_CARVEOUT", 1) != 0;
