@@ -1051,18 +1051,26 @@ __global__ void __launch_bounds__(256)
   block_channel_fold(a, b, C8, sh, sums);
 }
 
-// bn_bwd_reduce in the library-kernel shape (see bn_bwd_apply_light_kernel): 128-thread CTAs that each fold
-// 128 * 2 * rounds vectors and leave one fp64 atomic per channel sum.  (f - mu) is accumulated and invstd applied once
-// at the end, which keeps the per-thread constants to sc / sf / mu.  sh: [4 warps][2*C] floats.
+// bn_bwd_reduce for sharing the SMs with a GEMM: 128-thread CTAs that CLAIM chunks of 2048 vectors from a global
+// counter until the tensor is exhausted.  Whatever subset of the grid is resident does all the work -- alone that is
+// the whole grid (5 CTAs per SM, 8 vectors in flight per thread), next to the dW GEMM of the other stream the two or
+// three CTAs per SM that fit beside it; CTAs that start late find nothing left and leave (a static share per CTA made
+// the kernel wait for the GEMM: 143 us against 52 alone).  (f - mu) is accumulated and invstd applied once at the end,
+// which keeps the per-thread constants to sc / sf / mu.  The next claim is in flight while a chunk is folded.
+// ctr[0] = next chunk, ctr[1] = CTAs done; the last CTA to leave resets both for the next launch that uses the slot.
+// sh: [4 warps][2*C] floats.
+static constexpr int kRedChunk = 2048;  // vectors per claim: 128 threads x 4 x 4
 template <int XF, int GF, bool RELU>
-__global__ void __launch_bounds__(128, 6)
+__global__ void __launch_bounds__(128, 5)
     bn_bwd_reduce_light_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy, int64_t nvec,
-                               int C8, int rounds, const float* __restrict__ scale_shift,
+                               int C8, unsigned n_chunks, unsigned* __restrict__ ctr,
+                               const float* __restrict__ scale_shift,
                                const float* __restrict__ mean_invstd, double* __restrict__ sums) {
-  constexpr int U = 2;
   extern __shared__ float sh[];
+  __shared__ unsigned s_claim[2];
   const int C = C8 * 8;
   const int cg = threadIdx.x % C8;
+  if (threadIdx.x == 0) s_claim[0] = atomicAdd(&ctr[0], 1u);
   float sc[8], sf[8], mu[8], a[8], b[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -1090,57 +1098,80 @@ __global__ void __launch_bounds__(128, 6)
       b[2 * e + 1] = fmaf(g.y, f.y - mu[2 * e + 1], b[2 * e + 1]);
     }
   };
-  // the next round's four vectors are in flight while this round's are folded (a CTA alone on its SM partition
-  // otherwise exposes one load round trip per round: 3.7 TB/s for the whole grid)
-  int64_t i = (int64_t)blockIdx.x * (128 * U) * rounds + threadIdx.x;
-  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);  // g = 0 contributes nothing
-  auto fetch = [&](int64_t at, uint4& xa, uint4& da, uint4& xb, uint4& db) {
-    xa = da = xb = db = zero;
-    if (at < nvec) {
-      xa = ld_stream(x + at);
-      da = ld_stream(dy + at);
-    }
-    if (at + 128 < nvec) {
-      xb = ld_stream(x + at + 128);
-      db = ld_stream(dy + at + 128);
-    }
-  };
-  uint4 x0, d0, x1, d1;
-  fetch(i, x0, d0, x1, d1);
-#pragma unroll 1
-  for (int r = 0; r < rounds; ++r) {
-    i += 128 * U;
-    uint4 nx0, nd0, nx1, nd1;
-    if (r + 1 < rounds) fetch(i, nx0, nd0, nx1, nd1);
-    else nx0 = nd0 = nx1 = nd1 = zero;
-    one(x0, d0);
-    one(x1, d1);
-    x0 = nx0, d0 = nd0, x1 = nx1, d1 = nd1;
-  }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) b[j] *= __ldg(mean_invstd + C + cg * 8 + j);
-  // fold: lanes of one channel group, then the four warp rows, then one fp64 atomic per sum
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int o = C8; o < 32; o <<= 1) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      a[j] += __shfl_xor_sync(0xffffffffu, a[j], o);
-      b[j] += __shfl_xor_sync(0xffffffffu, b[j], o);
-    }
-  }
-  float* row = sh + (size_t)warp * 2 * C;
-  if (lane < C8) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      row[cg * 8 + j] = a[j];
-      row[C + cg * 8 + j] = b[j];
-    }
-  }
   __syncthreads();
-  for (int k = threadIdx.x; k < 2 * C; k += 128) {
-    const float t = (sh[k] + sh[2 * C + k]) + (sh[4 * C + k] + sh[6 * C + k]);
-    atomicAdd(&sums[k], (double)t);
+  unsigned chunk = s_claim[0];
+  bool any = false;
+  int par = 1;
+  while (chunk < n_chunks) {
+    any = true;
+    if (threadIdx.x == 0) s_claim[par] = atomicAdd(&ctr[0], 1u);  // next claim, read after the barrier below
+    const int64_t base = (int64_t)chunk * kRedChunk + threadIdx.x;
+    if (base - threadIdx.x + kRedChunk <= nvec) {
+#pragma unroll 1
+      for (int r = 0; r < 4; ++r) {
+        const int64_t i = base + r * 512;
+        uint4 xv[4], dv[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          xv[k] = ld_stream(x + i + k * 128);
+          dv[k] = ld_stream(dy + i + k * 128);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) one(xv[k], dv[k]);
+      }
+    } else {
+      for (int64_t i = base; i < nvec; i += 128) one(ld_stream(x + i), ld_stream(dy + i));
+    }
+    __syncthreads();
+    chunk = s_claim[par];
+    par ^= 1;
   }
+  if (any) {  // uniform per CTA
+#pragma unroll
+    for (int j = 0; j < 8; ++j) b[j] *= __ldg(mean_invstd + C + cg * 8 + j);
+    // fold: lanes of one channel group, then the four warp rows, then one fp64 atomic per sum
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int o = C8; o < 32; o <<= 1) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        a[j] += __shfl_xor_sync(0xffffffffu, a[j], o);
+        b[j] += __shfl_xor_sync(0xffffffffu, b[j], o);
+      }
+    }
+    float* row = sh + (size_t)warp * 2 * C;
+    if (lane < C8) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        row[cg * 8 + j] = a[j];
+        row[C + cg * 8 + j] = b[j];
+      }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < 2 * C; k += 128) {
+      const float t = (sh[k] + sh[2 * C + k]) + (sh[4 * C + k] + sh[6 * C + k]);
+      atomicAdd(&sums[k], (double)t);
+    }
+  }
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&ctr[1], 1u) == gridDim.x - 1) {  // every CTA has made its last claim
+      ctr[0] = 0u;
+      ctr[1] = 0u;
+    }
+  }
+}
+// claim counters of the launches in flight: a launch takes the next slot (zero outside a launch)
+static unsigned* red_counter_slot() {
+  static unsigned* pool = nullptr;
+  static int next = 0;
+  constexpr int kSlots = 256;
+  if (pool == nullptr) {
+    if (cudaMalloc(&pool, kSlots * 2 * sizeof(unsigned)) != cudaSuccess) return nullptr;
+    cudaMemset(pool, 0, kSlots * 2 * sizeof(unsigned));
+  }
+  unsigned* p = pool + 2 * next;
+  next = (next + 1) % kSlots;
+  return p;
 }
 
 static size_t bn_reduce_smem(int C) {  // bn_reduce_nhwc_kernel: [8 warps][2*C] on its fold path
@@ -1634,20 +1665,20 @@ int ghnd_bn_bwd_reduce(const void* dy, int dy_fmt, const void* x, int x_fmt, int
       // 3 CTAs/SM x 8 warps x 8 x 16-byte loads in flight; fewer CTAs also means fewer same-address
       // fp64 atomics in the tail (2*C per CTA)
       static const int light = tune_int("GHND_BN_LIGHT", 3);  // A/B switch: 0 = the persistent kernels
-      if (light & 2) {
-        // ~8 CTAs per SM over the whole launch: enough of them to balance, few enough atomics (2*C per CTA)
-        int rounds = (int)(nvec / ((int64_t)256 * 8 * num_sms()));
-        rounds = rounds < 4 ? 4 : (rounds > 32 ? 32 : rounds);
-        const int64_t blocks = (nvec + (int64_t)256 * rounds - 1) / ((int64_t)256 * rounds);
+      unsigned* ctr = (light & 2) ? red_counter_slot() : nullptr;
+      if (ctr != nullptr) {
+        const unsigned n_chunks = (unsigned)((nvec + kRedChunk - 1) / kRedChunk);
+        int64_t blocks = (int64_t)num_sms() * 5;
+        if (blocks > n_chunks) blocks = n_chunks;
         const size_t smem = (size_t)8 * C * sizeof(float);
         share_sm_with_gemm<bn_bwd_reduce_light_kernel<GHND_F16, GHND_BF16, true>>();
         share_sm_with_gemm<bn_bwd_reduce_light_kernel<GHND_F16, GHND_BF16, false>>();
         if (relu)
           bn_bwd_reduce_light_kernel<GHND_F16, GHND_BF16, true><<<(unsigned)blocks, 128, smem, st>>>(
-              (const uint4*)x, (const uint4*)dy, nvec, C / 8, rounds, scale_shift, mean_invstd, sums);
+              (const uint4*)x, (const uint4*)dy, nvec, C / 8, n_chunks, ctr, scale_shift, mean_invstd, sums);
         else
           bn_bwd_reduce_light_kernel<GHND_F16, GHND_BF16, false><<<(unsigned)blocks, 128, smem, st>>>(
-              (const uint4*)x, (const uint4*)dy, nvec, C / 8, rounds, scale_shift, mean_invstd, sums);
+              (const uint4*)x, (const uint4*)dy, nvec, C / 8, n_chunks, ctr, scale_shift, mean_invstd, sums);
         GHND_LAUNCH_CHECK("bn_bwd_reduce_light_kernel");
         return GHND_OK;
       }
