@@ -31,7 +31,7 @@ import os
 # form divides by gamma (undefined for a channel whose gamma is exactly 0).
 FUSE_BN_REDUCE = os.environ.get("GHND_FUSE_BN_REDUCE", "0") == "1"
 # A/B switch: the bottleneck-side dW launches on the side stream (default) or in the data-gradient chain
-NARROW_DW_SIDE = os.environ.get("GHND_NARROW_DW_SIDE", "1") != "0"
+NARROW_DW_SIDE = int(os.environ.get("GHND_NARROW_DW_SIDE", "1"))  # 0 chain, 1 side stream at once, 2 side stream, deferred
 
 LEVELS = ("layer1", "layer2", "layer3", "layer4")
 PLANES = {"layer1": 64, "layer2": 128, "layer3": 256, "layer4": 512}
@@ -622,6 +622,11 @@ class StudentLayer1Runner(object):
         # the two bottleneck-side dW launches feed nothing on the data-gradient chain: like the wide dW GEMMs they
         # run on the side stream (one after the other there, so they may share the workspace)
         narrow_side = side if NARROW_DW_SIDE else None
+        # mode 2: both launches wait until the end of the layer's backward pass (forked right here they fill every SM
+        # for 22 us each and the small kernels of the chain below queue behind them for ~11 us twice).  Measured
+        # WORSE than mode 1 (same box, 150 steps x 3: 770.3 / 768.4 -> 766.2 / 766.5 / 765.0 img/s): at the end they
+        # hold the SMs the conv1 dW GEMM is waiting for.
+        defer = narrow_side is not None and NARROW_DW_SIDE == 2
 
         def dw_dec2():
             ops.wgrad_narrow(self.z, self.g_raw3, self.gr[d + "2.weight"], False, 2, 2, 0, pre=bz.scale_shift,
@@ -630,7 +635,9 @@ class StudentLayer1Runner(object):
         def dw_enc7():
             ops.wgrad_narrow(self.g_z, self.e2.out, self.gr[e + "7.weight"], True, 2, 2, 1, ws=self.wws)
 
-        if narrow_side is not None:
+        if defer:
+            pass
+        elif narrow_side is not None:
             narrow_side.fork()
             narrow_side.run(dw_dec2)
         else:
@@ -642,7 +649,9 @@ class StudentLayer1Runner(object):
         ops.bn_bwd_apply(self.g_zact, self.z, self.g_z, bz.bn.weight, bz.scale_shift, bz.mean_invstd, True,
                          bz.sums, self.gr[d + "0.weight"], self.gr[d + "0.bias"], planar=True)
         # enc7 (narrow-out conv)
-        if narrow_side is not None:
+        if defer:
+            pass
+        elif narrow_side is not None:
             narrow_side.fork()
             narrow_side.run(dw_enc7)
         else:
@@ -651,6 +660,10 @@ class StudentLayer1Runner(object):
         self.e2.backward(side)
         self.e1.backward(side)
         self.e0.backward(side)
+        if defer:
+            narrow_side.fork()
+            narrow_side.run(dw_dec2)
+            narrow_side.run(dw_enc7)
 
 
 def _same_frozen_layers(teacher_body, student_body, names):
