@@ -527,6 +527,44 @@ def test_bn_train_fwd_bwd(ops, C, relu):
     assert rel(dg.cpu(), dg_ref) < 1e-3 and rel(db.cpu(), db_ref) < 1e-3
 
 
+@pytest.mark.parametrize("C,relu", [(256, True), (64, False)])
+def test_bn_bwd_reduce_claims_chunks(ops, C, relu):
+    """bn_bwd_reduce_light_kernel: CTAs claim 2048-vector chunks from a counter that the last CTA resets.  A tensor
+    with more chunks than CTAs (several claims per CTA, ragged last chunk), launched repeatedly and replayed from a
+    CUDA graph: every launch must start from a zeroed counter and give the sums of a fp64 reference."""
+    torch.manual_seed(3 * C + relu)
+    N, H, W = 2, 151, 160 * 256 // C + 1
+    x = (torch.randn(N, H, W, C, device="cuda") * 1.5 + 0.3).to(torch.float16)
+    g = torch.randn(N, H, W, C, device="cuda").to(torch.bfloat16)
+    assert x.numel() // 8 > 2048 * 148 * 5 and (x.numel() // 8) % 2048 != 0
+    sc = torch.rand(C, device="cuda") + 0.5
+    sf = torch.randn(C, device="cuda") * 0.2
+    mu = torch.randn(C, device="cuda") * 0.3
+    inv = torch.rand(C, device="cuda") + 0.5
+    ss, mi = torch.cat([sc, sf]).contiguous(), torch.cat([mu, inv]).contiguous()
+    xd, gd = x.double(), g.double()
+    if relu:
+        gd = gd * ((x.float() * sc + sf) > 0)
+    ref = torch.cat([gd.sum((0, 1, 2)), (gd * ((xd - mu.double()) * inv.double())).sum((0, 1, 2))])
+    sums = torch.empty(2 * C, dtype=torch.float64, device="cuda")
+    for _ in range(3):
+        sums.fill_(float("nan"))
+        ops.bn_bwd_reduce(g, x, ss, mi, relu, sums)
+        assert rel(sums, ref) < 1e-4, rel(sums, ref)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=s):
+            ops.bn_bwd_reduce(g, x, ss, mi, relu, sums)
+        for _ in range(3):
+            sums.fill_(float("nan"))
+            graph.replay()
+            torch.cuda.synchronize()
+            assert rel(sums, ref) < 1e-4, rel(sums, ref)
+    torch.cuda.current_stream().wait_stream(s)
+
+
 def test_bn_planar(ops):
     torch.manual_seed(1)
     N, C, H, W = 2, 3, 28, 36
@@ -849,13 +887,15 @@ def test_adam(ops):
 
 def test_switched_off_paths_still_pass():
     """The A/B switches select the older kernels (direct-load / SIMT bottleneck-side kernels, un-fused stem +
-    pool, no CTA pairs, no conv halo mode).  They are read once per process, so the same kernel tests run again
+    pool, no CTA pairs, no conv halo mode, persistent BatchNorm-backward kernels).  They are read once per process, so the same kernel tests run again
     in a child process with every switch off: the fall-back paths stay correct."""
     import subprocess
     import sys
-    env = dict(os.environ, GHND_NARROW_TMA="0", GHND_STEM_POOL="0", GHND_CONV_PAIR="0", GHND_CONV_HALO="0")
+    env = dict(os.environ, GHND_NARROW_TMA="0", GHND_STEM_POOL="0", GHND_CONV_PAIR="0", GHND_CONV_HALO="0",
+               GHND_BN_LIGHT="0", GHND_S2_SHARE="0")  # persistent BN-backward kernels, full-width s2 dgrad grids
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "tests/test_gpu_kernels.py", "-k",
-                        "test_narrow_convs or test_conv_fwd or test_conv_dgrad or test_stem or test_narrow_out_minmax"],
+                        "test_narrow_convs or test_conv_fwd or test_conv_dgrad or test_stem or test_narrow_out_minmax "
+                        "or test_bn_train_fwd_bwd"],
                        cwd=root, env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
