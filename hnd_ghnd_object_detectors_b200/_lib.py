@@ -43,6 +43,13 @@ class WgradDesc(Structure):
                 ("dy_fmt", c_int), ("dw", c_void_p)]
 
 
+class PackWeightDesc(Structure):
+    _fields_ = [("w_oihw", c_void_p), ("scale_o", c_void_p), ("O", c_int), ("I", c_int), ("R", c_int), ("S", c_int),
+                ("transpose", c_int), ("dst", c_void_p), ("dst_fmt", c_int)]
+
+
+PACK_MAX = 16  # GHND_PACK_MAX
+
 _P = c_void_p
 _I = c_int
 _L = c_int64
@@ -76,6 +83,7 @@ SIGNATURES = {
     "ghnd_wgrad_plan_run": (_I, [_P, _P]),
     "ghnd_wgrad_plan_destroy": (None, [_P]),
     "ghnd_pack_weight": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _I, _P]),
+    "ghnd_pack_weights": (_I, [POINTER(PackWeightDesc), _I, _P]),
     "ghnd_unpack_wgrad": (_I, [_P, _P, _I, _I, _I, _I, _F, _P]),
     "ghnd_conv_narrow_workspace_bytes": (_Z, [_I, _I, _I, _I]),
     "ghnd_conv_narrow_out": (_I, [_P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _Z, _P]),

@@ -1299,6 +1299,40 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, const float* __r
   }
 }
 
+struct WeightPackBatch {
+  ghnd_pack_weight_desc_t d[GHND_PACK_MAX];
+};
+// blockIdx.y = tensor; same index arithmetic as pack_weight_kernel
+__global__ void pack_weights_kernel(const __grid_constant__ WeightPackBatch b) {
+  const ghnd_pack_weight_desc_t& d = b.d[blockIdx.y];
+  const int O = d.O, I = d.I, R = d.R, S = d.S;
+  const int64_t total = (int64_t)O * I * R * S;
+  uint16_t* dst = static_cast<uint16_t*>(d.dst);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t t = i;
+    int o, c, r, s;
+    if (!d.transpose) {  // [O][R][S][I]
+      c = (int)(t % I);
+      t /= I;
+      s = (int)(t % S);
+      t /= S;
+      r = (int)(t % R);
+      o = (int)(t / R);
+    } else {  // [I][R][S][O]
+      o = (int)(t % O);
+      t /= O;
+      s = (int)(t % S);
+      t /= S;
+      r = (int)(t % R);
+      c = (int)(t / R);
+    }
+    float v = d.w_oihw[(((int64_t)o * I + c) * R + r) * S + s];
+    if (d.scale_o != nullptr) v *= d.scale_o[o];
+    dst[i] = float_to_h16(v, d.dst_fmt);
+  }
+}
+
 __global__ void unpack_wgrad_kernel(const float* __restrict__ dw, float* __restrict__ dst, int O, int I,
                                     int R, int S, float alpha) {
   const int64_t total = (int64_t)O * I * R * S;
@@ -1791,6 +1825,27 @@ int ghnd_pack_weight(const float* w_oihw, const float* scale_o, int O, int I, in
   pack_weight_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
       w_oihw, scale_o, O, I, R, S, transpose, (uint16_t*)dst, dst_fmt);
   GHND_LAUNCH_CHECK("pack_weight_kernel");
+  return GHND_OK;
+}
+
+int ghnd_pack_weights(const ghnd_pack_weight_desc_t* descs, int n, void* stream) {
+  GHND_CHECK_ARG(descs && n > 0 && n <= GHND_PACK_MAX, "pack_weights: 1..%d tensors per launch (got %d)",
+                 GHND_PACK_MAX, n);
+  WeightPackBatch b;
+  memset(&b, 0, sizeof(b));
+  int64_t largest = 0;
+  for (int k = 0; k < n; ++k) {
+    const ghnd_pack_weight_desc_t& d = descs[k];
+    GHND_CHECK_ARG(d.w_oihw && d.dst && fmt16(d.dst_fmt) && d.O > 0 && d.I > 0 && d.R > 0 && d.S > 0,
+                   "pack_weights: bad argument in entry %d", k);
+    b.d[k] = d;
+    const int64_t total = (int64_t)d.O * d.I * d.R * d.S;
+    if (total > largest) largest = total;
+  }
+  int gx = (int)((largest + 255) / 256);
+  if (gx > 64) gx = 64;
+  pack_weights_kernel<<<dim3((unsigned)gx, (unsigned)n), 256, 0, (cudaStream_t)stream>>>(b);
+  GHND_LAUNCH_CHECK("pack_weights_kernel");
   return GHND_OK;
 }
 

@@ -31,6 +31,10 @@ import os
 # form divides by gamma (undefined for a channel whose gamma is exactly 0).
 FUSE_BN_REDUCE = os.environ.get("GHND_FUSE_BN_REDUCE", "0") == "1"
 # A/B switch: the bottleneck-side dW launches on the side stream (default) or in the data-gradient chain
+# A/B switch: the student's weight repacking as ONE launch on the MAIN stream in front of the stem kernel (default).
+# As twelve launches on the side stream it started only when the stem kernel (every SM, all shared memory) let go, and
+# the first layer1 conv, which waits for it, started 37 us after the stem had finished (in-graph timeline).
+PREPACK_BATCHED = os.environ.get("GHND_PREPACK_BATCHED", "1") != "0"
 NARROW_DW_SIDE = int(os.environ.get("GHND_NARROW_DW_SIDE", "1"))  # 0 chain, 1 side stream at once, 2 side stream, deferred
 
 LEVELS = ("layer1", "layer2", "layer3", "layer4")
@@ -595,6 +599,19 @@ class StudentLayer1Runner(object):
         return (self.e0, self.e1, self.e2, self.d4, self.d7, self.d9)
 
     def prepack(self):
+        """This step's packed weights of the six wide units (forward + transposed).  PREPACK_BATCHED: ONE launch
+        (ops.pack_weights) instead of twelve."""
+        units = [u for u in self.wide_units() if u.train]
+        if PREPACK_BATCHED and units:
+            items = []
+            for u in units:
+                items.append((u.conv.weight, None, False, u.w))
+                if getattr(u, "wt", None) is not None:
+                    items.append((u.conv.weight, None, True, u.wt))
+            ops.pack_weights(items)
+            for u in units:
+                u.prepacked = True
+            return
         for u in self.wide_units():
             u.prepack()
 
@@ -815,9 +832,14 @@ class GhndPlan(object):
         if side is not None:
             # branch 1 (side): this step's weight repacking, then the whole teacher forward;
             # branch 2 (main): student stem + layer1.  They meet at the (shared) frozen trunk.
-            side.fork()
-            side.run(self.s_l1.prepack)
-            packed = side.mark()
+            if PREPACK_BATCHED:
+                self.s_l1.prepack()  # one small launch in front of the stem kernel
+                packed = None
+                side.fork()
+            else:
+                side.fork()
+                side.run(self.s_l1.prepack)
+                packed = side.mark()
             side.run(self.s_stem.convert_image)  # bf16 copy of the packed image: off the backward tail
             if self.stem2 is not None:
                 self.stem2.forward()  # both conv1's; the two pools + layer1's then run side by side
@@ -829,7 +851,8 @@ class GhndPlan(object):
             else:
                 self._teacher_forward()
             self.s_stem.forward()
-            torch.cuda.current_stream().wait_event(packed)
+            if packed is not None:
+                torch.cuda.current_stream().wait_event(packed)
             self.s_l1.forward()
             side.join()
         else:

@@ -332,6 +332,28 @@ def pack_weight(w, scale=None, transpose=False, dtype=torch.float16, out=None):
     return out
 
 
+def pack_weights(items):
+    """items: list of (w OIHW fp32, scale or None, transpose, out) -- the arguments of pack_weight -- repacked by
+    ONE launch per GHND_PACK_MAX tensors (ghnd_pack_weights)."""
+    for k0 in range(0, len(items), _lib.PACK_MAX):
+        chunk = items[k0:k0 + _lib.PACK_MAX]
+        descs = (_lib.PackWeightDesc * len(chunk))()
+        keep = []
+        for d, (w, scale, transpose, out) in zip(descs, chunk):
+            _need_cuda(w)
+            wf = w.detach()
+            if wf.dtype != torch.float32 or not wf.is_contiguous():
+                wf = wf.float().contiguous()
+            keep.append(wf)
+            o, i, r, s = wf.shape
+            assert out.numel() == wf.numel()
+            d.w_oihw, d.scale_o = wf.data_ptr(), (scale.data_ptr() if scale is not None else None)
+            d.O, d.I, d.R, d.S, d.transpose = o, i, r, s, int(bool(transpose))
+            d.dst, d.dst_fmt = out.data_ptr(), fmt_of(out.dtype)
+        call("ghnd_pack_weights", descs, len(chunk), stream_ptr())
+        _count()
+
+
 def unpack_wgrad(dw, out, alpha=1.0):
     """[O][R][S][I] fp32 -> OIHW fp32 into `out`."""
     o, i, r, s = out.shape

@@ -201,6 +201,18 @@ void ghnd_wgrad_plan_destroy(ghnd_wgrad_plan_t* plan);
  * I_pad / O to O_pad in the packed tensor. */
 int ghnd_pack_weight(const float* w_oihw, const float* scale_o, int O, int I, int R, int S,
                      int transpose, void* dst, int dst_fmt, void* stream);
+/* Several repacks in ONE launch (the student's layer1 repacks 12 tensors at the start of every step: as 12 small
+ * launches they queued behind the stem kernel and held the first layer1 conv back).  descs: HOST array of n <=
+ * GHND_PACK_MAX entries with the arguments of ghnd_pack_weight. */
+#define GHND_PACK_MAX 16
+typedef struct {
+  const float* w_oihw;
+  const float* scale_o; /* may be NULL */
+  int O, I, R, S, transpose;
+  void* dst;
+  int dst_fmt;
+} ghnd_pack_weight_desc_t;
+int ghnd_pack_weights(const ghnd_pack_weight_desc_t* descs, int n, void* stream);
 /* inverse for gradients: dw [O][R][S][I] fp32 -> OIHW fp32 (scaled by alpha) */
 int ghnd_unpack_wgrad(const float* dw_orsi, float* dst_oihw, int O, int I, int R, int S,
                       float alpha, void* stream);

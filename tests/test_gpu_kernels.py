@@ -885,6 +885,29 @@ def test_adam(ops):
     assert rel(md.cpu(), m) < 1e-6 and rel(vd.cpu(), v) < 1e-6
 
 
+def test_pack_weights_batched_is_bitwise_the_per_tensor_pack(ops):
+    """ghnd_pack_weights (one launch for up to 16 tensors) against ghnd_pack_weight, both layouts, with and without
+    a per-output scale, more tensors than one launch holds."""
+    torch.manual_seed(11)
+    shapes = [(64, 64, 2, 2), (256, 64, 2, 2), (64, 256, 2, 2), (128, 64, 2, 2), (256, 128, 2, 2), (256, 256, 2, 2),
+              (64, 64, 3, 3), (128, 256, 1, 1), (64, 128, 1, 1)]
+    items, refs = [], []
+    for k, shp in enumerate(shapes):
+        w = torch.randn(shp, device="cuda")
+        scale = (torch.rand(shp[0], device="cuda") + 0.5) if k % 3 == 0 else None
+        for transpose in (False, True):
+            dt = torch.float16 if (k + transpose) % 2 == 0 else torch.bfloat16
+            o, i, r, s_ = shp
+            out = torch.full((i, r, s_, o) if transpose else (o, r, s_, i), 7.0, dtype=dt, device="cuda")
+            items.append((w, scale, transpose, out))
+            refs.append(ops.pack_weight(w, scale, transpose, dtype=dt))
+    assert len(items) > 16
+    ops.pack_weights(items)
+    torch.cuda.synchronize()
+    for (w, scale, transpose, out), ref in zip(items, refs):
+        assert torch.equal(out, ref), (tuple(w.shape), transpose)
+
+
 def test_switched_off_paths_still_pass():
     """The A/B switches select the older kernels (direct-load / SIMT bottleneck-side kernels, un-fused stem +
     pool, no CTA pairs, no conv halo mode, persistent BatchNorm-backward kernels).  They are read once per process, so the same kernel tests run again
