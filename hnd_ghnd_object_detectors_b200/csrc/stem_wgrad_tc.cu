@@ -6,8 +6,12 @@
 // 128-row tiles, N = 64 output channels, K = output pixels (~1.1 M per 4-image batch).  Both
 // operands come straight from global memory by TMA with the pixel axis as the strided (GEMM-K)
 // axis, i.e. they sit in shared memory MN-major:
-//   A atom r : box {32 elem, 32 px} of the packed image row 2ho+r -> [32 px][64 B], SWIZZLE_64B
-//   B        : box {64 ch,  32 px} of g                           -> [32 px][128 B], SWIZZLE_128B
+//   A        : ONE box {32 elem, 32 px, 13 image rows} per stage  -> 13 atoms [32 px][64 B], SWIZZLE_64B
+//   B        : box {64 ch,  32 px, 4 output rows} of g            -> 4 x [32 px][128 B], SWIZZLE_128B
+// A stage covers FOUR output rows ho0..ho0+3 of 32 pixels: output row ho0+i reads the image rows 2(ho0+i)+r, i.e.
+// atoms 2i..2i+6 of the 13 resident ones -- the MMA descriptors of row i simply start 2i atoms further.  With one
+// output row per stage every image row was fetched 3.5 times per column class (7 atoms per 32 pixels: 14 KB of A
+// for 4 KB of B, 625 MB of L2 -> SM traffic per launch, the limit of this kernel); now it is 13 atoms per 4 rows.
 // Output columns are split in four classes wo = 4j+q so that consecutive pixels of a class start
 // 64 B apart in the packed row (no overlapping TMA rows), exactly like the forward stem kernel.
 // Every CTA owns a contiguous range of pixel tiles, accumulates the whole 224x64 dw in TMEM
@@ -17,17 +21,20 @@
 namespace ghnd {
 
 static constexpr int kSwtThreads = 192;      // warp0 TMA, warp1 MMA, warps 2..5 epilogue
-static constexpr int kSwtPix = 32;           // pixels (GEMM-K) per pipeline stage
+static constexpr int kSwtPix = 32;           // pixels along W per stage
+static constexpr int kSwtRows = 4;           // output rows per stage: GEMM-K = 4 x 32 pixels
 static constexpr int kSwtAtom = kSwtPix * 64;   // one [32 px][64 B] A atom = 2 KB
-static constexpr int kSwtABytes = 8 * kSwtAtom; // 7 filter rows + 1 unused atom (M = 2 x 128)
-static constexpr int kSwtBBytes = kSwtPix * 128;
-static constexpr int kSwtStage = kSwtABytes + kSwtBBytes;  // 20 KB
-static constexpr int kSwtStages = 8;
+static constexpr int kSwtImgRows = 2 * (kSwtRows - 1) + 7;  // 13 image rows feed 4 output rows
+static constexpr int kSwtABytes = (kSwtImgRows + 1) * kSwtAtom;  // + 1 unused atom (M = 2 x 128 reads 8 per row)
+static constexpr int kSwtBRow = kSwtPix * 128;  // g of one output row: 4 KB
+static constexpr int kSwtBBytes = kSwtRows * kSwtBRow;
+static constexpr int kSwtStage = kSwtABytes + kSwtBBytes;  // 44 KB
+static constexpr int kSwtStages = 4;
 
 struct StemWgradParams {
   CUtensorMap tmap_x[4];  // per column class q
   CUtensorMap tmap_g[4];
-  int n_img, ho, tiles_j;
+  int n_img, ho, tiles_j;  // ho = groups of kSwtRows output rows per image
   int total_tiles;        // n_img * ho * 4 * tiles_j
   FastDiv fd_tiles_j, fd_ho;
   uint32_t idesc;
@@ -86,11 +93,11 @@ __global__ void __launch_bounds__(kSwtThreads, 1)
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 128);
-  // the unused 8th A atom of every stage is read by the MMA (rows 96..127 of M tile 1, discarded):
-  // give it defined contents once
+  // the atom after the last image row is read by the MMAs of the stage's last output row (rows 96..127 of
+  // M tile 1, discarded; for the other output rows those rows see a real image row): defined contents once
   for (int i = threadIdx.x; i < kSwtStages * (kSwtAtom / 16); i += kSwtThreads) {
     const int st = i / (kSwtAtom / 16), o = i - st * (kSwtAtom / 16);
-    reinterpret_cast<uint4*>(smem + (size_t)st * kSwtStage + 7 * kSwtAtom)[o] = make_uint4(0, 0, 0, 0);
+    reinterpret_cast<uint4*>(smem + (size_t)st * kSwtStage + kSwtImgRows * kSwtAtom)[o] = make_uint4(0, 0, 0, 0);
   }
   fence_proxy_async();
   tc_fence_before();
@@ -112,12 +119,11 @@ __global__ void __launch_bounds__(kSwtThreads, 1)
       mbar_wait(&empty_bar[stage], phase ^ 1);
       if (elect_one()) {
         uint8_t* sa = smem + (size_t)stage * kSwtStage;
-        mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(7 * kSwtAtom + kSwtBBytes));
-#pragma unroll
-        for (int r = 0; r < 7; ++r)
-          tma_load_4d(sa + r * kSwtAtom, &p.tmap_x[q], &full_bar[stage], 0, jt * kSwtPix, 2 * ho + r,
-                      img);
-        tma_load_4d(sa + kSwtABytes, &p.tmap_g[q], &full_bar[stage], 0, jt * kSwtPix, ho, img);
+        mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(kSwtImgRows * kSwtAtom + kSwtBBytes));
+        // ho = group of four output rows: image rows 8*ho .. 8*ho + 12, g rows 4*ho .. 4*ho + 3 (rows past the
+        // tensors are zero-filled by TMA)
+        tma_load_4d(sa, &p.tmap_x[q], &full_bar[stage], 0, jt * kSwtPix, 2 * kSwtRows * ho, img);
+        tma_load_4d(sa + kSwtABytes, &p.tmap_g[q], &full_bar[stage], 0, jt * kSwtPix, kSwtRows * ho, img);
       }
       __syncwarp();
       if (++stage == kSwtStages) {
@@ -138,13 +144,17 @@ __global__ void __launch_bounds__(kSwtThreads, 1)
       tc_fence_after();
       if (elect_one()) {
         const uint32_t sa = smem_base + (uint32_t)(stage * kSwtStage);
-        const uint32_t b_lo = (((sa + kSwtABytes) >> 4) & 0x3fffu) | ((uint32_t)(kSwtBBytes >> 4) << 16);
 #pragma unroll
-        for (int m = 0; m < 2; ++m) {
-          const uint32_t a_lo =
-              (((sa + m * 4 * kSwtAtom) >> 4) & 0x3fffu) | ((uint32_t)(kSwtAtom >> 4) << 16);
-          umma_pair_stem(tmem_base + (uint32_t)(m * 64), a_lo, b_lo, a_hi, b_hi, p.idesc,
-                         (uint32_t)(t != t_begin));
+        for (int i = 0; i < kSwtRows; ++i) {  // output row i of the stage: atoms 2i .. 2i + 7, g row i
+          const uint32_t b_lo =
+              (((sa + kSwtABytes + i * kSwtBRow) >> 4) & 0x3fffu) | ((uint32_t)(kSwtBRow >> 4) << 16);
+#pragma unroll
+          for (int m = 0; m < 2; ++m) {
+            const uint32_t a_lo =
+                (((sa + (2 * i + m * 4) * kSwtAtom) >> 4) & 0x3fffu) | ((uint32_t)(kSwtAtom >> 4) << 16);
+            umma_pair_stem(tmem_base + (uint32_t)(m * 64), a_lo, b_lo, a_hi, b_hi, p.idesc,
+                           (uint32_t)(t != t_begin || i != 0));
+          }
         }
         umma_commit(&empty_bar[stage]);
       }
@@ -222,14 +232,14 @@ int ghnd_stem_wgrad_plan_create(const void* x_packed, const void* g, int fmt, co
       const uint8_t* base = static_cast<const uint8_t*>(x_packed) + (size_t)q * 8 * 2;
       uint64_t dims[4] = {32, (uint64_t)J, (uint64_t)rows, (uint64_t)N};
       uint64_t str[4] = {2, 64, (uint64_t)RP * 2, (uint64_t)rows * RP * 2};
-      uint32_t box[4] = {32, (uint32_t)kSwtPix, 1, 1};
+      uint32_t box[4] = {32, (uint32_t)kSwtPix, (uint32_t)kSwtImgRows, 1};
       rc = encode_tmap(&p.tmap_x[q], 2, 4, const_cast<uint8_t*>(base), dims, str, box, 64);
     }
     if (rc == GHND_OK) {
       const uint8_t* base = static_cast<const uint8_t*>(g) + (size_t)q * 64 * 2;
       uint64_t dims[4] = {64, (uint64_t)J, (uint64_t)Ho, (uint64_t)N};
       uint64_t str[4] = {2, 4 * 128, (uint64_t)Wo * 128, (uint64_t)Ho * Wo * 128};
-      uint32_t box[4] = {64, (uint32_t)kSwtPix, 1, 1};
+      uint32_t box[4] = {64, (uint32_t)kSwtPix, (uint32_t)kSwtRows, 1};
       rc = encode_tmap(&p.tmap_g[q], 2, 4, const_cast<uint8_t*>(base), dims, str, box, 128);
     }
   }
@@ -238,11 +248,11 @@ int ghnd_stem_wgrad_plan_create(const void* x_packed, const void* g, int fmt, co
     return rc;
   }
   p.n_img = N;
-  p.ho = Ho;
+  p.ho = (Ho + kSwtRows - 1) / kSwtRows;
   p.tiles_j = (J0 + kSwtPix - 1) / kSwtPix;
-  p.total_tiles = N * Ho * 4 * p.tiles_j;
+  p.total_tiles = N * p.ho * 4 * p.tiles_j;
   p.fd_tiles_j = make_fastdiv(p.tiles_j);
-  p.fd_ho = make_fastdiv(Ho);
+  p.fd_ho = make_fastdiv(p.ho);
   p.idesc = make_idesc(fmt, fmt, 1, 1, 128, 64);
   p.accum = static_cast<float*>(workspace);
   plan->scale = scale_o;
