@@ -49,6 +49,7 @@ class PackWeightDesc(Structure):
 
 
 PACK_MAX = 16  # GHND_PACK_MAX
+SUMS_ZEROED = 0x100  # GHND_SUMS_ZEROED
 
 _P = c_void_p
 _I = c_int

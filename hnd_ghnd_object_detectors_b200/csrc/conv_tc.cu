@@ -1267,6 +1267,7 @@ struct ConvLaunch {
 
 struct ghnd_conv_plan {
   std::vector<ghnd::ConvLaunch> launches;
+  bool stats_zeroed = false;  // GHND_SUMS_ZEROED: the caller zeroes the statistics buffer once per step
 };
 
 namespace ghnd {
@@ -1803,10 +1804,15 @@ static int max_conv_pairs() {
 
 extern "C" {
 
-int ghnd_conv_plan_create(const ghnd_conv_desc_t* d, ghnd_conv_plan_t** out) {
+int ghnd_conv_plan_create(const ghnd_conv_desc_t* d_in, ghnd_conv_plan_t** out) {
   using namespace ghnd;
-  GHND_CHECK_ARG(d && out, "conv_plan_create: null argument");
+  GHND_CHECK_ARG(d_in && out, "conv_plan_create: null argument");
   *out = nullptr;
+  // GHND_SUMS_ZEROED in stats_mode: the caller zeroes `stats` once per step, the plan only accumulates
+  ghnd_conv_desc_t d_copy = *d_in;
+  const bool stats_zeroed = (d_copy.stats_mode & GHND_SUMS_ZEROED) != 0;
+  d_copy.stats_mode &= ~GHND_SUMS_ZEROED;
+  const ghnd_conv_desc_t* d = &d_copy;
   GHND_CHECK_ARG(d->kind == GHND_CONV_FWD || d->kind == GHND_CONV_DGRAD, "conv: bad kind %d",
                  d->kind);
   GHND_CHECK_ARG(d->N > 0 && d->H > 0 && d->W > 0, "conv: bad geometry N=%d H=%d W=%d", d->N, d->H,
@@ -1848,6 +1854,7 @@ int ghnd_conv_plan_create(const ghnd_conv_desc_t* d, ghnd_conv_plan_t** out) {
   GHND_CHECK_ARG(Ho > 0 && Wo > 0, "conv: empty output");
 
   ghnd_conv_plan* plan = new ghnd_conv_plan();
+  plan->stats_zeroed = stats_zeroed;
   int rc = GHND_OK;
   const int taps_total = d->R * d->S;
 
@@ -2071,7 +2078,7 @@ int ghnd_conv_plan_run(const ghnd_conv_plan_t* plan, void* stream) {
   using namespace ghnd;
   GHND_CHECK_ARG(plan != nullptr, "conv_plan_run: null plan");
   for (const ConvLaunch& L : plan->launches) {
-    if (L.p.stats != nullptr)
+    if (L.p.stats != nullptr && !plan->stats_zeroed)
       GHND_CUDA(cudaMemsetAsync(L.p.stats, 0, (size_t)2 * L.p.cout * sizeof(double),
                                 (cudaStream_t)stream));
     GHND_CUDA(launch_conv(L, (cudaStream_t)stream));
@@ -2087,7 +2094,7 @@ int ghnd_conv_plan_run_range(const ghnd_conv_plan_t* plan, int first, int count,
                  (int)plan->launches.size());
   for (int i = first; i < first + count; ++i) {
     const ConvLaunch& L = plan->launches[i];
-    if (L.p.stats != nullptr && i == 0)
+    if (L.p.stats != nullptr && i == 0 && !plan->stats_zeroed)
       GHND_CUDA(cudaMemsetAsync(L.p.stats, 0, (size_t)2 * L.p.cout * sizeof(double),
                                 (cudaStream_t)stream));
     GHND_CUDA(launch_conv(L, (cudaStream_t)stream));

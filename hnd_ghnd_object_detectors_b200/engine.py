@@ -35,6 +35,8 @@ FUSE_BN_REDUCE = os.environ.get("GHND_FUSE_BN_REDUCE", "0") == "1"
 # As twelve launches on the side stream it started only when the stem kernel (every SM, all shared memory) let go, and
 # the first layer1 conv, which waits for it, started 37 us after the stem had finished (in-graph timeline).
 PREPACK_BATCHED = os.environ.get("GHND_PREPACK_BATCHED", "1") != "0"
+# A/B switch: one memset per step over all BatchNorm reduction buffers (SumsPool) instead of one memset node per use
+SUMS_POOL = os.environ.get("GHND_SUMS_POOL", "1") != "0"
 NARROW_DW_SIDE = int(os.environ.get("GHND_NARROW_DW_SIDE", "1"))  # 0 chain, 1 side stream at once, 2 side stream, deferred
 
 LEVELS = ("layer1", "layer2", "layer3", "layer4")
@@ -349,12 +351,41 @@ class StemRunner(object):
         self.wgrad.run()
 
 
+class SumsPool(object):
+    """One fp64 allocation for every per-step BatchNorm reduction buffer of a plan (forward statistics and backward
+    sums of each BN separately), zeroed by ONE memset at the start of the step.  The reductions then only accumulate
+    (GHND_SUMS_ZEROED) instead of each heading its kernel with a memset node of its own: inside the CUDA graph a
+    kernel -> memset -> kernel hop costs ~9 us against ~2 us for kernel -> kernel (in-graph timeline), and the
+    student's layer1 has fifteen of them on its critical chain."""
+    current = None  # the pool new _BN objects draw from (set by GhndPlan while it builds the student's layer1)
+
+    def __init__(self, device, n_doubles=16384):
+        self.buf = torch.zeros(n_doubles, dtype=torch.float64, device=device)
+        self.used = 0
+
+    def take(self, n):
+        n = (n + 15) // 16 * 16
+        assert self.used + n <= self.buf.numel(), "SumsPool exhausted"
+        v = self.buf[self.used:self.used + n]
+        self.used += n
+        return v
+
+    def zero(self):
+        if self.used:
+            self.buf[:self.used].zero_()
+
+
 class _BN(object):
     """Training-mode nn.BatchNorm2d state for one NHWC tensor (or the planar bottleneck)."""
 
     def __init__(self, bn, C, count, dev):
         self.bn, self.C, self.count = bn, C, count
-        self.sums = _empty((2 * C,), torch.float64, dev)
+        pool = SumsPool.current
+        self.pooled = pool is not None  # forward / backward sums are zeroed by the plan, once per step
+        if self.pooled:
+            self.sums, self.sums_b = pool.take(2 * C)[:2 * C], pool.take(2 * C)[:2 * C]
+        else:
+            self.sums = self.sums_b = _empty((2 * C,), torch.float64, dev)
         self.scale_shift = _empty((2 * C,), torch.float32, dev)
         self.mean_invstd = _empty((2 * C,), torch.float32, dev)
 
@@ -402,7 +433,7 @@ class _WideUnit(object):
             self.out_g = _empty((N, self.Ho, self.Wo, K), grad_dtype, dev) if need_out_g else None
             # batch statistics of the stored conv output are accumulated by the conv epilogue
             self.plan = ops.ConvPlan(CONV_FWD, N, H, W, C, K, R, S, 1, pad, x, self.w, self.raw,
-                                     stats=self.bn.sums)
+                                     stats=self.bn.sums, stats_zeroed=self.bn.pooled)
         else:
             # eval: BN folded into the conv (scale into the weights, shift as bias, ReLU in epilogue)
             self.raw = self.out_g = None
@@ -449,9 +480,10 @@ class _WideUnit(object):
         if g_x is not None:
             self.wt = _empty((C, R, S, K), grad_dtype, dev)
             if below is not None and FUSE_BN_REDUCE:
-                act, relu, sums = below
+                act, relu, sums, pooled = below
                 self.dgrad = ops.ConvPlan(CONV_DGRAD, N, H, W, C, K, R, S, 1, self.pad, self.g_raw, self.wt,
-                                          g_x, mask=act, stats=sums, stats_mode=1, mask_stats_only=not relu)
+                                          g_x, mask=act, stats=sums, stats_mode=1, mask_stats_only=not relu,
+                                          stats_zeroed=pooled)
             else:
                 self.dgrad = ops.ConvPlan(CONV_DGRAD, N, H, W, C, K, R, S, 1, self.pad, self.g_raw, self.wt, g_x)
 
@@ -462,9 +494,10 @@ class _WideUnit(object):
     def backward(self, side=None):
         bn = self.bn
         if not self.reduce_fused:  # else: the dgrad that produced g_out already left the sums
-            ops.bn_bwd_reduce(self.g_out, self.raw, bn.scale_shift, bn.mean_invstd, self.relu, bn.sums)
+            ops.bn_bwd_reduce(self.g_out, self.raw, bn.scale_shift, bn.mean_invstd, self.relu, bn.sums_b,
+                              zeroed=bn.pooled)
         ops.bn_bwd_apply(self.g_out, self.raw, self.g_raw, bn.bn.weight, bn.scale_shift, bn.mean_invstd,
-                         self.relu, bn.sums, self.dgamma, self.dbeta, fused_sums=self.reduce_fused)
+                         self.relu, bn.sums_b, self.dgamma, self.dbeta, fused_sums=self.reduce_fused)
         if side is not None:  # dW next to the dgrad chain (reads g_raw / x_g only)
             side.fork()
             side.run(self._wgrad)
@@ -540,14 +573,14 @@ class StudentLayer1Runner(object):
     def forward_decoder(self, z=None):
         z = self.z if z is None else z
         if self.train:
-            ops.bn_stats(z, self.bnz.sums, planar=True)
+            ops.bn_stats(z, self.bnz.sums, planar=True, zeroed=self.bnz.pooled)
             self.bnz.finalize()
         else:
             self.bnz.eval_params()
         ops.conv_narrow_in(z, self.dec2.weight, 0, pre=self.bnz.scale_shift, pre_relu=True, y=self.raw3,
                            ws=self.nws)
         if self.train:
-            ops.bn_stats(self.raw3, self.bn3.sums)
+            ops.bn_stats(self.raw3, self.bn3.sums, zeroed=self.bn3.pooled)
             self.bn3.finalize_apply(self.raw3, self.act3, False, y2=self.act3_g)
         else:
             self.bn3.eval_params()
@@ -570,14 +603,14 @@ class StudentLayer1Runner(object):
         g = lambda u: _empty((N, u.H, u.W, u.C), gd, dev)
         self.g_d7out, self.g_d4out, self.g_act3 = g(self.d9), g(self.d7), g(self.d4)
         def below(u):  # the BN under a unit's input, for the fused backward reductions
-            return (u.out, u.relu, u.bn.sums)
+            return (u.out, u.relu, u.bn.sums_b, u.bn.pooled)
         fuse = FUSE_BN_REDUCE
         self.d9.plan_backward(g_out, self.g_d7out, grads, (d + "9.weight", d + "10.weight", d + "10.bias"), gd,
                               below=below(self.d7))
         self.d7.plan_backward(self.g_d7out, self.g_d4out, grads, (d + "7.weight", d + "8.weight", d + "8.bias"), gd,
                               below=below(self.d4))
         self.d4.plan_backward(self.g_d4out, self.g_act3, grads, (d + "4.weight", d + "5.weight", d + "5.bias"), gd,
-                              below=(self.act3, False, self.bn3.sums))
+                              below=(self.act3, False, self.bn3.sums_b, self.bn3.pooled))
         self.d7.reduce_fused = self.d4.reduce_fused = self.bn3_reduce_fused = fuse
         self.g_raw3 = _empty((N, self.H3, self.W3, 64), gd, dev)
         self.g_zact = _empty(tuple(self.z.shape), torch.float32, dev)  # grad wrt relu(bn0(z))
@@ -630,9 +663,10 @@ class StudentLayer1Runner(object):
         # BN dec[3] (no ReLU) on raw3
         b3 = self.bn3
         if not self.bn3_reduce_fused:
-            ops.bn_bwd_reduce(self.g_act3, self.raw3, b3.scale_shift, b3.mean_invstd, False, b3.sums)
+            ops.bn_bwd_reduce(self.g_act3, self.raw3, b3.scale_shift, b3.mean_invstd, False, b3.sums_b,
+                              zeroed=b3.pooled)
         ops.bn_bwd_apply(self.g_act3, self.raw3, self.g_raw3, b3.bn.weight, b3.scale_shift, b3.mean_invstd,
-                         False, b3.sums, self.gr[d + "3.weight"], self.gr[d + "3.bias"],
+                         False, b3.sums_b, self.gr[d + "3.weight"], self.gr[d + "3.bias"],
                          fused_sums=self.bn3_reduce_fused)
         # dec2 (narrow-in conv on relu(bn0(z)))
         bz = self.bnz
@@ -662,9 +696,10 @@ class StudentLayer1Runner(object):
         ops.conv_narrow_out_dgrad(self.g_raw3, self.dec2.weight, 0, self.Hz, self.Wz, dx=self.g_zact,
                                   ws=self.nws)
         # BN dec[0] + ReLU on the planar bottleneck
-        ops.bn_bwd_reduce(self.g_zact, self.z, bz.scale_shift, bz.mean_invstd, True, bz.sums, planar=True)
+        ops.bn_bwd_reduce(self.g_zact, self.z, bz.scale_shift, bz.mean_invstd, True, bz.sums_b, planar=True,
+                          zeroed=bz.pooled)
         ops.bn_bwd_apply(self.g_zact, self.z, self.g_z, bz.bn.weight, bz.scale_shift, bz.mean_invstd, True,
-                         bz.sums, self.gr[d + "0.weight"], self.gr[d + "0.bias"], planar=True)
+                         bz.sums_b, self.gr[d + "0.weight"], self.gr[d + "0.bias"], planar=True)
         # enc7 (narrow-out conv)
         if defer:
             pass
@@ -776,9 +811,15 @@ class GhndPlan(object):
         grads = self.flat.grads
         self.s_stem = StemRunner(student_body, self.packed, N, Hp, Wp, act_dtype, grad_dtype, True,
                                  shared=(self.stem2, 64) if self.stem2 else None)
-        self.s_l1 = StudentLayer1Runner(student_body.layer1, self.s_stem.out, N, self.s_stem.Ho,
-                                        self.s_stem.Wo, act_dtype, grad_dtype, True,
-                                        out=self.trunk_in[N:] if self.shared else None)
+        # every BatchNorm reduction buffer of the student's layer1 in one allocation, zeroed once per step
+        self.sums_pool = SumsPool(dev) if SUMS_POOL else None
+        SumsPool.current = self.sums_pool
+        try:
+            self.s_l1 = StudentLayer1Runner(student_body.layer1, self.s_stem.out, N, self.s_stem.Ho,
+                                            self.s_stem.Wo, act_dtype, grad_dtype, True,
+                                            out=self.trunk_in[N:] if self.shared else None)
+        finally:
+            SumsPool.current = None
         self.s_layers = {}
         if self.shared:
             x, H, W = self.trunk_in, H1, W1
@@ -834,12 +875,11 @@ class GhndPlan(object):
             # branch 2 (main): student stem + layer1.  They meet at the (shared) frozen trunk.
             if PREPACK_BATCHED:
                 self.s_l1.prepack()  # one small launch in front of the stem kernel
-                packed = None
                 side.fork()
             else:
                 side.fork()
                 side.run(self.s_l1.prepack)
-                packed = side.mark()
+            packed = None if PREPACK_BATCHED else side.mark()
             side.run(self.s_stem.convert_image)  # bf16 copy of the packed image: off the backward tail
             if self.stem2 is not None:
                 self.stem2.forward()  # both conv1's; the two pools + layer1's then run side by side
@@ -876,6 +916,10 @@ class GhndPlan(object):
         self.s_stem.backward(self.s_l1.g_x, self.flat.grads["backbone.body.conv1.weight"])
         if side is not None:
             side.join()
+        if self.sums_pool is not None:
+            # every reduction buffer has been consumed: leave the pool zeroed for the next step (it is created
+            # zeroed; as the first node of the step the fill kernel sat 11 us in front of the next launch)
+            self.sums_pool.zero()
         return self.loss_out
 
     def _teacher_forward(self):

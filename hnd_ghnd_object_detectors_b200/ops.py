@@ -169,7 +169,7 @@ class ConvPlan(object):
 
     def __init__(self, kind, N, H, W, C, K, R, S, stride, pad, src, weights, dst, bias=None,
                  residual=None, relu=False, mask=None, accumulate=False, stats=None, stats_mode=0,
-                 mask_stats_only=False):
+                 mask_stats_only=False, stats_zeroed=False):
         d = _lib.ConvDesc()
         d.kind = kind
         d.N, d.H, d.W, d.C, d.K, d.R, d.S, d.stride, d.pad = N, H, W, C, K, R, S, stride, pad
@@ -186,7 +186,7 @@ class ConvPlan(object):
         if stats is not None:
             assert stats.dtype == torch.float64 and stats.numel() >= 2 * (K if kind == _lib.CONV_FWD else C)
         d.stats = stats.data_ptr() if stats is not None else None
-        d.stats_mode = int(stats_mode)
+        d.stats_mode = int(stats_mode) | (_lib.SUMS_ZEROED if (stats_zeroed and stats is not None) else 0)
         d.mask_stats_only = int(bool(mask_stats_only))
         self._keep = (src, weights, dst, bias, residual, mask, stats)  # buffers must outlive the plan
         self.desc = "%s N%d %dx%d C%d K%d %dx%d s%d p%d%s%s%s%s" % (
@@ -598,13 +598,15 @@ class StemWgradPlan(object):
 # ------------------------------------------------------------------------------------------------
 # BatchNorm (training) and Adam
 # ------------------------------------------------------------------------------------------------
-def bn_stats(x, sums, planar=False):
+def bn_stats(x, sums, planar=False, zeroed=False):
+    """zeroed: the caller has zeroed `sums` (one memset per step over all such buffers, GHND_SUMS_ZEROED)."""
+    flag = _lib.SUMS_ZEROED if zeroed else 0
     if planar:
         n, c, h, w = x.shape
-        call("ghnd_bn_stats", ptr(x), 0, 1, n, h * w, c, ptr(sums), stream_ptr())
+        call("ghnd_bn_stats", ptr(x), 0, 1 | flag, n, h * w, c, ptr(sums), stream_ptr())
     else:
         n, h, w, c = x.shape
-        call("ghnd_bn_stats", ptr(x), fmt_of(x.dtype), 0, n, h * w, c, ptr(sums), stream_ptr())
+        call("ghnd_bn_stats", ptr(x), fmt_of(x.dtype), flag, n, h * w, c, ptr(sums), stream_ptr())
     _count()
     return sums
 
@@ -700,14 +702,15 @@ def avgpool_linear(x, oh, ow, lw, lb, softmax, out=None):
     return out
 
 
-def bn_bwd_reduce(dy, x, scale_shift, mean_invstd, relu, sums, planar=False):
+def bn_bwd_reduce(dy, x, scale_shift, mean_invstd, relu, sums, planar=False, zeroed=False):
+    flag = _lib.SUMS_ZEROED if zeroed else 0  # see bn_stats
     if planar:
         n, c, h, w = x.shape
-        call("ghnd_bn_bwd_reduce", ptr(dy), 0, ptr(x), 0, 1, n, h * w, c, ptr(scale_shift), ptr(mean_invstd),
-             int(bool(relu)), ptr(sums), stream_ptr())
+        call("ghnd_bn_bwd_reduce", ptr(dy), 0, ptr(x), 0, 1 | flag, n, h * w, c, ptr(scale_shift),
+             ptr(mean_invstd), int(bool(relu)), ptr(sums), stream_ptr())
     else:
         n, h, w, c = x.shape
-        call("ghnd_bn_bwd_reduce", ptr(dy), fmt_of(dy.dtype), ptr(x), fmt_of(x.dtype), 0, n, h * w, c,
+        call("ghnd_bn_bwd_reduce", ptr(dy), fmt_of(dy.dtype), ptr(x), fmt_of(x.dtype), flag, n, h * w, c,
              ptr(scale_shift), ptr(mean_invstd), int(bool(relu)), ptr(sums), stream_ptr())
     _count()
     return sums

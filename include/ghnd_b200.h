@@ -335,6 +335,12 @@ void ghnd_stem_wgrad_plan_destroy(ghnd_stem_wgrad_plan_t* plan);
  * resnet_layer.py:43-64; batch statistics, biased var for normalisation, unbiased for running).
  * x is NHWC 16-bit with npix = N*H*W pixels, or planar fp32 (planar=1: [N][C][HW]).
  * ------------------------------------------------------------------------------------------ */
+/* The reductions below (and a conv launch with `stats`) zero their [2C] double buffer with a memset node of their
+ * own before accumulating.  Inside a CUDA graph every such node costs ~6 us on a dependent chain (kernel -> memset
+ * -> kernel instead of kernel -> kernel); a caller that keeps all these buffers in one allocation and zeroes it ONCE
+ * per step ORs GHND_SUMS_ZEROED into `planar` (ghnd_bn_stats, ghnd_bn_bwd_reduce) or `stats_mode`
+ * (ghnd_conv_desc_t): the call then only accumulates. */
+#define GHND_SUMS_ZEROED 0x100
 /* sums[2C] (double) = {sum x, sum x^2}; zeroed by the call itself before accumulation. */
 int ghnd_bn_stats(const void* x, int fmt, int planar, int N, int64_t hw, int C, double* sums,
                   void* stream);

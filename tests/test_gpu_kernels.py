@@ -544,7 +544,8 @@ def test_bn_bwd_reduce_claims_chunks(ops, C, relu):
     ss, mi = torch.cat([sc, sf]).contiguous(), torch.cat([mu, inv]).contiguous()
     xd, gd = x.double(), g.double()
     if relu:
-        gd = gd * ((x.float() * sc + sf) > 0)
+        # the kernel tests fmaf(x, sc, sf) > 0: one rounding of the exact value, i.e. the sign of the fp64 expression
+        gd = gd * ((xd * sc.double() + sf.double()) > 0)
     ref = torch.cat([gd.sum((0, 1, 2)), (gd * ((xd - mu.double()) * inv.double())).sum((0, 1, 2))])
     sums = torch.empty(2 * C, dtype=torch.float64, device="cuda")
     for _ in range(3):
