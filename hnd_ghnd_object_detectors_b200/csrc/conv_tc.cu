@@ -39,7 +39,7 @@ static constexpr int kEpiWarp0 = 3;
 static constexpr int kBlockM = 128;
 static constexpr int kMaxTaps = 9;
 static constexpr int kMaxStages = 8;
-static constexpr int kMaxRing = 4;
+static constexpr int kMaxRing = 8;
 static constexpr int kMaxASlots = 4;
 static constexpr int kChunkBytes = kBlockM * 128;  // one [128 rows][64 ch] 16-bit staging tile
 // GEMM-K per "unit": 64 x 16-bit = 128 B rows (SWIZZLE_128B) for the wide convs, or
@@ -96,7 +96,7 @@ struct ConvKernelParams {
   int epi_half;     // f16 outputs without mask / statistics: bias, residual and ReLU in packed half2
                     // after ONE fp32 -> f16 conversion of the accumulator (half the epilogue math)
   int epi_debug;    // what-if switches for profiling ONLY (results become wrong): 1 = no TMA store,
-                    // 2 = no proxy fence, 4 = no tcgen05.ld, 8 = no bias/ReLU/operand math
+                    // 2 = no proxy fence, 4 = no tcgen05.ld, 8 = no bias/ReLU/operand math, 16 = no weight loads
   int epi_prefetch; // issue the next chunk's tcgen05.ld as soon as the current chunk is staged
   int epi_bufs;     // output staging tiles per epilogue group (2: the TMA store of chunk i drains
                     // while chunk i+1 is staged)
@@ -874,12 +874,14 @@ __global__ void __launch_bounds__(kConvThreads, 1)
               }
             }
           } else {
-          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(nu * (p.a_box_bytes + p.b_bytes)));
+          const bool no_b = (p.epi_debug & 16) != 0;  // what-if: no weight loads (results are wrong)
+          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(nu * (p.a_box_bytes + (no_b ? 0 : p.b_bytes))));
           for (int j = 0; j < nu; ++j) {
             const ConvTap tap = p.taps[tt];
             tma_load_4d(sa + j * p.a_bytes, &p.tmap_a[tap.map], &full_bar[stage], kk * p.kblock,
                         w0 + tap.dw, h0 + tap.dh, img);
-            if (p.mc)  // this CTA's half of the weight tile, to both CTAs (tmap_b's box is block_n / 2 rows)
+            if (no_b) {
+            } else if (p.mc)  // this CTA's half of the weight tile, to both CTAs (tmap_b's box is block_n / 2 rows)
               tma_load_2d_mc(sb + j * p.b_bytes + walk.rank * b_half, &p.tmap_b, &full_bar[stage],
                              tap.wk * p.cin + kk * p.kblock, n_tile * p.block_n + walk.rank * (p.block_n >> 1),
                              (uint16_t)3);
@@ -1624,6 +1626,14 @@ static int finish_launch(ConvLaunch* L, const ghnd_conv_desc_t* d, int gemm_cin,
     // aliasing).  Seen on B200 as a rare cudaErrorLaunchFailure in the C64->K256 "+res" convs.
     ring = (kSmemBudget - fixed - 3 * p.stage_bytes) / (n_in * kChunkBytes);
     ring = ring >= 4 ? 4 : 2;
+    // experiment: forced ring depth (even, <= kMaxRing), the operand stages get what is left (>= 2)
+    static const int ring_env = [] {
+      const char* e = getenv("GHND_CONV_RING");
+      return e == nullptr ? 0 : atoi(e);
+    }();
+    if (ring_env >= 2 && ring_env <= kMaxRing && ring_env % 2 == 0 &&
+        (kSmemBudget - fixed - ring_env * n_in * kChunkBytes) / p.stage_bytes >= 2)
+      ring = ring_env;
   }
   p.ring = ring > 0 ? ring : 1;
   p.fd_ring = make_fastdiv(p.ring);
