@@ -594,3 +594,19 @@ def test_full_size_step_properties(env):
     assert not torch.equal(student.backbone.body.layer1.decoder[10].running_mean, rm0)
     loss2 = box(images, targets_for(images))
     assert abs(loss2.item() - loss.item()) <= 1e-4 * loss.item()
+
+
+def test_engine_switches_off_still_match_oracle():
+    """The engine-level A/B switches are read once per process: the step-level parity tests run again in a child
+    process with the older paths selected (a memset node per BatchNorm reduction instead of the SumsPool, twelve
+    per-tensor weight repacks on the side stream, persistent BN-backward kernels, bottleneck-side dW in the
+    data-gradient chain, full-width stride-2 dgrad grids)."""
+    import subprocess
+    import sys
+    env = dict(os.environ, GHND_SUMS_POOL="0", GHND_PREPACK_BATCHED="0", GHND_BN_LIGHT="0", GHND_NARROW_DW_SIDE="0",
+               GHND_S2_SHARE="0")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "tests/test_gpu_distill.py", "-k",
+                        "test_ghnd_step_matches_oracle_and_golden or test_second_step_and_fused_adam"],
+                       cwd=root, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
