@@ -113,6 +113,7 @@ SIGNATURES = {
     "ghnd_stem_wgrad_plan_run": (_I, [_P, _P]),
     "ghnd_stem_wgrad_plan_destroy": (None, [_P]),
     "ghnd_bn_stats": (_I, [_P, _I, _I, _I, _L, _I, _P, _P]),
+    "ghnd_bn_stats_finalize": (_I, [_P, _I, _I, _I, _L, _I, _P, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P]),
     "ghnd_bn_finalize": (_I, [_P, _L, _I, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P]),
     "ghnd_bn_eval_params": (_I, [_I, _P, _P, _P, _P, _F, _P, _P]),
     "ghnd_bn_apply": (_I, [_P, _I, _P, _I, _P, _I, _L, _I, _P, _I, _P]),

@@ -10,6 +10,7 @@ static inline int tune_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return (v && *v) ? atoi(v) : dflt;
 }
+static unsigned* red_counter_slot();  // {claim, done} counters of a launch in flight (defined with the BN kernels)
 static inline int grid_for(int64_t work_items, int threads, int per_sm = 8) {
   int64_t b = (work_items + threads - 1) / threads;
   int64_t cap = (int64_t)num_sms() * per_sm;
@@ -541,6 +542,73 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count
     const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
     running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
     running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+// Forward statistics of a planar tensor AND the finalize step in one launch: every block adds its partial sums, the
+// block that takes the last ticket (ctr[1], reset for the next launch) reads the totals back through L2 and does what
+// bn_finalize_kernel does.  Saves one launch on the student's chain in the bottleneck section, where every launch
+// queues behind a teacher conv that holds all SMs (in-graph timeline: bn_finalize started 34 us after the reduce
+// had finished and the narrow conv after it another 41 us later).
+__global__ void __launch_bounds__(256)
+    bn_stats_finalize_planar_kernel(const float* __restrict__ x, int64_t hw, int C, double* __restrict__ sums,
+                                    unsigned* __restrict__ ctr, double count, const float* __restrict__ gamma,
+                                    const float* __restrict__ beta, float eps, float momentum,
+                                    float* __restrict__ running_mean, float* __restrict__ running_var,
+                                    int64_t* __restrict__ nbt, float* __restrict__ scale_shift,
+                                    float* __restrict__ mean_invstd) {
+  const int c = blockIdx.y, n = blockIdx.z;
+  const float* xp = x + ((int64_t)n * C + c) * hw;
+  double a = 0.0, b = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = xp[i];
+    a += v;
+    b += (double)v * v;
+  }
+  __shared__ double ra[8], rb[8];
+  __shared__ unsigned s_last;
+  a = warp_sum(a);
+  b = warp_sum(b);
+  if ((threadIdx.x & 31) == 0) {
+    ra[threadIdx.x >> 5] = a;
+    rb[threadIdx.x >> 5] = b;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ta = 0, tb = 0;
+    for (int w = 0; w < 8; ++w) {
+      ta += ra[w];
+      tb += rb[w];
+    }
+    atomicAdd(&sums[c], ta);
+    atomicAdd(&sums[C + c], tb);
+    __threadfence();
+    const unsigned total = gridDim.x * gridDim.y * gridDim.z;
+    s_last = atomicAdd(&ctr[1], 1u) == total - 1 ? 1u : 0u;
+  }
+  __syncthreads();
+  if (s_last == 0u) return;
+  __threadfence();
+  if (threadIdx.x == 0) {
+    ctr[1] = 0u;
+    if (nbt != nullptr) *nbt += 1;
+  }
+  for (int k = threadIdx.x; k < C; k += blockDim.x) {
+    const double mean = __ldcg(&sums[k]) / count;
+    double var = __ldcg(&sums[C + k]) / count - mean * mean;  // biased
+    if (var < 0.0) var = 0.0;
+    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float g = gamma ? gamma[k] : 1.f, bb = beta ? beta[k] : 0.f;
+    const float sc = g * invstd;
+    scale_shift[k] = sc;
+    scale_shift[C + k] = bb - (float)mean * sc;
+    mean_invstd[k] = (float)mean;
+    mean_invstd[C + k] = invstd;
+    if (running_mean != nullptr) {
+      const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+      running_mean[k] = (1.f - momentum) * running_mean[k] + momentum * (float)mean;
+      running_var[k] = (1.f - momentum) * running_var[k] + momentum * (float)unbiased;
+    }
   }
 }
 
@@ -1566,6 +1634,33 @@ int ghnd_bn_stats(const void* x, int fmt, int planar, int N, int64_t hw, int C, 
         (const uint4*)x, fmt, nullptr, 0, npix, C, nullptr, nullptr, 0, sums);
   }
   GHND_LAUNCH_CHECK("bn_reduce_kernel");
+  return GHND_OK;
+}
+
+int ghnd_bn_stats_finalize(const void* x, int fmt, int planar, int N, int64_t hw, int C, double* sums,
+                           const float* gamma, const float* beta, float eps, float momentum, float* running_mean,
+                           float* running_var, int64_t* num_batches_tracked, float* scale_shift,
+                           float* mean_invstd, void* stream) {
+  GHND_CHECK_ARG(x && sums && scale_shift && mean_invstd && N > 0 && hw > 0 && C > 0,
+                 "bn_stats_finalize: bad argument");
+  GHND_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr),
+                 "bn_stats_finalize: running_mean/var must both be given or both be null");
+  const bool zeroed = (planar & GHND_SUMS_ZEROED) != 0;
+  unsigned* ctr = (planar & ~GHND_SUMS_ZEROED) ? red_counter_slot() : nullptr;
+  if (ctr == nullptr) {  // NHWC (or no counter pool): the two launches
+    int rc = ghnd_bn_stats(x, fmt, planar, N, hw, C, sums, stream);
+    if (rc != GHND_OK) return rc;
+    return ghnd_bn_finalize(sums, (int64_t)N * hw, C, gamma, beta, eps, momentum, running_mean, running_var,
+                            num_batches_tracked, scale_shift, mean_invstd, stream);
+  }
+  GHND_CHECK_ARG(bn_geom_ok(1, C), "bn_stats_finalize: unsupported channel count %d", C);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!zeroed) GHND_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
+  dim3 grid((unsigned)grid_for(hw, 256 * 8, 2), (unsigned)C, (unsigned)N);
+  bn_stats_finalize_planar_kernel<<<grid, 256, 0, st>>>(
+      (const float*)x, hw, C, sums, ctr, (double)N * (double)hw, gamma, beta, eps, momentum, running_mean,
+      running_var, num_batches_tracked, scale_shift, mean_invstd);
+  GHND_LAUNCH_CHECK("bn_stats_finalize_planar_kernel");
   return GHND_OK;
 }
 

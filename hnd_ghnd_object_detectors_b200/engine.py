@@ -573,8 +573,11 @@ class StudentLayer1Runner(object):
     def forward_decoder(self, z=None):
         z = self.z if z is None else z
         if self.train:
-            ops.bn_stats(z, self.bnz.sums, planar=True, zeroed=self.bnz.pooled)
-            self.bnz.finalize()
+            bz = self.bnz  # statistics of z and the finalize step in one launch
+            ops.bn_stats_finalize(z, bz.sums, bz.bn.weight, bz.bn.bias, bz.bn.eps,
+                                  0.1 if bz.bn.momentum is None else bz.bn.momentum, bz.bn.running_mean,
+                                  bz.bn.running_var, bz.bn.num_batches_tracked, bz.scale_shift, bz.mean_invstd,
+                                  planar=True, zeroed=bz.pooled)
         else:
             self.bnz.eval_params()
         ops.conv_narrow_in(z, self.dec2.weight, 0, pre=self.bnz.scale_shift, pre_relu=True, y=self.raw3,

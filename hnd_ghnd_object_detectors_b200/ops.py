@@ -611,6 +611,22 @@ def bn_stats(x, sums, planar=False, zeroed=False):
     return sums
 
 
+def bn_stats_finalize(x, sums, gamma, beta, eps, momentum, running_mean, running_var, nbt, scale_shift,
+                      mean_invstd, planar=False, zeroed=False):
+    """bn_stats + bn_finalize (count = the number of pixels of x) as one launch for planar tensors."""
+    flag = _lib.SUMS_ZEROED if zeroed else 0
+    if planar:
+        n, c, h, w = x.shape
+        fmt, pl = 0, 1 | flag
+    else:
+        n, h, w, c = x.shape
+        fmt, pl = fmt_of(x.dtype), flag
+    call("ghnd_bn_stats_finalize", ptr(x), fmt, pl, n, h * w, c, ptr(sums), ptr(gamma), ptr(beta), float(eps),
+         float(momentum), ptr(running_mean), ptr(running_var), ptr(nbt), ptr(scale_shift), ptr(mean_invstd),
+         stream_ptr())
+    _count(1 if planar else 2)
+
+
 def bn_finalize(sums, count, C, gamma, beta, eps, momentum, running_mean, running_var, nbt, scale_shift,
                 mean_invstd):
     call("ghnd_bn_finalize", ptr(sums), int(count), C, ptr(gamma), ptr(beta), float(eps), float(momentum),

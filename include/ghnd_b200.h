@@ -344,6 +344,12 @@ void ghnd_stem_wgrad_plan_destroy(ghnd_stem_wgrad_plan_t* plan);
 /* sums[2C] (double) = {sum x, sum x^2}; zeroed by the call itself before accumulation. */
 int ghnd_bn_stats(const void* x, int fmt, int planar, int N, int64_t hw, int C, double* sums,
                   void* stream);
+/* ghnd_bn_stats followed by ghnd_bn_finalize (count = N*hw) as ONE launch for planar tensors (the last block to finish
+ * finalizes); NHWC tensors take the two launches.  `planar` accepts GHND_SUMS_ZEROED like ghnd_bn_stats. */
+int ghnd_bn_stats_finalize(const void* x, int fmt, int planar, int N, int64_t hw, int C, double* sums,
+                           const float* gamma, const float* beta, float eps, float momentum, float* running_mean,
+                           float* running_var, int64_t* num_batches_tracked, float* scale_shift,
+                           float* mean_invstd, void* stream);
 /* From sums: scale_shift[2C] = {gamma*invstd, beta-mean*gamma*invstd}, mean_invstd[2C];
  * running stats updated in place (momentum), num_batches_tracked += 1 (int64, nullable). */
 int ghnd_bn_finalize(const double* sums, int64_t count, int C, const float* gamma,

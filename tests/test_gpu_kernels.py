@@ -566,6 +566,40 @@ def test_bn_bwd_reduce_claims_chunks(ops, C, relu):
     torch.cuda.current_stream().wait_stream(s)
 
 
+def test_bn_stats_finalize_planar_one_launch(ops):
+    """ghnd_bn_stats_finalize on a planar tensor (the last block finalizes) against bn_stats + bn_finalize; launched
+    repeatedly (the ticket counter resets itself) and with a caller-zeroed sums buffer."""
+    torch.manual_seed(5)
+    N, C, H, W = 3, 3, 67, 301
+    x = (torch.randn(N, C, H, W, device="cuda") * 1.7 + 0.4).contiguous()
+    gamma, beta = torch.rand(C, device="cuda") + 0.5, torch.randn(C, device="cuda")
+
+    def two_launches():
+        sums = torch.empty(2 * C, dtype=torch.float64, device="cuda")
+        ss, mi = torch.empty(2 * C, device="cuda"), torch.empty(2 * C, device="cuda")
+        rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+        nbt = torch.zeros((), dtype=torch.long, device="cuda")
+        ops.bn_stats(x, sums, planar=True)
+        ops.bn_finalize(sums, N * H * W, C, gamma, beta, 1e-5, 0.1, rm, rv, nbt, ss, mi)
+        return ss, mi, rm, rv, nbt
+
+    ref = two_launches()
+    for zeroed in (False, True, False):
+        sums = torch.zeros(2 * C, dtype=torch.float64, device="cuda") if zeroed else \
+            torch.full((2 * C,), float("nan"), dtype=torch.float64, device="cuda")
+        ss, mi = torch.empty(2 * C, device="cuda"), torch.empty(2 * C, device="cuda")
+        rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+        nbt = torch.zeros((), dtype=torch.long, device="cuda")
+        ops.bn_stats_finalize(x, sums, gamma, beta, 1e-5, 0.1, rm, rv, nbt, ss, mi, planar=True, zeroed=zeroed)
+        torch.cuda.synchronize()
+        for got, want in zip((ss, mi, rm, rv), ref[:4]):
+            assert rel(got, want) < 1e-6, rel(got, want)  # fp64 atomics: the order of the partial sums may differ
+        assert int(nbt) == 1
+    # against torch
+    mean = x.double().mean((0, 2, 3))
+    assert rel(mi[:C], mean) < 1e-6
+
+
 def test_bn_planar(ops):
     torch.manual_seed(1)
     N, C, H, W = 2, 3, 28, 36
